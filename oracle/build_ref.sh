@@ -1,0 +1,68 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE -- builds the parity oracle from the UNMODIFIED reference sources.
+#
+# Compiles the reference's own hot-path translation units where they lie under
+# $RSR_REFERENCE (default /root/reference, read-only) plus oracle/ref_harness.cpp into
+#   oracle/_ref/librsr_ref.so          (git-ignored; travels to the GPU box with gpurun)
+#   oracle/_ref/rglv_triangle_test     (the reference's own rglv_triangle.t.cxx, run as a check)
+# Nothing from the reference tree is copied into the repository; the two g++-compat overlay
+# headers are generated into oracle/_ref/overlay/ by make_overlay.py at build time.
+# The reference's own build system (bazel / MSVC) is not used.
+#
+# Flags follow SURVEY.md 8(c): -O2 -msse4.1 -ffp-contract=off, no -march=native, no fast-math.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${RSR_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src/rgl/rglv" ]; then
+  echo "build_ref.sh: reference tree not found at $REF (expected on the GPU box; using prebuilt $OUT)" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj"
+python3 "$HERE/make_overlay.py" "$REF" "$OUT/overlay"
+
+CXX="${CXX:-g++}"
+FLAGS=(-std=c++17 -O2 -msse4.1 -ffp-contract=off -fpermissive -w -Wno-psabi -fPIC -DPLATFORM_NULL -DNDEBUG
+       -I"$OUT/overlay" -I"$REF" -I"$REF/3rdparty/fmt/include"
+       -include "$HERE/ref_shim.h" '-D__declspec(x)=__attribute__((aligned(16)))')
+
+SRCS=(
+  src/rgl/rglv/rglv_gpu.cxx
+  src/rgl/rglv/rglv_gl.cxx
+  src/rgl/rglv/rglv_math.cxx
+  src/rgl/rglr/rglr_algorithm.cxx
+  src/rgl/rglr/rglr_canvas_util.cxx
+  src/rgl/rglr/rglr_texture.cxx
+  src/rgl/rglr/rglr_texture_sampler.cxx
+  src/rcl/rclmt/rclmt_jobsys.cxx
+  src/rcl/rclmt/rclmt_barrier.cxx
+  src/rml/rmlm/rmlm_mat4.cxx
+  src/viewer/shaders.cxx
+  src/viewer/shaders_envmap.cxx
+  src/viewer/shaders_wireframe.cxx
+  3rdparty/fmt/src/format.cc
+)
+OBJS=()
+pids=()
+for s in "${SRCS[@]}"; do
+  o="$OUT/obj/$(echo "$s" | tr '/' '_').o"
+  OBJS+=("$o")
+  if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ] || [ "$HERE/ref_shim.h" -nt "$o" ]; then
+    "$CXX" "${FLAGS[@]}" -c "$REF/$s" -o "$o" &
+    pids+=($!)
+  fi
+done
+ho="$OUT/obj/ref_harness.o"
+"$CXX" "${FLAGS[@]}" -c "$HERE/ref_harness.cpp" -o "$ho" &
+pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+"$CXX" -shared -o "$OUT/librsr_ref.so" "${OBJS[@]}" "$ho" -lpthread
+
+# the reference's own rasteriser test (plain main(), no gtest): fill-rule KAT + UV interpolation
+"$CXX" "${FLAGS[@]}" "$REF/src/rgl/rglv/rglv_triangle.t.cxx" \
+    "$OUT/obj/src_rgl_rglr_rglr_algorithm.cxx.o" "$OUT/obj/3rdparty_fmt_src_format.cc.o" \
+    -o "$OUT/rglv_triangle_test" -lpthread
+"$OUT/rglv_triangle_test" > "$OUT/rglv_triangle_test.log" 2>&1 \
+  && echo "build_ref.sh: reference rglv_triangle.t.cxx PASSED" \
+  || { echo "build_ref.sh: reference rglv_triangle.t.cxx FAILED"; cat "$OUT/rglv_triangle_test.log"; exit 1; }
+echo "build_ref.sh: built $OUT/librsr_ref.so"

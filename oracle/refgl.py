@@ -1,0 +1,304 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of oracle/_ref/librsr_ref.so (the unmodified reference).
+
+`RefGPU` exposes the reference's `rglv::GPU` + `rglv::GL` surface (src/rgl/rglv/rglv_gl.hxx:182-344,
+src/rgl/rglv/rglv_gpu.hxx:152-168) with the reference's own method names, so one scene-building
+function can drive both this oracle and the CUDA product (`rsr_b200.GPU`) and the outputs can be
+compared bit for bit.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs import
+this module.  Nothing under rsr_b200/ does.
+"""
+from __future__ import annotations
+
+import atexit
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "librsr_ref.so")
+
+_lib = None
+_threads = None
+
+
+def build(force: bool = False) -> bool:
+    """Build oracle/_ref/librsr_ref.so when the reference tree is present. Returns availability."""
+    ref = os.environ.get("RSR_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref, "src", "rgl", "rglv")) and (force or not os.path.exists(LIB_PATH)):
+        subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+    return os.path.exists(LIB_PATH)
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"reference oracle not built: {LIB_PATH} (run oracle/build_ref.sh)")
+        L = C.CDLL(LIB_PATH)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        fp = C.POINTER(C.c_float)
+        sigs = {
+            "ref_init": (ci, [ci]),
+            "ref_work_start": (None, []),
+            "ref_work_end": (None, []),
+            "ref_shutdown": (None, []),
+            "ref_set_double_buffer": (None, [ci]),
+            "ref_gpu_create": (vp, []),
+            "ref_gpu_destroy": (None, [vp]),
+            "ref_gpu_reset": (None, [vp, ci, ci, ci, ci]),
+            "ref_gpu_run": (None, [vp]),
+            "ref_gl_enable": (None, [vp, ci]),
+            "ref_gl_disable": (None, [vp, ci]),
+            "ref_gl_depth_func": (None, [vp, ci]),
+            "ref_gl_depth_write_mask": (None, [vp, ci]),
+            "ref_gl_color_write_mask": (None, [vp, ci]),
+            "ref_gl_cull_face": (None, [vp, ci]),
+            "ref_gl_scissor": (None, [vp, ci, ci, ci, ci]),
+            "ref_gl_viewport": (None, [vp, ci, ci, ci, ci]),
+            "ref_gl_use_program": (None, [vp, ci]),
+            "ref_gl_renderbuffer_type": (None, [vp, ci, ci]),
+            "ref_gl_clear_color": (None, [vp, cf, cf, cf]),
+            "ref_gl_clear_depth": (None, [vp, cf]),
+            "ref_gl_view_matrix": (None, [vp, vp]),
+            "ref_gl_projection_matrix": (None, [vp, vp]),
+            "ref_gl_normal_matrix": (None, [vp, vp]),
+            "ref_gl_use_buffer": (None, [vp, ci, vp]),
+            "ref_gl_uniforms": (None, [vp, vp, ci]),
+            "ref_gl_bind_texture": (None, [vp, ci, vp, ci, ci, ci, ci]),
+            "ref_gl_bind_texture3": (None, [vp, vp, ci]),
+            "ref_gl_clear": (None, [vp, ci]),
+            "ref_gl_draw_elements": (None, [vp, ci, vp, ci]),
+            "ref_gl_draw_arrays": (None, [vp, ci]),
+            "ref_gl_draw_elements_instanced": (None, [vp, ci, vp, ci]),
+            "ref_gl_draw_arrays_instanced": (None, [vp, ci, ci]),
+            "ref_gl_store_color_tc": (None, [vp, vp, ci, ci, ci, ci]),
+            "ref_gl_store_color_fp": (None, [vp, vp, ci, ci, ci, ci]),
+            "ref_gl_store_depth": (None, [vp, vp]),
+            "ref_make_mipmap": (None, [vp, ci, vp]),
+            "ref_rcp": (None, [vp, vp, ci]),
+            "ref_rsqrt": (None, [vp, vp, ci]),
+            "ref_oneover": (None, [vp, vp, ci]),
+            "ref_mat4_mul": (None, [vp, vp, vp]),
+            "ref_mat4_inverse": (None, [vp, vp]),
+            "ref_raster_coverage": (None, [vp, ci, ci, vp]),
+            "ref_vraster_coverage": (None, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+        }
+        for name, (res, args) in sigs.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def init(threads: int | None = None) -> int:
+    """jobsys::init -- once per process; later calls return the thread count in use."""
+    global _threads
+    if _threads is None:
+        n = threads or os.cpu_count() or 1
+        _threads = lib().ref_init(int(n))
+        atexit.register(lib().ref_shutdown)
+    return _threads
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class RefGPU:
+    """The reference `rglv::GPU` (with `rqv::Install`ed programs) and its recording `GL` context."""
+
+    def __init__(self, threads: int | None = None, double_buffer: bool = False):
+        init(threads)
+        self.L = lib()
+        self.L.ref_set_double_buffer(1 if double_buffer else 0)
+        self.h = self.L.ref_gpu_create()
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.ref_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- rglv::GPU --------------------------------------------------------------------------
+    def Reset(self, size, tile_blocks=(8, 8)):
+        self._keep = []
+        self.size = (int(size[0]), int(size[1]))
+        self.L.ref_gpu_reset(self.h, self.size[0], self.size[1], int(tile_blocks[0]), int(tile_blocks[1]))
+        # GLState::reset() (rglv_gl.hxx:152-179) leaves the attachment types uninitialised; every
+        # reference caller sets them right after Reset (node/gpu.cxx:132-133).  Do the same.
+        self.RenderbufferType(2, 0)  # GL_COLOR_ATTACHMENT0 <- RB_COLOR_DEPTH
+        self.RenderbufferType(0, 0)  # GL_DEPTH_ATTACHMENT  <- RB_COLOR_DEPTH
+
+    def Run(self, manage_workers: bool = True):
+        if manage_workers:
+            self.L.ref_work_start()
+        self.L.ref_gpu_run(self.h)
+        if manage_workers:
+            self.L.ref_work_end()
+
+    # -- rglv::GL ---------------------------------------------------------------------------
+    def Enable(self, cap): self.L.ref_gl_enable(self.h, cap)
+    def Disable(self, cap): self.L.ref_gl_disable(self.h, cap)
+    def DepthFunc(self, v): self.L.ref_gl_depth_func(self.h, v)
+    def DepthWriteMask(self, v): self.L.ref_gl_depth_write_mask(self.h, int(bool(v)))
+    def ColorWriteMask(self, v): self.L.ref_gl_color_write_mask(self.h, int(bool(v)))
+    def CullFace(self, v): self.L.ref_gl_cull_face(self.h, v)
+    def Scissor(self, x, y, w, h): self.L.ref_gl_scissor(self.h, x, y, w, h)
+    def Viewport(self, x, y, w, h): self.L.ref_gl_viewport(self.h, x, y, w, h)
+    def UseProgram(self, pid): self.L.ref_gl_use_program(self.h, pid)
+    def RenderbufferType(self, attachment, t): self.L.ref_gl_renderbuffer_type(self.h, attachment, t)
+    def ClearColor(self, rgb): self.L.ref_gl_clear_color(self.h, float(rgb[0]), float(rgb[1]), float(rgb[2]))
+    def ClearDepth(self, d): self.L.ref_gl_clear_depth(self.h, float(d))
+
+    def _mat(self, m):
+        """accepts a 4x4 row-major numpy matrix (math convention); the reference stores column-major"""
+        a = _f32(np.asarray(m, dtype=np.float32).T.reshape(16))
+        self._keep.append(a)
+        return _ptr(a)
+
+    def ViewMatrix(self, m): self.L.ref_gl_view_matrix(self.h, self._mat(m))
+    def ProjectionMatrix(self, m): self.L.ref_gl_projection_matrix(self.h, self._mat(m))
+    def NormalMatrix(self, m): self.L.ref_gl_normal_matrix(self.h, self._mat(m))
+
+    def UseBuffer(self, slot, arr):
+        """arr: float32 array (one SoA component) or None; a (3,N)/(2,N) array binds slot..slot+k"""
+        if arr is None:
+            self.L.ref_gl_use_buffer(self.h, slot, None)
+            return
+        a = np.asarray(arr)
+        if a.ndim == 2:
+            for i in range(a.shape[0]):
+                self.UseBuffer(slot + i, a[i])
+            return
+        a = _f32(a)
+        assert a.ctypes.data % 16 == 0 or a.size == 0, "SoA arrays must be 16-byte aligned"
+        self._keep.append(a)
+        self.L.ref_gl_use_buffer(self.h, slot, _ptr(a))
+
+    def UseUniforms(self, data):
+        b = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        assert b.size <= 128
+        self._keep.append(b)
+        self.L.ref_gl_uniforms(self.h, _ptr(b), int(b.size))
+
+    def BindTexture(self, unit, texels, width, height, stride, mode):
+        t = _f32(texels)
+        self._keep.append(t)
+        self.L.ref_gl_bind_texture(self.h, unit, _ptr(t), width, height, stride, mode)
+
+    def BindTexture3(self, depth, dim):
+        t = _f32(depth)
+        self._keep.append(t)
+        self.L.ref_gl_bind_texture3(self.h, _ptr(t), dim)
+
+    def Clear(self, bits): self.L.ref_gl_clear(self.h, bits)
+
+    def DrawElements(self, count, indices, hint=0):
+        idx = np.ascontiguousarray(indices, dtype=np.uint16)
+        self._keep.append(idx)
+        self.L.ref_gl_draw_elements(self.h, int(count), _ptr(idx), int(hint))
+
+    def DrawArrays(self, count): self.L.ref_gl_draw_arrays(self.h, int(count))
+
+    def DrawElementsInstanced(self, count, indices, instance_cnt):
+        idx = np.ascontiguousarray(indices, dtype=np.uint16)
+        self._keep.append(idx)
+        self.L.ref_gl_draw_elements_instanced(self.h, int(count), _ptr(idx), int(instance_cnt))
+
+    def DrawArraysInstanced(self, count, instance_cnt):
+        self.L.ref_gl_draw_arrays_instanced(self.h, int(count), int(instance_cnt))
+
+    def StoreColor(self, dst: np.ndarray, gamma: bool = True):
+        """dst: (H, W) uint32 -> CMD_STORE_COLOR_FULL_LINEAR_TC; (H, W, 4) float32 -> ..._LINEAR_FP"""
+        if dst.dtype == np.uint32:
+            h, w = dst.shape
+            self._keep.append(dst)
+            self.L.ref_gl_store_color_tc(self.h, _ptr(dst), w, h, dst.strides[0] // 4, int(bool(gamma)))
+        else:
+            assert dst.dtype == np.float32 and dst.ndim == 3 and dst.shape[2] == 4
+            h, w, _ = dst.shape
+            self._keep.append(dst)
+            self.L.ref_gl_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 0)
+
+    def StoreColorHalf(self, dst: np.ndarray):
+        assert dst.dtype == np.float32 and dst.ndim == 3 and dst.shape[2] == 4
+        h, w, _ = dst.shape
+        self._keep.append(dst)
+        self.L.ref_gl_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 1)
+
+    def StoreDepth(self, dst: np.ndarray):
+        assert dst.dtype == np.float32 and dst.flags.c_contiguous
+        self._keep.append(dst)
+        self.L.ref_gl_store_depth(self.h, _ptr(dst))
+
+
+# -- free helpers ------------------------------------------------------------------------------
+
+def make_mipmap(base: np.ndarray) -> np.ndarray:
+    """(dim, dim, 4) float32 -> (2*dim, dim, 4) with the reference's stacked mip chain"""
+    base = _f32(base)
+    dim = base.shape[0]
+    assert base.shape == (dim, dim, 4)
+    out = np.zeros((2 * dim, dim, 4), dtype=np.float32)
+    lib().ref_make_mipmap(_ptr(base), dim, _ptr(out))
+    return out
+
+
+def _map1(fn, x):
+    a = _f32(x).reshape(-1)
+    out = np.empty_like(a)
+    fn(_ptr(a), _ptr(out), a.size)
+    return out.reshape(np.shape(x))
+
+
+def rcp(x): return _map1(lib().ref_rcp, x)
+def rsqrt(x): return _map1(lib().ref_rsqrt, x)
+def oneover(x): return _map1(lib().ref_oneover, x)
+
+
+def mat4_mul(a, b):
+    """row-major numpy in/out (math convention)"""
+    aa, bb = _f32(np.asarray(a).T.reshape(16)), _f32(np.asarray(b).T.reshape(16))
+    out = np.empty(16, np.float32)
+    lib().ref_mat4_mul(_ptr(aa), _ptr(bb), _ptr(out))
+    return out.reshape(4, 4).T.copy()
+
+
+def mat4_inverse(a):
+    aa = _f32(np.asarray(a).T.reshape(16))
+    out = np.empty(16, np.float32)
+    lib().ref_mat4_inverse(_ptr(aa), _ptr(out))
+    return out.reshape(4, 4).T.copy()
+
+
+def raster_coverage(xy, w, h):
+    a = _f32(xy).reshape(6)
+    out = np.zeros((h, w), np.uint8)
+    lib().ref_raster_coverage(_ptr(a), w, h, _ptr(out))
+    return out
+
+
+def vraster_coverage(x3, y3, rect, w, h):
+    xs = np.ascontiguousarray(x3, dtype=np.int32)
+    ys = np.ascontiguousarray(y3, dtype=np.int32)
+    out = np.zeros((h, w), np.uint8)
+    lib().ref_vraster_coverage(_ptr(xs), _ptr(ys), rect[0], rect[1], rect[2], rect[3], w, h, _ptr(out))
+    return out
