@@ -1,0 +1,192 @@
+/* rsrcu.h -- C ABI of the B200 (sm_100a) rasteriser that replaces rsr's software `rglv::GPU`.
+ *
+ * Boundary: the reference records GL calls into `rglv::GL` (src/rgl/rglv/rglv_gl.hxx:182-344) and
+ * `rglv::GPU::RunImpl` (src/rgl/rglv/rglv_gpu.cxx:90-116) decodes that stream, bins triangles
+ * (`BinImpl` :119-260) and draws tiles (`DrawImpl` :263-432).  A drop-in replaces exactly
+ * RunImpl: it walks the same command stream and, per command, calls one function below.
+ * INTEGRATION.md shows the ~60-line RunImpl replacement a maintainer would add.
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every call returns RSRCU_OK (0) or an error code,
+ *    `rsrcu_last_error()` returns a thread-local human-readable message for the last failure.
+ *  - one context per `rglv::GPU`; calls on one context are serialised by the caller (the reference
+ *    runs RunImpl on a single job thread); contexts are independent and may live on different
+ *    devices (split-frame sharding: one context per GPU).
+ *  - host pointers are borrowed only for the duration of the call (data is staged/uploaded before
+ *    the call returns) unless a call says otherwise (store destinations are written by
+ *    `rsrcu_end_frame`/`rsrcu_sync`).
+ *  - matrices are 16 floats, column-major, exactly `rmlm::mat4::ff` (src/rml/rmlm/rmlm_mat4.hxx:14).
+ *  - there is no CPU fallback: if no CUDA device is present `rsrcu_create` fails.
+ */
+#ifndef RSRCU_H
+#define RSRCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSRCU_OK                 0
+#define RSRCU_ERR_NO_DEVICE      1   /* no CUDA device / driver */
+#define RSRCU_ERR_CUDA           2   /* a CUDA runtime call failed */
+#define RSRCU_ERR_INVALID        3   /* bad argument or call order */
+#define RSRCU_ERR_NO_PROGRAM     4   /* (program id, fragment state key) not in the dispatch table;
+                                        the reference calls std::exit(1) here (rglv_gpu.cxx:199-202) */
+#define RSRCU_ERR_UNSUPPORTED    5   /* state the reference itself cannot render (e.g. >2048 px) */
+#define RSRCU_ERR_OVERFLOW       6   /* a device-side buffer (clip records) overflowed */
+
+/* constants: same numeric values as src/rgl/rglv/rglv_gl.hxx:20-62 */
+#define RSRCU_GL_FRONT 1
+#define RSRCU_GL_BACK 2
+#define RSRCU_GL_NEAREST_MIPMAP_NEAREST 0
+#define RSRCU_GL_LINEAR_MIPMAP_NEAREST 1
+#define RSRCU_GL_COLOR_BUFFER_BIT 1
+#define RSRCU_GL_DEPTH_BUFFER_BIT 2
+#define RSRCU_GL_STENCIL_BUFFER_BIT 4
+#define RSRCU_GL_LESS 0
+#define RSRCU_GL_LEQUAL 1
+#define RSRCU_GL_EQUAL 2
+#define RSRCU_RB_COLOR_DEPTH 0
+#define RSRCU_RB_RGBF32 1
+#define RSRCU_RB_RGBAF32 2
+#define RSRCU_RB_F32 3
+#define RSRCU_HINT_READ4 1
+#define RSRCU_HINT_DENSE 2
+
+/* upload policy for rsrcu_bind_buffer / rsrcu_bind_texture / index data */
+#define RSRCU_UPLOAD_ALWAYS 0   /* contents may have changed since the last call: copy again */
+#define RSRCU_UPLOAD_STATIC 1   /* (pointer, size) identifies immutable data: copy once, then reuse */
+
+typedef struct rsrcu_ctx rsrcu_ctx;
+
+/* POD mirror of `rglv::GLState` (src/rgl/rglv/rglv_gl.hxx:80-179) without the raw pointers:
+ * vertex buffers, textures and uniforms are attached with the bind calls below and are captured
+ * together with this struct by the next draw / clear / store, like `GL::MaybeUpdateState`
+ * (src/rgl/rglv/rglv_gl.cxx:100-106) captures `cs_`. */
+typedef struct RsrState {
+	float clear_color[4];         /* GLState::clearColor */
+	float clear_depth;            /* GLState::clearDepth */
+	int32_t culling_enabled;      /* GL_CULL_FACE */
+	int32_t cull_face;            /* RSRCU_GL_FRONT / RSRCU_GL_BACK (3 = both; see DESIGN.md quirk list) */
+	int32_t scissor_enabled;      /* no program of the reference's table is installed with scissor */
+	int32_t scissor_origin[2], scissor_size[2];
+	int32_t viewport_origin[2];
+	int32_t viewport_size[2];     /* {0,0} = unset => target size (std::optional in the reference) */
+	int32_t blending_enabled;
+	int32_t color_write_mask;
+	int32_t depth_write_mask;
+	int32_t depth_test_enabled;
+	int32_t depth_func;           /* RSRCU_GL_LESS / LEQUAL / EQUAL */
+	int32_t program_id;           /* ids of src/viewer/shaders*.hxx: Amy 4, Many 6, OBJ2 8, ... */
+	int32_t color0_attachment_type; /* RSRCU_RB_* */
+	int32_t depth_attachment_type;
+	float view_matrix[16];
+	float projection_matrix[16];
+	float normal_matrix[16];      /* carried for API parity; like the reference, shading uses
+	                                 transpose(inverse(view)) (rglv_gpu_impl.hxx:45-51) */
+	uint32_t uniforms_valid;      /* 0 = UseUniforms(-1) */
+	float uniforms[32];           /* one UNIFORM_BUFFER_SIZE block (rglv_gl.hxx:62) */
+} RsrState;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device`.  Harvests this host CPU's rcpps / rsqrtps tables
+ * (the reference's `oneover` / `normalize` depend on them: rmlv_mvec4.hxx:630-650,
+ * rmlv_soa.hxx:243-248), verifies the table model against the instruction, uploads them. */
+int rsrcu_create(int device, rsrcu_ctx** out);
+int rsrcu_destroy(rsrcu_ctx* ctx);
+const char* rsrcu_last_error(void);
+
+/* Overrides the harvested approximation tables (to reproduce a frame rendered by the reference on
+ * another CPU, e.g. a committed golden image).  rcp: 2048 entries = bits of rcpps(1 + i/2048);
+ * rsqrt: 2 x 1024 entries = bits of rsqrtps(1 + i/1024) then rsqrtps(2 * (1 + i/1024)). */
+int rsrcu_set_host_luts(rsrcu_ctx* ctx, const uint32_t* rcp2048, const uint32_t* rsqrt2x1024);
+int rsrcu_get_host_luts(rsrcu_ctx* ctx, uint32_t* rcp2048, uint32_t* rsqrt2x1024);
+
+/* ---- frame recording: one call per reference stream command ---------------------------------- */
+
+/* GPU::Reset (rglv_gpu.cxx:50-56).  tile_*_blocks are the reference's tile size in 8x8 blocks
+ * (default 8x8 => 64x64 px); the device uses its own 32x32 tiles and only needs these to
+ * reproduce the reference's int32 edge-function start point.  width,height <= 2048 and even. */
+int rsrcu_begin_frame(rsrcu_ctx* ctx, int width, int height, int tile_w_blocks, int tile_h_blocks);
+
+/* CMD_STATE (rglv_gpu.cxx:139-147) */
+int rsrcu_set_state(rsrcu_ctx* ctx, const RsrState* state);
+
+/* GLState::buffers[slot] (rglv_gl.hxx:104): SoA float arrays, slots 0-2 position, 3-5 normal,
+ * 6-8 colour/kd, 9-10 uv, 15 per-instance mat4 array.  n_floats makes the extent explicit (the
+ * reference scans the index buffer instead, rglv_gpu_impl.hxx:332-334).  NULL unbinds. */
+int rsrcu_bind_buffer(rsrcu_ctx* ctx, int slot, const float* host_ptr, size_t n_floats, int upload);
+
+/* GLState::tus[unit] (rglv_gl.hxx:64-77,106): RGBA32F texels, `height` rows of the base level;
+ * for power-of-two square textures the mip chain is stacked below (2*height rows in memory,
+ * rglr_texture.cxx:33-81) and must be included: rows_in_memory says how many rows to upload. */
+int rsrcu_bind_texture(rsrcu_ctx* ctx, int unit, const float* host_ptr, int width, int height,
+                       int stride, int filter, int rows_in_memory, int upload);
+
+/* GLState::tu3ptr/tu3dim: float32 depth (shadow) map, dim x dim */
+int rsrcu_bind_depth_texture(rsrcu_ctx* ctx, const float* host_ptr, int dim, int upload);
+
+/* CMD_CLEAR (rglv_gpu.cxx:148-155, :311-344) */
+int rsrcu_clear(rsrcu_ctx* ctx, int bits);
+
+/* CMD_DRAW_ELEMENTS / _INSTANCED (rglv_gpu.cxx:216-243): count = number of indices (3 per
+ * triangle), uint16 indices, instance_count = 0 selects the non-instanced path. */
+int rsrcu_draw_elements(rsrcu_ctx* ctx, int count, const uint16_t* indices, int hint,
+                        int instance_count, int upload);
+
+/* CMD_DRAW_ARRAYS / _INSTANCED (rglv_gpu.cxx:192-215) */
+int rsrcu_draw_arrays(rsrcu_ctx* ctx, int count, int instance_count);
+
+/* CMD_STORE_COLOR_FULL_LINEAR_TC (rglv_gpu.cxx:177-185, :384-395): post program of the current
+ * state + sRGB/linear conversion to 0x00RRGGBB.  dst = host memory (pinned or pageable), written
+ * when the frame completes; dst == NULL keeps the result on the device only
+ * (see rsrcu_device_truecolor). */
+int rsrcu_store_color_tc(rsrcu_ctx* ctx, int enable_gamma, uint32_t* dst, int width, int height,
+                         int stride_px);
+
+/* CMD_STORE_COLOR_FULL_LINEAR_FP / CMD_STORE_COLOR_HALF_LINEAR_FP (rglv_gpu.cxx:156-169, :345-370):
+ * RGBA32F, alpha = what the tile buffer holds (depth for RB_COLOR_DEPTH). */
+int rsrcu_store_color_fp(rsrcu_ctx* ctx, float* dst, int width, int height, int stride_px, int half);
+
+/* CMD_STORE_DEPTH_FULL_LINEAR_FP (rglv_gpu.cxx:186-191, :396-405).  The reference implements it
+ * for RB_F32 depth attachments only; here RB_COLOR_DEPTH (depth in alpha) is accepted too. */
+int rsrcu_store_depth(rsrcu_ctx* ctx, float* dst);
+
+/* CMD_EOF: uploads the recorded frame, enqueues every kernel and the device->host copies of the
+ * store destinations on the context's stream, and returns without waiting. */
+int rsrcu_end_frame(rsrcu_ctx* ctx);
+
+/* Waits for the frame; reports device-side errors (clip buffer overflow...) */
+int rsrcu_sync(rsrcu_ctx* ctx);
+
+/* ---- device-side access (viewer presents from the device-resolved buffer; bench; sharding) --- */
+
+/* device pointer + pitch (pixels) of the last true-colour store of the current/last frame */
+int rsrcu_device_truecolor(rsrcu_ctx* ctx, void** dev_ptr, int* stride_px);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+int rsrcu_stream(rsrcu_ctx* ctx, void** stream);
+
+/* counters of the last completed frame (filled by rsrcu_sync) */
+typedef struct RsrStats {
+	uint64_t triangles_submitted;   /* sum over draws of prims x instances */
+	uint64_t triangles_binned;      /* accepted after cull / frustum */
+	uint64_t triangles_clipped;     /* sent through the clipper */
+	uint64_t bin_entries;           /* (triangle, tile) pairs */
+	uint64_t fragments_shaded;      /* pixels that passed coverage and depth and were written */
+	uint64_t kernel_launches;       /* kernels launched for the frame */
+} RsrStats;
+int rsrcu_get_stats(rsrcu_ctx* ctx, RsrStats* out);
+
+/* last frame's device time per stage in milliseconds (CUDA events on the context stream):
+ * [0] vertex [1] setup+clip [2] bin count [3] bin scan [4] bin fill [5] tile raster+resolve
+ * [6] whole frame incl. uploads and readback.  Requires rsrcu_set_profiling(ctx, 1). */
+int rsrcu_set_profiling(rsrcu_ctx* ctx, int enabled);
+int rsrcu_get_stage_ms(rsrcu_ctx* ctx, float* ms7);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSRCU_H */

@@ -1,0 +1,377 @@
+"""rsr_b200 -- B200 (sm_100a) rasteriser behind the rsr `rglv::GL` / `rglv::GPU` drawing API.
+
+`GPU` mirrors the reference's host interface for the frame-rendering hot path
+(src/rgl/rglv/rglv_gl.hxx:182-344 `rglv::GL`, src/rgl/rglv/rglv_gpu.hxx:152-168 `rglv::GPU`)
+with the reference's own method names and argument meaning, on top of the C ABI declared in
+include/rsrcu.h (librsrcu.so, hand-written CUDA for sm_100a).  There is no CPU path: if the
+library or a CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+# -- constants: src/rgl/rglv/rglv_gl.hxx:20-62 ---------------------------------------------------
+GL_CULL_FACE, GL_SCISSOR_TEST, GL_BLEND, GL_DEPTH_TEST = 1, 2, 3, 4
+GL_FRONT, GL_BACK, GL_FRONT_AND_BACK = 1, 2, 3
+GL_NEAREST_MIPMAP_NEAREST, GL_LINEAR_MIPMAP_NEAREST = 0, 1
+GL_COLOR_BUFFER_BIT, GL_DEPTH_BUFFER_BIT, GL_STENCIL_BUFFER_BIT = 1, 2, 4
+RGL_HINT_READ4, RGL_HINT_DENSE = 1, 2
+GL_LESS, GL_LEQUAL, GL_EQUAL = 0, 1, 2
+GL_DEPTH_ATTACHMENT, GL_STENCIL_ATTACHMENT, GL_COLOR_ATTACHMENT0 = 0, 1, 2
+RB_COLOR_DEPTH, RB_RGBF32, RB_RGBAF32, RB_F32 = 0, 1, 2, 3
+
+# program ids: src/viewer/shaders.hxx, shaders_envmap.hxx, shaders_wireframe.hxx
+PROGRAM_DEFAULT_POST, PROGRAM_EXPOSURE_POST, PROGRAM_IQ_POST = 1, 2, 3
+PROGRAM_AMY, PROGRAM_DEPTH, PROGRAM_MANY, PROGRAM_OBJ1, PROGRAM_OBJ2, PROGRAM_OBJ2S = 4, 5, 6, 7, 8, 9
+PROGRAM_ENVMAP, PROGRAM_WIREFRAME, PROGRAM_TEXT, PROGRAM_PATTERN, PROGRAM_ALPHATEXTURE = 10, 11, 26, 41, 65
+
+UPLOAD_ALWAYS, UPLOAD_STATIC = 0, 1
+
+RSRCU_OK = 0
+ERROR_NAMES = {1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "NO_PROGRAM", 5: "UNSUPPORTED", 6: "OVERFLOW"}
+
+
+class RsrError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rsrcu error {code} ({ERROR_NAMES.get(code, '?')}): {message}")
+        self.code = code
+
+
+class RsrState(C.Structure):
+    """POD mirror of include/rsrcu.h `RsrState` (itself a mirror of rglv::GLState)."""
+    _fields_ = [
+        ("clear_color", C.c_float * 4),
+        ("clear_depth", C.c_float),
+        ("culling_enabled", C.c_int32),
+        ("cull_face", C.c_int32),
+        ("scissor_enabled", C.c_int32),
+        ("scissor_origin", C.c_int32 * 2),
+        ("scissor_size", C.c_int32 * 2),
+        ("viewport_origin", C.c_int32 * 2),
+        ("viewport_size", C.c_int32 * 2),
+        ("blending_enabled", C.c_int32),
+        ("color_write_mask", C.c_int32),
+        ("depth_write_mask", C.c_int32),
+        ("depth_test_enabled", C.c_int32),
+        ("depth_func", C.c_int32),
+        ("program_id", C.c_int32),
+        ("color0_attachment_type", C.c_int32),
+        ("depth_attachment_type", C.c_int32),
+        ("view_matrix", C.c_float * 16),
+        ("projection_matrix", C.c_float * 16),
+        ("normal_matrix", C.c_float * 16),
+        ("uniforms_valid", C.c_uint32),
+        ("uniforms", C.c_float * 32),
+    ]
+
+
+class RsrStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("triangles_submitted", "triangles_binned", "triangles_clipped",
+                                           "bin_entries", "fragments_shaded", "kernel_launches")]
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library():
+    """Loads librsrcu.so (building it first when sources are newer and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this box: a prebuilt .so must be there
+            if not os.path.exists(_build.LIB):
+                raise RuntimeError(f"librsrcu.so is missing and cannot be built: {exc}") from exc
+    L = C.CDLL(_build.LIB)
+    vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
+    sig = {
+        "rsrcu_create": [ci, C.POINTER(vp)],
+        "rsrcu_destroy": [vp],
+        "rsrcu_set_host_luts": [vp, vp, vp],
+        "rsrcu_get_host_luts": [vp, vp, vp],
+        "rsrcu_begin_frame": [vp, ci, ci, ci, ci],
+        "rsrcu_set_state": [vp, C.POINTER(RsrState)],
+        "rsrcu_bind_buffer": [vp, ci, vp, sz, ci],
+        "rsrcu_bind_texture": [vp, ci, vp, ci, ci, ci, ci, ci, ci],
+        "rsrcu_bind_depth_texture": [vp, vp, ci, ci],
+        "rsrcu_clear": [vp, ci],
+        "rsrcu_draw_elements": [vp, ci, vp, ci, ci, ci],
+        "rsrcu_draw_arrays": [vp, ci, ci],
+        "rsrcu_store_color_tc": [vp, ci, vp, ci, ci, ci],
+        "rsrcu_store_color_fp": [vp, vp, ci, ci, ci, ci],
+        "rsrcu_store_depth": [vp, vp],
+        "rsrcu_end_frame": [vp],
+        "rsrcu_sync": [vp],
+        "rsrcu_device_truecolor": [vp, C.POINTER(vp), C.POINTER(ci)],
+        "rsrcu_stream": [vp, C.POINTER(vp)],
+        "rsrcu_get_stats": [vp, C.POINTER(RsrStats)],
+        "rsrcu_set_profiling": [vp, ci],
+        "rsrcu_get_stage_ms": [vp, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = ci
+    L.rsrcu_last_error.restype = C.c_char_p
+    L.rsrcu_last_error.argtypes = []
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
+    "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
+    "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
+    "rsrcu_store_color_tc", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
+)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GPU:
+    """`rglv::GPU` + its recording `rglv::GL` context, rendered by the CUDA library.
+
+    Usage follows the reference (node/gpu.cxx:107-161, node/truecolor.cxx:90-108):
+    Reset(size, tileBlocks); state + draw calls; StoreColor(...); Run().
+    """
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        self._check(self.L.rsrcu_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+        self._keep = []
+        self._state = RsrState()
+        self._reset_state()
+        self._dirty = True
+        self.size = (0, 0)
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != RSRCU_OK:
+            raise RsrError(rc, self.L.rsrcu_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rsrcu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _reset_state(self):
+        """GLState::reset (rglv_gl.hxx:152-179) + the attachment defaults every caller sets"""
+        s = self._state
+        C.memset(C.byref(s), 0, C.sizeof(s))
+        s.clear_color[:] = [0.0, 0.0, 0.0, 1.0]
+        s.clear_depth = 1.0
+        s.cull_face = GL_BACK
+        s.color_write_mask = 1
+        s.depth_write_mask = 1
+        s.depth_test_enabled = 1
+        s.depth_func = GL_LESS
+        s.color0_attachment_type = RB_COLOR_DEPTH
+        s.depth_attachment_type = RB_COLOR_DEPTH
+        ident = np.eye(4, dtype=np.float32).reshape(16)
+        s.view_matrix[:] = ident
+        s.projection_matrix[:] = ident
+        s.normal_matrix[:] = ident
+
+    def _flush_state(self):
+        if self._dirty:
+            self._check(self.L.rsrcu_set_state(self.h, C.byref(self._state)))
+            self._dirty = False
+
+    # -- rglv::GPU ------------------------------------------------------------------------------
+    def Reset(self, size, tile_blocks=(8, 8)):
+        self._keep = []
+        self.size = (int(size[0]), int(size[1]))
+        self._check(self.L.rsrcu_begin_frame(self.h, self.size[0], self.size[1], int(tile_blocks[0]), int(tile_blocks[1])))
+        self._reset_state()
+        self._dirty = True
+
+    def Run(self, manage_workers: bool = True, sync: bool = True):
+        """GPU::Run: end of recording -> kernels; `sync` waits and fills the store destinations"""
+        self._check(self.L.rsrcu_end_frame(self.h))
+        if sync:
+            self.Sync()
+
+    def Sync(self):
+        self._check(self.L.rsrcu_sync(self.h))
+
+    # -- rglv::GL -------------------------------------------------------------------------------
+    def _cap(self, cap, value):
+        s = self._state
+        if cap == GL_CULL_FACE: s.culling_enabled = value
+        elif cap == GL_SCISSOR_TEST: s.scissor_enabled = value
+        elif cap == GL_BLEND: s.blending_enabled = value
+        elif cap == GL_DEPTH_TEST: s.depth_test_enabled = value
+        else: raise ValueError("unknown glEnable value")
+        self._dirty = True
+
+    def Enable(self, cap): self._cap(cap, 1)
+    def Disable(self, cap): self._cap(cap, 0)
+
+    def DepthFunc(self, v): self._state.depth_func = v; self._dirty = True
+    def DepthWriteMask(self, v): self._state.depth_write_mask = int(bool(v)); self._dirty = True
+    def ColorWriteMask(self, v): self._state.color_write_mask = int(bool(v)); self._dirty = True
+    def CullFace(self, v): self._state.cull_face = v; self._dirty = True
+
+    def Scissor(self, x, y, w, h):
+        self._state.scissor_origin[:] = [x, y]; self._state.scissor_size[:] = [w, h]; self._dirty = True
+
+    def Viewport(self, x, y, w, h):
+        self._state.viewport_origin[:] = [x, y]; self._state.viewport_size[:] = [w, h]; self._dirty = True
+
+    def UseProgram(self, pid): self._state.program_id = int(pid); self._dirty = True
+
+    def RenderbufferType(self, attachment, t):
+        if attachment == GL_DEPTH_ATTACHMENT: self._state.depth_attachment_type = t
+        elif attachment == GL_COLOR_ATTACHMENT0: self._state.color0_attachment_type = t
+        self._dirty = True
+
+    def ClearColor(self, rgb):
+        self._state.clear_color[:] = [float(rgb[0]), float(rgb[1]), float(rgb[2]), 1.0]; self._dirty = True
+
+    def ClearDepth(self, d): self._state.clear_depth = float(d); self._dirty = True
+
+    @staticmethod
+    def _mat(m):
+        """4x4 row-major numpy matrix (math convention) -> the reference's column-major ff[16]"""
+        return np.ascontiguousarray(np.asarray(m, dtype=np.float32).T.reshape(16))
+
+    def ViewMatrix(self, m): self._state.view_matrix[:] = self._mat(m); self._dirty = True
+    def ProjectionMatrix(self, m): self._state.projection_matrix[:] = self._mat(m); self._dirty = True
+    def NormalMatrix(self, m): self._state.normal_matrix[:] = self._mat(m); self._dirty = True
+
+    def UseBuffer(self, slot, arr, upload=UPLOAD_ALWAYS):
+        if arr is None:
+            self._check(self.L.rsrcu_bind_buffer(self.h, slot, None, 0, upload))
+            return
+        a = np.asarray(arr)
+        if a.ndim == 2:
+            for i in range(a.shape[0]):
+                self.UseBuffer(slot + i, a[i], upload)
+            return
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        self._keep.append(a)
+        self._check(self.L.rsrcu_bind_buffer(self.h, slot, _ptr(a), a.size, upload))
+
+    def UseUniforms(self, data):
+        b = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        assert b.size <= 128
+        buf = np.zeros(128, np.uint8)
+        buf[:b.size] = b
+        self._state.uniforms[:] = buf.view(np.float32)
+        self._state.uniforms_valid = 1
+        self._dirty = True
+
+    def BindTexture(self, unit, texels, width, height, stride, mode, upload=UPLOAD_ALWAYS):
+        t = np.ascontiguousarray(texels, dtype=np.float32)
+        rows = t.size // (4 * stride)
+        self._keep.append(t)
+        self._check(self.L.rsrcu_bind_texture(self.h, unit, _ptr(t), width, height, stride, mode, rows, upload))
+
+    def BindTexture3(self, depth, dim, upload=UPLOAD_ALWAYS):
+        t = np.ascontiguousarray(depth, dtype=np.float32)
+        self._keep.append(t)
+        self._check(self.L.rsrcu_bind_depth_texture(self.h, _ptr(t), dim, upload))
+
+    def Clear(self, bits):
+        self._flush_state()
+        self._check(self.L.rsrcu_clear(self.h, bits))
+
+    def DrawElements(self, count, indices, hint=0, upload=UPLOAD_ALWAYS):
+        idx = np.ascontiguousarray(indices, dtype=np.uint16)
+        self._keep.append(idx)
+        self._flush_state()
+        self._check(self.L.rsrcu_draw_elements(self.h, int(count), _ptr(idx), int(hint), 0, upload))
+
+    def DrawArrays(self, count):
+        self._flush_state()
+        self._check(self.L.rsrcu_draw_arrays(self.h, int(count), 0))
+
+    def DrawElementsInstanced(self, count, indices, instance_cnt, upload=UPLOAD_ALWAYS):
+        idx = np.ascontiguousarray(indices, dtype=np.uint16)
+        self._keep.append(idx)
+        self._flush_state()
+        self._check(self.L.rsrcu_draw_elements(self.h, int(count), _ptr(idx), 0, int(instance_cnt), upload))
+
+    def DrawArraysInstanced(self, count, instance_cnt):
+        self._flush_state()
+        self._check(self.L.rsrcu_draw_arrays(self.h, int(count), int(instance_cnt)))
+
+    def StoreColor(self, dst, gamma: bool = True):
+        """(H, W) uint32 -> CMD_STORE_COLOR_FULL_LINEAR_TC; (H, W, 4) float32 -> ..._LINEAR_FP;
+        None -> true-colour resolve kept on the device (see device_truecolor)"""
+        self._flush_state()
+        if dst is None:
+            self._check(self.L.rsrcu_store_color_tc(self.h, int(bool(gamma)), None, self.size[0], self.size[1], self.size[0]))
+        elif dst.dtype == np.uint32:
+            h, w = dst.shape
+            self._keep.append(dst)
+            self._check(self.L.rsrcu_store_color_tc(self.h, int(bool(gamma)), _ptr(dst), w, h, dst.strides[0] // 4))
+        else:
+            assert dst.dtype == np.float32 and dst.ndim == 3 and dst.shape[2] == 4
+            h, w, _ = dst.shape
+            self._keep.append(dst)
+            self._check(self.L.rsrcu_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 0))
+
+    def StoreDepth(self, dst):
+        assert dst.dtype == np.float32 and dst.flags.c_contiguous
+        self._flush_state()
+        self._keep.append(dst)
+        self._check(self.L.rsrcu_store_depth(self.h, _ptr(dst)))
+
+    # -- beyond the reference surface -------------------------------------------------------------
+    def stats(self) -> dict:
+        st = RsrStats()
+        self._check(self.L.rsrcu_get_stats(self.h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in RsrStats._fields_}
+
+    def set_profiling(self, on: bool): self._check(self.L.rsrcu_set_profiling(self.h, int(bool(on))))
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * 7)()
+        self._check(self.L.rsrcu_get_stage_ms(self.h, ms))
+        return dict(zip(("vertex", "setup", "bin_count", "bin_scan", "bin_fill", "tile", "frame"), [float(x) for x in ms]))
+
+    def device_truecolor(self):
+        p, s = C.c_void_p(), C.c_int()
+        self._check(self.L.rsrcu_device_truecolor(self.h, C.byref(p), C.byref(s)))
+        return p.value, s.value
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        self._check(self.L.rsrcu_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def get_host_luts(self):
+        rcp = np.zeros(2048, np.uint32)
+        rsq = np.zeros(2048, np.uint32)
+        self._check(self.L.rsrcu_get_host_luts(self.h, _ptr(rcp), _ptr(rsq)))
+        return rcp, rsq
+
+    def set_host_luts(self, rcp, rsq):
+        rcp = np.ascontiguousarray(rcp, dtype=np.uint32)
+        rsq = np.ascontiguousarray(rsq, dtype=np.uint32)
+        assert rcp.size == 2048 and rsq.size == 2048
+        self._check(self.L.rsrcu_set_host_luts(self.h, _ptr(rcp), _ptr(rsq)))

@@ -1,0 +1,91 @@
+// dev_math.cuh -- device equivalents of the reference's rml SIMD math (src/rml/rmlv/rmlv_mvec4.hxx,
+// rmlv_soa.hxx, rmlm_soa.hxx) at one-lane granularity.
+//
+// Everything here is IEEE fp32 round-to-nearest evaluated in the order the reference writes it.
+// The translation unit is compiled with -fmad=false so nvcc never contracts a*b+c into FFMA
+// (the reference is SSE: separate mulps/addps), with the default -prec-div / -prec-sqrt (IEEE
+// division and square root, like divps / sqrtps) and without -ftz.
+//
+// The two operations that are NOT IEEE on the CPU, rcpps and rsqrtps, are reproduced from
+// tables harvested from the host CPU (host_luts.cpp):
+//   rcpps(x)   depends on sign, exponent and the top 11 mantissa bits  -> 2048 entries
+//   rsqrtps(x) depends on exponent parity and the top 10 mantissa bits -> 2 x 1024 entries
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rsr {
+
+struct ApproxLuts {
+	uint32_t rcp[2048];
+	uint32_t rsqrt[2048];
+};
+
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+
+// _mm_max_ps / _mm_min_ps: second operand wins on NaN / equality (rmlv_mvec4.hxx:543-544)
+__device__ __forceinline__ float sse_max(float a, float b) { return (a > b) ? a : b; }
+__device__ __forceinline__ float sse_min(float a, float b) { return (a < b) ? a : b; }
+
+// _mm_cvttps_epi32: truncate; out of range and NaN give the "integer indefinite" 0x80000000
+__device__ __forceinline__ int cvtt(float f) {
+	return (fabsf(f) < 2147483648.0f) ? __float2int_rz(f) : static_cast<int>(0x80000000u); }
+
+// _mm_cvtepi32_ps
+__device__ __forceinline__ float itof(int i) { return __int2float_rn(i); }
+
+// rmlv::fract (rmlv_mvec4.hxx:578-585): a - float(trunc(a))
+__device__ __forceinline__ float fract_sse(float a) { return a - itof(cvtt(a)); }
+
+// rcpps, bit exact against the harvested table
+__device__ __forceinline__ float rcp_intel(float x, const uint32_t* __restrict__ lut) {
+	const uint32_t b = f2u(x);
+	const uint32_t sign = b & 0x80000000u;
+	const int E = static_cast<int>((b >> 23) & 0xffu);
+	const uint32_t m = b & 0x007fffffu;
+	if (E == 0) { return u2f(sign | 0x7f800000u); }              // zero and denormals -> +-inf
+	if (E == 255) { return m ? u2f(b | 0x00400000u) : u2f(sign); }  // nan -> qnan, inf -> +-0
+	const uint32_t r = lut[m >> 12];
+	const int re = static_cast<int>(r >> 23) + (127 - E);
+	if (re <= 0) { return u2f(sign); }                            // would be denormal -> +-0
+	return u2f(sign | (static_cast<uint32_t>(re) << 23) | (r & 0x007fffffu)); }
+
+// rsqrtps, bit exact against the harvested table
+__device__ __forceinline__ float rsqrt_intel(float x, const uint32_t* __restrict__ lut) {
+	const uint32_t b = f2u(x);
+	const uint32_t sign = b & 0x80000000u;
+	const int E = static_cast<int>((b >> 23) & 0xffu);
+	const uint32_t m = b & 0x007fffffu;
+	if (E == 255 && m) { return u2f(b | 0x00400000u); }           // nan
+	if (E == 0) { return u2f(sign | 0x7f800000u); }               // +-0 and denormals -> +-inf
+	if (sign) { return u2f(0xffc00000u); }                        // negative -> real indefinite
+	if (E == 255) { return 0.0f; }                                // +inf -> +0
+	const int e = E - 127;
+	const int p = e & 1;
+	const int k = (e - p) >> 1;
+	const uint32_t r = lut[(p << 10) | (m >> 13)];
+	return u2f(r - (static_cast<uint32_t>(k) << 23)); }
+
+// rmlv::oneover (rmlv_mvec4.hxx:630-650): rcpps + one Newton-Raphson step
+__device__ __forceinline__ float oneover(float a, const uint32_t* __restrict__ rcpLut) {
+	const float r = rcp_intel(a, rcpLut);
+	const float muls = a * (r * r);
+	return (r + r) - muls; }
+
+// qmat4 * qfloat4 (rmlm_soa.hxx:58-64), column-major m
+__device__ __forceinline__ void mat4_mul(const float* __restrict__ m, float x, float y, float z, float w,
+                                         float& ox, float& oy, float& oz, float& ow) {
+	ox = ((m[0] * x + m[4] * y) + m[8] * z) + m[12] * w;
+	oy = ((m[1] * x + m[5] * y) + m[9] * z) + m[13] * w;
+	oz = ((m[2] * x + m[6] * y) + m[10] * z) + m[14] * w;
+	ow = ((m[3] * x + m[7] * y) + m[11] * z) + m[15] * w; }
+
+// mul_w0(qmat4, qfloat3) (rmlm_soa.hxx:42-47)
+__device__ __forceinline__ void mat4_mul_w0(const float* __restrict__ m, float x, float y, float z,
+                                            float& ox, float& oy, float& oz) {
+	ox = (m[0] * x + m[4] * y) + m[8] * z;
+	oy = (m[1] * x + m[5] * y) + m[9] * z;
+	oz = (m[2] * x + m[6] * y) + m[10] * z; }
+
+}  // namespace rsr

@@ -1,0 +1,384 @@
+// programs.cuh -- the reference's shader programs (src/viewer/shaders.hxx, shaders_envmap.hxx,
+// shaders_wireframe.hxx) instantiated as CUDA device functors.
+//
+// The reference's program concept (`rglv::BaseProgram`, src/rgl/rglv/rglv_gpu_shaders.hxx:21-95)
+// is kept: each program has an `id`, an `earlyZ` flag, a vertex stage producing gl_Position plus
+// a block of varyings, and a fragment stage working on one 2x2 quad (4 lanes) at a time.
+// Varyings are a flat float[NV] per vertex; every reference program interpolates all of them
+// with the perspective barycentrics BP (`Interpolants::Interpolate`), which the tile kernel does
+// generically.
+//
+// Lane order inside a quad is the reference's: 0=(x,y) 1=(x+1,y) 2=(x,y+1) 3=(x+1,y+1).
+#pragma once
+#include "dev_math.cuh"
+
+namespace rsr {
+
+constexpr int kMaxVaryings = 16;
+
+struct TexUnit {
+	const float4* texels;   // device pointer
+	uint32_t texelCount;    // for clamping out-of-range gathers (reference reads out of bounds)
+	int width, height, stride;
+	int kind;               // 0 = non-pow2 nearest, 1 = pow2 mip nearest, 2 = pow2 mip bilinear
+	int power; };
+
+struct DevState {
+	float vm[16], pm[16], nm[16], vpm[16];     // rglv::Matrices (rglv_gpu_shaders.hxx:14-18)
+	float uniforms[32];
+	float DSx, DSy, DOx, DOy;                  // GPU::DSDO (rglv_gpu.hxx:265-270)
+	float clearColor[4];
+	float clearDepth;
+	int programId;
+	int cullingEnabled, cullFace;
+	int scissorX0, scissorY0, scissorX1, scissorY1;   // GPU::ScissorRect (rglv_gpu.hxx:272-276)
+	int depthTest, depthFunc, depthWrite, colorWrite, blend;
+	int color0Type, depthType;
+	const float* buffers[16];
+	TexUnit tu[2];
+	const float* tu3;
+	int tu3dim; };
+
+// SoA vertex attributes of one vertex (the reference's VertexInput structs)
+struct VertexIn {
+	float px, py, pz;      // slots 0-2
+	float nx, ny, nz;      // slots 3-5
+	float kx, ky, kz;      // slots 6-8
+	float u, v;            // slots 9-10
+	const float* imat; };  // slot 15: per-instance mat4 (column-major)
+
+struct FragIn {
+	const DevState* st;
+	const uint32_t* rcpLut;
+	const uint32_t* rsqrtLut;
+	float fragX[4], fragY[4];   // gl_FragCoord
+	float depth[4];             // gl_FragDepth
+	float BPx[4], BPy[4], BPz[4]; };
+
+// ---- texture units (src/rgl/rglr/rglr_texture_sampler.cxx) -------------------------------------
+
+__device__ __forceinline__ float4 fetch_texel(const TexUnit& tu, int ofs) {
+	// the reference would read out of bounds for wild coordinates; stay inside the allocation
+	const uint32_t o = static_cast<uint32_t>(ofs);
+	return __ldg(tu.texels + (o < tu.texelCount ? o : 0u)); }
+
+// coarse per-quad level of detail (rglr_texture_sampler.cxx:25-42): lanes 1 - 0 only
+__device__ __forceinline__ int level_of_detail(float u0, float u1, float v0, float v1) {
+	const float dux = u1 - u0;
+	const float dvx = v1 - v0;
+	const float sqd = dux * dux + dvx * dvx;
+	return (static_cast<int>(f2u(sqd)) - (127 << 23)) >> 24; }
+
+__device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[4], const float (&v)[4],
+                                            float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4]) {
+	if (tu.kind == 0) {
+		// TextureUnitRGBAF32_NM_ONEMAP_WRAP_NEAREST (rglr_texture_sampler.cxx:289-311)
+		const float fw = itof(tu.width), fh = itof(tu.height);
+		const float almostOne = u2f(0x3f7fffffu);
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			const int pxU = cvtt(fract_sse(u[l] + 100.0f) * fw);
+			const int pxV = cvtt((almostOne - fract_sse(v[l] + 100.0f)) * fh);
+			const float4 t = fetch_texel(tu, pxV * tu.stride + pxU);
+			r[l] = t.x; g[l] = t.y; b[l] = t.z; a[l] = t.w; }
+		return; }
+
+	const int POWER = tu.power;
+	const float baseDim = itof(1 << POWER);
+	int lod = level_of_detail(u[0] * baseDim, u[1] * baseDim, v[0] * baseDim, v[1] * baseDim);
+	lod = min(max(lod, 0), POWER);
+
+	if (tu.kind == 1) {
+		// ..._P2_MIPMAP_WRAP_NEAREST (rglr_texture_sampler.cxx:59-109)
+		const float levelDim = itof(1 << (POWER - lod));
+		const int levelBeginRow = static_cast<int>((0xfffffffeu << (POWER - lod)) & ((1u << (POWER + 1)) - 1u));
+		const float almostOne = u2f(0x3f7fffffu);
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			const int levelX = cvtt(fract_sse(u[l] + 10.0f) * levelDim);
+			const int levelY = cvtt((almostOne - fract_sse(v[l] + 10.0f)) * levelDim);
+			const int ofs = ((levelBeginRow + levelY) << POWER) + levelX;
+			const float4 t = fetch_texel(tu, ofs);
+			r[l] = t.x; g[l] = t.y; b[l] = t.z; a[l] = t.w; }
+		return; }
+
+	// ..._P2_MIPMAP_WRAP_LINEAR (rglr_texture_sampler.cxx:166-286)
+	const int levelDimI = 1 << (POWER - lod);
+	const int wrapMask = levelDimI - 1;
+	const int levelLastRow = static_cast<int>((0xffffffffu << (POWER - lod)) & ((1u << (POWER + 1)) - 1u)) - 1;
+	const float levelDim = itof(levelDimI);
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+		const float levelX = u[l] * levelDim;
+		const float levelY = v[l] * levelDim;
+		int tx0 = cvtt(levelX - 0.5f);
+		int ty0 = cvtt(levelY - 0.5f);
+		int tx1 = tx0 + 1;
+		int ty1 = ty0 + 1;
+		const float fx = (levelX - itof(tx0)) - 0.5f;
+		const float fy = (levelY - itof(ty0)) - 0.5f;
+		const float fx1 = 1.0f - fx;
+		const float fy1 = 1.0f - fy;
+		const float w00 = fx1 * fy1;
+		const float w10 = fx * fy1;
+		const float w01 = fx1 * fy;
+		const float w11 = fx * fy;
+		tx0 &= wrapMask; ty0 &= wrapMask; tx1 &= wrapMask; ty1 &= wrapMask;
+		const int by0 = levelLastRow - ty0;
+		const int by1 = levelLastRow - ty1;
+		const float4 p00 = fetch_texel(tu, (by0 << POWER) + tx0);
+		const float4 p10 = fetch_texel(tu, (by0 << POWER) + tx1);
+		const float4 p01 = fetch_texel(tu, (by1 << POWER) + tx0);
+		const float4 p11 = fetch_texel(tu, (by1 << POWER) + tx1);
+		r[l] = ((p00.x * w00 + p10.x * w10) + p01.x * w01) + p11.x * w11;
+		g[l] = ((p00.y * w00 + p10.y * w10) + p01.y * w01) + p11.y * w11;
+		b[l] = ((p00.z * w00 + p10.z * w10) + p01.z * w01) + p11.z * w11;
+		a[l] = ((p00.w * w00 + p10.w * w10) + p01.w * w01) + p11.w * w11; }}
+
+// DepthTextureUnit::sample (rglr_texture_sampler.hxx:61-79): nearest, clamp-to-border(-1)
+__device__ __forceinline__ float sample_depth(const DevState& st, float cx, float cy) {
+	const float dimf = itof(st.tu3dim);
+	const bool hit = (cx >= 0.0f) && (cx < 1.0f) && (cy >= 0.0f) && (cy < 1.0f);
+	const int px = cvtt(cx * dimf);
+	const int py = cvtt((1.0f - cy) * dimf);
+	const int ofs = (py * st.tu3dim + px) & (st.tu3dim * st.tu3dim - 1);
+	const float c = st.tu3 ? __ldg(st.tu3 + ofs) : 0.0f;
+	return hit ? c : -1.0f; }
+
+// ---- programs ---------------------------------------------------------------------------------
+// ShadeVertex: writes clip position and NV varyings.
+// ShadeFragment: attrs[k][lane]; writes colour (r,g,b,a)[lane]; may clear bits of `mask` (discard).
+
+struct ProgBase {   // rglv::BaseProgram
+	static constexpr int id = 0;
+	static constexpr bool earlyZ = true;
+	static constexpr int NV = 0; };
+
+struct ProgAmy : ProgBase {   // shaders.hxx:69-161
+	static constexpr int id = 4;
+	static constexpr int NV = 2;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
+		vary[0] = v.u; vary[1] = v.v;
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+		sample_quad(f.st->tu[0], at[0], at[1], r, g, b, a); } };
+
+struct ProgAlphaTexture : ProgAmy {   // shaders.hxx:164-229
+	static constexpr int id = 65;
+	static constexpr bool earlyZ = false;
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
+		sample_quad(f.st->tu[0], at[0], at[1], r, g, b, a);
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { if (!(a[l] > 0.0f)) { mask &= ~(1u << l); } } } };
+
+struct ProgText : ProgBase {   // shaders.hxx:232-318
+	static constexpr int id = 26;
+	static constexpr bool earlyZ = false;
+	static constexpr int NV = 5;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
+		vary[0] = v.kx; vary[1] = v.ky; vary[2] = v.kz; vary[3] = v.u; vary[4] = v.v;
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
+		sample_quad(f.st->tu[0], at[3], at[4], r, g, b, a);
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			r[l] *= at[0][l]; g[l] *= at[1][l]; b[l] *= at[2][l];
+			if (!(a[l] > 0.0f)) { mask &= ~(1u << l); } } } };
+
+struct ProgDepth : ProgAmy {   // shaders.hxx:321-419
+	static constexpr int id = 5;
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+		const float zNear = 10.0f, zFar = 1000.0f;
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			float tmp = sample_depth(*f.st, at[0][l], at[1][l]);
+			tmp = (2.0f * zNear) / ((zFar + zNear) - tmp * (zFar - zNear));
+			r[l] = tmp; g[l] = tmp; b[l] = tmp; a[l] = 1.0f; } } };
+
+struct ProgPattern : ProgBase {   // shaders.hxx:422-479; uniforms: vec4 offset, vec4 dim
+	static constexpr int id = 41;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float*) {
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+		const float offx = f.st->uniforms[0], offy = f.st->uniforms[1], dimy = f.st->uniforms[5];
+		float u[4], v[4];
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			u[l] = f.fragX[l] / dimy + offx;
+			v[l] = f.fragY[l] / dimy + offy; }
+		sample_quad(f.st->tu[0], u, v, r, g, b, a); } };
+
+struct ProgMany : ProgBase {   // shaders.hxx:482-583; uniforms: float magic
+	static constexpr int id = 6;
+	static constexpr int NV = 2;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
+		float p1[4];
+		mat4_mul(v.imat, v.px, v.py, v.pz, 1.0f, p1[0], p1[1], p1[2], p1[3]);
+		vary[0] = v.u; vary[1] = v.v;
+		mat4_mul(s.vpm, p1[0], p1[1], p1[2], p1[3], pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+		const float magic = f.st->uniforms[0];
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { r[l] = at[0][l]; g[l] = at[1][l]; b[l] = magic; a[l] = 1.0f; } } };
+
+// lightPos - p with the reference's qfloat4::operator- (rmlv_soa.hxx:163: w uses rhs.z), then
+// length / normalize / dot over 4 components exactly as OBJ1/OBJ2 do
+__device__ __forceinline__ float obj_point_light(const float (&sp)[4], const float (&sn)[4],
+                                                 const uint32_t* rsqrtLut) {
+	const float dx = 0.0f - sp[0], dy = 0.0f - sp[1], dz = 0.0f - sp[2], dw = 1.0f - sp[2];
+	const float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+	const float distance = sqrtf(d2);
+	const float scale = rsqrt_intel(d2, rsqrtLut);
+	const float lx = dx * scale, ly = dy * scale, lz = dz * scale, lw = dw * scale;
+	float diffuse = sse_max(((sn[0] * lx + sn[1] * ly) + sn[2] * lz) + sn[3] * lw, 0.1f);
+	diffuse = diffuse * (100.0f / distance);
+	return diffuse; }
+
+struct ProgOBJ1 : ProgBase {   // shaders.hxx:586-698
+	static constexpr int id = 7;
+	static constexpr int NV = 3;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary,
+	                                   const uint32_t* rsqrtLut) {
+		float mvv[4], mvn[4];
+		mat4_mul(s.vm, v.px, v.py, v.pz, 1.0f, mvv[0], mvv[1], mvv[2], mvv[3]);
+		mat4_mul(s.vm, v.nx, v.ny, v.nz, 0.0f, mvn[0], mvn[1], mvn[2], mvn[3]);
+		const float diffuse = obj_point_light(mvv, mvn, rsqrtLut);
+		vary[0] = v.kx * diffuse; vary[1] = v.ky * diffuse; vary[2] = v.kz * diffuse;
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn&, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { r[l] = at[0][l]; g[l] = at[1][l]; b[l] = at[2][l]; a[l] = 1.0f; } } };
+
+struct ProgOBJ2 : ProgBase {   // shaders.hxx:701-818; varyings sp(4) sn(4) kd(3)
+	static constexpr int id = 8;
+	static constexpr int NV = 11;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
+		mat4_mul(s.vm, v.px, v.py, v.pz, 1.0f, vary[0], vary[1], vary[2], vary[3]);
+		mat4_mul(s.vm, v.nx, v.ny, v.nz, 0.0f, vary[4], vary[5], vary[6], vary[7]);
+		vary[8] = v.kx; vary[9] = v.ky; vary[10] = v.kz;
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			const float sp[4] = { at[0][l], at[1][l], at[2][l], at[3][l] };
+			const float sn[4] = { at[4][l], at[5][l], at[6][l], at[7][l] };
+			const float diffuse = obj_point_light(sp, sn, f.rsqrtLut);
+			r[l] = at[8][l] * diffuse; g[l] = at[9][l] * diffuse; b[l] = at[10][l] * diffuse; a[l] = 1.0f; } } };
+
+struct ProgOBJ2S : ProgBase {   // shaders.hxx:821-978; varyings sp(4) sn(4) kd(3) lp(4)
+	static constexpr int id = 9;
+	static constexpr int NV = 15;
+	// uniforms: mat4 modelToShadow (0..15), vec3 lpos (16..18), vec3 ldir (19..21), float lcos (22)
+	// (rmlv::vec3 is 3 packed floats in UniformsSD)
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
+		mat4_mul(s.vm, v.px, v.py, v.pz, 1.0f, vary[0], vary[1], vary[2], vary[3]);
+		mat4_mul(s.nm, v.nx, v.ny, v.nz, 1.0f, vary[4], vary[5], vary[6], vary[7]);
+		vary[8] = v.kx; vary[9] = v.ky; vary[10] = v.kz;
+		mat4_mul(s.uniforms, v.px, v.py, v.pz, 1.0f, vary[11], vary[12], vary[13], vary[14]);
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&);
+};
+
+struct ProgEnvmap : ProgBase {   // shaders_envmap.hxx:26-140
+	static constexpr int id = 10;
+	static constexpr int NV = 2;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary,
+	                                   const uint32_t* rsqrtLut) {
+		float p[4];
+		mat4_mul(s.vm, v.px, v.py, v.pz, 1.0f, p[0], p[1], p[2], p[3]);
+		const float es = rsqrt_intel((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2], rsqrtLut);
+		const float ex = p[0] * es, ey = p[1] * es, ez = p[2] * es;
+		// vn = mix(smoothNormal, faceNormal, 0.0F) = a + t*(b-a)   (rmlv_mvec4.hxx:533-535)
+		const float vnx = v.nx + 0.0f * (v.kx - v.nx);
+		const float vny = v.ny + 0.0f * (v.ky - v.ny);
+		const float vnz = v.nz + 0.0f * (v.kz - v.nz);
+		float tx, ty, tz;
+		mat4_mul_w0(s.nm, vnx, vny, vnz, tx, ty, tz);
+		const float ns = rsqrt_intel((tx * tx + ty * ty) + tz * tz, rsqrtLut);
+		const float nx = tx * ns, ny = ty * ns, nz = tz * ns;
+		// reflect(i, n) = i - 2.0F * dot(n, i) * n   (rglv_math.hxx:44-45)
+		const float k = 2.0f * ((nx * ex + ny * ey) + nz * ez);
+		const float rx = ex - k * nx, ry = ey - k * ny, rz = ez - k * nz;
+		const float m = 2.0f * sqrtf(((rx * rx) + (ry * ry)) + ((rz + 1.0f) * (rz + 1.0f)));
+		vary[0] = rx / m + 0.5f;
+		vary[1] = ry / m + 0.5f;
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+		sample_quad(f.st->tu[0], at[0], at[1], r, g, b, a);
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { a[l] = 0.5f; } } };
+
+struct ProgWireframe : ProgBase {   // shaders_wireframe.hxx:29-70 (vertex stage = BaseProgram)
+	static constexpr int id = 11;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float*) {
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void fwidth4(const float (&a)[4], float (&o)[4]) {
+		// rglv_fragment.hxx:11-19: dFdx = yyww - xxzz, dFdy = xyxy - zwzw
+		const float dx0 = a[1] - a[0], dx1 = a[3] - a[2];
+		const float dy0 = a[0] - a[2], dy1 = a[1] - a[3];
+		o[0] = fabsf(dx0) + fabsf(dy0); o[1] = fabsf(dx0) + fabsf(dy1);
+		o[2] = fabsf(dx1) + fabsf(dy0); o[3] = fabsf(dx1) + fabsf(dy1); }
+	__device__ static float smoothstep0(float bb, float t) {
+		// rmlv_mvec4.hxx:767-769 with a = 0
+		float x = (t - 0.0f) / (bb - 0.0f);
+		x = sse_max(sse_min(x, 1.0f), 0.0f);
+		return (x * x) * (3.0f - 2.0f * x); }
+	__device__ static void ShadeFragment(const FragIn& f, const float (&)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+		float dX[4], dY[4], dZ[4];
+		fwidth4(f.BPx, dX); fwidth4(f.BPy, dY); fwidth4(f.BPz, dZ);
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			const float ax = smoothstep0(dX[l] * 1.5f, f.BPx[l]);
+			const float ay = smoothstep0(dY[l] * 1.5f, f.BPy[l]);
+			const float az = smoothstep0(dZ[l] * 1.5f, f.BPz[l]);
+			const float e = sse_min(ax, sse_min(ay, az));
+			// mix(mvec4f, mvec4f, mvec4f) = a + t*(b-a)
+			r[l] = (0.1f + e * (0.5f - 0.1f)) * 4.0f;
+			g[l] = (0.1f + e * (0.6f - 0.1f)) * 4.0f;
+			b[l] = (0.1f + e * (0.7f - 0.1f)) * 4.0f;
+			a[l] = 0.0f; } } };
+
+__device__ inline void ProgOBJ2S::ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
+                                                float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+	const float* u = f.st->uniforms;
+	const float lposx = u[16], lposy = u[17], lposz = u[18];
+	const float ldx = u[19], ldy = u[20], ldz = u[21];
+	const float lcos = u[22];
+	const float lds = rsqrt_intel((ldx * ldx + ldy * ldy) + ldz * ldz, f.rsqrtLut);
+	const float ndx = ldx * lds, ndy = ldy * lds, ndz = ldz * lds;
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+		const float dx = lposx - at[0][l], dy = lposy - at[1][l], dz = lposz - at[2][l];
+		const float d2 = (dx * dx + dy * dy) + dz * dz;
+		const float s = rsqrt_intel(d2, f.rsqrtLut);
+		const float stlx = dx * s, stly = dy * s, stlz = dz * s;
+		const float distanceToLight = sqrtf(d2);
+		float attenuation = 100.0f / distanceToLight;
+		const float angle = ((-stlx) * ndx + (-stly) * ndy) + (-stlz) * ndz;
+		if (angle < lcos) { attenuation = 0.111f; }
+		const float n2 = (at[4][l] * at[4][l] + at[5][l] * at[5][l]) + at[6][l] * at[6][l];
+		const float ns = rsqrt_intel(n2, f.rsqrtLut);
+		const float nx = at[4][l] * ns, ny = at[5][l] * ns, nz = at[6][l] * ns;
+		const float diffuseFactor = sse_max(0.0f, (nx * stlx + ny * stly) + nz * stlz);
+		const float lpx = at[11][l] / at[14][l];
+		const float lpy = at[12][l] / at[14][l];
+		const float lpz = at[13][l] / at[14][l];
+		const float tmp = sample_depth(*f.st, lpx * 0.5f + 0.5f, lpy * 0.5f + 0.5f);
+		if ((lpz - 0.0005f) > tmp) { attenuation = 0.111f; }
+		r[l] = (attenuation * at[8][l]) * diffuseFactor;
+		g[l] = (attenuation * at[9][l]) * diffuseFactor;
+		b[l] = (attenuation * at[10][l]) * diffuseFactor;
+		a[l] = 1.0f; } }
+
+}  // namespace rsr

@@ -1,0 +1,805 @@
+// rsrcu.cu -- the C ABI of include/rsrcu.h: frame recording on the host, kernel orchestration on
+// one CUDA stream per context.  Replaces rglv::GPU::RunImpl / BinImpl / DrawImpl
+// (src/rgl/rglv/rglv_gpu.cxx:90-432); the CPU job system (src/rcl/rclmt) has no counterpart here:
+// tiles are CTAs of one grid launch, frames are ordered by the stream.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rsrcu.h"
+#include "tile_kernel.cuh"
+
+namespace rsr {
+void harvest_luts(uint32_t* rcp2048, uint32_t* rsqrt2048);
+uint64_t verify_luts(const uint32_t* rcp2048, const uint32_t* rsqrt2048);
+}
+
+namespace {
+
+using namespace rsr;
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_lastError = buf;
+	return code; }
+
+#define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+	return fail(RSRCU_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+
+// growable device allocation
+struct DevBuf {
+	void* ptr{nullptr};
+	size_t cap{0};
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap) { return cudaSuccess; }
+		if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+		size_t want = std::max(bytes + bytes / 4, static_cast<size_t>(1) << 16);
+		cudaError_t e = cudaMalloc(&ptr, want);
+		if (e == cudaSuccess) { cap = want; }
+		return e; }
+	void release() { if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; } } };
+
+// pinned host staging mirrored by a device arena: all per-frame ("upload always") data and the
+// small frame tables go through it with ONE host->device copy per frame
+struct UploadArena {
+	uint8_t* host{nullptr};
+	size_t hostCap{0};
+	DevBuf dev;
+	size_t used{0};
+	cudaError_t reserveHost(size_t bytes) {
+		if (bytes <= hostCap) { return cudaSuccess; }
+		size_t want = std::max(bytes + bytes / 2, static_cast<size_t>(1) << 20);
+		uint8_t* nh = nullptr;
+		cudaError_t e = cudaMallocHost(&nh, want);
+		if (e != cudaSuccess) { return e; }
+		if (host) { std::memcpy(nh, host, used); cudaFreeHost(host); }
+		host = nh; hostCap = want;
+		return cudaSuccess; }
+	// returns offset
+	cudaError_t push(const void* src, size_t bytes, size_t& offset) {
+		const size_t at = (used + 255) & ~static_cast<size_t>(255);
+		cudaError_t e = reserveHost(at + bytes);
+		if (e != cudaSuccess) { return e; }
+		if (src) { std::memcpy(host + at, src, bytes); }
+		used = at + bytes;
+		offset = at;
+		return cudaSuccess; }
+	void release() { if (host) { cudaFreeHost(host); host = nullptr; hostCap = 0; } dev.release(); } };
+
+struct StaticAlloc { void* dev; size_t bytes; };
+
+struct PendingCopy { void* hostDst; const void* devSrc; size_t rowBytes; size_t rows; size_t hostPitch; size_t devPitch; };
+
+// a device pointer that is either absolute (static cache) or an offset into the frame arena
+struct DevRef { bool arena{false}; size_t off{0}; const void* abs{nullptr}; bool null{true}; };
+
+struct HostTex { DevRef ref; uint32_t texelCount{0}; int width{8}, height{8}, stride{8}, filter{0}; };
+
+struct HostState {
+	RsrState st;
+	DevRef buffers[16];
+	size_t bufferFloats[16];
+	HostTex tus[2];
+	DevRef tu3; int tu3dim{256}; };
+
+struct HostDraw {
+	DevDraw d;
+	DevRef indices; };
+
+}  // namespace
+
+struct rsrcu_ctx {
+	int device{0};
+	cudaStream_t stream{nullptr};
+	cudaEvent_t evStage[8]{};
+	bool profiling{false};
+	float stageMs[7]{};
+
+	ApproxLuts hostLuts;
+	ApproxLuts* devLuts{nullptr};
+
+	// recording
+	bool inFrame{false};
+	bool framePending{false};
+	int width{0}, height{0}, refTileW{64}, refTileH{64};
+	RsrState curState;
+	bool haveState{false};
+	bool stateDirty{true};
+	DevRef curBuffers[16];
+	size_t curBufferFloats[16]{};
+	HostTex curTus[2];
+	DevRef curTu3; int curTu3dim{256};
+	std::vector<HostState> states;
+	std::vector<HostDraw> draws;
+	std::vector<FrameCmd> cmds;
+	std::vector<int> cmdDstKind;      // 0 none, 1 tc, 2 fp, 3 depth
+	std::vector<PendingCopy> copies;
+	uint64_t trianglesSubmitted{0};
+
+	UploadArena arena;
+	std::unordered_map<const void*, StaticAlloc> staticCache;
+
+	// device work buffers
+	DevBuf ptvb, vflags, triInfo, clipRecs, segActive, counts, gsum, tileBase, tileCount, lists, counters;
+	DevBuf tcOut, fpOut, depthOut;
+	uint32_t clipCapacity{1u << 16};
+	uint32_t listCapacity{1u << 22};
+	int tcStride{0};
+	Counters* hostCounters{nullptr};   // pinned
+	RsrStats stats{};
+	uint64_t launches{0};
+};
+
+namespace {
+
+int keyOf(const RsrState& s) {
+	uint32_t key = 0;
+	key |= static_cast<uint32_t>(s.scissor_enabled != 0);
+	key |= (s.depth_test_enabled != 0) << 1;
+	if (s.depth_test_enabled) { key |= s.depth_func << 2; }
+	key |= (s.blending_enabled != 0) << 4;
+	key |= (s.depth_write_mask != 0) << 5;
+	key |= (s.color_write_mask != 0) << 6;
+	key |= s.color0_attachment_type << 7;
+	key |= s.depth_attachment_type << 9;
+	return static_cast<int>(key); }
+
+// the reference's dispatch tables (src/viewer/shaders.cxx:54-126, shaders_envmap.cxx:45-60,
+// shaders_wireframe.cxx:18-23): (program id, FragmentStateKey) pairs that have a tile program
+bool drawProgramInstalled(int programId, int key) {
+	static const struct { int id; int key; } table[] = {
+		{4, 0x6e2}, {4, 0x62}, {4, 0x72},
+		{65, 0x6e2}, {65, 0x62}, {65, 0x72},
+		{26, 0x72},
+		{41, 0x6e2}, {41, 0x62}, {41, 0x72},
+		{5, 0x62}, {6, 0x62}, {7, 0x62}, {8, 0x62}, {9, 0x62},
+		{11, 0x62},
+		{10, 0x22}, {10, 0x5a}, {10, 0x6e2}, {10, 0x62}, {10, 0x72}, {10, 0x50} };
+	for (const auto& e : table) { if (e.id == programId && e.key == key) { return true; } }
+	return false; }
+
+int programVaryings(int programId) {
+	switch (programId) {
+	case 4: case 65: case 5: case 6: case 10: return 2;
+	case 26: return 5;
+	case 7: return 3;
+	case 8: return 11;
+	case 9: return 15;
+	default: return 0; } }
+
+bool bltProgramInstalled(int programId) { return programId == 1 || programId == 2; }
+
+// ---- host-side matrix preparation, same operation order as the reference ----------------------
+
+// rmlm::operator*(mat4, mat4) (rmlm_mat4.hxx:197-207), column-major
+void mat4Mul(const float* lhs, const float* rhs, float* out) {
+	for (int row = 0; row < 4; ++row) {
+		for (int col = 0; col < 4; ++col) {
+			float ax;
+			ax = lhs[0 * 4 + row] * rhs[col * 4 + 0];
+			ax += lhs[1 * 4 + row] * rhs[col * 4 + 1];
+			ax += lhs[2 * 4 + row] * rhs[col * 4 + 2];
+			ax += lhs[3 * 4 + row] * rhs[col * 4 + 3];
+			out[col * 4 + row] = ax; } } }
+
+// rmlm::inverse (rmlm_mat4.cxx:25-186): cofactor expansion (the gluInvertMatrix scheme).  Each
+// output element is a signed sum of six triple products, accumulated left to right; the table
+// lists the factors and signs in that order so the float result is identical.
+void mat4Inverse(const float* m, float* inv) {
+	struct Term { int s, a, b, c; };
+	static const struct { int out; Term t[6]; } rows[16] = {
+		{0,  {{+1,5,10,15},{-1,5,11,14},{-1,9,6,15},{+1,9,7,14},{+1,13,6,11},{-1,13,7,10}}},
+		{4,  {{-1,4,10,15},{+1,4,11,14},{+1,8,6,15},{-1,8,7,14},{-1,12,6,11},{+1,12,7,10}}},
+		{8,  {{+1,4,9,15},{-1,4,11,13},{-1,8,5,15},{+1,8,7,13},{+1,12,5,11},{-1,12,7,9}}},
+		{12, {{-1,4,9,14},{+1,4,10,13},{+1,8,5,14},{-1,8,6,13},{-1,12,5,10},{+1,12,6,9}}},
+		{1,  {{-1,1,10,15},{+1,1,11,14},{+1,9,2,15},{-1,9,3,14},{-1,13,2,11},{+1,13,3,10}}},
+		{5,  {{+1,0,10,15},{-1,0,11,14},{-1,8,2,15},{+1,8,3,14},{+1,12,2,11},{-1,12,3,10}}},
+		{9,  {{-1,0,9,15},{+1,0,11,13},{+1,8,1,15},{-1,8,3,13},{-1,12,1,11},{+1,12,3,9}}},
+		{13, {{+1,0,9,14},{-1,0,10,13},{-1,8,1,14},{+1,8,2,13},{+1,12,1,10},{-1,12,2,9}}},
+		{2,  {{+1,1,6,15},{-1,1,7,14},{-1,5,2,15},{+1,5,3,14},{+1,13,2,7},{-1,13,3,6}}},
+		{6,  {{-1,0,6,15},{+1,0,7,14},{+1,4,2,15},{-1,4,3,14},{-1,12,2,7},{+1,12,3,6}}},
+		{10, {{+1,0,5,15},{-1,0,7,13},{-1,4,1,15},{+1,4,3,13},{+1,12,1,7},{-1,12,3,5}}},
+		{14, {{-1,0,5,14},{+1,0,6,13},{+1,4,1,14},{-1,4,2,13},{-1,12,1,6},{+1,12,2,5}}},
+		{3,  {{-1,1,6,11},{+1,1,7,10},{+1,5,2,11},{-1,5,3,10},{-1,9,2,7},{+1,9,3,6}}},
+		{7,  {{+1,0,6,11},{-1,0,7,10},{-1,4,2,11},{+1,4,3,10},{+1,8,2,7},{-1,8,3,6}}},
+		{11, {{-1,0,5,11},{+1,0,7,9},{+1,4,1,11},{-1,4,3,9},{-1,8,1,7},{+1,8,3,5}}},
+		{15, {{+1,0,5,10},{-1,0,6,9},{-1,4,1,10},{+1,4,2,9},{+1,8,1,6},{-1,8,2,5}}} };
+	for (const auto& r : rows) {
+		float acc = 0.0f;
+		for (int k = 0; k < 6; ++k) {
+			const Term& t = r.t[k];
+			volatile float p = m[t.a] * m[t.b];
+			volatile float q = p * m[t.c];
+			const float term = q;
+			if (k == 0) { acc = (t.s > 0) ? term : -term; }
+			else { acc = (t.s > 0) ? (acc + term) : (acc - term); } }
+		inv[r.out] = acc; }
+	const float det = ((m[0] * inv[0] + m[1] * inv[4]) + m[2] * inv[8]) + m[3] * inv[12];
+	const float invdet = 1.0f / det;
+	for (int i = 0; i < 16; ++i) { inv[i] *= invdet; } }
+
+void mat4Transpose(const float* m, float* out) {
+	for (int c = 0; c < 4; ++c) { for (int r = 0; r < 4; ++r) { out[c * 4 + r] = m[r * 4 + c]; } } }
+
+const void* resolve(const rsrcu_ctx* c, const DevRef& r) {
+	if (r.null) { return nullptr; }
+	if (r.arena) { return static_cast<const uint8_t*>(c->arena.dev.ptr) + r.off; }
+	return r.abs; }
+
+int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef& out) {
+	if (!host || bytes == 0) { out = DevRef{}; return RSRCU_OK; }
+	if (upload == RSRCU_UPLOAD_STATIC) {
+		auto it = c->staticCache.find(host);
+		if (it != c->staticCache.end() && it->second.bytes == bytes) {
+			out.null = false; out.arena = false; out.abs = it->second.dev;
+			return RSRCU_OK; }
+		if (it != c->staticCache.end()) { cudaFree(it->second.dev); c->staticCache.erase(it); }
+		void* d = nullptr;
+		CU(cudaMalloc(&d, bytes));
+		CU(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+		c->staticCache[host] = StaticAlloc{d, bytes};
+		out.null = false; out.arena = false; out.abs = d;
+		return RSRCU_OK; }
+	size_t off = 0;
+	CU(c->arena.push(host, bytes, off));
+	out.null = false; out.arena = true; out.off = off;
+	return RSRCU_OK; }
+
+// GL::MaybeUpdateState (rglv_gl.cxx:100-106): snapshot on first use after a change
+int snapshotState(rsrcu_ctx* c) {
+	if (!c->haveState) { return fail(RSRCU_ERR_INVALID, "no state set (rsrcu_set_state) before a command"); }
+	if (!c->stateDirty && !c->states.empty()) { return RSRCU_OK; }
+	HostState hs;
+	hs.st = c->curState;
+	for (int i = 0; i < 16; ++i) { hs.buffers[i] = c->curBuffers[i]; hs.bufferFloats[i] = c->curBufferFloats[i]; }
+	hs.tus[0] = c->curTus[0]; hs.tus[1] = c->curTus[1];
+	hs.tu3 = c->curTu3; hs.tu3dim = c->curTu3dim;
+	c->states.push_back(hs);
+	c->stateDirty = false;
+	return RSRCU_OK; }
+
+}  // namespace
+
+extern "C" {
+
+const char* rsrcu_last_error(void) { return g_lastError.c_str(); }
+
+int rsrcu_create(int device, rsrcu_ctx** out) {
+	if (!out) { return fail(RSRCU_ERR_INVALID, "out is null"); }
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		return fail(RSRCU_ERR_NO_DEVICE, "no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e)); }
+	if (device < 0 || device >= n) { return fail(RSRCU_ERR_INVALID, "device %d out of range (%d devices)", device, n); }
+	CU(cudaSetDevice(device));
+	auto* c = new rsrcu_ctx();
+	c->device = device;
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (auto& ev : c->evStage) { CU(cudaEventCreate(&ev)); }
+	rsr::harvest_luts(c->hostLuts.rcp, c->hostLuts.rsqrt);
+	static std::once_flag once;
+	static uint64_t mismatches = 0;
+	std::call_once(once, [&]() { mismatches = rsr::verify_luts(c->hostLuts.rcp, c->hostLuts.rsqrt); });
+	if (mismatches != 0) {
+		delete c;
+		return fail(RSRCU_ERR_UNSUPPORTED, "host rcpps/rsqrtps do not follow the table model (%llu mismatches); "
+		            "bit-exact parity with the reference on this CPU is not possible", static_cast<unsigned long long>(mismatches)); }
+	CU(cudaMalloc(&c->devLuts, sizeof(ApproxLuts)));
+	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
+	CU(cudaMallocHost(&c->hostCounters, sizeof(Counters)));
+	std::memset(c->hostCounters, 0, sizeof(Counters));
+	CU(c->counters.reserve(sizeof(Counters)));
+	*out = c;
+	return RSRCU_OK; }
+
+int rsrcu_destroy(rsrcu_ctx* c) {
+	if (!c) { return RSRCU_OK; }
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->clipRecs, &c->segActive, &c->counts, &c->gsum, &c->tileBase,
+	                   &c->tileCount, &c->lists, &c->counters, &c->tcOut, &c->fpOut, &c->depthOut }) { b->release(); }
+	c->arena.release();
+	if (c->devLuts) { cudaFree(c->devLuts); }
+	if (c->hostCounters) { cudaFreeHost(c->hostCounters); }
+	for (auto& ev : c->evStage) { cudaEventDestroy(ev); }
+	cudaStreamDestroy(c->stream);
+	delete c;
+	return RSRCU_OK; }
+
+int rsrcu_set_host_luts(rsrcu_ctx* c, const uint32_t* rcp2048, const uint32_t* rsqrt2x1024) {
+	if (!c || !rcp2048 || !rsqrt2x1024) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	std::memcpy(c->hostLuts.rcp, rcp2048, sizeof(c->hostLuts.rcp));
+	std::memcpy(c->hostLuts.rsqrt, rsqrt2x1024, sizeof(c->hostLuts.rsqrt));
+	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
+	return RSRCU_OK; }
+
+int rsrcu_get_host_luts(rsrcu_ctx* c, uint32_t* rcp2048, uint32_t* rsqrt2x1024) {
+	if (!c || !rcp2048 || !rsqrt2x1024) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	std::memcpy(rcp2048, c->hostLuts.rcp, sizeof(c->hostLuts.rcp));
+	std::memcpy(rsqrt2x1024, c->hostLuts.rsqrt, sizeof(c->hostLuts.rsqrt));
+	return RSRCU_OK; }
+
+int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int tileHBlocks) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (width <= 0 || height <= 0 || (width & 1) || (height & 1)) {
+		return fail(RSRCU_ERR_INVALID, "target %dx%d: dimensions must be positive and even (2x2 quads)", width, height); }
+	if (width > 2048 || height > 2048) {
+		return fail(RSRCU_ERR_UNSUPPORTED, "target %dx%d: the reference's guard band ends at 2048 px "
+		            "(rglv_view_frustum.hxx:36-39); render larger images as sub-frames", width, height); }
+	if (tileWBlocks <= 0 || tileHBlocks <= 0) { return fail(RSRCU_ERR_INVALID, "tile blocks must be positive"); }
+	CU(cudaSetDevice(c->device));
+	if (c->framePending) { int r = rsrcu_sync(c); if (r != RSRCU_OK) { return r; } }
+	c->width = width; c->height = height;
+	const int rw = tileWBlocks * 8, rh = tileHBlocks * 8;
+	// the device tile must lie inside one reference tile to reproduce its start point exactly;
+	// otherwise use the device tile itself (identical unless an int32 edge product overflows)
+	c->refTileW = (rw % kTile == 0) ? rw : kTile;
+	c->refTileH = (rh % kTile == 0) ? rh : kTile;
+	c->states.clear(); c->draws.clear(); c->cmds.clear(); c->cmdDstKind.clear(); c->copies.clear();
+	c->arena.used = 0;
+	c->trianglesSubmitted = 0;
+	c->haveState = false; c->stateDirty = true;
+	for (auto& b : c->curBuffers) { b = DevRef{}; }
+	for (auto& f : c->curBufferFloats) { f = 0; }
+	c->curTus[0] = HostTex{}; c->curTus[1] = HostTex{};
+	c->curTu3 = DevRef{}; c->curTu3dim = 256;
+	c->inFrame = true;
+	return RSRCU_OK; }
+
+int rsrcu_set_state(rsrcu_ctx* c, const RsrState* st) {
+	if (!c || !st) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_set_state outside begin/end frame"); }
+	c->curState = *st;
+	c->haveState = true;
+	c->stateDirty = true;
+	return RSRCU_OK; }
+
+int rsrcu_bind_buffer(rsrcu_ctx* c, int slot, const float* host, size_t nFloats, int upload) {
+	if (!c || slot < 0 || slot >= 16) { return fail(RSRCU_ERR_INVALID, "bad buffer slot %d", slot); }
+	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_buffer outside begin/end frame"); }
+	CU(cudaSetDevice(c->device));
+	int r = uploadData(c, host, nFloats * sizeof(float), upload, c->curBuffers[slot]);
+	if (r != RSRCU_OK) { return r; }
+	c->curBufferFloats[slot] = host ? nFloats : 0;
+	c->stateDirty = true;
+	return RSRCU_OK; }
+
+int rsrcu_bind_texture(rsrcu_ctx* c, int unit, const float* host, int width, int height, int stride, int filter,
+                       int rowsInMemory, int upload) {
+	if (!c || unit < 0 || unit > 1) { return fail(RSRCU_ERR_INVALID, "bad texture unit %d", unit); }
+	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_texture outside begin/end frame"); }
+	CU(cudaSetDevice(c->device));
+	HostTex& t = c->curTus[unit];
+	const size_t texels = static_cast<size_t>(stride) * static_cast<size_t>(rowsInMemory);
+	int r = uploadData(c, host, texels * 16, upload, t.ref);
+	if (r != RSRCU_OK) { return r; }
+	t.texelCount = static_cast<uint32_t>(texels);
+	t.width = width; t.height = height; t.stride = stride; t.filter = filter;
+	c->stateDirty = true;
+	return RSRCU_OK; }
+
+int rsrcu_bind_depth_texture(rsrcu_ctx* c, const float* host, int dim, int upload) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_depth_texture outside begin/end frame"); }
+	CU(cudaSetDevice(c->device));
+	int r = uploadData(c, host, static_cast<size_t>(dim) * dim * sizeof(float), upload, c->curTu3);
+	if (r != RSRCU_OK) { return r; }
+	c->curTu3dim = dim;
+	c->stateDirty = true;
+	return RSRCU_OK; }
+
+static int pushCmd(rsrcu_ctx* c, int type, int arg, void* dst, int stride, int kind) {
+	int r = snapshotState(c);
+	if (r != RSRCU_OK) { return r; }
+	FrameCmd cmd{};
+	cmd.type = type; cmd.state = static_cast<int>(c->states.size()) - 1; cmd.arg = arg; cmd.dst = dst; cmd.dstStride = stride;
+	c->cmds.push_back(cmd);
+	c->cmdDstKind.push_back(kind);
+	return RSRCU_OK; }
+
+int rsrcu_clear(rsrcu_ctx* c, int bits) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_clear outside begin/end frame"); }
+	if (bits & RSRCU_GL_STENCIL_BUFFER_BIT) { return fail(RSRCU_ERR_UNSUPPORTED, "CLEAR on STENCIL not implemented (rglv_gpu.cxx:313-315)"); }
+	if (c->haveState && c->curState.color0_attachment_type == RSRCU_RB_COLOR_DEPTH &&
+	    bits != (RSRCU_GL_COLOR_BUFFER_BIT | RSRCU_GL_DEPTH_BUFFER_BIT)) {
+		return fail(RSRCU_ERR_UNSUPPORTED, "must clear color and depth when using RB_COLOR_DEPTH (rglv_gpu.cxx:317-319)"); }
+	return pushCmd(c, kCmdClear, bits, nullptr, 0, 0); }
+
+static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int instanceCount, int upload, bool arrays) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "draw outside begin/end frame"); }
+	if (count < 0) { return fail(RSRCU_ERR_INVALID, "negative count"); }
+	int r = snapshotState(c);
+	if (r != RSRCU_OK) { return r; }
+	const HostState& hs = c->states.back();
+	const RsrState& st = hs.st;
+	const int key = keyOf(st);
+	if (!drawProgramInstalled(st.program_id, key)) {
+		return fail(RSRCU_ERR_NO_PROGRAM, "no dispatch entry for program %d state key 0x%x (src/viewer/shaders.cxx:54-126)", st.program_id, key); }
+	const bool instanced = instanceCount > 0;
+	const int instances = instanced ? instanceCount : 1;
+	if (instances > 65536) { return fail(RSRCU_ERR_INVALID, "instance id must fit uint16 (rglv_gpu_impl.hxx:490)"); }
+	const int prims = count / 3;
+	if (prims == 0) { return RSRCU_OK; }
+
+	HostDraw hd{};
+	DevDraw& d = hd.d;
+	d.state = static_cast<int>(c->states.size()) - 1;
+	d.prims = prims;
+	d.instances = instances;
+	d.instanced = instanced ? 1 : 0;
+	// vertex extent: explicit buffer length (slot 0) or, for arrays, the count
+	size_t nverts = 0;
+	if (arrays) { nverts = static_cast<size_t>(prims) * 3; }
+	else {
+		nverts = hs.bufferFloats[0];
+		if (hs.buffers[0].null) {
+			// no position buffer: every vertex is the origin; need max index + 1
+			uint16_t mx = 0;
+			for (int i = 0; i < prims * 3; ++i) { mx = std::max(mx, indices[i]); }
+			nverts = static_cast<size_t>(mx) + 1; } }
+	if (!arrays && !hs.buffers[0].null && nverts == 0) { return fail(RSRCU_ERR_INVALID, "position buffer has no length"); }
+	if (arrays && !hs.buffers[0].null && hs.bufferFloats[0] < nverts) {
+		return fail(RSRCU_ERR_INVALID, "DrawArrays count %d exceeds bound position buffer (%zu floats)", count, hs.bufferFloats[0]); }
+	for (int slot : {1, 2, 3, 4, 5, 6, 7, 8, 9, 10}) {
+		if (!hs.buffers[slot].null && hs.bufferFloats[slot] < nverts) {
+			return fail(RSRCU_ERR_INVALID, "buffer slot %d shorter (%zu) than the position buffer (%zu)", slot, hs.bufferFloats[slot], nverts); } }
+	if (instanced && (st.program_id == 6) && (hs.buffers[15].null || hs.bufferFloats[15] < static_cast<size_t>(instances) * 16)) {
+		return fail(RSRCU_ERR_INVALID, "instanced draw needs %d mat4 in slot 15", instances); }
+	d.nverts = static_cast<int>(nverts);
+	d.nvary = programVaryings(st.program_id);
+	d.strideF4 = 2 + (d.nvary + 3) / 4;
+	d.N = static_cast<uint32_t>(prims) * static_cast<uint32_t>(instances);
+	if (!arrays) {
+		if (!indices) { return fail(RSRCU_ERR_INVALID, "null index pointer"); }
+		r = uploadData(c, indices, static_cast<size_t>(prims) * 3 * sizeof(uint16_t), upload, hd.indices);
+		if (r != RSRCU_OK) { return r; } }
+	c->trianglesSubmitted += d.N;
+	c->draws.push_back(hd);
+	FrameCmd cmd{};
+	cmd.type = kCmdDraw; cmd.state = d.state; cmd.arg = static_cast<int>(c->draws.size()) - 1;
+	c->cmds.push_back(cmd);
+	c->cmdDstKind.push_back(0);
+	return RSRCU_OK; }
+
+int rsrcu_draw_elements(rsrcu_ctx* c, int count, const uint16_t* indices, int hint, int instanceCount, int upload) {
+	(void)hint;   // DENSE|READ4 only selects between two equivalent CPU bin loops (rglv_gpu_impl.hxx:274-294)
+	return recordDraw(c, count, indices, instanceCount, upload, false); }
+
+int rsrcu_draw_arrays(rsrcu_ctx* c, int count, int instanceCount) {
+	return recordDraw(c, count, nullptr, instanceCount, RSRCU_UPLOAD_ALWAYS, true); }
+
+int rsrcu_store_color_tc(rsrcu_ctx* c, int gamma, uint32_t* dst, int width, int height, int stridePx) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
+	if (c->haveState && !bltProgramInstalled(c->curState.program_id)) {
+		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67; IQ post is not built yet)", c->curState.program_id); }
+	CU(cudaSetDevice(c->device));
+	CU(c->tcOut.reserve(static_cast<size_t>(width) * height * 4));
+	c->tcStride = width;
+	int r = pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, c->tcOut.ptr, width, 1);
+	if (r != RSRCU_OK) { return r; }
+	if (dst) {
+		c->copies.push_back(PendingCopy{dst, c->tcOut.ptr, static_cast<size_t>(width) * 4, static_cast<size_t>(height),
+		                                static_cast<size_t>(stridePx) * 4, static_cast<size_t>(width) * 4}); }
+	return RSRCU_OK; }
+
+int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int stridePx, int half) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (half) { return fail(RSRCU_ERR_UNSUPPORTED, "CMD_STORE_COLOR_HALF_LINEAR_FP is not built yet"); }
+	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target", width, height); }
+	CU(cudaSetDevice(c->device));
+	CU(c->fpOut.reserve(static_cast<size_t>(width) * height * 16));
+	int r = pushCmd(c, kCmdStoreFP, 0, c->fpOut.ptr, width, 2);
+	if (r != RSRCU_OK) { return r; }
+	if (dst) {
+		c->copies.push_back(PendingCopy{dst, c->fpOut.ptr, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
+		                                static_cast<size_t>(stridePx) * 16, static_cast<size_t>(width) * 16}); }
+	return RSRCU_OK; }
+
+int rsrcu_store_depth(rsrcu_ctx* c, float* dst) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	CU(cudaSetDevice(c->device));
+	CU(c->depthOut.reserve(static_cast<size_t>(c->width) * c->height * 4));
+	int r = pushCmd(c, kCmdStoreDepth, 0, c->depthOut.ptr, c->width, 3);
+	if (r != RSRCU_OK) { return r; }
+	if (dst) {
+		c->copies.push_back(PendingCopy{dst, c->depthOut.ptr, static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->height),
+		                                static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->width) * 4}); }
+	return RSRCU_OK; }
+
+int rsrcu_end_frame(rsrcu_ctx* c) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_end_frame without begin"); }
+	CU(cudaSetDevice(c->device));
+	c->inFrame = false;
+	cudaStream_t st = c->stream;
+	c->launches = 0;
+
+	const int W = c->width, H = c->height;
+	FrameParams fp{};
+	fp.width = W; fp.height = H;
+	fp.tilesX = (W + kTile - 1) / kTile; fp.tilesY = (H + kTile - 1) / kTile;
+	fp.refTileW = c->refTileW; fp.refTileH = c->refTileH;
+	{
+		// CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
+		const int half = std::max(W, H) / 2;
+		fp.guardFactor = (2048.0f - static_cast<float>(half)) / static_cast<float>(half); }
+	fp.ndraws = static_cast<int>(c->draws.size());
+	fp.ncmds = static_cast<int>(c->cmds.size());
+	const int ntiles = fp.tilesX * fp.tilesY;
+
+	// ---- layout: ids, vertex records, segments, chunks ------------------------------------
+	uint64_t vjobs = 0, pjobs = 0, ids = 0, ptvbF4 = 0, nvertsTotal = 0;
+	std::vector<BinSeg> segs;
+	std::vector<uint32_t> chunkSegBegin;
+	uint32_t chunkFill = kChunk;   // force a new chunk for the first segment
+	auto addSeg = [&](uint32_t draw, uint32_t kind, uint32_t start, uint32_t len) {
+		if (chunkFill + len > kChunk) { chunkSegBegin.push_back(static_cast<uint32_t>(segs.size())); chunkFill = 0; }
+		segs.push_back(BinSeg{draw, kind, start, len});
+		chunkFill += len; };
+	for (size_t di = 0; di < c->draws.size(); ++di) {
+		DevDraw& d = c->draws[di].d;
+		d.vjobBase = static_cast<uint32_t>(vjobs);
+		d.pjobBase = static_cast<uint32_t>(pjobs);
+		d.idBase = static_cast<uint32_t>(ids);
+		d.vbaseF4 = static_cast<uint32_t>(ptvbF4);
+		d.flagBase = static_cast<uint32_t>(nvertsTotal);
+		const uint64_t nv = static_cast<uint64_t>(d.nverts) * d.instances;
+		vjobs += nv; nvertsTotal += nv; ptvbF4 += nv * d.strideF4;
+		pjobs += d.N;
+		ids += static_cast<uint64_t>(d.N) * (1 + kMaxFan);
+		for (uint32_t s0 = 0; s0 < d.N; s0 += kChunk) { addSeg(static_cast<uint32_t>(di), 0, s0, std::min<uint32_t>(kChunk, d.N - s0)); }
+		d.clipSegBase = static_cast<uint32_t>(segs.size());
+		// clip segments must be addressable as clipSegBase + source/kChunk
+		for (uint32_t s0 = 0; s0 < d.N; s0 += kChunk) { addSeg(static_cast<uint32_t>(di), 1, s0, std::min<uint32_t>(kChunk, d.N - s0)); } }
+	chunkSegBegin.push_back(static_cast<uint32_t>(segs.size()));
+	const int nchunks = static_cast<int>(chunkSegBegin.size()) - 1;
+	if (ids >= 0xfffffff0ull || ptvbF4 >= 0x7ffffff0ull || vjobs >= 0xfffffff0ull) {
+		return fail(RSRCU_ERR_UNSUPPORTED, "frame too large for 32-bit ids (%llu ids, %llu vertex records)",
+		            static_cast<unsigned long long>(ids), static_cast<unsigned long long>(ptvbF4)); }
+	fp.totalVJobs = static_cast<uint32_t>(vjobs);
+	fp.totalPJobs = static_cast<uint32_t>(pjobs);
+	fp.clipCapacity = c->clipCapacity;
+	fp.listCapacity = c->listCapacity;
+
+	// ---- frame tables into the arena (state / draw tables need final device addresses) -----
+	size_t offStates = 0, offDraws = 0, offCmds = 0, offSegs = 0, offChunks = 0;
+	CU(c->arena.push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
+	CU(c->arena.push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
+	CU(c->arena.push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
+	CU(c->arena.push(nullptr, sizeof(BinSeg) * std::max<size_t>(1, segs.size()), offSegs));
+	CU(c->arena.push(nullptr, sizeof(uint32_t) * chunkSegBegin.size(), offChunks));
+	CU(c->arena.dev.reserve(c->arena.used));
+
+	for (size_t i = 0; i < c->states.size(); ++i) {
+		const HostState& hs = c->states[i];
+		const RsrState& s = hs.st;
+		DevState ds{};
+		std::memcpy(ds.vm, s.view_matrix, sizeof(ds.vm));
+		std::memcpy(ds.pm, s.projection_matrix, sizeof(ds.pm));
+		// MakeMatrices (rglv_gpu_impl.hxx:45-51)
+		float inv[16];
+		mat4Inverse(s.view_matrix, inv);
+		mat4Transpose(inv, ds.nm);
+		mat4Mul(s.projection_matrix, s.view_matrix, ds.vpm);
+		if (s.uniforms_valid) { std::memcpy(ds.uniforms, s.uniforms, sizeof(ds.uniforms)); }
+		// GPU::DSDO (rglv_gpu.hxx:265-270): integer halves
+		const int vw = (s.viewport_size[0] > 0 && s.viewport_size[1] > 0) ? s.viewport_size[0] : W;
+		const int vh = (s.viewport_size[0] > 0 && s.viewport_size[1] > 0) ? s.viewport_size[1] : H;
+		ds.DSx = static_cast<float>(vw / 2);
+		ds.DSy = static_cast<float>(-vh / 2);
+		ds.DOx = static_cast<float>(vw / 2 + s.viewport_origin[0]);
+		ds.DOy = static_cast<float>(H - (vh / 2 + s.viewport_origin[1]));
+		std::memcpy(ds.clearColor, s.clear_color, sizeof(ds.clearColor));
+		ds.clearDepth = s.clear_depth;
+		ds.programId = s.program_id;
+		ds.cullingEnabled = s.culling_enabled; ds.cullFace = s.cull_face;
+		if (!s.scissor_enabled) { ds.scissorX0 = 0; ds.scissorY0 = 0; ds.scissorX1 = W; ds.scissorY1 = H; }
+		else {
+			// gl_offset_and_size_to_irect (rglv_gpu.hxx:258-263)
+			const int left = s.scissor_origin[0], right = left + s.scissor_size[0];
+			const int bottom = H - s.scissor_origin[1] - 1, top = bottom - s.scissor_size[1];
+			ds.scissorX0 = left; ds.scissorY0 = top; ds.scissorX1 = right; ds.scissorY1 = bottom; }
+		ds.depthTest = s.depth_test_enabled; ds.depthFunc = s.depth_func; ds.depthWrite = s.depth_write_mask;
+		ds.colorWrite = s.color_write_mask; ds.blend = s.blending_enabled;
+		ds.color0Type = s.color0_attachment_type; ds.depthType = s.depth_attachment_type;
+		for (int b = 0; b < 16; ++b) { ds.buffers[b] = static_cast<const float*>(resolve(c, hs.buffers[b])); }
+		for (int u = 0; u < 2; ++u) {
+			const HostTex& ht = hs.tus[u];
+			TexUnit& tu = ds.tu[u];
+			tu.texels = static_cast<const float4*>(resolve(c, ht.ref));
+			tu.texelCount = ht.texelCount;
+			tu.width = ht.width; tu.height = ht.height; tu.stride = ht.stride;
+			// MakeTextureUnit (rglr_texture_sampler.cxx:314-363)
+			int power = 0;
+			while ((1 << (power + 1)) <= ht.width) { ++power; }
+			const bool isPow2 = ((1 << power) == ht.width) && ht.width == ht.height && ht.stride == ht.width;
+			tu.power = power;
+			tu.kind = !isPow2 ? 0 : (ht.filter ? 2 : 1); }
+		ds.tu3 = static_cast<const float*>(resolve(c, hs.tu3));
+		ds.tu3dim = hs.tu3dim;
+		std::memcpy(c->arena.host + offStates + i * sizeof(DevState), &ds, sizeof(ds)); }
+	for (size_t i = 0; i < c->draws.size(); ++i) {
+		DevDraw d = c->draws[i].d;
+		d.indices = static_cast<const uint16_t*>(resolve(c, c->draws[i].indices));
+		std::memcpy(c->arena.host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
+	if (!c->cmds.empty()) { std::memcpy(c->arena.host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
+	if (!segs.empty()) { std::memcpy(c->arena.host + offSegs, segs.data(), sizeof(BinSeg) * segs.size()); }
+	std::memcpy(c->arena.host + offChunks, chunkSegBegin.data(), sizeof(uint32_t) * chunkSegBegin.size());
+
+	// texture units with pow2 dims outside 4..1024 cannot be made by the reference (exit(1))
+	for (const HostDraw& hd : c->draws) {
+		const HostState& hs = c->states[hd.d.state];
+		const int pid = hs.st.program_id;
+		const bool usesTu0 = (pid == 4 || pid == 65 || pid == 26 || pid == 41 || pid == 10);
+		if (usesTu0) {
+			const HostTex& ht = hs.tus[0];
+			if (ht.ref.null) { return fail(RSRCU_ERR_INVALID, "program %d samples texture unit 0 but none is bound", pid); }
+			int power = 0; while ((1 << (power + 1)) <= ht.width) { ++power; }
+			const bool isPow2 = ((1 << power) == ht.width) && ht.width == ht.height && ht.stride == ht.width;
+			if (isPow2 && (ht.width < 4 || ht.width > 1024)) {
+				return fail(RSRCU_ERR_UNSUPPORTED, "can't make TextureUnit for pow2 size %d (rglr_texture_sampler.cxx:333-357)", ht.width); } } }
+
+	// ---- device buffers -------------------------------------------------------------------
+	CU(c->ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
+	CU(c->vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
+	CU(c->triInfo.reserve(std::max<uint64_t>(1, ids) * 4));
+	CU(c->clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
+	CU(c->segActive.reserve(std::max<size_t>(1, segs.size()) * 4));
+	CU(c->counts.reserve(static_cast<size_t>(std::max(1, nchunks)) * ntiles * 4));
+	const int ngroups = std::max(1, std::min(64, nchunks));
+	const int chunksPerGroup = (std::max(1, nchunks) + ngroups - 1) / ngroups;
+	CU(c->gsum.reserve(static_cast<size_t>(ngroups) * ntiles * 4));
+	CU(c->tileBase.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(c->tileCount.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(c->lists.reserve(static_cast<size_t>(c->listCapacity) * 4));
+
+	const uint8_t* ab = static_cast<const uint8_t*>(c->arena.dev.ptr);
+	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
+	const DevDraw* dDraws = reinterpret_cast<const DevDraw*>(ab + offDraws);
+	const FrameCmd* dCmds = reinterpret_cast<const FrameCmd*>(ab + offCmds);
+	const BinSeg* dSegs = reinterpret_cast<const BinSeg*>(ab + offSegs);
+	const uint32_t* dChunks = reinterpret_cast<const uint32_t*>(ab + offChunks);
+	Counters* dCtr = static_cast<Counters*>(c->counters.ptr);
+
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
+	CU(cudaMemcpyAsync(c->arena.dev.ptr, c->arena.host, c->arena.used, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(dCtr, 0, sizeof(Counters), st));
+	CU(cudaMemsetAsync(c->segActive.ptr, 0, std::max<size_t>(1, segs.size()) * 4, st));
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[1], st)); }
+
+	if (fp.totalVJobs) {
+		vertex_kernel<<<(fp.totalVJobs + 255) / 256, 256, 0, st>>>(dDraws, dStates, fp, c->devLuts,
+			static_cast<float4*>(c->ptvb.ptr), static_cast<uint8_t*>(c->vflags.ptr));
+		++c->launches; }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[2], st)); }
+	if (fp.totalPJobs) {
+		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, dStates, fp, c->devLuts,
+			static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
+			static_cast<uint32_t*>(c->triInfo.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
+			static_cast<unsigned int*>(c->segActive.ptr), dCtr);
+		++c->launches; }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[3], st)); }
+
+	const size_t binSmem = static_cast<size_t>(kBinWarps) * ntiles * 4;
+	if (binSmem > 48 * 1024) {
+		CU(cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(binSmem)));
+		CU(cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(binSmem))); }
+	const int binBlocks = (nchunks + kBinWarps - 1) / kBinWarps;
+	if (nchunks > 0) {
+		bin_kernel<false><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, ntiles, fp.tilesX,
+			static_cast<const uint32_t*>(c->triInfo.ptr), static_cast<const ClipRec*>(c->clipRecs.ptr),
+			static_cast<const unsigned int*>(c->segActive.ptr), static_cast<uint32_t*>(c->counts.ptr),
+			static_cast<uint32_t*>(c->lists.ptr), c->listCapacity);
+		++c->launches; }
+	else { CU(cudaMemsetAsync(c->counts.ptr, 0, static_cast<size_t>(ntiles) * 4, st)); }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[4], st)); }
+	{
+		const int nc = std::max(1, nchunks);
+		dim3 grid((ntiles + 255) / 256, ngroups);
+		scan_group_sums<<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(c->counts.ptr), nc, ntiles, chunksPerGroup,
+			static_cast<uint32_t*>(c->gsum.ptr));
+		scan_tiles<<<1, 1024, 0, st>>>(static_cast<uint32_t*>(c->gsum.ptr), ngroups, ntiles, static_cast<uint32_t*>(c->tileBase.ptr),
+			static_cast<uint32_t*>(c->tileCount.ptr), dCtr, c->listCapacity);
+		scan_apply<<<grid, 256, 0, st>>>(static_cast<uint32_t*>(c->counts.ptr), nc, ntiles, chunksPerGroup,
+			static_cast<const uint32_t*>(c->gsum.ptr));
+		c->launches += 3; }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[5], st)); }
+	if (nchunks > 0) {
+		bin_kernel<true><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, ntiles, fp.tilesX,
+			static_cast<const uint32_t*>(c->triInfo.ptr), static_cast<const ClipRec*>(c->clipRecs.ptr),
+			static_cast<const unsigned int*>(c->segActive.ptr), static_cast<uint32_t*>(c->counts.ptr),
+			static_cast<uint32_t*>(c->lists.ptr), c->listCapacity);
+		++c->launches; }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], st)); }
+
+	TileArgs ta{};
+	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
+	ta.ptvb = static_cast<const float4*>(c->ptvb.ptr);
+	ta.triInfo = static_cast<const uint32_t*>(c->triInfo.ptr);
+	ta.clipRecs = static_cast<const ClipRec*>(c->clipRecs.ptr);
+	ta.lists = static_cast<const uint32_t*>(c->lists.ptr);
+	ta.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);
+	ta.tileCount = static_cast<const uint32_t*>(c->tileCount.ptr);
+	ta.ctr = dCtr;
+	tile_kernel<<<ntiles, kTileThreads, 0, st>>>(ta);
+	++c->launches;
+	CU(cudaGetLastError());
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], st)); }
+
+	for (const PendingCopy& pc : c->copies) {
+		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, st)); }
+	CU(cudaMemcpyAsync(c->hostCounters, dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+	c->framePending = true;
+	return RSRCU_OK; }
+
+int rsrcu_sync(rsrcu_ctx* c) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	if (!c->framePending) { return RSRCU_OK; }
+	c->framePending = false;
+	const Counters& k = *c->hostCounters;
+	c->stats.triangles_submitted = c->trianglesSubmitted;
+	c->stats.triangles_binned = k.binned;
+	c->stats.triangles_clipped = k.clipped;
+	c->stats.bin_entries = k.entries;
+	c->stats.fragments_shaded = k.fragments;
+	c->stats.kernel_launches = c->launches;
+	if (c->profiling) {
+		for (int i = 0; i < 6; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); }
+		// stage order of the header: vertex, setup, count, scan, fill, tile
+		cudaEventElapsedTime(&c->stageMs[6], c->evStage[0], c->evStage[7]); }
+	if (k.overflow & 2u) {
+		// grow for the next frame and report: this frame's tile lists were truncated
+		const uint64_t need = k.entries + k.entries / 4;
+		c->listCapacity = static_cast<uint32_t>(std::min<uint64_t>(need, 0xfffffff0ull));
+		return fail(RSRCU_ERR_OVERFLOW, "tile list capacity exceeded (%llu entries); capacity raised, render the frame again",
+		            static_cast<unsigned long long>(k.entries)); }
+	if (k.overflow & 1u) {
+		c->clipCapacity = c->clipCapacity * 2;
+		return fail(RSRCU_ERR_OVERFLOW, "clip record capacity exceeded (%u needed); capacity raised, render the frame again", k.clipAlloc); }
+	return RSRCU_OK; }
+
+int rsrcu_device_truecolor(rsrcu_ctx* c, void** devPtr, int* stridePx) {
+	if (!c || !devPtr || !stridePx) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	*devPtr = c->tcOut.ptr; *stridePx = c->tcStride;
+	return RSRCU_OK; }
+
+int rsrcu_stream(rsrcu_ctx* c, void** stream) {
+	if (!c || !stream) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	*stream = c->stream;
+	return RSRCU_OK; }
+
+int rsrcu_get_stats(rsrcu_ctx* c, RsrStats* out) {
+	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	*out = c->stats;
+	return RSRCU_OK; }
+
+int rsrcu_set_profiling(rsrcu_ctx* c, int enabled) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	c->profiling = enabled != 0;
+	return RSRCU_OK; }
+
+int rsrcu_get_stage_ms(rsrcu_ctx* c, float* ms7) {
+	if (!c || !ms7) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	// evStage: 0 start, 1 after upload, 2 after vertex, 3 after setup, 4 after count, 5 after scan, 6 after fill, 7 after tile
+	for (int i = 0; i < 7; ++i) { ms7[i] = c->stageMs[i]; }
+	return RSRCU_OK; }
+
+}  // extern "C"

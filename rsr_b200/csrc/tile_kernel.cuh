@@ -1,0 +1,447 @@
+// tile_kernel.cuh -- K6: one CTA per 32x32 screen tile, one thread per 2x2 quad.
+//
+// The CTA keeps the tile's colour + depth in shared memory (SoA per quad lane: conflict free) for
+// the whole frame: clear -> every draw's triangles in submission order -> resolve/stores.  It
+// replaces GPU::DrawImpl (rglv_gpu.cxx:263-432) + GPUTileImpl::DrawTriangles / DrawClipped
+// (rglv_gpu_impl.hxx:841-998) + VTriangleRasterizer / TriangleRasterizer (rglv_triangle.hxx)
+// + TriangleProgram::Render (rglv_gpu_impl.hxx:166-222) + FilterTile (rglr_algorithm.hxx:31-104).
+//
+// Per draw the tile's list segment is consumed in batches of 256 triangles:
+//   setup   thread t sets up triangle t: fixed-point vertices, int32 edge constants evaluated at
+//           the reference's own start point, bbox, 1/area, depth and 1/w per vertex -> smem
+//   filter  each warp (a 16x8 pixel region) ballots which of the 256 bboxes touch its region
+//   raster  for each surviving triangle, in order, every thread evaluates the three edge
+//           functions at its quad's four pixels; covered quads run depth test, perspective
+//           interpolation and the fragment program, then update the tile in shared memory.
+#pragma once
+#include "kernels.cuh"
+
+namespace rsr {
+
+// ryg's float->sRGB8 table (3rdparty/ryg-srgb/ryg-srgb.h:71-85, public domain, Fabian Giesen);
+// data only -- the reference resolves through it, so bit-exact output needs the same numbers.
+__constant__ uint32_t kSrgbTab4[104] = {
+	0x0073000d, 0x007a000d, 0x0080000d, 0x0087000d, 0x008d000d, 0x0094000d, 0x009a000d, 0x00a1000d,
+	0x00a7001a, 0x00b4001a, 0x00c1001a, 0x00ce001a, 0x00da001a, 0x00e7001a, 0x00f4001a, 0x0101001a,
+	0x010e0033, 0x01280033, 0x01410033, 0x015b0033, 0x01750033, 0x018f0033, 0x01a80033, 0x01c20033,
+	0x01dc0067, 0x020f0067, 0x02430067, 0x02760067, 0x02aa0067, 0x02dd0067, 0x03110067, 0x03440067,
+	0x037800ce, 0x03df00ce, 0x044600ce, 0x04ad00ce, 0x051400ce, 0x057b00c5, 0x05dd00bc, 0x063b00b5,
+	0x06970158, 0x07420142, 0x07e30130, 0x087b0120, 0x090b0112, 0x09940106, 0x0a1700fc, 0x0a9500f2,
+	0x0b0f01cb, 0x0bf401ae, 0x0ccb0195, 0x0d950180, 0x0e56016e, 0x0f0d015e, 0x0fbc0150, 0x10630143,
+	0x11070264, 0x1238023e, 0x1357021d, 0x14660201, 0x156601e9, 0x165a01d3, 0x174401c0, 0x182401af,
+	0x18fe0331, 0x1a9602fe, 0x1c1502d2, 0x1d7e02ad, 0x1ed4028d, 0x201a0270, 0x21520256, 0x227d0240,
+	0x239f0443, 0x25c003fe, 0x27bf03c4, 0x29a10392, 0x2b6a0367, 0x2d1d0341, 0x2ebe031f, 0x304d0300,
+	0x31d105b0, 0x34a80555, 0x37520507, 0x39d504c5, 0x3c37048b, 0x3e7c0458, 0x40a8042a, 0x42bd0401,
+	0x44c20798, 0x488e071e, 0x4c1c06b6, 0x4f76065d, 0x52a50610, 0x55ac05cc, 0x5892058f, 0x5b590559,
+	0x5e0c0a23, 0x631c0980, 0x67db08f6, 0x6c55087f, 0x70940818, 0x74a007bd, 0x787d076c, 0x7c330723,
+};
+
+struct TileShared {
+	float chan[4][4][kTileThreads];      // [r,g,b,depth][quad lane][thread]
+	int ec[3][kBatch];                   // edge functions at the tile origin
+	int edx[3][kBatch];
+	int edy[3][kBatch];
+	uint32_t bbox[kBatch];               // tile-local minx | miny<<6 | maxx<<12 | maxy<<18 | clipped<<24
+	float scale[kBatch];
+	float z[3][kBatch];
+	float iw[3][kBatch];
+	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
+};
+
+struct TileArgs {
+	FrameParams fp;
+	const FrameCmd* cmds;
+	const DevDraw* draws;
+	const DevState* states;
+	const ApproxLuts* luts;
+	const float4* ptvb;
+	const uint32_t* triInfo;
+	const ClipRec* clipRecs;
+	const uint32_t* lists;
+	const uint32_t* tileBase;
+	const uint32_t* tileCount;
+	Counters* ctr; };
+
+__device__ __forceinline__ bool top_left(int dy, int dx) { return (dy > 0) || (dy == 0 && dx > 0); }
+
+// Edge setup for one triangle of this tile.  `wide` selects the reference's 4-wide int32 path
+// (VTriangleRasterizer::Draw, rglv_triangle.hxx:193-240: all products wrap) or the scalar int64
+// path used for clipped triangles (TriangleRasterizer::Draw, :79-131).
+__device__ __forceinline__ void setup_edges(TileShared& sh, int slot, bool wide, bool clipped,
+                                            int x1, int x2, int x3, int y1, int y2, int y3,
+                                            int ox, int oy, int rl, int rt, int rr, int rb) {
+	int vminx = max(min(min(x1, x2), x3) >> 4, rl);
+	const int vmaxx = min((max(max(x1, x2), x3) + 15) >> 4, rr);
+	int vminy = max(min(min(y1, y2), y3) >> 4, rt);
+	const int vmaxy = min((max(max(y1, y2), y3) + 15) >> 4, rb);
+	vminx &= ~1;
+	vminy &= ~1;
+
+	const int lminx = max(vminx, ox) - ox, lmaxx = min(vmaxx, ox + kTile) - ox;
+	const int lminy = max(vminy, oy) - oy, lmaxy = min(vmaxy, oy + kTile) - oy;
+	if (lminx >= lmaxx || lminy >= lmaxy) { sh.bbox[slot] = 0; return; }
+
+	const uint32_t ux1 = x1, ux2 = x2, ux3 = x3, uy1 = y1, uy2 = y2, uy3 = y3;
+	const int dx12 = static_cast<int>(ux1 - ux2), dy12 = static_cast<int>(uy2 - uy1);
+	const int dx23 = static_cast<int>(ux2 - ux3), dy23 = static_cast<int>(uy3 - uy2);
+	const int dx31 = static_cast<int>(ux3 - ux1), dy31 = static_cast<int>(uy1 - uy3);
+	int c1, c2, c3;
+	float scale;
+	if (wide) {
+		const uint32_t sx = (static_cast<uint32_t>(vminx) << 4) + 8u;
+		const uint32_t sy = (static_cast<uint32_t>(vminy) << 4) + 8u;
+		uint32_t u1 = static_cast<uint32_t>(dy12) * (sx - ux1) + static_cast<uint32_t>(dx12) * (sy - uy1);
+		uint32_t u2 = static_cast<uint32_t>(dy23) * (sx - ux2) + static_cast<uint32_t>(dx23) * (sy - uy2);
+		uint32_t u3 = static_cast<uint32_t>(dy31) * (sx - ux3) + static_cast<uint32_t>(dx31) * (sy - uy3);
+		u1 = u1 + (top_left(dy12, dx12) ? 1u : 0u) - 1u;
+		u2 = u2 + (top_left(dy23, dx23) ? 1u : 0u) - 1u;
+		u3 = u3 + (top_left(dy31, dx31) ? 1u : 0u) - 1u;
+		c1 = static_cast<int>(u1) >> 4;
+		c2 = static_cast<int>(u2) >> 4;
+		c3 = static_cast<int>(u3) >> 4;
+		const int sum = static_cast<int>(static_cast<uint32_t>(c1) + static_cast<uint32_t>(c2) + static_cast<uint32_t>(c3));
+		scale = 1.0f / itof(sum); }
+	else {
+		const long long ldx12 = static_cast<long long>(x1) - x2, ldy12 = static_cast<long long>(y2) - y1;
+		const long long ldx23 = static_cast<long long>(x2) - x3, ldy23 = static_cast<long long>(y3) - y2;
+		const long long ldx31 = static_cast<long long>(x3) - x1, ldy31 = static_cast<long long>(y1) - y3;
+		const long long sx = (static_cast<long long>(vminx) << 4) + 8;
+		const long long sy = (static_cast<long long>(vminy) << 4) + 8;
+		long long l1 = ldy12 * (sx - x1) + ldx12 * (sy - y1);
+		long long l2 = ldy23 * (sx - x2) + ldx23 * (sy - y2);
+		long long l3 = ldy31 * (sx - x3) + ldx31 * (sy - y3);
+		if (ldy12 > 0 || (ldy12 == 0 && ldx12 > 0)) { l1++; } --l1;
+		if (ldy23 > 0 || (ldy23 == 0 && ldx23 > 0)) { l2++; } --l2;
+		if (ldy31 > 0 || (ldy31 == 0 && ldx31 > 0)) { l3++; } --l3;
+		l1 >>= 4; l2 >>= 4; l3 >>= 4;
+		c1 = static_cast<int>(l1); c2 = static_cast<int>(l2); c3 = static_cast<int>(l3);
+		scale = 1.0f / __ll2float_rn(l1 + l2 + l3); }
+
+	// move the start point from the reference's (vminx, vminy) to this tile's origin
+	const uint32_t mx = static_cast<uint32_t>(ox - vminx), my = static_cast<uint32_t>(oy - vminy);
+	sh.ec[0][slot] = static_cast<int>(static_cast<uint32_t>(c1) + mx * static_cast<uint32_t>(dy12) + my * static_cast<uint32_t>(dx12));
+	sh.ec[1][slot] = static_cast<int>(static_cast<uint32_t>(c2) + mx * static_cast<uint32_t>(dy23) + my * static_cast<uint32_t>(dx23));
+	sh.ec[2][slot] = static_cast<int>(static_cast<uint32_t>(c3) + mx * static_cast<uint32_t>(dy31) + my * static_cast<uint32_t>(dx31));
+	sh.edx[0][slot] = dx12; sh.edx[1][slot] = dx23; sh.edx[2][slot] = dx31;
+	sh.edy[0][slot] = dy12; sh.edy[1][slot] = dy23; sh.edy[2][slot] = dy31;
+	sh.scale[slot] = scale;
+	sh.bbox[slot] = static_cast<uint32_t>(lminx) | (static_cast<uint32_t>(lminy) << 6) |
+	                (static_cast<uint32_t>(lmaxx) << 12) | (static_cast<uint32_t>(lmaxy) << 18) |
+	                (clipped ? (1u << 24) : 0u); }
+
+__device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_t id, const DevDraw& d, const TileArgs& A,
+                                               int ox, int oy, int rl, int rt, int rr, int rb) {
+	const uint32_t local = id - d.idBase;
+	if (local < d.N) {
+		// GPUTileImpl::DrawTriangles (rglv_gpu_impl.hxx:880-946)
+		const uint32_t iid = local / static_cast<uint32_t>(d.prims);
+		const uint32_t prim = local - iid * static_cast<uint32_t>(d.prims);
+		uint32_t i0, i1, i2;
+		if (d.indices) { i0 = __ldg(d.indices + 3 * prim); i1 = __ldg(d.indices + 3 * prim + 1); i2 = __ldg(d.indices + 3 * prim + 2); }
+		else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
+		if (__ldg(A.triInfo + id) & kBackface) { const uint32_t t = i0; i0 = i2; i2 = t; }   // :467-470
+		const uint32_t vb = d.vbaseF4 + (iid * static_cast<uint32_t>(d.nverts)) * d.strideF4;
+		const uint32_t a0 = vb + i0 * d.strideF4, a1 = vb + i1 * d.strideF4, a2 = vb + i2 * d.strideF4;
+		const float4 v0 = __ldg(A.ptvb + a0), v1 = __ldg(A.ptvb + a1), v2 = __ldg(A.ptvb + a2);
+		sh.z[0][slot] = v0.z; sh.z[1][slot] = v1.z; sh.z[2][slot] = v2.z;
+		sh.iw[0][slot] = v0.w; sh.iw[1][slot] = v1.w; sh.iw[2][slot] = v2.w;
+		sh.vref[0][slot] = a0 + 2; sh.vref[1][slot] = a1 + 2; sh.vref[2][slot] = a2 + 2;
+		setup_edges(sh, slot, true, false,
+		            cvtt(16.0f * v0.x), cvtt(16.0f * v1.x), cvtt(16.0f * v2.x),
+		            cvtt(16.0f * v0.y), cvtt(16.0f * v1.y), cvtt(16.0f * v2.y), ox, oy, rl, rt, rr, rb); }
+	else {
+		// GPUTileImpl::DrawClipped (rglv_gpu_impl.hxx:949-998)
+		const uint32_t q = local - d.N;
+		const uint32_t src = q / kMaxFan, k = q - src * kMaxFan;
+		const uint32_t recIdx = __ldg(A.triInfo + d.idBase + src) & kNoClipRec;
+		const ClipRec& rec = A.clipRecs[recIdx];
+		const uint32_t base = recIdx * static_cast<uint32_t>(sizeof(ClipRec) / 16) + 2u;   // float4 index of v[0]
+		const uint32_t vsz = sizeof(ClipVertex) / 16;
+		const uint32_t j0 = 0, j1 = k + 1, j2 = k + 2;
+		const float4 v0 = rec.v[j0].dev, v1 = rec.v[j1].dev, v2 = rec.v[j2].dev;
+		sh.z[0][slot] = v0.z; sh.z[1][slot] = v1.z; sh.z[2][slot] = v2.z;
+		sh.iw[0][slot] = v0.w; sh.iw[1][slot] = v1.w; sh.iw[2][slot] = v2.w;
+		sh.vref[0][slot] = 0x80000000u | (base + j0 * vsz + 1u);
+		sh.vref[1][slot] = 0x80000000u | (base + j1 * vsz + 1u);
+		sh.vref[2][slot] = 0x80000000u | (base + j2 * vsz + 1u);
+		setup_edges(sh, slot, false, true,
+		            cvtt(v0.x * 16.0f), cvtt(v1.x * 16.0f), cvtt(v2.x * 16.0f),
+		            cvtt(v0.y * 16.0f), cvtt(v1.y * 16.0f), cvtt(v2.y * 16.0f), ox, oy, rl, rt, rr, rb); } }
+
+__device__ __forceinline__ bool depth_pass(int func, float frag, float dest) {
+	return func == 0 ? (frag < dest) : (func == 1 ? (frag <= dest) : (frag == dest)); }
+
+// TriangleProgram::Render for one quad (rglv_gpu_impl.hxx:166-222)
+template <class P>
+__device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, const int i, const TileArgs& A, const DevDraw& d,
+                                                const DevState& s, const int (&e1)[4], const int (&e2)[4], const uint32_t triMask,
+                                                const int px, const int py, const bool clipped) {
+	const float scale = sh.scale[i];
+	float BSx[4], BSy[4], BSz[4], fragDepth[4];
+	const float z0 = sh.z[0][i], z1 = sh.z[1][i], z2 = sh.z[2][i];
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+		BSx[l] = itof(e2[l]) * scale;
+		BSz[l] = itof(e1[l]) * scale;
+		BSy[l] = (1.0f - BSx[l]) - BSz[l];
+		fragDepth[l] = (BSx[l] * z0 + BSy[l] * z1) + BSz[l] * z2; }
+
+	uint32_t fragMask = triMask;
+	float destDepth[4];
+	if (P::earlyZ && s.depthTest) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			destDepth[l] = sh.chan[3][l][t];
+			if (!depth_pass(s.depthFunc, fragDepth[l], destDepth[l])) { fragMask &= ~(1u << l); } }
+		if (fragMask == 0) { return 0; } }
+	if (P::earlyZ && s.depthWrite) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { if (fragMask & (1u << l)) { sh.chan[3][l][t] = fragDepth[l]; } } }
+
+	// perspective-correct barycentrics
+	FragIn f;
+	f.st = &s;
+	f.rcpLut = A.luts->rcp;
+	f.rsqrtLut = A.luts->rsqrt;
+	const float iw0 = sh.iw[0][i], iw1 = sh.iw[1][i], iw2 = sh.iw[2][i];
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+		const float fragW = oneover((BSx[l] * iw0 + BSy[l] * iw1) + BSz[l] * iw2, A.luts->rcp);
+		f.BPx[l] = (iw0 * BSx[l]) * fragW;
+		f.BPz[l] = (iw2 * BSz[l]) * fragW;
+		f.BPy[l] = (1.0f - f.BPx[l]) - f.BPz[l];
+		f.depth[l] = fragDepth[l];
+		f.fragX[l] = (itof(px) + 0.5f) + static_cast<float>(l & 1);
+		// rglv_triangle.hxx:297 (4-wide) vs :160 (scalar, clipped triangles): the two differ by one row
+		f.fragY[l] = clipped ? ((itof(A.fp.height - py) - 0.5f) + ((l & 2) ? 0.0f : 1.0f))
+		                     : (((itof(A.fp.height) - 0.5f) - itof(py)) - ((l & 2) ? 1.0f : 0.0f)); }
+
+	// varyings: Interpolants::Interpolate(BS, BP) -- every reference program uses BP
+	float at[kMaxVaryings][4];
+	if constexpr (P::NV > 0) {
+		const uint32_t r0 = sh.vref[0][i], r1 = sh.vref[1][i], r2 = sh.vref[2][i];
+		const float4* base = (r0 & 0x80000000u) ? reinterpret_cast<const float4*>(A.clipRecs) : A.ptvb;
+		const float4* p0 = base + (r0 & 0x7fffffffu);
+		const float4* p1 = base + (r1 & 0x7fffffffu);
+		const float4* p2 = base + (r2 & 0x7fffffffu);
+#pragma unroll
+		for (int k4 = 0; k4 < (P::NV + 3) / 4; ++k4) {
+			const float4 a = __ldg(p0 + k4), b = __ldg(p1 + k4), c = __ldg(p2 + k4);
+			const float av[4] = { a.x, a.y, a.z, a.w }, bv[4] = { b.x, b.y, b.z, b.w }, cv[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+			for (int c4 = 0; c4 < 4; ++c4) {
+				const int k = k4 * 4 + c4;
+				if (k < P::NV) {
+#pragma unroll
+					for (int l = 0; l < 4; ++l) {
+						at[k][l] = (f.BPx[l] * av[c4] + f.BPy[l] * bv[c4]) + f.BPz[l] * cv[c4]; } } } } }
+
+	float cr[4], cg[4], cb[4], ca[4];
+	P::ShadeFragment(f, at, cr, cg, cb, ca, fragMask);
+
+	if (!P::earlyZ && s.depthTest) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			destDepth[l] = sh.chan[3][l][t];
+			if (!depth_pass(s.depthFunc, fragDepth[l], destDepth[l])) { fragMask &= ~(1u << l); } }
+		if (fragMask == 0) { return 0; } }
+	if (!P::earlyZ && s.depthWrite) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { if (fragMask & (1u << l)) { sh.chan[3][l][t] = fragDepth[l]; } } }
+
+	if (s.colorWrite) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) {
+			if (fragMask & (1u << l)) {
+				if (s.blend) {
+					// BlendAlpha (rglv_gpu_impl.hxx:80-84)
+					const float alpha = ca[l];
+					const float oma = 1.0f - alpha;
+					sh.chan[0][l][t] = cr[l] * alpha + sh.chan[0][l][t] * oma;
+					sh.chan[1][l][t] = cg[l] * alpha + sh.chan[1][l][t] * oma;
+					sh.chan[2][l][t] = cb[l] * alpha + sh.chan[2][l][t] * oma; }
+				else {
+					sh.chan[0][l][t] = cr[l];
+					sh.chan[1][l][t] = cg[l];
+					sh.chan[2][l][t] = cb[l]; } } } }
+	return __popc(fragMask); }
+
+template <class P>
+__device__ __noinline__ unsigned draw_segment(TileShared& sh, const TileArgs& A, const DevDraw& d, const DevState& s,
+                                              const uint32_t* __restrict__ list, uint32_t n,
+                                              int ox, int oy, int rl, int rt, int rr, int rb) {
+	const int t = threadIdx.x;
+	const int warp = t >> 5, lane = t & 31;
+	// warp region: 16x8 pixels = 8x4 quads; 2 regions across, 4 down
+	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
+	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;   // tile-local quad origin
+	unsigned frags = 0;
+
+	for (uint32_t b0 = 0; b0 < n; b0 += kBatch) {
+		const int nb = min(static_cast<uint32_t>(kBatch), n - b0);
+		__syncthreads();
+		if (t < nb) { setup_triangle(sh, t, __ldg(list + b0 + t), d, A, ox, oy, rl, rt, rr, rb); }
+		__syncthreads();
+
+		for (int k = 0; k < nb; k += 32) {
+			const int i = k + lane;
+			bool hit = false;
+			if (i < nb) {
+				const uint32_t bb = sh.bbox[i];
+				const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+				hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+			unsigned m = __ballot_sync(0xffffffffu, hit);
+			while (m) {
+				const int j = __ffs(m) - 1;
+				m &= m - 1;
+				const int ti = k + j;
+				const uint32_t bb = sh.bbox[ti];
+				const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+				if (lx < minx || lx >= maxx || ly < miny || ly >= maxy) { continue; }
+				int e1[4], e2[4];
+				uint32_t covered = 0;
+				{
+					const uint32_t ulx = lx, uly = ly;
+					const uint32_t dy1 = sh.edy[0][ti], dx1 = sh.edx[0][ti];
+					const uint32_t dy2 = sh.edy[1][ti], dx2 = sh.edx[1][ti];
+					const uint32_t dy3 = sh.edy[2][ti], dx3 = sh.edx[2][ti];
+					const uint32_t a1 = static_cast<uint32_t>(sh.ec[0][ti]) + ulx * dy1 + uly * dx1;
+					const uint32_t a2 = static_cast<uint32_t>(sh.ec[1][ti]) + ulx * dy2 + uly * dx2;
+					const uint32_t a3 = static_cast<uint32_t>(sh.ec[2][ti]) + ulx * dy3 + uly * dx3;
+					const uint32_t q1[4] = { a1, a1 + dy1, a1 + dx1, a1 + dx1 + dy1 };
+					const uint32_t q2[4] = { a2, a2 + dy2, a2 + dx2, a2 + dx2 + dy2 };
+					const uint32_t q3[4] = { a3, a3 + dy3, a3 + dx3, a3 + dx3 + dy3 };
+#pragma unroll
+					for (int l = 0; l < 4; ++l) {
+						e1[l] = static_cast<int>(q1[l]);
+						e2[l] = static_cast<int>(q2[l]);
+						if (static_cast<int>(q1[l] | q2[l] | q3[l]) >= 0) { covered |= (1u << l); } } }
+				if (covered == 0) { continue; }
+				frags += render_quad<P>(sh, t, ti, A, d, s, e1, e2, covered, ox + lx, oy + ly, (bb >> 24) & 1u); } } }
+	return frags; }
+
+// sRGB::to_tc / LinearColor::to_tc (rglr_canvas_util.hxx:15-62, ryg-srgb.h:183-223)
+__device__ __forceinline__ uint32_t srgb8(float f) {
+	const float clampMin = u2f((127u - 13u) << 23);
+	const float almostOne = u2f(0x3f7fffffu);
+	float c = sse_max(f, clampMin);
+	c = sse_min(c, almostOne);
+	const uint32_t bits = f2u(c);
+	const uint32_t tab = kSrgbTab4[(bits >> 20) - (127u - 13u) * 8u];
+	const uint32_t tmul = (bits >> 12) & 0xffu;
+	// _mm_madd_epi16(tab, tmul | 0x02000000): lo16*lo16 + hi16*hi16
+	const uint32_t prod = (tab & 0xffffu) * tmul + (tab >> 16) * 0x200u;
+	return prod >> 16; }
+
+__device__ __forceinline__ uint32_t linear8(float f) {
+	float r = sse_min(f, 1.0f);
+	r = sse_max(r, 0.0f);
+	return static_cast<uint32_t>(cvtt(r * 255.0f)); }
+
+__global__ void __launch_bounds__(kTileThreads)
+tile_kernel(TileArgs A) {
+	__shared__ TileShared sh;
+	const int t = threadIdx.x;
+	const int tile = blockIdx.x;
+	const int tileX = tile % A.fp.tilesX, tileY = tile / A.fp.tilesX;
+	const int ox = tileX * kTile, oy = tileY * kTile;
+	const int warp = t >> 5, lane = t & 31;
+	const int lx = (warp & 1) * 16 + (lane & 7) * 2, ly = (warp >> 1) * 8 + (lane >> 3) * 2;
+	const int px = ox + lx, py = oy + ly;
+	const bool onScreen = (px < A.fp.width) && (py < A.fp.height);
+
+	// the reference tile this device tile lies in: only its corner matters (edge start point)
+	const int rl = (ox / A.fp.refTileW) * A.fp.refTileW, rt = (oy / A.fp.refTileH) * A.fp.refTileH;
+	const int rr = min(rl + A.fp.refTileW, A.fp.width), rb = min(rt + A.fp.refTileH, A.fp.height);
+
+	const uint32_t* list = A.lists + A.tileBase[tile];
+	const uint32_t listLen = A.tileCount[tile];
+	uint32_t cursor = 0;
+	unsigned frags = 0;
+
+#pragma unroll
+	for (int c = 0; c < 4; ++c) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { sh.chan[c][l][t] = 0.0f; } }
+
+	for (int ci = 0; ci < A.fp.ncmds; ++ci) {
+		const FrameCmd cmd = A.cmds[ci];
+		const DevState& s = A.states[cmd.state];
+		switch (cmd.type) {
+		case kCmdClear: {
+			// GPU::DrawImpl CMD_CLEAR (rglv_gpu.cxx:311-344)
+			const bool clearColor = (cmd.arg & 1) != 0, clearDepth = (cmd.arg & 2) != 0;
+#pragma unroll
+			for (int l = 0; l < 4; ++l) {
+				if (clearColor) { sh.chan[0][l][t] = s.clearColor[0]; sh.chan[1][l][t] = s.clearColor[1]; sh.chan[2][l][t] = s.clearColor[2]; }
+				if (clearDepth) { sh.chan[3][l][t] = s.clearDepth; } } }
+			break;
+		case kCmdDraw: {
+			const DevDraw& d = A.draws[cmd.arg];
+			// this draw's slice of the (id-sorted) tile list
+			const uint32_t idEnd = d.idBase + d.N * (1u + kMaxFan);
+			uint32_t lo = cursor, hi = listLen;
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (__ldg(list + mid) < idEnd) { lo = mid + 1; } else { hi = mid; } }
+			const uint32_t n = lo - cursor;
+			if (n > 0) {
+				const uint32_t* seg = list + cursor;
+				switch (s.programId) {
+				case ProgAmy::id:          frags += draw_segment<ProgAmy>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgAlphaTexture::id: frags += draw_segment<ProgAlphaTexture>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgText::id:         frags += draw_segment<ProgText>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgDepth::id:        frags += draw_segment<ProgDepth>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgPattern::id:      frags += draw_segment<ProgPattern>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgMany::id:         frags += draw_segment<ProgMany>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgOBJ1::id:         frags += draw_segment<ProgOBJ1>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgOBJ2::id:         frags += draw_segment<ProgOBJ2>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgOBJ2S::id:        frags += draw_segment<ProgOBJ2S>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgEnvmap::id:       frags += draw_segment<ProgEnvmap>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				case ProgWireframe::id:    frags += draw_segment<ProgWireframe>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+				default: break; }
+				cursor = lo; } }
+			break;
+		case kCmdStoreTC: {
+			// GPUBltImpl::StoreTrueColor -> FilterTile<SHADER, sRGB|LinearColor>
+			if (onScreen) {
+				uint32_t out[4];
+#pragma unroll
+				for (int l = 0; l < 4; ++l) {
+					float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
+					if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
+						const float ex = s.uniforms[0];
+						r = r * ex; g = g * ex; b = b * ex; }
+					out[l] = (cmd.arg & 1) ? ((srgb8(r) << 16) | (srgb8(g) << 8) | srgb8(b))
+					                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
+				uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
+				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
+				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_uint2(out[2], out[3]); } }
+			break;
+		case kCmdStoreFP: {
+			// Copy(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:247-279): alpha = 0
+			if (onScreen) {
+				float4* dst = static_cast<float4*>(cmd.dst);
+#pragma unroll
+				for (int l = 0; l < 4; ++l) {
+					dst[static_cast<size_t>(py + (l >> 1)) * cmd.dstStride + px + (l & 1)] =
+						make_float4(sh.chan[0][l][t], sh.chan[1][l][t], sh.chan[2][l][t], 0.0f); } } }
+			break;
+		case kCmdStoreDepth: {
+			if (onScreen) {
+				float* dst = static_cast<float*>(cmd.dst);
+				*reinterpret_cast<float2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_float2(sh.chan[3][0][t], sh.chan[3][1][t]);
+				*reinterpret_cast<float2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_float2(sh.chan[3][2][t], sh.chan[3][3][t]); } }
+			break;
+		default: break; } }
+
+	// fragment statistics: one atomic per CTA
+	for (int o = 16; o > 0; o >>= 1) { frags += __shfl_down_sync(0xffffffffu, frags, o); }
+	__shared__ unsigned blockFrags;
+	if (t == 0) { blockFrags = 0; }
+	__syncthreads();
+	if (lane == 0 && frags) { atomicAdd(&blockFrags, frags); }
+	__syncthreads();
+	if (t == 0 && blockFrags) { atomicAdd(&A.ctr->fragments, static_cast<unsigned long long>(blockFrags)); } }
+
+}  // namespace rsr

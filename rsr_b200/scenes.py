@@ -1,0 +1,316 @@
+"""Synthetic scenes + camera helpers shared by tests, smoke() and bench.py.
+
+A scene is a function `build(gl, out, ...)` that records one frame into any object exposing the
+reference's `rglv::GL` method names -- `rsr_b200.GPU` (CUDA) or `oracle.refgl.RefGPU` (the
+unmodified reference) -- so both renderers see byte-identical inputs.  Mesh / texture
+generation is input preparation, not part of the hot path; everything is seeded.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import (GL_BACK, GL_BLEND, GL_COLOR_BUFFER_BIT, GL_CULL_FACE, GL_DEPTH_BUFFER_BIT, GL_FRONT,
+               GL_LINEAR_MIPMAP_NEAREST, GL_NEAREST_MIPMAP_NEAREST, PROGRAM_AMY, PROGRAM_DEFAULT_POST,
+               PROGRAM_MANY, PROGRAM_OBJ2)
+
+
+# ---- aligned SoA arrays (the reference's LoadMD does _mm_load_ps on 4 floats at a time) --------
+
+def aligned_f32(n: int, fill: float = 0.0) -> np.ndarray:
+    """float32 array of length n padded to a multiple of 4, 64-byte aligned"""
+    n4 = (int(n) + 3) & ~3
+    raw = np.zeros(n4 * 4 + 64, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 64
+    a = raw[off:off + n4 * 4].view(np.float32)
+    a[:] = fill
+    return a
+
+
+def soa(arr: np.ndarray) -> np.ndarray:
+    """(k, n) array -> (k, n4) aligned, zero padded"""
+    arr = np.asarray(arr, dtype=np.float32)
+    k, n = arr.shape
+    n4 = (n + 3) & ~3
+    raw = np.zeros(k * n4 * 4 + 64, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 64
+    out = raw[off:off + k * n4 * 4].view(np.float32).reshape(k, n4)
+    out[:, :n] = arr
+    return out
+
+
+# ---- matrices (row-major numpy, math convention; the GL wrappers transpose) ---------------------
+
+def perspective(fovy_deg: float, aspect: float, znear: float, zfar: float) -> np.ndarray:
+    f = 1.0 / np.tan(np.radians(fovy_deg) / 2.0)
+    m = np.zeros((4, 4), np.float64)
+    m[0, 0] = f / aspect
+    m[1, 1] = f
+    m[2, 2] = (zfar + znear) / (znear - zfar)
+    m[2, 3] = 2.0 * zfar * znear / (znear - zfar)
+    m[3, 2] = -1.0
+    return m.astype(np.float32)
+
+
+def frustum(l, r, b, t, n, f) -> np.ndarray:
+    m = np.zeros((4, 4), np.float64)
+    m[0, 0] = 2 * n / (r - l); m[0, 2] = (r + l) / (r - l)
+    m[1, 1] = 2 * n / (t - b); m[1, 2] = (t + b) / (t - b)
+    m[2, 2] = -(f + n) / (f - n); m[2, 3] = -2 * f * n / (f - n)
+    m[3, 2] = -1.0
+    return m.astype(np.float32)
+
+
+def subframe_projection(fovy_deg, aspect, znear, zfar, gx, gy, nx, ny) -> np.ndarray:
+    """off-axis frustum of sub-frame (gx, gy) of an nx x ny grid (gy = 0 is the TOP row)"""
+    top = znear * np.tan(np.radians(fovy_deg) / 2.0)
+    right = top * aspect
+    l = -right + 2 * right * gx / nx
+    r = -right + 2 * right * (gx + 1) / nx
+    t = top - 2 * top * gy / ny
+    b = top - 2 * top * (gy + 1) / ny
+    return frustum(l, r, b, t, znear, zfar)
+
+
+def orthographic(l, r, b, t, n, f) -> np.ndarray:
+    m = np.eye(4, dtype=np.float64)
+    m[0, 0] = 2 / (r - l); m[0, 3] = -(r + l) / (r - l)
+    m[1, 1] = 2 / (t - b); m[1, 3] = -(t + b) / (t - b)
+    m[2, 2] = -2 / (f - n); m[2, 3] = -(f + n) / (f - n)
+    return m.astype(np.float32)
+
+
+def translate(x, y, z) -> np.ndarray:
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = [x, y, z]
+    return m
+
+
+def scale(x, y=None, z=None) -> np.ndarray:
+    y = x if y is None else y
+    z = x if z is None else z
+    return np.diag([x, y, z, 1.0]).astype(np.float32)
+
+
+def rotate(theta, x, y, z) -> np.ndarray:
+    v = np.array([x, y, z], np.float64)
+    v /= np.linalg.norm(v)
+    c, s = np.cos(theta), np.sin(theta)
+    t = 1 - c
+    x, y, z = v
+    m = np.eye(4, dtype=np.float64)
+    m[:3, :3] = [[t * x * x + c, t * x * y - s * z, t * x * z + s * y],
+                 [t * x * y + s * z, t * y * y + c, t * y * z - s * x],
+                 [t * x * z - s * y, t * y * z + s * x, t * z * z + c]]
+    return m.astype(np.float32)
+
+
+def look_at(eye, center, up=(0, 1, 0)) -> np.ndarray:
+    eye, center, up = (np.asarray(v, np.float64) for v in (eye, center, up))
+    f = center - eye
+    f /= np.linalg.norm(f)
+    s = np.cross(f, up)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    m = np.eye(4, dtype=np.float64)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, -f
+    m[:3, 3] = -m[:3, :3] @ eye
+    return m.astype(np.float32)
+
+
+# ---- meshes -------------------------------------------------------------------------------------
+
+def grid_mesh(nx: int, ny: int, w: float, h: float, wave: float = 0.0):
+    """(pos(3,N), normal(3,N), uv(2,N), indices) of an nx x ny vertex grid in the xy plane"""
+    xs, ys = np.meshgrid(np.linspace(-w / 2, w / 2, nx), np.linspace(-h / 2, h / 2, ny))
+    zs = wave * np.sin(xs * 2.0) * np.cos(ys * 3.0)
+    pos = np.stack([xs.ravel(), ys.ravel(), zs.ravel()]).astype(np.float32)
+    nrm = np.zeros_like(pos)
+    nrm[2] = 1.0
+    uv = np.stack([(xs.ravel() / w + 0.5), (ys.ravel() / h + 0.5)]).astype(np.float32)
+    j, i = np.meshgrid(np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+    a = (j * nx + i).ravel()
+    idx = np.stack([a, a + 1, a + nx, a + 1, a + nx + 1, a + nx], axis=1).ravel().astype(np.uint16)
+    assert pos.shape[1] <= 32768
+    return pos, nrm, uv, idx
+
+
+def cube_mesh(size: float = 1.0):
+    """24-vertex cube with per-face normals and uv"""
+    s = size / 2
+    faces = [((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (-1, 0, 0), (0, 1, 0)),
+             ((1, 0, 0), (0, 0, -1), (0, 1, 0)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)),
+             ((0, 1, 0), (1, 0, 0), (0, 0, -1)), ((0, -1, 0), (1, 0, 0), (0, 0, 1))]
+    pos, nrm, uv, idx = [], [], [], []
+    for n, u, v in faces:
+        n, u, v = (np.array(a, np.float32) for a in (n, u, v))
+        base = len(pos)
+        for (cu, cv) in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+            pos.append((n + cu * u + cv * v) * s)
+            nrm.append(n)
+            uv.append(((cu + 1) / 2, (cv + 1) / 2))
+        idx += [base, base + 1, base + 2, base, base + 2, base + 3]
+    return (np.array(pos, np.float32).T.copy(), np.array(nrm, np.float32).T.copy(),
+            np.array(uv, np.float32).T.copy(), np.array(idx, np.uint16))
+
+
+def icosphere(divs: int, radius: float = 1.0):
+    """subdivided icosahedron: (pos(3,N), normal(3,N), indices int32 (M,3))"""
+    t = (1.0 + 5 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5],
+                  [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], np.int64)
+    for _ in range(divs):
+        edges = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+        key = np.sort(edges, axis=1)
+        uniq, inv = np.unique(key, axis=0, return_inverse=True)
+        mid = v[uniq[:, 0]] + v[uniq[:, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        base = len(v)
+        v = np.concatenate([v, mid])
+        n = len(f)
+        a, b, c = base + inv[:n], base + inv[n:2 * n], base + inv[2 * n:]
+        f = np.concatenate([np.stack([f[:, 0], a, c], 1), np.stack([f[:, 1], b, a], 1),
+                            np.stack([f[:, 2], c, b], 1), np.stack([a, b, c], 1)])
+    pos = (v * radius).T.astype(np.float32)
+    nrm = v.T.astype(np.float32)
+    return pos, nrm, f.astype(np.int32)
+
+
+def split_mesh_u16(pos, nrm, faces, max_verts=32768):
+    """split an indexed mesh into hunks addressable with uint16 indices (re-indexed per hunk)"""
+    hunks = []
+    nf = len(faces)
+    start = 0
+    per = max(1, nf // max(1, int(np.ceil(pos.shape[1] * 1.3 / max_verts))))
+    while start < nf:
+        sub = faces[start:start + per]
+        used, inv = np.unique(sub.ravel(), return_inverse=True)
+        while len(used) > max_verts:
+            per = per // 2
+            sub = faces[start:start + per]
+            used, inv = np.unique(sub.ravel(), return_inverse=True)
+        hunks.append((pos[:, used].copy(), nrm[:, used].copy(), inv.astype(np.uint16)))
+        start += len(sub)
+    return hunks
+
+
+def hash_texture(dim: int, seed: int, tex_id: int = 0) -> np.ndarray:
+    """(dim, dim, 4) float32 in [0,1): cheap integer hash of (seed, id, x, y, channel)"""
+    y, x = np.meshgrid(np.arange(dim, dtype=np.uint64), np.arange(dim, dtype=np.uint64), indexing="ij")
+    out = np.empty((dim, dim, 4), np.float32)
+    for ch in range(4):
+        h = (x * np.uint64(73856093)) ^ (y * np.uint64(19349663)) ^ np.uint64((seed * 83492791 + tex_id * 2654435761 + ch * 97) & 0xFFFFFFFF)
+        h = (h ^ (h >> np.uint64(13))) * np.uint64(0x5bd1e995) & np.uint64(0xFFFFFFFF)
+        h = h ^ (h >> np.uint64(15))
+        out[..., ch] = (h & np.uint64(0xFFFFFF)).astype(np.float32) / np.float32(1 << 24)
+    return out
+
+
+def make_mipmap(base: np.ndarray) -> np.ndarray:
+    """stacked mip chain as the reference builds it (rglr_texture.cxx:33-81): (2*dim, dim, 4).
+    2x2 box: ((a + b) + c) + d, then / 4 -- in float32, same order."""
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    dim = base.shape[0]
+    out = np.zeros((2 * dim, dim, 4), np.float32)
+    out[:dim] = base
+    src, row, size = base, dim, dim
+    while size > 1:
+        s = ((src[0::2, 0::2] + src[0::2, 1::2]) + src[1::2, 0::2]) + src[1::2, 1::2]
+        s = (s / np.float32(4.0)).astype(np.float32)
+        size //= 2
+        out[row:row + size, :size] = s
+        src = s
+        row += size
+    return out
+
+
+# ---- scenes -------------------------------------------------------------------------------------
+
+def begin(gl, size, clear=(0.2, 0.3, 0.4), tile_blocks=(8, 8)):
+    """what node/gpu.cxx:126-137 does at the start of every frame"""
+    gl.Reset(size, tile_blocks)
+    gl.ClearColor(clear)
+    gl.ClearDepth(1.0)
+    gl.Clear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT)
+
+
+def finish(gl, out, gamma=True, depth=None, program=PROGRAM_DEFAULT_POST):
+    """node/truecolor.cxx:90-108"""
+    gl.UseProgram(program)
+    if depth is not None:
+        gl.StoreDepth(depth)
+    gl.StoreColor(out, gamma)
+
+
+class WavyGridScene:
+    """textured, depth-tested wavy grid (program Amy, bilinear or nearest)"""
+
+    def __init__(self, n=40, tex_dim=256, seed=1, wave=0.5, bilinear=True):
+        pos, nrm, uv, idx = grid_mesh(n, n, 8.0, 5.0, wave)
+        self.pos, self.nrm, self.uv, self.idx = soa(pos), soa(nrm), soa(uv), idx
+        self.tex = make_mipmap(hash_texture(tex_dim, seed))
+        self.tex_dim = tex_dim
+        self.filter = GL_LINEAR_MIPMAP_NEAREST if bilinear else GL_NEAREST_MIPMAP_NEAREST
+        self.triangles = len(idx) // 3
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, cull=None):
+        w, h = size
+        begin(gl, size, tile_blocks=tile_blocks)
+        gl.UseProgram(PROGRAM_AMY)
+        gl.ViewMatrix(translate(0, 0, -6) @ rotate(0.3 + t, 0.2, 1.0, 0.1))
+        gl.ProjectionMatrix(perspective(45.0, w / h, 1.0, 100.0) if proj is None else proj)
+        if cull is not None:
+            gl.Enable(GL_CULL_FACE)
+            gl.CullFace(cull)
+        gl.UseBuffer(0, self.pos)
+        gl.UseBuffer(3, self.nrm)
+        gl.UseBuffer(9, self.uv)
+        gl.BindTexture(0, self.tex, self.tex_dim, self.tex_dim, self.tex_dim, self.filter)
+        gl.DrawElements(len(self.idx), self.idx, 0)
+        finish(gl, out, True, depth)
+
+
+class CubesScene:
+    """instanced cubes (program Many) + lit cubes (program OBJ2), fixed seed"""
+
+    def __init__(self, instances=300, seed=1):
+        pos, nrm, uv, idx = cube_mesh(1.0)
+        self.pos, self.nrm, self.uv, self.idx = soa(pos), soa(nrm), soa(uv), idx
+        rng = np.random.default_rng(seed)
+        self.kd = soa(rng.random((3, pos.shape[1])).astype(np.float32))
+        mats = []
+        for i in range(instances):
+            p = rng.uniform(-12, 12, 3)
+            p[2] = rng.uniform(-30, -6)
+            m = translate(*p) @ rotate(rng.uniform(0, 6.28), *rng.uniform(-1, 1, 3)) @ scale(rng.uniform(0.3, 1.5))
+            mats.append(m.T.reshape(16))   # column-major, as rmlm::mat4::ff
+        self.mats = aligned_f32(instances * 16)
+        self.mats[:instances * 16] = np.concatenate(mats)
+        self.instances = instances
+        self.triangles = (len(idx) // 3) * instances + (len(idx) // 3) * 8
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None):
+        w, h = size
+        begin(gl, size, clear=(0.05, 0.05, 0.08), tile_blocks=tile_blocks)
+        proj = perspective(60.0, w / h, 1.0, 200.0) if proj is None else proj
+        gl.Enable(GL_CULL_FACE)
+        gl.CullFace(GL_BACK)
+        gl.UseProgram(PROGRAM_MANY)
+        gl.UseUniforms(np.array([0.25], np.float32))
+        gl.ViewMatrix(rotate(0.1 * t, 0, 1, 0))
+        gl.ProjectionMatrix(proj)
+        gl.UseBuffer(0, self.pos)
+        gl.UseBuffer(3, self.nrm)
+        gl.UseBuffer(9, self.uv)
+        gl.UseBuffer(15, self.mats)
+        gl.DrawElementsInstanced(len(self.idx), self.idx, self.instances)
+        gl.UseProgram(PROGRAM_OBJ2)
+        gl.UseBuffer(6, self.kd)
+        for k in range(8):
+            ang = 0.7 * k + t
+            gl.ViewMatrix(translate(4 * np.cos(ang), 3 * np.sin(ang), -9 - k) @ rotate(ang, 1, 1, 0) @ scale(2.0))
+            gl.DrawElements(len(self.idx), self.idx, 0)
+        finish(gl, out, True, depth)
