@@ -1,0 +1,288 @@
+#!/usr/bin/env python3
+"""bench.py -- frames/s of the frame-rendering hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c4|c3] [--impl reference]
+
+A step is one frame of the workload.  Default workload = BASELINE.json configs[1]: the bundled-
+scene-shaped frame sequence at 1920x1080 (`rsr_b200.scenes.BundledLikeScene`, synthetic, seeded).
+One JSON line is printed by rank 0:
+  value  frames/s with every input resident in HBM (device timed, CUDA events, L2 flushed
+         between iterations), aggregate over ranks (each rank renders its own frames: weak scaling)
+  e2e    frames/s through the public API with HOST buffers: per frame the host rebuilds and
+         uploads the instance matrices + state and reads the 1080p frame back
+  roofline / cpu_baseline / clocks / gpu_launches as the contract asks
+`--impl reference` times the reference's own CPU renderer (oracle/_ref) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames_per_sec_1080p"
+SIZE = (1920, 1080)
+
+
+def make_scene(name):
+    from rsr_b200 import scenes
+    if name == "c2":
+        return scenes.BundledLikeScene(), SIZE, "c2_bundled_like_1920x1080"
+    if name == "c4":
+        return scenes.FillStressScene(), SIZE, "c4_fill_stress_8layers_1920x1080_subframe"
+    if name == "c3":
+        return scenes.GeometryStressScene(), SIZE, "c3_geometry_stress_1920x1080_subframe"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = f"/tmp/rsr_clocks_{os.getpid()}.csv"
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def time_reference(scene, size, steps, warmup, threads=None, budget_s=25.0):
+    """the reference's multithreaded CPU renderer on this box's cores, method of perf.cxx:216-235:
+    priming frames, N timed frames, discard the worst 5 %, report the mean of the rest"""
+    from oracle import refgl
+    threads = refgl.init(threads or os.cpu_count())
+    g = refgl.RefGPU(double_buffer=True)   # the reference's default: bin of frame N overlaps draw of N-1
+    out = np.zeros((size[1], size[0]), np.uint32)
+    refgl.lib().ref_work_start()
+    times = []
+    t_begin = time.perf_counter()
+    n = 0
+    try:
+        for i in range(warmup + steps):
+            scene.record(g, size, out, t=i / 60.0)
+            t0 = time.perf_counter()
+            g.Run(manage_workers=False)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+                n += 1
+            if time.perf_counter() - t_begin > budget_s and n >= 3:
+                break
+    finally:
+        refgl.lib().ref_work_end()
+        g.close()
+    times.sort()
+    keep = times[:max(1, int(len(times) * 0.95))]
+    ms = 1e3 * sum(keep) / len(keep)
+    return {"ms_per_frame": ms, "fps": 1e3 / ms, "frames": len(times), "threads": threads}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    scene, size, workload = make_scene(args.workload)
+    W, H = size
+    config = {"workload": workload, "triangles_per_frame": scene.triangles, "draws_per_frame": getattr(scene, "draws", None),
+              "width": W, "height": H, "cache": "L2 flushed (256 MiB memset) before every timed frame"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = time_reference(scene, size, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": r["frames"], "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic", "config": config,
+                "mtris_per_s": scene.triangles * r["fps"] / 1e6,
+                "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
+                                 "sample": f"{r['frames']} frames of the same workload, doubleBuffer=true, worst 5% dropped"},
+                "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import rsr_b200
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    gpu = rsr_b200.GPU(local_rank)
+    gpu.set_profiling(True)
+    stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: everything static, result stays on the device -----------------
+    def frame_resident(i):
+        scene.record(gpu, size, None, t=0.0, static=True)
+        gpu.Run(sync=False)
+
+    for i in range(args.warmup):
+        frame_resident(i)
+        gpu.Sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tile_ms, stage_acc = [], {}
+    stats = None
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(i & 0xff)
+            ev[i][0].record(stream)
+        frame_resident(i)
+        with torch.cuda.stream(stream):
+            ev[i][1].record(stream)
+        gpu.Sync()
+        st = gpu.stage_ms()
+        tile_ms.append(st["tile"])
+        for k, v in st.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        stats = gpu.stats()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    ms_per_step = dev_ms_max / args.steps
+    value = world * args.steps / (dev_ms_max / 1e3)
+
+    # ---- end-to-end leg: host buffers in, host frame out --------------------------------------
+    host_out = torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    for i in range(2):
+        scene.record(gpu, size, host_out, t=i / 60.0)
+        gpu.Run()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        scene.record(gpu, size, host_out, t=i / 60.0)
+        gpu.Run()          # end_frame + sync: uploads, kernels, read-back
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_fps = world * args.steps / float(t.item())
+    h2d = int(scene.groups * scene.cubes * 64 + 4096) if hasattr(scene, "groups") else 4096
+    d2h = W * H * 4
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (tile_kernel) -----------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    tile_avg_ms = sum(tile_ms) / len(tile_ms)
+    tex_texels = getattr(scene, "unique_texels", lambda s: 0)(stats)
+    vertex_bytes = getattr(scene, "vertex_record_bytes", 0)
+    algo_bytes = 4 * W * H + 4 * stats["bin_entries"] + vertex_bytes + 16 * tex_texels
+    achieved = algo_bytes / (tile_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_ms": tile_avg_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                "stage_ms": {k: v / args.steps for k, v in stage_acc.items()}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            r = time_reference(scene, size, 30, 3, budget_s=20.0)
+            cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
+                   "sample": f"{r['frames']} frames of the same workload on the host cores, doubleBuffer=true, worst 5% dropped"}
+        except Exception as exc:  # oracle not shipped: say so, never fake
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {exc}"}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i32", "data": "synthetic", "config": config,
+            "mtris_per_s": scene.triangles * value / 1e6,
+            "gpix_per_s": stats["fragments_shaded"] * value / 1e9,
+            "fragments_per_frame": stats["fragments_shaded"], "bin_entries_per_frame": stats["bin_entries"],
+            "clocks": clocks,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "timing": "wall clock around record+upload+kernels+readback+sync, max over ranks"},
+            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -67,13 +67,13 @@ struct BinSeg {
 	uint32_t start;
 	uint32_t len; };
 
-enum FrameCmdType : int { kCmdClear = 1, kCmdDraw = 2, kCmdStoreTC = 3, kCmdStoreFP = 4, kCmdStoreDepth = 5, kCmdStoreHalfFP = 6 };
+enum FrameCmdType : int { kCmdClear = 1, kCmdStoreTC = 3, kCmdStoreFP = 4, kCmdStoreDepth = 5, kCmdStoreHalfFP = 6 };
 
-struct FrameCmd {
+struct FrameCmd {       // non-draw commands only; draws are found through the tile lists
 	int type;
 	int state;      // state in effect
-	int arg;        // clear bits / draw index / gamma flag
-	int pad;
+	int arg;        // clear bits / gamma flag
+	int beforeDraw; // number of draws recorded before this command
 	void* dst;      // device destination for stores
 	int dstStride;  // in pixels
 	int pad2; };

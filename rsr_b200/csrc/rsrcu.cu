@@ -129,7 +129,9 @@ struct rsrcu_ctx {
 	std::vector<PendingCopy> copies;
 	uint64_t trianglesSubmitted{0};
 
-	UploadArena arena;
+	UploadArena arenas[2];            // double-buffered: frame N+1 records while frame N's upload is in flight
+	cudaEvent_t arenaFree[2]{};
+	int cur{0};
 	std::unordered_map<const void*, StaticAlloc> staticCache;
 
 	// device work buffers
@@ -236,7 +238,7 @@ void mat4Transpose(const float* m, float* out) {
 
 const void* resolve(const rsrcu_ctx* c, const DevRef& r) {
 	if (r.null) { return nullptr; }
-	if (r.arena) { return static_cast<const uint8_t*>(c->arena.dev.ptr) + r.off; }
+	if (r.arena) { return static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr) + r.off; }
 	return r.abs; }
 
 int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef& out) {
@@ -254,7 +256,7 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 		out.null = false; out.arena = false; out.abs = d;
 		return RSRCU_OK; }
 	size_t off = 0;
-	CU(c->arena.push(host, bytes, off));
+	CU(c->arenas[c->cur].push(host, bytes, off));
 	out.null = false; out.arena = true; out.off = off;
 	return RSRCU_OK; }
 
@@ -289,6 +291,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	c->device = device;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (auto& ev : c->evStage) { CU(cudaEventCreate(&ev)); }
+	for (auto& ev : c->arenaFree) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	rsr::harvest_luts(c->hostLuts.rcp, c->hostLuts.rsqrt);
 	static std::once_flag once;
 	static uint64_t mismatches = 0;
@@ -312,7 +315,8 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->clipRecs, &c->segActive, &c->counts, &c->gsum, &c->tileBase,
 	                   &c->tileCount, &c->lists, &c->counters, &c->tcOut, &c->fpOut, &c->depthOut }) { b->release(); }
-	c->arena.release();
+	c->arenas[0].release(); c->arenas[1].release();
+	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
 	if (c->hostCounters) { cudaFreeHost(c->hostCounters); }
 	for (auto& ev : c->evStage) { cudaEventDestroy(ev); }
@@ -344,7 +348,9 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 		            "(rglv_view_frustum.hxx:36-39); render larger images as sub-frames", width, height); }
 	if (tileWBlocks <= 0 || tileHBlocks <= 0) { return fail(RSRCU_ERR_INVALID, "tile blocks must be positive"); }
 	CU(cudaSetDevice(c->device));
-	if (c->framePending) { int r = rsrcu_sync(c); if (r != RSRCU_OK) { return r; } }
+	// take the other staging arena; wait only until the frame that last used it has been uploaded
+	c->cur ^= 1;
+	CU(cudaEventSynchronize(c->arenaFree[c->cur]));
 	c->width = width; c->height = height;
 	const int rw = tileWBlocks * 8, rh = tileHBlocks * 8;
 	// the device tile must lie inside one reference tile to reproduce its start point exactly;
@@ -352,7 +358,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->refTileW = (rw % kTile == 0) ? rw : kTile;
 	c->refTileH = (rh % kTile == 0) ? rh : kTile;
 	c->states.clear(); c->draws.clear(); c->cmds.clear(); c->cmdDstKind.clear(); c->copies.clear();
-	c->arena.used = 0;
+	c->arenas[c->cur].used = 0;
 	c->trianglesSubmitted = 0;
 	c->haveState = false; c->stateDirty = true;
 	for (auto& b : c->curBuffers) { b = DevRef{}; }
@@ -409,6 +415,7 @@ static int pushCmd(rsrcu_ctx* c, int type, int arg, void* dst, int stride, int k
 	if (r != RSRCU_OK) { return r; }
 	FrameCmd cmd{};
 	cmd.type = type; cmd.state = static_cast<int>(c->states.size()) - 1; cmd.arg = arg; cmd.dst = dst; cmd.dstStride = stride;
+	cmd.beforeDraw = static_cast<int>(c->draws.size());
 	c->cmds.push_back(cmd);
 	c->cmdDstKind.push_back(kind);
 	return RSRCU_OK; }
@@ -471,10 +478,6 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 		if (r != RSRCU_OK) { return r; } }
 	c->trianglesSubmitted += d.N;
 	c->draws.push_back(hd);
-	FrameCmd cmd{};
-	cmd.type = kCmdDraw; cmd.state = d.state; cmd.arg = static_cast<int>(c->draws.size()) - 1;
-	c->cmds.push_back(cmd);
-	c->cmdDstKind.push_back(0);
 	return RSRCU_OK; }
 
 int rsrcu_draw_elements(rsrcu_ctx* c, int count, const uint16_t* indices, int hint, int instanceCount, int upload) {
@@ -579,12 +582,12 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 
 	// ---- frame tables into the arena (state / draw tables need final device addresses) -----
 	size_t offStates = 0, offDraws = 0, offCmds = 0, offSegs = 0, offChunks = 0;
-	CU(c->arena.push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
-	CU(c->arena.push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
-	CU(c->arena.push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
-	CU(c->arena.push(nullptr, sizeof(BinSeg) * std::max<size_t>(1, segs.size()), offSegs));
-	CU(c->arena.push(nullptr, sizeof(uint32_t) * chunkSegBegin.size(), offChunks));
-	CU(c->arena.dev.reserve(c->arena.used));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(BinSeg) * std::max<size_t>(1, segs.size()), offSegs));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(uint32_t) * chunkSegBegin.size(), offChunks));
+	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
 
 	for (size_t i = 0; i < c->states.size(); ++i) {
 		const HostState& hs = c->states[i];
@@ -633,14 +636,14 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 			tu.kind = !isPow2 ? 0 : (ht.filter ? 2 : 1); }
 		ds.tu3 = static_cast<const float*>(resolve(c, hs.tu3));
 		ds.tu3dim = hs.tu3dim;
-		std::memcpy(c->arena.host + offStates + i * sizeof(DevState), &ds, sizeof(ds)); }
+		std::memcpy(c->arenas[c->cur].host + offStates + i * sizeof(DevState), &ds, sizeof(ds)); }
 	for (size_t i = 0; i < c->draws.size(); ++i) {
 		DevDraw d = c->draws[i].d;
 		d.indices = static_cast<const uint16_t*>(resolve(c, c->draws[i].indices));
-		std::memcpy(c->arena.host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
-	if (!c->cmds.empty()) { std::memcpy(c->arena.host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
-	if (!segs.empty()) { std::memcpy(c->arena.host + offSegs, segs.data(), sizeof(BinSeg) * segs.size()); }
-	std::memcpy(c->arena.host + offChunks, chunkSegBegin.data(), sizeof(uint32_t) * chunkSegBegin.size());
+		std::memcpy(c->arenas[c->cur].host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
+	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
+	if (!segs.empty()) { std::memcpy(c->arenas[c->cur].host + offSegs, segs.data(), sizeof(BinSeg) * segs.size()); }
+	std::memcpy(c->arenas[c->cur].host + offChunks, chunkSegBegin.data(), sizeof(uint32_t) * chunkSegBegin.size());
 
 	// texture units with pow2 dims outside 4..1024 cannot be made by the reference (exit(1))
 	for (const HostDraw& hd : c->draws) {
@@ -669,7 +672,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	CU(c->tileCount.reserve(static_cast<size_t>(ntiles) * 4));
 	CU(c->lists.reserve(static_cast<size_t>(c->listCapacity) * 4));
 
-	const uint8_t* ab = static_cast<const uint8_t*>(c->arena.dev.ptr);
+	const uint8_t* ab = static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr);
 	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
 	const DevDraw* dDraws = reinterpret_cast<const DevDraw*>(ab + offDraws);
 	const FrameCmd* dCmds = reinterpret_cast<const FrameCmd*>(ab + offCmds);
@@ -678,7 +681,8 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	Counters* dCtr = static_cast<Counters*>(c->counters.ptr);
 
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
-	CU(cudaMemcpyAsync(c->arena.dev.ptr, c->arena.host, c->arena.used, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->arenas[c->cur].dev.ptr, c->arenas[c->cur].host, c->arenas[c->cur].used, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->arenaFree[c->cur], st));
 	CU(cudaMemsetAsync(dCtr, 0, sizeof(Counters), st));
 	CU(cudaMemsetAsync(c->segActive.ptr, 0, std::max<size_t>(1, segs.size()) * 4, st));
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[1], st)); }

@@ -364,76 +364,91 @@ tile_kernel(TileArgs A) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { sh.chan[c][l][t] = 0.0f; } }
 
-	for (int ci = 0; ci < A.fp.ncmds; ++ci) {
-		const FrameCmd cmd = A.cmds[ci];
-		const DevState& s = A.states[cmd.state];
-		switch (cmd.type) {
-		case kCmdClear: {
-			// GPU::DrawImpl CMD_CLEAR (rglv_gpu.cxx:311-344)
-			const bool clearColor = (cmd.arg & 1) != 0, clearDepth = (cmd.arg & 2) != 0;
-#pragma unroll
-			for (int l = 0; l < 4; ++l) {
-				if (clearColor) { sh.chan[0][l][t] = s.clearColor[0]; sh.chan[1][l][t] = s.clearColor[1]; sh.chan[2][l][t] = s.clearColor[2]; }
-				if (clearDepth) { sh.chan[3][l][t] = s.clearDepth; } } }
-			break;
-		case kCmdDraw: {
-			const DevDraw& d = A.draws[cmd.arg];
-			// this draw's slice of the (id-sorted) tile list
-			const uint32_t idEnd = d.idBase + d.N * (1u + kMaxFan);
-			uint32_t lo = cursor, hi = listLen;
+	// Frame walk.  A.cmds holds the non-draw commands (clear / stores) in submission order, each
+	// tagged with the number of draws recorded before it; draws are discovered from the tile's own
+	// id-sorted list, so a tile only pays for the draws that actually touch it.
+	int ci = 0;
+	while (true) {
+		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
+		if (cursor < listLen) {
+			const uint32_t id = __ldg(list + cursor);
+			int lo = 0, hi = A.fp.ndraws - 1;
 			while (lo < hi) {
-				const uint32_t mid = (lo + hi) >> 1;
-				if (__ldg(list + mid) < idEnd) { lo = mid + 1; } else { hi = mid; } }
-			const uint32_t n = lo - cursor;
-			if (n > 0) {
-				const uint32_t* seg = list + cursor;
-				switch (s.programId) {
-				case ProgAmy::id:          frags += draw_segment<ProgAmy>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgAlphaTexture::id: frags += draw_segment<ProgAlphaTexture>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgText::id:         frags += draw_segment<ProgText>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgDepth::id:        frags += draw_segment<ProgDepth>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgPattern::id:      frags += draw_segment<ProgPattern>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgMany::id:         frags += draw_segment<ProgMany>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgOBJ1::id:         frags += draw_segment<ProgOBJ1>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgOBJ2::id:         frags += draw_segment<ProgOBJ2>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgOBJ2S::id:        frags += draw_segment<ProgOBJ2S>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgEnvmap::id:       frags += draw_segment<ProgEnvmap>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				case ProgWireframe::id:    frags += draw_segment<ProgWireframe>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-				default: break; }
-				cursor = lo; } }
-			break;
-		case kCmdStoreTC: {
-			// GPUBltImpl::StoreTrueColor -> FilterTile<SHADER, sRGB|LinearColor>
-			if (onScreen) {
-				uint32_t out[4];
+				const int mid = (lo + hi + 1) >> 1;
+				if (A.draws[mid].idBase <= id) { lo = mid; } else { hi = mid - 1; } }
+			di = lo; }
+		// non-draw commands that precede that draw
+		while (ci < A.fp.ncmds && A.cmds[ci].beforeDraw <= di) {
+			const FrameCmd cmd = A.cmds[ci];
+			++ci;
+			const DevState& s = A.states[cmd.state];
+			switch (cmd.type) {
+			case kCmdClear: {
+				// GPU::DrawImpl CMD_CLEAR (rglv_gpu.cxx:311-344)
+				const bool clearColor = (cmd.arg & 1) != 0, clearDepth = (cmd.arg & 2) != 0;
 #pragma unroll
 				for (int l = 0; l < 4; ++l) {
-					float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
-					if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
-						const float ex = s.uniforms[0];
-						r = r * ex; g = g * ex; b = b * ex; }
-					out[l] = (cmd.arg & 1) ? ((srgb8(r) << 16) | (srgb8(g) << 8) | srgb8(b))
-					                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
-				uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
-				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
-				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_uint2(out[2], out[3]); } }
-			break;
-		case kCmdStoreFP: {
-			// Copy(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:247-279): alpha = 0
-			if (onScreen) {
-				float4* dst = static_cast<float4*>(cmd.dst);
+					if (clearColor) { sh.chan[0][l][t] = s.clearColor[0]; sh.chan[1][l][t] = s.clearColor[1]; sh.chan[2][l][t] = s.clearColor[2]; }
+					if (clearDepth) { sh.chan[3][l][t] = s.clearDepth; } } }
+				break;
+			case kCmdStoreTC: {
+				// GPUBltImpl::StoreTrueColor -> FilterTile<SHADER, sRGB|LinearColor>
+				if (onScreen) {
+					uint32_t out[4];
 #pragma unroll
-				for (int l = 0; l < 4; ++l) {
-					dst[static_cast<size_t>(py + (l >> 1)) * cmd.dstStride + px + (l & 1)] =
-						make_float4(sh.chan[0][l][t], sh.chan[1][l][t], sh.chan[2][l][t], 0.0f); } } }
-			break;
-		case kCmdStoreDepth: {
-			if (onScreen) {
-				float* dst = static_cast<float*>(cmd.dst);
-				*reinterpret_cast<float2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_float2(sh.chan[3][0][t], sh.chan[3][1][t]);
-				*reinterpret_cast<float2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_float2(sh.chan[3][2][t], sh.chan[3][3][t]); } }
-			break;
-		default: break; } }
+					for (int l = 0; l < 4; ++l) {
+						float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
+						if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
+							const float ex = s.uniforms[0];
+							r = r * ex; g = g * ex; b = b * ex; }
+						out[l] = (cmd.arg & 1) ? ((srgb8(r) << 16) | (srgb8(g) << 8) | srgb8(b))
+						                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
+					uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
+					*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
+					*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_uint2(out[2], out[3]); } }
+				break;
+			case kCmdStoreFP: {
+				// Copy(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:247-279): alpha = 0
+				if (onScreen) {
+					float4* dst = static_cast<float4*>(cmd.dst);
+#pragma unroll
+					for (int l = 0; l < 4; ++l) {
+						dst[static_cast<size_t>(py + (l >> 1)) * cmd.dstStride + px + (l & 1)] =
+							make_float4(sh.chan[0][l][t], sh.chan[1][l][t], sh.chan[2][l][t], 0.0f); } } }
+				break;
+			case kCmdStoreDepth: {
+				if (onScreen) {
+					float* dst = static_cast<float*>(cmd.dst);
+					*reinterpret_cast<float2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_float2(sh.chan[3][0][t], sh.chan[3][1][t]);
+					*reinterpret_cast<float2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_float2(sh.chan[3][2][t], sh.chan[3][3][t]); } }
+				break;
+			default: break; } }
+		if (di >= A.fp.ndraws) { break; }
+
+		// this draw's slice of the (id-sorted) tile list
+		const DevDraw& d = A.draws[di];
+		const DevState& s = A.states[d.state];
+		const uint32_t idEnd = d.idBase + d.N * (1u + kMaxFan);
+		uint32_t lo = cursor, hi = listLen;
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (__ldg(list + mid) < idEnd) { lo = mid + 1; } else { hi = mid; } }
+		const uint32_t n = lo - cursor;
+		const uint32_t* seg = list + cursor;
+		switch (s.programId) {
+		case ProgAmy::id:          frags += draw_segment<ProgAmy>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgAlphaTexture::id: frags += draw_segment<ProgAlphaTexture>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgText::id:         frags += draw_segment<ProgText>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgDepth::id:        frags += draw_segment<ProgDepth>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgPattern::id:      frags += draw_segment<ProgPattern>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgMany::id:         frags += draw_segment<ProgMany>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgOBJ1::id:         frags += draw_segment<ProgOBJ1>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgOBJ2::id:         frags += draw_segment<ProgOBJ2>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgOBJ2S::id:        frags += draw_segment<ProgOBJ2S>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgEnvmap::id:       frags += draw_segment<ProgEnvmap>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		case ProgWireframe::id:    frags += draw_segment<ProgWireframe>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		default: break; }
+		cursor = max(lo, cursor + 1); }
 
 	// fragment statistics: one atomic per CTA
 	for (int o = 16; o > 0; o >>= 1) { frags += __shfl_down_sync(0xffffffffu, frags, o); }

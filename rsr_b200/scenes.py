@@ -314,3 +314,115 @@ class CubesScene:
             gl.ViewMatrix(translate(4 * np.cos(ang), 3 * np.sin(ang), -9 - k) @ rotate(ang, 1, 1, 0) @ scale(2.0))
             gl.DrawElements(len(self.idx), self.idx, 0)
         finish(gl, out, True, depth)
+
+
+class BundledLikeScene:
+    """C2: the shape of the reference's bundled scenes at once, all synthetic and seeded --
+    a lit OBJ2 mesh (data/scene/colortest.lua: 168-face mesh, program OBJ2), a 24x24 field of
+    bilinear-textured Amy quads with two 512^2 mip-mapped textures, one draw per quad
+    (data/scene/tucker-and-dino.lua), and 3 x 3000 instanced cubes, program Many
+    (data/scene/instanced-cubes.lua; matrices from a fixed seed instead of std::random_device,
+    node/many.cxx:56).  ~110 k triangles, 580 draws."""
+
+    def __init__(self, seed=1, cubes=3000, groups=3, field=24):
+        rng = np.random.default_rng(seed)
+        # lit mesh: icosphere(divs=1) = 80 faces x 2 + a cube = 172 faces
+        p, n, f = icosphere(1, 1.0)
+        self.m_pos, self.m_nrm = soa(p), soa(n)
+        self.m_kd = soa((rng.random((3, p.shape[1])) * 0.09).astype(np.float32))
+        self.m_idx = f.astype(np.uint16).ravel()
+        # textured quads
+        q = np.array([[0, 1, 1, 0], [0, 0, 1, 1], [0, 0, 0, 0]], np.float32)
+        self.q_pos = soa(q)
+        self.q_uv = soa(q[:2])
+        self.q_idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+        self.tex = [make_mipmap(hash_texture(512, seed + 10, i)) for i in range(2)]
+        self.field = field
+        # instanced cubes
+        cp, cn, cuv, cidx = cube_mesh(1.0)
+        self.c_pos, self.c_nrm, self.c_uv, self.c_idx = soa(cp), soa(cn), soa(cuv), cidx
+        self.cubes = cubes
+        self.groups = groups
+        self.base = []
+        for g in range(groups):
+            pos = rng.uniform(-60, 60, (cubes, 3)).astype(np.float32)
+            pos[:, 2] = rng.uniform(-160, -20, cubes)
+            axis = rng.uniform(-1, 1, (cubes, 3))
+            ang = rng.uniform(0, 6.28, cubes)
+            sc = rng.uniform(0.4, 1.6, cubes)
+            self.base.append((pos, axis, ang, sc))
+        self.mats = [aligned_f32(cubes * 16) for _ in range(groups)]
+        self.triangles = (len(self.m_idx) // 3) * 2 + field * field * 2 + groups * cubes * (len(cidx) // 3)
+        self.draws = 2 + field * field + groups
+        self._update_instances(0.0)
+
+    def _update_instances(self, t):
+        """per-frame CPU work of the $many node (node/many.cxx:188-226): rebuild instance matrices"""
+        for g in range(self.groups):
+            pos, axis, ang, sc = self.base[g]
+            a = ang + t * (0.5 + 0.1 * g)
+            ax = axis / np.linalg.norm(axis, axis=1, keepdims=True)
+            c, s = np.cos(a), np.sin(a)
+            x, y, z = ax[:, 0], ax[:, 1], ax[:, 2]
+            tt = 1 - c
+            m = np.zeros((self.cubes, 4, 4), np.float32)
+            m[:, 0, 0] = tt * x * x + c; m[:, 0, 1] = tt * x * y - s * z; m[:, 0, 2] = tt * x * z + s * y
+            m[:, 1, 0] = tt * x * y + s * z; m[:, 1, 1] = tt * y * y + c; m[:, 1, 2] = tt * y * z - s * x
+            m[:, 2, 0] = tt * x * z - s * y; m[:, 2, 1] = tt * y * z + s * x; m[:, 2, 2] = tt * z * z + c
+            m[:, :3, :3] *= sc[:, None, None]
+            m[:, :3, 3] = pos
+            m[:, 3, 3] = 1.0
+            self.mats[g][:self.cubes * 16] = m.transpose(0, 2, 1).reshape(-1)   # column-major
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True):
+        """static=True marks every buffer immutable (device-resident bench leg); otherwise the
+        instance matrices are rebuilt and re-uploaded each frame like the reference's $many node"""
+        w, h = size
+        up = {"upload": 1} if hasattr(gl, "stats") else {}
+        dyn = up if static else {}
+        if not static:
+            self._update_instances(t)
+        begin(gl, size, clear=(0.222, 0.222, 0.333), tile_blocks=tile_blocks)
+        proj = perspective(45.0, w / h, 1.0, 400.0) if proj is None else proj
+        gl.ProjectionMatrix(proj)
+
+        # instanced cubes
+        gl.Enable(GL_CULL_FACE)
+        gl.CullFace(GL_BACK)
+        gl.UseProgram(PROGRAM_MANY)
+        gl.UseUniforms(np.array([0.5], np.float32))
+        gl.ViewMatrix(rotate(0.05 * t, 0, 1, 0))
+        gl.UseBuffer(0, self.c_pos, **up)
+        gl.UseBuffer(3, self.c_nrm, **up)
+        gl.UseBuffer(9, self.c_uv, **up)
+        for g in range(self.groups):
+            gl.UseBuffer(15, self.mats[g], **dyn)
+            gl.DrawElementsInstanced(len(self.c_idx), self.c_idx, self.cubes, **up)
+
+        # lit meshes
+        gl.UseProgram(PROGRAM_OBJ2)
+        gl.UseBuffer(0, self.m_pos, **up)
+        gl.UseBuffer(3, self.m_nrm, **up)
+        gl.UseBuffer(6, self.m_kd, **up)
+        gl.UseBuffer(9, None)
+        gl.UseBuffer(10, None)
+        for k in range(2):
+            gl.ViewMatrix(translate(-3.0 + 6.0 * k, 1.5 * np.sin(t + k), -9.0) @ rotate(0.7 * t + k, 0.3, 1.0, 0.2) @ scale(1.6))
+            gl.DrawElements(len(self.m_idx), self.m_idx, 0, **up)
+
+        # textured quad field, orthographic-like placement in front of the camera
+        gl.Disable(GL_CULL_FACE)
+        gl.UseProgram(PROGRAM_AMY)
+        gl.UseBuffer(0, self.q_pos, **up)
+        gl.UseBuffer(3, None); gl.UseBuffer(4, None); gl.UseBuffer(5, None)
+        gl.UseBuffer(6, None); gl.UseBuffer(7, None); gl.UseBuffer(8, None)
+        gl.UseBuffer(9, self.q_uv, **up)
+        n = self.field
+        ox, oy = np.sin(t) * 0.5, np.cos(t) * 0.5
+        for j in range(n):
+            for i in range(n):
+                k = (i + j) & 1
+                gl.BindTexture(0, self.tex[k], 512, 512, 512, GL_LINEAR_MIPMAP_NEAREST, **up)
+                gl.ViewMatrix(translate((i - n / 2) * 1.0 + ox, (j - n / 2) * 0.55 + oy - 1.0, -30.0 - 0.01 * (i + j)) @ scale(0.9, 0.5, 1.0))
+                gl.DrawElements(6, self.q_idx, 0, **up)
+        finish(gl, out, gamma, depth)
