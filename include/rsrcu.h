@@ -162,6 +162,40 @@ int rsrcu_end_frame(rsrcu_ctx* ctx);
 /* Waits for the frame; reports device-side errors (clip buffer overflow...) */
 int rsrcu_sync(rsrcu_ctx* ctx);
 
+/* ---- packed command stream ---------------------------------------------------------------------
+ * The reference hands `GPU::RunImpl` one byte-packed command stream per frame
+ * (`FastPackedStream`, src/rgl/rglv/rglv_packed_stream.hxx:14-131; opcodes rglv_gpu_protocol.hxx:7-53).
+ * rsrcu_run_stream is the same idea for this ABI: one call decodes a whole recorded frame
+ * (begin_frame ... end_frame) without per-command FFI overhead.  Records are 8-byte aligned:
+ *   uint32 opcode, uint32 record_bytes (header included), payload
+ * payloads (all fields little-endian, pointers as uint64 host addresses, borrowed for the call):
+ *   RSRCU_OP_BEGIN_FRAME   int32 width, height, tile_w_blocks, tile_h_blocks
+ *   RSRCU_OP_STATE         RsrState
+ *   RSRCU_OP_BIND_BUFFER   int32 slot, upload; uint64 ptr; uint64 n_floats
+ *   RSRCU_OP_BIND_TEXTURE  int32 unit, width, height, stride, filter, rows_in_memory, upload, pad; uint64 ptr
+ *   RSRCU_OP_BIND_DEPTH    int32 dim, upload; uint64 ptr
+ *   RSRCU_OP_CLEAR         int32 bits, pad
+ *   RSRCU_OP_DRAW_ELEMENTS int32 count, hint, instance_count, upload; uint64 ptr
+ *   RSRCU_OP_DRAW_ARRAYS   int32 count, instance_count
+ *   RSRCU_OP_STORE_TC      int32 gamma, width, height, stride_px; uint64 ptr
+ *   RSRCU_OP_STORE_FP      int32 half, width, height, stride_px; uint64 ptr
+ *   RSRCU_OP_STORE_DEPTH   uint64 ptr
+ *   RSRCU_OP_END_FRAME     (no payload)
+ */
+#define RSRCU_OP_BEGIN_FRAME 1
+#define RSRCU_OP_STATE 2
+#define RSRCU_OP_BIND_BUFFER 3
+#define RSRCU_OP_BIND_TEXTURE 4
+#define RSRCU_OP_BIND_DEPTH 5
+#define RSRCU_OP_CLEAR 6
+#define RSRCU_OP_DRAW_ELEMENTS 7
+#define RSRCU_OP_DRAW_ARRAYS 8
+#define RSRCU_OP_STORE_TC 9
+#define RSRCU_OP_STORE_FP 10
+#define RSRCU_OP_STORE_DEPTH 11
+#define RSRCU_OP_END_FRAME 12
+int rsrcu_run_stream(rsrcu_ctx* ctx, const void* stream, size_t bytes);
+
 /* ---- device-side access (viewer presents from the device-resolved buffer; bench; sharding) --- */
 
 /* device pointer + pitch (pixels) of the last true-colour store of the current/last frame */

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import struct
 
 import numpy as np
 
@@ -113,6 +114,7 @@ def load_library():
         "rsrcu_store_depth": [vp, vp],
         "rsrcu_end_frame": [vp],
         "rsrcu_sync": [vp],
+        "rsrcu_run_stream": [vp, vp, sz],
         "rsrcu_device_truecolor": [vp, C.POINTER(vp), C.POINTER(ci)],
         "rsrcu_stream": [vp, C.POINTER(vp)],
         "rsrcu_get_stats": [vp, C.POINTER(RsrStats)],
@@ -134,6 +136,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
     "rsrcu_store_color_tc", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
 
@@ -142,20 +145,46 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+(OP_BEGIN_FRAME, OP_STATE, OP_BIND_BUFFER, OP_BIND_TEXTURE, OP_BIND_DEPTH, OP_CLEAR, OP_DRAW_ELEMENTS,
+ OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME) = range(1, 13)
+
+
+def _addr(a) -> int:
+    return 0 if a is None else a.ctypes.data
+
+
+class RecordedFrame:
+    """One frame as a packed command stream (include/rsrcu.h "packed command stream") plus the
+    numpy arrays its pointers refer to.  Replayable with GPU.Submit()."""
+
+    def __init__(self, data: bytes, keep: list, size):
+        self.data = data
+        self.buf = (C.c_char * len(data)).from_buffer_copy(data)
+        self.keep = keep
+        self.size = size
+
+
 class GPU:
     """`rglv::GPU` + its recording `rglv::GL` context, rendered by the CUDA library.
 
     Usage follows the reference (node/gpu.cxx:107-161, node/truecolor.cxx:90-108):
     Reset(size, tileBlocks); state + draw calls; StoreColor(...); Run().
+
+    Like the reference, GL calls are *recorded* (into the packed stream of include/rsrcu.h) and the
+    whole frame is handed to the renderer by Run() -> rsrcu_run_stream.  With direct=True every GL
+    call goes through its own C-ABI entry point instead (same result; used by the tests to cover
+    both routes).
     """
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, direct: bool = False):
         self.L = load_library()
         h = C.c_void_p()
         self._check(self.L.rsrcu_create(int(device), C.byref(h)))
         self.h = h
         self.device = device
+        self.direct = direct
         self._keep = []
+        self._rec = bytearray()
         self._state = RsrState()
         self._reset_state()
         self._dirty = True
@@ -195,24 +224,52 @@ class GPU:
         s.projection_matrix[:] = ident
         s.normal_matrix[:] = ident
 
+    def _emit(self, op: int, payload: bytes):
+        pad = (-len(payload)) % 8
+        self._rec += struct.pack("<II", op, 8 + len(payload) + pad) + payload + b"\0" * pad
+
     def _flush_state(self):
         if self._dirty:
-            self._check(self.L.rsrcu_set_state(self.h, C.byref(self._state)))
+            if self.direct:
+                self._check(self.L.rsrcu_set_state(self.h, C.byref(self._state)))
+            else:
+                self._emit(OP_STATE, bytes(self._state))
             self._dirty = False
 
     # -- rglv::GPU ------------------------------------------------------------------------------
     def Reset(self, size, tile_blocks=(8, 8)):
         self._keep = []
+        self._rec = bytearray()
         self.size = (int(size[0]), int(size[1]))
-        self._check(self.L.rsrcu_begin_frame(self.h, self.size[0], self.size[1], int(tile_blocks[0]), int(tile_blocks[1])))
+        if self.direct:
+            self._check(self.L.rsrcu_begin_frame(self.h, self.size[0], self.size[1], int(tile_blocks[0]), int(tile_blocks[1])))
+        else:
+            self._emit(OP_BEGIN_FRAME, struct.pack("<iiii", self.size[0], self.size[1], int(tile_blocks[0]), int(tile_blocks[1])))
         self._reset_state()
         self._dirty = True
 
-    def Run(self, manage_workers: bool = True, sync: bool = True):
-        """GPU::Run: end of recording -> kernels; `sync` waits and fills the store destinations"""
-        self._check(self.L.rsrcu_end_frame(self.h))
+    def Finish(self) -> RecordedFrame:
+        """closes the recording and returns it (stream mode only)"""
+        assert not self.direct
+        self._emit(OP_END_FRAME, b"")
+        rec = RecordedFrame(bytes(self._rec), self._keep, self.size)
+        self._rec = bytearray()
+        return rec
+
+    def Submit(self, rec: RecordedFrame, sync: bool = True):
+        """GPU::Run on a recorded frame: one C-ABI call (rsrcu_run_stream)"""
+        self._check(self.L.rsrcu_run_stream(self.h, rec.buf, len(rec.data)))
         if sync:
             self.Sync()
+
+    def Run(self, manage_workers: bool = True, sync: bool = True):
+        """GPU::Run: end of recording -> kernels; `sync` waits and fills the store destinations"""
+        if self.direct:
+            self._check(self.L.rsrcu_end_frame(self.h))
+            if sync:
+                self.Sync()
+        else:
+            self.Submit(self.Finish(), sync)
 
     def Sync(self):
         self._check(self.L.rsrcu_sync(self.h))
@@ -263,17 +320,19 @@ class GPU:
     def NormalMatrix(self, m): self._state.normal_matrix[:] = self._mat(m); self._dirty = True
 
     def UseBuffer(self, slot, arr, upload=UPLOAD_ALWAYS):
-        if arr is None:
-            self._check(self.L.rsrcu_bind_buffer(self.h, slot, None, 0, upload))
-            return
-        a = np.asarray(arr)
-        if a.ndim == 2:
-            for i in range(a.shape[0]):
-                self.UseBuffer(slot + i, a[i], upload)
-            return
-        a = np.ascontiguousarray(a, dtype=np.float32)
-        self._keep.append(a)
-        self._check(self.L.rsrcu_bind_buffer(self.h, slot, _ptr(a), a.size, upload))
+        if arr is not None:
+            a = np.asarray(arr)
+            if a.ndim == 2:
+                for i in range(a.shape[0]):
+                    self.UseBuffer(slot + i, a[i], upload)
+                return
+            arr = np.ascontiguousarray(a, dtype=np.float32)
+            self._keep.append(arr)
+        n = 0 if arr is None else arr.size
+        if self.direct:
+            self._check(self.L.rsrcu_bind_buffer(self.h, slot, _ptr(arr), n, upload))
+        else:
+            self._emit(OP_BIND_BUFFER, struct.pack("<iiQQ", slot, upload, _addr(arr), n))
 
     def UseUniforms(self, data):
         b = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
@@ -288,58 +347,80 @@ class GPU:
         t = np.ascontiguousarray(texels, dtype=np.float32)
         rows = t.size // (4 * stride)
         self._keep.append(t)
-        self._check(self.L.rsrcu_bind_texture(self.h, unit, _ptr(t), width, height, stride, mode, rows, upload))
+        if self.direct:
+            self._check(self.L.rsrcu_bind_texture(self.h, unit, _ptr(t), width, height, stride, mode, rows, upload))
+        else:
+            self._emit(OP_BIND_TEXTURE, struct.pack("<iiiiiiiiQ", unit, width, height, stride, mode, rows, upload, 0, _addr(t)))
 
     def BindTexture3(self, depth, dim, upload=UPLOAD_ALWAYS):
         t = np.ascontiguousarray(depth, dtype=np.float32)
         self._keep.append(t)
-        self._check(self.L.rsrcu_bind_depth_texture(self.h, _ptr(t), dim, upload))
+        if self.direct:
+            self._check(self.L.rsrcu_bind_depth_texture(self.h, _ptr(t), dim, upload))
+        else:
+            self._emit(OP_BIND_DEPTH, struct.pack("<iiQ", dim, upload, _addr(t)))
 
     def Clear(self, bits):
         self._flush_state()
-        self._check(self.L.rsrcu_clear(self.h, bits))
+        if self.direct:
+            self._check(self.L.rsrcu_clear(self.h, bits))
+        else:
+            self._emit(OP_CLEAR, struct.pack("<ii", bits, 0))
 
-    def DrawElements(self, count, indices, hint=0, upload=UPLOAD_ALWAYS):
+    def _draw_elements(self, count, indices, hint, instances, upload):
         idx = np.ascontiguousarray(indices, dtype=np.uint16)
         self._keep.append(idx)
         self._flush_state()
-        self._check(self.L.rsrcu_draw_elements(self.h, int(count), _ptr(idx), int(hint), 0, upload))
+        if self.direct:
+            self._check(self.L.rsrcu_draw_elements(self.h, int(count), _ptr(idx), int(hint), int(instances), upload))
+        else:
+            self._emit(OP_DRAW_ELEMENTS, struct.pack("<iiiiQ", int(count), int(hint), int(instances), upload, _addr(idx)))
 
-    def DrawArrays(self, count):
+    def _draw_arrays(self, count, instances):
         self._flush_state()
-        self._check(self.L.rsrcu_draw_arrays(self.h, int(count), 0))
+        if self.direct:
+            self._check(self.L.rsrcu_draw_arrays(self.h, int(count), int(instances)))
+        else:
+            self._emit(OP_DRAW_ARRAYS, struct.pack("<ii", int(count), int(instances)))
 
-    def DrawElementsInstanced(self, count, indices, instance_cnt, upload=UPLOAD_ALWAYS):
-        idx = np.ascontiguousarray(indices, dtype=np.uint16)
-        self._keep.append(idx)
-        self._flush_state()
-        self._check(self.L.rsrcu_draw_elements(self.h, int(count), _ptr(idx), 0, int(instance_cnt), upload))
-
-    def DrawArraysInstanced(self, count, instance_cnt):
-        self._flush_state()
-        self._check(self.L.rsrcu_draw_arrays(self.h, int(count), int(instance_cnt)))
+    def DrawElements(self, count, indices, hint=0, upload=UPLOAD_ALWAYS): self._draw_elements(count, indices, hint, 0, upload)
+    def DrawArrays(self, count): self._draw_arrays(count, 0)
+    def DrawElementsInstanced(self, count, indices, instance_cnt, upload=UPLOAD_ALWAYS): self._draw_elements(count, indices, 0, instance_cnt, upload)
+    def DrawArraysInstanced(self, count, instance_cnt): self._draw_arrays(count, instance_cnt)
 
     def StoreColor(self, dst, gamma: bool = True):
         """(H, W) uint32 -> CMD_STORE_COLOR_FULL_LINEAR_TC; (H, W, 4) float32 -> ..._LINEAR_FP;
         None -> true-colour resolve kept on the device (see device_truecolor)"""
         self._flush_state()
-        if dst is None:
-            self._check(self.L.rsrcu_store_color_tc(self.h, int(bool(gamma)), None, self.size[0], self.size[1], self.size[0]))
-        elif dst.dtype == np.uint32:
-            h, w = dst.shape
-            self._keep.append(dst)
-            self._check(self.L.rsrcu_store_color_tc(self.h, int(bool(gamma)), _ptr(dst), w, h, dst.strides[0] // 4))
+        if dst is None or dst.dtype == np.uint32:
+            if dst is None:
+                w, h = self.size
+                stride = w
+            else:
+                h, w = dst.shape
+                stride = dst.strides[0] // 4
+                self._keep.append(dst)
+            if self.direct:
+                self._check(self.L.rsrcu_store_color_tc(self.h, int(bool(gamma)), _ptr(dst), w, h, stride))
+            else:
+                self._emit(OP_STORE_TC, struct.pack("<iiiiQ", int(bool(gamma)), w, h, stride, _addr(dst)))
         else:
             assert dst.dtype == np.float32 and dst.ndim == 3 and dst.shape[2] == 4
             h, w, _ = dst.shape
             self._keep.append(dst)
-            self._check(self.L.rsrcu_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 0))
+            if self.direct:
+                self._check(self.L.rsrcu_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 0))
+            else:
+                self._emit(OP_STORE_FP, struct.pack("<iiiiQ", 0, w, h, dst.strides[0] // 16, _addr(dst)))
 
     def StoreDepth(self, dst):
         assert dst.dtype == np.float32 and dst.flags.c_contiguous
         self._flush_state()
         self._keep.append(dst)
-        self._check(self.L.rsrcu_store_depth(self.h, _ptr(dst)))
+        if self.direct:
+            self._check(self.L.rsrcu_store_depth(self.h, _ptr(dst)))
+        else:
+            self._emit(OP_STORE_DEPTH, struct.pack("<Q", _addr(dst)))
 
     # -- beyond the reference surface -------------------------------------------------------------
     def stats(self) -> dict:

@@ -551,10 +551,13 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	std::vector<BinSeg> segs;
 	std::vector<uint32_t> chunkSegBegin;
 	uint32_t chunkFill = kChunk;   // force a new chunk for the first segment
+	uint32_t chunkSegs = 0;
+	constexpr uint32_t kMaxSegsPerChunk = 8;   // a warp walks its segments serially: keep the chain short
 	auto addSeg = [&](uint32_t draw, uint32_t kind, uint32_t start, uint32_t len) {
-		if (chunkFill + len > kChunk) { chunkSegBegin.push_back(static_cast<uint32_t>(segs.size())); chunkFill = 0; }
+		if (chunkFill + len > kChunk || chunkSegs >= kMaxSegsPerChunk) {
+			chunkSegBegin.push_back(static_cast<uint32_t>(segs.size())); chunkFill = 0; chunkSegs = 0; }
 		segs.push_back(BinSeg{draw, kind, start, len});
-		chunkFill += len; };
+		chunkFill += len; ++chunkSegs; };
 	for (size_t di = 0; di < c->draws.size(); ++di) {
 		DevDraw& d = c->draws[di].d;
 		d.vjobBase = static_cast<uint32_t>(vjobs);
@@ -778,6 +781,47 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	if (k.overflow & 1u) {
 		c->clipCapacity = c->clipCapacity * 2;
 		return fail(RSRCU_ERR_OVERFLOW, "clip record capacity exceeded (%u needed); capacity raised, render the frame again", k.clipAlloc); }
+	return RSRCU_OK; }
+
+int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
+	if (!c || !stream) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	const uint8_t* p = static_cast<const uint8_t*>(stream);
+	const uint8_t* end = p + bytes;
+	while (p + 8 <= end) {
+		uint32_t op, size;
+		std::memcpy(&op, p, 4); std::memcpy(&size, p + 4, 4);
+		if (size < 8 || (size & 7) || p + size > end) { return fail(RSRCU_ERR_INVALID, "malformed stream record (op %u size %u)", op, size); }
+		const uint8_t* q = p + 8;
+		const size_t payload = size - 8;
+		auto i32 = [&](int k) { int32_t v; std::memcpy(&v, q + 4 * k, 4); return v; };
+		auto u64 = [&](int byteOfs) { uint64_t v; std::memcpy(&v, q + byteOfs, 8); return v; };
+		auto need = [&](size_t n) { return payload >= n; };
+		int r = RSRCU_OK;
+		switch (op) {
+		case RSRCU_OP_BEGIN_FRAME: if (!need(16)) { goto bad; } r = rsrcu_begin_frame(c, i32(0), i32(1), i32(2), i32(3)); break;
+		case RSRCU_OP_STATE: { if (!need(sizeof(RsrState))) { goto bad; } RsrState st; std::memcpy(&st, q, sizeof(st)); r = rsrcu_set_state(c, &st); } break;
+		case RSRCU_OP_BIND_BUFFER: if (!need(24)) { goto bad; }
+			r = rsrcu_bind_buffer(c, i32(0), reinterpret_cast<const float*>(u64(8)), static_cast<size_t>(u64(16)), i32(1)); break;
+		case RSRCU_OP_BIND_TEXTURE: if (!need(40)) { goto bad; }
+			r = rsrcu_bind_texture(c, i32(0), reinterpret_cast<const float*>(u64(32)), i32(1), i32(2), i32(3), i32(4), i32(5), i32(6)); break;
+		case RSRCU_OP_BIND_DEPTH: if (!need(16)) { goto bad; }
+			r = rsrcu_bind_depth_texture(c, reinterpret_cast<const float*>(u64(8)), i32(0), i32(1)); break;
+		case RSRCU_OP_CLEAR: if (!need(8)) { goto bad; } r = rsrcu_clear(c, i32(0)); break;
+		case RSRCU_OP_DRAW_ELEMENTS: if (!need(24)) { goto bad; }
+			r = rsrcu_draw_elements(c, i32(0), reinterpret_cast<const uint16_t*>(u64(16)), i32(1), i32(2), i32(3)); break;
+		case RSRCU_OP_DRAW_ARRAYS: if (!need(8)) { goto bad; } r = rsrcu_draw_arrays(c, i32(0), i32(1)); break;
+		case RSRCU_OP_STORE_TC: if (!need(24)) { goto bad; }
+			r = rsrcu_store_color_tc(c, i32(0), reinterpret_cast<uint32_t*>(u64(16)), i32(1), i32(2), i32(3)); break;
+		case RSRCU_OP_STORE_FP: if (!need(24)) { goto bad; }
+			r = rsrcu_store_color_fp(c, reinterpret_cast<float*>(u64(16)), i32(1), i32(2), i32(3), i32(0)); break;
+		case RSRCU_OP_STORE_DEPTH: if (!need(8)) { goto bad; } r = rsrcu_store_depth(c, reinterpret_cast<float*>(u64(0))); break;
+		case RSRCU_OP_END_FRAME: r = rsrcu_end_frame(c); break;
+		default: return fail(RSRCU_ERR_INVALID, "unknown stream opcode %u", op); }
+		if (r != RSRCU_OK) { return r; }
+		p += size;
+		continue;
+	bad:
+		return fail(RSRCU_ERR_INVALID, "stream record op %u too short (%zu bytes)", op, payload); }
 	return RSRCU_OK; }
 
 int rsrcu_device_truecolor(rsrcu_ctx* c, void** devPtr, int* stridePx) {

@@ -351,13 +351,13 @@ class BundledLikeScene:
             ang = rng.uniform(0, 6.28, cubes)
             sc = rng.uniform(0.4, 1.6, cubes)
             self.base.append((pos, axis, ang, sc))
-        self.mats = [aligned_f32(cubes * 16) for _ in range(groups)]
         self.triangles = (len(self.m_idx) // 3) * 2 + field * field * 2 + groups * cubes * (len(cidx) // 3)
         self.draws = 2 + field * field + groups
-        self._update_instances(0.0)
+        self.mats = self.instance_matrices(0.0)
 
-    def _update_instances(self, t):
+    def instance_matrices(self, t):
         """per-frame CPU work of the $many node (node/many.cxx:188-226): rebuild instance matrices"""
+        out = []
         for g in range(self.groups):
             pos, axis, ang, sc = self.base[g]
             a = ang + t * (0.5 + 0.1 * g)
@@ -372,7 +372,10 @@ class BundledLikeScene:
             m[:, :3, :3] *= sc[:, None, None]
             m[:, :3, 3] = pos
             m[:, 3, 3] = 1.0
-            self.mats[g][:self.cubes * 16] = m.transpose(0, 2, 1).reshape(-1)   # column-major
+            a16 = aligned_f32(self.cubes * 16)
+            a16[:self.cubes * 16] = m.transpose(0, 2, 1).reshape(-1)   # column-major
+            out.append(a16)
+        return out
 
     def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True):
         """static=True marks every buffer immutable (device-resident bench leg); otherwise the
@@ -380,8 +383,7 @@ class BundledLikeScene:
         w, h = size
         up = {"upload": 1} if hasattr(gl, "stats") else {}
         dyn = up if static else {}
-        if not static:
-            self._update_instances(t)
+        mats = self.mats if static else self.instance_matrices(t)
         begin(gl, size, clear=(0.222, 0.222, 0.333), tile_blocks=tile_blocks)
         proj = perspective(45.0, w / h, 1.0, 400.0) if proj is None else proj
         gl.ProjectionMatrix(proj)
@@ -396,7 +398,7 @@ class BundledLikeScene:
         gl.UseBuffer(3, self.c_nrm, **up)
         gl.UseBuffer(9, self.c_uv, **up)
         for g in range(self.groups):
-            gl.UseBuffer(15, self.mats[g], **dyn)
+            gl.UseBuffer(15, mats[g], **dyn)
             gl.DrawElementsInstanced(len(self.c_idx), self.c_idx, self.cubes, **up)
 
         # lit meshes
