@@ -428,3 +428,94 @@ class BundledLikeScene:
                 gl.ViewMatrix(translate((i - n / 2) * 1.0 + ox, (j - n / 2) * 0.55 + oy - 1.0, -30.0 - 0.01 * (i + j)) @ scale(0.9, 0.5, 1.0))
                 gl.DrawElements(6, self.q_idx, 0, **up)
         finish(gl, out, gamma, depth)
+
+
+class SoupScene:
+    """seeded random triangle soup in clip-ish space: slivers, degenerates, triangles crossing the
+    near plane and the guard band, back faces -- the cases the reference's binner/clipper special-case
+    (rglv_gpu_impl.hxx:427-494, :678-793)"""
+
+    def __init__(self, n=600, seed=3, spread=1.6, near_cross=True, program=PROGRAM_AMY, cull=None, blend=False,
+                 instanced=0, depth_func=None, tex_dim=64, bilinear=True, tiny=False):
+        rng = np.random.default_rng(seed)
+        c = rng.uniform(-spread, spread, (n, 1, 3))
+        c[:, :, 2] = rng.uniform(-12.0, 0.5 if near_cross else -1.5, (n, 1))
+        ext = rng.choice([0.02, 0.2, 1.0, 4.0], size=(n, 1, 1), p=[0.3, 0.4, 0.2, 0.1]) if not tiny else 0.02
+        tri = c + rng.normal(0, 1, (n, 3, 3)) * ext
+        # a few exact degenerates and slivers
+        tri[::50, 2] = tri[::50, 1]
+        tri[7::60, 2] = tri[7::60, 0] + (tri[7::60, 1] - tri[7::60, 0]) * 0.5 + 1e-4
+        pos = tri.reshape(-1, 3).T
+        self.pos = soa(pos)
+        self.nrm = soa(rng.normal(0, 1, pos.shape))
+        self.kd = soa(rng.random(pos.shape))
+        self.uv = soa(rng.uniform(-0.5, 2.5, (2, pos.shape[1])))
+        self.idx = np.arange(3 * n, dtype=np.uint16)
+        self.tex = make_mipmap(hash_texture(tex_dim, seed))
+        self.tex_dim = tex_dim
+        self.filter = GL_LINEAR_MIPMAP_NEAREST if bilinear else GL_NEAREST_MIPMAP_NEAREST
+        self.program, self.cull, self.blend, self.depth_func = program, cull, blend, depth_func
+        self.instanced = instanced
+        if instanced:
+            mats = [(translate(*rng.uniform(-2, 2, 3)) @ rotate(rng.uniform(0, 6), *rng.uniform(-1, 1, 3))).T.reshape(16)
+                    for _ in range(instanced)]
+            self.mats = aligned_f32(instanced * 16)
+            self.mats[:instanced * 16] = np.concatenate(mats)
+        self.shadow = rng.random((256, 256)).astype(np.float32)
+        self.triangles = n * max(1, instanced)
+
+    def record(self, gl, size, out, depth=None, tile_blocks=(8, 8), arrays=False, gamma=True, fp_out=None,
+               attachments=None, post=PROGRAM_DEFAULT_POST, post_uniform=None):
+        from . import (GL_COLOR_ATTACHMENT0, GL_DEPTH_ATTACHMENT, PROGRAM_OBJ2S, PROGRAM_PATTERN, RB_F32, RB_RGBF32)
+        w, h = size
+        gl.Reset(size, tile_blocks)
+        if attachments == "split":
+            gl.RenderbufferType(GL_COLOR_ATTACHMENT0, RB_RGBF32)
+            gl.RenderbufferType(GL_DEPTH_ATTACHMENT, RB_F32)
+        gl.ClearColor((0.1, 0.2, 0.3))
+        gl.ClearDepth(1.0)
+        gl.Clear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT)
+        gl.UseProgram(self.program)
+        gl.ViewMatrix(translate(0.1, -0.05, -1.0) @ rotate(0.2, 0.1, 1.0, 0.3))
+        gl.ProjectionMatrix(perspective(70.0, w / h, 0.5, 50.0))
+        if self.cull is not None:
+            gl.Enable(GL_CULL_FACE)
+            gl.CullFace(self.cull)
+        if self.blend:
+            gl.Enable(GL_BLEND)
+        if self.depth_func is not None:
+            gl.DepthFunc(self.depth_func)
+        gl.UseBuffer(0, self.pos)
+        gl.UseBuffer(3, self.nrm)
+        gl.UseBuffer(6, self.kd)
+        gl.UseBuffer(9, self.uv)
+        gl.BindTexture(0, self.tex, self.tex_dim, self.tex_dim, self.tex_dim, self.filter)
+        if self.program == PROGRAM_MANY:
+            gl.UseUniforms(np.array([0.75], np.float32))
+        if self.program == PROGRAM_PATTERN:
+            gl.UseUniforms(np.array([0.25, 0.5, 0, 0, 0, float(h), 0, 0], np.float32))
+        if self.program == PROGRAM_OBJ2S:
+            m2s = (perspective(60.0, 1.0, 0.5, 60.0) @ translate(0.3, 0.2, -2.0)).T.reshape(16)
+            u = np.concatenate([m2s, [0.5, 2.0, 1.0], [0.1, -0.6, -0.8], [0.3]]).astype(np.float32)
+            gl.UseUniforms(u)
+            gl.BindTexture3(self.shadow, 256)
+        if self.program == 5:  # Depth program samples the depth texture
+            gl.BindTexture3(self.shadow, 256)
+        if self.instanced:
+            gl.UseBuffer(15, self.mats)
+            if arrays:
+                gl.DrawArraysInstanced(len(self.idx), self.instanced)
+            else:
+                gl.DrawElementsInstanced(len(self.idx), self.idx, self.instanced)
+        elif arrays:
+            gl.DrawArrays(len(self.idx))
+        else:
+            gl.DrawElements(len(self.idx), self.idx, 0)
+        gl.UseProgram(post)
+        if post_uniform is not None:
+            gl.UseUniforms(np.array([post_uniform], np.float32))
+        if depth is not None:
+            gl.StoreDepth(depth)
+        if fp_out is not None:
+            gl.StoreColor(fp_out)
+        gl.StoreColor(out, gamma)
