@@ -1,0 +1,99 @@
+"""-m gpu: the CUDA path against (a) the committed golden frames the reference rendered in the build
+container -- with that CPU's rcpps/rsqrtps tables loaded through rsrcu_set_host_luts, so the check
+does not depend on this box's CPU -- and (b) the C restatement on the same seeded inputs."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import rsr_b200 as R
+from oracle import restate
+from rsr_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+make_golden = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(make_golden)
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.cases().keys()))
+def test_cuda_reproduces_golden_frames(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    factory, kw = make_golden.cases()[name]
+    size = tuple(int(v) for v in g["size"])
+    gpu = R.GPU(0)
+    try:
+        gpu.set_host_luts(g["rcp"], g["rsqrt"])
+        out = np.zeros((size[1], size[0]), np.uint32)
+        factory().record(gpu, size, out, **kw)
+        gpu.Run()
+    finally:
+        gpu.close()
+    assert np.array_equal(out, g["frame"]), f"{np.count_nonzero(out != g['frame'])} pixels differ from the golden frame"
+
+
+def test_host_lut_harvest_equals_oracle_harvest(cuda_gpu):
+    rcp, rsq = cuda_gpu.get_host_luts()
+    want = restate.harvest_luts()
+    assert np.array_equal(rcp, want[0]) and np.array_equal(rsq, want[1])
+
+
+@pytest.mark.parametrize("case", ["c2_1080p", "soup_1080p"])
+def test_cuda_equals_restatement_with_depth(case, cuda_gpu):
+    """depth buffers bit for bit (the reference cannot store depth from RB_COLOR_DEPTH; the restatement can)"""
+    sc, kw = {"c2_1080p": (scenes.BundledLikeScene(cubes=500), {"t": 0.25}),
+              "soup_1080p": (scenes.SoupScene(n=800, seed=23), {})}[case]
+    size = (1920, 1080)
+    a, da = np.zeros((size[1], size[0]), np.uint32), np.zeros((size[1], size[0]), np.float32)
+    b, db = np.zeros_like(a), np.zeros_like(da)
+    sc.record(cuda_gpu, size, a, da, **kw)
+    cuda_gpu.Run()
+    rst = restate.RestateGPU()
+    sc.record(rst, size, b, db, **kw)
+    rst.Run()
+    assert np.array_equal(a, b), f"{np.count_nonzero(a != b)} colour pixels differ"
+    assert np.array_equal(da.view(np.uint32), db.view(np.uint32)), "depth buffers differ"
+    assert cuda_gpu.stats()["fragments_shaded"] == rst.fragments
+
+
+def test_determinism_and_idempotence(cuda_gpu):
+    """same recorded frame twice -> same bytes (size-independent property)"""
+    sc = scenes.BundledLikeScene(cubes=800)
+    a = np.zeros((1080, 1920), np.uint32)
+    sc.record(cuda_gpu, (1920, 1080), a, t=0.3, static=True)
+    rec = cuda_gpu.Finish()
+    cuda_gpu.Submit(rec)
+    first = a.copy()
+    a[:] = 0
+    cuda_gpu.Submit(rec)
+    assert np.array_equal(first, a)
+
+
+def test_submission_order_decides_equal_depth(cuda_gpu, ref_gpu):
+    """two coplanar quads with different textures: LESS keeps the first one drawn, everywhere"""
+    class Coplanar:
+        def __init__(self):
+            q = np.array([[-1, 1, 1, -1], [-1, -1, 1, 1], [0, 0, 0, 0]], np.float32)
+            self.pos, self.uv = scenes.soa(q), scenes.soa((q[:2] + 1) / 2)
+            self.idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+            self.t0 = scenes.make_mipmap(scenes.hash_texture(32, 1, 0))
+            self.t1 = scenes.make_mipmap(scenes.hash_texture(32, 1, 1))
+
+        def record(self, gl, size, out, depth=None):
+            scenes.begin(gl, size)
+            gl.UseProgram(R.PROGRAM_AMY)
+            gl.ViewMatrix(scenes.translate(0, 0, -3))
+            gl.ProjectionMatrix(scenes.perspective(40.0, size[0] / size[1], 1, 10))
+            gl.UseBuffer(0, self.pos); gl.UseBuffer(9, self.uv)
+            for t in (self.t0, self.t1):
+                gl.BindTexture(0, t, 32, 32, 32, R.GL_NEAREST_MIPMAP_NEAREST)
+                gl.DrawElements(6, self.idx, 0)
+            scenes.finish(gl, out)
+    sc = Coplanar()
+    a, b = np.zeros((360, 640), np.uint32), np.zeros((360, 640), np.uint32)
+    sc.record(cuda_gpu, (640, 360), a); cuda_gpu.Run()
+    sc.record(ref_gpu, (640, 360), b); ref_gpu.Run()
+    assert np.array_equal(a, b)
