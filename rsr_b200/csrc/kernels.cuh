@@ -23,7 +23,7 @@ namespace rsr {
 constexpr int kTile = 32;                 // device tile edge in pixels (independent of the reference's)
 constexpr int kTileThreads = 256;         // one thread per 2x2 quad
 constexpr int kBatch = 256;               // triangles set up per pass of the tile kernel
-constexpr int kChunk = 1024;              // ids per bin row
+constexpr int kMaxChunkShift = 10;        // a bin row covers at most 1024 triangle ids (chosen per frame)
 constexpr int kBinWarps = 4;              // warps per bin CTA
 constexpr int kMaxFan = 6;                // a clipped triangle has <= 8 vertices => <= 6 fan triangles
 constexpr int kClipVaryF4 = 4;            // float4s of varyings per clipped vertex (>= kMaxVaryings/4)
@@ -49,7 +49,7 @@ struct DevDraw {
 	uint32_t vjobBase;      // prefix of instances*nverts
 	uint32_t pjobBase;      // prefix of N
 	uint32_t clipSegBase;   // first clip segment of this draw in the segment table
-	uint32_t pad; };
+	uint32_t batchKey; };   // program id | pipeline flags << 8: draws with equal keys may share a raster batch
 
 struct ClipVertex {
 	float4 dev;                       // device x, y, ndc z, 1/w  (rglv_gpu_impl.hxx:763-767)
@@ -85,6 +85,7 @@ struct FrameParams {
 	float guardFactor;           // CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
 	int ndraws, ncmds;
 	uint32_t totalVJobs, totalPJobs;
+	int segShift;                // log2(triangles per bin segment), 6..10, chosen per frame
 	uint32_t clipCapacity;       // ClipRec capacity
 	uint32_t listCapacity; };
 
@@ -343,7 +344,7 @@ setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ sta
 		else if (pointsOutside) {
 			atomicAdd(&ctr->clipped, 1ull);
 			out = clip_triangle(d, s, fp, r0, r1, r2, luts, clipRecs, ctr);
-			if (out != (kClipSrc | kNoClipRec)) { atomicAdd(&segActive[d.clipSegBase + local / kChunk], 1u); } }
+			if (out != (kClipSrc | kNoClipRec)) { atomicAdd(&segActive[d.clipSegBase + (local >> fp.segShift)], 1u); } }
 		else {
 			const float4 a = __ldg(r0), b = __ldg(r1), c = __ldg(r2);
 			// rmlg::Area (rmlg_triangle.hxx:18-27)

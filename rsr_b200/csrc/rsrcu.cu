@@ -472,6 +472,7 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	d.nvary = programVaryings(st.program_id);
 	d.strideF4 = 2 + (d.nvary + 3) / 4;
 	d.N = static_cast<uint32_t>(prims) * static_cast<uint32_t>(instances);
+	d.batchKey = static_cast<uint32_t>(st.program_id & 0xff) | (static_cast<uint32_t>(key) << 8);
 	if (!arrays) {
 		if (!indices) { return fail(RSRCU_ERR_INVALID, "null index pointer"); }
 		r = uploadData(c, indices, static_cast<size_t>(prims) * 3 * sizeof(uint16_t), upload, hd.indices);
@@ -550,14 +551,24 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	uint64_t vjobs = 0, pjobs = 0, ids = 0, ptvbF4 = 0, nvertsTotal = 0;
 	std::vector<BinSeg> segs;
 	std::vector<uint32_t> chunkSegBegin;
-	uint32_t chunkFill = kChunk;   // force a new chunk for the first segment
-	uint32_t chunkSegs = 0;
-	constexpr uint32_t kMaxSegsPerChunk = 8;   // a warp walks its segments serially: keep the chain short
+	// Segment length: small frames get short segments so that enough warps (one per chunk row) are
+	// in flight; large frames use 1024 to keep the count matrix (rows x tiles) small.
+	uint64_t totalTris = 0;
+	for (const HostDraw& hd : c->draws) { totalTris += hd.d.N; }
+	int segShift = 6;
+	while (segShift < kMaxChunkShift && (totalTris >> segShift) > 2048) { ++segShift; }
+	const uint32_t segLen = 1u << segShift;
+	fp.segShift = segShift;
+	// A chunk (= one warp, one row of the count matrix) holds consecutive segments: at most segLen
+	// triangle ids and 8 triangle segments (the warp walks them serially); clip segments are almost
+	// always inactive and cost next to nothing, so up to 64 of them ride along.
+	uint32_t chunkFill = segLen, chunkTriSegs = 0, chunkSegs = 0;   // force a new chunk first
 	auto addSeg = [&](uint32_t draw, uint32_t kind, uint32_t start, uint32_t len) {
-		if (chunkFill + len > kChunk || chunkSegs >= kMaxSegsPerChunk) {
-			chunkSegBegin.push_back(static_cast<uint32_t>(segs.size())); chunkFill = 0; chunkSegs = 0; }
+		const uint32_t cost = kind == 0 ? len : 0;
+		if (chunkFill + cost > segLen || (kind == 0 && chunkTriSegs >= 8) || chunkSegs >= 64) {
+			chunkSegBegin.push_back(static_cast<uint32_t>(segs.size())); chunkFill = 0; chunkTriSegs = 0; chunkSegs = 0; }
 		segs.push_back(BinSeg{draw, kind, start, len});
-		chunkFill += len; ++chunkSegs; };
+		chunkFill += cost; chunkTriSegs += (kind == 0); ++chunkSegs; };
 	for (size_t di = 0; di < c->draws.size(); ++di) {
 		DevDraw& d = c->draws[di].d;
 		d.vjobBase = static_cast<uint32_t>(vjobs);
@@ -569,12 +580,13 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		vjobs += nv; nvertsTotal += nv; ptvbF4 += nv * d.strideF4;
 		pjobs += d.N;
 		ids += static_cast<uint64_t>(d.N) * (1 + kMaxFan);
-		for (uint32_t s0 = 0; s0 < d.N; s0 += kChunk) { addSeg(static_cast<uint32_t>(di), 0, s0, std::min<uint32_t>(kChunk, d.N - s0)); }
+		for (uint32_t s0 = 0; s0 < d.N; s0 += segLen) { addSeg(static_cast<uint32_t>(di), 0, s0, std::min<uint32_t>(segLen, d.N - s0)); }
 		d.clipSegBase = static_cast<uint32_t>(segs.size());
-		// clip segments must be addressable as clipSegBase + source/kChunk
-		for (uint32_t s0 = 0; s0 < d.N; s0 += kChunk) { addSeg(static_cast<uint32_t>(di), 1, s0, std::min<uint32_t>(kChunk, d.N - s0)); } }
+		// clip segments must be addressable as clipSegBase + (source >> segShift)
+		for (uint32_t s0 = 0; s0 < d.N; s0 += segLen) { addSeg(static_cast<uint32_t>(di), 1, s0, std::min<uint32_t>(segLen, d.N - s0)); } }
 	chunkSegBegin.push_back(static_cast<uint32_t>(segs.size()));
 	const int nchunks = static_cast<int>(chunkSegBegin.size()) - 1;
+	if (c->states.size() > 65535) { return fail(RSRCU_ERR_UNSUPPORTED, "more than 65535 state snapshots in one frame"); }
 	if (ids >= 0xfffffff0ull || ptvbF4 >= 0x7ffffff0ull || vjobs >= 0xfffffff0ull) {
 		return fail(RSRCU_ERR_UNSUPPORTED, "frame too large for 32-bit ids (%llu ids, %llu vertex records)",
 		            static_cast<unsigned long long>(ids), static_cast<unsigned long long>(ptvbF4)); }

@@ -36,6 +36,8 @@ __constant__ uint32_t kSrgbTab4[104] = {
 	0x5e0c0a23, 0x631c0980, 0x67db08f6, 0x6c55087f, 0x70940818, 0x74a007bd, 0x787d076c, 0x7c330723,
 };
 
+constexpr int kSmemDraws = 1024;
+
 struct TileShared {
 	float chan[4][4][kTileThreads];      // [r,g,b,depth][quad lane][thread]
 	int ec[3][kBatch];                   // edge functions at the tile origin
@@ -46,6 +48,9 @@ struct TileShared {
 	float z[3][kBatch];
 	float iw[3][kBatch];
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
+	uint16_t state[kBatch];              // DevState index of the triangle's draw
+	uint32_t drawIdBase[kSmemDraws];     // idBase of the first kSmemDraws draws (id -> draw lookup)
+	int firstBad;
 };
 
 struct TileArgs {
@@ -173,7 +178,7 @@ __device__ __forceinline__ bool depth_pass(int func, float frag, float dest) {
 
 // TriangleProgram::Render for one quad (rglv_gpu_impl.hxx:166-222)
 template <class P>
-__device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, const int i, const TileArgs& A, const DevDraw& d,
+__device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, const int i, const TileArgs& A,
                                                 const DevState& s, const int (&e1)[4], const int (&e2)[4], const uint32_t triMask,
                                                 const int px, const int py, const bool clipped) {
 	const float scale = sh.scale[i];
@@ -266,58 +271,63 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 					sh.chan[2][l][t] = cb[l]; } } } }
 	return __popc(fragMask); }
 
+// id -> index of the draw that owns it (draw id ranges are disjoint and increasing)
+__device__ __forceinline__ int find_draw_of_id(const TileShared& sh, const TileArgs& A, uint32_t id) {
+	int lo = 0, hi = A.fp.ndraws - 1;
+	if (A.fp.ndraws <= kSmemDraws) {
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			if (sh.drawIdBase[mid] <= id) { lo = mid; } else { hi = mid - 1; } } }
+	else {
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			if (A.draws[mid].idBase <= id) { lo = mid; } else { hi = mid - 1; } } }
+	return lo; }
+
+// rasterises the nb triangles that setup_triangle placed in shared memory, in order
 template <class P>
-__device__ __noinline__ unsigned draw_segment(TileShared& sh, const TileArgs& A, const DevDraw& d, const DevState& s,
-                                              const uint32_t* __restrict__ list, uint32_t n,
-                                              int ox, int oy, int rl, int rt, int rr, int rb) {
+__device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	// warp region: 16x8 pixels = 8x4 quads; 2 regions across, 4 down
 	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
 	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;   // tile-local quad origin
 	unsigned frags = 0;
-
-	for (uint32_t b0 = 0; b0 < n; b0 += kBatch) {
-		const int nb = min(static_cast<uint32_t>(kBatch), n - b0);
-		__syncthreads();
-		if (t < nb) { setup_triangle(sh, t, __ldg(list + b0 + t), d, A, ox, oy, rl, rt, rr, rb); }
-		__syncthreads();
-
-		for (int k = 0; k < nb; k += 32) {
-			const int i = k + lane;
-			bool hit = false;
-			if (i < nb) {
-				const uint32_t bb = sh.bbox[i];
-				const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
-				hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
-			unsigned m = __ballot_sync(0xffffffffu, hit);
-			while (m) {
-				const int j = __ffs(m) - 1;
-				m &= m - 1;
-				const int ti = k + j;
-				const uint32_t bb = sh.bbox[ti];
-				const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
-				if (lx < minx || lx >= maxx || ly < miny || ly >= maxy) { continue; }
-				int e1[4], e2[4];
-				uint32_t covered = 0;
-				{
-					const uint32_t ulx = lx, uly = ly;
-					const uint32_t dy1 = sh.edy[0][ti], dx1 = sh.edx[0][ti];
-					const uint32_t dy2 = sh.edy[1][ti], dx2 = sh.edx[1][ti];
-					const uint32_t dy3 = sh.edy[2][ti], dx3 = sh.edx[2][ti];
-					const uint32_t a1 = static_cast<uint32_t>(sh.ec[0][ti]) + ulx * dy1 + uly * dx1;
-					const uint32_t a2 = static_cast<uint32_t>(sh.ec[1][ti]) + ulx * dy2 + uly * dx2;
-					const uint32_t a3 = static_cast<uint32_t>(sh.ec[2][ti]) + ulx * dy3 + uly * dx3;
-					const uint32_t q1[4] = { a1, a1 + dy1, a1 + dx1, a1 + dx1 + dy1 };
-					const uint32_t q2[4] = { a2, a2 + dy2, a2 + dx2, a2 + dx2 + dy2 };
-					const uint32_t q3[4] = { a3, a3 + dy3, a3 + dx3, a3 + dx3 + dy3 };
+	for (int k = 0; k < nb; k += 32) {
+		const int i = k + lane;
+		bool hit = false;
+		if (i < nb) {
+			const uint32_t bb = sh.bbox[i];
+			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+			hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+		unsigned m = __ballot_sync(0xffffffffu, hit);
+		while (m) {
+			const int j = __ffs(m) - 1;
+			m &= m - 1;
+			const int ti = k + j;
+			const uint32_t bb = sh.bbox[ti];
+			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+			if (lx < minx || lx >= maxx || ly < miny || ly >= maxy) { continue; }
+			int e1[4], e2[4];
+			uint32_t covered = 0;
+			{
+				const uint32_t ulx = lx, uly = ly;
+				const uint32_t dy1 = sh.edy[0][ti], dx1 = sh.edx[0][ti];
+				const uint32_t dy2 = sh.edy[1][ti], dx2 = sh.edx[1][ti];
+				const uint32_t dy3 = sh.edy[2][ti], dx3 = sh.edx[2][ti];
+				const uint32_t a1 = static_cast<uint32_t>(sh.ec[0][ti]) + ulx * dy1 + uly * dx1;
+				const uint32_t a2 = static_cast<uint32_t>(sh.ec[1][ti]) + ulx * dy2 + uly * dx2;
+				const uint32_t a3 = static_cast<uint32_t>(sh.ec[2][ti]) + ulx * dy3 + uly * dx3;
+				const uint32_t q1[4] = { a1, a1 + dy1, a1 + dx1, a1 + dx1 + dy1 };
+				const uint32_t q2[4] = { a2, a2 + dy2, a2 + dx2, a2 + dx2 + dy2 };
+				const uint32_t q3[4] = { a3, a3 + dy3, a3 + dx3, a3 + dx3 + dy3 };
 #pragma unroll
-					for (int l = 0; l < 4; ++l) {
-						e1[l] = static_cast<int>(q1[l]);
-						e2[l] = static_cast<int>(q2[l]);
-						if (static_cast<int>(q1[l] | q2[l] | q3[l]) >= 0) { covered |= (1u << l); } } }
-				if (covered == 0) { continue; }
-				frags += render_quad<P>(sh, t, ti, A, d, s, e1, e2, covered, ox + lx, oy + ly, (bb >> 24) & 1u); } } }
+				for (int l = 0; l < 4; ++l) {
+					e1[l] = static_cast<int>(q1[l]);
+					e2[l] = static_cast<int>(q2[l]);
+					if (static_cast<int>(q1[l] | q2[l] | q3[l]) >= 0) { covered |= (1u << l); } } }
+			if (covered == 0) { continue; }
+			frags += render_quad<P>(sh, t, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (bb >> 24) & 1u); } }
 	return frags; }
 
 // sRGB::to_tc / LinearColor::to_tc (rglr_canvas_util.hxx:15-62, ryg-srgb.h:183-223)
@@ -366,17 +376,16 @@ tile_kernel(TileArgs A) {
 
 	// Frame walk.  A.cmds holds the non-draw commands (clear / stores) in submission order, each
 	// tagged with the number of draws recorded before it; draws are discovered from the tile's own
-	// id-sorted list, so a tile only pays for the draws that actually touch it.
+	// id-sorted list, so a tile only pays for the draws that touch it.  Up to 256 consecutive
+	// list entries are rasterised as one batch as long as they share a program + pipeline flags
+	// (DevDraw::batchKey) and no clear/store command lies between them -- a scene made of hundreds
+	// of tiny draws (one per textured quad) still fills whole batches.
+	for (int i = t; i < min(A.fp.ndraws, kSmemDraws); i += kTileThreads) { sh.drawIdBase[i] = A.draws[i].idBase; }
+	__syncthreads();
 	int ci = 0;
 	while (true) {
 		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
-		if (cursor < listLen) {
-			const uint32_t id = __ldg(list + cursor);
-			int lo = 0, hi = A.fp.ndraws - 1;
-			while (lo < hi) {
-				const int mid = (lo + hi + 1) >> 1;
-				if (A.draws[mid].idBase <= id) { lo = mid; } else { hi = mid - 1; } }
-			di = lo; }
+		if (cursor < listLen) { di = find_draw_of_id(sh, A, __ldg(list + cursor)); }
 		// non-draw commands that precede that draw
 		while (ci < A.fp.ncmds && A.cmds[ci].beforeDraw <= di) {
 			const FrameCmd cmd = A.cmds[ci];
@@ -425,30 +434,39 @@ tile_kernel(TileArgs A) {
 			default: break; } }
 		if (di >= A.fp.ndraws) { break; }
 
-		// this draw's slice of the (id-sorted) tile list
-		const DevDraw& d = A.draws[di];
-		const DevState& s = A.states[d.state];
-		const uint32_t idEnd = d.idBase + d.N * (1u + kMaxFan);
-		uint32_t lo = cursor, hi = listLen;
-		while (lo < hi) {
-			const uint32_t mid = (lo + hi) >> 1;
-			if (__ldg(list + mid) < idEnd) { lo = mid + 1; } else { hi = mid; } }
-		const uint32_t n = lo - cursor;
-		const uint32_t* seg = list + cursor;
-		switch (s.programId) {
-		case ProgAmy::id:          frags += draw_segment<ProgAmy>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgAlphaTexture::id: frags += draw_segment<ProgAlphaTexture>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgText::id:         frags += draw_segment<ProgText>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgDepth::id:        frags += draw_segment<ProgDepth>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgPattern::id:      frags += draw_segment<ProgPattern>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgMany::id:         frags += draw_segment<ProgMany>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgOBJ1::id:         frags += draw_segment<ProgOBJ1>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgOBJ2::id:         frags += draw_segment<ProgOBJ2>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgOBJ2S::id:        frags += draw_segment<ProgOBJ2S>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgEnvmap::id:       frags += draw_segment<ProgEnvmap>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
-		case ProgWireframe::id:    frags += draw_segment<ProgWireframe>(sh, A, d, s, seg, n, ox, oy, rl, rt, rr, rb); break;
+		const int bound = (ci < A.fp.ncmds) ? A.cmds[ci].beforeDraw : 0x7fffffff;   // draws >= bound come after cmds[ci]
+		const uint32_t key0 = A.draws[di].batchKey;
+		const int avail = static_cast<int>(min(static_cast<uint32_t>(kBatch), listLen - cursor));
+		__syncthreads();   // previous batch fully rasterised before its records are overwritten
+		if (t == 0) { sh.firstBad = avail; }
+		__syncthreads();
+		uint32_t myId = 0;
+		int myDraw = 0;
+		if (t < avail) {
+			myId = __ldg(list + cursor + t);
+			myDraw = find_draw_of_id(sh, A, myId);
+			if (myDraw >= bound || A.draws[myDraw].batchKey != key0) { atomicMin(&sh.firstBad, t); } }
+		__syncthreads();
+		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
+		if (t < nb) {
+			const DevDraw& d = A.draws[myDraw];
+			sh.state[t] = static_cast<uint16_t>(d.state);
+			setup_triangle(sh, t, myId, d, A, ox, oy, rl, rt, rr, rb); }
+		__syncthreads();
+		switch (key0 & 0xffu) {
+		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, nb, ox, oy); break;
+		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, nb, ox, oy); break;
+		case ProgText::id:         frags += draw_batch<ProgText>(sh, A, nb, ox, oy); break;
+		case ProgDepth::id:        frags += draw_batch<ProgDepth>(sh, A, nb, ox, oy); break;
+		case ProgPattern::id:      frags += draw_batch<ProgPattern>(sh, A, nb, ox, oy); break;
+		case ProgMany::id:         frags += draw_batch<ProgMany>(sh, A, nb, ox, oy); break;
+		case ProgOBJ1::id:         frags += draw_batch<ProgOBJ1>(sh, A, nb, ox, oy); break;
+		case ProgOBJ2::id:         frags += draw_batch<ProgOBJ2>(sh, A, nb, ox, oy); break;
+		case ProgOBJ2S::id:        frags += draw_batch<ProgOBJ2S>(sh, A, nb, ox, oy); break;
+		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, nb, ox, oy); break;
+		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, nb, ox, oy); break;
 		default: break; }
-		cursor = max(lo, cursor + 1); }
+		cursor += static_cast<uint32_t>(max(nb, 1)); }
 
 	// fragment statistics: one atomic per CTA
 	for (int o = 16; o > 0; o >>= 1) { frags += __shfl_down_sync(0xffffffffu, frags, o); }
