@@ -445,6 +445,7 @@ __global__ void scan_group_sums(const uint32_t* __restrict__ counts, int nchunks
 	if (t >= ntiles) { return; }
 	const int c0 = g * chunksPerGroup, c1 = min(c0 + chunksPerGroup, nchunks);
 	uint32_t s = 0;
+#pragma unroll 8
 	for (int c = c0; c < c1; ++c) { s += counts[static_cast<size_t>(c) * ntiles + t]; }
 	gsum[static_cast<size_t>(g) * ntiles + t] = s; }
 
@@ -461,10 +462,13 @@ scan_tiles(uint32_t* __restrict__ gsum, int ngroups, int ntiles, uint32_t* __res
 		const int t = t0 + tid;
 		uint32_t total = 0;
 		if (t < ntiles) {
-			for (int g = 0; g < ngroups; ++g) {
-				const uint32_t v = gsum[static_cast<size_t>(g) * ntiles + t];
-				gsum[static_cast<size_t>(g) * ntiles + t] = total;
-				total += v; } }
+			for (int g = 0; g < ngroups; g += 8) {
+				uint32_t v[8];
+#pragma unroll
+				for (int k = 0; k < 8; ++k) { v[k] = (g + k < ngroups) ? gsum[static_cast<size_t>(g + k) * ntiles + t] : 0u; }
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					if (g + k < ngroups) { gsum[static_cast<size_t>(g + k) * ntiles + t] = total; total += v[k]; } } } }
 		// block exclusive scan of total
 		uint32_t incl = total;
 		for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) { incl += n; } }
@@ -479,6 +483,7 @@ scan_tiles(uint32_t* __restrict__ gsum, int ngroups, int ntiles, uint32_t* __res
 		if (t < ntiles) {
 			tileBase[t] = before;
 			tileCount[t] = total;
+#pragma unroll 8
 			for (int g = 0; g < ngroups; ++g) { gsum[static_cast<size_t>(g) * ntiles + t] += before; } }
 		__syncthreads();
 		if (tid == 1023) { carry = before + total; }
@@ -494,10 +499,13 @@ __global__ void scan_apply(uint32_t* __restrict__ counts, int nchunks, int ntile
 	if (t >= ntiles) { return; }
 	const int c0 = g * chunksPerGroup, c1 = min(c0 + chunksPerGroup, nchunks);
 	uint32_t run = gsum[static_cast<size_t>(g) * ntiles + t];
-	for (int c = c0; c < c1; ++c) {
-		const size_t o = static_cast<size_t>(c) * ntiles + t;
-		const uint32_t v = counts[o];
-		counts[o] = run;
-		run += v; } }
+	// 8 independent loads in flight, then 8 stores: the chain is the adds, not the memory round trips
+	for (int c = c0; c < c1; c += 8) {
+		uint32_t v[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) { v[k] = (c + k < c1) ? counts[static_cast<size_t>(c + k) * ntiles + t] : 0u; }
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			if (c + k < c1) { counts[static_cast<size_t>(c + k) * ntiles + t] = run; run += v[k]; } } } }
 
 }  // namespace rsr

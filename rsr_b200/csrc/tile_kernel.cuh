@@ -348,7 +348,7 @@ __device__ __forceinline__ uint32_t linear8(float f) {
 	r = sse_max(r, 0.0f);
 	return static_cast<uint32_t>(cvtt(r * 255.0f)); }
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
 tile_kernel(TileArgs A) {
 	__shared__ TileShared sh;
 	const int t = threadIdx.x;
