@@ -373,6 +373,43 @@ __device__ __forceinline__ void bin_items(bool valid, uint32_t info, uint32_t id
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned ltMask = (1u << lane) - 1u;
 	const int tx0 = info & 63, ty0 = (info >> 6) & 63, tx1 = (info >> 12) & 63, ty1 = (info >> 18) & 63;
+	const unsigned validMask = __ballot_sync(0xffffffffu, valid);
+	if (validMask == 0) { return; }
+
+	// Two ways to hand out list slots in submission order for these 32 triangles:
+	//  (a) tile-serial: repeatedly take the smallest tile index any lane still has to visit; the lanes
+	//      covering it get consecutive slots by ballot.  One step per distinct tile: good for small
+	//      triangles (a few tiles in total).
+	//  (b) tile-parallel: every lane owns one tile of the union bbox and walks the 32 triangles in
+	//      order.  32 steps per 32 tiles of the union: good for large, overlapping triangles.
+	const unsigned ux0 = __reduce_min_sync(0xffffffffu, valid ? static_cast<unsigned>(tx0) : 63u);
+	const unsigned uy0 = __reduce_min_sync(0xffffffffu, valid ? static_cast<unsigned>(ty0) : 63u);
+	const unsigned ux1 = __reduce_max_sync(0xffffffffu, valid ? static_cast<unsigned>(tx1) : 0u);
+	const unsigned uy1 = __reduce_max_sync(0xffffffffu, valid ? static_cast<unsigned>(ty1) : 0u);
+	const unsigned sumTiles = __reduce_add_sync(0xffffffffu, valid ? static_cast<unsigned>((tx1 - tx0 + 1) * (ty1 - ty0 + 1)) : 0u);
+	const unsigned uw = ux1 - ux0 + 1u, uh = uy1 - uy0 + 1u, U = uw * uh;
+	if (sumTiles >= 48u && U * 2u < sumTiles * 5u) {
+		for (unsigned base = 0; base < U; base += 32u) {
+			const unsigned u = base + lane;
+			const int tx = static_cast<int>(ux0 + u % uw), ty = static_cast<int>(uy0 + u / uw);
+			const bool own = u < U;
+			const uint32_t T = static_cast<uint32_t>(ty * tilesX + tx);
+			const uint32_t start = own ? row[T] : 0u;
+			uint32_t cnt = 0;
+			unsigned m = validMask;
+			while (m) {
+				const int j = __ffs(m) - 1;
+				m &= m - 1;
+				const uint32_t bj = __shfl_sync(0xffffffffu, info, j);
+				const uint32_t idj = __shfl_sync(0xffffffffu, id, j);
+				const int jx0 = bj & 63, jy0 = (bj >> 6) & 63, jx1 = (bj >> 12) & 63, jy1 = (bj >> 18) & 63;
+				if (own && tx >= jx0 && tx <= jx1 && ty >= jy0 && ty <= jy1) {
+					if (FILL) { const uint32_t pos = start + cnt; if (pos < listCapacity) { lists[pos] = idj; } }
+					++cnt; } }
+			if (own && cnt) { row[T] = start + cnt; } }
+		__syncwarp();
+		return; }
+
 	int cx = tx0, cy = ty0;
 	uint32_t cur = valid ? static_cast<uint32_t>(cy * tilesX + cx) : 0xffffffffu;
 	while (true) {

@@ -556,7 +556,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	uint64_t totalTris = 0;
 	for (const HostDraw& hd : c->draws) { totalTris += hd.d.N; }
 	int segShift = 6;
-	while (segShift < kMaxChunkShift && (totalTris >> segShift) > 768) { ++segShift; }
+	while (segShift < kMaxChunkShift && (totalTris >> segShift) > 1536) { ++segShift; }
 	const uint32_t segLen = 1u << segShift;
 	fp.segShift = segShift;
 	// A chunk (= one warp, one row of the count matrix) holds consecutive segments: at most segLen
