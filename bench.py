@@ -33,13 +33,15 @@ SIZE = (1920, 1080)
 
 
 def make_scene(name):
+    """workloads: c2 (default, BASELINE.json configs[1]); c3 / c4 = one 1920x1080 sub-frame of the 4K
+    geometry / fill stress (the largest target the reference itself can render); c5 = 8K split-frame"""
     from rsr_b200 import scenes
-    if name == "c2":
+    if name in ("c2", "c5"):
         return scenes.BundledLikeScene(), SIZE, "c2_bundled_like_1920x1080"
     if name == "c4":
-        return scenes.FillStressScene(), SIZE, "c4_fill_stress_8layers_1920x1080_subframe"
+        return scenes.FillStressScene(layers=8, size=SIZE, quads=(2, 2)), SIZE, "c4_fill_stress_8layers_bilinear_1to1_1920x1080_subframe"
     if name == "c3":
-        return scenes.GeometryStressScene(), SIZE, "c3_geometry_stress_1920x1080_subframe"
+        return scenes.GeometryStressScene(spheres=30, divs=6, size=SIZE), SIZE, "c3_geometry_stress_2p46Mtris_1920x1080_subframe"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -128,6 +130,80 @@ def time_reference(scene, size, steps, warmup, threads=None, budget_s=25.0):
     return {"ms_per_frame": ms, "fps": 1e3 / ms, "frames": len(times), "threads": threads}
 
 
+def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flush, barrier):
+    """C5: one 7680x4320 frame = 4x4 sub-frames of 1920x1080 (the reference's guard band ends at 2048 px),
+    sub-frames dealt round-robin to the ranks, each rank resolves its sub-frames straight into a torch
+    buffer and NCCL gathers them to the presenting GPU (rank 0).  Strong scaling: the frame is fixed."""
+    from rsr_b200 import scenes
+    from rsr_b200.subframes import SubframePlan
+    plan = SubframePlan(7680, 4320, world, 1920, 1080)
+    mine = plan.owned_by(rank)
+    dev = f"cuda:{local_rank}"
+    P = scenes.perspective(45.0, 7680 / 4320, 1.0, 400.0)
+    local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
+    recs = []
+    for k, sf in enumerate(mine):
+        scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf), device_out=(local[k].data_ptr(), 1920))
+        recs.append(gpu.Finish())
+    gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
+    frame = torch.zeros((4320, 7680), dtype=torch.int32, device=dev) if rank == 0 else None
+    cur = torch.cuda.current_stream()
+
+    def step():
+        for rec in recs:
+            gpu.Submit(rec, sync=False)
+        done = torch.cuda.Event()
+        with torch.cuda.stream(stream):
+            done.record(stream)
+        cur.wait_event(done)                       # NCCL runs on torch's stream, after the render stream
+        if world > 1:
+            dist.gather(local, gathered, dst=0)
+        if rank == 0:
+            parts = gathered if world > 1 else [local]
+            for r, part in enumerate(parts):
+                for k, sf in enumerate(plan.owned_by(r)):
+                    frame[sf.y0:sf.y0 + sf.height, sf.x0:sf.x0 + sf.width].copy_(part[k])
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_ms = 0.0
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        step()
+        e1.record(cur)
+        torch.cuda.synchronize()
+        t_ms += e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    st = gpu.stats()
+    if rank == 0:
+        checksum = int(frame.to(torch.int64).sum().item())
+        line = {"metric": "frames_per_sec_8k_split_frame", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32+i32", "data": "synthetic",
+                "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
+                           "subframes_per_rank": len(mine), "exchange": "NCCL gather of resolved sub-frames to rank 0" if world > 1 else "none",
+                           "cache": "L2 flushed before every timed frame"},
+                "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks, "frame_checksum": checksum,
+                "gpu_launches": int(st["kernel_launches"]) * len(mine) * args.steps}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +258,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident leg: everything static, result stays on the device -----------------
+    if args.workload == "c5":
+        return bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flush, barrier)
+
     scene.record(gpu, size, None, t=0.0, static=True)
     resident = gpu.Finish()        # the recorded command stream of one frame; replayed every step
 
@@ -242,8 +321,8 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_fps = world * args.steps / float(t.item())
-    h2d = int(scene.groups * scene.cubes * 64 + 4096) if hasattr(scene, "groups") else 4096
-    d2h = W * H * 4
+    e2e_stats = gpu.stats()
+    h2d, d2h = e2e_stats["h2d_bytes"], e2e_stats["d2h_bytes"]
 
     if rank != 0:
         return 0
@@ -256,8 +335,8 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tile_avg_ms = sum(tile_ms) / len(tile_ms)
-    tex_texels = getattr(scene, "unique_texels", lambda s: 0)(stats)
-    vertex_bytes = getattr(scene, "vertex_record_bytes", 0)
+    tex_texels = scene.unique_texels(stats)
+    vertex_bytes = scene.vertex_record_bytes
     algo_bytes = 4 * W * H + 4 * stats["bin_entries"] + vertex_bytes + 16 * tex_texels
     achieved = algo_bytes / (tile_avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -147,6 +147,11 @@ int rsrcu_draw_arrays(rsrcu_ctx* ctx, int count, int instance_count);
 int rsrcu_store_color_tc(rsrcu_ctx* ctx, int enable_gamma, uint32_t* dst, int width, int height,
                          int stride_px);
 
+/* Same store, but the destination is DEVICE memory owned by the caller (e.g. a torch tensor that is
+ * then gathered to the presenting GPU over NCCL): the tile kernel resolves straight into it. */
+int rsrcu_store_color_tc_device(rsrcu_ctx* ctx, int enable_gamma, void* device_dst, int width, int height,
+                                int stride_px);
+
 /* CMD_STORE_COLOR_FULL_LINEAR_FP / CMD_STORE_COLOR_HALF_LINEAR_FP (rglv_gpu.cxx:156-169, :345-370):
  * RGBA32F, alpha = what the tile buffer holds (depth for RB_COLOR_DEPTH). */
 int rsrcu_store_color_fp(rsrcu_ctx* ctx, float* dst, int width, int height, int stride_px, int half);
@@ -181,6 +186,7 @@ int rsrcu_sync(rsrcu_ctx* ctx);
  *   RSRCU_OP_STORE_FP      int32 half, width, height, stride_px; uint64 ptr
  *   RSRCU_OP_STORE_DEPTH   uint64 ptr
  *   RSRCU_OP_END_FRAME     (no payload)
+ *   RSRCU_OP_STORE_TC_DEV  int32 gamma, width, height, stride_px; uint64 device ptr
  */
 #define RSRCU_OP_BEGIN_FRAME 1
 #define RSRCU_OP_STATE 2
@@ -194,6 +200,7 @@ int rsrcu_sync(rsrcu_ctx* ctx);
 #define RSRCU_OP_STORE_FP 10
 #define RSRCU_OP_STORE_DEPTH 11
 #define RSRCU_OP_END_FRAME 12
+#define RSRCU_OP_STORE_TC_DEV 13
 int rsrcu_run_stream(rsrcu_ctx* ctx, const void* stream, size_t bytes);
 
 /* ---- device-side access (viewer presents from the device-resolved buffer; bench; sharding) --- */
@@ -211,6 +218,8 @@ typedef struct RsrStats {
 	uint64_t bin_entries;           /* (triangle, tile) pairs */
 	uint64_t fragments_shaded;      /* pixels that passed coverage and depth and were written */
 	uint64_t kernel_launches;       /* kernels launched for the frame */
+	uint64_t h2d_bytes;             /* bytes copied host->device for the frame (upload arena) */
+	uint64_t d2h_bytes;             /* bytes copied device->host for the frame (store destinations) */
 } RsrStats;
 int rsrcu_get_stats(rsrcu_ctx* ctx, RsrStats* out);
 

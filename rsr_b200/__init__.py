@@ -73,7 +73,7 @@ class RsrState(C.Structure):
 
 class RsrStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("triangles_submitted", "triangles_binned", "triangles_clipped",
-                                           "bin_entries", "fragments_shaded", "kernel_launches")]
+                                           "bin_entries", "fragments_shaded", "kernel_launches", "h2d_bytes", "d2h_bytes")]
 
 
 _lib = None
@@ -110,6 +110,7 @@ def load_library():
         "rsrcu_draw_elements": [vp, ci, vp, ci, ci, ci],
         "rsrcu_draw_arrays": [vp, ci, ci],
         "rsrcu_store_color_tc": [vp, ci, vp, ci, ci, ci],
+        "rsrcu_store_color_tc_device": [vp, ci, vp, ci, ci, ci],
         "rsrcu_store_color_fp": [vp, vp, ci, ci, ci, ci],
         "rsrcu_store_depth": [vp, vp],
         "rsrcu_end_frame": [vp],
@@ -135,7 +136,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
     "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
-    "rsrcu_store_color_tc", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
@@ -146,7 +147,7 @@ def _ptr(a):
 
 
 (OP_BEGIN_FRAME, OP_STATE, OP_BIND_BUFFER, OP_BIND_TEXTURE, OP_BIND_DEPTH, OP_CLEAR, OP_DRAW_ELEMENTS,
- OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME) = range(1, 13)
+ OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME, OP_STORE_TC_DEV) = range(1, 14)
 
 
 def _addr(a) -> int:
@@ -412,6 +413,15 @@ class GPU:
                 self._check(self.L.rsrcu_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 0))
             else:
                 self._emit(OP_STORE_FP, struct.pack("<iiiiQ", 0, w, h, dst.strides[0] // 16, _addr(dst)))
+
+    def StoreColorDevice(self, device_ptr: int, stride_px: int, gamma: bool = True):
+        """true-colour resolve straight into caller-owned DEVICE memory (e.g. tensor.data_ptr())"""
+        self._flush_state()
+        w, h = self.size
+        if self.direct:
+            self._check(self.L.rsrcu_store_color_tc_device(self.h, int(bool(gamma)), C.c_void_p(device_ptr), w, h, stride_px))
+        else:
+            self._emit(OP_STORE_TC_DEV, struct.pack("<iiiiQ", int(bool(gamma)), w, h, stride_px, int(device_ptr)))
 
     def StoreDepth(self, dst):
         assert dst.dtype == np.float32 and dst.flags.c_contiguous

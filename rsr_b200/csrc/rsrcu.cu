@@ -143,6 +143,7 @@ struct rsrcu_ctx {
 	Counters* hostCounters{nullptr};   // pinned
 	RsrStats stats{};
 	uint64_t launches{0};
+	uint64_t lastH2D{0}, lastD2H{0};
 };
 
 namespace {
@@ -503,6 +504,14 @@ int rsrcu_store_color_tc(rsrcu_ctx* c, int gamma, uint32_t* dst, int width, int 
 		                                static_cast<size_t>(stridePx) * 4, static_cast<size_t>(width) * 4}); }
 	return RSRCU_OK; }
 
+int rsrcu_store_color_tc_device(rsrcu_ctx* c, int gamma, void* deviceDst, int width, int height, int stridePx) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (!deviceDst) { return fail(RSRCU_ERR_INVALID, "null device destination"); }
+	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
+	if (c->haveState && !bltProgramInstalled(c->curState.program_id)) {
+		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d", c->curState.program_id); }
+	return pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, deviceDst, stridePx, 1); }
+
 int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int stridePx, int half) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	if (half) { return fail(RSRCU_ERR_UNSUPPORTED, "CMD_STORE_COLOR_HALF_LINEAR_FP is not built yet"); }
@@ -761,7 +770,10 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	CU(cudaGetLastError());
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], st)); }
 
+	c->lastH2D = c->arenas[c->cur].used;
+	c->lastD2H = 0;
 	for (const PendingCopy& pc : c->copies) {
+		c->lastD2H += pc.rowBytes * pc.rows;
 		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, st)); }
 	CU(cudaMemcpyAsync(c->hostCounters, dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
 	c->framePending = true;
@@ -780,6 +792,8 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	c->stats.bin_entries = k.entries;
 	c->stats.fragments_shaded = k.fragments;
 	c->stats.kernel_launches = c->launches;
+	c->stats.h2d_bytes = c->lastH2D;
+	c->stats.d2h_bytes = c->lastD2H;
 	if (c->profiling) {
 		for (int i = 0; i < 6; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); }
 		// stage order of the header: vertex, setup, count, scan, fill, tile
@@ -828,6 +842,8 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 			r = rsrcu_store_color_fp(c, reinterpret_cast<float*>(u64(16)), i32(1), i32(2), i32(3), i32(0)); break;
 		case RSRCU_OP_STORE_DEPTH: if (!need(8)) { goto bad; } r = rsrcu_store_depth(c, reinterpret_cast<float*>(u64(0))); break;
 		case RSRCU_OP_END_FRAME: r = rsrcu_end_frame(c); break;
+		case RSRCU_OP_STORE_TC_DEV: if (!need(24)) { goto bad; }
+			r = rsrcu_store_color_tc_device(c, i32(0), reinterpret_cast<void*>(u64(16)), i32(1), i32(2), i32(3)); break;
 		default: return fail(RSRCU_ERR_INVALID, "unknown stream opcode %u", op); }
 		if (r != RSRCU_OK) { return r; }
 		p += size;

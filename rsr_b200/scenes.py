@@ -179,22 +179,20 @@ def icosphere(divs: int, radius: float = 1.0):
     return pos, nrm, f.astype(np.int32)
 
 
-def split_mesh_u16(pos, nrm, faces, max_verts=32768):
-    """split an indexed mesh into hunks addressable with uint16 indices (re-indexed per hunk)"""
-    hunks = []
-    nf = len(faces)
-    start = 0
-    per = max(1, nf // max(1, int(np.ceil(pos.shape[1] * 1.3 / max_verts))))
-    while start < nf:
+def split_mesh_u16(pos, nrm, faces, max_verts=32768, hunks=4):
+    """split an indexed mesh into `hunks` spatially coherent pieces addressable with uint16 indices
+    (faces sorted by centroid longitude, re-indexed per piece)"""
+    cen = pos[:, faces].mean(axis=2)                       # (3, M)
+    order = np.argsort(np.arctan2(cen[2], cen[0]), kind="stable")
+    faces = faces[order]
+    out = []
+    per = -(-len(faces) // hunks)
+    for start in range(0, len(faces), per):
         sub = faces[start:start + per]
         used, inv = np.unique(sub.ravel(), return_inverse=True)
-        while len(used) > max_verts:
-            per = per // 2
-            sub = faces[start:start + per]
-            used, inv = np.unique(sub.ravel(), return_inverse=True)
-        hunks.append((pos[:, used].copy(), nrm[:, used].copy(), inv.astype(np.uint16)))
-        start += len(sub)
-    return hunks
+        assert len(used) <= max_verts, "hunk needs more than uint16-addressable vertices; raise `hunks`"
+        out.append((pos[:, used].copy(), nrm[:, used].copy(), inv.astype(np.uint16)))
+    return out
 
 
 def hash_texture(dim: int, seed: int, tex_id: int = 0) -> np.ndarray:
@@ -354,6 +352,11 @@ class BundledLikeScene:
         self.triangles = (len(self.m_idx) // 3) * 2 + field * field * 2 + groups * cubes * (len(cidx) // 3)
         self.draws = 2 + field * field + groups
         self.mats = self.instance_matrices(0.0)
+        self.vertex_record_bytes = 48 * (groups * cubes * cp.shape[1] + field * field * 4) + 80 * 2 * p.shape[1]
+
+    def unique_texels(self, stats):
+        """upper bound used for the roofline: the two 512^2 base levels"""
+        return 2 * 512 * 512
 
     def instance_matrices(self, t):
         """per-frame CPU work of the $many node (node/many.cxx:188-226): rebuild instance matrices"""
@@ -377,9 +380,10 @@ class BundledLikeScene:
             out.append(a16)
         return out
 
-    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True):
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True, device_out=None):
         """static=True marks every buffer immutable (device-resident bench leg); otherwise the
-        instance matrices are rebuilt and re-uploaded each frame like the reference's $many node"""
+        instance matrices are rebuilt and re-uploaded each frame like the reference's $many node.
+        device_out=(device pointer, stride px): resolve into caller-owned device memory instead"""
         w, h = size
         up = {"upload": 1} if hasattr(gl, "stats") else {}
         dyn = up if static else {}
@@ -427,7 +431,11 @@ class BundledLikeScene:
                 gl.BindTexture(0, self.tex[k], 512, 512, 512, GL_LINEAR_MIPMAP_NEAREST, **up)
                 gl.ViewMatrix(translate((i - n / 2) * 1.0 + ox, (j - n / 2) * 0.55 + oy - 1.0, -30.0 - 0.01 * (i + j)) @ scale(0.9, 0.5, 1.0))
                 gl.DrawElements(6, self.q_idx, 0, **up)
-        finish(gl, out, gamma, depth)
+        if device_out is not None:
+            gl.UseProgram(PROGRAM_DEFAULT_POST)
+            gl.StoreColorDevice(device_out[0], device_out[1], gamma)
+        else:
+            finish(gl, out, gamma, depth)
 
 
 class SoupScene:
@@ -519,3 +527,100 @@ class SoupScene:
         if fp_out is not None:
             gl.StoreColor(fp_out)
         gl.StoreColor(out, gamma)
+
+
+class FillStressScene:
+    """C4: `layers` full-screen layers drawn back to front (every fragment passes LESS and is shaded),
+    each layer a grid of quads, every quad bound to its own distinct 1024^2 mip-mapped RGBA32F texture
+    sampled 1 texel : 1 pixel with bilinear filtering (program Amy).  No texel is reused across
+    quads, so texture traffic really comes from HBM.  `size` is one <= 2048 px (sub-)frame."""
+
+    def __init__(self, layers=8, size=(1920, 1080), quads=(2, 2), seed=11, tex_dim=1024, front_to_back=False):
+        self.layers, self.size, self.quads, self.tex_dim = layers, size, quads, tex_dim
+        w, h = size
+        qw, qh = w // quads[0], h // quads[1]
+        assert qw <= tex_dim and qh <= tex_dim
+        self.items = []
+        for layer in range(layers):
+            for qy in range(quads[1]):
+                for qx in range(quads[0]):
+                    x0, y0 = qx * qw, qy * qh
+                    z = -(2.0 + layer) if front_to_back else -(2.0 + (layers - 1 - layer))
+                    pos = np.array([[x0, x0 + qw, x0 + qw, x0], [y0, y0, y0 + qh, y0 + qh], [z, z, z, z]], np.float32)
+                    uv = np.array([[0, qw / tex_dim, qw / tex_dim, 0], [0, 0, qh / tex_dim, qh / tex_dim]], np.float32)
+                    tid = len(self.items)
+                    tex = make_mipmap(hash_texture(tex_dim, seed, tid))
+                    self.items.append((soa(pos), soa(uv), tex))
+        self.idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+        self.triangles = 2 * len(self.items)
+        self.draws = len(self.items)
+        self.vertex_record_bytes = 48 * 4 * len(self.items)
+
+    def unique_texels(self, stats):
+        # 1:1 mapping by construction: every shaded fragment touches its own texel (+ shared borders)
+        return self.layers * self.size[0] * self.size[1]
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), static=False, gamma=True):
+        assert tuple(size) == tuple(self.size)
+        w, h = size
+        up = {"upload": 1} if hasattr(gl, "stats") else {}
+        begin(gl, size, clear=(0.0, 0.0, 0.0), tile_blocks=tile_blocks)
+        gl.UseProgram(PROGRAM_AMY)
+        gl.ViewMatrix(np.eye(4, dtype=np.float32))
+        gl.ProjectionMatrix(orthographic(0, w, 0, h, 1.0, 20.0))
+        for pos, uv, tex in self.items:
+            gl.UseBuffer(0, pos, **up)
+            gl.UseBuffer(9, uv, **up)
+            gl.BindTexture(0, tex, self.tex_dim, self.tex_dim, self.tex_dim, GL_LINEAR_MIPMAP_NEAREST, **up)
+            gl.DrawElements(6, self.idx, 0, **up)
+        finish(gl, out, gamma, depth)
+
+
+class GeometryStressScene:
+    """C3: a field of finely subdivided icospheres, each triangle ~1 pixel, back faces culled, program
+    Amy with uv = normal.xy; sphere centres from a fixed seed.  The mesh is split into uint16-indexable
+    hunks (<= 32768 vertices each) like the reference's 4-hunk icosphere (rglv_icosphere.cxx:16-145)."""
+
+    def __init__(self, spheres=30, divs=6, seed=7, size=(1920, 1080), radius_px=90.0, tex_dim=256):
+        p, n, f = icosphere(divs, 1.0)
+        self.hunks = []
+        for hp, hn, hidx in split_mesh_u16(p, n, f, 32768):
+            self.hunks.append((soa(hp), soa(hn), soa(hn[:2] * 0.5 + 0.5), hidx))
+        rng = np.random.default_rng(seed)
+        self.size = size
+        self.fov, self.zn, self.zf = 45.0, 1.0, 400.0
+        w, h = size
+        # world radius that projects to radius_px at depth z:  r = radius_px * 2 z tan(fov/2) / h
+        self.centres = []
+        for _ in range(spheres):
+            z = rng.uniform(20.0, 120.0)
+            r = radius_px * 2 * z * np.tan(np.radians(self.fov) / 2) / h
+            half_h = z * np.tan(np.radians(self.fov) / 2)
+            half_w = half_h * w / h
+            self.centres.append((rng.uniform(-half_w, half_w), rng.uniform(-half_h, half_h), -z, r, rng.uniform(0, 6.28)))
+        self.tex = make_mipmap(hash_texture(tex_dim, seed))
+        self.tex_dim = tex_dim
+        self.triangles = spheres * len(f)
+        self.draws = spheres * len(self.hunks)
+        self.vertex_record_bytes = 48 * spheres * p.shape[1]
+
+    def unique_texels(self, stats):
+        return min(stats["fragments_shaded"], self.tex_dim * self.tex_dim * 4 // 3)
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True):
+        w, h = size
+        up = {"upload": 1} if hasattr(gl, "stats") else {}
+        begin(gl, size, clear=(0.02, 0.02, 0.05), tile_blocks=tile_blocks)
+        gl.UseProgram(PROGRAM_AMY)
+        gl.Enable(GL_CULL_FACE)
+        gl.CullFace(GL_BACK)
+        gl.ProjectionMatrix(perspective(self.fov, w / h, self.zn, self.zf) if proj is None else proj)
+        gl.BindTexture(0, self.tex, self.tex_dim, self.tex_dim, self.tex_dim, GL_LINEAR_MIPMAP_NEAREST, **up)
+        for (cx, cy, cz, r, ang) in self.centres:
+            gl.ViewMatrix(translate(cx, cy, cz) @ rotate(ang + 0.2 * t, 0.3, 1.0, 0.1) @ scale(r))
+            for hp, hn, huv, hidx in self.hunks:
+                gl.UseBuffer(0, hp, **up)
+                gl.UseBuffer(3, hn, **up)
+                gl.UseBuffer(9, huv, **up)
+                gl.DrawElements(len(hidx), hidx, 0, **up)
+        finish(gl, out, gamma, depth)
