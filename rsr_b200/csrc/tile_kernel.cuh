@@ -49,6 +49,7 @@ struct TileShared {
 	float iw[3][kBatch];
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
+	uint16_t queue[kTileThreads / 32][64];   // per-warp (triangle, quad) work items awaiting shading
 	uint32_t drawIdBase[kSmemDraws];     // idBase of the first kSmemDraws draws (id -> draw lookup)
 	int firstBad;
 };
@@ -284,50 +285,106 @@ __device__ __forceinline__ int find_draw_of_id(const TileShared& sh, const TileA
 			if (A.draws[mid].idBase <= id) { lo = mid; } else { hi = mid - 1; } } }
 	return lo; }
 
-// rasterises the nb triangles that setup_triangle placed in shared memory, in order
+// edge functions of triangle ti at the four pixels of the quad whose tile-local origin is (lx, ly);
+// returns the coverage mask (bit l = lane l inside all three edges); 0 if the quad is outside the
+// triangle's bbox (the reference never visits it)
+__device__ __forceinline__ uint32_t quad_coverage(const TileShared& sh, int ti, int lx, int ly, int (&e1)[4], int (&e2)[4]) {
+	const uint32_t bb = sh.bbox[ti];
+	const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+	if (lx < minx || lx >= maxx || ly < miny || ly >= maxy) { return 0; }
+	const uint32_t ulx = lx, uly = ly;
+	const uint32_t dy1 = sh.edy[0][ti], dx1 = sh.edx[0][ti];
+	const uint32_t dy2 = sh.edy[1][ti], dx2 = sh.edx[1][ti];
+	const uint32_t dy3 = sh.edy[2][ti], dx3 = sh.edx[2][ti];
+	const uint32_t a1 = static_cast<uint32_t>(sh.ec[0][ti]) + ulx * dy1 + uly * dx1;
+	const uint32_t a2 = static_cast<uint32_t>(sh.ec[1][ti]) + ulx * dy2 + uly * dx2;
+	const uint32_t a3 = static_cast<uint32_t>(sh.ec[2][ti]) + ulx * dy3 + uly * dx3;
+	const uint32_t q1[4] = { a1, a1 + dy1, a1 + dx1, a1 + dx1 + dy1 };
+	const uint32_t q2[4] = { a2, a2 + dy2, a2 + dx2, a2 + dx2 + dy2 };
+	const uint32_t q3[4] = { a3, a3 + dy3, a3 + dx3, a3 + dx3 + dy3 };
+	uint32_t covered = 0;
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+		e1[l] = static_cast<int>(q1[l]);
+		e2[l] = static_cast<int>(q2[l]);
+		if (static_cast<int>(q1[l] | q2[l] | q3[l]) >= 0) { covered |= (1u << l); } }
+	return covered; }
+
+// Rasterises the nb triangles that setup_triangle placed in shared memory, in order.
+//
+// Each warp owns a 16x8-pixel region (32 quads, quad q "belongs" to lane q).  Coverage and shading
+// are decoupled so that small triangles do not leave 30 of 32 lanes idle while one quad is shaded:
+//   produce  for each triangle whose bbox touches the region (ballot), every lane tests its own
+//            quad; covered quads are appended, in triangle order, to a per-warp queue of
+//            (triangle, quad) work items;
+//   consume  whenever 32 items are queued (or at the end) lane i shades item i -- any triangle, any
+//            quad of the region.  Items aimed at the same quad must retire in queue order
+//            (depth LESS ties, blending): __match_any_sync groups them and the group is replayed
+//            rank by rank.  With little overdraw inside 32 consecutive items that is one pass.
 template <class P>
 __device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
-	// warp region: 16x8 pixels = 8x4 quads; 2 regions across, 4 down
-	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
-	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;   // tile-local quad origin
+	const unsigned ltMask = (1u << lane) - 1u;
+	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;            // region origin (tile-local)
+	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;   // own quad origin
+	uint16_t* queue = sh.queue[warp];
 	unsigned frags = 0;
-	for (int k = 0; k < nb; k += 32) {
-		const int i = k + lane;
-		bool hit = false;
-		if (i < nb) {
-			const uint32_t bb = sh.bbox[i];
-			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
-			hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
-		unsigned m = __ballot_sync(0xffffffffu, hit);
-		while (m) {
-			const int j = __ffs(m) - 1;
-			m &= m - 1;
-			const int ti = k + j;
-			const uint32_t bb = sh.bbox[ti];
-			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
-			if (lx < minx || lx >= maxx || ly < miny || ly >= maxy) { continue; }
+	int qn = 0;            // queued items
+	int k = 0, kbase = 0;  // next triangle group / base of the current one
+	unsigned pending = 0;  // triangles of the current group that touch the region, not yet tested
+
+	while (true) {
+		// ---- produce ------------------------------------------------------------------------
+		while (qn < 32) {
+			if (pending == 0) {
+				if (k >= nb) { break; }
+				const int i = k + lane;
+				bool hit = false;
+				if (i < nb) {
+					const uint32_t bb = sh.bbox[i];
+					const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+					hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+				pending = __ballot_sync(0xffffffffu, hit);
+				kbase = k;
+				k += 32;
+				continue; }
+			const int j = __ffs(pending) - 1;
+			pending &= pending - 1;
+			const int ti = kbase + j;
 			int e1[4], e2[4];
-			uint32_t covered = 0;
-			{
-				const uint32_t ulx = lx, uly = ly;
-				const uint32_t dy1 = sh.edy[0][ti], dx1 = sh.edx[0][ti];
-				const uint32_t dy2 = sh.edy[1][ti], dx2 = sh.edx[1][ti];
-				const uint32_t dy3 = sh.edy[2][ti], dx3 = sh.edx[2][ti];
-				const uint32_t a1 = static_cast<uint32_t>(sh.ec[0][ti]) + ulx * dy1 + uly * dx1;
-				const uint32_t a2 = static_cast<uint32_t>(sh.ec[1][ti]) + ulx * dy2 + uly * dx2;
-				const uint32_t a3 = static_cast<uint32_t>(sh.ec[2][ti]) + ulx * dy3 + uly * dx3;
-				const uint32_t q1[4] = { a1, a1 + dy1, a1 + dx1, a1 + dx1 + dy1 };
-				const uint32_t q2[4] = { a2, a2 + dy2, a2 + dx2, a2 + dx2 + dy2 };
-				const uint32_t q3[4] = { a3, a3 + dy3, a3 + dx3, a3 + dx3 + dy3 };
-#pragma unroll
-				for (int l = 0; l < 4; ++l) {
-					e1[l] = static_cast<int>(q1[l]);
-					e2[l] = static_cast<int>(q2[l]);
-					if (static_cast<int>(q1[l] | q2[l] | q3[l]) >= 0) { covered |= (1u << l); } } }
-			if (covered == 0) { continue; }
-			frags += render_quad<P>(sh, t, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (bb >> 24) & 1u); } }
+			const bool covered = quad_coverage(sh, ti, lx, ly, e1, e2) != 0;
+			const unsigned cm = __ballot_sync(0xffffffffu, covered);
+			if (cm) {
+				if (covered) { queue[qn + __popc(cm & ltMask)] = static_cast<uint16_t>((ti << 5) | lane); }
+				qn += __popc(cm);
+				__syncwarp(); } }
+		if (qn == 0) { break; }
+
+		// ---- consume up to 32 items ------------------------------------------------------------
+		const int n = min(qn, 32);
+		const bool have = lane < n;
+		const unsigned item = have ? queue[lane] : 0u;
+		const int ti = static_cast<int>(item >> 5), ql = static_cast<int>(item & 31u);
+		const unsigned peers = __match_any_sync(0xffffffffu, have ? ql : (32 + lane));
+		const int rank = __popc(peers & ltMask);
+		const int maxRank = static_cast<int>(__reduce_max_sync(0xffffffffu, have ? static_cast<unsigned>(rank) : 0u));
+		const int qx = rx + (ql & 7) * 2, qy = ry + (ql >> 3) * 2;
+		for (int r = 0; r <= maxRank; ++r) {
+			if (have && rank == r) {
+				int e1[4], e2[4];
+				const uint32_t covered = quad_coverage(sh, ti, qx, qy, e1, e2);
+				frags += render_quad<P>(sh, warp * 32 + ql, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + qx, oy + qy,
+				                        (sh.bbox[ti] >> 24) & 1u); }
+			__syncwarp(); }
+		// keep the items that did not fit
+		const int rest = qn - n;
+		unsigned carry = 0;
+		if (lane < rest) { carry = queue[32 + lane]; }
+		__syncwarp();
+		if (lane < rest) { queue[lane] = static_cast<uint16_t>(carry); }
+		__syncwarp();
+		qn = rest; }
 	return frags; }
 
 // sRGB::to_tc / LinearColor::to_tc (rglr_canvas_util.hxx:15-62, ryg-srgb.h:183-223)
