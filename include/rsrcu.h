@@ -105,6 +105,11 @@ const char* rsrcu_last_error(void);
 int rsrcu_set_host_luts(rsrcu_ctx* ctx, const uint32_t* rcp2048, const uint32_t* rsqrt2x1024);
 int rsrcu_get_host_luts(rsrcu_ctx* ctx, uint32_t* rcp2048, uint32_t* rsqrt2x1024);
 
+/* Drops every RSRCU_UPLOAD_STATIC allocation (device copies of meshes / textures).  Static data is
+ * keyed by host pointer + byte size and must stay alive and unchanged while cached; call this
+ * before freeing or rewriting such memory. */
+int rsrcu_release_static(rsrcu_ctx* ctx);
+
 /* ---- frame recording: one call per reference stream command ---------------------------------- */
 
 /* GPU::Reset (rglv_gpu.cxx:50-56).  tile_*_blocks are the reference's tile size in 8x8 blocks

@@ -101,6 +101,7 @@ def load_library():
         "rsrcu_destroy": [vp],
         "rsrcu_set_host_luts": [vp, vp, vp],
         "rsrcu_get_host_luts": [vp, vp, vp],
+        "rsrcu_release_static": [vp],
         "rsrcu_begin_frame": [vp, ci, ci, ci, ci],
         "rsrcu_set_state": [vp, C.POINTER(RsrState)],
         "rsrcu_bind_buffer": [vp, ci, vp, sz, ci],
@@ -134,7 +135,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
-    "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
+    "rsrcu_release_static", "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
     "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_run_stream",
@@ -185,11 +186,23 @@ class GPU:
         self.device = device
         self.direct = direct
         self._keep = []
+        self._static = {}   # address -> array: pins RSRCU_UPLOAD_STATIC memory so the address cannot be recycled
         self._rec = bytearray()
         self._state = RsrState()
         self._reset_state()
         self._dirty = True
         self.size = (0, 0)
+
+    def _hold(self, arr, upload):
+        if upload == UPLOAD_STATIC:
+            self._static[arr.ctypes.data] = arr
+        else:
+            self._keep.append(arr)
+
+    def release_static(self):
+        """forget every cached static upload (and let the pinned host arrays go)"""
+        self._check(self.L.rsrcu_release_static(self.h))
+        self._static.clear()
 
     # -- plumbing -------------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -328,7 +341,7 @@ class GPU:
                     self.UseBuffer(slot + i, a[i], upload)
                 return
             arr = np.ascontiguousarray(a, dtype=np.float32)
-            self._keep.append(arr)
+            self._hold(arr, upload)
         n = 0 if arr is None else arr.size
         if self.direct:
             self._check(self.L.rsrcu_bind_buffer(self.h, slot, _ptr(arr), n, upload))
@@ -347,7 +360,7 @@ class GPU:
     def BindTexture(self, unit, texels, width, height, stride, mode, upload=UPLOAD_ALWAYS):
         t = np.ascontiguousarray(texels, dtype=np.float32)
         rows = t.size // (4 * stride)
-        self._keep.append(t)
+        self._hold(t, upload)
         if self.direct:
             self._check(self.L.rsrcu_bind_texture(self.h, unit, _ptr(t), width, height, stride, mode, rows, upload))
         else:
@@ -355,7 +368,7 @@ class GPU:
 
     def BindTexture3(self, depth, dim, upload=UPLOAD_ALWAYS):
         t = np.ascontiguousarray(depth, dtype=np.float32)
-        self._keep.append(t)
+        self._hold(t, upload)
         if self.direct:
             self._check(self.L.rsrcu_bind_depth_texture(self.h, _ptr(t), dim, upload))
         else:
@@ -370,7 +383,7 @@ class GPU:
 
     def _draw_elements(self, count, indices, hint, instances, upload):
         idx = np.ascontiguousarray(indices, dtype=np.uint16)
-        self._keep.append(idx)
+        self._hold(idx, upload)
         self._flush_state()
         if self.direct:
             self._check(self.L.rsrcu_draw_elements(self.h, int(count), _ptr(idx), int(hint), int(instances), upload))

@@ -340,6 +340,14 @@ int rsrcu_get_host_luts(rsrcu_ctx* c, uint32_t* rcp2048, uint32_t* rsqrt2x1024) 
 	std::memcpy(rsqrt2x1024, c->hostLuts.rsqrt, sizeof(c->hostLuts.rsqrt));
 	return RSRCU_OK; }
 
+int rsrcu_release_static(rsrcu_ctx* c) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
+	c->staticCache.clear();
+	return RSRCU_OK; }
+
 int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int tileHBlocks) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	if (width <= 0 || height <= 0 || (width & 1) || (height & 1)) {

@@ -97,3 +97,27 @@ def test_submission_order_decides_equal_depth(cuda_gpu, ref_gpu):
     sc.record(cuda_gpu, (640, 360), a); cuda_gpu.Run()
     sc.record(ref_gpu, (640, 360), b); ref_gpu.Run()
     assert np.array_equal(a, b)
+
+
+def test_static_uploads_pin_their_host_memory(cuda_gpu):
+    """RSRCU_UPLOAD_STATIC is keyed by host pointer + size: the Python mirror must keep such arrays alive,
+    or a recycled address would silently serve stale vertices (regression)"""
+    frames = []
+    for z in (-3.0, -6.0):
+        q = scenes.soa(np.array([[-1, 1, 1, -1], [-1, -1, 1, 1], [z, z, z, z]], np.float32))
+        uv = scenes.soa(np.array([[0, 1, 1, 0], [0, 0, 1, 1]], np.float32))
+        tex = scenes.make_mipmap(scenes.hash_texture(16, 3))
+        out = np.zeros((180, 320), np.uint32)
+        scenes.begin(cuda_gpu, (320, 180))
+        cuda_gpu.UseProgram(R.PROGRAM_AMY)
+        cuda_gpu.ProjectionMatrix(scenes.perspective(45.0, 320 / 180, 1, 20))
+        cuda_gpu.UseBuffer(0, q, upload=R.UPLOAD_STATIC)
+        cuda_gpu.UseBuffer(9, uv, upload=R.UPLOAD_STATIC)
+        cuda_gpu.BindTexture(0, tex, 16, 16, 16, R.GL_NEAREST_MIPMAP_NEAREST, upload=R.UPLOAD_STATIC)
+        cuda_gpu.DrawElements(6, np.array([0, 1, 2, 0, 2, 3], np.uint16), 0)
+        scenes.finish(cuda_gpu, out)
+        cuda_gpu.Run()
+        frames.append(out)
+        del q, uv, tex
+    bg = frames[0][0, 0]
+    assert np.count_nonzero(frames[0] != bg) > 2 * np.count_nonzero(frames[1] != bg) > 0
