@@ -49,7 +49,7 @@ struct TileShared {
 	float iw[3][kBatch];
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
-	uint16_t queue[kTileThreads / 32][64];   // per-warp (triangle, quad) work items awaiting shading
+	uint16_t queue[kTileThreads / 32][160];   // per-warp (triangle, quad) work items awaiting shading
 	uint32_t drawIdBase[kSmemDraws];     // idBase of the first kSmemDraws draws (id -> draw lookup)
 	int firstBad;
 };
@@ -330,9 +330,12 @@ __device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, i
 	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;   // own quad origin
 	uint16_t* queue = sh.queue[warp];
 	unsigned frags = 0;
-	int qn = 0;            // queued items
-	int k = 0, kbase = 0;  // next triangle group / base of the current one
-	unsigned pending = 0;  // triangles of the current group that touch the region, not yet tested
+	int qn = 0;              // queued items
+	int k = 0, kbase = 0;    // next triangle group / base of the current one
+	unsigned pending = 0;    // triangles of the current group that touch the region, not yet tested
+	unsigned smallMask = 0;  // ... of which the part inside the region is at most 2x2 quads
+	// bbox of triangle (kbase + lane) clipped to the region, in region quad units (valid if pending bit set)
+	int bqx0 = 0, bqy0 = 0, bqx1 = 0, bqy1 = 0;
 
 	while (true) {
 		// ---- produce ------------------------------------------------------------------------
@@ -340,16 +343,49 @@ __device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, i
 			if (pending == 0) {
 				if (k >= nb) { break; }
 				const int i = k + lane;
-				bool hit = false;
+				bool hit = false, small = false;
 				if (i < nb) {
 					const uint32_t bb = sh.bbox[i];
 					const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
-					hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+					hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry);
+					if (hit) {
+						bqx0 = (max(minx, rx) - rx) >> 1; bqx1 = (min(maxx, rx + 16) - 1 - rx) >> 1;
+						bqy0 = (max(miny, ry) - ry) >> 1; bqy1 = (min(maxy, ry + 8) - 1 - ry) >> 1;
+						small = (bqx1 - bqx0 <= 1) && (bqy1 - bqy0 <= 1); } }
 				pending = __ballot_sync(0xffffffffu, hit);
+				smallMask = __ballot_sync(0xffffffffu, small);
 				kbase = k;
 				k += 32;
 				continue; }
 			const int j = __ffs(pending) - 1;
+			if ((smallMask >> j) & 1u) {
+				// run of small triangles: one lane per triangle, each tests its <= 2x2 quads
+				const unsigned large = pending & ~smallMask;
+				const unsigned run = large ? (pending & ((1u << (__ffs(large) - 1)) - 1u)) : pending;
+				pending &= ~run;
+				const bool mine = (run >> lane) & 1u;
+				const int ti = kbase + lane;
+				unsigned cov = 0;   // bit c: candidate quad c = (dy*2 + dx) of the 2x2 block is covered
+				if (mine) {
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const int qx = bqx0 + (c & 1), qy = bqy0 + (c >> 1);
+						if (qx <= bqx1 && qy <= bqy1) {
+							int e1[4], e2[4];
+							if (quad_coverage(sh, ti, rx + qx * 2, ry + qy * 2, e1, e2)) { cov |= 1u << c; } } } }
+				const int cnt = __popc(cov);
+				int incl = cnt;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) { incl += v; } }
+				int pos = qn + incl - cnt;
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					if ((cov >> c) & 1u) {
+						const int ql = (bqy0 + (c >> 1)) * 8 + bqx0 + (c & 1);
+						queue[pos++] = static_cast<uint16_t>((ti << 5) | ql); } }
+				qn += __shfl_sync(0xffffffffu, incl, 31);
+				__syncwarp();
+				continue; }
 			pending &= pending - 1;
 			const int ti = kbase + j;
 			int e1[4], e2[4];
@@ -377,13 +413,14 @@ __device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, i
 				frags += render_quad<P>(sh, warp * 32 + ql, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + qx, oy + qy,
 				                        (sh.bbox[ti] >> 24) & 1u); }
 			__syncwarp(); }
-		// keep the items that did not fit
+		// keep the items that did not fit (the queue holds at most 31 + 128)
 		const int rest = qn - n;
-		unsigned carry = 0;
-		if (lane < rest) { carry = queue[32 + lane]; }
-		__syncwarp();
-		if (lane < rest) { queue[lane] = static_cast<uint16_t>(carry); }
-		__syncwarp();
+		for (int base = 0; base < rest; base += 32) {
+			unsigned carry = 0;
+			if (base + lane < rest) { carry = queue[32 + base + lane]; }
+			__syncwarp();
+			if (base + lane < rest) { queue[base + lane] = static_cast<uint16_t>(carry); }
+			__syncwarp(); }
 		qn = rest; }
 	return frags; }
 
