@@ -322,7 +322,7 @@ __device__ __forceinline__ uint32_t quad_coverage(const TileShared& sh, int ti, 
 //            (depth LESS ties, blending): __match_any_sync groups them and the group is replayed
 //            rank by rank.  With little overdraw inside 32 consecutive items that is one pass.
 template <class P>
-__device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
+__device__ __noinline__ unsigned draw_batch_queued(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
@@ -423,6 +423,38 @@ __device__ __noinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, i
 			__syncwarp(); }
 		qn = rest; }
 	return frags; }
+
+// Direct variant: every lane tests and shades its own quad, triangle by triangle.  No queue
+// traffic; best when triangles are large (most lanes covered) or the batch is short.
+template <class P>
+__device__ __noinline__ unsigned draw_batch_direct(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
+	const int t = threadIdx.x;
+	const int warp = t >> 5, lane = t & 31;
+	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
+	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;
+	unsigned frags = 0;
+	for (int k = 0; k < nb; k += 32) {
+		const int i = k + lane;
+		bool hit = false;
+		if (i < nb) {
+			const uint32_t bb = sh.bbox[i];
+			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
+			hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+		unsigned m = __ballot_sync(0xffffffffu, hit);
+		while (m) {
+			const int j = __ffs(m) - 1;
+			m &= m - 1;
+			const int ti = k + j;
+			int e1[4], e2[4];
+			const uint32_t covered = quad_coverage(sh, ti, lx, ly, e1, e2);
+			if (covered == 0) { continue; }
+			frags += render_quad<P>(sh, t, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
+	return frags; }
+
+// picks the variant per batch: long batches of small triangles go through the work queue
+template <class P>
+__device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, int nb, int ox, int oy, bool queued) {
+	return queued ? draw_batch_queued<P>(sh, A, nb, ox, oy) : draw_batch_direct<P>(sh, A, nb, ox, oy); }
 
 // sRGB::to_tc / LinearColor::to_tc (rglr_canvas_util.hxx:15-62, ryg-srgb.h:183-223)
 __device__ __forceinline__ uint32_t srgb8(float f) {
@@ -542,23 +574,27 @@ tile_kernel(TileArgs A) {
 			if (myDraw >= bound || A.draws[myDraw].batchKey != key0) { atomicMin(&sh.firstBad, t); } }
 		__syncthreads();
 		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
+		bool tiny = false;
 		if (t < nb) {
 			const DevDraw& d = A.draws[myDraw];
 			sh.state[t] = static_cast<uint16_t>(d.state);
-			setup_triangle(sh, t, myId, d, A, ox, oy, rl, rt, rr, rb); }
-		__syncthreads();
+			setup_triangle(sh, t, myId, d, A, ox, oy, rl, rt, rr, rb);
+			const uint32_t bb = sh.bbox[t];
+			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
+		// (this barrier also publishes the setup records)
+		const bool queued = nb >= 96 && __syncthreads_count(tiny) * 2 > nb;
 		switch (key0 & 0xffu) {
-		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, nb, ox, oy); break;
-		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, nb, ox, oy); break;
-		case ProgText::id:         frags += draw_batch<ProgText>(sh, A, nb, ox, oy); break;
-		case ProgDepth::id:        frags += draw_batch<ProgDepth>(sh, A, nb, ox, oy); break;
-		case ProgPattern::id:      frags += draw_batch<ProgPattern>(sh, A, nb, ox, oy); break;
-		case ProgMany::id:         frags += draw_batch<ProgMany>(sh, A, nb, ox, oy); break;
-		case ProgOBJ1::id:         frags += draw_batch<ProgOBJ1>(sh, A, nb, ox, oy); break;
-		case ProgOBJ2::id:         frags += draw_batch<ProgOBJ2>(sh, A, nb, ox, oy); break;
-		case ProgOBJ2S::id:        frags += draw_batch<ProgOBJ2S>(sh, A, nb, ox, oy); break;
-		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, nb, ox, oy); break;
-		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, nb, ox, oy); break;
+		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, nb, ox, oy, queued); break;
+		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, nb, ox, oy, queued); break;
+		case ProgText::id:         frags += draw_batch<ProgText>(sh, A, nb, ox, oy, queued); break;
+		case ProgDepth::id:        frags += draw_batch<ProgDepth>(sh, A, nb, ox, oy, queued); break;
+		case ProgPattern::id:      frags += draw_batch<ProgPattern>(sh, A, nb, ox, oy, queued); break;
+		case ProgMany::id:         frags += draw_batch<ProgMany>(sh, A, nb, ox, oy, queued); break;
+		case ProgOBJ1::id:         frags += draw_batch<ProgOBJ1>(sh, A, nb, ox, oy, queued); break;
+		case ProgOBJ2::id:         frags += draw_batch<ProgOBJ2>(sh, A, nb, ox, oy, queued); break;
+		case ProgOBJ2S::id:        frags += draw_batch<ProgOBJ2S>(sh, A, nb, ox, oy, queued); break;
+		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, nb, ox, oy, queued); break;
+		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, nb, ox, oy, queued); break;
 		default: break; }
 		cursor += static_cast<uint32_t>(max(nb, 1)); }
 
