@@ -582,7 +582,8 @@ tile_kernel(TileArgs A) {
 			const uint32_t bb = sh.bbox[t];
 			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
 		// (this barrier also publishes the setup records)
-		const bool queued = nb >= 96 && __syncthreads_count(tiny) * 2 > nb;
+		const int ntiny = __syncthreads_count(tiny);
+		const bool queued = nb >= 96 && ntiny * 2 > nb;
 		switch (key0 & 0xffu) {
 		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, nb, ox, oy, queued); break;
 		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, nb, ox, oy, queued); break;
