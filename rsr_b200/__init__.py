@@ -116,6 +116,7 @@ def load_library():
         "rsrcu_store_depth": [vp, vp],
         "rsrcu_end_frame": [vp],
         "rsrcu_sync": [vp],
+        "rsrcu_sync_frame": [vp, ci],
         "rsrcu_run_stream": [vp, vp, sz],
         "rsrcu_device_truecolor": [vp, C.POINTER(vp), C.POINTER(ci)],
         "rsrcu_stream": [vp, C.POINTER(vp)],
@@ -138,7 +139,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_release_static", "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
     "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
-    "rsrcu_run_stream",
+    "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
 
@@ -287,6 +288,10 @@ class GPU:
 
     def Sync(self):
         self._check(self.L.rsrcu_sync(self.h))
+
+    def SyncFrame(self, lag: int = 1):
+        """wait until the frame `lag` submissions ago has landed in its store destinations"""
+        self._check(self.L.rsrcu_sync_frame(self.h, lag))
 
     # -- rglv::GL -------------------------------------------------------------------------------
     def _cap(self, cap, value):

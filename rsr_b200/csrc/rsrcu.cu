@@ -104,6 +104,10 @@ struct HostDraw {
 struct rsrcu_ctx {
 	int device{0};
 	cudaStream_t stream{nullptr};
+	cudaStream_t copyStream{nullptr};   // device->host copies of finished frames overlap the next frame's kernels
+	cudaEvent_t evRendered{nullptr};
+	cudaEvent_t evCopied[2]{};
+	int outSlot{0};                     // store targets are double-buffered
 	cudaEvent_t evStage[8]{};
 	bool profiling{false};
 	float stageMs[7]{};
@@ -136,11 +140,11 @@ struct rsrcu_ctx {
 
 	// device work buffers
 	DevBuf ptvb, vflags, triInfo, clipRecs, segActive, counts, gsum, tileBase, tileCount, lists, counters;
-	DevBuf tcOut, fpOut, depthOut;
+	DevBuf tcOut[2], fpOut[2], depthOut[2];
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 22};
 	int tcStride{0};
-	Counters* hostCounters{nullptr};   // pinned
+	Counters* hostCounters{nullptr};   // pinned, [2]
 	RsrStats stats{};
 	uint64_t launches{0};
 	uint64_t lastH2D{0}, lastD2H{0};
@@ -291,6 +295,9 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	auto* c = new rsrcu_ctx();
 	c->device = device;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->evRendered, cudaEventDisableTiming));
+	for (auto& ev : c->evCopied) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evStage) { CU(cudaEventCreate(&ev)); }
 	for (auto& ev : c->arenaFree) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	rsr::harvest_luts(c->hostLuts.rcp, c->hostLuts.rsqrt);
@@ -303,8 +310,8 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 		            "bit-exact parity with the reference on this CPU is not possible", static_cast<unsigned long long>(mismatches)); }
 	CU(cudaMalloc(&c->devLuts, sizeof(ApproxLuts)));
 	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
-	CU(cudaMallocHost(&c->hostCounters, sizeof(Counters)));
-	std::memset(c->hostCounters, 0, sizeof(Counters));
+	CU(cudaMallocHost(&c->hostCounters, 2 * sizeof(Counters)));
+	std::memset(c->hostCounters, 0, 2 * sizeof(Counters));
 	CU(c->counters.reserve(sizeof(Counters)));
 	*out = c;
 	return RSRCU_OK; }
@@ -313,14 +320,18 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	if (!c) { return RSRCU_OK; }
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->copyStream);
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->clipRecs, &c->segActive, &c->counts, &c->gsum, &c->tileBase,
-	                   &c->tileCount, &c->lists, &c->counters, &c->tcOut, &c->fpOut, &c->depthOut }) { b->release(); }
+	                   &c->tileCount, &c->lists, &c->counters, &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
 	if (c->hostCounters) { cudaFreeHost(c->hostCounters); }
 	for (auto& ev : c->evStage) { cudaEventDestroy(ev); }
+	cudaEventDestroy(c->evRendered);
+	for (auto& ev : c->evCopied) { cudaEventDestroy(ev); }
+	cudaStreamDestroy(c->copyStream);
 	cudaStreamDestroy(c->stream);
 	delete c;
 	return RSRCU_OK; }
@@ -359,6 +370,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	CU(cudaSetDevice(c->device));
 	// take the other staging arena; wait only until the frame that last used it has been uploaded
 	c->cur ^= 1;
+	c->outSlot ^= 1;
 	CU(cudaEventSynchronize(c->arenaFree[c->cur]));
 	c->width = width; c->height = height;
 	const int rw = tileWBlocks * 8, rh = tileHBlocks * 8;
@@ -503,12 +515,12 @@ int rsrcu_store_color_tc(rsrcu_ctx* c, int gamma, uint32_t* dst, int width, int 
 	if (c->haveState && !bltProgramInstalled(c->curState.program_id)) {
 		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67; IQ post is not built yet)", c->curState.program_id); }
 	CU(cudaSetDevice(c->device));
-	CU(c->tcOut.reserve(static_cast<size_t>(width) * height * 4));
+	CU(c->tcOut[c->outSlot].reserve(static_cast<size_t>(width) * height * 4));
 	c->tcStride = width;
-	int r = pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, c->tcOut.ptr, width, 1);
+	int r = pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, c->tcOut[c->outSlot].ptr, width, 1);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->tcOut.ptr, static_cast<size_t>(width) * 4, static_cast<size_t>(height),
+		c->copies.push_back(PendingCopy{dst, c->tcOut[c->outSlot].ptr, static_cast<size_t>(width) * 4, static_cast<size_t>(height),
 		                                static_cast<size_t>(stridePx) * 4, static_cast<size_t>(width) * 4}); }
 	return RSRCU_OK; }
 
@@ -525,22 +537,22 @@ int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int st
 	if (half) { return fail(RSRCU_ERR_UNSUPPORTED, "CMD_STORE_COLOR_HALF_LINEAR_FP is not built yet"); }
 	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target", width, height); }
 	CU(cudaSetDevice(c->device));
-	CU(c->fpOut.reserve(static_cast<size_t>(width) * height * 16));
-	int r = pushCmd(c, kCmdStoreFP, 0, c->fpOut.ptr, width, 2);
+	CU(c->fpOut[c->outSlot].reserve(static_cast<size_t>(width) * height * 16));
+	int r = pushCmd(c, kCmdStoreFP, 0, c->fpOut[c->outSlot].ptr, width, 2);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->fpOut.ptr, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
+		c->copies.push_back(PendingCopy{dst, c->fpOut[c->outSlot].ptr, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
 		                                static_cast<size_t>(stridePx) * 16, static_cast<size_t>(width) * 16}); }
 	return RSRCU_OK; }
 
 int rsrcu_store_depth(rsrcu_ctx* c, float* dst) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	CU(cudaSetDevice(c->device));
-	CU(c->depthOut.reserve(static_cast<size_t>(c->width) * c->height * 4));
-	int r = pushCmd(c, kCmdStoreDepth, 0, c->depthOut.ptr, c->width, 3);
+	CU(c->depthOut[c->outSlot].reserve(static_cast<size_t>(c->width) * c->height * 4));
+	int r = pushCmd(c, kCmdStoreDepth, 0, c->depthOut[c->outSlot].ptr, c->width, 3);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->depthOut.ptr, static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->height),
+		c->copies.push_back(PendingCopy{dst, c->depthOut[c->outSlot].ptr, static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->height),
 		                                static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->width) * 4}); }
 	return RSRCU_OK; }
 
@@ -715,6 +727,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaMemcpyAsync(c->arenas[c->cur].dev.ptr, c->arenas[c->cur].host, c->arenas[c->cur].used, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(c->arenaFree[c->cur], st));
+	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot ^ 1], 0));   // previous frame's counters have been read back
 	CU(cudaMemsetAsync(dCtr, 0, sizeof(Counters), st));
 	CU(cudaMemsetAsync(c->segActive.ptr, 0, std::max<size_t>(1, segs.size()) * 4, st));
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[1], st)); }
@@ -773,6 +786,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	ta.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);
 	ta.tileCount = static_cast<const uint32_t*>(c->tileCount.ptr);
 	ta.ctr = dCtr;
+	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last resolved into this slot has been read back
 	tile_kernel<<<ntiles, kTileThreads, 0, st>>>(ta);
 	++c->launches;
 	CU(cudaGetLastError());
@@ -780,10 +794,13 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 
 	c->lastH2D = c->arenas[c->cur].used;
 	c->lastD2H = 0;
+	CU(cudaEventRecord(c->evRendered, st));
+	CU(cudaStreamWaitEvent(c->copyStream, c->evRendered, 0));
 	for (const PendingCopy& pc : c->copies) {
 		c->lastD2H += pc.rowBytes * pc.rows;
-		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, st)); }
-	CU(cudaMemcpyAsync(c->hostCounters, dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); }
+	CU(cudaMemcpyAsync(c->hostCounters + c->outSlot, dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, c->copyStream));
+	CU(cudaEventRecord(c->evCopied[c->outSlot], c->copyStream));
 	c->framePending = true;
 	return RSRCU_OK; }
 
@@ -791,9 +808,10 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->copyStream));
 	if (!c->framePending) { return RSRCU_OK; }
 	c->framePending = false;
-	const Counters& k = *c->hostCounters;
+	const Counters& k = c->hostCounters[c->outSlot];
 	c->stats.triangles_submitted = c->trianglesSubmitted;
 	c->stats.triangles_binned = k.binned;
 	c->stats.triangles_clipped = k.clipped;
@@ -860,9 +878,15 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 		return fail(RSRCU_ERR_INVALID, "stream record op %u too short (%zu bytes)", op, payload); }
 	return RSRCU_OK; }
 
+int rsrcu_sync_frame(rsrcu_ctx* c, int lag) {
+	if (!c || lag < 0 || lag > 1) { return fail(RSRCU_ERR_INVALID, "lag must be 0 or 1"); }
+	CU(cudaSetDevice(c->device));
+	CU(cudaEventSynchronize(c->evCopied[(c->outSlot + lag) & 1]));
+	return RSRCU_OK; }
+
 int rsrcu_device_truecolor(rsrcu_ctx* c, void** devPtr, int* stridePx) {
 	if (!c || !devPtr || !stridePx) { return fail(RSRCU_ERR_INVALID, "null argument"); }
-	*devPtr = c->tcOut.ptr; *stridePx = c->tcStride;
+	*devPtr = c->tcOut[c->outSlot].ptr; *stridePx = c->tcStride;
 	return RSRCU_OK; }
 
 int rsrcu_stream(rsrcu_ctx* c, void** stream) {

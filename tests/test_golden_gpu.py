@@ -121,3 +121,28 @@ def test_static_uploads_pin_their_host_memory(cuda_gpu):
         del q, uv, tex
     bg = frames[0][0, 0]
     assert np.count_nonzero(frames[0] != bg) > 2 * np.count_nonzero(frames[1] != bg) > 0
+
+
+def test_two_deep_frame_pipelining(cuda_gpu):
+    """frames submitted back to back without a full sync land, in order, in their own destinations"""
+    sc = scenes.CubesScene(instances=150)
+    size = (640, 360)
+    want = []
+    for i in range(5):
+        out = np.zeros((size[1], size[0]), np.uint32)
+        sc.record(cuda_gpu, size, out, t=0.3 * i)
+        cuda_gpu.Run()
+        want.append(out)
+    bufs = [np.zeros((size[1], size[0]), np.uint32) for _ in range(5)]
+    recs = []
+    for i in range(5):
+        sc.record(cuda_gpu, size, bufs[i], t=0.3 * i)
+        recs.append(cuda_gpu.Finish())
+    for i, rec in enumerate(recs):
+        cuda_gpu.Submit(rec, sync=False)
+        if i > 0:
+            cuda_gpu.SyncFrame(1)
+            assert np.array_equal(bufs[i - 1], want[i - 1]), f"frame {i - 1} not complete after SyncFrame(1)"
+    cuda_gpu.Sync()
+    assert all(np.array_equal(a, b) for a, b in zip(bufs, want))
+    assert not np.array_equal(want[0], want[4])
