@@ -187,6 +187,7 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
+    gpu.Sync()
     st = gpu.stats()
     if rank == 0:
         checksum = int(frame.to(torch.int64).sum().item())
