@@ -16,6 +16,7 @@
 // in (instance, index) order, then that draw's clipped fan triangles) and every per-tile list is
 // written in increasing id order.
 #pragma once
+#include <cstddef>
 #include "programs.cuh"
 
 namespace rsr {
@@ -44,7 +45,7 @@ struct DevDraw {
 	uint32_t vbaseF4;       // first record, in float4 units
 	uint32_t flagBase;      // first vertex flag byte
 	const uint16_t* indices;   // nullptr = DrawArrays
-	uint32_t idBase;        // ids: [idBase, idBase+N) triangles, [idBase+N, idBase+7N) clip fans
+	uint32_t idBase;        // (unused; triangles are identified by their global index pjobBase + local)
 	uint32_t N;             // prims * instances
 	uint32_t vjobBase;      // prefix of instances*nverts
 	uint32_t pjobBase;      // prefix of N
@@ -59,7 +60,22 @@ struct ClipRec {
 	int nverts;
 	int backfacing;
 	uint32_t fan[kMaxFan];            // packed tile bbox per fan triangle or kReject
+	uint32_t draw, key, state, pad;   // owning draw, its batch key and state index
 	ClipVertex v[8]; };
+static_assert(sizeof(ClipRec) % 16 == 0 && offsetof(ClipRec, v) == 48, "ClipRec layout");
+
+// Everything the tile kernel needs to set up one accepted (unclipped) triangle, written once by K2:
+// 28.4 fixed-point vertices (back faces already re-wound), ndc z and 1/w per vertex, where the
+// varyings live, and the owning draw.  One 80-byte record = five 128-bit loads, no further gathers.
+struct TriRec {
+	int X[3], Y[3];
+	float z[3], iw[3];
+	uint32_t vref[3];
+	uint32_t draw;
+	uint32_t key, state, pad0, pad1; };
+static_assert(sizeof(TriRec) == 80, "TriRec layout");
+
+constexpr uint32_t kFanIdBit = 0x80000000u;   // list entry: fan triangle (clipRec index << 3 | k) instead of a triangle index
 
 struct BinSeg {
 	uint32_t draw;
@@ -222,7 +238,7 @@ __device__ __forceinline__ float clip_dist(int plane, const float* c) {
 	case 3: return c[3] - c[0];   // Right
 	default: return c[3] - c[1]; } }  // Top
 
-__device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, const DevState& s, const FrameParams& fp,
+__device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIndex, const DevState& s, const FrameParams& fp,
                                                const float4* __restrict__ r0, const float4* __restrict__ r1,
                                                const float4* __restrict__ r2, const ApproxLuts* __restrict__ luts,
                                                ClipRec* __restrict__ clipRecs, Counters* __restrict__ ctr) {
@@ -291,6 +307,7 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, const DevState&
 	ClipRec& rec = clipRecs[slot];
 	rec.nverts = na;
 	rec.backfacing = backfacing ? 1 : 0;
+	rec.draw = drawIndex; rec.key = d.batchKey; rec.state = static_cast<uint32_t>(d.state); rec.pad = 0;
 	for (int i = 0; i < na; ++i) {
 		const CVert& src = backfacing ? A[na - 1 - i] : A[i];
 		rec.v[i].dev = make_float4(src.c[0], src.c[1], src.c[2], src.c[3]);
@@ -313,8 +330,8 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, const DevState&
 __global__ void __launch_bounds__(256)
 setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ states, FrameParams fp,
              const ApproxLuts* __restrict__ luts, const float4* __restrict__ ptvb, const uint8_t* __restrict__ vflags,
-             uint32_t* __restrict__ triInfo, ClipRec* __restrict__ clipRecs, unsigned int* __restrict__ segActive,
-             Counters* __restrict__ ctr) {
+             uint32_t* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
+             unsigned int* __restrict__ segActive, Counters* __restrict__ ctr) {
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	if (job >= fp.totalPJobs) { return; }
 	const int di = find_draw(draws, fp.ndraws, job, false);
@@ -343,7 +360,7 @@ setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ sta
 		if (primOutside) { out = kReject; }
 		else if (pointsOutside) {
 			atomicAdd(&ctr->clipped, 1ull);
-			out = clip_triangle(d, s, fp, r0, r1, r2, luts, clipRecs, ctr);
+			out = clip_triangle(d, static_cast<uint32_t>(di), s, fp, r0, r1, r2, luts, clipRecs, ctr);
 			if (out != (kClipSrc | kNoClipRec)) { atomicAdd(&segActive[d.clipSegBase + (local >> fp.segShift)], 1u); } }
 		else {
 			const float4 a = __ldg(r0), b = __ldg(r1), c = __ldg(r2);
@@ -358,8 +375,25 @@ setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ sta
 			uint32_t packed;
 			if (notCulled && tile_bbox(s, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), true, packed, fp)) {
 				out = packed | (front ? 0u : kBackface);
-				atomicAdd(&ctr->binned, 1ull); } } }
-	triInfo[d.idBase + local] = out; }
+				atomicAdd(&ctr->binned, 1ull);
+				// triangle record for the tile kernel; back faces are drawn with i0 <-> i2 swapped
+				// (rglv_gpu_impl.hxx:467-470), fixed point = trunc(16 * dev) (:885-886)
+				const float4 v0 = front ? a : c, v2 = front ? c : a;
+				const uint32_t j0 = front ? i0 : i2, j2 = front ? i2 : i0;
+				const uint32_t vbF4 = d.vbaseF4 + vb * d.strideF4 + 2u;
+				TriRec rec;
+				rec.X[0] = cvtt(16.0f * v0.x); rec.X[1] = cvtt(16.0f * b.x); rec.X[2] = cvtt(16.0f * v2.x);
+				rec.Y[0] = cvtt(16.0f * v0.y); rec.Y[1] = cvtt(16.0f * b.y); rec.Y[2] = cvtt(16.0f * v2.y);
+				rec.z[0] = v0.z; rec.z[1] = b.z; rec.z[2] = v2.z;
+				rec.iw[0] = v0.w; rec.iw[1] = b.w; rec.iw[2] = v2.w;
+				rec.vref[0] = vbF4 + j0 * d.strideF4; rec.vref[1] = vbF4 + i1 * d.strideF4; rec.vref[2] = vbF4 + j2 * d.strideF4;
+				rec.draw = static_cast<uint32_t>(di); rec.key = d.batchKey; rec.state = static_cast<uint32_t>(d.state);
+				rec.pad0 = rec.pad1 = 0;
+				const uint4* src = reinterpret_cast<const uint4*>(&rec);
+				uint4* dst = reinterpret_cast<uint4*>(triRecs + job);
+#pragma unroll
+				for (int q = 0; q < 5; ++q) { dst[q] = src[q]; } } } }
+	triInfo[job] = out; }
 
 // ---------------------------------------------------------------------------------------------
 // K3/K5: order-preserving binning.  One warp owns one chunk (row).  32 ids at a time; the warp
@@ -451,7 +485,7 @@ bin_kernel(const DevDraw* __restrict__ draws, const BinSeg* __restrict__ segs, c
 		if (seg.kind == 0) {
 			for (uint32_t i = 0; i < seg.len; i += 32) {
 				const uint32_t li = i + lane;
-				const uint32_t id = d.idBase + seg.start + li;
+				const uint32_t id = d.pjobBase + seg.start + li;   // global triangle index
 				const uint32_t info = (li < seg.len) ? __ldg(triInfo + id) : kReject;
 				const bool valid = (info != kReject) && !(info & kClipSrc);
 				bin_items<FILL>(valid, info, id, tilesX, row, lists, listCapacity); } }
@@ -460,16 +494,15 @@ bin_kernel(const DevDraw* __restrict__ draws, const BinSeg* __restrict__ segs, c
 			for (uint32_t i = 0; i < seg.len; i += 32) {
 				const uint32_t li = i + lane;
 				const uint32_t src = seg.start + li;
-				const uint32_t info = (li < seg.len) ? __ldg(triInfo + d.idBase + src) : kReject;
+				const uint32_t info = (li < seg.len) ? __ldg(triInfo + d.pjobBase + src) : kReject;
 				const bool isClip = (info != kReject) && (info & kClipSrc) && ((info & kNoClipRec) != kNoClipRec);
 				unsigned m = __ballot_sync(0xffffffffu, isClip);
 				while (m) {
 					const int j = __ffs(m) - 1;
 					m &= m - 1;
 					const uint32_t recIdx = __shfl_sync(0xffffffffu, info, j) & kNoClipRec;
-					const uint32_t srcJ = __shfl_sync(0xffffffffu, src, j);
 					const uint32_t fi = (lane < kMaxFan) ? clipRecs[recIdx].fan[lane] : kReject;
-					const uint32_t id = d.idBase + d.N + srcJ * kMaxFan + lane;
+					const uint32_t id = kFanIdBit | (recIdx << 3) | lane;
 					bin_items<FILL>(fi != kReject, fi, id, tilesX, row, lists, listCapacity); } } } }
 	__syncwarp();
 	if (!FILL) { for (int t = lane; t < ntiles; t += 32) { grow[t] = row[t]; } } }

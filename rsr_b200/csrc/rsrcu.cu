@@ -139,7 +139,7 @@ struct rsrcu_ctx {
 	std::unordered_map<const void*, StaticAlloc> staticCache;
 
 	// device work buffers
-	DevBuf ptvb, vflags, triInfo, clipRecs, segActive, counts, gsum, tileBase, tileCount, lists, counters;
+	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, segActive, counts, gsum, tileBase, tileCount, lists, counters;
 	DevBuf tcOut[2], fpOut[2], depthOut[2];
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 22};
@@ -255,6 +255,7 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 			return RSRCU_OK; }
 		if (it != c->staticCache.end()) { cudaFree(it->second.dev); c->staticCache.erase(it); }
 		void* d = nullptr;
+		CU(cudaSetDevice(c->device));
 		CU(cudaMalloc(&d, bytes));
 		CU(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
 		c->staticCache[host] = StaticAlloc{d, bytes};
@@ -322,7 +323,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->clipRecs, &c->segActive, &c->counts, &c->gsum, &c->tileBase,
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->segActive, &c->counts, &c->gsum, &c->tileBase,
 	                   &c->tileCount, &c->lists, &c->counters, &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
@@ -400,7 +401,6 @@ int rsrcu_set_state(rsrcu_ctx* c, const RsrState* st) {
 int rsrcu_bind_buffer(rsrcu_ctx* c, int slot, const float* host, size_t nFloats, int upload) {
 	if (!c || slot < 0 || slot >= 16) { return fail(RSRCU_ERR_INVALID, "bad buffer slot %d", slot); }
 	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_buffer outside begin/end frame"); }
-	CU(cudaSetDevice(c->device));
 	int r = uploadData(c, host, nFloats * sizeof(float), upload, c->curBuffers[slot]);
 	if (r != RSRCU_OK) { return r; }
 	c->curBufferFloats[slot] = host ? nFloats : 0;
@@ -411,7 +411,6 @@ int rsrcu_bind_texture(rsrcu_ctx* c, int unit, const float* host, int width, int
                        int rowsInMemory, int upload) {
 	if (!c || unit < 0 || unit > 1) { return fail(RSRCU_ERR_INVALID, "bad texture unit %d", unit); }
 	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_texture outside begin/end frame"); }
-	CU(cudaSetDevice(c->device));
 	HostTex& t = c->curTus[unit];
 	const size_t texels = static_cast<size_t>(stride) * static_cast<size_t>(rowsInMemory);
 	int r = uploadData(c, host, texels * 16, upload, t.ref);
@@ -424,7 +423,6 @@ int rsrcu_bind_texture(rsrcu_ctx* c, int unit, const float* host, int width, int
 int rsrcu_bind_depth_texture(rsrcu_ctx* c, const float* host, int dim, int upload) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_depth_texture outside begin/end frame"); }
-	CU(cudaSetDevice(c->device));
 	int r = uploadData(c, host, static_cast<size_t>(dim) * dim * sizeof(float), upload, c->curTu3);
 	if (r != RSRCU_OK) { return r; }
 	c->curTu3dim = dim;
@@ -616,7 +614,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	chunkSegBegin.push_back(static_cast<uint32_t>(segs.size()));
 	const int nchunks = static_cast<int>(chunkSegBegin.size()) - 1;
 	if (c->states.size() > 65535) { return fail(RSRCU_ERR_UNSUPPORTED, "more than 65535 state snapshots in one frame"); }
-	if (ids >= 0xfffffff0ull || ptvbF4 >= 0x7ffffff0ull || vjobs >= 0xfffffff0ull) {
+	if (pjobs >= 0x7ffffff0ull || c->clipCapacity >= (1u << 27) || ptvbF4 >= 0x7ffffff0ull || vjobs >= 0xfffffff0ull) {
 		return fail(RSRCU_ERR_UNSUPPORTED, "frame too large for 32-bit ids (%llu ids, %llu vertex records)",
 		            static_cast<unsigned long long>(ids), static_cast<unsigned long long>(ptvbF4)); }
 	fp.totalVJobs = static_cast<uint32_t>(vjobs);
@@ -640,9 +638,10 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		std::memcpy(ds.vm, s.view_matrix, sizeof(ds.vm));
 		std::memcpy(ds.pm, s.projection_matrix, sizeof(ds.pm));
 		// MakeMatrices (rglv_gpu_impl.hxx:45-51)
-		float inv[16];
-		mat4Inverse(s.view_matrix, inv);
-		mat4Transpose(inv, ds.nm);
+		if (s.program_id == 9 || s.program_id == 10) {   // only OBJ2S and Envmap read gl_NormalMatrix
+			float inv[16];
+			mat4Inverse(s.view_matrix, inv);
+			mat4Transpose(inv, ds.nm); }
 		mat4Mul(s.projection_matrix, s.view_matrix, ds.vpm);
 		if (s.uniforms_valid) { std::memcpy(ds.uniforms, s.uniforms, sizeof(ds.uniforms)); }
 		// GPU::DSDO (rglv_gpu.hxx:265-270): integer halves
@@ -705,7 +704,8 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	// ---- device buffers -------------------------------------------------------------------
 	CU(c->ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
 	CU(c->vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
-	CU(c->triInfo.reserve(std::max<uint64_t>(1, ids) * 4));
+	CU(c->triInfo.reserve(std::max<uint64_t>(1, pjobs) * 4));
+	CU(c->triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
 	CU(c->clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
 	CU(c->segActive.reserve(std::max<size_t>(1, segs.size()) * 4));
 	CU(c->counts.reserve(static_cast<size_t>(std::max(1, nchunks)) * ntiles * 4));
@@ -740,7 +740,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (fp.totalPJobs) {
 		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, dStates, fp, c->devLuts,
 			static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
-			static_cast<uint32_t*>(c->triInfo.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
+			static_cast<uint32_t*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
 			static_cast<unsigned int*>(c->segActive.ptr), dCtr);
 		++c->launches; }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[3], st)); }
@@ -780,7 +780,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	TileArgs ta{};
 	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
 	ta.ptvb = static_cast<const float4*>(c->ptvb.ptr);
-	ta.triInfo = static_cast<const uint32_t*>(c->triInfo.ptr);
+	ta.triRecs = static_cast<const TriRec*>(c->triRecs.ptr);
 	ta.clipRecs = static_cast<const ClipRec*>(c->clipRecs.ptr);
 	ta.lists = static_cast<const uint32_t*>(c->lists.ptr);
 	ta.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);

@@ -36,8 +36,6 @@ __constant__ uint32_t kSrgbTab4[104] = {
 	0x5e0c0a23, 0x631c0980, 0x67db08f6, 0x6c55087f, 0x70940818, 0x74a007bd, 0x787d076c, 0x7c330723,
 };
 
-constexpr int kSmemDraws = 1024;
-
 struct TileShared {
 	float chan[4][4][kTileThreads];      // [r,g,b,depth][quad lane][thread]
 	int ec[3][kBatch];                   // edge functions at the tile origin
@@ -50,7 +48,6 @@ struct TileShared {
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
 	uint16_t queue[kTileThreads / 32][160];   // per-warp (triangle, quad) work items awaiting shading
-	uint32_t drawIdBase[kSmemDraws];     // idBase of the first kSmemDraws draws (id -> draw lookup)
 	int firstBad;
 };
 
@@ -61,7 +58,7 @@ struct TileArgs {
 	const DevState* states;
 	const ApproxLuts* luts;
 	const float4* ptvb;
-	const uint32_t* triInfo;
+	const TriRec* triRecs;
 	const ClipRec* clipRecs;
 	const uint32_t* lists;
 	const uint32_t* tileBase;
@@ -135,33 +132,31 @@ __device__ __forceinline__ void setup_edges(TileShared& sh, int slot, bool wide,
 	                (static_cast<uint32_t>(lmaxx) << 12) | (static_cast<uint32_t>(lmaxy) << 18) |
 	                (clipped ? (1u << 24) : 0u); }
 
-__device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_t id, const DevDraw& d, const TileArgs& A,
+// list entry -> (draw index, batch key, state index) of its triangle
+__device__ __forceinline__ uint3 entry_owner(const TileArgs& A, uint32_t id) {
+	if (id & kFanIdBit) {
+		const ClipRec& rec = A.clipRecs[(id & ~kFanIdBit) >> 3];
+		return make_uint3(rec.draw, rec.key, rec.state); }
+	const uint4 w = __ldg(reinterpret_cast<const uint4*>(A.triRecs + id) + 4);   // key, state, pad, pad
+	const uint32_t draw = __ldg(reinterpret_cast<const uint32_t*>(A.triRecs + id) + 15);
+	return make_uint3(draw, w.x, w.y); }
+
+__device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_t id, const TileArgs& A,
                                                int ox, int oy, int rl, int rt, int rr, int rb) {
-	const uint32_t local = id - d.idBase;
-	if (local < d.N) {
-		// GPUTileImpl::DrawTriangles (rglv_gpu_impl.hxx:880-946)
-		const uint32_t iid = local / static_cast<uint32_t>(d.prims);
-		const uint32_t prim = local - iid * static_cast<uint32_t>(d.prims);
-		uint32_t i0, i1, i2;
-		if (d.indices) { i0 = __ldg(d.indices + 3 * prim); i1 = __ldg(d.indices + 3 * prim + 1); i2 = __ldg(d.indices + 3 * prim + 2); }
-		else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
-		if (__ldg(A.triInfo + id) & kBackface) { const uint32_t t = i0; i0 = i2; i2 = t; }   // :467-470
-		const uint32_t vb = d.vbaseF4 + (iid * static_cast<uint32_t>(d.nverts)) * d.strideF4;
-		const uint32_t a0 = vb + i0 * d.strideF4, a1 = vb + i1 * d.strideF4, a2 = vb + i2 * d.strideF4;
-		const float4 v0 = __ldg(A.ptvb + a0), v1 = __ldg(A.ptvb + a1), v2 = __ldg(A.ptvb + a2);
-		sh.z[0][slot] = v0.z; sh.z[1][slot] = v1.z; sh.z[2][slot] = v2.z;
-		sh.iw[0][slot] = v0.w; sh.iw[1][slot] = v1.w; sh.iw[2][slot] = v2.w;
-		sh.vref[0][slot] = a0 + 2; sh.vref[1][slot] = a1 + 2; sh.vref[2][slot] = a2 + 2;
-		setup_edges(sh, slot, true, false,
-		            cvtt(16.0f * v0.x), cvtt(16.0f * v1.x), cvtt(16.0f * v2.x),
-		            cvtt(16.0f * v0.y), cvtt(16.0f * v1.y), cvtt(16.0f * v2.y), ox, oy, rl, rt, rr, rb); }
+	if (!(id & kFanIdBit)) {
+		// GPUTileImpl::DrawTriangles (rglv_gpu_impl.hxx:880-946): everything was prepared by K2
+		const uint4* r = reinterpret_cast<const uint4*>(A.triRecs + id);
+		const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2), q3 = __ldg(r + 3);
+		sh.z[0][slot] = __uint_as_float(q1.z); sh.z[1][slot] = __uint_as_float(q1.w); sh.z[2][slot] = __uint_as_float(q2.x);
+		sh.iw[0][slot] = __uint_as_float(q2.y); sh.iw[1][slot] = __uint_as_float(q2.z); sh.iw[2][slot] = __uint_as_float(q2.w);
+		sh.vref[0][slot] = q3.x; sh.vref[1][slot] = q3.y; sh.vref[2][slot] = q3.z;
+		setup_edges(sh, slot, true, false, static_cast<int>(q0.x), static_cast<int>(q0.y), static_cast<int>(q0.z),
+		            static_cast<int>(q0.w), static_cast<int>(q1.x), static_cast<int>(q1.y), ox, oy, rl, rt, rr, rb); }
 	else {
 		// GPUTileImpl::DrawClipped (rglv_gpu_impl.hxx:949-998)
-		const uint32_t q = local - d.N;
-		const uint32_t src = q / kMaxFan, k = q - src * kMaxFan;
-		const uint32_t recIdx = __ldg(A.triInfo + d.idBase + src) & kNoClipRec;
+		const uint32_t recIdx = (id & ~kFanIdBit) >> 3, k = id & 7u;
 		const ClipRec& rec = A.clipRecs[recIdx];
-		const uint32_t base = recIdx * static_cast<uint32_t>(sizeof(ClipRec) / 16) + 2u;   // float4 index of v[0]
+		const uint32_t base = recIdx * static_cast<uint32_t>(sizeof(ClipRec) / 16) + 3u;   // float4 index of v[0]
 		const uint32_t vsz = sizeof(ClipVertex) / 16;
 		const uint32_t j0 = 0, j1 = k + 1, j2 = k + 2;
 		const float4 v0 = rec.v[j0].dev, v1 = rec.v[j1].dev, v2 = rec.v[j2].dev;
@@ -271,19 +266,6 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 					sh.chan[1][l][t] = cg[l];
 					sh.chan[2][l][t] = cb[l]; } } } }
 	return __popc(fragMask); }
-
-// id -> index of the draw that owns it (draw id ranges are disjoint and increasing)
-__device__ __forceinline__ int find_draw_of_id(const TileShared& sh, const TileArgs& A, uint32_t id) {
-	int lo = 0, hi = A.fp.ndraws - 1;
-	if (A.fp.ndraws <= kSmemDraws) {
-		while (lo < hi) {
-			const int mid = (lo + hi + 1) >> 1;
-			if (sh.drawIdBase[mid] <= id) { lo = mid; } else { hi = mid - 1; } } }
-	else {
-		while (lo < hi) {
-			const int mid = (lo + hi + 1) >> 1;
-			if (A.draws[mid].idBase <= id) { lo = mid; } else { hi = mid - 1; } } }
-	return lo; }
 
 // edge functions of triangle ti at the four pixels of the quad whose tile-local origin is (lx, ly);
 // returns the coverage mask (bit l = lane l inside all three edges); 0 if the quad is outside the
@@ -506,12 +488,14 @@ tile_kernel(TileArgs A) {
 	// list entries are rasterised as one batch as long as they share a program + pipeline flags
 	// (DevDraw::batchKey) and no clear/store command lies between them -- a scene made of hundreds
 	// of tiny draws (one per textured quad) still fills whole batches.
-	for (int i = t; i < min(A.fp.ndraws, kSmemDraws); i += kTileThreads) { sh.drawIdBase[i] = A.draws[i].idBase; }
-	__syncthreads();
 	int ci = 0;
 	while (true) {
 		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
-		if (cursor < listLen) { di = find_draw_of_id(sh, A, __ldg(list + cursor)); }
+		uint32_t key0 = 0;
+		if (cursor < listLen) {
+			const uint3 o = entry_owner(A, __ldg(list + cursor));
+			di = static_cast<int>(o.x);
+			key0 = o.y; }
 		// non-draw commands that precede that draw
 		while (ci < A.fp.ncmds && A.cmds[ci].beforeDraw <= di) {
 			const FrameCmd cmd = A.cmds[ci];
@@ -561,24 +545,23 @@ tile_kernel(TileArgs A) {
 		if (di >= A.fp.ndraws) { break; }
 
 		const int bound = (ci < A.fp.ncmds) ? A.cmds[ci].beforeDraw : 0x7fffffff;   // draws >= bound come after cmds[ci]
-		const uint32_t key0 = A.draws[di].batchKey;
 		const int avail = static_cast<int>(min(static_cast<uint32_t>(kBatch), listLen - cursor));
 		__syncthreads();   // previous batch fully rasterised before its records are overwritten
 		if (t == 0) { sh.firstBad = avail; }
 		__syncthreads();
 		uint32_t myId = 0;
-		int myDraw = 0;
+		uint32_t myState = 0;
 		if (t < avail) {
 			myId = __ldg(list + cursor + t);
-			myDraw = find_draw_of_id(sh, A, myId);
-			if (myDraw >= bound || A.draws[myDraw].batchKey != key0) { atomicMin(&sh.firstBad, t); } }
+			const uint3 o = entry_owner(A, myId);
+			myState = o.z;
+			if (static_cast<int>(o.x) >= bound || o.y != key0) { atomicMin(&sh.firstBad, t); } }
 		__syncthreads();
 		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
 		bool tiny = false;
 		if (t < nb) {
-			const DevDraw& d = A.draws[myDraw];
-			sh.state[t] = static_cast<uint16_t>(d.state);
-			setup_triangle(sh, t, myId, d, A, ox, oy, rl, rt, rr, rb);
+			sh.state[t] = static_cast<uint16_t>(myState);
+			setup_triangle(sh, t, myId, A, ox, oy, rl, rt, rr, rb);
 			const uint32_t bb = sh.bbox[t];
 			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
 		// (this barrier also publishes the setup records)
