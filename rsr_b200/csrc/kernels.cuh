@@ -402,11 +402,15 @@ setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ sta
 // ---------------------------------------------------------------------------------------------
 
 template <bool FILL>
-__device__ __forceinline__ void bin_items(bool valid, uint32_t info, uint32_t id, int tilesX, uint32_t* __restrict__ row,
-                                          uint32_t* __restrict__ lists, uint32_t listCapacity) {
+__device__ __forceinline__ void bin_items(bool valid, uint32_t info, uint32_t id, int tilesX, int bandY0, int bandY1,
+                                          uint32_t* __restrict__ row, uint32_t* __restrict__ lists, uint32_t listCapacity) {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned ltMask = (1u << lane) - 1u;
-	const int tx0 = info & 63, ty0 = (info >> 6) & 63, tx1 = (info >> 12) & 63, ty1 = (info >> 18) & 63;
+	// this warp only bins into tile rows [bandY0, bandY1]
+	const int tx0 = info & 63, tx1 = (info >> 12) & 63;
+	const int ty0 = max(static_cast<int>((info >> 6) & 63), bandY0), ty1 = min(static_cast<int>((info >> 18) & 63), bandY1);
+	valid = valid && (ty0 <= ty1);
+	info = pack_tiles(tx0, max(ty0, 0), tx1, max(ty1, 0));
 	const unsigned validMask = __ballot_sync(0xffffffffu, valid);
 	if (validMask == 0) { return; }
 
@@ -466,16 +470,22 @@ __device__ __forceinline__ void bin_items(bool valid, uint32_t info, uint32_t id
 template <bool FILL>
 __global__ void __launch_bounds__(kBinWarps * 32)
 bin_kernel(const DevDraw* __restrict__ draws, const BinSeg* __restrict__ segs, const uint32_t* __restrict__ chunkSegBegin,
-           int nchunks, int ntiles, int tilesX, const uint32_t* __restrict__ triInfo, const ClipRec* __restrict__ clipRecs,
+           int nchunks, int nbands, int ntiles, int tilesX, const uint32_t* __restrict__ triInfo, const ClipRec* __restrict__ clipRecs,
            const unsigned int* __restrict__ segActive, uint32_t* __restrict__ counts, uint32_t* __restrict__ lists,
            uint32_t listCapacity) {
 	extern __shared__ uint32_t smemRows[];
 	const int warp = threadIdx.x >> 5;
 	const unsigned lane = threadIdx.x & 31u;
-	const int chunk = blockIdx.x * kBinWarps + warp;
-	if (chunk >= nchunks) { return; }
+	// one warp per (chunk, band of tile rows): a frame with few triangles that each cover hundreds of
+	// tiles is split over nbands warps per chunk instead of serialising on one
+	const int rowIdx = blockIdx.x * kBinWarps + warp;
+	if (rowIdx >= nchunks * nbands) { return; }
+	const int chunk = rowIdx / nbands, band = rowIdx - chunk * nbands;
+	const int tilesY = ntiles / tilesX;
+	const int rowsPerBand = (tilesY + nbands - 1) / nbands;
+	const int bandY0 = band * rowsPerBand, bandY1 = min(bandY0 + rowsPerBand, tilesY) - 1;
 	uint32_t* row = smemRows + static_cast<size_t>(warp) * ntiles;
-	uint32_t* grow = counts + static_cast<size_t>(chunk) * ntiles;
+	uint32_t* grow = counts + static_cast<size_t>(rowIdx) * ntiles;
 	for (int t = lane; t < ntiles; t += 32) { row[t] = FILL ? grow[t] : 0u; }
 	__syncwarp();
 
@@ -488,7 +498,7 @@ bin_kernel(const DevDraw* __restrict__ draws, const BinSeg* __restrict__ segs, c
 				const uint32_t id = d.pjobBase + seg.start + li;   // global triangle index
 				const uint32_t info = (li < seg.len) ? __ldg(triInfo + id) : kReject;
 				const bool valid = (info != kReject) && !(info & kClipSrc);
-				bin_items<FILL>(valid, info, id, tilesX, row, lists, listCapacity); } }
+				bin_items<FILL>(valid, info, id, tilesX, bandY0, bandY1, row, lists, listCapacity); } }
 		else {
 			if (segActive[si] == 0) { continue; }
 			for (uint32_t i = 0; i < seg.len; i += 32) {
@@ -503,7 +513,7 @@ bin_kernel(const DevDraw* __restrict__ draws, const BinSeg* __restrict__ segs, c
 					const uint32_t recIdx = __shfl_sync(0xffffffffu, info, j) & kNoClipRec;
 					const uint32_t fi = (lane < kMaxFan) ? clipRecs[recIdx].fan[lane] : kReject;
 					const uint32_t id = kFanIdBit | (recIdx << 3) | lane;
-					bin_items<FILL>(fi != kReject, fi, id, tilesX, row, lists, listCapacity); } } } }
+					bin_items<FILL>(fi != kReject, fi, id, tilesX, bandY0, bandY1, row, lists, listCapacity); } } } }
 	__syncwarp();
 	if (!FILL) { for (int t = lane; t < ntiles; t += 32) { grow[t] = row[t]; } } }
 
@@ -552,9 +562,7 @@ scan_tiles(uint32_t* __restrict__ gsum, int ngroups, int ntiles, uint32_t* __res
 		const uint32_t before = carry + ((tid >> 5) ? warpSums[(tid >> 5) - 1] : 0u) + (incl - total);
 		if (t < ntiles) {
 			tileBase[t] = before;
-			tileCount[t] = total;
-#pragma unroll 8
-			for (int g = 0; g < ngroups; ++g) { gsum[static_cast<size_t>(g) * ntiles + t] += before; } }
+			tileCount[t] = total; }
 		__syncthreads();
 		if (tid == 1023) { carry = before + total; }
 		__syncthreads(); }
@@ -563,12 +571,12 @@ scan_tiles(uint32_t* __restrict__ gsum, int ngroups, int ntiles, uint32_t* __res
 		if (carry > listCapacity) { atomicOr(&ctr->overflow, 2u); } } }
 
 __global__ void scan_apply(uint32_t* __restrict__ counts, int nchunks, int ntiles, int chunksPerGroup,
-                           const uint32_t* __restrict__ gsum) {
+                           const uint32_t* __restrict__ gsum, const uint32_t* __restrict__ tileBase) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	const int g = blockIdx.y;
 	if (t >= ntiles) { return; }
 	const int c0 = g * chunksPerGroup, c1 = min(c0 + chunksPerGroup, nchunks);
-	uint32_t run = gsum[static_cast<size_t>(g) * ntiles + t];
+	uint32_t run = gsum[static_cast<size_t>(g) * ntiles + t] + tileBase[t];
 	// 8 independent loads in flight, then 8 stores: the chain is the adds, not the memory round trips
 	for (int c = c0; c < c1; c += 8) {
 		uint32_t v[8];

@@ -708,9 +708,13 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	CU(c->triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
 	CU(c->clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
 	CU(c->segActive.reserve(std::max<size_t>(1, segs.size()) * 4));
-	CU(c->counts.reserve(static_cast<size_t>(std::max(1, nchunks)) * ntiles * 4));
-	const int ngroups = std::max(1, std::min(64, nchunks));
-	const int chunksPerGroup = (std::max(1, nchunks) + ngroups - 1) / ngroups;
+	// few chunks (few triangles) => split each chunk's tile rows over several warps ("bands")
+	int nbands = 1;
+	while (nbands < 16 && nchunks * nbands < 256 && nbands * 2 <= fp.tilesY) { nbands *= 2; }
+	const int nrows = std::max(1, nchunks) * nbands;
+	CU(c->counts.reserve(static_cast<size_t>(nrows) * ntiles * 4));
+	const int ngroups = std::max(1, std::min(64, nrows));
+	const int chunksPerGroup = (nrows + ngroups - 1) / ngroups;
 	CU(c->gsum.reserve(static_cast<size_t>(ngroups) * ntiles * 4));
 	CU(c->tileBase.reserve(static_cast<size_t>(ntiles) * 4));
 	CU(c->tileCount.reserve(static_cast<size_t>(ntiles) * 4));
@@ -749,28 +753,28 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (binSmem > 48 * 1024) {
 		CU(cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(binSmem)));
 		CU(cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(binSmem))); }
-	const int binBlocks = (nchunks + kBinWarps - 1) / kBinWarps;
+	const int binBlocks = (nchunks * nbands + kBinWarps - 1) / kBinWarps;
 	if (nchunks > 0) {
-		bin_kernel<false><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, ntiles, fp.tilesX,
+		bin_kernel<false><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, nbands, ntiles, fp.tilesX,
 			static_cast<const uint32_t*>(c->triInfo.ptr), static_cast<const ClipRec*>(c->clipRecs.ptr),
 			static_cast<const unsigned int*>(c->segActive.ptr), static_cast<uint32_t*>(c->counts.ptr),
 			static_cast<uint32_t*>(c->lists.ptr), c->listCapacity);
 		++c->launches; }
-	else { CU(cudaMemsetAsync(c->counts.ptr, 0, static_cast<size_t>(ntiles) * 4, st)); }
+	else { CU(cudaMemsetAsync(c->counts.ptr, 0, static_cast<size_t>(nrows) * ntiles * 4, st)); }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[4], st)); }
 	{
-		const int nc = std::max(1, nchunks);
+		const int nc = nrows;
 		dim3 grid((ntiles + 255) / 256, ngroups);
 		scan_group_sums<<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(c->counts.ptr), nc, ntiles, chunksPerGroup,
 			static_cast<uint32_t*>(c->gsum.ptr));
 		scan_tiles<<<1, 1024, 0, st>>>(static_cast<uint32_t*>(c->gsum.ptr), ngroups, ntiles, static_cast<uint32_t*>(c->tileBase.ptr),
 			static_cast<uint32_t*>(c->tileCount.ptr), dCtr, c->listCapacity);
 		scan_apply<<<grid, 256, 0, st>>>(static_cast<uint32_t*>(c->counts.ptr), nc, ntiles, chunksPerGroup,
-			static_cast<const uint32_t*>(c->gsum.ptr));
+			static_cast<const uint32_t*>(c->gsum.ptr), static_cast<const uint32_t*>(c->tileBase.ptr));
 		c->launches += 3; }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[5], st)); }
 	if (nchunks > 0) {
-		bin_kernel<true><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, ntiles, fp.tilesX,
+		bin_kernel<true><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, nbands, ntiles, fp.tilesX,
 			static_cast<const uint32_t*>(c->triInfo.ptr), static_cast<const ClipRec*>(c->clipRecs.ptr),
 			static_cast<const unsigned int*>(c->segActive.ptr), static_cast<uint32_t*>(c->counts.ptr),
 			static_cast<uint32_t*>(c->lists.ptr), c->listCapacity);
