@@ -99,6 +99,22 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of tile_kernel from the committed `ncu --set full`
+    capture of the same workload (profiles/, tools/capture_profiles.sh); None if there is none"""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_tile_kernel_{workload}.txt")))
+    if not files:
+        return None
+    total = 0.0
+    for line in open(files[-1]):
+        m = re.search(r"dram__bytes_(read|write)\.sum \[(\w+)\] = ([0-9.]+)", line)
+        if m:
+            total += float(m.group(3)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(2)]
+    return total or None
+
+
 def time_reference(scene, size, steps, warmup, threads=None, budget_s=25.0):
     """the reference's multithreaded CPU renderer on this box's cores, method of perf.cxx:216-235:
     priming frames, N timed frames, discard the worst 5 %, report the mean of the rest"""
@@ -347,7 +363,7 @@ def main():
     algo_bytes = 4 * W * H + 4 * stats["bin_entries"] + vertex_bytes + 16 * tex_texels
     achieved = algo_bytes / (tile_avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
+                "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": tile_avg_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "stage_ms": {k: v / args.steps for k, v in stage_acc.items()}}
 
