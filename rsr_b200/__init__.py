@@ -275,7 +275,15 @@ class GPU:
         """GPU::Run on a recorded frame: one C-ABI call (rsrcu_run_stream)"""
         self._check(self.L.rsrcu_run_stream(self.h, rec.buf, len(rec.data)))
         if sync:
-            self.Sync()
+            try:
+                self.Sync()
+            except RsrError as e:
+                if e.code != 6:
+                    raise
+                # a device buffer (tile lists / clip records) was too small; the library has grown
+                # it -- render the same frame again
+                self._check(self.L.rsrcu_run_stream(self.h, rec.buf, len(rec.data)))
+                self.Sync()
 
     def Run(self, manage_workers: bool = True, sync: bool = True):
         """GPU::Run: end of recording -> kernels; `sync` waits and fills the store destinations"""

@@ -142,7 +142,7 @@ struct rsrcu_ctx {
 	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, segActive, counts, gsum, tileBase, tileCount, lists, counters;
 	DevBuf tcOut[2], fpOut[2], depthOut[2];
 	uint32_t clipCapacity{1u << 16};
-	uint32_t listCapacity{1u << 22};
+	uint32_t listCapacity{1u << 24};
 	int tcStride{0};
 	Counters* hostCounters{nullptr};   // pinned, [2]
 	RsrStats stats{};
