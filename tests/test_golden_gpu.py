@@ -148,38 +148,25 @@ def test_two_deep_frame_pipelining(cuda_gpu):
     assert not np.array_equal(want[0], want[4])
 
 
-def test_tile_list_overflow_is_reported_and_recovered(ref_gpu):
+def test_tile_list_overflow_is_reported_and_recovered(ref_gpu, monkeypatch):
     """more (triangle, tile) pairs than the list buffer holds: the frame reports OVERFLOW, the buffer
     grows, and rendering the same frame again gives the reference's pixels"""
-    import ctypes
+    monkeypatch.setenv("RSRCU_LIST_CAPACITY", "2000")
     g = R.GPU(0)
     try:
-        # 400 full-screen triangles x 2040 tiles = 816 k entries per draw; 24 draws > 16 M entries
-        n = 400
-        x = np.tile(np.array([-3.0, 3.0, 0.0], np.float32), n)
-        y = np.tile(np.array([-3.0, -3.0, 3.0], np.float32), n)
-        z = np.repeat(np.linspace(-0.9, 0.9, n).astype(np.float32), 3)
-        pos = scenes.soa(np.stack([x, y, z]))
-        idx = np.arange(3 * n, dtype=np.uint16)
-        tex = scenes.make_mipmap(scenes.hash_texture(16, 2))
-
-        def record(gl, out):
-            scenes.begin(gl, (1920, 1080))
-            gl.UseProgram(R.PROGRAM_AMY)
-            gl.UseBuffer(0, pos)
-            gl.BindTexture(0, tex, 16, 16, 16, R.GL_NEAREST_MIPMAP_NEAREST)
-            for _ in range(24):
-                gl.DrawElements(len(idx), idx, 0)
-            scenes.finish(gl, out)
-        a = np.zeros((1080, 1920), np.uint32)
-        record(g, a)
+        sc = scenes.CubesScene(instances=300)
+        a = np.zeros((360, 640), np.uint32)
+        sc.record(g, (640, 360), a)
         rec = g.Finish()
         g._check(g.L.rsrcu_run_stream(g.h, rec.buf, len(rec.data)))
         with pytest.raises(R.RsrError) as e:
             g.Sync()
         assert e.value.code == 6
-        g.Submit(rec)            # capacity was raised
-        assert g.stats()["bin_entries"] == 24 * n * 2040
-        assert np.unique(a).size == 1 and a[0, 0] != 0
+        g.Submit(rec)            # capacity was raised by the failed attempt
+        assert g.stats()["bin_entries"] > 2000
+        b = np.zeros_like(a)
+        sc.record(ref_gpu, (640, 360), b)
+        ref_gpu.Run()
+        assert np.array_equal(a, b)
     finally:
         g.close()
