@@ -98,6 +98,7 @@ struct FrameParams {
 	int width, height;
 	int tilesX, tilesY;
 	int refTileW, refTileH;      // the reference tile the edge start point is taken from
+	int postTileW, postTileH;    // the reference's actual tile size in pixels (FilterTile's running coordinates)
 	float guardFactor;           // CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
 	int ndraws, ncmds;
 	uint32_t totalVJobs, totalPJobs;

@@ -119,7 +119,7 @@ struct rsrcu_ctx {
 	// recording
 	bool inFrame{false};
 	bool framePending{false};
-	int width{0}, height{0}, refTileW{64}, refTileH{64};
+	int width{0}, height{0}, refTileW{64}, refTileH{64}, postTileW{64}, postTileH{64};
 	RsrState curState;
 	bool haveState{false};
 	bool stateDirty{true};
@@ -188,7 +188,7 @@ int programVaryings(int programId) {
 	case 9: return 15;
 	default: return 0; } }
 
-bool bltProgramInstalled(int programId) { return programId == 1 || programId == 2; }
+bool bltProgramInstalled(int programId) { return programId == 1 || programId == 2 || programId == 3; }
 
 // ---- host-side matrix preparation, same operation order as the reference ----------------------
 
@@ -383,6 +383,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	// otherwise use the device tile itself (identical unless an int32 edge product overflows)
 	c->refTileW = (rw % kTile == 0) ? rw : kTile;
 	c->refTileH = (rh % kTile == 0) ? rh : kTile;
+	c->postTileW = rw; c->postTileH = rh;
 	c->states.clear(); c->draws.clear(); c->cmds.clear(); c->cmdDstKind.clear(); c->copies.clear();
 	c->arenas[c->cur].used = 0;
 	c->trianglesSubmitted = 0;
@@ -515,7 +516,7 @@ int rsrcu_store_color_tc(rsrcu_ctx* c, int gamma, uint32_t* dst, int width, int 
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
 	if (c->haveState && !bltProgramInstalled(c->curState.program_id)) {
-		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67; IQ post is not built yet)", c->curState.program_id); }
+		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67)", c->curState.program_id); }
 	CU(cudaSetDevice(c->device));
 	CU(c->tcOut[c->outSlot].reserve(static_cast<size_t>(width) * height * 4));
 	c->tcStride = width;
@@ -570,6 +571,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	fp.width = W; fp.height = H;
 	fp.tilesX = (W + kTile - 1) / kTile; fp.tilesY = (H + kTile - 1) / kTile;
 	fp.refTileW = c->refTileW; fp.refTileH = c->refTileH;
+	fp.postTileW = c->postTileW; fp.postTileH = c->postTileH;
 	{
 		// CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
 		const int half = std::max(W, H) / 2;

@@ -438,6 +438,56 @@ template <class P>
 __device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, int nb, int ox, int oy, bool queued) {
 	return queued ? draw_batch_queued<P>(sh, A, nb, ox, oy) : draw_batch_direct<P>(sh, A, nb, ox, oy); }
 
+// ---- IQPostProgram::ShadeCanvas (src/viewer/shaders.hxx:56-66) --------------------------------
+// pow(x, y) = exp2f4(log2f4(x) * y)  (rmlv_mvec4.hxx:652-654, 3rdparty/sse-pow/sse_pow.h:19-95):
+// degree-3 / degree-5 minimax polynomials, Horner form, separate mul and add
+
+__device__ __forceinline__ float sse_exp2(float x) {
+	x = sse_min(x, 129.00000f);
+	x = sse_max(x, -126.99999f);
+	const int ipart = __float2int_rn(x - 0.5f);                    // _mm_cvtps_epi32: round to nearest even
+	const float fpart = x - itof(ipart);
+	const float expipart = u2f(static_cast<uint32_t>(ipart + 127) << 23);
+	float p = 7.8024521e-2f;
+	p = p * fpart + 2.2606716e-1f;
+	p = p * fpart + 6.9583356e-1f;
+	p = p * fpart + 9.9992520e-1f;
+	return expipart * p; }
+
+__device__ __forceinline__ float sse_log2(float x) {
+	const uint32_t i = f2u(x);
+	const float e = itof(static_cast<int>((i & 0x7f800000u) >> 23) - 127);
+	const float m = u2f((i & 0x007fffffu) | 0x3f800000u);
+	float p = 0.0596515482674574969533f;
+	p = p * m + -0.465725644288844778798f;
+	p = p * m + 1.48116647521213171641f;
+	p = p * m + -2.52074962577807006663f;
+	p = p * m + 2.8882704548164776201f;
+	p = p * (m - 1.0f);
+	return p + e; }
+
+__device__ __forceinline__ float sse_pow(float x, float y) { return sse_exp2(sse_log2(x) * y); }
+
+// rmlv::sin (rmlv_mvec4.hxx:735-738): scale by 1/pi, wrap1 (:687-691), sin1hp (:714-719)
+__device__ __forceinline__ float sse_sin(float x) {
+	float M = x * static_cast<float>(1.0 / 3.14159265358979323846);
+	const int whole = cvtt(M);
+	M = M - itof(whole);
+	M = u2f(f2u(M) ^ (static_cast<uint32_t>(whole) << 31));
+	const float y = M - (M * fabsf(M));
+	return y * (3.1f + 3.6f * fabsf(y)); }
+
+__device__ __forceinline__ void post_iq(float& r, float& g, float& b, float qx, float qy) {
+	r = sse_pow(r, 0.45f); g = sse_pow(g, 0.5f); b = sse_pow(b, 0.55f);
+	const float vig = 0.2f + 0.8f * sse_pow((((16.0f * qx) * qy) * (1.0f - qx)) * (1.0f - qy), 0.2f);
+	r = r * vig; g = g * vig; b = b * vig;
+	// (1.0 / 255.0) * hash3(q.x + 13.0*q.y), hash3(n) = fract(sin({n, n+1, n+2}) * 43758.5453123F)
+	const float n = qx + 13.0f * qy;
+	const float k = static_cast<float>(1.0 / 255.0);
+	r = r + k * fract_sse(sse_sin(n) * 43758.5453123f);
+	g = g + k * fract_sse(sse_sin(n + 1.0f) * 43758.5453123f);
+	b = b + k * fract_sse(sse_sin(n + 2.0f) * 43758.5453123f); }
+
 // sRGB::to_tc / LinearColor::to_tc (rglr_canvas_util.hxx:15-62, ryg-srgb.h:183-223)
 __device__ __forceinline__ uint32_t srgb8(float f) {
 	const float clampMin = u2f((127u - 13u) << 23);
@@ -520,6 +570,17 @@ tile_kernel(TileArgs A) {
 						if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
 							const float ex = s.uniforms[0];
 							r = r * ex; g = g * ex; b = b * ex; }
+						else if (s.programId == 3) {
+							// FilterTile's running fragment coordinate (rglr_algorithm.hxx:75-96): starts at the
+							// reference tile's left/top edge and is advanced by repeated float adds per quad
+							const int ptx = (px / A.fp.postTileW) * A.fp.postTileW, pty = (py / A.fp.postTileH) * A.fp.postTileH;
+							const float iw = 1.0f / itof(A.fp.width), ih = 1.0f / itof(A.fp.height);
+							float fcx = (itof(ptx) + 0.5f) / itof(A.fp.width) + ((l & 1) ? iw : 0.0f);
+							float fcy = ((itof(A.fp.height - pty)) - 0.5f) / itof(A.fp.height) - ((l & 2) ? ih : 0.0f);
+							const float fcdx = iw * 2.0f, fcdy = -ih * 2.0f;
+							for (int kx = ptx; kx < px; kx += 2) { fcx += fcdx; }
+							for (int ky = pty; ky < py; ky += 2) { fcy += fcdy; }
+							post_iq(r, g, b, fcx, fcy); }
 						out[l] = (cmd.arg & 1) ? ((srgb8(r) << 16) | (srgb8(g) << 8) | srgb8(b))
 						                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
 					uint32_t* dst = static_cast<uint32_t*>(cmd.dst);

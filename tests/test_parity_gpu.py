@@ -138,3 +138,13 @@ def test_unknown_program_is_an_error(cuda_gpu):
     with pytest.raises(R.RsrError) as e:
         cuda_gpu.Run()
     assert e.value.code == 4
+
+
+@pytest.mark.parametrize("gamma", [False, True])
+@pytest.mark.parametrize("tile_blocks", [(8, 8), (4, 4), (3, 5)])
+def test_iq_post_program(gamma, tile_blocks, ref_gpu, cuda_gpu):
+    """IQPostProgram (pow via sse_pow polynomials, vignette, sin-hash dither); its fragment coordinate is a
+    running float sum that starts at each reference tile's edge, so the tile size matters here"""
+    scene = SoupScene(n=300, seed=72)
+    outs = render_both(scene, (640, 360), ref_gpu, cuda_gpu, gamma=gamma, post=R.PROGRAM_IQ_POST, tile_blocks=tile_blocks)
+    assert_identical(outs, f"IQ post gamma={gamma} tiles={tile_blocks}")
