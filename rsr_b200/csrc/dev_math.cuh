@@ -67,6 +67,38 @@ __device__ __forceinline__ float rsqrt_intel(float x, const uint32_t* __restrict
 	const uint32_t r = lut[(p << 10) | (m >> 13)];
 	return u2f(r - (static_cast<uint32_t>(k) << 23)); }
 
+// ---- packed fp32x2 (sm_100a FMUL2 / FFMA2) ------------------------------------------------------
+// Two IEEE fp32 lanes per instruction; each lane rounds exactly like the scalar op, so the SSE
+// order of operations is kept.  ptxas contracts mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2
+// even under --fmad false (tools/ubench/f32x2.cu), so sums are written fma(a, ONE, b) and
+// differences fma(b, -ONE, a) with ONE read from __constant__ memory, which the compiler cannot
+// fold: round(a*1 + b) == round(a + b) bit for bit (0 mismatches over 2^23 random pairs, same file).
+__constant__ float2 kOne2 = {1.0f, 1.0f};
+__constant__ float2 kNegOne2 = {-1.0f, -1.0f};
+
+struct f2 { unsigned long long v; };
+
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 dup2(float a) { return mk2(a, a); }
+__device__ __forceinline__ float lo2(f2 a) { float x, y; asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return x; }
+__device__ __forceinline__ float hi2(f2 a) { float x, y; asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return y; }
+__device__ __forceinline__ f2 one2() { return mk2(kOne2.x, kOne2.y); }
+__device__ __forceinline__ f2 negone2() { return mk2(kNegOne2.x, kNegOne2.y); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, float s) { return mul2(a, dup2(s)); }   // SASS: FMUL2 Rd, Ra.F32x2, Rs.F32
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return fma2(a, one2(), b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return fma2(b, negone2(), a); }
+
+// rcpps for the common case 1 <= exponent <= 252 (result is a normal number): two table lanes at a
+// time; `ok` is cleared when a lane needs the general routine
+__device__ __forceinline__ float rcp_fast(float x, const uint32_t* __restrict__ lut, bool& ok) {
+	const uint32_t b = f2u(x);
+	const uint32_t e = b & 0x7f800000u;
+	ok = ok && ((e - 0x00800000u) < 0x7e000000u);
+	const uint32_t r = lut[(b >> 12) & 0x7ffu];
+	return u2f(((r + 0x3f800000u) - e) | (b & 0x80000000u)); }
+
 // rmlv::oneover (rmlv_mvec4.hxx:630-650): rcpps + one Newton-Raphson step
 __device__ __forceinline__ float oneover(float a, const uint32_t* __restrict__ rcpLut) {
 	const float r = rcp_intel(a, rcpLut);

@@ -102,38 +102,50 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 			r[l] = t.x; g[l] = t.y; b[l] = t.z; a[l] = t.w; }
 		return; }
 
-	// ..._P2_MIPMAP_WRAP_LINEAR (rglr_texture_sampler.cxx:166-286)
+	// ..._P2_MIPMAP_WRAP_LINEAR (rglr_texture_sampler.cxx:166-286).  Coordinates and weights are
+	// computed for two pixels at a time (packed pairs); the four taps of one pixel are blended two
+	// channels at a time (the 128-bit texel is two register pairs) with the weight broadcast.
 	const int levelDimI = 1 << (POWER - lod);
 	const int wrapMask = levelDimI - 1;
 	const int levelLastRow = static_cast<int>((0xffffffffu << (POWER - lod)) & ((1u << (POWER + 1)) - 1u)) - 1;
 	const float levelDim = itof(levelDimI);
+	const uint32_t lastTexel = tu.texelCount - 1u;
+	const f2 one = one2();
+	const f2 negHalf = dup2(-0.5f);
 #pragma unroll
-	for (int l = 0; l < 4; ++l) {
-		const float levelX = u[l] * levelDim;
-		const float levelY = v[l] * levelDim;
-		int tx0 = cvtt(levelX - 0.5f);
-		int ty0 = cvtt(levelY - 0.5f);
-		int tx1 = tx0 + 1;
-		int ty1 = ty0 + 1;
-		const float fx = (levelX - itof(tx0)) - 0.5f;
-		const float fy = (levelY - itof(ty0)) - 0.5f;
-		const float fx1 = 1.0f - fx;
-		const float fy1 = 1.0f - fy;
-		const float w00 = fx1 * fy1;
-		const float w10 = fx * fy1;
-		const float w01 = fx1 * fy;
-		const float w11 = fx * fy;
-		tx0 &= wrapMask; ty0 &= wrapMask; tx1 &= wrapMask; ty1 &= wrapMask;
-		const int by0 = levelLastRow - ty0;
-		const int by1 = levelLastRow - ty1;
-		const float4 p00 = fetch_texel(tu, (by0 << POWER) + tx0);
-		const float4 p10 = fetch_texel(tu, (by0 << POWER) + tx1);
-		const float4 p01 = fetch_texel(tu, (by1 << POWER) + tx0);
-		const float4 p11 = fetch_texel(tu, (by1 << POWER) + tx1);
-		r[l] = ((p00.x * w00 + p10.x * w10) + p01.x * w01) + p11.x * w11;
-		g[l] = ((p00.y * w00 + p10.y * w10) + p01.y * w01) + p11.y * w11;
-		b[l] = ((p00.z * w00 + p10.z * w10) + p01.z * w01) + p11.z * w11;
-		a[l] = ((p00.w * w00 + p10.w * w10) + p01.w * w01) + p11.w * w11; }}
+	for (int h = 0; h < 2; ++h) {
+		const f2 levelX = mul2(mk2(u[2 * h], u[2 * h + 1]), levelDim);
+		const f2 levelY = mul2(mk2(v[2 * h], v[2 * h + 1]), levelDim);
+		const f2 sx = add2(levelX, negHalf);   // levelX - 0.5
+		const f2 sy = add2(levelY, negHalf);
+		const int tx0[2] = { cvtt(lo2(sx)), cvtt(hi2(sx)) };
+		const int ty0[2] = { cvtt(lo2(sy)), cvtt(hi2(sy)) };
+		const f2 fx = add2(sub2(levelX, mk2(itof(tx0[0]), itof(tx0[1]))), negHalf);
+		const f2 fy = add2(sub2(levelY, mk2(itof(ty0[0]), itof(ty0[1]))), negHalf);
+		const f2 fx1 = sub2(one, fx);
+		const f2 fy1 = sub2(one, fy);
+		const f2 w00 = mul2(fx1, fy1);
+		const f2 w10 = mul2(fx, fy1);
+		const f2 w01 = mul2(fx1, fy);
+		const f2 w11 = mul2(fx, fy);
+#pragma unroll
+		for (int j = 0; j < 2; ++j) {
+			const int l = 2 * h + j;
+			const int x0 = tx0[j] & wrapMask, x1 = (tx0[j] + 1) & wrapMask;
+			const int by0 = levelLastRow - (ty0[j] & wrapMask);
+			const int by1 = levelLastRow - ((ty0[j] + 1) & wrapMask);
+			// (the reference would read out of bounds for a texture without its mip rows; stay inside)
+			const float4 p00 = __ldg(tu.texels + min(static_cast<uint32_t>((by0 << POWER) + x0), lastTexel));
+			const float4 p10 = __ldg(tu.texels + min(static_cast<uint32_t>((by0 << POWER) + x1), lastTexel));
+			const float4 p01 = __ldg(tu.texels + min(static_cast<uint32_t>((by1 << POWER) + x0), lastTexel));
+			const float4 p11 = __ldg(tu.texels + min(static_cast<uint32_t>((by1 << POWER) + x1), lastTexel));
+			const float a00 = j ? hi2(w00) : lo2(w00), a10 = j ? hi2(w10) : lo2(w10);
+			const float a01 = j ? hi2(w01) : lo2(w01), a11 = j ? hi2(w11) : lo2(w11);
+			const f2 rg = add2(add2(add2(mul2(mk2(p00.x, p00.y), a00), mul2(mk2(p10.x, p10.y), a10)), mul2(mk2(p01.x, p01.y), a01)),
+			                   mul2(mk2(p11.x, p11.y), a11));
+			const f2 ba = add2(add2(add2(mul2(mk2(p00.z, p00.w), a00), mul2(mk2(p10.z, p10.w), a10)), mul2(mk2(p01.z, p01.w), a01)),
+			                   mul2(mk2(p11.z, p11.w), a11));
+			r[l] = lo2(rg); g[l] = hi2(rg); b[l] = lo2(ba); a[l] = hi2(ba); } } }
 
 // DepthTextureUnit::sample (rglr_texture_sampler.hxx:61-79): nearest, clamp-to-border(-1)
 __device__ __forceinline__ float sample_depth(const DevState& st, float cx, float cy) {

@@ -48,6 +48,7 @@ struct TileShared {
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
 	uint16_t queue[kTileThreads / 32][160];   // per-warp (triangle, quad) work items awaiting shading
+	uint32_t rcpLut[2048];               // rcpps table (dev_math.cuh), staged once per CTA
 	int firstBad;
 };
 
@@ -172,30 +173,47 @@ __device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_
 __device__ __forceinline__ bool depth_pass(int func, float frag, float dest) {
 	return func == 0 ? (frag < dest) : (func == 1 ? (frag <= dest) : (frag == dest)); }
 
-// TriangleProgram::Render for one quad (rglv_gpu_impl.hxx:166-222)
-template <class P>
-__device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, const int i, const TileArgs& A,
+// FragmentStateKey bits (rglv_gpu.hxx, keyOf in rsrcu.cu) as seen by the tile kernel
+constexpr uint32_t kKeyDepthTest = 2u, kKeyBlend = 16u, kKeyDepthWrite = 32u, kKeyColorWrite = 64u;
+// the pipeline every bundled scene uses: depth test LESS, depth + colour writes, no blending
+constexpr uint32_t kKeyFastMask = 0x7eu, kKeyFastValue = 0x62u;
+
+// TriangleProgram::Render for one quad (rglv_gpu_impl.hxx:166-222).
+// FAST: the pipeline flags are the compile-time combination above; otherwise `flags` (uniform for
+// the batch) is decoded at run time.  The four lanes of the reference's SSE registers are two
+// packed pairs here: (0,1) and (2,3).
+template <class P, bool FAST>
+__device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, const int i, const TileArgs& A, const uint32_t flags,
                                                 const DevState& s, const int (&e1)[4], const int (&e2)[4], const uint32_t triMask,
                                                 const int px, const int py, const bool clipped) {
+	const bool depthTest = FAST ? true : (flags & kKeyDepthTest) != 0;
+	const int depthFunc = FAST ? 0 : static_cast<int>((flags >> 2) & 3u);
+	const bool depthWrite = FAST ? true : (flags & kKeyDepthWrite) != 0;
+	const bool colorWrite = FAST ? true : (flags & kKeyColorWrite) != 0;
+	const bool blend = FAST ? false : (flags & kKeyBlend) != 0;
+
 	const float scale = sh.scale[i];
-	float BSx[4], BSy[4], BSz[4], fragDepth[4];
+	const f2 one = one2();
+	f2 BSx[2], BSy[2], BSz[2];
+	float fragDepth[4];
 	const float z0 = sh.z[0][i], z1 = sh.z[1][i], z2 = sh.z[2][i];
 #pragma unroll
-	for (int l = 0; l < 4; ++l) {
-		BSx[l] = itof(e2[l]) * scale;
-		BSz[l] = itof(e1[l]) * scale;
-		BSy[l] = (1.0f - BSx[l]) - BSz[l];
-		fragDepth[l] = (BSx[l] * z0 + BSy[l] * z1) + BSz[l] * z2; }
+	for (int h = 0; h < 2; ++h) {
+		BSx[h] = mul2(mk2(itof(e2[2 * h]), itof(e2[2 * h + 1])), scale);
+		BSz[h] = mul2(mk2(itof(e1[2 * h]), itof(e1[2 * h + 1])), scale);
+		BSy[h] = sub2(sub2(one, BSx[h]), BSz[h]);
+		const f2 fd = add2(add2(mul2(BSx[h], z0), mul2(BSy[h], z1)), mul2(BSz[h], z2));
+		fragDepth[2 * h] = lo2(fd); fragDepth[2 * h + 1] = hi2(fd); }
 
 	uint32_t fragMask = triMask;
-	float destDepth[4];
-	if (P::earlyZ && s.depthTest) {
+	if (P::earlyZ && depthTest) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
-			destDepth[l] = sh.chan[3][l][t];
-			if (!depth_pass(s.depthFunc, fragDepth[l], destDepth[l])) { fragMask &= ~(1u << l); } }
+			const float dest = sh.chan[3][l][t];
+			const bool pass = FAST ? (fragDepth[l] < dest) : depth_pass(depthFunc, fragDepth[l], dest);
+			if (!pass) { fragMask &= ~(1u << l); } }
 		if (fragMask == 0) { return 0; } }
-	if (P::earlyZ && s.depthWrite) {
+	if (P::earlyZ && depthWrite) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { if (fragMask & (1u << l)) { sh.chan[3][l][t] = fragDepth[l]; } } }
 
@@ -205,12 +223,34 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 	f.rcpLut = A.luts->rcp;
 	f.rsqrtLut = A.luts->rsqrt;
 	const float iw0 = sh.iw[0][i], iw1 = sh.iw[1][i], iw2 = sh.iw[2][i];
+	f2 BPx[2], BPy[2], BPz[2], wsum[2], wx[2], wz[2];
+	float rcp[4];
+	bool ok = true;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		wx[h] = mul2(BSx[h], iw0);
+		wz[h] = mul2(BSz[h], iw2);
+		wsum[h] = add2(add2(wx[h], mul2(BSy[h], iw1)), wz[h]);
+		rcp[2 * h] = rcp_fast(lo2(wsum[h]), sh.rcpLut, ok);
+		rcp[2 * h + 1] = rcp_fast(hi2(wsum[h]), sh.rcpLut, ok); }
+	if (!ok) {
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			rcp[2 * h] = rcp_intel(lo2(wsum[h]), sh.rcpLut);
+			rcp[2 * h + 1] = rcp_intel(hi2(wsum[h]), sh.rcpLut); } }
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		// oneover (rmlv_mvec4.hxx:630-650): r = rcpps(a); (r + r) - a * (r * r)
+		const f2 r = mk2(rcp[2 * h], rcp[2 * h + 1]);
+		const f2 fragW = sub2(add2(r, r), mul2(wsum[h], mul2(r, r)));
+		BPx[h] = mul2(wx[h], fragW);
+		BPz[h] = mul2(wz[h], fragW);
+		BPy[h] = sub2(sub2(one, BPx[h]), BPz[h]);
+		f.BPx[2 * h] = lo2(BPx[h]); f.BPx[2 * h + 1] = hi2(BPx[h]);
+		f.BPy[2 * h] = lo2(BPy[h]); f.BPy[2 * h + 1] = hi2(BPy[h]);
+		f.BPz[2 * h] = lo2(BPz[h]); f.BPz[2 * h + 1] = hi2(BPz[h]); }
 #pragma unroll
 	for (int l = 0; l < 4; ++l) {
-		const float fragW = oneover((BSx[l] * iw0 + BSy[l] * iw1) + BSz[l] * iw2, A.luts->rcp);
-		f.BPx[l] = (iw0 * BSx[l]) * fragW;
-		f.BPz[l] = (iw2 * BSz[l]) * fragW;
-		f.BPy[l] = (1.0f - f.BPx[l]) - f.BPz[l];
 		f.depth[l] = fragDepth[l];
 		f.fragX[l] = (itof(px) + 0.5f) + static_cast<float>(l & 1);
 		// rglv_triangle.hxx:297 (4-wide) vs :160 (scalar, clipped triangles): the two differ by one row
@@ -234,27 +274,29 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 				const int k = k4 * 4 + c4;
 				if (k < P::NV) {
 #pragma unroll
-					for (int l = 0; l < 4; ++l) {
-						at[k][l] = (f.BPx[l] * av[c4] + f.BPy[l] * bv[c4]) + f.BPz[l] * cv[c4]; } } } } }
+					for (int h = 0; h < 2; ++h) {
+						const f2 v = add2(add2(mul2(BPx[h], av[c4]), mul2(BPy[h], bv[c4])), mul2(BPz[h], cv[c4]));
+						at[k][2 * h] = lo2(v); at[k][2 * h + 1] = hi2(v); } } } } }
 
 	float cr[4], cg[4], cb[4], ca[4];
 	P::ShadeFragment(f, at, cr, cg, cb, ca, fragMask);
 
-	if (!P::earlyZ && s.depthTest) {
+	if (!P::earlyZ && depthTest) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
-			destDepth[l] = sh.chan[3][l][t];
-			if (!depth_pass(s.depthFunc, fragDepth[l], destDepth[l])) { fragMask &= ~(1u << l); } }
+			const float dest = sh.chan[3][l][t];
+			const bool pass = FAST ? (fragDepth[l] < dest) : depth_pass(depthFunc, fragDepth[l], dest);
+			if (!pass) { fragMask &= ~(1u << l); } }
 		if (fragMask == 0) { return 0; } }
-	if (!P::earlyZ && s.depthWrite) {
+	if (!P::earlyZ && depthWrite) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { if (fragMask & (1u << l)) { sh.chan[3][l][t] = fragDepth[l]; } } }
 
-	if (s.colorWrite) {
+	if (colorWrite) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
 			if (fragMask & (1u << l)) {
-				if (s.blend) {
+				if (blend) {
 					// BlendAlpha (rglv_gpu_impl.hxx:80-84)
 					const float alpha = ca[l];
 					const float oma = 1.0f - alpha;
@@ -303,8 +345,8 @@ __device__ __forceinline__ uint32_t quad_coverage(const TileShared& sh, int ti, 
 //            quad of the region.  Items aimed at the same quad must retire in queue order
 //            (depth LESS ties, blending): __match_any_sync groups them and the group is replayed
 //            rank by rank.  With little overdraw inside 32 consecutive items that is one pass.
-template <class P>
-__device__ __noinline__ unsigned draw_batch_queued(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
+template <class P, bool FAST>
+__device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const TileArgs& A, const uint32_t flags, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
@@ -392,7 +434,7 @@ __device__ __noinline__ unsigned draw_batch_queued(TileShared& sh, const TileArg
 			if (have && rank == r) {
 				int e1[4], e2[4];
 				const uint32_t covered = quad_coverage(sh, ti, qx, qy, e1, e2);
-				frags += render_quad<P>(sh, warp * 32 + ql, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + qx, oy + qy,
+				frags += render_quad<P, FAST>(sh, warp * 32 + ql, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + qx, oy + qy,
 				                        (sh.bbox[ti] >> 24) & 1u); }
 			__syncwarp(); }
 		// keep the items that did not fit (the queue holds at most 31 + 128)
@@ -408,8 +450,8 @@ __device__ __noinline__ unsigned draw_batch_queued(TileShared& sh, const TileArg
 
 // Direct variant: every lane tests and shades its own quad, triangle by triangle.  No queue
 // traffic; best when triangles are large (most lanes covered) or the batch is short.
-template <class P>
-__device__ __noinline__ unsigned draw_batch_direct(TileShared& sh, const TileArgs& A, int nb, int ox, int oy) {
+template <class P, bool FAST>
+__device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const TileArgs& A, const uint32_t flags, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
@@ -430,13 +472,18 @@ __device__ __noinline__ unsigned draw_batch_direct(TileShared& sh, const TileArg
 			int e1[4], e2[4];
 			const uint32_t covered = quad_coverage(sh, ti, lx, ly, e1, e2);
 			if (covered == 0) { continue; }
-			frags += render_quad<P>(sh, t, ti, A, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
+			frags += render_quad<P, FAST>(sh, t, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
 	return frags; }
 
-// picks the variant per batch: long batches of small triangles go through the work queue
+// picks the variant per batch: long batches of small triangles go through the work queue; the
+// common pipeline state gets the specialised instantiation
 template <class P>
-__device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, int nb, int ox, int oy, bool queued) {
-	return queued ? draw_batch_queued<P>(sh, A, nb, ox, oy) : draw_batch_direct<P>(sh, A, nb, ox, oy); }
+__device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, uint32_t key, int nb, int ox, int oy, bool queued) {
+	const uint32_t flags = key >> 8;
+	const bool fast = (flags & kKeyFastMask) == kKeyFastValue;
+	if (queued) {
+		return fast ? draw_batch_queued<P, true>(sh, A, flags, nb, ox, oy) : draw_batch_queued<P, false>(sh, A, flags, nb, ox, oy); }
+	return fast ? draw_batch_direct<P, true>(sh, A, flags, nb, ox, oy) : draw_batch_direct<P, false>(sh, A, flags, nb, ox, oy); }
 
 // ---- IQPostProgram::ShadeCanvas (src/viewer/shaders.hxx:56-66) --------------------------------
 // pow(x, y) = exp2f4(log2f4(x) * y)  (rmlv_mvec4.hxx:652-654, 3rdparty/sse-pow/sse_pow.h:19-95):
@@ -507,7 +554,7 @@ __device__ __forceinline__ uint32_t linear8(float f) {
 	return static_cast<uint32_t>(cvtt(r * 255.0f)); }
 
 __global__ void __launch_bounds__(kTileThreads, 4)
-tile_kernel(TileArgs A) {
+tile_kernel(const __grid_constant__ TileArgs A) {
 	__shared__ TileShared sh;
 	const int t = threadIdx.x;
 	const int tile = blockIdx.x;
@@ -524,6 +571,9 @@ tile_kernel(TileArgs A) {
 
 	const uint32_t* list = A.lists + A.tileBase[tile];
 	const uint32_t listLen = A.tileCount[tile];
+	if (listLen) {
+#pragma unroll
+		for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = __ldg(A.luts->rcp + k * kTileThreads + t); } }
 	uint32_t cursor = 0;
 	unsigned frags = 0;
 
@@ -629,17 +679,17 @@ tile_kernel(TileArgs A) {
 		const int ntiny = __syncthreads_count(tiny);
 		const bool queued = nb >= 96 && ntiny * 2 > nb;
 		switch (key0 & 0xffu) {
-		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, nb, ox, oy, queued); break;
-		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, nb, ox, oy, queued); break;
-		case ProgText::id:         frags += draw_batch<ProgText>(sh, A, nb, ox, oy, queued); break;
-		case ProgDepth::id:        frags += draw_batch<ProgDepth>(sh, A, nb, ox, oy, queued); break;
-		case ProgPattern::id:      frags += draw_batch<ProgPattern>(sh, A, nb, ox, oy, queued); break;
-		case ProgMany::id:         frags += draw_batch<ProgMany>(sh, A, nb, ox, oy, queued); break;
-		case ProgOBJ1::id:         frags += draw_batch<ProgOBJ1>(sh, A, nb, ox, oy, queued); break;
-		case ProgOBJ2::id:         frags += draw_batch<ProgOBJ2>(sh, A, nb, ox, oy, queued); break;
-		case ProgOBJ2S::id:        frags += draw_batch<ProgOBJ2S>(sh, A, nb, ox, oy, queued); break;
-		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, nb, ox, oy, queued); break;
-		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, nb, ox, oy, queued); break;
+		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgText::id:         frags += draw_batch<ProgText>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgDepth::id:        frags += draw_batch<ProgDepth>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgPattern::id:      frags += draw_batch<ProgPattern>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgMany::id:         frags += draw_batch<ProgMany>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgOBJ1::id:         frags += draw_batch<ProgOBJ1>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgOBJ2::id:         frags += draw_batch<ProgOBJ2>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgOBJ2S::id:        frags += draw_batch<ProgOBJ2S>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, key0, nb, ox, oy, queued); break;
+		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, key0, nb, ox, oy, queued); break;
 		default: break; }
 		cursor += static_cast<uint32_t>(max(nb, 1)); }
 
