@@ -94,7 +94,7 @@ def load_library():
         except Exception as exc:  # no nvcc on this box: a prebuilt .so must be there
             if not os.path.exists(_build.LIB):
                 raise RuntimeError(f"librsrcu.so is missing and cannot be built: {exc}") from exc
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(os.environ.get("RSRCU_LIB") or _build.LIB)   # RSRCU_LIB: tuning variants (build.build_variant)
     vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
     sig = {
         "rsrcu_create": [ci, C.POINTER(vp)],
@@ -469,7 +469,9 @@ class GPU:
     def stage_ms(self) -> dict:
         ms = (C.c_float * 7)()
         self._check(self.L.rsrcu_get_stage_ms(self.h, ms))
-        return dict(zip(("vertex", "setup", "bin_count", "bin_scan", "bin_fill", "tile", "frame"), [float(x) for x in ms]))
+        # slot 2 (a separate count kernel of an earlier design) is always 0 now: the setup kernel counts
+        names = ("vertex", "setup_count", None, "bin_scan", "bin_fill", "tile", "frame")
+        return {k: float(x) for k, x in zip(names, ms) if k}
 
     def device_truecolor(self):
         p, s = C.c_void_p(), C.c_int()

@@ -53,6 +53,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Developer knob: builds rsr_b200/variants/librsrcu_<name>.so with extra -D flags (kernel tuning
+    experiments; select it at run time with RSRCU_LIB=<path>)."""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f"librsrcu_{name}.so")
+    obj = os.path.join(HERE, "host_luts.o")
+    if not os.path.exists(obj):
+        build(force=True)
+    subprocess.check_call([_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", out,
+                           os.path.join(CSRC, "rsrcu.cu"), obj])
+    return out
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

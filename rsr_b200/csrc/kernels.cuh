@@ -3,18 +3,20 @@
 //   K1 vertex_kernel      ShadeVertex + frustum flags + pdiv + viewport  (rglv_gpu_impl.hxx:372-385)
 //   K2 setup_kernel       per-triangle classify / cull / tile bbox, Sutherland-Hodgman clip
 //                                                        (rglv_gpu_impl.hxx:391-494, :678-793)
-//   K3 bin_kernel<COUNT>  per-(chunk,tile) counts, submission order preserved
-//   K4 scan_*             prefix sums -> per-tile list offsets
-//   K5 bin_kernel<FILL>   writes the per-tile triangle lists
-//   K6 tile_kernel        one CTA per 32x32 screen tile: clear, edge-function raster with depth
+//                         ... and the per-tile entry counts (fire-and-forget atomics); the last CTA
+//                         to finish turns the counts into list offsets (exclusive scan)
+//   K5 fill_kernel        appends (order key, triangle) entries to the per-tile lists, unordered
+//   K6 tile_kernel        one CTA per 32x32 screen tile: sort its list by order key, clear, edge-function raster with depth
 //                         test, interpolation, fragment programs, blend, resolve / sRGB store
 //                                (rglv_gpu.cxx:263-432, rglv_gpu_impl.hxx:166-222, :841-998,
 //                                 rglv_triangle.hxx:79-304, rglr_algorithm.hxx:31-104)
 //
-// Work that the reference does on one thread (BinImpl) is spread over the whole GPU; ordering is
-// kept by construction: triangle ids increase in submission order (per draw: unclipped triangles
-// in (instance, index) order, then that draw's clipped fan triangles) and every per-tile list is
-// written in increasing id order.
+// Work that the reference does on one thread (BinImpl) is spread over the whole GPU.  Submission
+// order -- which depth-LESS ties and blending depend on -- is carried by a 32-bit ORDER KEY per list
+// entry: per draw, [idBase, idBase+N) are its triangles in (instance, index) order and
+// [idBase+N, idBase+7N) the <= 6 fan triangles of each clipped source, so "unclipped first, then
+// clipped, per draw" (rglv_gpu_impl.hxx:498-508) is ascending key order.  Lists are appended in any
+// order with atomics; each tile CTA sorts its own list by key before rasterising.
 #pragma once
 #include <cstddef>
 #include "programs.cuh"
@@ -24,10 +26,11 @@ namespace rsr {
 constexpr int kTile = 32;                 // device tile edge in pixels (independent of the reference's)
 constexpr int kTileThreads = 256;         // one thread per 2x2 quad
 constexpr int kBatch = 256;               // triangles set up per pass of the tile kernel
-constexpr int kMaxChunkShift = 10;        // a bin row covers at most 1024 triangle ids (chosen per frame)
-constexpr int kBinWarps = 4;              // warps per bin CTA
 constexpr int kMaxFan = 6;                // a clipped triangle has <= 8 vertices => <= 6 fan triangles
 constexpr int kClipVaryF4 = 4;            // float4s of varyings per clipped vertex (>= kMaxVaryings/4)
+constexpr int kMaxGroups = 64;            // list cells per tile
+constexpr int kLargeTiles = 32;           // default of FrameParams::largeTiles
+constexpr int kTileLargeCap = 128;        // queued items one tile can take (more: the frame is rendered again with a higher threshold)
 
 constexpr uint32_t kReject = 0xffffffffu;
 constexpr uint32_t kClipSrc = 0x40000000u;
@@ -45,11 +48,11 @@ struct DevDraw {
 	uint32_t vbaseF4;       // first record, in float4 units
 	uint32_t flagBase;      // first vertex flag byte
 	const uint16_t* indices;   // nullptr = DrawArrays
-	uint32_t idBase;        // (unused; triangles are identified by their global index pjobBase + local)
+	uint32_t idBase;        // first order key of this draw: 7 x (triangles of all earlier draws)
 	uint32_t N;             // prims * instances
 	uint32_t vjobBase;      // prefix of instances*nverts
 	uint32_t pjobBase;      // prefix of N
-	uint32_t clipSegBase;   // first clip segment of this draw in the segment table
+	uint32_t pad0;
 	uint32_t batchKey; };   // program id | pipeline flags << 8: draws with equal keys may share a raster batch
 
 struct ClipVertex {
@@ -60,7 +63,7 @@ struct ClipRec {
 	int nverts;
 	int backfacing;
 	uint32_t fan[kMaxFan];            // packed tile bbox per fan triangle or kReject
-	uint32_t draw, key, state, pad;   // owning draw, its batch key and state index
+	uint32_t draw, key, state, okeyBase;   // owning draw, its batch key, state index | list group << 16, order key of fan triangle 0
 	ClipVertex v[8]; };
 static_assert(sizeof(ClipRec) % 16 == 0 && offsetof(ClipRec, v) == 48, "ClipRec layout");
 
@@ -76,12 +79,7 @@ struct TriRec {
 static_assert(sizeof(TriRec) == 80, "TriRec layout");
 
 constexpr uint32_t kFanIdBit = 0x80000000u;   // list entry: fan triangle (clipRec index << 3 | k) instead of a triangle index
-
-struct BinSeg {
-	uint32_t draw;
-	uint32_t kind;    // 0 = triangles [start, start+len), 1 = clip sources [start, start+len)
-	uint32_t start;
-	uint32_t len; };
+constexpr uint32_t kRunStartBit = 0x40000000u;   // list entry: first entry of the ascending run one warp appended to the cell
 
 enum FrameCmdType : int { kCmdClear = 1, kCmdStoreTC = 3, kCmdStoreFP = 4, kCmdStoreDepth = 5, kCmdStoreHalfFP = 6 };
 
@@ -102,13 +100,18 @@ struct FrameParams {
 	float guardFactor;           // CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
 	int ndraws, ncmds;
 	uint32_t totalVJobs, totalPJobs;
-	int segShift;                // log2(triangles per bin segment), 6..10, chosen per frame
+	uint32_t totalKeys;          // order keys in use: 7 x triangles
+	int groups, groupShift;      // list cells per tile: cell g of a tile holds the triangles [g << groupShift, (g+1) << groupShift)
+	uint32_t largeCapacity;      // capacity of the large-item queue
+	int largeTiles;              // an item covering more tiles than this goes to the queue instead of the lists
 	uint32_t clipCapacity;       // ClipRec capacity
 	uint32_t listCapacity; };
 
 struct Counters {
 	unsigned int clipAlloc;          // ClipRec bump allocator
 	unsigned int overflow;           // bit 0 clip records, bit 1 tile lists
+	unsigned int ticket;             // CTAs of K2 that have finished counting
+	unsigned int nLarge;             // items queued for the cooperative part of K5
 	unsigned long long binned;       // triangles accepted for binning (incl. clip fan triangles)
 	unsigned long long clipped;      // triangles sent to the clipper
 	unsigned long long entries;      // (triangle, tile) pairs
@@ -239,7 +242,7 @@ __device__ __forceinline__ float clip_dist(int plane, const float* c) {
 	case 3: return c[3] - c[0];   // Right
 	default: return c[3] - c[1]; } }  // Top
 
-__device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIndex, const DevState& s, const FrameParams& fp,
+__device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIndex, uint32_t local, const DevState& s, const FrameParams& fp,
                                                const float4* __restrict__ r0, const float4* __restrict__ r1,
                                                const float4* __restrict__ r2, const ApproxLuts* __restrict__ luts,
                                                ClipRec* __restrict__ clipRecs, Counters* __restrict__ ctr) {
@@ -308,7 +311,10 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 	ClipRec& rec = clipRecs[slot];
 	rec.nverts = na;
 	rec.backfacing = backfacing ? 1 : 0;
-	rec.draw = drawIndex; rec.key = d.batchKey; rec.state = static_cast<uint32_t>(d.state); rec.pad = 0;
+	// fan triangles are drawn after every unclipped triangle of their draw: they go to the list cell of the draw's last triangle
+	rec.draw = drawIndex; rec.key = d.batchKey;
+	rec.state = static_cast<uint32_t>(d.state) | (((d.pjobBase + d.N - 1u) >> fp.groupShift) << 16);
+	rec.okeyBase = d.idBase + d.N + local * static_cast<uint32_t>(kMaxFan);
 	for (int i = 0; i < na; ++i) {
 		const CVert& src = backfacing ? A[na - 1 - i] : A[i];
 		rec.v[i].dev = make_float4(src.c[0], src.c[1], src.c[2], src.c[3]);
@@ -328,263 +334,257 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 	if (nbinned) { atomicAdd(&ctr->binned, static_cast<unsigned long long>(nbinned)); }
 	return kClipSrc | slot; }
 
+// ---------------------------------------------------------------------------------------------
+// Binning: one ITEM = one triangle (or clip fan triangle) with its tile range, order key and code.
+// A tile's list is split into `groups` CELLS by triangle index range; cell (tile, g) receives its
+// entries through an atomic cursor, in any order (the tile kernel sorts each cell by order key).
+// K2 counts (COUNT), its last CTA scans the cell counts into list offsets, K5 writes (FILL).
+// Lanes of a warp hold consecutive triangles, which mostly hit the same few tiles: lanes aiming at
+// the same cell are found with __match_any_sync and share ONE atomic.
+// ---------------------------------------------------------------------------------------------
+
+struct LargeItem { uint32_t packed, okey, code, group; };
+
+struct BinArgs {
+	uint32_t* cellCount;         // [tile * groups + g], zeroed per frame; COUNT adds
+	uint32_t* cellCursor;        // same shape, zeroed per frame; FILL takes slots
+	const uint32_t* tileBase;    // [tile]: list offset of the tile's first cell (+ the total at the end)
+	const uint32_t* cellRel;     // [tile * groups + g]: offset of the cell inside its tile's list (groups > 1 only)
+	uint2* lists;
+	LargeItem* large; };
+
+template <bool FILL>
+__device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t okey, uint32_t code, uint32_t group,
+                                         const FrameParams& fp, const BinArgs& B, Counters* __restrict__ ctr) {
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned ltMask = (1u << lane) - 1u;
+	const int tx0 = packed & 63, ty0 = (packed >> 6) & 63, tx1 = (packed >> 12) & 63, ty1 = (packed >> 18) & 63;
+	const int w = tx1 - tx0 + 1, ntile = valid ? w * (ty1 - ty0 + 1) : 0;
+	const bool large = ntile > fp.largeTiles;
+	if (!FILL && large) {
+		// never binned: every tile CTA scans the (short) queue itself -- a triangle that covers more than
+		// largeTiles tiles costs far more to rasterise than the one bbox test per tile this adds
+		const unsigned slot = atomicAdd(&ctr->nLarge, 1u);
+		if (slot < fp.largeCapacity) { B.large[slot] = LargeItem{packed, okey, code, group}; }
+		else { atomicOr(&ctr->overflow, 4u); } }
+	// Small items that cover up to 4 tiles (dense meshes: the long lists) are walked tile by tile in
+	// increasing tile index: each step serves the smallest tile index any lane is at, and the lanes
+	// at that tile take consecutive slots in lane (= submission) order with one atomic.  A warp thus
+	// adds ONE ascending run to a cell, which lets the tile kernel order long cells by runs.
+	const bool small = valid && !large;
+	const bool walked = small && ntile <= 4;
+	int cx = tx0, cy = ty0;
+	uint32_t cur = walked ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu;
+	while (true) {
+		const uint32_t tile = __reduce_min_sync(0xffffffffu, cur);
+		if (tile == 0xffffffffu) { break; }
+		const int leader = __ffs(__ballot_sync(0xffffffffu, cur == tile)) - 1;
+		const uint32_t g = __shfl_sync(0xffffffffu, group, leader);   // (lanes differ in group only among clip fans)
+		const bool mine = (cur == tile) && (group == g);
+		const unsigned m = __ballot_sync(0xffffffffu, mine);
+		const uint32_t cell = tile * static_cast<uint32_t>(fp.groups) + g;
+		if (!FILL) {
+			if (static_cast<int>(lane) == leader) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(m))); } }
+		else {
+			uint32_t base = 0;
+			if (static_cast<int>(lane) == leader) {
+				base = atomicAdd(B.cellCursor + cell, static_cast<uint32_t>(__popc(m))) + __ldg(B.tileBase + tile);
+				if (fp.groups > 1) { base += __ldg(B.cellRel + cell); } }
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (mine) {
+				const uint32_t rank = __popc(m & ltMask);
+				const uint32_t pos = base + rank;
+				if (pos < fp.listCapacity) { B.lists[pos] = make_uint2(okey, rank ? code : (code | kRunStartBit)); } } }
+		if (mine) {
+			++cx;
+			if (cx > tx1) { cx = tx0; ++cy; }
+			cur = (cy <= ty1) ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu; } }
+
+	// Items that cover more tiles make short lists (few of them fit a tile): every lane appends on its
+	// own, four independent atomics in flight.
+	if (small && !walked) {
+		for (int i0 = 0; i0 < ntile; i0 += 4) {
+			uint32_t cell[4], pos[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int i = min(i0 + q, ntile - 1);
+				cell[q] = static_cast<uint32_t>(((ty0 + i / w) * fp.tilesX + tx0 + i % w) * fp.groups) + group; }
+			if (!FILL) {
+#pragma unroll
+				for (int q = 0; q < 4; ++q) { if (i0 + q < ntile) { atomicAdd(B.cellCount + cell[q], 1u); } } }
+			else {
+#pragma unroll
+				for (int q = 0; q < 4; ++q) { pos[q] = (i0 + q < ntile) ? atomicAdd(B.cellCursor + cell[q], 1u) : 0u; }
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					if (i0 + q < ntile) {
+						uint32_t p = pos[q] + __ldg(B.tileBase + cell[q] / static_cast<uint32_t>(fp.groups));
+						if (fp.groups > 1) { p += __ldg(B.cellRel + cell[q]); }
+						if (p < fp.listCapacity) { B.lists[p] = make_uint2(okey, code | kRunStartBit); } } } } } } }
+
+// the items of triangle `job`: itself, or the fan triangles of its clip record
+template <bool FILL>
+__device__ __forceinline__ void bin_triangle(uint32_t job, uint2 info, const FrameParams& fp, const ClipRec* __restrict__ clipRecs,
+                                             const BinArgs& B, Counters* __restrict__ ctr) {
+	const bool isClip = (info.x != kReject) && (info.x & kClipSrc);
+	const bool hasRec = isClip && ((info.x & kNoClipRec) != kNoClipRec);
+	const uint32_t recIdx = info.x & kNoClipRec;
+	const uint32_t group = hasRec ? (clipRecs[recIdx].state >> 16) : (job >> fp.groupShift);
+	const int nslots = __any_sync(0xffffffffu, hasRec) ? kMaxFan : 1;
+	for (int slot = 0; slot < nslots; ++slot) {
+		uint32_t packed = kReject, okey = 0, code = 0;
+		if (hasRec) {
+			packed = clipRecs[recIdx].fan[slot];
+			okey = clipRecs[recIdx].okeyBase + static_cast<uint32_t>(slot);
+			code = kFanIdBit | (recIdx << 3) | static_cast<uint32_t>(slot); }
+		else if (!isClip && slot == 0 && info.x != kReject) { packed = info.x; okey = info.y; code = job; }
+		bin_item<FILL>(packed != kReject, packed, okey, code, group, fp, B, ctr); } }
+
+// Called by every thread of every CTA at the end of a kernel: the last CTA to get here scans
+// count[0..n) (n <= 4096) into base[0..n] (threadFenceReduction pattern: every thread's writes and
+// atomics are ordered before its CTA's ticket).
+__device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint32_t* __restrict__ base, const int n,
+                                                     const uint32_t listCapacity, Counters* __restrict__ ctr) {
+	__shared__ bool lastBlock;
+	__shared__ uint32_t warpSums[8];
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) { lastBlock = (atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1); }
+	__syncthreads();
+	if (!lastBlock) { return; }
+	__threadfence();
+	uint32_t v[16];   // 256 threads x 16 = 4096 tiles (the largest target is 2048 px = 64 x 64 tiles)
+	uint32_t sum = 0;
+#pragma unroll
+	for (int q = 0; q < 16; ++q) {
+		const int i = static_cast<int>(threadIdx.x) * 16 + q;
+		v[q] = (i < n) ? __ldcg(count + i) : 0u;
+		sum += v[q]; }
+	uint32_t incl = sum;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) { incl += x; } }
+	if (lane == 31) { warpSums[warp] = incl; }
+	__syncthreads();
+	uint32_t before = incl - sum;
+	for (int w = 0; w < warp; ++w) { before += warpSums[w]; }
+#pragma unroll
+	for (int q = 0; q < 16; ++q) {
+		const int i = static_cast<int>(threadIdx.x) * 16 + q;
+		if (i < n) { base[i] = before; }
+		before += v[q]; }
+	if (threadIdx.x == 255) {
+		base[n] = before;
+		ctr->entries = before;
+		if (before > listCapacity) { atomicOr(&ctr->overflow, 2u); } } }
+
 __global__ void __launch_bounds__(256)
 setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ states, FrameParams fp,
              const ApproxLuts* __restrict__ luts, const float4* __restrict__ ptvb, const uint8_t* __restrict__ vflags,
-             uint32_t* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
-             unsigned int* __restrict__ segActive, Counters* __restrict__ ctr) {
+             uint2* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
+             BinArgs B, uint32_t* __restrict__ tileBase, Counters* __restrict__ ctr) {
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
-	if (job >= fp.totalPJobs) { return; }
-	const int di = find_draw(draws, fp.ndraws, job, false);
-	const DevDraw& d = draws[di];
-	const DevState& s = states[d.state];
-	const uint32_t local = job - d.pjobBase;
-	const uint32_t iid = local / static_cast<uint32_t>(d.prims);
-	const uint32_t prim = local - iid * static_cast<uint32_t>(d.prims);
+	uint2 myInfo = make_uint2(kReject, 0u);
+	if (job < fp.totalPJobs) {
+		const int di = find_draw(draws, fp.ndraws, job, false);
+		const DevDraw& d = draws[di];
+		const DevState& s = states[d.state];
+		const uint32_t local = job - d.pjobBase;
+		const uint32_t iid = local / static_cast<uint32_t>(d.prims);
+		const uint32_t prim = local - iid * static_cast<uint32_t>(d.prims);
 
-	uint32_t i0, i1, i2;
-	if (d.indices) {
-		i0 = __ldg(d.indices + 3 * prim); i1 = __ldg(d.indices + 3 * prim + 1); i2 = __ldg(d.indices + 3 * prim + 2); }
-	else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
-	const uint32_t nverts = static_cast<uint32_t>(d.nverts);
-	uint32_t out = kReject;
-	if (i0 < nverts && i1 < nverts && i2 < nverts) {
-		const uint32_t vb = iid * nverts;
-		const uint32_t cf0 = vflags[d.flagBase + vb + i0];
-		const uint32_t cf1 = vflags[d.flagBase + vb + i1];
-		const uint32_t cf2 = vflags[d.flagBase + vb + i2];
-		const float4* r0 = ptvb + d.vbaseF4 + static_cast<size_t>(vb + i0) * d.strideF4;
-		const float4* r1 = ptvb + d.vbaseF4 + static_cast<size_t>(vb + i1) * d.strideF4;
-		const float4* r2 = ptvb + d.vbaseF4 + static_cast<size_t>(vb + i2) * d.strideF4;
-		const bool pointsOutside = (cf0 | cf1 | cf2) != 0;
-		const bool primOutside = (cf0 & cf1 & cf2) != 0;
-		if (primOutside) { out = kReject; }
-		else if (pointsOutside) {
-			atomicAdd(&ctr->clipped, 1ull);
-			out = clip_triangle(d, static_cast<uint32_t>(di), s, fp, r0, r1, r2, luts, clipRecs, ctr);
-			if (out != (kClipSrc | kNoClipRec)) { atomicAdd(&segActive[d.clipSegBase + (local >> fp.segShift)], 1u); } }
-		else {
-			const float4 a = __ldg(r0), b = __ldg(r1), c = __ldg(r2);
-			// rmlg::Area (rmlg_triangle.hxx:18-27)
-			const float d31x = c.x - a.x, d31y = c.y - a.y;
-			const float d21x = b.x - a.x, d21y = b.y - a.y;
-			const float area = d31x * d21y - d31y * d21x;
-			const bool front = area > 0.0f;
-			const bool keepBacks = !(s.cullingEnabled && s.cullFace == 2);
-			const bool keepFronts = !(s.cullingEnabled && s.cullFace == 1);
-			const bool notCulled = front ? keepFronts : keepBacks;
-			uint32_t packed;
-			if (notCulled && tile_bbox(s, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), true, packed, fp)) {
-				out = packed | (front ? 0u : kBackface);
-				atomicAdd(&ctr->binned, 1ull);
-				// triangle record for the tile kernel; back faces are drawn with i0 <-> i2 swapped
-				// (rglv_gpu_impl.hxx:467-470), fixed point = trunc(16 * dev) (:885-886)
-				const float4 v0 = front ? a : c, v2 = front ? c : a;
-				const uint32_t j0 = front ? i0 : i2, j2 = front ? i2 : i0;
-				const uint32_t vbF4 = d.vbaseF4 + vb * d.strideF4 + 2u;
-				TriRec rec;
-				rec.X[0] = cvtt(16.0f * v0.x); rec.X[1] = cvtt(16.0f * b.x); rec.X[2] = cvtt(16.0f * v2.x);
-				rec.Y[0] = cvtt(16.0f * v0.y); rec.Y[1] = cvtt(16.0f * b.y); rec.Y[2] = cvtt(16.0f * v2.y);
-				rec.z[0] = v0.z; rec.z[1] = b.z; rec.z[2] = v2.z;
-				rec.iw[0] = v0.w; rec.iw[1] = b.w; rec.iw[2] = v2.w;
-				rec.vref[0] = vbF4 + j0 * d.strideF4; rec.vref[1] = vbF4 + i1 * d.strideF4; rec.vref[2] = vbF4 + j2 * d.strideF4;
-				rec.draw = static_cast<uint32_t>(di); rec.key = d.batchKey; rec.state = static_cast<uint32_t>(d.state);
-				rec.pad0 = rec.pad1 = 0;
-				const uint4* src = reinterpret_cast<const uint4*>(&rec);
-				uint4* dst = reinterpret_cast<uint4*>(triRecs + job);
+		uint32_t i0, i1, i2;
+		if (d.indices) {
+			i0 = __ldg(d.indices + 3 * prim); i1 = __ldg(d.indices + 3 * prim + 1); i2 = __ldg(d.indices + 3 * prim + 2); }
+		else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
+		const uint32_t nverts = static_cast<uint32_t>(d.nverts);
+		uint32_t out = kReject;
+		if (i0 < nverts && i1 < nverts && i2 < nverts) {
+			const uint32_t vb = iid * nverts;
+			const uint32_t cf0 = vflags[d.flagBase + vb + i0];
+			const uint32_t cf1 = vflags[d.flagBase + vb + i1];
+			const uint32_t cf2 = vflags[d.flagBase + vb + i2];
+			const float4* r0 = ptvb + d.vbaseF4 + static_cast<size_t>(vb + i0) * d.strideF4;
+			const float4* r1 = ptvb + d.vbaseF4 + static_cast<size_t>(vb + i1) * d.strideF4;
+			const float4* r2 = ptvb + d.vbaseF4 + static_cast<size_t>(vb + i2) * d.strideF4;
+			const bool pointsOutside = (cf0 | cf1 | cf2) != 0;
+			const bool primOutside = (cf0 & cf1 & cf2) != 0;
+			if (primOutside) { out = kReject; }
+			else if (pointsOutside) {
+				atomicAdd(&ctr->clipped, 1ull);
+				out = clip_triangle(d, static_cast<uint32_t>(di), local, s, fp, r0, r1, r2, luts, clipRecs, ctr); }
+			else {
+				const float4 a = __ldg(r0), b = __ldg(r1), c = __ldg(r2);
+				// rmlg::Area (rmlg_triangle.hxx:18-27)
+				const float d31x = c.x - a.x, d31y = c.y - a.y;
+				const float d21x = b.x - a.x, d21y = b.y - a.y;
+				const float area = d31x * d21y - d31y * d21x;
+				const bool front = area > 0.0f;
+				const bool keepBacks = !(s.cullingEnabled && s.cullFace == 2);
+				const bool keepFronts = !(s.cullingEnabled && s.cullFace == 1);
+				const bool notCulled = front ? keepFronts : keepBacks;
+				uint32_t packed;
+				if (notCulled && tile_bbox(s, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), true, packed, fp)) {
+					out = packed | (front ? 0u : kBackface);
+					atomicAdd(&ctr->binned, 1ull);
+					// triangle record for the tile kernel; back faces are drawn with i0 <-> i2 swapped
+					// (rglv_gpu_impl.hxx:467-470), fixed point = trunc(16 * dev) (:885-886)
+					const float4 v0 = front ? a : c, v2 = front ? c : a;
+					const uint32_t j0 = front ? i0 : i2, j2 = front ? i2 : i0;
+					const uint32_t vbF4 = d.vbaseF4 + vb * d.strideF4 + 2u;
+					TriRec rec;
+					rec.X[0] = cvtt(16.0f * v0.x); rec.X[1] = cvtt(16.0f * b.x); rec.X[2] = cvtt(16.0f * v2.x);
+					rec.Y[0] = cvtt(16.0f * v0.y); rec.Y[1] = cvtt(16.0f * b.y); rec.Y[2] = cvtt(16.0f * v2.y);
+					rec.z[0] = v0.z; rec.z[1] = b.z; rec.z[2] = v2.z;
+					rec.iw[0] = v0.w; rec.iw[1] = b.w; rec.iw[2] = v2.w;
+					rec.vref[0] = vbF4 + j0 * d.strideF4; rec.vref[1] = vbF4 + i1 * d.strideF4; rec.vref[2] = vbF4 + j2 * d.strideF4;
+					rec.draw = static_cast<uint32_t>(di); rec.key = d.batchKey; rec.state = static_cast<uint32_t>(d.state);
+					rec.pad0 = rec.pad1 = 0;
+					const uint4* src = reinterpret_cast<const uint4*>(&rec);
+					uint4* dst = reinterpret_cast<uint4*>(triRecs + job);
 #pragma unroll
-				for (int q = 0; q < 5; ++q) { dst[q] = src[q]; } } } }
-	triInfo[job] = out; }
+					for (int q = 0; q < 5; ++q) { dst[q] = src[q]; } } } }
+		myInfo = make_uint2(out, d.idBase + local);
+		triInfo[job] = myInfo; }
+	bin_triangle<false>(job, myInfo, fp, clipRecs, B, ctr);
+	if (fp.groups > 1) { return; }   // K3 (cell_scan_kernel) prepares the offsets of multi-cell lists
+	tile_scan_last_block(B.cellCount, tileBase, fp.tilesX * fp.tilesY, fp.listCapacity, ctr); }
 
 // ---------------------------------------------------------------------------------------------
-// K3/K5: order-preserving binning.  One warp owns one chunk (row).  32 ids at a time; the warp
-// repeatedly takes the smallest tile index any lane still has to visit (__reduce_min_sync), all
-// lanes that cover that tile get consecutive slots in lane (= submission) order via a ballot.
+// K3 (frames with several cells per tile only): one warp per tile turns the tile's cell counts into
+// offsets inside the tile's list and the tile's total; the last CTA scans the totals.
 // ---------------------------------------------------------------------------------------------
 
-template <bool FILL>
-__device__ __forceinline__ void bin_items(bool valid, uint32_t info, uint32_t id, int tilesX, int bandY0, int bandY1,
-                                          uint32_t* __restrict__ row, uint32_t* __restrict__ lists, uint32_t listCapacity) {
-	const unsigned lane = threadIdx.x & 31u;
-	const unsigned ltMask = (1u << lane) - 1u;
-	// this warp only bins into tile rows [bandY0, bandY1]
-	const int tx0 = info & 63, tx1 = (info >> 12) & 63;
-	const int ty0 = max(static_cast<int>((info >> 6) & 63), bandY0), ty1 = min(static_cast<int>((info >> 18) & 63), bandY1);
-	valid = valid && (ty0 <= ty1);
-	info = pack_tiles(tx0, max(ty0, 0), tx1, max(ty1, 0));
-	const unsigned validMask = __ballot_sync(0xffffffffu, valid);
-	if (validMask == 0) { return; }
-
-	// Two ways to hand out list slots in submission order for these 32 triangles:
-	//  (a) tile-serial: repeatedly take the smallest tile index any lane still has to visit; the lanes
-	//      covering it get consecutive slots by ballot.  One step per distinct tile: good for small
-	//      triangles (a few tiles in total).
-	//  (b) tile-parallel: every lane owns one tile of the union bbox and walks the 32 triangles in
-	//      order.  32 steps per 32 tiles of the union: good for large, overlapping triangles.
-	const unsigned ux0 = __reduce_min_sync(0xffffffffu, valid ? static_cast<unsigned>(tx0) : 63u);
-	const unsigned uy0 = __reduce_min_sync(0xffffffffu, valid ? static_cast<unsigned>(ty0) : 63u);
-	const unsigned ux1 = __reduce_max_sync(0xffffffffu, valid ? static_cast<unsigned>(tx1) : 0u);
-	const unsigned uy1 = __reduce_max_sync(0xffffffffu, valid ? static_cast<unsigned>(ty1) : 0u);
-	const unsigned sumTiles = __reduce_add_sync(0xffffffffu, valid ? static_cast<unsigned>((tx1 - tx0 + 1) * (ty1 - ty0 + 1)) : 0u);
-	const unsigned uw = ux1 - ux0 + 1u, uh = uy1 - uy0 + 1u, U = uw * uh;
-	if (sumTiles >= 48u && U * 2u < sumTiles * 5u) {
-		for (unsigned base = 0; base < U; base += 32u) {
-			const unsigned u = base + lane;
-			const int tx = static_cast<int>(ux0 + u % uw), ty = static_cast<int>(uy0 + u / uw);
-			const bool own = u < U;
-			const uint32_t T = static_cast<uint32_t>(ty * tilesX + tx);
-			const uint32_t start = own ? row[T] : 0u;
-			uint32_t cnt = 0;
-			unsigned m = validMask;
-			while (m) {
-				const int j = __ffs(m) - 1;
-				m &= m - 1;
-				const uint32_t bj = __shfl_sync(0xffffffffu, info, j);
-				const uint32_t idj = __shfl_sync(0xffffffffu, id, j);
-				const int jx0 = bj & 63, jy0 = (bj >> 6) & 63, jx1 = (bj >> 12) & 63, jy1 = (bj >> 18) & 63;
-				if (own && tx >= jx0 && tx <= jx1 && ty >= jy0 && ty <= jy1) {
-					if (FILL) { const uint32_t pos = start + cnt; if (pos < listCapacity) { lists[pos] = idj; } }
-					++cnt; } }
-			if (own && cnt) { row[T] = start + cnt; } }
-		__syncwarp();
-		return; }
-
-	int cx = tx0, cy = ty0;
-	uint32_t cur = valid ? static_cast<uint32_t>(cy * tilesX + cx) : 0xffffffffu;
-	while (true) {
-		const uint32_t B = __reduce_min_sync(0xffffffffu, cur);
-		if (B == 0xffffffffu) { break; }
-		const bool mine = (cur == B);
-		const unsigned m = __ballot_sync(0xffffffffu, mine);
-		const uint32_t base = row[B];
-		__syncwarp();
-		if (mine) {
-			if (FILL) {
-				const uint32_t pos = base + __popc(m & ltMask);
-				if (pos < listCapacity) { lists[pos] = id; } }
-			if ((m & ltMask) == 0) { row[B] = base + __popc(m); }
-			++cx;
-			if (cx > tx1) { cx = tx0; ++cy; }
-			cur = (cy > ty1) ? 0xffffffffu : static_cast<uint32_t>(cy * tilesX + cx); }
-		__syncwarp(); } }
-
-template <bool FILL>
-__global__ void __launch_bounds__(kBinWarps * 32)
-bin_kernel(const DevDraw* __restrict__ draws, const BinSeg* __restrict__ segs, const uint32_t* __restrict__ chunkSegBegin,
-           int nchunks, int nbands, int ntiles, int tilesX, const uint32_t* __restrict__ triInfo, const ClipRec* __restrict__ clipRecs,
-           const unsigned int* __restrict__ segActive, uint32_t* __restrict__ counts, uint32_t* __restrict__ lists,
-           uint32_t listCapacity) {
-	extern __shared__ uint32_t smemRows[];
-	const int warp = threadIdx.x >> 5;
-	const unsigned lane = threadIdx.x & 31u;
-	// one warp per (chunk, band of tile rows): a frame with few triangles that each cover hundreds of
-	// tiles is split over nbands warps per chunk instead of serialising on one
-	const int rowIdx = blockIdx.x * kBinWarps + warp;
-	if (rowIdx >= nchunks * nbands) { return; }
-	const int chunk = rowIdx / nbands, band = rowIdx - chunk * nbands;
-	const int tilesY = ntiles / tilesX;
-	const int rowsPerBand = (tilesY + nbands - 1) / nbands;
-	const int bandY0 = band * rowsPerBand, bandY1 = min(bandY0 + rowsPerBand, tilesY) - 1;
-	uint32_t* row = smemRows + static_cast<size_t>(warp) * ntiles;
-	uint32_t* grow = counts + static_cast<size_t>(rowIdx) * ntiles;
-	for (int t = lane; t < ntiles; t += 32) { row[t] = FILL ? grow[t] : 0u; }
-	__syncwarp();
-
-	for (uint32_t si = chunkSegBegin[chunk]; si < chunkSegBegin[chunk + 1]; ++si) {
-		const BinSeg seg = segs[si];
-		const DevDraw& d = draws[seg.draw];
-		if (seg.kind == 0) {
-			for (uint32_t i = 0; i < seg.len; i += 32) {
-				const uint32_t li = i + lane;
-				const uint32_t id = d.pjobBase + seg.start + li;   // global triangle index
-				const uint32_t info = (li < seg.len) ? __ldg(triInfo + id) : kReject;
-				const bool valid = (info != kReject) && !(info & kClipSrc);
-				bin_items<FILL>(valid, info, id, tilesX, bandY0, bandY1, row, lists, listCapacity); } }
-		else {
-			if (segActive[si] == 0) { continue; }
-			for (uint32_t i = 0; i < seg.len; i += 32) {
-				const uint32_t li = i + lane;
-				const uint32_t src = seg.start + li;
-				const uint32_t info = (li < seg.len) ? __ldg(triInfo + d.pjobBase + src) : kReject;
-				const bool isClip = (info != kReject) && (info & kClipSrc) && ((info & kNoClipRec) != kNoClipRec);
-				unsigned m = __ballot_sync(0xffffffffu, isClip);
-				while (m) {
-					const int j = __ffs(m) - 1;
-					m &= m - 1;
-					const uint32_t recIdx = __shfl_sync(0xffffffffu, info, j) & kNoClipRec;
-					const uint32_t fi = (lane < kMaxFan) ? clipRecs[recIdx].fan[lane] : kReject;
-					const uint32_t id = kFanIdBit | (recIdx << 3) | lane;
-					bin_items<FILL>(fi != kReject, fi, id, tilesX, bandY0, bandY1, row, lists, listCapacity); } } } }
-	__syncwarp();
-	if (!FILL) { for (int t = lane; t < ntiles; t += 32) { grow[t] = row[t]; } } }
-
-// K4: counts[chunk][tile] -> absolute list offsets, in place.  Three small kernels.
-__global__ void scan_group_sums(const uint32_t* __restrict__ counts, int nchunks, int ntiles, int chunksPerGroup,
-                                uint32_t* __restrict__ gsum) {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int g = blockIdx.y;
-	if (t >= ntiles) { return; }
-	const int c0 = g * chunksPerGroup, c1 = min(c0 + chunksPerGroup, nchunks);
-	uint32_t s = 0;
-#pragma unroll 8
-	for (int c = c0; c < c1; ++c) { s += counts[static_cast<size_t>(c) * ntiles + t]; }
-	gsum[static_cast<size_t>(g) * ntiles + t] = s; }
-
-__global__ void __launch_bounds__(1024)
-scan_tiles(uint32_t* __restrict__ gsum, int ngroups, int ntiles, uint32_t* __restrict__ tileBase,
-           uint32_t* __restrict__ tileCount, Counters* __restrict__ ctr, uint32_t listCapacity) {
-	// single CTA; ntiles <= 4096 => <= 4 tiles per thread
-	__shared__ uint32_t warpSums[32];
-	__shared__ uint32_t carry;
-	const int tid = threadIdx.x;
-	if (tid == 0) { carry = 0; }
-	__syncthreads();
-	for (int t0 = 0; t0 < ntiles; t0 += 1024) {
-		const int t = t0 + tid;
-		uint32_t total = 0;
-		if (t < ntiles) {
-			for (int g = 0; g < ngroups; g += 8) {
-				uint32_t v[8];
+__global__ void __launch_bounds__(256)
+cell_scan_kernel(FrameParams fp, const uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellRel,
+                 uint32_t* __restrict__ tileTotal, uint32_t* __restrict__ tileBase, Counters* __restrict__ ctr) {
+	const int ntiles = fp.tilesX * fp.tilesY;
+	const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (tile < ntiles) {
+		const int G = fp.groups;   // <= kMaxGroups = 64: two cells per lane
+		const uint32_t* cnt = cellCount + static_cast<size_t>(tile) * G;
+		const uint32_t a = (2 * lane < G) ? __ldcg(cnt + 2 * lane) : 0u;
+		const uint32_t b = (2 * lane + 1 < G) ? __ldcg(cnt + 2 * lane + 1) : 0u;
+		uint32_t incl = a + b;
 #pragma unroll
-				for (int k = 0; k < 8; ++k) { v[k] = (g + k < ngroups) ? gsum[static_cast<size_t>(g + k) * ntiles + t] : 0u; }
-#pragma unroll
-				for (int k = 0; k < 8; ++k) {
-					if (g + k < ngroups) { gsum[static_cast<size_t>(g + k) * ntiles + t] = total; total += v[k]; } } } }
-		// block exclusive scan of total
-		uint32_t incl = total;
-		for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) { incl += n; } }
-		if ((tid & 31) == 31) { warpSums[tid >> 5] = incl; }
-		__syncthreads();
-		if (tid < 32) {
-			uint32_t w = warpSums[tid];
-			for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) { w += n; } }
-			warpSums[tid] = w; }
-		__syncthreads();
-		const uint32_t before = carry + ((tid >> 5) ? warpSums[(tid >> 5) - 1] : 0u) + (incl - total);
-		if (t < ntiles) {
-			tileBase[t] = before;
-			tileCount[t] = total; }
-		__syncthreads();
-		if (tid == 1023) { carry = before + total; }
-		__syncthreads(); }
-	if (tid == 0) {
-		ctr->entries = carry;
-		if (carry > listCapacity) { atomicOr(&ctr->overflow, 2u); } } }
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) { incl += n; } }
+		const uint32_t before = incl - (a + b);
+		if (2 * lane < G) { cellRel[static_cast<size_t>(tile) * G + 2 * lane] = before; }
+		if (2 * lane + 1 < G) { cellRel[static_cast<size_t>(tile) * G + 2 * lane + 1] = before + a; }
+		if (lane == 31) { tileTotal[tile] = incl; } }
+	tile_scan_last_block(tileTotal, tileBase, ntiles, fp.listCapacity, ctr); }
 
-__global__ void scan_apply(uint32_t* __restrict__ counts, int nchunks, int ntiles, int chunksPerGroup,
-                           const uint32_t* __restrict__ gsum, const uint32_t* __restrict__ tileBase) {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int g = blockIdx.y;
-	if (t >= ntiles) { return; }
-	const int c0 = g * chunksPerGroup, c1 = min(c0 + chunksPerGroup, nchunks);
-	uint32_t run = gsum[static_cast<size_t>(g) * ntiles + t] + tileBase[t];
-	// 8 independent loads in flight, then 8 stores: the chain is the adds, not the memory round trips
-	for (int c = c0; c < c1; c += 8) {
-		uint32_t v[8];
-#pragma unroll
-		for (int k = 0; k < 8; ++k) { v[k] = (c + k < c1) ? counts[static_cast<size_t>(c + k) * ntiles + t] : 0u; }
-#pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			if (c + k < c1) { counts[static_cast<size_t>(c + k) * ntiles + t] = run; run += v[k]; } } } }
+// ---------------------------------------------------------------------------------------------
+// K5: list fill: one thread per triangle id (bin_item<FILL>); queued large items are skipped.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+fill_kernel(FrameParams fp, const uint2* __restrict__ triInfo, const ClipRec* __restrict__ clipRecs,
+            BinArgs B, Counters* __restrict__ ctr) {
+	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
+	uint2 info = make_uint2(kReject, 0u);
+	if (job < fp.totalPJobs) { info = triInfo[job]; }
+	bin_triangle<true>(job, info, fp, clipRecs, B, ctr); }
 
 }  // namespace rsr

@@ -140,10 +140,12 @@ struct rsrcu_ctx {
 	std::unordered_map<const void*, StaticAlloc> staticCache;
 
 	// device work buffers
-	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, segActive, counts, gsum, tileBase, tileCount, lists, counters;
+	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, lists, largeItems, counters;   // counters: Counters | cellCount[] | cellCursor[]
 	DevBuf tcOut[2], fpOut[2], depthOut[2];
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 24};
+	uint32_t largeCapacity{1u << 16};
+	int largeTiles{kLargeTiles};
 	int tcStride{0};
 	Counters* hostCounters{nullptr};   // pinned, [2]
 	RsrStats stats{};
@@ -313,11 +315,11 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	if (const char* cap = std::getenv("RSRCU_LIST_CAPACITY")) {   // initial tile-list capacity in entries (tests)
 		const long v = std::atol(cap);
 		if (v > 0) { c->listCapacity = static_cast<uint32_t>(v); } }
+	CU(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TileShared))));
 	CU(cudaMalloc(&c->devLuts, sizeof(ApproxLuts)));
 	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
 	CU(cudaMallocHost(&c->hostCounters, 2 * sizeof(Counters)));
 	std::memset(c->hostCounters, 0, 2 * sizeof(Counters));
-	CU(c->counters.reserve(sizeof(Counters)));
 	*out = c;
 	return RSRCU_OK; }
 
@@ -327,8 +329,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->segActive, &c->counts, &c->gsum, &c->tileBase,
-	                   &c->tileCount, &c->lists, &c->counters, &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->lists, &c->largeItems, &c->counters, &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
@@ -580,28 +581,8 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	fp.ncmds = static_cast<int>(c->cmds.size());
 	const int ntiles = fp.tilesX * fp.tilesY;
 
-	// ---- layout: ids, vertex records, segments, chunks ------------------------------------
+	// ---- layout: jobs, order keys, vertex records ---------------------------------------------
 	uint64_t vjobs = 0, pjobs = 0, ids = 0, ptvbF4 = 0, nvertsTotal = 0;
-	std::vector<BinSeg> segs;
-	std::vector<uint32_t> chunkSegBegin;
-	// Segment length: small frames get short segments so that enough warps (one per chunk row) are
-	// in flight; large frames use 1024 to keep the count matrix (rows x tiles) small.
-	uint64_t totalTris = 0;
-	for (const HostDraw& hd : c->draws) { totalTris += hd.d.N; }
-	int segShift = 6;
-	while (segShift < kMaxChunkShift && (totalTris >> segShift) > 1536) { ++segShift; }
-	const uint32_t segLen = 1u << segShift;
-	fp.segShift = segShift;
-	// A chunk (= one warp, one row of the count matrix) holds consecutive segments: at most segLen
-	// triangle ids and 8 triangle segments (the warp walks them serially); clip segments are almost
-	// always inactive and cost next to nothing, so up to 64 of them ride along.
-	uint32_t chunkFill = segLen, chunkTriSegs = 0, chunkSegs = 0;   // force a new chunk first
-	auto addSeg = [&](uint32_t draw, uint32_t kind, uint32_t start, uint32_t len) {
-		const uint32_t cost = kind == 0 ? len : 0;
-		if (chunkFill + cost > segLen || (kind == 0 && chunkTriSegs >= 8) || chunkSegs >= 64) {
-			chunkSegBegin.push_back(static_cast<uint32_t>(segs.size())); chunkFill = 0; chunkTriSegs = 0; chunkSegs = 0; }
-		segs.push_back(BinSeg{draw, kind, start, len});
-		chunkFill += cost; chunkTriSegs += (kind == 0); ++chunkSegs; };
 	for (size_t di = 0; di < c->draws.size(); ++di) {
 		DevDraw& d = c->draws[di].d;
 		d.vjobBase = static_cast<uint32_t>(vjobs);
@@ -612,29 +593,29 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		const uint64_t nv = static_cast<uint64_t>(d.nverts) * d.instances;
 		vjobs += nv; nvertsTotal += nv; ptvbF4 += nv * d.strideF4;
 		pjobs += d.N;
-		ids += static_cast<uint64_t>(d.N) * (1 + kMaxFan);
-		for (uint32_t s0 = 0; s0 < d.N; s0 += segLen) { addSeg(static_cast<uint32_t>(di), 0, s0, std::min<uint32_t>(segLen, d.N - s0)); }
-		d.clipSegBase = static_cast<uint32_t>(segs.size());
-		// clip segments must be addressable as clipSegBase + (source >> segShift)
-		for (uint32_t s0 = 0; s0 < d.N; s0 += segLen) { addSeg(static_cast<uint32_t>(di), 1, s0, std::min<uint32_t>(segLen, d.N - s0)); } }
-	chunkSegBegin.push_back(static_cast<uint32_t>(segs.size()));
-	const int nchunks = static_cast<int>(chunkSegBegin.size()) - 1;
+		ids += static_cast<uint64_t>(d.N) * (1 + kMaxFan); }
 	if (c->states.size() > 65535) { return fail(RSRCU_ERR_UNSUPPORTED, "more than 65535 state snapshots in one frame"); }
-	if (pjobs >= 0x7ffffff0ull || c->clipCapacity >= (1u << 27) || ptvbF4 >= 0x7ffffff0ull || vjobs >= 0xfffffff0ull) {
+	if (pjobs >= 0x7ffffff0ull || ids >= 0xfffffff0ull || c->clipCapacity >= (1u << 24) || ptvbF4 >= 0x7ffffff0ull || vjobs >= 0xfffffff0ull) {
 		return fail(RSRCU_ERR_UNSUPPORTED, "frame too large for 32-bit ids (%llu ids, %llu vertex records)",
 		            static_cast<unsigned long long>(ids), static_cast<unsigned long long>(ptvbF4)); }
 	fp.totalVJobs = static_cast<uint32_t>(vjobs);
 	fp.totalPJobs = static_cast<uint32_t>(pjobs);
+	fp.totalKeys = static_cast<uint32_t>(std::max<uint64_t>(ids, 1));
+	// list cells per tile: one for small frames (a tile's whole list is sorted at once); frames with millions of
+	// triangles split every list by triangle index range so that a cell stays within one raster batch
+	fp.groupShift = 31;
+	if (pjobs > (1u << 18)) { fp.groupShift = 15; while ((pjobs >> fp.groupShift) >= static_cast<uint64_t>(kMaxGroups)) { ++fp.groupShift; } }
+	fp.groups = static_cast<int>(pjobs >> fp.groupShift) + 1;
+	fp.largeCapacity = c->largeCapacity;
+	fp.largeTiles = c->largeTiles;
 	fp.clipCapacity = c->clipCapacity;
 	fp.listCapacity = c->listCapacity;
 
 	// ---- frame tables into the arena (state / draw tables need final device addresses) -----
-	size_t offStates = 0, offDraws = 0, offCmds = 0, offSegs = 0, offChunks = 0;
+	size_t offStates = 0, offDraws = 0, offCmds = 0;
 	CU(c->arenas[c->cur].push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
 	CU(c->arenas[c->cur].push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
 	CU(c->arenas[c->cur].push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
-	CU(c->arenas[c->cur].push(nullptr, sizeof(BinSeg) * std::max<size_t>(1, segs.size()), offSegs));
-	CU(c->arenas[c->cur].push(nullptr, sizeof(uint32_t) * chunkSegBegin.size(), offChunks));
 	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
 
 	for (size_t i = 0; i < c->states.size(); ++i) {
@@ -691,8 +672,6 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		d.indices = static_cast<const uint16_t*>(resolve(c, c->draws[i].indices));
 		std::memcpy(c->arenas[c->cur].host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
 	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
-	if (!segs.empty()) { std::memcpy(c->arenas[c->cur].host + offSegs, segs.data(), sizeof(BinSeg) * segs.size()); }
-	std::memcpy(c->arenas[c->cur].host + offChunks, chunkSegBegin.data(), sizeof(uint32_t) * chunkSegBegin.size());
 
 	// texture units with pow2 dims outside 4..1024 cannot be made by the reference (exit(1))
 	for (const HostDraw& hd : c->draws) {
@@ -710,36 +689,37 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	// ---- device buffers -------------------------------------------------------------------
 	CU(c->ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
 	CU(c->vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
-	CU(c->triInfo.reserve(std::max<uint64_t>(1, pjobs) * 4));
+	CU(c->triInfo.reserve(std::max<uint64_t>(1, pjobs) * sizeof(uint2)));
 	CU(c->triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
 	CU(c->clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
-	CU(c->segActive.reserve(std::max<size_t>(1, segs.size()) * 4));
-	// few chunks (few triangles) => split each chunk's tile rows over several warps ("bands")
-	int nbands = 1;
-	while (nbands < 16 && nchunks * nbands < 256 && nbands * 2 <= fp.tilesY) { nbands *= 2; }
-	const int nrows = std::max(1, nchunks) * nbands;
-	CU(c->counts.reserve(static_cast<size_t>(nrows) * ntiles * 4));
-	const int ngroups = std::max(1, std::min(64, nrows));
-	const int chunksPerGroup = (nrows + ngroups - 1) / ngroups;
-	CU(c->gsum.reserve(static_cast<size_t>(ngroups) * ntiles * 4));
-	CU(c->tileBase.reserve(static_cast<size_t>(ntiles) * 4));
-	CU(c->tileCount.reserve(static_cast<size_t>(ntiles) * 4));
-	CU(c->lists.reserve(static_cast<size_t>(c->listCapacity) * 4));
+	const size_t ncells = static_cast<size_t>(ntiles) * fp.groups;
+	const size_t ctrlBytes = 64 + ncells * 8;   // Counters | cellCount[] | cellCursor[]
+	static_assert(sizeof(Counters) <= 64, "control block layout");
+	CU(c->counters.reserve(ctrlBytes));
+	CU(c->tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
+	CU(c->cellRel.reserve(ncells * 4));
+	CU(c->tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(c->lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
+	CU(c->largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
 
 	const uint8_t* ab = static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr);
 	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
 	const DevDraw* dDraws = reinterpret_cast<const DevDraw*>(ab + offDraws);
 	const FrameCmd* dCmds = reinterpret_cast<const FrameCmd*>(ab + offCmds);
-	const BinSeg* dSegs = reinterpret_cast<const BinSeg*>(ab + offSegs);
-	const uint32_t* dChunks = reinterpret_cast<const uint32_t*>(ab + offChunks);
 	Counters* dCtr = static_cast<Counters*>(c->counters.ptr);
+	BinArgs bin{};
+	bin.cellCount = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->counters.ptr) + 64);
+	bin.cellCursor = bin.cellCount + ncells;
+	bin.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);
+	bin.cellRel = static_cast<const uint32_t*>(c->cellRel.ptr);
+	bin.lists = static_cast<uint2*>(c->lists.ptr);
+	bin.large = static_cast<LargeItem*>(c->largeItems.ptr);
 
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaMemcpyAsync(c->arenas[c->cur].dev.ptr, c->arenas[c->cur].host, c->arenas[c->cur].used, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(c->arenaFree[c->cur], st));
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot ^ 1], 0));   // previous frame's counters have been read back
-	CU(cudaMemsetAsync(dCtr, 0, sizeof(Counters), st));
-	CU(cudaMemsetAsync(c->segActive.ptr, 0, std::max<size_t>(1, segs.size()) * 4, st));
+	CU(cudaMemsetAsync(dCtr, 0, ctrlBytes, st));
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[1], st)); }
 
 	if (fp.totalVJobs) {
@@ -750,40 +730,18 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (fp.totalPJobs) {
 		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, dStates, fp, c->devLuts,
 			static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
-			static_cast<uint32_t*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
-			static_cast<unsigned int*>(c->segActive.ptr), dCtr);
+			static_cast<uint2*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
+			bin, static_cast<uint32_t*>(c->tileBase.ptr), dCtr);
 		++c->launches; }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[3], st)); }
-
-	const size_t binSmem = static_cast<size_t>(kBinWarps) * ntiles * 4;
-	if (binSmem > 48 * 1024) {
-		CU(cudaFuncSetAttribute(bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(binSmem)));
-		CU(cudaFuncSetAttribute(bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(binSmem))); }
-	const int binBlocks = (nchunks * nbands + kBinWarps - 1) / kBinWarps;
-	if (nchunks > 0) {
-		bin_kernel<false><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, nbands, ntiles, fp.tilesX,
-			static_cast<const uint32_t*>(c->triInfo.ptr), static_cast<const ClipRec*>(c->clipRecs.ptr),
-			static_cast<const unsigned int*>(c->segActive.ptr), static_cast<uint32_t*>(c->counts.ptr),
-			static_cast<uint32_t*>(c->lists.ptr), c->listCapacity);
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
+	if (fp.totalPJobs && fp.groups > 1) {
+		cell_scan_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(fp, bin.cellCount, static_cast<uint32_t*>(c->cellRel.ptr),
+			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), dCtr);
 		++c->launches; }
-	else { CU(cudaMemsetAsync(c->counts.ptr, 0, static_cast<size_t>(nrows) * ntiles * 4, st)); }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[4], st)); }
-	{
-		const int nc = nrows;
-		dim3 grid((ntiles + 255) / 256, ngroups);
-		scan_group_sums<<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(c->counts.ptr), nc, ntiles, chunksPerGroup,
-			static_cast<uint32_t*>(c->gsum.ptr));
-		scan_tiles<<<1, 1024, 0, st>>>(static_cast<uint32_t*>(c->gsum.ptr), ngroups, ntiles, static_cast<uint32_t*>(c->tileBase.ptr),
-			static_cast<uint32_t*>(c->tileCount.ptr), dCtr, c->listCapacity);
-		scan_apply<<<grid, 256, 0, st>>>(static_cast<uint32_t*>(c->counts.ptr), nc, ntiles, chunksPerGroup,
-			static_cast<const uint32_t*>(c->gsum.ptr), static_cast<const uint32_t*>(c->tileBase.ptr));
-		c->launches += 3; }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[5], st)); }
-	if (nchunks > 0) {
-		bin_kernel<true><<<binBlocks, kBinWarps * 32, binSmem, st>>>(dDraws, dSegs, dChunks, nchunks, nbands, ntiles, fp.tilesX,
-			static_cast<const uint32_t*>(c->triInfo.ptr), static_cast<const ClipRec*>(c->clipRecs.ptr),
-			static_cast<const unsigned int*>(c->segActive.ptr), static_cast<uint32_t*>(c->counts.ptr),
-			static_cast<uint32_t*>(c->lists.ptr), c->listCapacity);
+	if (fp.totalPJobs) {
+		fill_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(fp, static_cast<const uint2*>(c->triInfo.ptr),
+			static_cast<const ClipRec*>(c->clipRecs.ptr), bin, dCtr);
 		++c->launches; }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], st)); }
 
@@ -792,12 +750,13 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	ta.ptvb = static_cast<const float4*>(c->ptvb.ptr);
 	ta.triRecs = static_cast<const TriRec*>(c->triRecs.ptr);
 	ta.clipRecs = static_cast<const ClipRec*>(c->clipRecs.ptr);
-	ta.lists = static_cast<const uint32_t*>(c->lists.ptr);
-	ta.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);
-	ta.tileCount = static_cast<const uint32_t*>(c->tileCount.ptr);
+	ta.lists = static_cast<const uint2*>(c->lists.ptr);
+	ta.tileBase = bin.tileBase;
+	ta.cellRel = bin.cellRel;
+	ta.large = bin.large;
 	ta.ctr = dCtr;
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last resolved into this slot has been read back
-	tile_kernel<<<ntiles, kTileThreads, 0, st>>>(ta);
+	tile_kernel<<<ntiles, kTileThreads, sizeof(TileShared), st>>>(ta);
 	++c->launches;
 	CU(cudaGetLastError());
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], st)); }
@@ -840,6 +799,13 @@ int rsrcu_sync(rsrcu_ctx* c) {
 		c->listCapacity = static_cast<uint32_t>(std::min<uint64_t>(need, 0xfffffff0ull));
 		return fail(RSRCU_ERR_OVERFLOW, "tile list capacity exceeded (%llu entries); capacity raised, render the frame again",
 		            static_cast<unsigned long long>(k.entries)); }
+	if (k.overflow & 8u) {
+		c->largeTiles = std::min(c->largeTiles * 4, 1 << 12);
+		return fail(RSRCU_ERR_OVERFLOW, "a tile is covered by more than %d queued large triangles; threshold raised to %d tiles, render the frame again",
+		            kTileLargeCap, c->largeTiles); }
+	if (k.overflow & 4u) {
+		c->largeCapacity = std::max(c->largeCapacity * 2, k.nLarge + k.nLarge / 4);
+		return fail(RSRCU_ERR_OVERFLOW, "large-item queue exceeded (%u items); capacity raised, render the frame again", k.nLarge); }
 	if (k.overflow & 1u) {
 		c->clipCapacity = c->clipCapacity * 2;
 		return fail(RSRCU_ERR_OVERFLOW, "clip record capacity exceeded (%u needed); capacity raised, render the frame again", k.clipAlloc); }

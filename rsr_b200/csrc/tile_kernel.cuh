@@ -36,6 +36,8 @@ __constant__ uint32_t kSrgbTab4[104] = {
 	0x5e0c0a23, 0x631c0980, 0x67db08f6, 0x6c55087f, 0x70940818, 0x74a007bd, 0x787d076c, 0x7c330723,
 };
 
+constexpr int kSortCap = 1024;           // most list entries sorted in one round
+
 struct TileShared {
 	float chan[4][4][kTileThreads];      // [r,g,b,depth][quad lane][thread]
 	int ec[3][kBatch];                   // edge functions at the tile origin
@@ -49,8 +51,16 @@ struct TileShared {
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
 	uint16_t queue[kTileThreads / 32][160];   // per-warp (triangle, quad) work items awaiting shading
 	uint32_t rcpLut[2048];               // rcpps table (dev_math.cuh), staged once per CTA
+	uint32_t sorted[kSortCap];           // triangle codes of the current chunk of the tile list, in submission order
+	uint32_t cellOff[kMaxGroups + 1];    // list offsets of this tile's cells (clamped to the list capacity)
+	uint32_t lgKey[kTileLargeCap], lgCode[kTileLargeCap];   // queued large items that cover this tile
+	uint8_t lgGroup[kTileLargeCap];
+	alignas(4) uint16_t lgPerGroup[kMaxGroups];
+	int lgCount;
 	int firstBad;
+	int sortCount;
 };
+static_assert(offsetof(TileShared, ec) % 8 == 0 && sizeof(int) * 9 * kBatch >= 8 * kSortCap, "sort scratch aliases ec/edx/edy");
 
 struct TileArgs {
 	FrameParams fp;
@@ -61,9 +71,10 @@ struct TileArgs {
 	const float4* ptvb;
 	const TriRec* triRecs;
 	const ClipRec* clipRecs;
-	const uint32_t* lists;
-	const uint32_t* tileBase;
-	const uint32_t* tileCount;
+	const uint2* lists;                  // (order key, triangle code) entries, unordered within a tile
+	const uint32_t* tileBase;            // [tile]: list offset of the tile's first cell, + the total at the end
+	const uint32_t* cellRel;             // [tile * groups + g]: offset of the cell inside the tile's list (groups > 1)
+	const LargeItem* large;              // queued large items (kernels.cuh)
 	Counters* ctr; };
 
 __device__ __forceinline__ bool top_left(int dy, int dx) { return (dy > 0) || (dy == 0 && dx > 0); }
@@ -137,7 +148,7 @@ __device__ __forceinline__ void setup_edges(TileShared& sh, int slot, bool wide,
 __device__ __forceinline__ uint3 entry_owner(const TileArgs& A, uint32_t id) {
 	if (id & kFanIdBit) {
 		const ClipRec& rec = A.clipRecs[(id & ~kFanIdBit) >> 3];
-		return make_uint3(rec.draw, rec.key, rec.state); }
+		return make_uint3(rec.draw, rec.key, rec.state & 0xffffu); }
 	const uint4 w = __ldg(reinterpret_cast<const uint4*>(A.triRecs + id) + 4);   // key, state, pad, pad
 	const uint32_t draw = __ldg(reinterpret_cast<const uint32_t*>(A.triRecs + id) + 15);
 	return make_uint3(draw, w.x, w.y); }
@@ -553,9 +564,213 @@ __device__ __forceinline__ uint32_t linear8(float f) {
 	r = sse_max(r, 0.0f);
 	return static_cast<uint32_t>(cvtt(r * 255.0f)); }
 
-__global__ void __launch_bounds__(kTileThreads, 4)
+// Brings the next entries of the tile's list into sh.sorted, in submission (order-key) order, and
+// returns how many.  The list is a sequence of cells (kernels.cuh); cells follow each other in
+// submission order, entries inside a cell arrive in any order -- almost: every warp of K5 appends
+// the entries it has for a cell as ONE ascending run, and runs of different warps cover disjoint
+// key ranges (clip fans aside).  Three ways to order a cell, cheapest first:
+//   A  cells that fit one raster batch are taken whole, several at a time, and rank-sorted inside
+//      each cell (keys are unique, so the rank is the position);
+//   B  a longer cell is a few hundred runs: find them (descents of the key sequence), rank the runs
+//      by first key (K5 flags the first entry of every run), check that they do not interleave, and gather entries run by run -- no
+//      per-entry sort, any length;
+//   C  if the runs do interleave (or there are too many): key ranges [nextKey, hi] are selected
+//      with one pass over the cell per range (halved until it fits) and sorted bitonically.
+// All threads of the CTA must call it.
+constexpr int kRunCap = 1024;
+
+struct ListCursor {
+	int g;                 // next cell
+	uint32_t taken;        // entries already taken from cell g (modes B and C)
+	int mode;              // of cell g: 0 = undecided / B, 2 = C
+	uint32_t nextKey;      // C: pending entries of cell g have order keys >= nextKey
+	uint32_t span; };
+
+__device__ __forceinline__ void sort_scratch(TileShared& sh, uint2* scr, const int n, const uint32_t begin, const int g0, const int gEnd) {
+	const int t = threadIdx.x;
+	if (n <= kTileThreads) {
+		// rank sort inside each cell (cells are already in order): entry t finds its cell, then counts
+		// the smaller keys of that cell
+		if (t < n) {
+			int lo = g0, hi = gEnd - 1;
+			while (lo < hi) {
+				const int mid = (lo + hi + 1) >> 1;
+				if (sh.cellOff[mid] - begin <= static_cast<uint32_t>(t)) { lo = mid; } else { hi = mid - 1; } }
+			const int cb = (gEnd > g0) ? static_cast<int>(sh.cellOff[lo] - begin) : 0;
+			const int ce = (gEnd > g0) ? static_cast<int>(sh.cellOff[lo + 1] - begin) : n;
+			const uint2 mine = scr[t];
+			int rank = cb;
+			for (int j = cb; j < ce; ++j) { rank += (scr[j].y < mine.y) ? 1 : 0; }
+			sh.sorted[rank] = mine.x; } }
+	else {
+		int P = 512;
+		while (P < n) { P <<= 1; }
+		unsigned long long* keys = reinterpret_cast<unsigned long long*>(scr);
+		for (int i = n + t; i < P; i += kTileThreads) { keys[i] = ~0ull; }
+		__syncthreads();
+		for (int k = 2; k <= P; k <<= 1) {
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				for (int i = t; i < P; i += kTileThreads) {
+					const int x = i ^ j;
+					if (x > i) {
+						const unsigned long long a = keys[i], b = keys[x];
+						if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[x] = a; } } }
+				__syncthreads(); } }
+		for (int i = t; i < n; i += kTileThreads) { sh.sorted[i] = scr[i].x; } }
+	__syncthreads(); }
+
+__device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restrict__ lists, const int G, const uint32_t totalKeys,
+                                          ListCursor& lc) {
+	const int t = threadIdx.x;
+	const int warp = t >> 5, lane = t & 31;
+	uint2* scr = reinterpret_cast<uint2*>(&sh.ec[0][0]);   // (code, key): key is the high word of the 64-bit view
+	__syncthreads();   // the previous batch is done with the batch records (scratch) and sh.sorted
+	while (lc.g < G && sh.cellOff[lc.g + 1] == sh.cellOff[lc.g] && sh.lgPerGroup[lc.g] == 0) { ++lc.g; }
+	if (lc.g >= G) { return 0; }
+	const uint32_t begin = sh.cellOff[lc.g];
+	const uint32_t listSize = sh.cellOff[lc.g + 1] - begin;
+	const uint32_t nlarge0 = sh.lgPerGroup[lc.g];
+	const uint32_t size0 = listSize + nlarge0;      // entries of cell g: its part of the list + queued large items
+	const uint2* list = lists + begin;
+
+	if (size0 <= static_cast<uint32_t>(kBatch)) {
+		// ---- A: whole cells ------------------------------------------------------------------
+		const int g0 = lc.g;
+		int gEnd = g0 + 1;
+		uint32_t nl = nlarge0;
+		while (gEnd < G && (sh.cellOff[gEnd + 1] - begin) + nl + sh.lgPerGroup[gEnd] <= static_cast<uint32_t>(kBatch)) { nl += sh.lgPerGroup[gEnd]; ++gEnd; }
+		const int nlist = static_cast<int>(sh.cellOff[gEnd] - begin);
+		const int n = nlist + static_cast<int>(nl);
+		if (t < nlist) { const uint2 e = __ldg(list + t); scr[t] = make_uint2(e.y & ~kRunStartBit, e.x); }
+		if (nl) {
+			if (t == 0) { sh.sortCount = nlist; }
+			__syncthreads();
+			if (t < sh.lgCount && sh.lgGroup[t] >= g0 && sh.lgGroup[t] < gEnd) { scr[atomicAdd(&sh.sortCount, 1)] = make_uint2(sh.lgCode[t], sh.lgKey[t]); } }
+		lc.g = gEnd;
+		__syncthreads();
+		// (with queued items mixed in, cells are no longer contiguous in the scratch: rank over everything)
+		sort_scratch(sh, scr, n, begin, nl ? 0 : g0, nl ? 0 : gEnd);
+		return n; }
+
+	if (lc.mode != 2 && nlarge0 == 0) {
+		// ---- B: runs -------------------------------------------------------------------------
+		uint32_t* rStart = reinterpret_cast<uint32_t*>(&sh.ec[0][0]);   // 4 x kRunCap words inside the batch records
+		uint32_t* rKey = rStart + kRunCap;
+		uint32_t* rOrder = rKey + kRunCap;
+		uint32_t* rPre = rOrder + kRunCap;
+		static_assert(offsetof(TileShared, vref) - offsetof(TileShared, ec) >= 16 * kRunCap, "run scratch aliases the batch records");
+		uint32_t* warpCnt = reinterpret_cast<uint32_t*>(sh.queue);
+		if (t == 0) { sh.sortCount = 0; sh.firstBad = 0; }
+		__syncthreads();
+		for (uint32_t strip = 0; strip < size0; strip += kTileThreads) {
+			const uint32_t i = strip + t;
+			uint32_t key = 0;
+			bool isStart = false;
+			if (i < size0) {
+				const uint2 e = __ldg(list + i);
+				key = e.x;
+				isStart = (e.y & kRunStartBit) != 0; }
+			const unsigned m = __ballot_sync(0xffffffffu, isStart);
+			if (lane == 0) { warpCnt[warp] = __popc(m); }
+			__syncthreads();
+			uint32_t idx = static_cast<uint32_t>(sh.sortCount) + __popc(m & ((1u << lane) - 1u));
+			uint32_t total = 0;
+#pragma unroll
+			for (int w = 0; w < kTileThreads / 32; ++w) { const uint32_t c = warpCnt[w]; if (w < warp) { idx += c; } total += c; }
+			if (isStart && idx < static_cast<uint32_t>(kRunCap)) { rStart[idx] = i; rKey[idx] = key; }
+			__syncthreads();
+			if (t == 0) { sh.sortCount += static_cast<int>(total); } }
+		__syncthreads();
+		const int R = sh.sortCount;
+		if (R <= kRunCap) {
+			// rank the runs by first key; lengths follow from the next run in memory order
+			for (int r = t; r < R; r += kTileThreads) {
+				const uint32_t k = rKey[r];
+				int rank = 0;
+				for (int q = 0; q < R; ++q) { rank += (rKey[q] < k) ? 1 : 0; }
+				rOrder[rank] = static_cast<uint32_t>(r); }
+			__syncthreads();
+			// runs must not interleave: the last key of a run lies below the first key of the next one
+			for (int p = t; p + 1 < R; p += kTileThreads) {
+				const uint32_t r = rOrder[p], nx = rOrder[p + 1];
+				const uint32_t end = (r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0;
+				if (__ldg(list + end - 1).x > rKey[nx]) { sh.firstBad = 1; } }
+			// exclusive prefix of the run lengths in key order (serial per thread over R / 256 runs, then a block scan)
+			const int per = (R + kTileThreads - 1) / kTileThreads;
+			const int p0 = min(t * per, R), p1 = min(p0 + per, R);
+			uint32_t sum = 0;
+			for (int p = p0; p < p1; ++p) {
+				const uint32_t r = rOrder[p];
+				sum += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
+			uint32_t incl = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) { incl += v; } }
+			__syncthreads();   // (warpCnt reuse; sh.firstBad complete)
+			if (lane == 31) { warpCnt[warp] = incl; }
+			__syncthreads();
+			uint32_t before = incl - sum;
+			for (int w = 0; w < warp; ++w) { before += warpCnt[w]; }
+			for (int p = p0; p < p1; ++p) {
+				const uint32_t r = rOrder[p];
+				rPre[p] = before;
+				before += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
+			__syncthreads();
+			if (sh.firstBad == 0) {
+				const int n = static_cast<int>(min(static_cast<uint32_t>(kSortCap), size0 - lc.taken));
+				for (int i = t; i < n; i += kTileThreads) {
+					const uint32_t pos = lc.taken + static_cast<uint32_t>(i);
+					int lo = 0, hi = R - 1;
+					while (lo < hi) {
+						const int mid = (lo + hi + 1) >> 1;
+						if (rPre[mid] <= pos) { lo = mid; } else { hi = mid - 1; } }
+					sh.sorted[i] = __ldg(list + rStart[rOrder[lo]] + (pos - rPre[lo])).y & ~kRunStartBit; }
+				lc.taken += static_cast<uint32_t>(n);
+				if (lc.taken >= size0) { ++lc.g; lc.taken = 0; lc.mode = 0; }
+				__syncthreads();
+				return n; } }
+		// interleaved or too many runs (only before anything was taken: the run structure does not change)
+		lc.mode = 2;
+		__syncthreads(); }
+
+	// ---- C: key ranges -------------------------------------------------------------------------
+	if (lc.taken == 0) {
+		lc.nextKey = 0;
+		const uint32_t rounds = (size0 + (3 * kSortCap / 4) - 1) / (3 * kSortCap / 4);
+		lc.span = max(totalKeys / (rounds * static_cast<uint32_t>(G)), 1u); }
+	int n;
+	while (true) {
+		if (t == 0) { sh.sortCount = 0; }
+		__syncthreads();
+		const uint32_t room = 0xffffffffu - lc.nextKey;
+		const uint32_t hi = lc.nextKey + min(lc.span - 1u, room);
+		for (uint32_t i = t; i < listSize; i += kTileThreads) {
+			const uint2 e = __ldg(list + i);
+			if (e.x >= lc.nextKey && e.x <= hi) {
+				const int slot = atomicAdd(&sh.sortCount, 1);
+				if (slot < kSortCap) { scr[slot] = make_uint2(e.y & ~kRunStartBit, e.x); } } }
+		if (nlarge0 && t < sh.lgCount && sh.lgGroup[t] == lc.g && sh.lgKey[t] >= lc.nextKey && sh.lgKey[t] <= hi) {
+			const int slot = atomicAdd(&sh.sortCount, 1);
+			if (slot < kSortCap) { scr[slot] = make_uint2(sh.lgCode[t], sh.lgKey[t]); } }
+		__syncthreads();
+		n = sh.sortCount;
+		__syncthreads();
+		if (n > kSortCap) { lc.span = max(lc.span >> 1, 1u); continue; }
+		if (n == 0 && hi != 0xffffffffu) { lc.nextKey = hi + 1u; lc.span = (lc.span < 0x80000000u) ? lc.span * 2u : 0xffffffffu; continue; }
+		if (n < kSortCap / 4) { lc.span = (lc.span < 0x80000000u) ? lc.span * 2u : 0xffffffffu; }
+		lc.nextKey = hi + 1u;
+		break; }
+	lc.taken += static_cast<uint32_t>(n);
+	if (lc.taken >= size0 || n == 0) { ++lc.g; lc.taken = 0; lc.mode = 0; }
+	sort_scratch(sh, scr, n, begin, 0, 0);
+	return n; }
+
+#ifndef RSR_TILE_CTAS
+#define RSR_TILE_CTAS 3
+#endif
+__global__ void __launch_bounds__(kTileThreads, RSR_TILE_CTAS)
 tile_kernel(const __grid_constant__ TileArgs A) {
-	__shared__ TileShared sh;
+	extern __shared__ __align__(16) unsigned char tileSmem[];
+	TileShared& sh = *reinterpret_cast<TileShared*>(tileSmem);
 	const int t = threadIdx.x;
 	const int tile = blockIdx.x;
 	const int tileX = tile % A.fp.tilesX, tileY = tile / A.fp.tilesX;
@@ -569,12 +784,36 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	const int rl = (ox / A.fp.refTileW) * A.fp.refTileW, rt = (oy / A.fp.refTileH) * A.fp.refTileH;
 	const int rr = min(rl + A.fp.refTileW, A.fp.width), rb = min(rt + A.fp.refTileH, A.fp.height);
 
-	const uint32_t* list = A.lists + A.tileBase[tile];
-	const uint32_t listLen = A.tileCount[tile];
+	// this tile's cells; a frame whose lists overflowed is rendered again by the host: stay inside the buffer meanwhile
+	const int G = A.fp.groups;
+	for (int g = t; g <= G; g += kTileThreads) {
+		uint32_t off = __ldg(A.tileBase + tile + (g == G ? 1 : 0));
+		if (g > 0 && g < G) { off += __ldg(A.cellRel + static_cast<size_t>(tile) * G + g); }
+		sh.cellOff[g] = min(off, A.fp.listCapacity); }
+	if (t < kMaxGroups) { sh.lgPerGroup[t] = 0; }
+	if (t == 0) { sh.lgCount = 0; }
+	__syncthreads();
+	// queued large items (kernels.cuh) that cover this tile: a short scan instead of one list entry per tile
+	const unsigned nLarge = min(A.ctr->nLarge, A.fp.largeCapacity);
+	for (unsigned i = t; i < nLarge; i += kTileThreads) {
+		const LargeItem it = A.large[i];
+		const int tx0 = it.packed & 63, ty0 = (it.packed >> 6) & 63, tx1 = (it.packed >> 12) & 63, ty1 = (it.packed >> 18) & 63;
+		if (tileX >= tx0 && tileX <= tx1 && tileY >= ty0 && tileY <= ty1) {
+			const int slot = atomicAdd(&sh.lgCount, 1);
+			if (slot < kTileLargeCap) {
+				sh.lgKey[slot] = it.okey; sh.lgCode[slot] = it.code; sh.lgGroup[slot] = static_cast<uint8_t>(it.group);
+				atomicAdd(reinterpret_cast<unsigned int*>(sh.lgPerGroup) + (it.group >> 1), (it.group & 1u) ? 0x10000u : 1u); } } }
+	__syncthreads();
+	if (sh.lgCount > kTileLargeCap) {
+		__syncthreads();
+		if (t == 0) { atomicOr(&A.ctr->overflow, 8u); sh.lgCount = kTileLargeCap; }
+		__syncthreads(); }
+	const uint32_t listLen = (sh.cellOff[G] - sh.cellOff[0]) + static_cast<uint32_t>(sh.lgCount);
+	ListCursor lc{0, 0u, 0, 0u, 1u};
+	int chunkN = 0, chunkPos = 0;
 	if (listLen) {
 #pragma unroll
 		for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = __ldg(A.luts->rcp + k * kTileThreads + t); } }
-	uint32_t cursor = 0;
 	unsigned frags = 0;
 
 #pragma unroll
@@ -590,10 +829,13 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	// of tiny draws (one per textured quad) still fills whole batches.
 	int ci = 0;
 	while (true) {
+		if (chunkPos == chunkN && lc.g < G) {
+			chunkN = load_chunk(sh, A.lists, G, A.fp.totalKeys, lc);
+			chunkPos = 0; }
 		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
 		uint32_t key0 = 0;
-		if (cursor < listLen) {
-			const uint3 o = entry_owner(A, __ldg(list + cursor));
+		if (chunkPos < chunkN) {
+			const uint3 o = entry_owner(A, sh.sorted[chunkPos]);
 			di = static_cast<int>(o.x);
 			key0 = o.y; }
 		// non-draw commands that precede that draw
@@ -656,14 +898,14 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		if (di >= A.fp.ndraws) { break; }
 
 		const int bound = (ci < A.fp.ncmds) ? A.cmds[ci].beforeDraw : 0x7fffffff;   // draws >= bound come after cmds[ci]
-		const int avail = static_cast<int>(min(static_cast<uint32_t>(kBatch), listLen - cursor));
+		const int avail = min(kBatch, chunkN - chunkPos);
 		__syncthreads();   // previous batch fully rasterised before its records are overwritten
 		if (t == 0) { sh.firstBad = avail; }
 		__syncthreads();
 		uint32_t myId = 0;
 		uint32_t myState = 0;
 		if (t < avail) {
-			myId = __ldg(list + cursor + t);
+			myId = sh.sorted[chunkPos + t];
 			const uint3 o = entry_owner(A, myId);
 			myState = o.z;
 			if (static_cast<int>(o.x) >= bound || o.y != key0) { atomicMin(&sh.firstBad, t); } }
@@ -691,15 +933,15 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, key0, nb, ox, oy, queued); break;
 		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, key0, nb, ox, oy, queued); break;
 		default: break; }
-		cursor += static_cast<uint32_t>(max(nb, 1)); }
+		chunkPos += max(nb, 1); }
 
 	// fragment statistics: one atomic per CTA
 	for (int o = 16; o > 0; o >>= 1) { frags += __shfl_down_sync(0xffffffffu, frags, o); }
-	__shared__ unsigned blockFrags;
-	if (t == 0) { blockFrags = 0; }
 	__syncthreads();
-	if (lane == 0 && frags) { atomicAdd(&blockFrags, frags); }
+	if (t == 0) { sh.sortCount = 0; }
 	__syncthreads();
-	if (t == 0 && blockFrags) { atomicAdd(&A.ctr->fragments, static_cast<unsigned long long>(blockFrags)); } }
+	if (lane == 0 && frags) { atomicAdd(&sh.sortCount, static_cast<int>(frags)); }
+	__syncthreads();
+	if (t == 0 && sh.sortCount) { atomicAdd(&A.ctr->fragments, static_cast<unsigned long long>(sh.sortCount)); } }
 
 }  // namespace rsr
