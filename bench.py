@@ -264,7 +264,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     gpu = rsr_b200.GPU(local_rank)
-    gpu.set_profiling(True)
+    gpu.set_profiling(1)           # events around the tile kernel (roofline) and the frame; per-stage events in a separate pass
     stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
@@ -302,13 +302,21 @@ def main():
         with torch.cuda.stream(stream):
             ev[i][1].record(stream)
         gpu.Sync()
-        st = gpu.stage_ms()
-        tile_ms.append(st["tile"])
-        for k, v in st.items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        tile_ms.append(gpu.stage_ms()["tile"])
         stats = gpu.stats()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    # per-stage breakdown: a few extra, untimed frames with an event after every kernel
+    gpu.set_profiling(2)
+    stage_acc, nstage = {}, 8
+    for i in range(nstage):
+        with torch.cuda.stream(stream):
+            flush.fill_(i & 0xff)
+        frame_resident(i)
+        gpu.Sync()
+        for k, v in gpu.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / nstage
+    gpu.set_profiling(0)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
@@ -365,7 +373,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": tile_avg_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                "stage_ms": {k: v / args.steps for k, v in stage_acc.items()}}
+                "stage_ms": stage_acc}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -232,13 +232,17 @@ typedef struct RsrStats {
 	uint64_t kernel_launches;       /* kernels launched for the frame */
 	uint64_t h2d_bytes;             /* bytes copied host->device for the frame (upload arena) */
 	uint64_t d2h_bytes;             /* bytes copied device->host for the frame (store destinations) */
+	uint64_t host_record_ns;        /* host time spent recording the frame (begin_frame .. end_frame, all calls) */
+	uint64_t host_submit_ns;        /* host time spent in rsrcu_end_frame (tables, upload, launches) */
 } RsrStats;
 int rsrcu_get_stats(rsrcu_ctx* ctx, RsrStats* out);
 
 /* last frame's device time per stage in milliseconds (CUDA events on the context stream):
- * [0] vertex [1] setup+clip [2] bin count [3] bin scan [4] bin fill [5] tile raster+resolve
- * [6] whole frame incl. uploads and readback.  Requires rsrcu_set_profiling(ctx, 1). */
-int rsrcu_set_profiling(rsrcu_ctx* ctx, int enabled);
+ * [0] vertex [1] setup+clip+tile counts [2] unused (0) [3] cell scan (frames with several list cells
+ * per tile) [4] list fill [5] tile sort+raster+resolve [6] whole frame incl. upload.
+ * level 0: off; 1: events around the tile kernel and the frame only ([5], [6]); 2: every stage (the
+ * extra events cost a few microseconds of stream time per frame). */
+int rsrcu_set_profiling(rsrcu_ctx* ctx, int level);
 int rsrcu_get_stage_ms(rsrcu_ctx* ctx, float* ms7);
 
 #ifdef __cplusplus

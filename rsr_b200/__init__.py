@@ -73,7 +73,8 @@ class RsrState(C.Structure):
 
 class RsrStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("triangles_submitted", "triangles_binned", "triangles_clipped",
-                                           "bin_entries", "fragments_shaded", "kernel_launches", "h2d_bytes", "d2h_bytes")]
+                                           "bin_entries", "fragments_shaded", "kernel_launches", "h2d_bytes", "d2h_bytes",
+                                           "host_record_ns", "host_submit_ns")]
 
 
 _lib = None
@@ -464,7 +465,9 @@ class GPU:
         self._check(self.L.rsrcu_get_stats(self.h, C.byref(st)))
         return {n: int(getattr(st, n)) for n, _ in RsrStats._fields_}
 
-    def set_profiling(self, on: bool): self._check(self.L.rsrcu_set_profiling(self.h, int(bool(on))))
+    def set_profiling(self, level):
+        """0 / False: off; 1 / True: CUDA events around the tile kernel and the frame; 2: around every stage"""
+        self._check(self.L.rsrcu_set_profiling(self.h, int(level)))
 
     def stage_ms(self) -> dict:
         ms = (C.c_float * 7)()

@@ -117,8 +117,11 @@ struct Counters {
 	unsigned long long entries;      // (triangle, tile) pairs
 	unsigned long long fragments; }; // pixels written
 
-__device__ __forceinline__ int find_draw(const DevDraw* __restrict__ draws, int ndraws, uint32_t job, bool vertexJobs) {
-	int lo = 0, hi = ndraws - 1;
+// Draw that owns a vertex / triangle job.  The host tabulates, per block of 256 jobs, the draw of the
+// block's first job: the search only covers the draws that start inside the block (usually none).
+__device__ __forceinline__ int find_draw(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, uint32_t job,
+                                         bool vertexJobs) {
+	int lo = static_cast<int>(__ldg(blockDraw + (job >> 8))), hi = static_cast<int>(__ldg(blockDraw + (job >> 8) + 1));
 	while (lo < hi) {
 		const int mid = (lo + hi + 1) >> 1;
 		const uint32_t b = vertexJobs ? draws[mid].vjobBase : draws[mid].pjobBase;
@@ -156,11 +159,11 @@ __device__ __forceinline__ void run_vertex_program(const DevState& s, const Vert
 	default: pos[0] = pos[1] = pos[2] = 0.0f; pos[3] = 1.0f; break; } }
 
 __global__ void __launch_bounds__(256)
-vertex_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ states, FrameParams fp,
+vertex_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
               const ApproxLuts* __restrict__ luts, float4* __restrict__ ptvb, uint8_t* __restrict__ vflags) {
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	if (job >= fp.totalVJobs) { return; }
-	const int di = find_draw(draws, fp.ndraws, job, true);
+	const int di = find_draw(draws, blockDraw, job, true);
 	const DevDraw& d = draws[di];
 	const DevState& s = states[d.state];
 	const uint32_t local = job - d.vjobBase;
@@ -367,42 +370,65 @@ __device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t o
 		const unsigned slot = atomicAdd(&ctr->nLarge, 1u);
 		if (slot < fp.largeCapacity) { B.large[slot] = LargeItem{packed, okey, code, group}; }
 		else { atomicOr(&ctr->overflow, 4u); } }
-	// Small items that cover up to 4 tiles (dense meshes: the long lists) are walked tile by tile in
-	// increasing tile index: each step serves the smallest tile index any lane is at, and the lanes
-	// at that tile take consecutive slots in lane (= submission) order with one atomic.  A warp thus
-	// adds ONE ascending run to a cell, which lets the tile kernel order long cells by runs.
+	// One-tile items (dense meshes of small triangles: the long lists): the lanes of a warp that aim at
+	// the same cell take consecutive slots in lane (= submission) order with ONE atomic, all cells at
+	// once.  A warp thus adds one ascending run to a cell, which lets the tile kernel order long cells
+	// run by run instead of entry by entry.
 	const bool small = valid && !large;
-	const bool walked = small && ntile <= 4;
-	int cx = tx0, cy = ty0;
-	uint32_t cur = walked ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu;
-	while (true) {
-		const uint32_t tile = __reduce_min_sync(0xffffffffu, cur);
-		if (tile == 0xffffffffu) { break; }
-		const int leader = __ffs(__ballot_sync(0xffffffffu, cur == tile)) - 1;
-		const uint32_t g = __shfl_sync(0xffffffffu, group, leader);   // (lanes differ in group only among clip fans)
-		const bool mine = (cur == tile) && (group == g);
-		const unsigned m = __ballot_sync(0xffffffffu, mine);
-		const uint32_t cell = tile * static_cast<uint32_t>(fp.groups) + g;
+	const bool single = small && ntile == 1 && fp.groups == 1;   // (frames with several cells per tile: see the walk below)
+	if (__any_sync(0xffffffffu, single)) {
+		const uint32_t cell = single ? static_cast<uint32_t>((ty0 * fp.tilesX + tx0) * fp.groups) + group : (0xffffff00u | lane);
+		const unsigned peers = __match_any_sync(0xffffffffu, cell);
+		const int leader = __ffs(peers) - 1;
+		const uint32_t rank = __popc(peers & ltMask);
 		if (!FILL) {
-			if (static_cast<int>(lane) == leader) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(m))); } }
+			if (single && rank == 0) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(peers))); } }
 		else {
 			uint32_t base = 0;
-			if (static_cast<int>(lane) == leader) {
-				base = atomicAdd(B.cellCursor + cell, static_cast<uint32_t>(__popc(m))) + __ldg(B.tileBase + tile);
+			if (single && rank == 0) {
+				base = atomicAdd(B.cellCursor + cell, static_cast<uint32_t>(__popc(peers))) + __ldg(B.tileBase + ty0 * fp.tilesX + tx0);
 				if (fp.groups > 1) { base += __ldg(B.cellRel + cell); } }
 			base = __shfl_sync(0xffffffffu, base, leader);
-			if (mine) {
-				const uint32_t rank = __popc(m & ltMask);
+			if (single) {
 				const uint32_t pos = base + rank;
-				if (pos < fp.listCapacity) { B.lists[pos] = make_uint2(okey, rank ? code : (code | kRunStartBit)); } } }
-		if (mine) {
-			++cx;
-			if (cx > tx1) { cx = tx0; ++cy; }
-			cur = (cy <= ty1) ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu; } }
+				if (pos < fp.listCapacity) { B.lists[pos] = make_uint2(okey, rank ? code : (code | kRunStartBit)); } } } }
+
+	// Frames with millions of triangles (several cells per tile): items of up to 4 tiles are walked tile by
+	// tile in increasing tile index -- each step serves the smallest tile index any lane is at, the
+	// lanes at that tile take consecutive slots in lane order with one atomic -- so that straddling
+	// triangles, too, stay inside the one ascending run per warp and cell.  (One atomic round trip per step: too slow for the
+	// medium-sized triangles of ordinary frames, whose short lists do not need runs.)
+	const bool walked = small && ntile <= 4 && fp.groups > 1;
+	if (fp.groups > 1) {
+		int cx = tx0, cy = ty0;
+		uint32_t cur = walked ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu;
+		while (true) {
+			const uint32_t tile = __reduce_min_sync(0xffffffffu, cur);
+			if (tile == 0xffffffffu) { break; }
+			const int leader = __ffs(__ballot_sync(0xffffffffu, cur == tile)) - 1;
+			const uint32_t g = __shfl_sync(0xffffffffu, group, leader);   // (lanes differ in group only among clip fans)
+			const bool mine = (cur == tile) && (group == g);
+			const unsigned m = __ballot_sync(0xffffffffu, mine);
+			const uint32_t cell = tile * static_cast<uint32_t>(fp.groups) + g;
+			if (!FILL) {
+				if (static_cast<int>(lane) == leader) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(m))); } }
+			else {
+				uint32_t base = 0;
+				if (static_cast<int>(lane) == leader) {
+					base = atomicAdd(B.cellCursor + cell, static_cast<uint32_t>(__popc(m))) + __ldg(B.tileBase + tile) + __ldg(B.cellRel + cell); }
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if (mine) {
+					const uint32_t rank = __popc(m & ltMask);
+					const uint32_t pos = base + rank;
+					if (pos < fp.listCapacity) { B.lists[pos] = make_uint2(okey, rank ? code : (code | kRunStartBit)); } } }
+			if (mine) {
+				++cx;
+				if (cx > tx1) { cx = tx0; ++cy; }
+				cur = (cy <= ty1) ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu; } } }
 
 	// Items that cover more tiles make short lists (few of them fit a tile): every lane appends on its
-	// own, four independent atomics in flight.
-	if (small && !walked) {
+	// own, four independent atomics in flight; each entry is a run of its own.
+	if (small && !single && !walked) {
 		for (int i0 = 0; i0 < ntile; i0 += 4) {
 			uint32_t cell[4], pos[4];
 #pragma unroll
@@ -479,14 +505,14 @@ __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint
 		if (before > listCapacity) { atomicOr(&ctr->overflow, 2u); } } }
 
 __global__ void __launch_bounds__(256)
-setup_kernel(const DevDraw* __restrict__ draws, const DevState* __restrict__ states, FrameParams fp,
+setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
              const ApproxLuts* __restrict__ luts, const float4* __restrict__ ptvb, const uint8_t* __restrict__ vflags,
              uint2* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
              BinArgs B, uint32_t* __restrict__ tileBase, Counters* __restrict__ ctr) {
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	uint2 myInfo = make_uint2(kReject, 0u);
 	if (job < fp.totalPJobs) {
-		const int di = find_draw(draws, fp.ndraws, job, false);
+		const int di = find_draw(draws, blockDraw, job, false);
 		const DevDraw& d = draws[di];
 		const DevState& s = states[d.state];
 		const uint32_t local = job - d.pjobBase;

@@ -3,6 +3,7 @@
 // (src/rgl/rglv/rglv_gpu.cxx:90-432); the CPU job system (src/rcl/rclmt) has no counterpart here:
 // tiles are CTAs of one grid launch, frames are ordered by the stream.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -82,6 +83,11 @@ struct UploadArena {
 
 struct StaticAlloc { void* dev; size_t bytes; };
 
+// direct-mapped front of the static cache: a frame binds the same few hundred pointers thousands of times
+struct PtrCacheEntry { const void* host; size_t bytes; void* dev; };
+constexpr size_t kPtrCacheSize = 2048;
+inline size_t ptrCacheIndex(const void* p) { return static_cast<size_t>((reinterpret_cast<uintptr_t>(p) >> 4) * 0x9E3779B97F4A7C15ull >> 53); }
+
 struct PendingCopy { void* hostDst; const void* devSrc; size_t rowBytes; size_t rows; size_t hostPitch; size_t devPitch; };
 
 // a device pointer that is either absolute (static cache) or an offset into the frame arena
@@ -89,12 +95,17 @@ struct DevRef { bool arena{false}; size_t off{0}; const void* abs{nullptr}; bool
 
 struct HostTex { DevRef ref; uint32_t texelCount{0}; int width{8}, height{8}, stride{8}, filter{0}; };
 
+// one state snapshot: the device record, built once when the snapshot is taken (pointer fields hold
+// encoded references until rsrcu_end_frame knows the arena's device address), plus what draw-time
+// validation needs
 struct HostState {
-	RsrState st;
-	DevRef buffers[16];
+	DevState ds;
 	size_t bufferFloats[16];
-	HostTex tus[2];
-	DevRef tu3; int tu3dim{256}; };
+	int programId, key;
+	bool posNull, tex0Null, hasArenaRef;
+	int tex0Width, tex0Height, tex0Stride; };
+
+constexpr uint64_t kArenaRefBit = 1ull << 63;   // encoded reference: offset into the frame arena instead of a device address
 
 struct HostDraw {
 	DevDraw d;
@@ -110,7 +121,7 @@ struct rsrcu_ctx {
 	cudaEvent_t evCopied[2]{};
 	int outSlot{0};                     // store targets are double-buffered
 	cudaEvent_t evStage[8]{};
-	bool profiling{false};
+	int profiling{0};                   // 0 off, 1 tile kernel + whole frame, 2 every stage
 	float stageMs[7]{};
 
 	ApproxLuts hostLuts;
@@ -120,7 +131,8 @@ struct rsrcu_ctx {
 	bool inFrame{false};
 	bool framePending{false};
 	int width{0}, height{0}, refTileW{64}, refTileH{64}, postTileW{64}, postTileH{64};
-	RsrState curState;
+	RsrState curState;                 // copy of the caller's state (direct API); packed streams are read in place
+	const RsrState* curStatePtr{nullptr};
 	bool haveState{false};
 	bool stateDirty{true};
 	DevRef curBuffers[16];
@@ -138,9 +150,11 @@ struct rsrcu_ctx {
 	cudaEvent_t arenaFree[2]{};
 	int cur{0};
 	std::unordered_map<const void*, StaticAlloc> staticCache;
+	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr});
 
 	// device work buffers
-	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, lists, largeItems, counters;   // counters: Counters | cellCount[] | cellCursor[]
+	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, lists, largeItems;
+	DevBuf counters[2];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
 	DevBuf tcOut[2], fpOut[2], depthOut[2];
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 24};
@@ -151,6 +165,8 @@ struct rsrcu_ctx {
 	RsrStats stats{};
 	uint64_t launches{0};
 	uint64_t lastH2D{0}, lastD2H{0};
+	std::chrono::steady_clock::time_point tBegin{};
+	uint64_t recordNs{0}, submitNs{0};
 };
 
 namespace {
@@ -249,11 +265,27 @@ const void* resolve(const rsrcu_ctx* c, const DevRef& r) {
 	if (r.arena) { return static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr) + r.off; }
 	return r.abs; }
 
+template <class T>
+const T* encodeRef(const DevRef& r, bool& anyArena) {
+	if (r.null) { return nullptr; }
+	if (r.arena) { anyArena = true; return reinterpret_cast<const T*>(static_cast<uintptr_t>(kArenaRefBit | r.off)); }
+	return static_cast<const T*>(r.abs); }
+
+template <class T>
+void patchRef(const T*& p, const uint8_t* arenaDev) {
+	const uint64_t v = reinterpret_cast<uintptr_t>(p);
+	if (v & kArenaRefBit) { p = reinterpret_cast<const T*>(arenaDev + (v & ~kArenaRefBit)); } }
+
 int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef& out) {
 	if (!host || bytes == 0) { out = DevRef{}; return RSRCU_OK; }
 	if (upload == RSRCU_UPLOAD_STATIC) {
+		PtrCacheEntry& pe = c->ptrCache[ptrCacheIndex(host)];
+		if (pe.host == host && pe.bytes == bytes) {
+			out.null = false; out.arena = false; out.abs = pe.dev;
+			return RSRCU_OK; }
 		auto it = c->staticCache.find(host);
 		if (it != c->staticCache.end() && it->second.bytes == bytes) {
+			pe = PtrCacheEntry{host, bytes, it->second.dev};
 			out.null = false; out.arena = false; out.abs = it->second.dev;
 			return RSRCU_OK; }
 		if (it != c->staticCache.end()) { cudaFree(it->second.dev); c->staticCache.erase(it); }
@@ -262,6 +294,7 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 		CU(cudaMalloc(&d, bytes));
 		CU(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
 		c->staticCache[host] = StaticAlloc{d, bytes};
+		pe = PtrCacheEntry{host, bytes, d};
 		out.null = false; out.arena = false; out.abs = d;
 		return RSRCU_OK; }
 	size_t off = 0;
@@ -269,16 +302,69 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 	out.null = false; out.arena = true; out.off = off;
 	return RSRCU_OK; }
 
-// GL::MaybeUpdateState (rglv_gl.cxx:100-106): snapshot on first use after a change
+// GL::MaybeUpdateState (rglv_gl.cxx:100-106): snapshot on first use after a change.  The device
+// record (DevState) is built here, once; rsrcu_end_frame only copies it into the upload arena.
 int snapshotState(rsrcu_ctx* c) {
 	if (!c->haveState) { return fail(RSRCU_ERR_INVALID, "no state set (rsrcu_set_state) before a command"); }
 	if (!c->stateDirty && !c->states.empty()) { return RSRCU_OK; }
-	HostState hs;
-	hs.st = c->curState;
-	for (int i = 0; i < 16; ++i) { hs.buffers[i] = c->curBuffers[i]; hs.bufferFloats[i] = c->curBufferFloats[i]; }
-	hs.tus[0] = c->curTus[0]; hs.tus[1] = c->curTus[1];
-	hs.tu3 = c->curTu3; hs.tu3dim = c->curTu3dim;
-	c->states.push_back(hs);
+	c->states.emplace_back();
+	HostState& hs = c->states.back();
+	const RsrState& s = *c->curStatePtr;
+	DevState& ds = hs.ds;
+	const int W = c->width, H = c->height;
+	std::memcpy(ds.vm, s.view_matrix, sizeof(ds.vm));
+	std::memcpy(ds.pm, s.projection_matrix, sizeof(ds.pm));
+	// MakeMatrices (rglv_gpu_impl.hxx:45-51)
+	if (s.program_id == 9 || s.program_id == 10) {   // only OBJ2S and Envmap read gl_NormalMatrix
+		float inv[16];
+		mat4Inverse(s.view_matrix, inv);
+		mat4Transpose(inv, ds.nm); }
+	mat4Mul(s.projection_matrix, s.view_matrix, ds.vpm);
+	if (s.uniforms_valid) { std::memcpy(ds.uniforms, s.uniforms, sizeof(ds.uniforms)); }
+	// GPU::DSDO (rglv_gpu.hxx:265-270): integer halves
+	const int vw = (s.viewport_size[0] > 0 && s.viewport_size[1] > 0) ? s.viewport_size[0] : W;
+	const int vh = (s.viewport_size[0] > 0 && s.viewport_size[1] > 0) ? s.viewport_size[1] : H;
+	ds.DSx = static_cast<float>(vw / 2);
+	ds.DSy = static_cast<float>(-vh / 2);
+	ds.DOx = static_cast<float>(vw / 2 + s.viewport_origin[0]);
+	ds.DOy = static_cast<float>(H - (vh / 2 + s.viewport_origin[1]));
+	std::memcpy(ds.clearColor, s.clear_color, sizeof(ds.clearColor));
+	ds.clearDepth = s.clear_depth;
+	ds.programId = s.program_id;
+	ds.cullingEnabled = s.culling_enabled; ds.cullFace = s.cull_face;
+	if (!s.scissor_enabled) { ds.scissorX0 = 0; ds.scissorY0 = 0; ds.scissorX1 = W; ds.scissorY1 = H; }
+	else {
+		// gl_offset_and_size_to_irect (rglv_gpu.hxx:258-263)
+		const int left = s.scissor_origin[0], right = left + s.scissor_size[0];
+		const int bottom = H - s.scissor_origin[1] - 1, top = bottom - s.scissor_size[1];
+		ds.scissorX0 = left; ds.scissorY0 = top; ds.scissorX1 = right; ds.scissorY1 = bottom; }
+	ds.depthTest = s.depth_test_enabled; ds.depthFunc = s.depth_func; ds.depthWrite = s.depth_write_mask;
+	ds.colorWrite = s.color_write_mask; ds.blend = s.blending_enabled;
+	ds.color0Type = s.color0_attachment_type; ds.depthType = s.depth_attachment_type;
+	bool anyArena = false;
+	for (int b = 0; b < 16; ++b) {
+		ds.buffers[b] = encodeRef<float>(c->curBuffers[b], anyArena);
+		hs.bufferFloats[b] = c->curBufferFloats[b]; }
+	for (int u = 0; u < 2; ++u) {
+		const HostTex& ht = c->curTus[u];
+		TexUnit& tu = ds.tu[u];
+		tu.texels = encodeRef<float4>(ht.ref, anyArena);
+		tu.texelCount = ht.texelCount;
+		tu.width = ht.width; tu.height = ht.height; tu.stride = ht.stride;
+		// MakeTextureUnit (rglr_texture_sampler.cxx:314-363)
+		int power = 0;
+		while ((1 << (power + 1)) <= ht.width) { ++power; }
+		const bool isPow2 = ((1 << power) == ht.width) && ht.width == ht.height && ht.stride == ht.width;
+		tu.power = power;
+		tu.kind = !isPow2 ? 0 : (ht.filter ? 2 : 1); }
+	ds.tu3 = encodeRef<float>(c->curTu3, anyArena);
+	ds.tu3dim = c->curTu3dim;
+	hs.programId = s.program_id;
+	hs.key = keyOf(s);
+	hs.posNull = c->curBuffers[0].null;
+	hs.tex0Null = c->curTus[0].ref.null;
+	hs.tex0Width = c->curTus[0].width; hs.tex0Height = c->curTus[0].height; hs.tex0Stride = c->curTus[0].stride;
+	hs.hasArenaRef = anyArena;
 	c->stateDirty = false;
 	return RSRCU_OK; }
 
@@ -329,7 +415,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->lists, &c->largeItems, &c->counters, &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
@@ -363,6 +449,7 @@ int rsrcu_release_static(rsrcu_ctx* c) {
 	CU(cudaStreamSynchronize(c->stream));
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	c->staticCache.clear();
+	std::fill(c->ptrCache.begin(), c->ptrCache.end(), PtrCacheEntry{nullptr, 0, nullptr});
 	return RSRCU_OK; }
 
 int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int tileHBlocks) {
@@ -394,12 +481,14 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->curTus[0] = HostTex{}; c->curTus[1] = HostTex{};
 	c->curTu3 = DevRef{}; c->curTu3dim = 256;
 	c->inFrame = true;
+	c->tBegin = std::chrono::steady_clock::now();
 	return RSRCU_OK; }
 
 int rsrcu_set_state(rsrcu_ctx* c, const RsrState* st) {
 	if (!c || !st) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_set_state outside begin/end frame"); }
 	c->curState = *st;
+	c->curStatePtr = &c->curState;
 	c->haveState = true;
 	c->stateDirty = true;
 	return RSRCU_OK; }
@@ -448,7 +537,7 @@ static int pushCmd(rsrcu_ctx* c, int type, int arg, void* dst, int stride, int k
 int rsrcu_clear(rsrcu_ctx* c, int bits) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_clear outside begin/end frame"); }
 	if (bits & RSRCU_GL_STENCIL_BUFFER_BIT) { return fail(RSRCU_ERR_UNSUPPORTED, "CLEAR on STENCIL not implemented (rglv_gpu.cxx:313-315)"); }
-	if (c->haveState && c->curState.color0_attachment_type == RSRCU_RB_COLOR_DEPTH &&
+	if (c->haveState && c->curStatePtr->color0_attachment_type == RSRCU_RB_COLOR_DEPTH &&
 	    bits != (RSRCU_GL_COLOR_BUFFER_BIT | RSRCU_GL_DEPTH_BUFFER_BIT)) {
 		return fail(RSRCU_ERR_UNSUPPORTED, "must clear color and depth when using RB_COLOR_DEPTH (rglv_gpu.cxx:317-319)"); }
 	return pushCmd(c, kCmdClear, bits, nullptr, 0, 0); }
@@ -459,10 +548,16 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	int r = snapshotState(c);
 	if (r != RSRCU_OK) { return r; }
 	const HostState& hs = c->states.back();
-	const RsrState& st = hs.st;
-	const int key = keyOf(st);
-	if (!drawProgramInstalled(st.program_id, key)) {
-		return fail(RSRCU_ERR_NO_PROGRAM, "no dispatch entry for program %d state key 0x%x (src/viewer/shaders.cxx:54-126)", st.program_id, key); }
+	const int key = hs.key, programId = hs.programId;
+	if (!drawProgramInstalled(programId, key)) {
+		return fail(RSRCU_ERR_NO_PROGRAM, "no dispatch entry for program %d state key 0x%x (src/viewer/shaders.cxx:54-126)", programId, key); }
+	if (programId == 4 || programId == 65 || programId == 26 || programId == 41 || programId == 10) {
+		// texture units with pow2 dims outside 4..1024 cannot be made by the reference (exit(1))
+		if (hs.tex0Null) { return fail(RSRCU_ERR_INVALID, "program %d samples texture unit 0 but none is bound", programId); }
+		int power = 0; while ((1 << (power + 1)) <= hs.tex0Width) { ++power; }
+		const bool isPow2 = ((1 << power) == hs.tex0Width) && hs.tex0Width == hs.tex0Height && hs.tex0Stride == hs.tex0Width;
+		if (isPow2 && (hs.tex0Width < 4 || hs.tex0Width > 1024)) {
+			return fail(RSRCU_ERR_UNSUPPORTED, "can't make TextureUnit for pow2 size %d (rglr_texture_sampler.cxx:333-357)", hs.tex0Width); } }
 	const bool instanced = instanceCount > 0;
 	const int instances = instanced ? instanceCount : 1;
 	if (instances > 65536) { return fail(RSRCU_ERR_INVALID, "instance id must fit uint16 (rglv_gpu_impl.hxx:490)"); }
@@ -480,24 +575,24 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	if (arrays) { nverts = static_cast<size_t>(prims) * 3; }
 	else {
 		nverts = hs.bufferFloats[0];
-		if (hs.buffers[0].null) {
+		if (hs.posNull) {
 			// no position buffer: every vertex is the origin; need max index + 1
 			uint16_t mx = 0;
 			for (int i = 0; i < prims * 3; ++i) { mx = std::max(mx, indices[i]); }
 			nverts = static_cast<size_t>(mx) + 1; } }
-	if (!arrays && !hs.buffers[0].null && nverts == 0) { return fail(RSRCU_ERR_INVALID, "position buffer has no length"); }
-	if (arrays && !hs.buffers[0].null && hs.bufferFloats[0] < nverts) {
+	if (!arrays && !hs.posNull && nverts == 0) { return fail(RSRCU_ERR_INVALID, "position buffer has no length"); }
+	if (arrays && !hs.posNull && hs.bufferFloats[0] < nverts) {
 		return fail(RSRCU_ERR_INVALID, "DrawArrays count %d exceeds bound position buffer (%zu floats)", count, hs.bufferFloats[0]); }
 	for (int slot : {1, 2, 3, 4, 5, 6, 7, 8, 9, 10}) {
-		if (!hs.buffers[slot].null && hs.bufferFloats[slot] < nverts) {
+		if (hs.ds.buffers[slot] != nullptr && hs.bufferFloats[slot] < nverts) {
 			return fail(RSRCU_ERR_INVALID, "buffer slot %d shorter (%zu) than the position buffer (%zu)", slot, hs.bufferFloats[slot], nverts); } }
-	if (instanced && (st.program_id == 6) && (hs.buffers[15].null || hs.bufferFloats[15] < static_cast<size_t>(instances) * 16)) {
+	if (instanced && (programId == 6) && (hs.ds.buffers[15] == nullptr || hs.bufferFloats[15] < static_cast<size_t>(instances) * 16)) {
 		return fail(RSRCU_ERR_INVALID, "instanced draw needs %d mat4 in slot 15", instances); }
 	d.nverts = static_cast<int>(nverts);
-	d.nvary = programVaryings(st.program_id);
+	d.nvary = programVaryings(programId);
 	d.strideF4 = 2 + (d.nvary + 3) / 4;
 	d.N = static_cast<uint32_t>(prims) * static_cast<uint32_t>(instances);
-	d.batchKey = static_cast<uint32_t>(st.program_id & 0xff) | (static_cast<uint32_t>(key) << 8);
+	d.batchKey = static_cast<uint32_t>(programId & 0xff) | (static_cast<uint32_t>(key) << 8);
 	if (!arrays) {
 		if (!indices) { return fail(RSRCU_ERR_INVALID, "null index pointer"); }
 		r = uploadData(c, indices, static_cast<size_t>(prims) * 3 * sizeof(uint16_t), upload, hd.indices);
@@ -516,8 +611,8 @@ int rsrcu_draw_arrays(rsrcu_ctx* c, int count, int instanceCount) {
 int rsrcu_store_color_tc(rsrcu_ctx* c, int gamma, uint32_t* dst, int width, int height, int stridePx) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
-	if (c->haveState && !bltProgramInstalled(c->curState.program_id)) {
-		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67)", c->curState.program_id); }
+	if (c->haveState && !bltProgramInstalled(c->curStatePtr->program_id)) {
+		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67)", c->curStatePtr->program_id); }
 	CU(cudaSetDevice(c->device));
 	CU(c->tcOut[c->outSlot].reserve(static_cast<size_t>(width) * height * 4));
 	c->tcStride = width;
@@ -532,8 +627,8 @@ int rsrcu_store_color_tc_device(rsrcu_ctx* c, int gamma, void* deviceDst, int wi
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	if (!deviceDst) { return fail(RSRCU_ERR_INVALID, "null device destination"); }
 	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
-	if (c->haveState && !bltProgramInstalled(c->curState.program_id)) {
-		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d", c->curState.program_id); }
+	if (c->haveState && !bltProgramInstalled(c->curStatePtr->program_id)) {
+		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d", c->curStatePtr->program_id); }
 	return pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, deviceDst, stridePx, 1); }
 
 int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int stridePx, int half) {
@@ -564,6 +659,8 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_end_frame without begin"); }
 	CU(cudaSetDevice(c->device));
 	c->inFrame = false;
+	const auto tSubmit = std::chrono::steady_clock::now();
+	c->recordNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(tSubmit - c->tBegin).count());
 	cudaStream_t st = c->stream;
 	c->launches = 0;
 
@@ -612,79 +709,42 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	fp.listCapacity = c->listCapacity;
 
 	// ---- frame tables into the arena (state / draw tables need final device addresses) -----
-	size_t offStates = 0, offDraws = 0, offCmds = 0;
+	size_t offStates = 0, offDraws = 0, offCmds = 0, offVBlocks = 0, offPBlocks = 0;
+	const size_t nVBlocks = static_cast<size_t>((vjobs + 255) / 256) + 1, nPBlocks = static_cast<size_t>((pjobs + 255) / 256) + 1;
 	CU(c->arenas[c->cur].push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
 	CU(c->arenas[c->cur].push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
 	CU(c->arenas[c->cur].push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(uint32_t) * nVBlocks, offVBlocks));
+	CU(c->arenas[c->cur].push(nullptr, sizeof(uint32_t) * nPBlocks, offPBlocks));
 	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
 
-	for (size_t i = 0; i < c->states.size(); ++i) {
-		const HostState& hs = c->states[i];
-		const RsrState& s = hs.st;
-		DevState ds{};
-		std::memcpy(ds.vm, s.view_matrix, sizeof(ds.vm));
-		std::memcpy(ds.pm, s.projection_matrix, sizeof(ds.pm));
-		// MakeMatrices (rglv_gpu_impl.hxx:45-51)
-		if (s.program_id == 9 || s.program_id == 10) {   // only OBJ2S and Envmap read gl_NormalMatrix
-			float inv[16];
-			mat4Inverse(s.view_matrix, inv);
-			mat4Transpose(inv, ds.nm); }
-		mat4Mul(s.projection_matrix, s.view_matrix, ds.vpm);
-		if (s.uniforms_valid) { std::memcpy(ds.uniforms, s.uniforms, sizeof(ds.uniforms)); }
-		// GPU::DSDO (rglv_gpu.hxx:265-270): integer halves
-		const int vw = (s.viewport_size[0] > 0 && s.viewport_size[1] > 0) ? s.viewport_size[0] : W;
-		const int vh = (s.viewport_size[0] > 0 && s.viewport_size[1] > 0) ? s.viewport_size[1] : H;
-		ds.DSx = static_cast<float>(vw / 2);
-		ds.DSy = static_cast<float>(-vh / 2);
-		ds.DOx = static_cast<float>(vw / 2 + s.viewport_origin[0]);
-		ds.DOy = static_cast<float>(H - (vh / 2 + s.viewport_origin[1]));
-		std::memcpy(ds.clearColor, s.clear_color, sizeof(ds.clearColor));
-		ds.clearDepth = s.clear_depth;
-		ds.programId = s.program_id;
-		ds.cullingEnabled = s.culling_enabled; ds.cullFace = s.cull_face;
-		if (!s.scissor_enabled) { ds.scissorX0 = 0; ds.scissorY0 = 0; ds.scissorX1 = W; ds.scissorY1 = H; }
-		else {
-			// gl_offset_and_size_to_irect (rglv_gpu.hxx:258-263)
-			const int left = s.scissor_origin[0], right = left + s.scissor_size[0];
-			const int bottom = H - s.scissor_origin[1] - 1, top = bottom - s.scissor_size[1];
-			ds.scissorX0 = left; ds.scissorY0 = top; ds.scissorX1 = right; ds.scissorY1 = bottom; }
-		ds.depthTest = s.depth_test_enabled; ds.depthFunc = s.depth_func; ds.depthWrite = s.depth_write_mask;
-		ds.colorWrite = s.color_write_mask; ds.blend = s.blending_enabled;
-		ds.color0Type = s.color0_attachment_type; ds.depthType = s.depth_attachment_type;
-		for (int b = 0; b < 16; ++b) { ds.buffers[b] = static_cast<const float*>(resolve(c, hs.buffers[b])); }
-		for (int u = 0; u < 2; ++u) {
-			const HostTex& ht = hs.tus[u];
-			TexUnit& tu = ds.tu[u];
-			tu.texels = static_cast<const float4*>(resolve(c, ht.ref));
-			tu.texelCount = ht.texelCount;
-			tu.width = ht.width; tu.height = ht.height; tu.stride = ht.stride;
-			// MakeTextureUnit (rglr_texture_sampler.cxx:314-363)
-			int power = 0;
-			while ((1 << (power + 1)) <= ht.width) { ++power; }
-			const bool isPow2 = ((1 << power) == ht.width) && ht.width == ht.height && ht.stride == ht.width;
-			tu.power = power;
-			tu.kind = !isPow2 ? 0 : (ht.filter ? 2 : 1); }
-		ds.tu3 = static_cast<const float*>(resolve(c, hs.tu3));
-		ds.tu3dim = hs.tu3dim;
-		std::memcpy(c->arenas[c->cur].host + offStates + i * sizeof(DevState), &ds, sizeof(ds)); }
+	{
+		const uint8_t* arenaDev = static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr);
+		DevState* out = reinterpret_cast<DevState*>(c->arenas[c->cur].host + offStates);
+		for (size_t i = 0; i < c->states.size(); ++i) {
+			const HostState& hs = c->states[i];
+			std::memcpy(out + i, &hs.ds, sizeof(DevState));
+			if (hs.hasArenaRef) {
+				for (int b = 0; b < 16; ++b) { patchRef(out[i].buffers[b], arenaDev); }
+				patchRef(out[i].tu[0].texels, arenaDev); patchRef(out[i].tu[1].texels, arenaDev);
+				patchRef(out[i].tu3, arenaDev); } } }
 	for (size_t i = 0; i < c->draws.size(); ++i) {
 		DevDraw d = c->draws[i].d;
 		d.indices = static_cast<const uint16_t*>(resolve(c, c->draws[i].indices));
 		std::memcpy(c->arenas[c->cur].host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
+	{
+		// draw of the first job of every block of 256 vertex / triangle jobs (find_draw, kernels.cuh)
+		uint32_t* vb = reinterpret_cast<uint32_t*>(c->arenas[c->cur].host + offVBlocks);
+		uint32_t* pb = reinterpret_cast<uint32_t*>(c->arenas[c->cur].host + offPBlocks);
+		size_t dv = 0, dp = 0;
+		const size_t nd = c->draws.size();
+		for (size_t b = 0; b < nVBlocks; ++b) {
+			while (dv + 1 < nd && c->draws[dv + 1].d.vjobBase <= b * 256) { ++dv; }
+			vb[b] = static_cast<uint32_t>(dv); }
+		for (size_t b = 0; b < nPBlocks; ++b) {
+			while (dp + 1 < nd && c->draws[dp + 1].d.pjobBase <= b * 256) { ++dp; }
+			pb[b] = static_cast<uint32_t>(dp); } }
 	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
-
-	// texture units with pow2 dims outside 4..1024 cannot be made by the reference (exit(1))
-	for (const HostDraw& hd : c->draws) {
-		const HostState& hs = c->states[hd.d.state];
-		const int pid = hs.st.program_id;
-		const bool usesTu0 = (pid == 4 || pid == 65 || pid == 26 || pid == 41 || pid == 10);
-		if (usesTu0) {
-			const HostTex& ht = hs.tus[0];
-			if (ht.ref.null) { return fail(RSRCU_ERR_INVALID, "program %d samples texture unit 0 but none is bound", pid); }
-			int power = 0; while ((1 << (power + 1)) <= ht.width) { ++power; }
-			const bool isPow2 = ((1 << power) == ht.width) && ht.width == ht.height && ht.stride == ht.width;
-			if (isPow2 && (ht.width < 4 || ht.width > 1024)) {
-				return fail(RSRCU_ERR_UNSUPPORTED, "can't make TextureUnit for pow2 size %d (rglr_texture_sampler.cxx:333-357)", ht.width); } } }
 
 	// ---- device buffers -------------------------------------------------------------------
 	CU(c->ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
@@ -695,7 +755,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	const size_t ncells = static_cast<size_t>(ntiles) * fp.groups;
 	const size_t ctrlBytes = 64 + ncells * 8;   // Counters | cellCount[] | cellCursor[]
 	static_assert(sizeof(Counters) <= 64, "control block layout");
-	CU(c->counters.reserve(ctrlBytes));
+	CU(c->counters[c->outSlot].reserve(ctrlBytes));
 	CU(c->tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
 	CU(c->cellRel.reserve(ncells * 4));
 	CU(c->tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
@@ -706,9 +766,9 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
 	const DevDraw* dDraws = reinterpret_cast<const DevDraw*>(ab + offDraws);
 	const FrameCmd* dCmds = reinterpret_cast<const FrameCmd*>(ab + offCmds);
-	Counters* dCtr = static_cast<Counters*>(c->counters.ptr);
+	Counters* dCtr = static_cast<Counters*>(c->counters[c->outSlot].ptr);
 	BinArgs bin{};
-	bin.cellCount = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->counters.ptr) + 64);
+	bin.cellCount = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->counters[c->outSlot].ptr) + 64);
 	bin.cellCursor = bin.cellCount + ncells;
 	bin.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);
 	bin.cellRel = static_cast<const uint32_t*>(c->cellRel.ptr);
@@ -718,27 +778,27 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaMemcpyAsync(c->arenas[c->cur].dev.ptr, c->arenas[c->cur].host, c->arenas[c->cur].used, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(c->arenaFree[c->cur], st));
-	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot ^ 1], 0));   // previous frame's counters have been read back
+	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame before the previous one (same counters / store targets) has been read back
 	CU(cudaMemsetAsync(dCtr, 0, ctrlBytes, st));
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[1], st)); }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[1], st)); }
 
 	if (fp.totalVJobs) {
-		vertex_kernel<<<(fp.totalVJobs + 255) / 256, 256, 0, st>>>(dDraws, dStates, fp, c->devLuts,
+		vertex_kernel<<<(fp.totalVJobs + 255) / 256, 256, 0, st>>>(dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp, c->devLuts,
 			static_cast<float4*>(c->ptvb.ptr), static_cast<uint8_t*>(c->vflags.ptr));
 		++c->launches; }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[2], st)); }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
 	if (fp.totalPJobs) {
-		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, dStates, fp, c->devLuts,
+		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp, c->devLuts,
 			static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
 			static_cast<uint2*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
 			bin, static_cast<uint32_t*>(c->tileBase.ptr), dCtr);
 		++c->launches; }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
 	if (fp.totalPJobs && fp.groups > 1) {
 		cell_scan_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(fp, bin.cellCount, static_cast<uint32_t*>(c->cellRel.ptr),
 			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), dCtr);
 		++c->launches; }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[5], st)); }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
 	if (fp.totalPJobs) {
 		fill_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(fp, static_cast<const uint2*>(c->triInfo.ptr),
 			static_cast<const ClipRec*>(c->clipRecs.ptr), bin, dCtr);
@@ -755,7 +815,6 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	ta.cellRel = bin.cellRel;
 	ta.large = bin.large;
 	ta.ctr = dCtr;
-	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last resolved into this slot has been read back
 	tile_kernel<<<ntiles, kTileThreads, sizeof(TileShared), st>>>(ta);
 	++c->launches;
 	CU(cudaGetLastError());
@@ -771,6 +830,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	CU(cudaMemcpyAsync(c->hostCounters + c->outSlot, dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, c->copyStream));
 	CU(cudaEventRecord(c->evCopied[c->outSlot], c->copyStream));
 	c->framePending = true;
+	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tSubmit).count());
 	return RSRCU_OK; }
 
 int rsrcu_sync(rsrcu_ctx* c) {
@@ -789,8 +849,12 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	c->stats.kernel_launches = c->launches;
 	c->stats.h2d_bytes = c->lastH2D;
 	c->stats.d2h_bytes = c->lastD2H;
+	c->stats.host_record_ns = c->recordNs;
+	c->stats.host_submit_ns = c->submitNs;
 	if (c->profiling) {
-		for (int i = 0; i < 6; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); }
+		for (int i = 0; i < 6; ++i) { c->stageMs[i] = 0.0f; }
+		if (c->profiling > 1) { for (int i = 0; i < 5; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); } }
+		cudaEventElapsedTime(&c->stageMs[5], c->evStage[6], c->evStage[7]);
 		// stage order of the header: vertex, setup, count, scan, fill, tile
 		cudaEventElapsedTime(&c->stageMs[6], c->evStage[0], c->evStage[7]); }
 	if (k.overflow & 2u) {
@@ -827,7 +891,10 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 		int r = RSRCU_OK;
 		switch (op) {
 		case RSRCU_OP_BEGIN_FRAME: if (!need(16)) { goto bad; } r = rsrcu_begin_frame(c, i32(0), i32(1), i32(2), i32(3)); break;
-		case RSRCU_OP_STATE: { if (!need(sizeof(RsrState))) { goto bad; } RsrState st; std::memcpy(&st, q, sizeof(st)); r = rsrcu_set_state(c, &st); } break;
+		case RSRCU_OP_STATE:
+			// read in place: the stream outlives the frame it records (rsrcu_end_frame runs inside this call)
+			if (!need(sizeof(RsrState)) || !c->inFrame) { goto bad; }
+			c->curStatePtr = reinterpret_cast<const RsrState*>(q); c->haveState = true; c->stateDirty = true; break;
 		case RSRCU_OP_BIND_BUFFER: if (!need(24)) { goto bad; }
 			r = rsrcu_bind_buffer(c, i32(0), reinterpret_cast<const float*>(u64(8)), static_cast<size_t>(u64(16)), i32(1)); break;
 		case RSRCU_OP_BIND_TEXTURE: if (!need(40)) { goto bad; }
@@ -852,6 +919,10 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 		continue;
 	bad:
 		return fail(RSRCU_ERR_INVALID, "stream record op %u too short (%zu bytes)", op, payload); }
+	if (c->inFrame && c->haveState && c->curStatePtr != &c->curState) {
+		// the frame continues in another call: keep the current state, the stream may go away
+		c->curState = *c->curStatePtr;
+		c->curStatePtr = &c->curState; }
 	return RSRCU_OK; }
 
 int rsrcu_sync_frame(rsrcu_ctx* c, int lag) {
@@ -877,7 +948,7 @@ int rsrcu_get_stats(rsrcu_ctx* c, RsrStats* out) {
 
 int rsrcu_set_profiling(rsrcu_ctx* c, int enabled) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
-	c->profiling = enabled != 0;
+	c->profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
 	return RSRCU_OK; }
 
 int rsrcu_get_stage_ms(rsrcu_ctx* c, float* ms7) {

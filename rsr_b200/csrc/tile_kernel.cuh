@@ -37,6 +37,7 @@ __constant__ uint32_t kSrgbTab4[104] = {
 };
 
 constexpr int kSortCap = 1024;           // most list entries sorted in one round
+constexpr int kRunCap = 1024;            // most runs of one cell that the run merge handles
 
 struct TileShared {
 	float chan[4][4][kTileThreads];      // [r,g,b,depth][quad lane][thread]
@@ -57,6 +58,7 @@ struct TileShared {
 	uint8_t lgGroup[kTileLargeCap];
 	alignas(4) uint16_t lgPerGroup[kMaxGroups];
 	int lgCount;
+	uint32_t runStart[kRunCap], runPre[kRunCap];   // long cell in run mode: start of each run / entries before it, in key order
 	int firstBad;
 	int sortCount;
 };
@@ -577,12 +579,12 @@ __device__ __forceinline__ uint32_t linear8(float f) {
 //   C  if the runs do interleave (or there are too many): key ranges [nextKey, hi] are selected
 //      with one pass over the cell per range (halved until it fits) and sorted bitonically.
 // All threads of the CTA must call it.
-constexpr int kRunCap = 1024;
 
 struct ListCursor {
 	int g;                 // next cell
 	uint32_t taken;        // entries already taken from cell g (modes B and C)
 	int mode;              // of cell g: 0 = undecided / B, 2 = C
+	int runs;              // B: runs of cell g (0 = not analysed yet)
 	uint32_t nextKey;      // C: pending entries of cell g have order keys >= nextKey
 	uint32_t span; };
 
@@ -654,83 +656,84 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restric
 
 	if (lc.mode != 2 && nlarge0 == 0) {
 		// ---- B: runs -------------------------------------------------------------------------
-		uint32_t* rStart = reinterpret_cast<uint32_t*>(&sh.ec[0][0]);   // 4 x kRunCap words inside the batch records
-		uint32_t* rKey = rStart + kRunCap;
-		uint32_t* rOrder = rKey + kRunCap;
-		uint32_t* rPre = rOrder + kRunCap;
-		static_assert(offsetof(TileShared, vref) - offsetof(TileShared, ec) >= 16 * kRunCap, "run scratch aliases the batch records");
-		uint32_t* warpCnt = reinterpret_cast<uint32_t*>(sh.queue);
-		if (t == 0) { sh.sortCount = 0; sh.firstBad = 0; }
-		__syncthreads();
-		for (uint32_t strip = 0; strip < size0; strip += kTileThreads) {
-			const uint32_t i = strip + t;
-			uint32_t key = 0;
-			bool isStart = false;
-			if (i < size0) {
-				const uint2 e = __ldg(list + i);
-				key = e.x;
-				isStart = (e.y & kRunStartBit) != 0; }
-			const unsigned m = __ballot_sync(0xffffffffu, isStart);
-			if (lane == 0) { warpCnt[warp] = __popc(m); }
+		if (lc.runs == 0) {
+			uint32_t* rStart = reinterpret_cast<uint32_t*>(&sh.ec[0][0]);   // 3 x kRunCap words inside the batch records
+			uint32_t* rKey = rStart + kRunCap;
+			uint32_t* rOrder = rKey + kRunCap;
+			static_assert(offsetof(TileShared, vref) - offsetof(TileShared, ec) >= 12 * kRunCap, "run scratch aliases the batch records");
+			uint32_t* warpCnt = reinterpret_cast<uint32_t*>(sh.queue);
+			if (t == 0) { sh.sortCount = 0; sh.firstBad = 0; }
 			__syncthreads();
-			uint32_t idx = static_cast<uint32_t>(sh.sortCount) + __popc(m & ((1u << lane) - 1u));
-			uint32_t total = 0;
-#pragma unroll
-			for (int w = 0; w < kTileThreads / 32; ++w) { const uint32_t c = warpCnt[w]; if (w < warp) { idx += c; } total += c; }
-			if (isStart && idx < static_cast<uint32_t>(kRunCap)) { rStart[idx] = i; rKey[idx] = key; }
-			__syncthreads();
-			if (t == 0) { sh.sortCount += static_cast<int>(total); } }
-		__syncthreads();
-		const int R = sh.sortCount;
-		if (R <= kRunCap) {
-			// rank the runs by first key; lengths follow from the next run in memory order
-			for (int r = t; r < R; r += kTileThreads) {
-				const uint32_t k = rKey[r];
-				int rank = 0;
-				for (int q = 0; q < R; ++q) { rank += (rKey[q] < k) ? 1 : 0; }
-				rOrder[rank] = static_cast<uint32_t>(r); }
-			__syncthreads();
-			// runs must not interleave: the last key of a run lies below the first key of the next one
-			for (int p = t; p + 1 < R; p += kTileThreads) {
-				const uint32_t r = rOrder[p], nx = rOrder[p + 1];
-				const uint32_t end = (r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0;
-				if (__ldg(list + end - 1).x > rKey[nx]) { sh.firstBad = 1; } }
-			// exclusive prefix of the run lengths in key order (serial per thread over R / 256 runs, then a block scan)
-			const int per = (R + kTileThreads - 1) / kTileThreads;
-			const int p0 = min(t * per, R), p1 = min(p0 + per, R);
-			uint32_t sum = 0;
-			for (int p = p0; p < p1; ++p) {
-				const uint32_t r = rOrder[p];
-				sum += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
-			uint32_t incl = sum;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) { incl += v; } }
-			__syncthreads();   // (warpCnt reuse; sh.firstBad complete)
-			if (lane == 31) { warpCnt[warp] = incl; }
-			__syncthreads();
-			uint32_t before = incl - sum;
-			for (int w = 0; w < warp; ++w) { before += warpCnt[w]; }
-			for (int p = p0; p < p1; ++p) {
-				const uint32_t r = rOrder[p];
-				rPre[p] = before;
-				before += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
-			__syncthreads();
-			if (sh.firstBad == 0) {
-				const int n = static_cast<int>(min(static_cast<uint32_t>(kSortCap), size0 - lc.taken));
-				for (int i = t; i < n; i += kTileThreads) {
-					const uint32_t pos = lc.taken + static_cast<uint32_t>(i);
-					int lo = 0, hi = R - 1;
-					while (lo < hi) {
-						const int mid = (lo + hi + 1) >> 1;
-						if (rPre[mid] <= pos) { lo = mid; } else { hi = mid - 1; } }
-					sh.sorted[i] = __ldg(list + rStart[rOrder[lo]] + (pos - rPre[lo])).y & ~kRunStartBit; }
-				lc.taken += static_cast<uint32_t>(n);
-				if (lc.taken >= size0) { ++lc.g; lc.taken = 0; lc.mode = 0; }
+			for (uint32_t strip = 0; strip < size0; strip += kTileThreads) {
+				const uint32_t i = strip + t;
+				uint32_t key = 0;
+				bool isStart = false;
+				if (i < size0) {
+					const uint2 e = __ldg(list + i);
+					key = e.x;
+					isStart = (e.y & kRunStartBit) != 0; }
+				const unsigned m = __ballot_sync(0xffffffffu, isStart);
+				if (lane == 0) { warpCnt[warp] = __popc(m); }
 				__syncthreads();
-				return n; } }
-		// interleaved or too many runs (only before anything was taken: the run structure does not change)
-		lc.mode = 2;
-		__syncthreads(); }
+				uint32_t idx = static_cast<uint32_t>(sh.sortCount) + __popc(m & ((1u << lane) - 1u));
+				uint32_t total = 0;
+#pragma unroll
+				for (int w = 0; w < kTileThreads / 32; ++w) { const uint32_t c = warpCnt[w]; if (w < warp) { idx += c; } total += c; }
+				if (isStart && idx < static_cast<uint32_t>(kRunCap)) { rStart[idx] = i; rKey[idx] = key; }
+				__syncthreads();
+				if (t == 0) { sh.sortCount += static_cast<int>(total); } }
+			__syncthreads();
+			const int R = sh.sortCount;
+			if (R <= kRunCap) {
+				// rank the runs by first key; lengths follow from the next run in memory order
+				for (int r = t; r < R; r += kTileThreads) {
+					const uint32_t k = rKey[r];
+					int rank = 0;
+					for (int q = 0; q < R; ++q) { rank += (rKey[q] < k) ? 1 : 0; }
+					rOrder[rank] = static_cast<uint32_t>(r); }
+				__syncthreads();
+				// runs must not interleave: the last key of a run lies below the first key of the next one
+				for (int p = t; p + 1 < R; p += kTileThreads) {
+					const uint32_t r = rOrder[p], nx = rOrder[p + 1];
+					const uint32_t end = (r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0;
+					if (__ldg(list + end - 1).x > rKey[nx]) { sh.firstBad = 1; } }
+				// exclusive prefix of the run lengths in key order (serial per thread over R / 256 runs, then a block scan)
+				const int per = (R + kTileThreads - 1) / kTileThreads;
+				const int p0 = min(t * per, R), p1 = min(p0 + per, R);
+				uint32_t sum = 0;
+				for (int p = p0; p < p1; ++p) {
+					const uint32_t r = rOrder[p];
+					sum += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
+				uint32_t incl = sum;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) { incl += v; } }
+				__syncthreads();   // (warpCnt reuse; sh.firstBad complete)
+				if (lane == 31) { warpCnt[warp] = incl; }
+				__syncthreads();
+				uint32_t before = incl - sum;
+				for (int w = 0; w < warp; ++w) { before += warpCnt[w]; }
+				for (int p = p0; p < p1; ++p) {
+					const uint32_t r = rOrder[p];
+					sh.runStart[p] = rStart[r];
+					sh.runPre[p] = before;
+					before += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
+				__syncthreads();
+				if (sh.firstBad == 0) { lc.runs = R; } }
+			if (lc.runs == 0) { lc.mode = 2; } }   // interleaved (clip fans) or too many runs
+		if (lc.runs) {
+			const int R = lc.runs;
+			const int n = static_cast<int>(min(static_cast<uint32_t>(kSortCap), size0 - lc.taken));
+			for (int i = t; i < n; i += kTileThreads) {
+				const uint32_t pos = lc.taken + static_cast<uint32_t>(i);
+				int lo = 0, hi = R - 1;
+				while (lo < hi) {
+					const int mid = (lo + hi + 1) >> 1;
+					if (sh.runPre[mid] <= pos) { lo = mid; } else { hi = mid - 1; } }
+				sh.sorted[i] = __ldg(list + sh.runStart[lo] + (pos - sh.runPre[lo])).y & ~kRunStartBit; }
+			lc.taken += static_cast<uint32_t>(n);
+			if (lc.taken >= size0) { ++lc.g; lc.taken = 0; lc.mode = 0; lc.runs = 0; }
+			__syncthreads();
+			return n; } }
 
 	// ---- C: key ranges -------------------------------------------------------------------------
 	if (lc.taken == 0) {
@@ -760,7 +763,7 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restric
 		lc.nextKey = hi + 1u;
 		break; }
 	lc.taken += static_cast<uint32_t>(n);
-	if (lc.taken >= size0 || n == 0) { ++lc.g; lc.taken = 0; lc.mode = 0; }
+	if (lc.taken >= size0 || n == 0) { ++lc.g; lc.taken = 0; lc.mode = 0; lc.runs = 0; }
 	sort_scratch(sh, scr, n, begin, 0, 0);
 	return n; }
 
@@ -809,7 +812,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		if (t == 0) { atomicOr(&A.ctr->overflow, 8u); sh.lgCount = kTileLargeCap; }
 		__syncthreads(); }
 	const uint32_t listLen = (sh.cellOff[G] - sh.cellOff[0]) + static_cast<uint32_t>(sh.lgCount);
-	ListCursor lc{0, 0u, 0, 0u, 1u};
+	ListCursor lc{0, 0u, 0, 0, 0u, 1u};
 	int chunkN = 0, chunkPos = 0;
 	if (listLen) {
 #pragma unroll

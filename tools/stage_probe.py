@@ -7,7 +7,7 @@ import rsr_b200 as R
 from rsr_b200 import scenes
 
 g = R.GPU(0)
-g.set_profiling(True)
+g.set_profiling(2)
 size = (1920, 1080)
 
 class Empty:
@@ -25,7 +25,7 @@ def probe(name, sc, **kw):
         if i >= 5:
             for k, v in g.stage_ms().items():
                 acc[k] = acc.get(k, 0) + v / 20
-    print(f"{name:28s}", {k: round(v, 3) for k, v in acc.items()}, "host_submit_ms", round(1e3 * float(np.median(host)), 3), g.stats()["bin_entries"])
+    print(f"{name:28s}", {k: round(v, 3) for k, v in acc.items()}, "host_submit_ms", round(1e3 * float(np.median(host)), 3), "record_us", g.stats()["host_record_ns"] // 1000, "end_frame_us", g.stats()["host_submit_ns"] // 1000, g.stats()["bin_entries"])
 
 probe("empty", Empty())
 c2 = scenes.BundledLikeScene()
