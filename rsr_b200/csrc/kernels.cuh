@@ -469,8 +469,8 @@ __device__ __forceinline__ void bin_triangle(uint32_t job, uint2 info, const Fra
 // Called by every thread of every CTA at the end of a kernel: the last CTA to get here scans
 // count[0..n) (n <= 4096) into base[0..n] (threadFenceReduction pattern: every thread's writes and
 // atomics are ordered before its CTA's ticket).
-__device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint32_t* __restrict__ base, const int n,
-                                                     const uint32_t listCapacity, Counters* __restrict__ ctr) {
+__device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint32_t* __restrict__ base, uint32_t* __restrict__ order,
+                                                     const int n, const uint32_t listCapacity, Counters* __restrict__ ctr) {
 	__shared__ bool lastBlock;
 	__shared__ uint32_t warpSums[8];
 	__threadfence();
@@ -502,13 +502,54 @@ __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint
 	if (threadIdx.x == 255) {
 		base[n] = before;
 		ctr->entries = before;
-		if (before > listCapacity) { atomicOr(&ctr->overflow, 2u); } } }
+		if (before > listCapacity) { atomicOr(&ctr->overflow, 2u); } }
+
+	// CTA -> tile order for the tile kernel: eight classes of list length (>= 2048, 1024, 512, 256, 64,
+	// 16, 1 entries, empty), longest first, tile index order inside a class (neighbouring tiles share
+	// texels and vertex records), so that the heavy tiles start early and the light ones fill the tail
+	// -- the reference sorts its tile jobs by list length for the same reason (rglv_gpu.cxx:100-108).
+	// Stable counting sort: thread t owns tiles 16t..16t+15, warp k scans class k.  (Rolled loops on
+	// purpose: this runs once per frame in one CTA, straight from a cold instruction cache.)
+	__shared__ uint16_t perThread[8][256];
+	__shared__ uint32_t classBase[8];
+	__shared__ uint8_t tileClass[4096];
+	for (int k = 0; k < 8; ++k) { perThread[k][threadIdx.x] = 0; }
+#pragma unroll 1
+	for (int q = 0; q < 16; ++q) {
+		const int i = static_cast<int>(threadIdx.x) * 16 + q;
+		if (i < n) {
+			const int lg = min(32 - __clz(v[q]), 12);                    // 0 for an empty list, 12 for >= 2048
+			const int k = static_cast<int>((0x0123445566667ull >> (4 * lg)) & 15ull);   // nibble table, lg = 0 first
+			tileClass[i] = static_cast<uint8_t>(k);
+			perThread[k][threadIdx.x] += 1; } }
+	__syncthreads();
+	{
+		uint32_t tot = 0;
+		for (int j = 0; j < 8; ++j) { tot += perThread[warp][lane * 8 + j]; }
+		uint32_t inc = tot;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) { inc += x; } }
+		uint32_t run = inc - tot;
+		for (int j = 0; j < 8; ++j) { const uint32_t c = perThread[warp][lane * 8 + j]; perThread[warp][lane * 8 + j] = static_cast<uint16_t>(run); run += c; }
+		if (lane == 31) { classBase[warp] = inc; } }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int k = 0; k < 8; ++k) { const uint32_t c = classBase[k]; classBase[k] = acc; acc += c; } }
+	__syncthreads();
+#pragma unroll 1
+	for (int q = 0; q < 16; ++q) {
+		const int i = static_cast<int>(threadIdx.x) * 16 + q;
+		if (i < n) {
+			const int k = tileClass[i];
+			order[classBase[k] + perThread[k][threadIdx.x]] = static_cast<uint32_t>(i);
+			perThread[k][threadIdx.x] += 1; } } }
 
 __global__ void __launch_bounds__(256)
 setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
              const ApproxLuts* __restrict__ luts, const float4* __restrict__ ptvb, const uint8_t* __restrict__ vflags,
              uint2* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
-             BinArgs B, uint32_t* __restrict__ tileBase, Counters* __restrict__ ctr) {
+             BinArgs B, uint32_t* __restrict__ tileBase, uint32_t* __restrict__ tileOrder, Counters* __restrict__ ctr) {
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	uint2 myInfo = make_uint2(kReject, 0u);
 	if (job < fp.totalPJobs) {
@@ -574,7 +615,7 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 		triInfo[job] = myInfo; }
 	bin_triangle<false>(job, myInfo, fp, clipRecs, B, ctr);
 	if (fp.groups > 1) { return; }   // K3 (cell_scan_kernel) prepares the offsets of multi-cell lists
-	tile_scan_last_block(B.cellCount, tileBase, fp.tilesX * fp.tilesY, fp.listCapacity, ctr); }
+	tile_scan_last_block(B.cellCount, tileBase, tileOrder, fp.tilesX * fp.tilesY, fp.listCapacity, ctr); }
 
 // ---------------------------------------------------------------------------------------------
 // K3 (frames with several cells per tile only): one warp per tile turns the tile's cell counts into
@@ -583,7 +624,8 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 
 __global__ void __launch_bounds__(256)
 cell_scan_kernel(FrameParams fp, const uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellRel,
-                 uint32_t* __restrict__ tileTotal, uint32_t* __restrict__ tileBase, Counters* __restrict__ ctr) {
+                 uint32_t* __restrict__ tileTotal, uint32_t* __restrict__ tileBase, uint32_t* __restrict__ tileOrder,
+                 Counters* __restrict__ ctr) {
 	const int ntiles = fp.tilesX * fp.tilesY;
 	const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
 	const int lane = threadIdx.x & 31;
@@ -599,7 +641,7 @@ cell_scan_kernel(FrameParams fp, const uint32_t* __restrict__ cellCount, uint32_
 		if (2 * lane < G) { cellRel[static_cast<size_t>(tile) * G + 2 * lane] = before; }
 		if (2 * lane + 1 < G) { cellRel[static_cast<size_t>(tile) * G + 2 * lane + 1] = before + a; }
 		if (lane == 31) { tileTotal[tile] = incl; } }
-	tile_scan_last_block(tileTotal, tileBase, ntiles, fp.listCapacity, ctr); }
+	tile_scan_last_block(tileTotal, tileBase, tileOrder, ntiles, fp.listCapacity, ctr); }
 
 // ---------------------------------------------------------------------------------------------
 // K5: list fill: one thread per triangle id (bin_item<FILL>); queued large items are skipped.

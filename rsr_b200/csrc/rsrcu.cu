@@ -153,7 +153,7 @@ struct rsrcu_ctx {
 	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr});
 
 	// device work buffers
-	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, lists, largeItems;
+	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems;
 	DevBuf counters[2];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
 	DevBuf tcOut[2], fpOut[2], depthOut[2];
 	uint32_t clipCapacity{1u << 16};
@@ -415,7 +415,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->tileOrder, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
@@ -759,6 +759,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	CU(c->tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
 	CU(c->cellRel.reserve(ncells * 4));
 	CU(c->tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(c->tileOrder.reserve(static_cast<size_t>(ntiles) * 4));
 	CU(c->lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
 	CU(c->largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
 
@@ -791,12 +792,12 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp, c->devLuts,
 			static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
 			static_cast<uint2*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
-			bin, static_cast<uint32_t*>(c->tileBase.ptr), dCtr);
+			bin, static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr);
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
 	if (fp.totalPJobs && fp.groups > 1) {
 		cell_scan_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(fp, bin.cellCount, static_cast<uint32_t*>(c->cellRel.ptr),
-			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), dCtr);
+			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr);
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
 	if (fp.totalPJobs) {
@@ -814,6 +815,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	ta.tileBase = bin.tileBase;
 	ta.cellRel = bin.cellRel;
 	ta.large = bin.large;
+	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(c->tileOrder.ptr) : nullptr;
 	ta.ctr = dCtr;
 	tile_kernel<<<ntiles, kTileThreads, sizeof(TileShared), st>>>(ta);
 	++c->launches;

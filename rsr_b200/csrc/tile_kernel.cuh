@@ -59,6 +59,7 @@ struct TileShared {
 	alignas(4) uint16_t lgPerGroup[kMaxGroups];
 	int lgCount;
 	uint32_t runStart[kRunCap], runPre[kRunCap];   // long cell in run mode: start of each run / entries before it, in key order
+	uint32_t srgbTab[104];               // ryg table: per-pixel indices diverge, constant memory would serialise
 	int firstBad;
 	int sortCount;
 };
@@ -77,6 +78,7 @@ struct TileArgs {
 	const uint32_t* tileBase;            // [tile]: list offset of the tile's first cell, + the total at the end
 	const uint32_t* cellRel;             // [tile * groups + g]: offset of the cell inside the tile's list (groups > 1)
 	const LargeItem* large;              // queued large items (kernels.cuh)
+	const uint32_t* tileOrder;           // CTA -> tile, tiles with the longest lists first (nullptr: identity)
 	Counters* ctr; };
 
 __device__ __forceinline__ bool top_left(int dy, int dx) { return (dy > 0) || (dy == 0 && dx > 0); }
@@ -549,13 +551,13 @@ __device__ __forceinline__ void post_iq(float& r, float& g, float& b, float qx, 
 	b = b + k * fract_sse(sse_sin(n + 2.0f) * 43758.5453123f); }
 
 // sRGB::to_tc / LinearColor::to_tc (rglr_canvas_util.hxx:15-62, ryg-srgb.h:183-223)
-__device__ __forceinline__ uint32_t srgb8(float f) {
+__device__ __forceinline__ uint32_t srgb8(float f, const uint32_t* __restrict__ srgbTab) {
 	const float clampMin = u2f((127u - 13u) << 23);
 	const float almostOne = u2f(0x3f7fffffu);
 	float c = sse_max(f, clampMin);
 	c = sse_min(c, almostOne);
 	const uint32_t bits = f2u(c);
-	const uint32_t tab = kSrgbTab4[(bits >> 20) - (127u - 13u) * 8u];
+	const uint32_t tab = srgbTab[(bits >> 20) - (127u - 13u) * 8u];
 	const uint32_t tmul = (bits >> 12) & 0xffu;
 	// _mm_madd_epi16(tab, tmul | 0x02000000): lo16*lo16 + hi16*hi16
 	const uint32_t prod = (tab & 0xffffu) * tmul + (tab >> 16) * 0x200u;
@@ -775,7 +777,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	extern __shared__ __align__(16) unsigned char tileSmem[];
 	TileShared& sh = *reinterpret_cast<TileShared*>(tileSmem);
 	const int t = threadIdx.x;
-	const int tile = blockIdx.x;
+	const int tile = A.tileOrder ? static_cast<int>(__ldg(A.tileOrder + blockIdx.x)) : static_cast<int>(blockIdx.x);   // longest lists first
 	const int tileX = tile % A.fp.tilesX, tileY = tile / A.fp.tilesX;
 	const int ox = tileX * kTile, oy = tileY * kTile;
 	const int warp = t >> 5, lane = t & 31;
@@ -794,6 +796,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		if (g > 0 && g < G) { off += __ldg(A.cellRel + static_cast<size_t>(tile) * G + g); }
 		sh.cellOff[g] = min(off, A.fp.listCapacity); }
 	if (t < kMaxGroups) { sh.lgPerGroup[t] = 0; }
+	if (t < 104) { sh.srgbTab[t] = kSrgbTab4[t]; }
 	if (t == 0) { sh.lgCount = 0; }
 	__syncthreads();
 	// queued large items (kernels.cuh) that cover this tile: a short scan instead of one list entry per tile
@@ -876,7 +879,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 							for (int kx = ptx; kx < px; kx += 2) { fcx += fcdx; }
 							for (int ky = pty; ky < py; ky += 2) { fcy += fcdy; }
 							post_iq(r, g, b, fcx, fcy); }
-						out[l] = (cmd.arg & 1) ? ((srgb8(r) << 16) | (srgb8(g) << 8) | srgb8(b))
+						out[l] = (cmd.arg & 1) ? ((srgb8(r, sh.srgbTab) << 16) | (srgb8(g, sh.srgbTab) << 8) | srgb8(b, sh.srgbTab))
 						                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
 					uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
 					*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
