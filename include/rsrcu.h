@@ -172,11 +172,13 @@ int rsrcu_end_frame(rsrcu_ctx* ctx);
 /* Waits for the frame; reports device-side errors (clip buffer overflow...) */
 int rsrcu_sync(rsrcu_ctx* ctx);
 
-/* Frames are pipelined two deep (upload arena, store targets and their device->host copies are
- * double-buffered; copies run on a second stream): rsrcu_sync_frame(ctx, 1) waits only until the
- * frame BEFORE the most recently submitted one has landed in its store destinations, so frame N's
- * read-back overlaps frame N+1's kernels -- the GPU counterpart of the reference's doubleBuffer
- * mode (rglv_gpu.cxx:16,111-112).  lag 0 = the latest frame.  Does not report device-side errors. */
+/* Frames are pipelined (upload arena double-buffered; store targets, counters and their device->host
+ * copies in a ring of three; copies run on a second stream): rsrcu_sync_frame(ctx, lag) waits only
+ * until the frame `lag` submissions before the most recent one (lag 0 = the latest, at most 2) has
+ * landed in its store destinations, so frame N's read-back overlaps the recording and the kernels of
+ * the frames after it -- the GPU counterpart of the reference's doubleBuffer mode
+ * (rglv_gpu.cxx:16,111-112).  A store destination must not be reused before its frame has been
+ * waited for.  Does not report device-side errors. */
 int rsrcu_sync_frame(rsrcu_ctx* ctx, int lag);
 
 /* ---- packed command stream ---------------------------------------------------------------------

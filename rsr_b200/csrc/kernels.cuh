@@ -133,6 +133,20 @@ __device__ __forceinline__ uint32_t pack_tiles(int tx0, int ty0, int tx1, int ty
 	       (static_cast<uint32_t>(tx1) << 12) | (static_cast<uint32_t>(ty1) << 18); }
 
 // ---------------------------------------------------------------------------------------------
+// K0: frame upload.  The SMs pull the frame's staging arena (pinned, mapped host memory: per-frame
+// buffers and the state / draw tables) into its device mirror and zero the control block.  A copy
+// engine would do the same, but a copy and a memset between two kernels of one stream cost two
+// engine hand-overs (tens of microseconds of idle GPU per frame, measured: tools/trace_run.py).
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+upload_kernel(const uint4* __restrict__ hostSrc, uint4* __restrict__ dst, size_t n16, uint4* __restrict__ zero, size_t nzero16) {
+	const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+	const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	for (size_t i = tid; i < n16; i += stride) { dst[i] = hostSrc[i]; }
+	for (size_t i = tid; i < nzero16; i += stride) { zero[i] = make_uint4(0u, 0u, 0u, 0u); } }
+
+// ---------------------------------------------------------------------------------------------
 // K1: vertex stage
 // ---------------------------------------------------------------------------------------------
 

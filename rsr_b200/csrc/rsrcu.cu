@@ -113,13 +113,26 @@ struct HostDraw {
 
 }  // namespace
 
+constexpr int kSlots = 3;
+
 struct rsrcu_ctx {
 	int device{0};
 	cudaStream_t stream{nullptr};
 	cudaStream_t copyStream{nullptr};   // device->host copies of finished frames overlap the next frame's kernels
-	cudaEvent_t evRendered{nullptr};
-	cudaEvent_t evCopied[2]{};
-	int outSlot{0};                     // store targets are double-buffered
+	cudaEvent_t evRendered[kSlots]{};
+	// read-back of the latest frame: enqueued behind the NEXT frame's upload (or at a sync) -- both go through the
+	// copy engines in submission order, and a device->host copy that is still waiting for its kernels must not
+	// hold up the upload the following frame's kernels wait for
+	std::vector<PendingCopy> deferredCopies;
+	// RSRCU_TRACE=1: timestamps of the first 64 frames (kernels start/end on the render stream, read-back start/end on
+	// the copy stream), printed by rsrcu_destroy -- a poor man's timeline for pipelining problems
+	bool trace{false};
+	std::vector<cudaEvent_t> traceEv;   // 4 per frame
+	int traceFrames{0};
+	int traceFrameOfSlot[kSlots]{};
+	int deferredSlot{-1};
+	cudaEvent_t evCopied[kSlots]{};
+	int outSlot{0};                     // store targets and counters live in a ring of kSlots: up to kSlots - 1 finished frames may still be on their way to the host
 	cudaEvent_t evStage[8]{};
 	int profiling{0};                   // 0 off, 1 tile kernel + whole frame, 2 every stage
 	float stageMs[7]{};
@@ -154,14 +167,14 @@ struct rsrcu_ctx {
 
 	// device work buffers
 	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems;
-	DevBuf counters[2];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
-	DevBuf tcOut[2], fpOut[2], depthOut[2];
+	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
+	DevBuf tcOut[kSlots], fpOut[kSlots], depthOut[kSlots];
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 24};
 	uint32_t largeCapacity{1u << 16};
 	int largeTiles{kLargeTiles};
 	int tcStride{0};
-	Counters* hostCounters{nullptr};   // pinned, [2]
+	Counters* hostCounters{nullptr};   // pinned, [kSlots]
 	RsrStats stats{};
 	uint64_t launches{0};
 	uint64_t lastH2D{0}, lastD2H{0};
@@ -368,6 +381,20 @@ int snapshotState(rsrcu_ctx* c) {
 	c->stateDirty = false;
 	return RSRCU_OK; }
 
+int flushDeferredCopies(rsrcu_ctx* c) {
+	if (c->deferredSlot < 0) { return RSRCU_OK; }
+	const int slot = c->deferredSlot;
+	c->deferredSlot = -1;
+	CU(cudaStreamWaitEvent(c->copyStream, c->evRendered[slot], 0));
+	const int tf = c->trace ? c->traceFrameOfSlot[slot] : -1;
+	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 2], c->copyStream)); }
+	for (const PendingCopy& pc : c->deferredCopies) {
+		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); }
+	CU(cudaMemcpyAsync(c->hostCounters + slot, c->counters[slot].ptr, sizeof(Counters), cudaMemcpyDeviceToHost, c->copyStream));
+	CU(cudaEventRecord(c->evCopied[slot], c->copyStream));
+	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 3], c->copyStream)); }
+	return RSRCU_OK; }
+
 }  // namespace
 
 extern "C" {
@@ -386,7 +413,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	c->device = device;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-	CU(cudaEventCreateWithFlags(&c->evRendered, cudaEventDisableTiming));
+	for (auto& ev : c->evRendered) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evCopied) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evStage) { CU(cudaEventCreate(&ev)); }
 	for (auto& ev : c->arenaFree) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
@@ -398,30 +425,42 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 		delete c;
 		return fail(RSRCU_ERR_UNSUPPORTED, "host rcpps/rsqrtps do not follow the table model (%llu mismatches); "
 		            "bit-exact parity with the reference on this CPU is not possible", static_cast<unsigned long long>(mismatches)); }
+	if (std::getenv("RSRCU_TRACE")) {
+		c->trace = true;
+		c->traceEv.resize(4 * 64);
+		for (auto& ev : c->traceEv) { CU(cudaEventCreate(&ev)); } }
 	if (const char* cap = std::getenv("RSRCU_LIST_CAPACITY")) {   // initial tile-list capacity in entries (tests)
 		const long v = std::atol(cap);
 		if (v > 0) { c->listCapacity = static_cast<uint32_t>(v); } }
 	CU(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TileShared))));
 	CU(cudaMalloc(&c->devLuts, sizeof(ApproxLuts)));
 	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
-	CU(cudaMallocHost(&c->hostCounters, 2 * sizeof(Counters)));
-	std::memset(c->hostCounters, 0, 2 * sizeof(Counters));
+	CU(cudaMallocHost(&c->hostCounters, kSlots * sizeof(Counters)));
+	std::memset(c->hostCounters, 0, kSlots * sizeof(Counters));
 	*out = c;
 	return RSRCU_OK; }
 
 int rsrcu_destroy(rsrcu_ctx* c) {
 	if (!c) { return RSRCU_OK; }
 	cudaSetDevice(c->device);
+	flushDeferredCopies(c);
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
+	if (c->trace) {
+		for (int f = 0; f + 1 < c->traceFrames; ++f) {
+			float t[4] = {0, 0, 0, 0};
+			for (int k = 0; k < 4; ++k) { if (cudaEventElapsedTime(&t[k], c->traceEv[0], c->traceEv[4 * f + k]) != cudaSuccess) { t[k] = -1.0f; cudaGetLastError(); } }
+			std::fprintf(stderr, "rsrcu trace frame %2d: kernels %8.1f .. %8.1f us   read-back %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f); }
+		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->tileOrder, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->tcOut[0], &c->tcOut[1], &c->fpOut[0], &c->fpOut[1], &c->depthOut[0], &c->depthOut[1] }) { b->release(); }
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->tileOrder, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->counters[2], &c->tcOut[0], &c->tcOut[1], &c->tcOut[2], &c->fpOut[0], &c->fpOut[1], &c->fpOut[2],
+	                   &c->depthOut[0], &c->depthOut[1], &c->depthOut[2] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
 	if (c->hostCounters) { cudaFreeHost(c->hostCounters); }
 	for (auto& ev : c->evStage) { cudaEventDestroy(ev); }
-	cudaEventDestroy(c->evRendered);
+	for (auto& ev : c->evRendered) { cudaEventDestroy(ev); }
 	for (auto& ev : c->evCopied) { cudaEventDestroy(ev); }
 	cudaStreamDestroy(c->copyStream);
 	cudaStreamDestroy(c->stream);
@@ -463,7 +502,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	CU(cudaSetDevice(c->device));
 	// take the other staging arena; wait only until the frame that last used it has been uploaded
 	c->cur ^= 1;
-	c->outSlot ^= 1;
+	c->outSlot = (c->outSlot + 1) % kSlots;
 	CU(cudaEventSynchronize(c->arenaFree[c->cur]));
 	c->width = width; c->height = height;
 	const int rw = tileWBlocks * 8, rh = tileHBlocks * 8;
@@ -777,11 +816,20 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	bin.large = static_cast<LargeItem*>(c->largeItems.ptr);
 
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
-	CU(cudaMemcpyAsync(c->arenas[c->cur].dev.ptr, c->arenas[c->cur].host, c->arenas[c->cur].used, cudaMemcpyHostToDevice, st));
+	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
+	{
+		// K0: upload + zeroed control block in one kernel (kernels.cuh)
+		const size_t n16 = (c->arenas[c->cur].used + 15) / 16, nz16 = (ctrlBytes + 15) / 16;
+		const int blocks = static_cast<int>(std::min<size_t>(148 * 8, (std::max(n16, nz16) + 255) / 256));
+		upload_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const uint4*>(c->arenas[c->cur].host),
+			static_cast<uint4*>(c->arenas[c->cur].dev.ptr), n16, reinterpret_cast<uint4*>(dCtr), nz16);
+		++c->launches; }
 	CU(cudaEventRecord(c->arenaFree[c->cur], st));
-	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame before the previous one (same counters / store targets) has been read back
-	CU(cudaMemsetAsync(dCtr, 0, ctrlBytes, st));
+	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }   // the previous frame's read-back
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[1], st)); }
+	const int traceIdx = (c->trace && c->traceFrames < 64) ? c->traceFrames++ : -1;
+	if (traceIdx >= 0) { c->traceFrameOfSlot[c->outSlot] = traceIdx; CU(cudaEventRecord(c->traceEv[4 * traceIdx], st)); }
+	else { c->traceFrameOfSlot[c->outSlot] = -1; }
 
 	if (fp.totalVJobs) {
 		vertex_kernel<<<(fp.totalVJobs + 255) / 256, 256, 0, st>>>(dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp, c->devLuts,
@@ -824,13 +872,11 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 
 	c->lastH2D = c->arenas[c->cur].used;
 	c->lastD2H = 0;
-	CU(cudaEventRecord(c->evRendered, st));
-	CU(cudaStreamWaitEvent(c->copyStream, c->evRendered, 0));
-	for (const PendingCopy& pc : c->copies) {
-		c->lastD2H += pc.rowBytes * pc.rows;
-		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); }
-	CU(cudaMemcpyAsync(c->hostCounters + c->outSlot, dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, c->copyStream));
-	CU(cudaEventRecord(c->evCopied[c->outSlot], c->copyStream));
+	CU(cudaEventRecord(c->evRendered[c->outSlot], st));
+	if (traceIdx >= 0) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 1], st)); }
+	for (const PendingCopy& pc : c->copies) { c->lastD2H += pc.rowBytes * pc.rows; }
+	c->deferredCopies = c->copies;
+	c->deferredSlot = c->outSlot;
 	c->framePending = true;
 	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tSubmit).count());
 	return RSRCU_OK; }
@@ -838,6 +884,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 int rsrcu_sync(rsrcu_ctx* c) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	CU(cudaSetDevice(c->device));
+	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaStreamSynchronize(c->copyStream));
 	if (!c->framePending) { return RSRCU_OK; }
@@ -928,9 +975,10 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 	return RSRCU_OK; }
 
 int rsrcu_sync_frame(rsrcu_ctx* c, int lag) {
-	if (!c || lag < 0 || lag > 1) { return fail(RSRCU_ERR_INVALID, "lag must be 0 or 1"); }
+	if (!c || lag < 0 || lag >= kSlots) { return fail(RSRCU_ERR_INVALID, "lag must be 0 .. %d", kSlots - 1); }
 	CU(cudaSetDevice(c->device));
-	CU(cudaEventSynchronize(c->evCopied[(c->outSlot + lag) & 1]));
+	if (lag == 0) { const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
+	CU(cudaEventSynchronize(c->evCopied[(c->outSlot + kSlots - lag) % kSlots]));
 	return RSRCU_OK; }
 
 int rsrcu_device_truecolor(rsrcu_ctx* c, void** devPtr, int* stridePx) {

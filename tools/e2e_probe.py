@@ -10,11 +10,11 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c4"
 scene, size, workload = bench.make_scene(name)
 W, H = size
 gpu = rsr_b200.GPU(0)
-host_out = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2)]
-for label, outs in (("readback", host_out), ("device-only", [None, None])):
+host_out = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(3)]
+for label, outs in (("readback", host_out), ("device-only", [None, None, None])):
     frames = []
     for i in range(62):
-        scene.record(gpu, size, outs[i & 1], t=i / 60.0, static=(label == "static"))
+        scene.record(gpu, size, outs[i % 3], t=i / 60.0, static=(label == "static"))
         frames.append(gpu.Finish())
     for rec in frames[:2]:
         gpu.Submit(rec)
@@ -25,8 +25,8 @@ for label, outs in (("readback", host_out), ("device-only", [None, None])):
         a = time.perf_counter()
         gpu.Submit(rec, sync=False)
         b = time.perf_counter()
-        if i > 0:
-            gpu.SyncFrame(1)
+        if i > 1:
+            gpu.SyncFrame(2)
         sub.append((b - a, time.perf_counter() - b))
     gpu.Sync()
     dt = time.perf_counter() - t0
