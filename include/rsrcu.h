@@ -234,6 +234,8 @@ typedef struct RsrStats {
 	uint64_t kernel_launches;       /* kernels launched for the frame */
 	uint64_t h2d_bytes;             /* bytes copied host->device for the frame (upload arena) */
 	uint64_t d2h_bytes;             /* bytes copied device->host for the frame (store destinations) */
+	uint64_t list_chunks_run_merge; /* tile-list chunks ordered by run merge ... */
+	uint64_t list_chunks_key_range; /* ... and by key ranges + bitonic sort (long lists) */
 	uint64_t host_record_ns;        /* host time spent recording the frame (begin_frame .. end_frame, all calls) */
 	uint64_t host_submit_ns;        /* host time spent in rsrcu_end_frame (tables, upload, launches) */
 } RsrStats;

@@ -115,7 +115,9 @@ struct Counters {
 	unsigned long long binned;       // triangles accepted for binning (incl. clip fan triangles)
 	unsigned long long clipped;      // triangles sent to the clipper
 	unsigned long long entries;      // (triangle, tile) pairs
-	unsigned long long fragments; }; // pixels written
+	unsigned long long fragments;    // pixels written
+	unsigned int chunksRunMerge;     // list chunks the tile kernel ordered by run merge (mode B) ...
+	unsigned int chunksKeyRange; };  // ... and by key ranges + bitonic sort (mode C)
 
 // Draw that owns a vertex / triangle job.  The host tabulates, per block of 256 jobs, the draw of the
 // block's first job: the search only covers the draws that start inside the block (usually none).

@@ -173,6 +173,7 @@ struct rsrcu_ctx {
 	uint32_t listCapacity{1u << 24};
 	uint32_t largeCapacity{1u << 16};
 	int largeTiles{kLargeTiles};
+	int forceGroupShift{0};            // RSRCU_GROUP_SHIFT (tests): list cells of 1 << shift triangles even in small frames
 	int tcStride{0};
 	Counters* hostCounters{nullptr};   // pinned, [kSlots]
 	RsrStats stats{};
@@ -429,6 +430,8 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 		c->trace = true;
 		c->traceEv.resize(4 * 64);
 		for (auto& ev : c->traceEv) { CU(cudaEventCreate(&ev)); } }
+	if (const char* v = std::getenv("RSRCU_LARGE_TILES")) { const int n = std::atoi(v); if (n > 0) { c->largeTiles = n; } }   // tests
+	if (const char* v = std::getenv("RSRCU_GROUP_SHIFT")) { const int n = std::atoi(v); if (n >= 5 && n < 31) { c->forceGroupShift = n; } }
 	if (const char* cap = std::getenv("RSRCU_LIST_CAPACITY")) {   // initial tile-list capacity in entries (tests)
 		const long v = std::atol(cap);
 		if (v > 0) { c->listCapacity = static_cast<uint32_t>(v); } }
@@ -740,7 +743,8 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	// list cells per tile: one for small frames (a tile's whole list is sorted at once); frames with millions of
 	// triangles split every list by triangle index range so that a cell stays within one raster batch
 	fp.groupShift = 31;
-	if (pjobs > (1u << 18)) { fp.groupShift = 15; while ((pjobs >> fp.groupShift) >= static_cast<uint64_t>(kMaxGroups)) { ++fp.groupShift; } }
+	if (c->forceGroupShift) { fp.groupShift = c->forceGroupShift; while ((pjobs >> fp.groupShift) >= static_cast<uint64_t>(kMaxGroups)) { ++fp.groupShift; } }
+	else if (pjobs > (1u << 18)) { fp.groupShift = 15; while ((pjobs >> fp.groupShift) >= static_cast<uint64_t>(kMaxGroups)) { ++fp.groupShift; } }
 	fp.groups = static_cast<int>(pjobs >> fp.groupShift) + 1;
 	fp.largeCapacity = c->largeCapacity;
 	fp.largeTiles = c->largeTiles;
@@ -898,6 +902,8 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	c->stats.kernel_launches = c->launches;
 	c->stats.h2d_bytes = c->lastH2D;
 	c->stats.d2h_bytes = c->lastD2H;
+	c->stats.list_chunks_run_merge = k.chunksRunMerge;
+	c->stats.list_chunks_key_range = k.chunksKeyRange;
 	c->stats.host_record_ns = c->recordNs;
 	c->stats.host_submit_ns = c->submitNs;
 	if (c->profiling) {

@@ -624,7 +624,7 @@ __device__ __forceinline__ void sort_scratch(TileShared& sh, uint2* scr, const i
 	__syncthreads(); }
 
 __device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restrict__ lists, const int G, const uint32_t totalKeys,
-                                          ListCursor& lc) {
+                                          ListCursor& lc, Counters* __restrict__ ctr) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	uint2* scr = reinterpret_cast<uint2*>(&sh.ec[0][0]);   // (code, key): key is the high word of the 64-bit view
@@ -724,6 +724,7 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restric
 			if (lc.runs == 0) { lc.mode = 2; } }   // interleaved (clip fans) or too many runs
 		if (lc.runs) {
 			const int R = lc.runs;
+			if (t == 0) { atomicAdd(&ctr->chunksRunMerge, 1u); }
 			const int n = static_cast<int>(min(static_cast<uint32_t>(kSortCap), size0 - lc.taken));
 			for (int i = t; i < n; i += kTileThreads) {
 				const uint32_t pos = lc.taken + static_cast<uint32_t>(i);
@@ -738,6 +739,7 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restric
 			return n; } }
 
 	// ---- C: key ranges -------------------------------------------------------------------------
+	if (t == 0) { atomicAdd(&ctr->chunksKeyRange, 1u); }
 	if (lc.taken == 0) {
 		lc.nextKey = 0;
 		const uint32_t rounds = (size0 + (3 * kSortCap / 4) - 1) / (3 * kSortCap / 4);
@@ -836,7 +838,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	int ci = 0;
 	while (true) {
 		if (chunkPos == chunkN && lc.g < G) {
-			chunkN = load_chunk(sh, A.lists, G, A.fp.totalKeys, lc);
+			chunkN = load_chunk(sh, A.lists, G, A.fp.totalKeys, lc, A.ctr);
 			chunkPos = 0; }
 		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
 		uint32_t key0 = 0;
@@ -925,7 +927,10 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
 		// (this barrier also publishes the setup records)
 		const int ntiny = __syncthreads_count(tiny);
-		const bool queued = nb >= 96 && ntiny * 2 > nb;
+#ifndef RSR_QUEUE_MIN_NB
+#define RSR_QUEUE_MIN_NB 96
+#endif
+		const bool queued = nb >= RSR_QUEUE_MIN_NB && ntiny * 2 > nb;
 		switch (key0 & 0xffu) {
 		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, key0, nb, ox, oy, queued); break;
 		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, key0, nb, ox, oy, queued); break;

@@ -474,8 +474,7 @@ class SoupScene:
 
     def record(self, gl, size, out, depth=None, tile_blocks=(8, 8), arrays=False, gamma=True, fp_out=None,
                attachments=None, post=PROGRAM_DEFAULT_POST, post_uniform=None):
-        from . import (GL_COLOR_ATTACHMENT0, GL_DEPTH_ATTACHMENT, PROGRAM_OBJ2S, PROGRAM_PATTERN, RB_F32, RB_RGBF32)
-        w, h = size
+        from . import GL_COLOR_ATTACHMENT0, GL_DEPTH_ATTACHMENT, RB_F32, RB_RGBF32
         gl.Reset(size, tile_blocks)
         if attachments == "split":
             gl.RenderbufferType(GL_COLOR_ATTACHMENT0, RB_RGBF32)
@@ -483,14 +482,32 @@ class SoupScene:
         gl.ClearColor((0.1, 0.2, 0.3))
         gl.ClearDepth(1.0)
         gl.Clear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT)
+        self.draw(gl, size, arrays)
+        gl.UseProgram(post)
+        if post_uniform is not None:
+            gl.UseUniforms(np.array([post_uniform], np.float32))
+        if depth is not None:
+            gl.StoreDepth(depth)
+        if fp_out is not None:
+            gl.StoreColor(fp_out)
+        gl.StoreColor(out, gamma)
+
+    def draw(self, gl, size, arrays=False):
+        """the soup's state and draw call alone (inside a frame somebody else begins and finishes)"""
+        from . import GL_BLEND, PROGRAM_OBJ2S, PROGRAM_PATTERN
+        w, h = size
         gl.UseProgram(self.program)
         gl.ViewMatrix(translate(0.1, -0.05, -1.0) @ rotate(0.2, 0.1, 1.0, 0.3))
         gl.ProjectionMatrix(perspective(70.0, w / h, 0.5, 50.0))
         if self.cull is not None:
             gl.Enable(GL_CULL_FACE)
             gl.CullFace(self.cull)
+        else:
+            gl.Disable(GL_CULL_FACE)
         if self.blend:
             gl.Enable(GL_BLEND)
+        else:
+            gl.Disable(GL_BLEND)
         if self.depth_func is not None:
             gl.DepthFunc(self.depth_func)
         gl.UseBuffer(0, self.pos)
@@ -519,14 +536,6 @@ class SoupScene:
             gl.DrawArrays(len(self.idx))
         else:
             gl.DrawElements(len(self.idx), self.idx, 0)
-        gl.UseProgram(post)
-        if post_uniform is not None:
-            gl.UseUniforms(np.array([post_uniform], np.float32))
-        if depth is not None:
-            gl.StoreDepth(depth)
-        if fp_out is not None:
-            gl.StoreColor(fp_out)
-        gl.StoreColor(out, gamma)
 
 
 class FillStressScene:
