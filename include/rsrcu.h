@@ -157,9 +157,17 @@ int rsrcu_store_color_tc(rsrcu_ctx* ctx, int enable_gamma, uint32_t* dst, int wi
 int rsrcu_store_color_tc_device(rsrcu_ctx* ctx, int enable_gamma, void* device_dst, int width, int height,
                                 int stride_px);
 
-/* CMD_STORE_COLOR_FULL_LINEAR_FP / CMD_STORE_COLOR_HALF_LINEAR_FP (rglv_gpu.cxx:156-169, :345-370):
- * RGBA32F, alpha = what the tile buffer holds (depth for RB_COLOR_DEPTH). */
+/* CMD_STORE_COLOR_FULL_LINEAR_FP (half = 0; Copy, rglr_algorithm.cxx:247-279) and
+ * CMD_STORE_COLOR_HALF_LINEAR_FP (half = 1; Downsample, rglr_algorithm.cxx:118-141: one pixel per
+ * 2x2 quad, ((p0 + p1) + p2) + p3 times 0.25) (rglv_gpu.cxx:156-169, :345-370): RGBA32F pixels,
+ * alpha = 0 as in the reference.  width/height describe dst: the target's size, or half of it. */
 int rsrcu_store_color_fp(rsrcu_ctx* ctx, float* dst, int width, int height, int stride_px, int half);
+
+/* CMD_STORE_COLOR_FULL_QUADS_FP (rglv_gpu.cxx:170-176, :371-383; Copy, rglr_algorithm.cxx:320-368):
+ * dst is a QFloat4Canvas -- 64 bytes per 2x2 quad {r[4], g[4], b[4], a[4]}, lanes = (x,y), (x+1,y),
+ * (x,y+1), (x+1,y+1); stride in quads.  The fourth plane is what the reference's tile buffer holds:
+ * depth for RB_COLOR_DEPTH, 1.0 for RB_RGBF32, the clear colour's alpha for RB_RGBAF32. */
+int rsrcu_store_color_quads(rsrcu_ctx* ctx, float* dst, int width, int height, int stride_quads);
 
 /* CMD_STORE_DEPTH_FULL_LINEAR_FP (rglv_gpu.cxx:186-191, :396-405).  The reference implements it
  * for RB_F32 depth attachments only; here RB_COLOR_DEPTH (depth in alpha) is accepted too. */
@@ -201,6 +209,7 @@ int rsrcu_sync_frame(rsrcu_ctx* ctx, int lag);
  *   RSRCU_OP_STORE_DEPTH   uint64 ptr
  *   RSRCU_OP_END_FRAME     (no payload)
  *   RSRCU_OP_STORE_TC_DEV  int32 gamma, width, height, stride_px; uint64 device ptr
+ *   RSRCU_OP_STORE_QUADS   int32 pad, width, height, stride_quads; uint64 ptr
  */
 #define RSRCU_OP_BEGIN_FRAME 1
 #define RSRCU_OP_STATE 2
@@ -215,6 +224,7 @@ int rsrcu_sync_frame(rsrcu_ctx* ctx, int lag);
 #define RSRCU_OP_STORE_DEPTH 11
 #define RSRCU_OP_END_FRAME 12
 #define RSRCU_OP_STORE_TC_DEV 13
+#define RSRCU_OP_STORE_QUADS 14
 int rsrcu_run_stream(rsrcu_ctx* ctx, const void* stream, size_t bytes);
 
 /* ---- device-side access (viewer presents from the device-resolved buffer; bench; sharding) --- */

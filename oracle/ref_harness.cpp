@@ -41,6 +41,7 @@ struct RefGPU {
 	rglv::GPU gpu;
 	std::deque<rglr::TrueColorCanvas> tcCanvases;
 	std::deque<rglr::FloatingPointCanvas> fpCanvases;
+	std::deque<rglr::QFloat4Canvas> qfCanvases;
 	explicit RefGPU(int threads) : gpu(threads, "oracle") {} };
 
 inline rglv::GL& IC(void* h) { return static_cast<RefGPU*>(h)->gpu.IC(); }
@@ -107,7 +108,8 @@ void ref_gpu_reset(void* h, int w, int hgt, int tileBlocksX, int tileBlocksY) {
 	auto* g = static_cast<RefGPU*>(h);
 	g->gpu.Reset(rmlv::ivec2{w, hgt}, rmlv::ivec2{tileBlocksX, tileBlocksY});
 	g->tcCanvases.clear();
-	g->fpCanvases.clear(); }
+	g->fpCanvases.clear();
+	g->qfCanvases.clear(); }
 
 /* Run one frame to completion.  Caller brackets with ref_work_start/ref_work_end. */
 void ref_gpu_run(void* h) {
@@ -172,6 +174,12 @@ void ref_gl_store_color_fp(void* h, float* dst, int w, int hgt, int stride, int 
 	auto* g = static_cast<RefGPU*>(h);
 	g->fpCanvases.emplace_back(reinterpret_cast<PixelToaster::FloatingPointPixel*>(dst), w, hgt, stride);
 	IC(h).StoreColor(&g->fpCanvases.back(), downsample != 0); }
+
+/* dst: quad-swizzled canvas, 64-byte qfloat4 {r[4], g[4], b[4], a[4]} per 2x2 quad, 16-byte aligned (streaming stores) */
+void ref_gl_store_color_quads(void* h, float* dst, int w, int hgt, int strideQuads) {
+	auto* g = static_cast<RefGPU*>(h);
+	g->qfCanvases.emplace_back(w, hgt, reinterpret_cast<rmlv::qfloat4*>(dst), strideQuads);
+	IC(h).StoreColor(&g->qfCanvases.back()); }
 
 void ref_gl_store_depth(void* h, float* dst) { IC(h).StoreDepth(dst); }
 

@@ -80,6 +80,7 @@ def lib():
             "ref_gl_draw_arrays_instanced": (None, [vp, ci, ci]),
             "ref_gl_store_color_tc": (None, [vp, vp, ci, ci, ci, ci]),
             "ref_gl_store_color_fp": (None, [vp, vp, ci, ci, ci, ci]),
+            "ref_gl_store_color_quads": (None, [vp, vp, ci, ci, ci]),
             "ref_gl_store_depth": (None, [vp, vp]),
             "ref_make_mipmap": (None, [vp, ci, vp]),
             "ref_rcp": (None, [vp, vp, ci]),
@@ -243,6 +244,13 @@ class RefGPU:
         h, w, _ = dst.shape
         self._keep.append(dst)
         self.L.ref_gl_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 1)
+
+    def StoreColorQuads(self, dst: np.ndarray):
+        """dst: (H/2, W/2, 4, 4) float32 = [quad row][quad][r,g,b,a][lane] -> CMD_STORE_COLOR_FULL_QUADS_FP"""
+        assert dst.dtype == np.float32 and dst.ndim == 4 and dst.shape[2:] == (4, 4) and dst.ctypes.data % 16 == 0
+        hq, wq = dst.shape[:2]
+        self._keep.append(dst)
+        self.L.ref_gl_store_color_quads(self.h, _ptr(dst), wq * 2, hq * 2, dst.strides[0] // 64)
 
     def StoreDepth(self, dst: np.ndarray):
         assert dst.dtype == np.float32 and dst.flags.c_contiguous

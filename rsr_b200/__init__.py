@@ -114,6 +114,7 @@ def load_library():
         "rsrcu_store_color_tc": [vp, ci, vp, ci, ci, ci],
         "rsrcu_store_color_tc_device": [vp, ci, vp, ci, ci, ci],
         "rsrcu_store_color_fp": [vp, vp, ci, ci, ci, ci],
+        "rsrcu_store_color_quads": [vp, vp, ci, ci, ci],
         "rsrcu_store_depth": [vp, vp],
         "rsrcu_end_frame": [vp],
         "rsrcu_sync": [vp],
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
     "rsrcu_release_static", "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
-    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
@@ -150,7 +151,7 @@ def _ptr(a):
 
 
 (OP_BEGIN_FRAME, OP_STATE, OP_BIND_BUFFER, OP_BIND_TEXTURE, OP_BIND_DEPTH, OP_CLEAR, OP_DRAW_ELEMENTS,
- OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME, OP_STORE_TC_DEV) = range(1, 14)
+ OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME, OP_STORE_TC_DEV, OP_STORE_QUADS) = range(1, 15)
 
 
 def _addr(a) -> int:
@@ -442,6 +443,29 @@ class GPU:
                 self._check(self.L.rsrcu_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 0))
             else:
                 self._emit(OP_STORE_FP, struct.pack("<iiiiQ", 0, w, h, dst.strides[0] // 16, _addr(dst)))
+
+    def StoreColorHalf(self, dst):
+        """(H/2, W/2, 4) float32 -> CMD_STORE_COLOR_HALF_LINEAR_FP (GL::StoreColor(dst, downsample=true))"""
+        assert dst.dtype == np.float32 and dst.ndim == 3 and dst.shape[2] == 4
+        self._flush_state()
+        h, w, _ = dst.shape
+        self._keep.append(dst)
+        if self.direct:
+            self._check(self.L.rsrcu_store_color_fp(self.h, _ptr(dst), w, h, dst.strides[0] // 16, 1))
+        else:
+            self._emit(OP_STORE_FP, struct.pack("<iiiiQ", 1, w, h, dst.strides[0] // 16, _addr(dst)))
+
+    def StoreColorQuads(self, dst):
+        """(H/2, W/2, 4, 4) float32 = [quad row][quad][r,g,b,a][lane] -> CMD_STORE_COLOR_FULL_QUADS_FP
+        (GL::StoreColor(QFloat4Canvas*))"""
+        assert dst.dtype == np.float32 and dst.ndim == 4 and dst.shape[2:] == (4, 4)
+        self._flush_state()
+        hq, wq = dst.shape[:2]
+        self._keep.append(dst)
+        if self.direct:
+            self._check(self.L.rsrcu_store_color_quads(self.h, _ptr(dst), wq * 2, hq * 2, dst.strides[0] // 64))
+        else:
+            self._emit(OP_STORE_QUADS, struct.pack("<iiiiQ", 0, wq * 2, hq * 2, dst.strides[0] // 64, _addr(dst)))
 
     def StoreColorDevice(self, device_ptr: int, stride_px: int, gamma: bool = True):
         """true-colour resolve straight into caller-owned DEVICE memory (e.g. tensor.data_ptr())"""

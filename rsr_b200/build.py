@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "librsrcu.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "550",
     # the reference is SSE code with separate mul/add: never contract into FMA, keep IEEE div/sqrt,
     # keep denormals (see csrc/dev_math.cuh)
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

@@ -81,7 +81,7 @@ static_assert(sizeof(TriRec) == 80, "TriRec layout");
 constexpr uint32_t kFanIdBit = 0x80000000u;   // list entry: fan triangle (clipRec index << 3 | k) instead of a triangle index
 constexpr uint32_t kRunStartBit = 0x40000000u;   // list entry: first entry of the ascending run one warp appended to the cell
 
-enum FrameCmdType : int { kCmdClear = 1, kCmdStoreTC = 3, kCmdStoreFP = 4, kCmdStoreDepth = 5, kCmdStoreHalfFP = 6 };
+enum FrameCmdType : int { kCmdClear = 1, kCmdStoreTC = 3, kCmdStoreFP = 4, kCmdStoreDepth = 5, kCmdStoreHalfFP = 6, kCmdStoreQuadsFP = 7 };
 
 struct FrameCmd {       // non-draw commands only; draws are found through the tile lists
 	int type;

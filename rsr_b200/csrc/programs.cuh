@@ -55,6 +55,10 @@ struct FragIn {
 	float depth[4];             // gl_FragDepth
 	float BPx[4], BPy[4], BPz[4]; };
 
+#ifndef RSR_TAP_MODE
+#define RSR_TAP_MODE 0
+#endif
+
 // ---- texture units (src/rgl/rglr/rglr_texture_sampler.cxx) -------------------------------------
 
 __device__ __forceinline__ float4 fetch_texel(const TexUnit& tu, int ofs) {
@@ -105,6 +109,9 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 	// ..._P2_MIPMAP_WRAP_LINEAR (rglr_texture_sampler.cxx:166-286).  Coordinates and weights are
 	// computed for two pixels at a time (packed pairs); the four taps of one pixel are blended two
 	// channels at a time (the 128-bit texel is two register pairs) with the weight broadcast.
+	// All 16 tap addresses of the quad are formed first so that every texel request is in flight
+	// before the first blend needs its data: pixel 0's taps as loads, the other twelve as L1
+	// prefetches (no destination registers), then the blends load them from L1 pixel by pixel.
 	const int levelDimI = 1 << (POWER - lod);
 	const int wrapMask = levelDimI - 1;
 	const int levelLastRow = static_cast<int>((0xffffffffu << (POWER - lod)) & ((1u << (POWER + 1)) - 1u)) - 1;
@@ -112,6 +119,8 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 	const uint32_t lastTexel = tu.texelCount - 1u;
 	const f2 one = one2();
 	const f2 negHalf = dup2(-0.5f);
+	uint32_t ofs[4][4];
+	f2 w00[2], w10[2], w01[2], w11[2];
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
 		const f2 levelX = mul2(mk2(u[2 * h], u[2 * h + 1]), levelDim);
@@ -124,10 +133,10 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 		const f2 fy = add2(sub2(levelY, mk2(itof(ty0[0]), itof(ty0[1]))), negHalf);
 		const f2 fx1 = sub2(one, fx);
 		const f2 fy1 = sub2(one, fy);
-		const f2 w00 = mul2(fx1, fy1);
-		const f2 w10 = mul2(fx, fy1);
-		const f2 w01 = mul2(fx1, fy);
-		const f2 w11 = mul2(fx, fy);
+		w00[h] = mul2(fx1, fy1);
+		w10[h] = mul2(fx, fy1);
+		w01[h] = mul2(fx1, fy);
+		w11[h] = mul2(fx, fy);
 #pragma unroll
 		for (int j = 0; j < 2; ++j) {
 			const int l = 2 * h + j;
@@ -135,17 +144,41 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 			const int by0 = levelLastRow - (ty0[j] & wrapMask);
 			const int by1 = levelLastRow - ((ty0[j] + 1) & wrapMask);
 			// (the reference would read out of bounds for a texture without its mip rows; stay inside)
-			const float4 p00 = __ldg(tu.texels + min(static_cast<uint32_t>((by0 << POWER) + x0), lastTexel));
-			const float4 p10 = __ldg(tu.texels + min(static_cast<uint32_t>((by0 << POWER) + x1), lastTexel));
-			const float4 p01 = __ldg(tu.texels + min(static_cast<uint32_t>((by1 << POWER) + x0), lastTexel));
-			const float4 p11 = __ldg(tu.texels + min(static_cast<uint32_t>((by1 << POWER) + x1), lastTexel));
-			const float a00 = j ? hi2(w00) : lo2(w00), a10 = j ? hi2(w10) : lo2(w10);
-			const float a01 = j ? hi2(w01) : lo2(w01), a11 = j ? hi2(w11) : lo2(w11);
-			const f2 rg = add2(add2(add2(mul2(mk2(p00.x, p00.y), a00), mul2(mk2(p10.x, p10.y), a10)), mul2(mk2(p01.x, p01.y), a01)),
-			                   mul2(mk2(p11.x, p11.y), a11));
-			const f2 ba = add2(add2(add2(mul2(mk2(p00.z, p00.w), a00), mul2(mk2(p10.z, p10.w), a10)), mul2(mk2(p01.z, p01.w), a01)),
-			                   mul2(mk2(p11.z, p11.w), a11));
-			r[l] = lo2(rg); g[l] = hi2(rg); b[l] = lo2(ba); a[l] = hi2(ba); } } }
+			ofs[l][0] = min(static_cast<uint32_t>((by0 << POWER) + x0), lastTexel);
+			ofs[l][1] = min(static_cast<uint32_t>((by0 << POWER) + x1), lastTexel);
+			ofs[l][2] = min(static_cast<uint32_t>((by1 << POWER) + x0), lastTexel);
+			ofs[l][3] = min(static_cast<uint32_t>((by1 << POWER) + x1), lastTexel); } }
+#if RSR_TAP_MODE == 2
+#pragma unroll
+	for (int l = 1; l < 4; ++l) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { asm volatile("prefetch.global.L1 [%0];" :: "l"(tu.texels + ofs[l][k])); } }
+#endif
+#if RSR_TAP_MODE == 1
+	float4 tap[4][4];
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { tap[l][k] = __ldg(tu.texels + ofs[l][k]); } }
+#endif
+#pragma unroll
+	for (int l = 0; l < 4; ++l) {
+		const int h = l >> 1, j = l & 1;
+#if RSR_TAP_MODE == 1
+		const float4 p00 = tap[l][0], p10 = tap[l][1], p01 = tap[l][2], p11 = tap[l][3];
+#else
+		const float4 p00 = __ldg(tu.texels + ofs[l][0]);
+		const float4 p10 = __ldg(tu.texels + ofs[l][1]);
+		const float4 p01 = __ldg(tu.texels + ofs[l][2]);
+		const float4 p11 = __ldg(tu.texels + ofs[l][3]);
+#endif
+		const float a00 = j ? hi2(w00[h]) : lo2(w00[h]), a10 = j ? hi2(w10[h]) : lo2(w10[h]);
+		const float a01 = j ? hi2(w01[h]) : lo2(w01[h]), a11 = j ? hi2(w11[h]) : lo2(w11[h]);
+		const f2 rg = add2(add2(add2(mul2(mk2(p00.x, p00.y), a00), mul2(mk2(p10.x, p10.y), a10)), mul2(mk2(p01.x, p01.y), a01)),
+		                   mul2(mk2(p11.x, p11.y), a11));
+		const f2 ba = add2(add2(add2(mul2(mk2(p00.z, p00.w), a00), mul2(mk2(p10.z, p10.w), a10)), mul2(mk2(p01.z, p01.w), a01)),
+		                   mul2(mk2(p11.z, p11.w), a11));
+		r[l] = lo2(rg); g[l] = hi2(rg); b[l] = lo2(ba); a[l] = hi2(ba); } }
 
 // DepthTextureUnit::sample (rglr_texture_sampler.hxx:61-79): nearest, clamp-to-border(-1)
 __device__ __forceinline__ float sample_depth(const DevState& st, float cx, float cy) {

@@ -168,7 +168,7 @@ struct rsrcu_ctx {
 	// device work buffers
 	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems;
 	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
-	DevBuf tcOut[kSlots], fpOut[kSlots], depthOut[kSlots];
+	DevBuf tcOut[kSlots], fpOut[kSlots], halfOut[kSlots], quadsOut[kSlots], depthOut[kSlots];
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 24};
 	uint32_t largeCapacity{1u << 16};
@@ -456,7 +456,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 			std::fprintf(stderr, "rsrcu trace frame %2d: kernels %8.1f .. %8.1f us   read-back %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f); }
 		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->tileOrder, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->counters[2], &c->tcOut[0], &c->tcOut[1], &c->tcOut[2], &c->fpOut[0], &c->fpOut[1], &c->fpOut[2],
+	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->tileOrder, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->counters[2], &c->tcOut[0], &c->tcOut[1], &c->tcOut[2], &c->fpOut[0], &c->fpOut[1], &c->fpOut[2], &c->halfOut[0], &c->halfOut[1], &c->halfOut[2], &c->quadsOut[0], &c->quadsOut[1], &c->quadsOut[2],
 	                   &c->depthOut[0], &c->depthOut[1], &c->depthOut[2] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
@@ -675,15 +675,30 @@ int rsrcu_store_color_tc_device(rsrcu_ctx* c, int gamma, void* deviceDst, int wi
 
 int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int stridePx, int half) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
-	if (half) { return fail(RSRCU_ERR_UNSUPPORTED, "CMD_STORE_COLOR_HALF_LINEAR_FP is not built yet"); }
-	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target", width, height); }
+	// the half-size canvas holds one pixel per 2x2 quad of the target (GL::StoreColor(dst, downsample), rglv_gl.cxx)
+	const int wantW = half ? c->width / 2 : c->width, wantH = half ? c->height / 2 : c->height;
+	if (width != wantW || height != wantH) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != %s target %dx%d", width, height, half ? "half" : "full", wantW, wantH); }
 	CU(cudaSetDevice(c->device));
-	CU(c->fpOut[c->outSlot].reserve(static_cast<size_t>(width) * height * 16));
-	int r = pushCmd(c, kCmdStoreFP, 0, c->fpOut[c->outSlot].ptr, width, 2);
+	DevBuf& out = half ? c->halfOut[c->outSlot] : c->fpOut[c->outSlot];
+	CU(out.reserve(static_cast<size_t>(width) * height * 16));
+	int r = pushCmd(c, half ? kCmdStoreHalfFP : kCmdStoreFP, 0, out.ptr, width, 2);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->fpOut[c->outSlot].ptr, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
+		c->copies.push_back(PendingCopy{dst, out.ptr, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
 		                                static_cast<size_t>(stridePx) * 16, static_cast<size_t>(width) * 16}); }
+	return RSRCU_OK; }
+
+int rsrcu_store_color_quads(rsrcu_ctx* c, float* dst, int width, int height, int strideQuads) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
+	if (strideQuads < width / 2) { return fail(RSRCU_ERR_INVALID, "quad canvas stride %d < %d quads per row", strideQuads, width / 2); }
+	CU(cudaSetDevice(c->device));
+	const size_t rowBytes = static_cast<size_t>(width / 2) * 64, rows = static_cast<size_t>(height / 2);
+	CU(c->quadsOut[c->outSlot].reserve(rowBytes * rows));
+	int r = pushCmd(c, kCmdStoreQuadsFP, 0, c->quadsOut[c->outSlot].ptr, width / 2, 2);
+	if (r != RSRCU_OK) { return r; }
+	if (dst) {
+		c->copies.push_back(PendingCopy{dst, c->quadsOut[c->outSlot].ptr, rowBytes, rows, static_cast<size_t>(strideQuads) * 64, rowBytes}); }
 	return RSRCU_OK; }
 
 int rsrcu_store_depth(rsrcu_ctx* c, float* dst) {
@@ -964,6 +979,8 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 			r = rsrcu_store_color_tc(c, i32(0), reinterpret_cast<uint32_t*>(u64(16)), i32(1), i32(2), i32(3)); break;
 		case RSRCU_OP_STORE_FP: if (!need(24)) { goto bad; }
 			r = rsrcu_store_color_fp(c, reinterpret_cast<float*>(u64(16)), i32(1), i32(2), i32(3), i32(0)); break;
+		case RSRCU_OP_STORE_QUADS: if (!need(24)) { goto bad; }
+			r = rsrcu_store_color_quads(c, reinterpret_cast<float*>(u64(16)), i32(1), i32(2), i32(3)); break;
 		case RSRCU_OP_STORE_DEPTH: if (!need(8)) { goto bad; } r = rsrcu_store_depth(c, reinterpret_cast<float*>(u64(0))); break;
 		case RSRCU_OP_END_FRAME: r = rsrcu_end_frame(c); break;
 		case RSRCU_OP_STORE_TC_DEV: if (!need(24)) { goto bad; }

@@ -896,6 +896,32 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 						dst[static_cast<size_t>(py + (l >> 1)) * cmd.dstStride + px + (l & 1)] =
 							make_float4(sh.chan[0][l][t], sh.chan[1][l][t], sh.chan[2][l][t], 0.0f); } } }
 				break;
+			case kCmdStoreHalfFP: {
+				// Downsample(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:118-141): one output
+				// pixel per quad, ((p0 + p1) + p2) + p3 then * 0.25, alpha = 0
+				if (onScreen) {
+					float4* dst = static_cast<float4*>(cmd.dst);
+					float avg[3];
+#pragma unroll
+					for (int ch = 0; ch < 3; ++ch) {
+						avg[ch] = (((sh.chan[ch][0][t] + sh.chan[ch][1][t]) + sh.chan[ch][2][t]) + sh.chan[ch][3][t]) * 0.25f; }
+					dst[static_cast<size_t>(py >> 1) * cmd.dstStride + (px >> 1)] = make_float4(avg[0], avg[1], avg[2], 0.0f); } }
+				break;
+			case kCmdStoreQuadsFP: {
+				// Copy(QFloat4Canvas | QFloat3Canvas -> QFloat4Canvas) (rglr_algorithm.cxx:320-368): the quad-
+				// swizzled layout itself, 64 bytes per 2x2 quad {r[4], g[4], b[4], a[4]}.  The fourth plane is
+				// what the reference's tile holds there: depth (RB_COLOR_DEPTH), 1.0 (RB_RGBF32), or the
+				// clear colour's alpha (RB_RGBAF32: no program writes alpha)
+				if (onScreen) {
+					float4* dst = static_cast<float4*>(cmd.dst) + (static_cast<size_t>(py >> 1) * cmd.dstStride + (px >> 1)) * 4;
+#pragma unroll
+					for (int ch = 0; ch < 3; ++ch) {
+						dst[ch] = make_float4(sh.chan[ch][0][t], sh.chan[ch][1][t], sh.chan[ch][2][t], sh.chan[ch][3][t]); }
+					if (s.color0Type == 0) { dst[3] = make_float4(sh.chan[3][0][t], sh.chan[3][1][t], sh.chan[3][2][t], sh.chan[3][3][t]); }
+					else {
+						const float a = (s.color0Type == 1) ? 1.0f : s.clearColor[3];
+						dst[3] = make_float4(a, a, a, a); } } }
+				break;
 			case kCmdStoreDepth: {
 				if (onScreen) {
 					float* dst = static_cast<float*>(cmd.dst);

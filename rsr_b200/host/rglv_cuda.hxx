@@ -112,6 +112,11 @@ public:
 		MaybeUpdateState();
 		const int32_t p[4] = { downsample ? 1 : 0, width, height, stridePx };
 		Emit(RSRCU_OP_STORE_FP, p, sizeof(p), reinterpret_cast<uint64_t>(dst)); }
+	// StoreColor(QFloat4Canvas*): quad-swizzled RGBA32F, 64 bytes per 2x2 quad, stride in quads
+	void StoreColorQuads(float* dst, int width, int height, int strideQuads) {
+		MaybeUpdateState();
+		const int32_t p[4] = { 0, width, height, strideQuads };
+		Emit(RSRCU_OP_STORE_QUADS, p, sizeof(p), reinterpret_cast<uint64_t>(dst)); }
 	void StoreDepth(float* dst) {
 		MaybeUpdateState();
 		Emit(RSRCU_OP_STORE_DEPTH, nullptr, 0, reinterpret_cast<uint64_t>(dst)); }

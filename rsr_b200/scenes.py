@@ -473,7 +473,7 @@ class SoupScene:
         self.triangles = n * max(1, instanced)
 
     def record(self, gl, size, out, depth=None, tile_blocks=(8, 8), arrays=False, gamma=True, fp_out=None,
-               attachments=None, post=PROGRAM_DEFAULT_POST, post_uniform=None):
+               attachments=None, post=PROGRAM_DEFAULT_POST, post_uniform=None, half_out=None, quads_out=None):
         from . import GL_COLOR_ATTACHMENT0, GL_DEPTH_ATTACHMENT, RB_F32, RB_RGBF32
         gl.Reset(size, tile_blocks)
         if attachments == "split":
@@ -490,6 +490,10 @@ class SoupScene:
             gl.StoreDepth(depth)
         if fp_out is not None:
             gl.StoreColor(fp_out)
+        if half_out is not None:
+            gl.StoreColorHalf(half_out)
+        if quads_out is not None:
+            gl.StoreColorQuads(quads_out)
         gl.StoreColor(out, gamma)
 
     def draw(self, gl, size, arrays=False):

@@ -148,3 +148,35 @@ def test_iq_post_program(gamma, tile_blocks, ref_gpu, cuda_gpu):
     scene = SoupScene(n=300, seed=72)
     outs = render_both(scene, (640, 360), ref_gpu, cuda_gpu, gamma=gamma, post=R.PROGRAM_IQ_POST, tile_blocks=tile_blocks)
     assert_identical(outs, f"IQ post gamma={gamma} tiles={tile_blocks}")
+
+
+def _aligned(shape):
+    """float32 array whose data is 16-byte aligned (the reference writes it with streaming stores)"""
+    n = int(np.prod(shape))
+    raw = np.zeros(n + 4, np.float32)
+    ofs = (-raw.ctypes.data // 4) % 4
+    return raw[ofs:ofs + n].reshape(shape)
+
+
+@pytest.mark.parametrize("attachments", [None, "split"])
+@pytest.mark.parametrize("size", [(640, 360), (248, 120)])   # (the reference itself needs widths that are multiples of 4)
+def test_half_size_and_quad_swizzled_float_stores(attachments, size, ref_gpu, cuda_gpu):
+    """CMD_STORE_COLOR_HALF_LINEAR_FP (Downsample) and CMD_STORE_COLOR_FULL_QUADS_FP (quad-swizzled copy; the
+    fourth plane holds depth for RB_COLOR_DEPTH and 1.0 for RB_RGBF32), bit for bit"""
+    w, h = size
+    scene = SoupScene(n=300, seed=77)
+    got = {}
+    for name, gl in (("ref", ref_gpu), ("cuda", cuda_gpu)):
+        color = np.zeros((h, w), np.uint32)
+        half = _aligned((h // 2, w // 2, 4))
+        quads = _aligned((h // 2, w // 2, 4, 4))
+        half[:] = -1.0
+        quads[:] = -1.0
+        scene.record(gl, size, color, half_out=half, quads_out=quads, attachments=attachments)
+        gl.Run()
+        got[name] = (color, half, quads)
+    (rc, rh, rq), (cc, ch, cq) = got["ref"], got["cuda"]
+    assert np.array_equal(rc, cc)
+    assert np.unique(rh.view(np.uint32)).size > 100
+    assert np.array_equal(rh.view(np.uint32), ch.view(np.uint32)), "half-size float store differs"
+    assert np.array_equal(rq.view(np.uint32), cq.view(np.uint32)), "quad-swizzled float store differs"
