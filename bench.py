@@ -148,22 +148,36 @@ def time_reference(scene, size, steps, warmup, threads=None, budget_s=25.0):
 
 def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flush, barrier):
     """C5: one 7680x4320 frame = 4x4 sub-frames of 1920x1080 (the reference's guard band ends at 2048 px),
-    sub-frames dealt round-robin to the ranks, each rank resolves its sub-frames straight into a torch
-    buffer and NCCL gathers them to the presenting GPU (rank 0).  Strong scaling: the frame is fixed."""
+    sub-frames dealt round-robin to the ranks.  Strong scaling: the frame is fixed.
+    --exchange p2p (default): every rank's tile kernel resolves straight into the presenting GPU's frame
+    buffer (CUDA-IPC mapping, peer stores over NVLink while it rasterises); a frame ends with one small
+    NCCL all-reduce as the completion barrier.  --exchange nccl: render locally, NCCL gather, assemble."""
     from rsr_b200 import scenes
+    from rsr_b200.present import PresentedFrame
     from rsr_b200.subframes import SubframePlan
     plan = SubframePlan(7680, 4320, world, 1920, 1080)
     mine = plan.owned_by(rank)
     dev = f"cuda:{local_rank}"
     P = scenes.perspective(45.0, 7680 / 4320, 1.0, 400.0)
-    local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
-    recs = []
-    for k, sf in enumerate(mine):
-        scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf), device_out=(local[k].data_ptr(), 1920))
-        recs.append(gpu.Finish())
-    gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
-    frame = torch.zeros((4320, 7680), dtype=torch.int32, device=dev) if rank == 0 else None
+    p2p = args.exchange == "p2p"
     cur = torch.cuda.current_stream()
+    recs = []
+    if p2p:
+        pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist)
+        gpu.EnablePeerAccess(pf.presenter_device)
+        frame = pf.local
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+        for sf in mine:
+            scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf),
+                         device_out=(pf.pointer(sf.x0, sf.y0), pf.stride_px))
+            recs.append(gpu.Finish())
+    else:
+        local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
+        for k, sf in enumerate(mine):
+            scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf), device_out=(local[k].data_ptr(), 1920))
+            recs.append(gpu.Finish())
+        gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
+        frame = torch.zeros((4320, 7680), dtype=torch.int32, device=dev) if rank == 0 else None
 
     def step():
         for rec in recs:
@@ -172,6 +186,10 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
         with torch.cuda.stream(stream):
             done.record(stream)
         cur.wait_event(done)                       # NCCL runs on torch's stream, after the render stream
+        if p2p:
+            if world > 1:
+                dist.all_reduce(token)             # every rank's kernels (and with them their peer stores) have completed
+            return
         if world > 1:
             dist.gather(local, gathered, dst=0)
         if rank == 0:
@@ -207,16 +225,19 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
     st = gpu.stats()
     if rank == 0:
         checksum = int(frame.to(torch.int64).sum().item())
+        exchange = "none" if world == 1 else ("tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce as barrier"
+                                              if p2p else "NCCL gather of resolved sub-frames to rank 0 + assembly copies")
         line = {"metric": "frames_per_sec_8k_split_frame", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32+i32", "data": "synthetic",
                 "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
-                           "subframes_per_rank": len(mine), "exchange": "NCCL gather of resolved sub-frames to rank 0" if world > 1 else "none",
+                           "subframes_per_rank": len(mine), "exchange": exchange,
                            "cache": "L2 flushed before every timed frame"},
                 "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks, "frame_checksum": checksum,
                 "gpu_launches": int(st["kernel_launches"]) * len(mine) * args.steps}
         print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -229,6 +250,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5 only: how resolved pixels reach the presenting GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

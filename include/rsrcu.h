@@ -157,6 +157,13 @@ int rsrcu_store_color_tc(rsrcu_ctx* ctx, int enable_gamma, uint32_t* dst, int wi
 int rsrcu_store_color_tc_device(rsrcu_ctx* ctx, int enable_gamma, void* device_dst, int width, int height,
                                 int stride_px);
 
+/* Split-frame presentation over NVLink: lets this context's kernels store into memory that lives on
+ * `peer_device` (cudaDeviceEnablePeerAccess; already-enabled is not an error).  The destination of
+ * rsrcu_store_color_tc_device may then be a (CUDA-IPC-opened or same-process) pointer into the presenting
+ * GPU's frame buffer: the tile kernel's resolve writes travel as peer stores while it rasterises, so
+ * there is no separate gather step. */
+int rsrcu_enable_peer_access(rsrcu_ctx* ctx, int peer_device);
+
 /* CMD_STORE_COLOR_FULL_LINEAR_FP (half = 0; Copy, rglr_algorithm.cxx:247-279) and
  * CMD_STORE_COLOR_HALF_LINEAR_FP (half = 1; Downsample, rglr_algorithm.cxx:118-141: one pixel per
  * 2x2 quad, ((p0 + p1) + p2) + p3 times 0.25) (rglv_gpu.cxx:156-169, :345-370): RGBA32F pixels,

@@ -673,6 +673,18 @@ int rsrcu_store_color_tc_device(rsrcu_ctx* c, int gamma, void* deviceDst, int wi
 		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d", c->curStatePtr->program_id); }
 	return pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, deviceDst, stridePx, 1); }
 
+int rsrcu_enable_peer_access(rsrcu_ctx* c, int peerDevice) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (peerDevice == c->device) { return RSRCU_OK; }
+	CU(cudaSetDevice(c->device));
+	int can = 0;
+	CU(cudaDeviceCanAccessPeer(&can, c->device, peerDevice));
+	if (!can) { return fail(RSRCU_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", c->device, peerDevice); }
+	const cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+	if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RSRCU_OK; }
+	CU(e);
+	return RSRCU_OK; }
+
 int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int stridePx, int half) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	// the half-size canvas holds one pixel per 2x2 quad of the target (GL::StoreColor(dst, downsample), rglv_gl.cxx)

@@ -1,0 +1,51 @@
+"""The presenting GPU's frame buffer, shared with the other ranks of the node.
+
+Split-frame rendering (BASELINE.json configs[4]): every rank renders the sub-frames it
+owns; the only exchange is getting resolved 8-bit pixels to the GPU that presents.  Instead of
+rendering into a local buffer and gathering afterwards, rank 0 allocates the whole frame once and
+hands the other ranks a CUDA-IPC mapping of it; their tile kernels then resolve straight into it --
+the pixels cross NVLink / NVSwitch as peer stores while the kernel is still rasterising other
+tiles, and a frame ends with one small barrier instead of a gather plus an assembly copy.
+PyTorch is plumbing here (allocation, IPC handle exchange over the process group).
+"""
+from __future__ import annotations
+
+
+class PresentedFrame:
+    """frame: (height, width) int32 tensor on the presenting rank's GPU; on other ranks a peer mapping"""
+
+    def __init__(self, width: int, height: int, rank: int, local_rank: int, world: int, dist=None, presenter: int = 0):
+        import torch
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.width, self.height = width, height
+        self.rank, self.world, self.presenter = rank, world, presenter
+        self.local = None
+        if rank == presenter:
+            self.local = torch.zeros((height, width), dtype=torch.int32, device=f"cuda:{local_rank}")
+        if world == 1:
+            self.frame = self.local
+            self.presenter_device = local_rank
+            return
+        box = [None]
+        if rank == presenter:
+            fn, args = reduce_tensor(self.local)
+            box = [(fn, args, local_rank)]
+        dist.broadcast_object_list(box, src=presenter)
+        fn, args, self.presenter_device = box[0]
+        if rank == presenter:
+            self.frame = self.local
+        else:
+            # open the handle from THIS rank's device (argument 6 of rebuild_cuda_tensor = the device whose context maps
+            # the memory): cudaIpcOpenMemHandle then maps the presenter's memory for this GPU with peer access
+            # over NVLink.  The tensor only carries the address; it is never used for torch compute.
+            args = list(args)
+            args[6] = local_rank
+            self.frame = fn(*args)
+
+    def pointer(self, x0: int, y0: int) -> int:
+        """device address of pixel (x0, y0) -- valid in this process for kernels on any GPU with peer access"""
+        return self.frame.data_ptr() + 4 * (y0 * self.width + x0)
+
+    @property
+    def stride_px(self) -> int:
+        return self.width
