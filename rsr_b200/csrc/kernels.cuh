@@ -130,6 +130,14 @@ __device__ __forceinline__ int find_draw(const DevDraw* __restrict__ draws, cons
 		if (b <= job) { lo = mid; } else { hi = mid - 1; } }
 	return lo; }
 
+// Programmatic dependent launch (sm_90+): every kernel of the frame is launched with the "programmatic
+// stream serialization" attribute.  pdl_launch_dependents lets the next kernel's CTAs become resident
+// (and run their prologue) as soon as every CTA of this grid has passed the call; pdl_wait blocks until
+// the previous grid has completed and its writes are visible.  Every kernel waits before it reads or
+// writes anything another kernel of the stream touches, so completion stays transitive.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 __device__ __forceinline__ uint32_t pack_tiles(int tx0, int ty0, int tx1, int ty1) {
 	return static_cast<uint32_t>(tx0) | (static_cast<uint32_t>(ty0) << 6) |
 	       (static_cast<uint32_t>(tx1) << 12) | (static_cast<uint32_t>(ty1) << 18); }
@@ -143,6 +151,8 @@ __device__ __forceinline__ uint32_t pack_tiles(int tx0, int ty0, int tx1, int ty
 
 __global__ void __launch_bounds__(256)
 upload_kernel(const uint4* __restrict__ hostSrc, uint4* __restrict__ dst, size_t n16, uint4* __restrict__ zero, size_t nzero16) {
+	pdl_launch_dependents();
+	pdl_wait();   // the previous frame's kernels still read the control block / may read this arena's mirror
 	const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
 	const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	for (size_t i = tid; i < n16; i += stride) { dst[i] = hostSrc[i]; }
@@ -177,6 +187,8 @@ __device__ __forceinline__ void run_vertex_program(const DevState& s, const Vert
 __global__ void __launch_bounds__(256)
 vertex_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
               const ApproxLuts* __restrict__ luts, float4* __restrict__ ptvb, uint8_t* __restrict__ vflags) {
+	pdl_launch_dependents();
+	pdl_wait();
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	if (job >= fp.totalVJobs) { return; }
 	const int di = find_draw(draws, blockDraw, job, true);
@@ -566,6 +578,8 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
              const ApproxLuts* __restrict__ luts, const float4* __restrict__ ptvb, const uint8_t* __restrict__ vflags,
              uint2* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
              BinArgs B, uint32_t* __restrict__ tileBase, uint32_t* __restrict__ tileOrder, Counters* __restrict__ ctr) {
+	pdl_launch_dependents();
+	pdl_wait();
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	uint2 myInfo = make_uint2(kReject, 0u);
 	if (job < fp.totalPJobs) {
@@ -642,6 +656,8 @@ __global__ void __launch_bounds__(256)
 cell_scan_kernel(FrameParams fp, const uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellRel,
                  uint32_t* __restrict__ tileTotal, uint32_t* __restrict__ tileBase, uint32_t* __restrict__ tileOrder,
                  Counters* __restrict__ ctr) {
+	pdl_launch_dependents();
+	pdl_wait();
 	const int ntiles = fp.tilesX * fp.tilesY;
 	const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
 	const int lane = threadIdx.x & 31;
@@ -666,6 +682,8 @@ cell_scan_kernel(FrameParams fp, const uint32_t* __restrict__ cellCount, uint32_
 __global__ void __launch_bounds__(256)
 fill_kernel(FrameParams fp, const uint2* __restrict__ triInfo, const ClipRec* __restrict__ clipRecs,
             BinArgs B, Counters* __restrict__ ctr) {
+	pdl_launch_dependents();
+	pdl_wait();
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	uint2 info = make_uint2(kReject, 0u);
 	if (job < fp.totalPJobs) { info = triInfo[job]; }

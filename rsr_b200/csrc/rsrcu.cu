@@ -382,6 +382,21 @@ int snapshotState(rsrcu_ctx* c) {
 	c->stateDirty = false;
 	return RSRCU_OK; }
 
+// every kernel of the frame is launched with programmatic stream serialization (see pdl_wait in kernels.cuh)
+template <class... KArgs, class... Args>
+cudaError_t launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(grid, 1, 1);
+	cfg.blockDim = dim3(block, 1, 1);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); }
+
 int flushDeferredCopies(rsrcu_ctx* c) {
 	if (c->deferredSlot < 0) { return RSRCU_OK; }
 	const int slot = c->deferredSlot;
@@ -852,36 +867,35 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		// K0: upload + zeroed control block in one kernel (kernels.cuh)
 		const size_t n16 = (c->arenas[c->cur].used + 15) / 16, nz16 = (ctrlBytes + 15) / 16;
 		const int blocks = static_cast<int>(std::min<size_t>(148 * 8, (std::max(n16, nz16) + 255) / 256));
-		upload_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const uint4*>(c->arenas[c->cur].host),
-			static_cast<uint4*>(c->arenas[c->cur].dev.ptr), n16, reinterpret_cast<uint4*>(dCtr), nz16);
+		CU(launchPdl(upload_kernel, static_cast<unsigned>(std::max(blocks, 1)), 256u, 0, st, reinterpret_cast<const uint4*>(c->arenas[c->cur].host),
+			static_cast<uint4*>(c->arenas[c->cur].dev.ptr), n16, reinterpret_cast<uint4*>(dCtr), nz16));
 		++c->launches; }
 	CU(cudaEventRecord(c->arenaFree[c->cur], st));
-	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }   // the previous frame's read-back
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[1], st)); }
 	const int traceIdx = (c->trace && c->traceFrames < 64) ? c->traceFrames++ : -1;
 	if (traceIdx >= 0) { c->traceFrameOfSlot[c->outSlot] = traceIdx; CU(cudaEventRecord(c->traceEv[4 * traceIdx], st)); }
 	else { c->traceFrameOfSlot[c->outSlot] = -1; }
 
 	if (fp.totalVJobs) {
-		vertex_kernel<<<(fp.totalVJobs + 255) / 256, 256, 0, st>>>(dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp, c->devLuts,
-			static_cast<float4*>(c->ptvb.ptr), static_cast<uint8_t*>(c->vflags.ptr));
+		CU(launchPdl(vertex_kernel, (fp.totalVJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(c->ptvb.ptr), static_cast<uint8_t*>(c->vflags.ptr)));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
 	if (fp.totalPJobs) {
-		setup_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp, c->devLuts,
-			static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
+		CU(launchPdl(setup_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp,
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
 			static_cast<uint2*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
-			bin, static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr);
+			bin, static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
 	if (fp.totalPJobs && fp.groups > 1) {
-		cell_scan_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(fp, bin.cellCount, static_cast<uint32_t*>(c->cellRel.ptr),
-			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr);
+		CU(launchPdl(cell_scan_kernel, static_cast<unsigned>((ntiles + 7) / 8), 256u, 0, st, fp, static_cast<const uint32_t*>(bin.cellCount), static_cast<uint32_t*>(c->cellRel.ptr),
+			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
 	if (fp.totalPJobs) {
-		fill_kernel<<<(fp.totalPJobs + 255) / 256, 256, 0, st>>>(fp, static_cast<const uint2*>(c->triInfo.ptr),
-			static_cast<const ClipRec*>(c->clipRecs.ptr), bin, dCtr);
+		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(c->triInfo.ptr),
+			static_cast<const ClipRec*>(c->clipRecs.ptr), bin, dCtr));
 		++c->launches; }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], st)); }
 
@@ -896,7 +910,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	ta.large = bin.large;
 	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(c->tileOrder.ptr) : nullptr;
 	ta.ctr = dCtr;
-	tile_kernel<<<ntiles, kTileThreads, sizeof(TileShared), st>>>(ta);
+	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), st, ta));
 	++c->launches;
 	CU(cudaGetLastError());
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], st)); }
@@ -909,6 +923,9 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	c->deferredCopies = c->copies;
 	c->deferredSlot = c->outSlot;
 	c->framePending = true;
+	// the read-back goes to the copy stream right away (it waits for evRendered there): the upload is a kernel
+	// (K0), so a queued device->host copy cannot hold up the next frame's upload on a copy engine
+	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
 	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tSubmit).count());
 	return RSRCU_OK; }
 

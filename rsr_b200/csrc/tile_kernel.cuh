@@ -37,7 +37,10 @@ __constant__ uint32_t kSrgbTab4[104] = {
 };
 
 constexpr int kSortCap = 1024;           // most list entries sorted in one round
-constexpr int kRunCap = 1024;            // most runs of one cell that the run merge handles
+#ifndef RSR_RUN_CAP
+#define RSR_RUN_CAP 1024
+#endif
+constexpr int kRunCap = RSR_RUN_CAP;     // most runs of one cell that the run merge handles
 
 struct TileShared {
 	float chan[4][4][kTileThreads];      // [r,g,b,depth][quad lane][thread]
@@ -62,6 +65,8 @@ struct TileShared {
 	uint32_t srgbTab[104];               // ryg table: per-pixel indices diverge, constant memory would serialise
 	int firstBad;
 	int sortCount;
+	int headDraw;                        // draw and batch key of the first entry of the batch being formed
+	uint32_t headKey;
 };
 static_assert(offsetof(TileShared, ec) % 8 == 0 && sizeof(int) * 9 * kBatch >= 8 * kSortCap, "sort scratch aliases ec/edx/edy");
 
@@ -80,6 +85,10 @@ struct TileArgs {
 	const LargeItem* large;              // queued large items (kernels.cuh)
 	const uint32_t* tileOrder;           // CTA -> tile, tiles with the longest lists first (nullptr: identity)
 	Counters* ctr; };
+
+__device__ __forceinline__ void prefetch_entry(const TileArgs& A, uint32_t id) {
+	const void* p = (id & kFanIdBit) ? static_cast<const void*>(A.clipRecs + ((id & ~kFanIdBit) >> 3)) : static_cast<const void*>(A.triRecs + id);
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 __device__ __forceinline__ bool top_left(int dy, int dx) { return (dy > 0) || (dy == 0 && dx > 0); }
 
@@ -148,21 +157,28 @@ __device__ __forceinline__ void setup_edges(TileShared& sh, int slot, bool wide,
 	                (static_cast<uint32_t>(lmaxx) << 12) | (static_cast<uint32_t>(lmaxy) << 18) |
 	                (clipped ? (1u << 24) : 0u); }
 
-// list entry -> (draw index, batch key, state index) of its triangle
-__device__ __forceinline__ uint3 entry_owner(const TileArgs& A, uint32_t id) {
+// The 80-byte triangle record (or, for a clip fan triangle, the owner words of its clip record) as the
+// tile kernel carries it in registers between "who owns this entry" and "set it up": ONE trip to
+// memory per list entry instead of two.
+struct EntryRec { uint4 q0, q1, q2, q3, q4; };
+
+__device__ __forceinline__ EntryRec load_entry(const TileArgs& A, uint32_t id) {
+	EntryRec e;
 	if (id & kFanIdBit) {
 		const ClipRec& rec = A.clipRecs[(id & ~kFanIdBit) >> 3];
-		return make_uint3(rec.draw, rec.key, rec.state & 0xffffu); }
-	const uint4 w = __ldg(reinterpret_cast<const uint4*>(A.triRecs + id) + 4);   // key, state, pad, pad
-	const uint32_t draw = __ldg(reinterpret_cast<const uint32_t*>(A.triRecs + id) + 15);
-	return make_uint3(draw, w.x, w.y); }
+		e.q0 = e.q1 = e.q2 = make_uint4(0u, 0u, 0u, 0u);
+		e.q3 = make_uint4(0u, 0u, 0u, rec.draw);
+		e.q4 = make_uint4(rec.key, rec.state & 0xffffu, 0u, 0u); }
+	else {
+		const uint4* r = reinterpret_cast<const uint4*>(A.triRecs + id);
+		e.q0 = __ldg(r); e.q1 = __ldg(r + 1); e.q2 = __ldg(r + 2); e.q3 = __ldg(r + 3); e.q4 = __ldg(r + 4); }
+	return e; }
 
-__device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_t id, const TileArgs& A,
+__device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_t id, const EntryRec& e, const TileArgs& A,
                                                int ox, int oy, int rl, int rt, int rr, int rb) {
 	if (!(id & kFanIdBit)) {
 		// GPUTileImpl::DrawTriangles (rglv_gpu_impl.hxx:880-946): everything was prepared by K2
-		const uint4* r = reinterpret_cast<const uint4*>(A.triRecs + id);
-		const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2), q3 = __ldg(r + 3);
+		const uint4 q0 = e.q0, q1 = e.q1, q2 = e.q2, q3 = e.q3;
 		sh.z[0][slot] = __uint_as_float(q1.z); sh.z[1][slot] = __uint_as_float(q1.w); sh.z[2][slot] = __uint_as_float(q2.x);
 		sh.iw[0][slot] = __uint_as_float(q2.y); sh.iw[1][slot] = __uint_as_float(q2.z); sh.iw[2][slot] = __uint_as_float(q2.w);
 		sh.vref[0][slot] = q3.x; sh.vref[1][slot] = q3.y; sh.vref[2][slot] = q3.z;
@@ -623,7 +639,7 @@ __device__ __forceinline__ void sort_scratch(TileShared& sh, uint2* scr, const i
 		for (int i = t; i < n; i += kTileThreads) { sh.sorted[i] = scr[i].x; } }
 	__syncthreads(); }
 
-__device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restrict__ lists, const int G, const uint32_t totalKeys,
+__device__ __forceinline__ int load_chunk(TileShared& sh, const TileArgs& A, const uint2* __restrict__ lists, const int G, const uint32_t totalKeys,
                                           ListCursor& lc, Counters* __restrict__ ctr) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
@@ -645,7 +661,10 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const uint2* __restric
 		while (gEnd < G && (sh.cellOff[gEnd + 1] - begin) + nl + sh.lgPerGroup[gEnd] <= static_cast<uint32_t>(kBatch)) { nl += sh.lgPerGroup[gEnd]; ++gEnd; }
 		const int nlist = static_cast<int>(sh.cellOff[gEnd] - begin);
 		const int n = nlist + static_cast<int>(nl);
-		if (t < nlist) { const uint2 e = __ldg(list + t); scr[t] = make_uint2(e.y & ~kRunStartBit, e.x); }
+		if (t < nlist) {
+			const uint2 e = __ldg(list + t);
+			scr[t] = make_uint2(e.y & ~kRunStartBit, e.x);
+			prefetch_entry(A, e.y & ~kRunStartBit); }   // the record's trip to memory overlaps the sort
 		if (nl) {
 			if (t == 0) { sh.sortCount = nlist; }
 			__syncthreads();
@@ -779,11 +798,27 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	extern __shared__ __align__(16) unsigned char tileSmem[];
 	TileShared& sh = *reinterpret_cast<TileShared*>(tileSmem);
 	const int t = threadIdx.x;
+	const int warp = t >> 5, lane = t & 31;
+	const int lx = (warp & 1) * 16 + (lane & 7) * 2, ly = (warp >> 1) * 8 + (lane >> 3) * 2;
+
+	// Everything up to the grid dependency wait touches only data that no kernel of the frame writes (the
+	// approximation tables, constants): with programmatic dependent launch this prologue runs while the
+	// list fill kernel is still draining.
+#pragma unroll
+	for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = __ldg(A.luts->rcp + k * kTileThreads + t); }
+	if (t < 104) { sh.srgbTab[t] = kSrgbTab4[t]; }
+	if (t < kMaxGroups) { sh.lgPerGroup[t] = 0; }
+	if (t == 0) { sh.lgCount = 0; }
+#pragma unroll
+	for (int c = 0; c < 4; ++c) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { sh.chan[c][l][t] = 0.0f; } }
+	pdl_launch_dependents();
+	pdl_wait();
+
 	const int tile = A.tileOrder ? static_cast<int>(__ldg(A.tileOrder + blockIdx.x)) : static_cast<int>(blockIdx.x);   // longest lists first
 	const int tileX = tile % A.fp.tilesX, tileY = tile / A.fp.tilesX;
 	const int ox = tileX * kTile, oy = tileY * kTile;
-	const int warp = t >> 5, lane = t & 31;
-	const int lx = (warp & 1) * 16 + (lane & 7) * 2, ly = (warp >> 1) * 8 + (lane >> 3) * 2;
 	const int px = ox + lx, py = oy + ly;
 	const bool onScreen = (px < A.fp.width) && (py < A.fp.height);
 
@@ -797,9 +832,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		uint32_t off = __ldg(A.tileBase + tile + (g == G ? 1 : 0));
 		if (g > 0 && g < G) { off += __ldg(A.cellRel + static_cast<size_t>(tile) * G + g); }
 		sh.cellOff[g] = min(off, A.fp.listCapacity); }
-	if (t < kMaxGroups) { sh.lgPerGroup[t] = 0; }
-	if (t < 104) { sh.srgbTab[t] = kSrgbTab4[t]; }
-	if (t == 0) { sh.lgCount = 0; }
+	if (t < A.fp.ncmds) { asm volatile("prefetch.global.L1 [%0];" :: "l"(A.cmds + t)); }
 	__syncthreads();
 	// queued large items (kernels.cuh) that cover this tile: a short scan instead of one list entry per tile
 	const unsigned nLarge = min(A.ctr->nLarge, A.fp.largeCapacity);
@@ -816,18 +849,9 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		__syncthreads();
 		if (t == 0) { atomicOr(&A.ctr->overflow, 8u); sh.lgCount = kTileLargeCap; }
 		__syncthreads(); }
-	const uint32_t listLen = (sh.cellOff[G] - sh.cellOff[0]) + static_cast<uint32_t>(sh.lgCount);
 	ListCursor lc{0, 0u, 0, 0, 0u, 1u};
 	int chunkN = 0, chunkPos = 0;
-	if (listLen) {
-#pragma unroll
-		for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = __ldg(A.luts->rcp + k * kTileThreads + t); } }
 	unsigned frags = 0;
-
-#pragma unroll
-	for (int c = 0; c < 4; ++c) {
-#pragma unroll
-		for (int l = 0; l < 4; ++l) { sh.chan[c][l][t] = 0.0f; } }
 
 	// Frame walk.  A.cmds holds the non-draw commands (clear / stores) in submission order, each
 	// tagged with the number of draws recorded before it; draws are discovered from the tile's own
@@ -838,14 +862,22 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	int ci = 0;
 	while (true) {
 		if (chunkPos == chunkN && lc.g < G) {
-			chunkN = load_chunk(sh, A.lists, G, A.fp.totalKeys, lc, A.ctr);
+			chunkN = load_chunk(sh, A, A.lists, G, A.fp.totalKeys, lc, A.ctr);
 			chunkPos = 0; }
-		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
-		uint32_t key0 = 0;
-		if (chunkPos < chunkN) {
-			const uint3 o = entry_owner(A, sh.sorted[chunkPos]);
-			di = static_cast<int>(o.x);
-			key0 = o.y; }
+		// every thread fetches the record of "its" entry of the next (up to) 256: one trip to memory serves
+		// both the question "which draw / program does the batch start with" and the triangle setup
+		const int avail = min(kBatch, chunkN - chunkPos);
+		uint32_t myId = 0;
+		EntryRec myRec;
+		myRec.q3 = make_uint4(0u, 0u, 0u, 0u); myRec.q4 = make_uint4(0u, 0u, 0u, 0u);
+		if (t < avail) {
+			myId = sh.sorted[chunkPos + t];
+			myRec = load_entry(A, myId); }
+		__syncthreads();   // previous batch fully rasterised: its records, sh.headDraw / headKey / firstBad may be overwritten
+		if (t == 0) { sh.headDraw = avail ? static_cast<int>(myRec.q3.w) : A.fp.ndraws; sh.headKey = myRec.q4.x; sh.firstBad = avail; }
+		__syncthreads();
+		const int di = sh.headDraw;   // draw owning the next list entry (ndraws = none left)
+		const uint32_t key0 = sh.headKey;
 		// non-draw commands that precede that draw
 		while (ci < A.fp.ncmds && A.cmds[ci].beforeDraw <= di) {
 			const FrameCmd cmd = A.cmds[ci];
@@ -932,23 +964,15 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		if (di >= A.fp.ndraws) { break; }
 
 		const int bound = (ci < A.fp.ncmds) ? A.cmds[ci].beforeDraw : 0x7fffffff;   // draws >= bound come after cmds[ci]
-		const int avail = min(kBatch, chunkN - chunkPos);
-		__syncthreads();   // previous batch fully rasterised before its records are overwritten
-		if (t == 0) { sh.firstBad = avail; }
-		__syncthreads();
-		uint32_t myId = 0;
-		uint32_t myState = 0;
-		if (t < avail) {
-			myId = sh.sorted[chunkPos + t];
-			const uint3 o = entry_owner(A, myId);
-			myState = o.z;
-			if (static_cast<int>(o.x) >= bound || o.y != key0) { atomicMin(&sh.firstBad, t); } }
+		if (t < avail && (static_cast<int>(myRec.q3.w) >= bound || myRec.q4.x != key0)) { atomicMin(&sh.firstBad, t); }
 		__syncthreads();
 		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
+		// start the trip for the records of the batch after this one while this one is rasterised
+		if (chunkPos + nb + t < chunkN) { prefetch_entry(A, sh.sorted[chunkPos + nb + t]); }
 		bool tiny = false;
 		if (t < nb) {
-			sh.state[t] = static_cast<uint16_t>(myState);
-			setup_triangle(sh, t, myId, A, ox, oy, rl, rt, rr, rb);
+			sh.state[t] = static_cast<uint16_t>(myRec.q4.y);
+			setup_triangle(sh, t, myId, myRec, A, ox, oy, rl, rt, rr, rb);
 			const uint32_t bb = sh.bbox[t];
 			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
 		// (this barrier also publishes the setup records)
