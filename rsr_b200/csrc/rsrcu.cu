@@ -900,6 +900,12 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], st)); }
 
 	TileArgs ta{};
+	for (int i = 0; i < kInlineCmds && i < fp.ncmds; ++i) {
+		ta.icmd[i] = c->cmds[i];
+		const DevState& ds = c->states[c->cmds[i].state].ds;
+		CmdState& cs = ta.icmdState[i];
+		std::memcpy(cs.clearColor, ds.clearColor, sizeof(cs.clearColor));
+		cs.clearDepth = ds.clearDepth; cs.programId = ds.programId; cs.uniform0 = ds.uniforms[0]; cs.color0Type = ds.color0Type; }
 	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
 	ta.ptvb = static_cast<const float4*>(c->ptvb.ptr);
 	ta.triRecs = static_cast<const TriRec*>(c->triRecs.ptr);
@@ -1047,6 +1053,15 @@ int rsrcu_get_stats(rsrcu_ctx* c, RsrStats* out) {
 	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	*out = c->stats;
 	return RSRCU_OK; }
+
+#ifdef RSR_PHASE_PROF
+/* developer builds only (rsr_b200.build.build_variant("phase", ["RSR_PHASE_PROF"])): accumulated clock64 cycles per tile-kernel phase; clears them */
+int rsrcu_debug_phase_cycles(unsigned long long* out16) {
+	if (cudaMemcpyFromSymbol(out16, g_phaseCycles, sizeof(unsigned long long) * 16) != cudaSuccess) { return RSRCU_ERR_CUDA; }
+	unsigned long long zero[16] = {};
+	cudaMemcpyToSymbol(g_phaseCycles, zero, sizeof(zero));
+	return RSRCU_OK; }
+#endif
 
 int rsrcu_set_profiling(rsrcu_ctx* c, int enabled) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }

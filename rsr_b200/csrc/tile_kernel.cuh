@@ -36,6 +36,16 @@ __constant__ uint32_t kSrgbTab4[104] = {
 	0x5e0c0a23, 0x631c0980, 0x67db08f6, 0x6c55087f, 0x70940818, 0x74a007bd, 0x787d076c, 0x7c330723,
 };
 
+// RSR_PHASE_PROF (developer build, tools/phase_probe.py): cycles thread 0 of every CTA spends per phase of the tile kernel
+#ifdef RSR_PHASE_PROF
+__device__ unsigned long long g_phaseCycles[16];
+#define PHASE_BEGIN() long long phaseLast = clock64(); int phaseCur = 0
+#define PHASE(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phaseCycles[phaseCur], static_cast<unsigned long long>(now_ - phaseLast)); phaseLast = now_; phaseCur = (k); } } while (0)
+#else
+#define PHASE_BEGIN() do {} while (0)
+#define PHASE(k) do {} while (0)
+#endif
+
 constexpr int kSortCap = 1024;           // most list entries sorted in one round
 #ifndef RSR_RUN_CAP
 #define RSR_RUN_CAP 1024
@@ -70,8 +80,17 @@ struct TileShared {
 };
 static_assert(offsetof(TileShared, ec) % 8 == 0 && sizeof(int) * 9 * kBatch >= 8 * kSortCap, "sort scratch aliases ec/edx/edy");
 
+constexpr int kInlineCmds = 6;
+
+// what the clear / store commands read from their state snapshot
+struct CmdState { float clearColor[4]; float clearDepth; int programId; float uniform0; int color0Type; };
+
 struct TileArgs {
 	FrameParams fp;
+	// the first non-draw commands of the frame (usually all of them: a clear and a store or two) and the
+	// state words they use travel as kernel parameters: no trips to memory for them in any tile CTA
+	FrameCmd icmd[kInlineCmds];
+	CmdState icmdState[kInlineCmds];
 	const FrameCmd* cmds;
 	const DevDraw* draws;
 	const DevState* states;
@@ -89,6 +108,9 @@ struct TileArgs {
 __device__ __forceinline__ void prefetch_entry(const TileArgs& A, uint32_t id) {
 	const void* p = (id & kFanIdBit) ? static_cast<const void*>(A.clipRecs + ((id & ~kFanIdBit) >> 3)) : static_cast<const void*>(A.triRecs + id);
 	asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+__device__ __forceinline__ int cmd_before_draw(const TileArgs& A, int ci) {
+	return (ci < kInlineCmds) ? A.icmd[ci].beforeDraw : A.cmds[ci].beforeDraw; }
 
 __device__ __forceinline__ bool top_left(int dy, int dx) { return (dy > 0) || (dy == 0 && dx > 0); }
 
@@ -800,6 +822,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	const int lx = (warp & 1) * 16 + (lane & 7) * 2, ly = (warp >> 1) * 8 + (lane >> 3) * 2;
+	PHASE_BEGIN();
 
 	// Everything up to the grid dependency wait touches only data that no kernel of the frame writes (the
 	// approximation tables, constants): with programmatic dependent launch this prologue runs while the
@@ -815,6 +838,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		for (int l = 0; l < 4; ++l) { sh.chan[c][l][t] = 0.0f; } }
 	pdl_launch_dependents();
 	pdl_wait();
+	PHASE(1);
 
 	const int tile = A.tileOrder ? static_cast<int>(__ldg(A.tileOrder + blockIdx.x)) : static_cast<int>(blockIdx.x);   // longest lists first
 	const int tileX = tile % A.fp.tilesX, tileY = tile / A.fp.tilesX;
@@ -832,10 +856,9 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		uint32_t off = __ldg(A.tileBase + tile + (g == G ? 1 : 0));
 		if (g > 0 && g < G) { off += __ldg(A.cellRel + static_cast<size_t>(tile) * G + g); }
 		sh.cellOff[g] = min(off, A.fp.listCapacity); }
-	if (t < A.fp.ncmds) { asm volatile("prefetch.global.L1 [%0];" :: "l"(A.cmds + t)); }
+	const unsigned nLarge = min(__ldcg(&A.ctr->nLarge), A.fp.largeCapacity);   // (issued with the offset loads: one trip for both)
 	__syncthreads();
 	// queued large items (kernels.cuh) that cover this tile: a short scan instead of one list entry per tile
-	const unsigned nLarge = min(A.ctr->nLarge, A.fp.largeCapacity);
 	for (unsigned i = t; i < nLarge; i += kTileThreads) {
 		const LargeItem it = A.large[i];
 		const int tx0 = it.packed & 63, ty0 = (it.packed >> 6) & 63, tx1 = (it.packed >> 12) & 63, ty1 = (it.packed >> 18) & 63;
@@ -862,8 +885,10 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	int ci = 0;
 	while (true) {
 		if (chunkPos == chunkN && lc.g < G) {
+			PHASE(2);
 			chunkN = load_chunk(sh, A, A.lists, G, A.fp.totalKeys, lc, A.ctr);
 			chunkPos = 0; }
+		PHASE(3);
 		// every thread fetches the record of "its" entry of the next (up to) 256: one trip to memory serves
 		// both the question "which draw / program does the batch start with" and the triangle setup
 		const int avail = min(kBatch, chunkN - chunkPos);
@@ -874,15 +899,23 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 			myId = sh.sorted[chunkPos + t];
 			myRec = load_entry(A, myId); }
 		__syncthreads();   // previous batch fully rasterised: its records, sh.headDraw / headKey / firstBad may be overwritten
+		PHASE(4);
 		if (t == 0) { sh.headDraw = avail ? static_cast<int>(myRec.q3.w) : A.fp.ndraws; sh.headKey = myRec.q4.x; sh.firstBad = avail; }
 		__syncthreads();
 		const int di = sh.headDraw;   // draw owning the next list entry (ndraws = none left)
 		const uint32_t key0 = sh.headKey;
+		PHASE(5);
 		// non-draw commands that precede that draw
-		while (ci < A.fp.ncmds && A.cmds[ci].beforeDraw <= di) {
-			const FrameCmd cmd = A.cmds[ci];
+		while (ci < A.fp.ncmds && cmd_before_draw(A, ci) <= di) {
+			FrameCmd cmd;
+			CmdState s;
+			if (ci < kInlineCmds) { cmd = A.icmd[ci]; s = A.icmdState[ci]; }
+			else {
+				cmd = A.cmds[ci];
+				const DevState& gs = A.states[cmd.state];
+				s.clearColor[0] = gs.clearColor[0]; s.clearColor[1] = gs.clearColor[1]; s.clearColor[2] = gs.clearColor[2]; s.clearColor[3] = gs.clearColor[3];
+				s.clearDepth = gs.clearDepth; s.programId = gs.programId; s.uniform0 = gs.uniforms[0]; s.color0Type = gs.color0Type; }
 			++ci;
-			const DevState& s = A.states[cmd.state];
 			switch (cmd.type) {
 			case kCmdClear: {
 				// GPU::DrawImpl CMD_CLEAR (rglv_gpu.cxx:311-344)
@@ -900,7 +933,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 					for (int l = 0; l < 4; ++l) {
 						float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
 						if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
-							const float ex = s.uniforms[0];
+							const float ex = s.uniform0;
 							r = r * ex; g = g * ex; b = b * ex; }
 						else if (s.programId == 3) {
 							// FilterTile's running fragment coordinate (rglr_algorithm.hxx:75-96): starts at the
@@ -962,8 +995,9 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 				break;
 			default: break; } }
 		if (di >= A.fp.ndraws) { break; }
+		PHASE(6);
 
-		const int bound = (ci < A.fp.ncmds) ? A.cmds[ci].beforeDraw : 0x7fffffff;   // draws >= bound come after cmds[ci]
+		const int bound = (ci < A.fp.ncmds) ? cmd_before_draw(A, ci) : 0x7fffffff;   // draws >= bound come after cmds[ci]
 		if (t < avail && (static_cast<int>(myRec.q3.w) >= bound || myRec.q4.x != key0)) { atomicMin(&sh.firstBad, t); }
 		__syncthreads();
 		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
@@ -977,6 +1011,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
 		// (this barrier also publishes the setup records)
 		const int ntiny = __syncthreads_count(tiny);
+		PHASE(7);
 #ifndef RSR_QUEUE_MIN_NB
 #define RSR_QUEUE_MIN_NB 96
 #endif
@@ -994,7 +1029,9 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, key0, nb, ox, oy, queued); break;
 		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, key0, nb, ox, oy, queued); break;
 		default: break; }
+		PHASE(8);
 		chunkPos += max(nb, 1); }
+	PHASE(9);
 
 	// fragment statistics: one atomic per CTA
 	for (int o = 16; o > 0; o >>= 1) { frags += __shfl_down_sync(0xffffffffu, frags, o); }
@@ -1003,6 +1040,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	__syncthreads();
 	if (lane == 0 && frags) { atomicAdd(&sh.sortCount, static_cast<int>(frags)); }
 	__syncthreads();
-	if (t == 0 && sh.sortCount) { atomicAdd(&A.ctr->fragments, static_cast<unsigned long long>(sh.sortCount)); } }
+	if (t == 0 && sh.sortCount) { atomicAdd(&A.ctr->fragments, static_cast<unsigned long long>(sh.sortCount)); }
+	PHASE(10); }
 
 }  // namespace rsr
