@@ -187,6 +187,14 @@ int rsrcu_end_frame(rsrcu_ctx* ctx);
 /* Waits for the frame; reports device-side errors (clip buffer overflow...) */
 int rsrcu_sync(rsrcu_ctx* ctx);
 
+/* Frame overlap (off by default).  When on, the front end of a frame (upload, vertex, setup, binning: latency-bound
+ * kernels that leave most of the GPU idle) runs on a second, high-priority stream into its own set of intermediate
+ * buffers, and only the tile kernel runs on the context's stream: the front end of frame N+1 executes while the tile
+ * kernel of frame N is still rasterising -- the counterpart of the reference binning frame N+1 on the main thread
+ * while the tile jobs of frame N run (doubleBuffer, rglv_gpu.cxx:16,111-112).  Frames still complete in order on
+ * the stream of rsrcu_stream(); work enqueued there by the caller is ordered against the tile kernels only. */
+int rsrcu_set_overlap(rsrcu_ctx* ctx, int enabled);
+
 /* Frames are pipelined (upload arena double-buffered; store targets, counters and their device->host
  * copies in a ring of three; copies run on a second stream): rsrcu_sync_frame(ctx, lag) waits only
  * until the frame `lag` submissions before the most recent one (lag 0 = the latest, at most 2) has

@@ -116,6 +116,7 @@ def load_library():
         "rsrcu_store_color_fp": [vp, vp, ci, ci, ci, ci],
         "rsrcu_store_color_quads": [vp, vp, ci, ci, ci],
         "rsrcu_enable_peer_access": [vp, ci],
+        "rsrcu_set_overlap": [vp, ci],
         "rsrcu_store_depth": [vp, vp],
         "rsrcu_end_frame": [vp],
         "rsrcu_sync": [vp],
@@ -141,7 +142,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
     "rsrcu_release_static", "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
-    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
@@ -476,6 +477,10 @@ class GPU:
             self._check(self.L.rsrcu_store_color_tc_device(self.h, int(bool(gamma)), C.c_void_p(device_ptr), w, h, stride_px))
         else:
             self._emit(OP_STORE_TC_DEV, struct.pack("<iiiiQ", int(bool(gamma)), w, h, stride_px, int(device_ptr)))
+
+    def set_overlap(self, enabled: bool):
+        """front end of frame N+1 (second stream, own intermediate buffers) under the tile kernel of frame N"""
+        self._check(self.L.rsrcu_set_overlap(self.h, int(bool(enabled))))
 
     def EnablePeerAccess(self, peer_device: int):
         """lets StoreColorDevice target memory of another GPU of the node (split-frame presentation over NVLink)"""

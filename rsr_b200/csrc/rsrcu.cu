@@ -166,7 +166,13 @@ struct rsrcu_ctx {
 	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr});
 
 	// device work buffers
-	DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems;
+	// the frame's intermediate buffers; two sets so that, in overlap mode, the front end (K0-K5) of frame N+1 can fill one
+	// set while the tile kernel of frame N still reads the other
+	struct WorkSet { DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems; } sets[2];
+	cudaStream_t frontStream{nullptr};   // overlap mode: K0-K5 run here (high priority), the tile kernel on `stream`
+	cudaEvent_t evFrontDone[2]{}, evTileDone[2]{};
+	bool overlap{false};
+	uint64_t frameNo{0};
 	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
 	DevBuf tcOut[kSlots], fpOut[kSlots], halfOut[kSlots], quadsOut[kSlots], depthOut[kSlots];
 	uint32_t clipCapacity{1u << 16};
@@ -405,7 +411,10 @@ int flushDeferredCopies(rsrcu_ctx* c) {
 	const int tf = c->trace ? c->traceFrameOfSlot[slot] : -1;
 	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 2], c->copyStream)); }
 	for (const PendingCopy& pc : c->deferredCopies) {
-		CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); }
+		if (pc.hostPitch == pc.rowBytes && pc.devPitch == pc.rowBytes) {   // contiguous on both sides: one linear copy (a 2-D copy pays per row)
+			CU(cudaMemcpyAsync(pc.hostDst, pc.devSrc, pc.rowBytes * pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); }
+		else {
+			CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); } }
 	CU(cudaMemcpyAsync(c->hostCounters + slot, c->counters[slot].ptr, sizeof(Counters), cudaMemcpyDeviceToHost, c->copyStream));
 	CU(cudaEventRecord(c->evCopied[slot], c->copyStream));
 	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 3], c->copyStream)); }
@@ -429,6 +438,12 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	c->device = device;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	{
+		int lo = 0, hi = 0;
+		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CU(cudaStreamCreateWithPriority(&c->frontStream, cudaStreamNonBlocking, hi)); }
+	for (auto& ev : c->evFrontDone) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
+	for (auto& ev : c->evTileDone) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evRendered) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evCopied) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evStage) { CU(cudaEventCreate(&ev)); }
@@ -462,6 +477,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	if (!c) { return RSRCU_OK; }
 	cudaSetDevice(c->device);
 	flushDeferredCopies(c);
+	cudaStreamSynchronize(c->frontStream);
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
 	if (c->trace) {
@@ -471,7 +487,9 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 			std::fprintf(stderr, "rsrcu trace frame %2d: kernels %8.1f .. %8.1f us   read-back %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f); }
 		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
-	for (DevBuf* b : { &c->ptvb, &c->vflags, &c->triInfo, &c->triRecs, &c->clipRecs, &c->tileBase, &c->cellRel, &c->tileTotal, &c->tileOrder, &c->lists, &c->largeItems, &c->counters[0], &c->counters[1], &c->counters[2], &c->tcOut[0], &c->tcOut[1], &c->tcOut[2], &c->fpOut[0], &c->fpOut[1], &c->fpOut[2], &c->halfOut[0], &c->halfOut[1], &c->halfOut[2], &c->quadsOut[0], &c->quadsOut[1], &c->quadsOut[2],
+	for (auto& w : c->sets) {
+		for (DevBuf* b : { &w.ptvb, &w.vflags, &w.triInfo, &w.triRecs, &w.clipRecs, &w.tileBase, &w.cellRel, &w.tileTotal, &w.tileOrder, &w.lists, &w.largeItems }) { b->release(); } }
+	for (DevBuf* b : { &c->counters[0], &c->counters[1], &c->counters[2], &c->tcOut[0], &c->tcOut[1], &c->tcOut[2], &c->fpOut[0], &c->fpOut[1], &c->fpOut[2], &c->halfOut[0], &c->halfOut[1], &c->halfOut[2], &c->quadsOut[0], &c->quadsOut[1], &c->quadsOut[2],
 	                   &c->depthOut[0], &c->depthOut[1], &c->depthOut[2] }) { b->release(); }
 	c->arenas[0].release(); c->arenas[1].release();
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
@@ -480,7 +498,10 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	for (auto& ev : c->evStage) { cudaEventDestroy(ev); }
 	for (auto& ev : c->evRendered) { cudaEventDestroy(ev); }
 	for (auto& ev : c->evCopied) { cudaEventDestroy(ev); }
+	for (auto& ev : c->evFrontDone) { cudaEventDestroy(ev); }
+	for (auto& ev : c->evTileDone) { cudaEventDestroy(ev); }
 	cudaStreamDestroy(c->copyStream);
+	cudaStreamDestroy(c->frontStream);
 	cudaStreamDestroy(c->stream);
 	delete c;
 	return RSRCU_OK; }
@@ -488,6 +509,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 int rsrcu_set_host_luts(rsrcu_ctx* c, const uint32_t* rcp2048, const uint32_t* rsqrt2x1024) {
 	if (!c || !rcp2048 || !rsqrt2x1024) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
 	std::memcpy(c->hostLuts.rcp, rcp2048, sizeof(c->hostLuts.rcp));
 	std::memcpy(c->hostLuts.rsqrt, rsqrt2x1024, sizeof(c->hostLuts.rsqrt));
@@ -503,6 +525,7 @@ int rsrcu_get_host_luts(rsrcu_ctx* c, uint32_t* rcp2048, uint32_t* rsqrt2x1024) 
 int rsrcu_release_static(rsrcu_ctx* c) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	c->staticCache.clear();
@@ -745,7 +768,13 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	c->inFrame = false;
 	const auto tSubmit = std::chrono::steady_clock::now();
 	c->recordNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(tSubmit - c->tBegin).count());
-	cudaStream_t st = c->stream;
+	// overlap mode: the front end of this frame runs on its own high-priority stream into work set (frame & 1) and only
+	// the tile kernel on the context's stream, so K0-K5 of frame N+1 fill the SMs the tile kernel of frame N leaves idle
+	const int si = c->overlap ? static_cast<int>(c->frameNo & 1) : 0;
+	++c->frameNo;
+	rsrcu_ctx::WorkSet& w = c->sets[si];
+	cudaStream_t st = c->overlap ? c->frontStream : c->stream;
+	cudaStream_t tileStream = c->stream;
 	c->launches = 0;
 
 	const int W = c->width, H = c->height;
@@ -832,21 +861,21 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
 
 	// ---- device buffers -------------------------------------------------------------------
-	CU(c->ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
-	CU(c->vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
-	CU(c->triInfo.reserve(std::max<uint64_t>(1, pjobs) * sizeof(uint2)));
-	CU(c->triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
-	CU(c->clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
+	CU(w.ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
+	CU(w.vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
+	CU(w.triInfo.reserve(std::max<uint64_t>(1, pjobs) * sizeof(uint2)));
+	CU(w.triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
+	CU(w.clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
 	const size_t ncells = static_cast<size_t>(ntiles) * fp.groups;
 	const size_t ctrlBytes = 64 + ncells * 8;   // Counters | cellCount[] | cellCursor[]
 	static_assert(sizeof(Counters) <= 64, "control block layout");
 	CU(c->counters[c->outSlot].reserve(ctrlBytes));
-	CU(c->tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
-	CU(c->cellRel.reserve(ncells * 4));
-	CU(c->tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
-	CU(c->tileOrder.reserve(static_cast<size_t>(ntiles) * 4));
-	CU(c->lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
-	CU(c->largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
+	CU(w.tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
+	CU(w.cellRel.reserve(ncells * 4));
+	CU(w.tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(w.tileOrder.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(w.lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
+	CU(w.largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
 
 	const uint8_t* ab = static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr);
 	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
@@ -856,11 +885,12 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	BinArgs bin{};
 	bin.cellCount = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->counters[c->outSlot].ptr) + 64);
 	bin.cellCursor = bin.cellCount + ncells;
-	bin.tileBase = static_cast<const uint32_t*>(c->tileBase.ptr);
-	bin.cellRel = static_cast<const uint32_t*>(c->cellRel.ptr);
-	bin.lists = static_cast<uint2*>(c->lists.ptr);
-	bin.large = static_cast<LargeItem*>(c->largeItems.ptr);
+	bin.tileBase = static_cast<const uint32_t*>(w.tileBase.ptr);
+	bin.cellRel = static_cast<const uint32_t*>(w.cellRel.ptr);
+	bin.lists = static_cast<uint2*>(w.lists.ptr);
+	bin.large = static_cast<LargeItem*>(w.largeItems.ptr);
 
+	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
 	{
@@ -878,26 +908,29 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 
 	if (fp.totalVJobs) {
 		CU(launchPdl(vertex_kernel, (fp.totalVJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
-			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(c->ptvb.ptr), static_cast<uint8_t*>(c->vflags.ptr)));
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(w.ptvb.ptr), static_cast<uint8_t*>(w.vflags.ptr)));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
 	if (fp.totalPJobs) {
 		CU(launchPdl(setup_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp,
-			static_cast<const ApproxLuts*>(c->devLuts), static_cast<const float4*>(c->ptvb.ptr), static_cast<const uint8_t*>(c->vflags.ptr),
-			static_cast<uint2*>(c->triInfo.ptr), static_cast<TriRec*>(c->triRecs.ptr), static_cast<ClipRec*>(c->clipRecs.ptr),
-			bin, static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr));
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<const float4*>(w.ptvb.ptr), static_cast<const uint8_t*>(w.vflags.ptr),
+			static_cast<uint2*>(w.triInfo.ptr), static_cast<TriRec*>(w.triRecs.ptr), static_cast<ClipRec*>(w.clipRecs.ptr),
+			bin, static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
 	if (fp.totalPJobs && fp.groups > 1) {
-		CU(launchPdl(cell_scan_kernel, static_cast<unsigned>((ntiles + 7) / 8), 256u, 0, st, fp, static_cast<const uint32_t*>(bin.cellCount), static_cast<uint32_t*>(c->cellRel.ptr),
-			static_cast<uint32_t*>(c->tileTotal.ptr), static_cast<uint32_t*>(c->tileBase.ptr), static_cast<uint32_t*>(c->tileOrder.ptr), dCtr));
+		CU(launchPdl(cell_scan_kernel, static_cast<unsigned>((ntiles + 7) / 8), 256u, 0, st, fp, static_cast<const uint32_t*>(bin.cellCount), static_cast<uint32_t*>(w.cellRel.ptr),
+			static_cast<uint32_t*>(w.tileTotal.ptr), static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
 	if (fp.totalPJobs) {
-		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(c->triInfo.ptr),
-			static_cast<const ClipRec*>(c->clipRecs.ptr), bin, dCtr));
+		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(w.triInfo.ptr),
+			static_cast<const ClipRec*>(w.clipRecs.ptr), bin, dCtr));
 		++c->launches; }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], st)); }
+	if (c->overlap) {
+		CU(cudaEventRecord(c->evFrontDone[si], st));
+		CU(cudaStreamWaitEvent(tileStream, c->evFrontDone[si], 0)); }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], tileStream)); }
 
 	TileArgs ta{};
 	for (int i = 0; i < kInlineCmds && i < fp.ncmds; ++i) {
@@ -907,24 +940,25 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		std::memcpy(cs.clearColor, ds.clearColor, sizeof(cs.clearColor));
 		cs.clearDepth = ds.clearDepth; cs.programId = ds.programId; cs.uniform0 = ds.uniforms[0]; cs.color0Type = ds.color0Type; }
 	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
-	ta.ptvb = static_cast<const float4*>(c->ptvb.ptr);
-	ta.triRecs = static_cast<const TriRec*>(c->triRecs.ptr);
-	ta.clipRecs = static_cast<const ClipRec*>(c->clipRecs.ptr);
-	ta.lists = static_cast<const uint2*>(c->lists.ptr);
+	ta.ptvb = static_cast<const float4*>(w.ptvb.ptr);
+	ta.triRecs = static_cast<const TriRec*>(w.triRecs.ptr);
+	ta.clipRecs = static_cast<const ClipRec*>(w.clipRecs.ptr);
+	ta.lists = static_cast<const uint2*>(w.lists.ptr);
 	ta.tileBase = bin.tileBase;
 	ta.cellRel = bin.cellRel;
 	ta.large = bin.large;
-	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(c->tileOrder.ptr) : nullptr;
+	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
 	ta.ctr = dCtr;
-	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), st, ta));
+	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
 	++c->launches;
 	CU(cudaGetLastError());
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], st)); }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], tileStream)); }
+	if (c->overlap) { CU(cudaEventRecord(c->evTileDone[si], tileStream)); }
 
 	c->lastH2D = c->arenas[c->cur].used;
 	c->lastD2H = 0;
-	CU(cudaEventRecord(c->evRendered[c->outSlot], st));
-	if (traceIdx >= 0) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 1], st)); }
+	CU(cudaEventRecord(c->evRendered[c->outSlot], tileStream));
+	if (traceIdx >= 0) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 1], tileStream)); }
 	for (const PendingCopy& pc : c->copies) { c->lastD2H += pc.rowBytes * pc.rows; }
 	c->deferredCopies = c->copies;
 	c->deferredSlot = c->outSlot;
@@ -939,6 +973,7 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	CU(cudaSetDevice(c->device));
 	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
+	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaStreamSynchronize(c->copyStream));
 	if (!c->framePending) { return RSRCU_OK; }
@@ -1062,6 +1097,15 @@ int rsrcu_debug_phase_cycles(unsigned long long* out16) {
 	cudaMemcpyToSymbol(g_phaseCycles, zero, sizeof(zero));
 	return RSRCU_OK; }
 #endif
+
+int rsrcu_set_overlap(rsrcu_ctx* c, int enabled) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_set_overlap inside begin/end frame"); }
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->frontStream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->overlap = enabled != 0;
+	return RSRCU_OK; }
 
 int rsrcu_set_profiling(rsrcu_ctx* c, int enabled) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }

@@ -148,6 +148,47 @@ def test_two_deep_frame_pipelining(cuda_gpu):
     assert not np.array_equal(want[0], want[4])
 
 
+def test_frame_overlap_mode_front_end_under_previous_tile_kernel():
+    """rsrcu_set_overlap: K0-K5 of frame N+1 run on a second stream into the other work set while the tile kernel
+    of frame N rasterises; alternating heavy / light / differently sized frames must still land bit-identical to the
+    same frames rendered one at a time"""
+    g = R.GPU(0)
+    try:
+        heavy = scenes.BundledLikeScene(cubes=400)
+        light = scenes.WavyGridScene(n=12)
+        cubes = scenes.CubesScene(instances=200)
+        plan = [(heavy, (1920, 1080)), (light, (640, 360)), (cubes, (1920, 1080)), (light, (1920, 1080)), (heavy, (640, 360)),
+                (cubes, (640, 360)), (heavy, (1920, 1080)), (light, (640, 360)), (cubes, (1920, 1080)), (heavy, (1920, 1080))]
+        want = []
+        for i, (sc, size) in enumerate(plan):
+            out = np.zeros((size[1], size[0]), np.uint32)
+            sc.record(g, size, out, t=0.25 * i)
+            g.Run()
+            want.append(out)
+        g.set_overlap(True)
+        for rounds in range(2):
+            bufs = [np.zeros_like(w) for w in want]
+            recs = []
+            for i, (sc, size) in enumerate(plan):
+                sc.record(g, size, bufs[i], t=0.25 * i)
+                recs.append(g.Finish())
+            for i, rec in enumerate(recs):
+                g.Submit(rec, sync=False)
+                if i > 1:
+                    g.SyncFrame(2)
+                    assert np.array_equal(bufs[i - 2], want[i - 2]), f"frame {i - 2} differs in overlap mode"
+            g.Sync()
+            for i, (a, b) in enumerate(zip(bufs, want)):
+                assert np.array_equal(a, b), f"frame {i} differs in overlap mode"
+        g.set_overlap(False)
+        out = np.zeros_like(want[0])
+        plan[0][0].record(g, plan[0][1], out, t=0.0)
+        g.Run()
+        assert np.array_equal(out, want[0])
+    finally:
+        g.close()
+
+
 def test_tile_list_overflow_is_reported_and_recovered(ref_gpu, monkeypatch):
     """more (triangle, tile) pairs than the list buffer holds: the frame reports OVERFLOW, the buffer
     grows, and rendering the same frame again gives the reference's pixels"""
