@@ -52,7 +52,7 @@ struct DevDraw {
 	uint32_t N;             // prims * instances
 	uint32_t vjobBase;      // prefix of instances*nverts
 	uint32_t pjobBase;      // prefix of N
-	uint32_t pad0;
+	uint32_t cullBits;      // bit 0 culling enabled, bits 1-2 cull face (GL_FRONT 1, GL_BACK 2, both 3), bit 3 scissor enabled
 	uint32_t batchKey; };   // program id | pipeline flags << 8: draws with equal keys may share a raster batch
 
 struct ClipVertex {
@@ -120,15 +120,25 @@ struct Counters {
 	unsigned int chunksKeyRange; };  // ... and by key ranges + bitonic sort (mode C)
 
 // Draw that owns a vertex / triangle job.  The host tabulates, per block of 256 jobs, the draw of the
-// block's first job: the search only covers the draws that start inside the block (usually none).
+// block's first job.  A block that lies inside one draw (the usual case) needs no search; a block that
+// spans many small draws (hundreds of two-triangle draws) stages their job bases in shared memory
+// with one coalesced trip and searches there -- a per-thread binary search over global memory is a
+// chain of up to eight dependent misses.  Every thread of the block must call it.
 __device__ __forceinline__ int find_draw(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, uint32_t job,
                                          bool vertexJobs) {
-	int lo = static_cast<int>(__ldg(blockDraw + (job >> 8))), hi = static_cast<int>(__ldg(blockDraw + (job >> 8) + 1));
+	__shared__ uint32_t sBase[260];
+	const int first = static_cast<int>(__ldg(blockDraw + blockIdx.x));
+	const int last = static_cast<int>(__ldg(blockDraw + blockIdx.x + 1));
+	if (last <= first) { return first; }
+	const int n = min(last - first + 1, 258);   // (every draw has at least one job: a block of 256 jobs spans <= 257 draws)
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		sBase[i] = vertexJobs ? __ldg(&draws[first + i].vjobBase) : __ldg(&draws[first + i].pjobBase); }
+	__syncthreads();
+	int lo = 0, hi = n - 1;
 	while (lo < hi) {
 		const int mid = (lo + hi + 1) >> 1;
-		const uint32_t b = vertexJobs ? draws[mid].vjobBase : draws[mid].pjobBase;
-		if (b <= job) { lo = mid; } else { hi = mid - 1; } }
-	return lo; }
+		if (sBase[mid] <= job) { lo = mid; } else { hi = mid - 1; } }
+	return first + lo; }
 
 // Programmatic dependent launch (sm_90+): every kernel of the frame is launched with the "programmatic
 // stream serialization" attribute.  pdl_launch_dependents lets the next kernel's CTAs become resident
@@ -190,8 +200,8 @@ vertex_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ bl
 	pdl_launch_dependents();
 	pdl_wait();
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
+	const int di = find_draw(draws, blockDraw, min(job, fp.totalVJobs - 1u), true);
 	if (job >= fp.totalVJobs) { return; }
-	const int di = find_draw(draws, blockDraw, job, true);
 	const DevDraw& d = draws[di];
 	const DevState& s = states[d.state];
 	const uint32_t local = job - d.vjobBase;
@@ -248,12 +258,12 @@ struct CVert { float c[4]; float vary[kMaxVaryings]; };
 
 // tile range of a device-space triangle; formulas of BinTriangles* (rglv_gpu_impl.hxx:452-465)
 // and ForEachCoveredTile (:796-817)
-__device__ __forceinline__ bool tile_bbox(const DevState& s, int ix0, int iy0, int ix1, int iy1, int ix2, int iy2,
+__device__ __forceinline__ bool tile_bbox(int sx0, int sy0, int sx1, int sy1, int ix0, int iy0, int ix1, int iy1, int ix2, int iy2,
                                           bool needNonEmpty, uint32_t& packed, const FrameParams& fp) {
-	const int vminx = max(min(ix0, min(ix1, ix2)), s.scissorX0);
-	const int vminy = max(min(iy0, min(iy1, iy2)), s.scissorY0);
-	const int vmaxx = min(max(ix0, max(ix1, ix2)) + 1, s.scissorX1 - 1);
-	const int vmaxy = min(max(iy0, max(iy1, iy2)) + 1, s.scissorY1 - 1);
+	const int vminx = max(min(ix0, min(ix1, ix2)), sx0);
+	const int vminy = max(min(iy0, min(iy1, iy2)), sy0);
+	const int vmaxx = min(max(ix0, max(ix1, ix2)) + 1, sx1 - 1);
+	const int vmaxy = min(max(iy0, max(iy1, iy2)) + 1, sy1 - 1);
 	if (needNonEmpty && !((vmaxx > vminx) && (vmaxy > vminy))) { return false; }
 	// C++ integer division truncates toward zero (vmax* may be negative for off-screen fans)
 	int tx0 = vminx / kTile, ty0 = vminy / kTile, tx1 = vmaxx / kTile, ty1 = vmaxy / kTile;
@@ -282,22 +292,30 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 	int na = 3;
 	const float4* recs[3] = { r0, r1, r2 };
 	const int nvary = d.nvary;
+	const int nvary4 = 4 * (d.strideF4 - 2);   // varyings as stored: whole float4s (the pad lanes stay 0)
 	for (int i = 0; i < 3; ++i) {
 		const float4 c = recs[i][1];
 		A[i].c[0] = c.x; A[i].c[1] = c.y; A[i].c[2] = c.z; A[i].c[3] = c.w;
-		for (int k = 0; k < kMaxVaryings; ++k) { A[i].vary[k] = 0.0f; }
 		for (int k = 0; k < d.strideF4 - 2; ++k) {
 			const float4 q = recs[i][2 + k];
 			A[i].vary[4 * k] = q.x; A[i].vary[4 * k + 1] = q.y; A[i].vary[4 * k + 2] = q.z; A[i].vary[4 * k + 3] = q.w; } }
 
 	// Sutherland-Hodgman against Left, Bottom, Near, Right, Top (rglv_gpu_impl.hxx:725-758)
 	for (int plane = 0; plane < 5 && na > 0; ++plane) {
+		// a plane every current vertex is inside of reproduces the polygon unchanged: skip the pass (most
+		// triangles cross one plane; only the first nvary4 varyings are live, the rest are never read)
+		bool allIn = true;
+		for (int i = 0; i < na; ++i) { allIn = allIn && (clip_dist(plane, A[i].c) >= 0.0f); }
+		if (allIn) { continue; }
 		int nb = 0;
 		bool hereIn = clip_dist(plane, A[0].c) >= 0.0f;
 		for (int hi = 0; hi < na; ++hi) {
 			const int ni = (hi + 1) % na;
 			const bool nextIn = clip_dist(plane, A[ni].c) >= 0.0f;
-			if (hereIn) { Bv[nb++] = A[hi]; }
+			if (hereIn) {
+				for (int k = 0; k < 4; ++k) { Bv[nb].c[k] = A[hi].c[k]; }
+				for (int k = 0; k < nvary4; ++k) { Bv[nb].vary[k] = A[hi].vary[k]; }
+				++nb; }
 			if (hereIn != nextIn) {
 				const CVert& from = hereIn ? A[hi] : A[ni];
 				const CVert& to = hereIn ? A[ni] : A[hi];
@@ -306,11 +324,11 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 				const float t = da / (da - db);
 				// mix(a, b, t) = (1 - t)*a + t*b   (rmlv_math.hxx:87-90)
 				const float omt = 1.0f - t;
-				CVert nv;
-				for (int k = 0; k < 4; ++k) { nv.c[k] = omt * from.c[k] + t * to.c[k]; }
-				for (int k = 0; k < kMaxVaryings; ++k) {
-					nv.vary[k] = (k < nvary) ? (omt * from.vary[k] + t * to.vary[k]) : 0.0f; }
-				if (nb < 9) { Bv[nb++] = nv; }
+				if (nb < 9) {
+					for (int k = 0; k < 4; ++k) { Bv[nb].c[k] = omt * from.c[k] + t * to.c[k]; }
+					for (int k = 0; k < nvary4; ++k) {
+						Bv[nb].vary[k] = (k < nvary) ? (omt * from.vary[k] + t * to.vary[k]) : 0.0f; }
+					++nb; }
 				hereIn = !hereIn; } }
 		CVert* tmp = A; A = Bv; Bv = tmp;
 		na = nb; }
@@ -350,7 +368,8 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 		const CVert& src = backfacing ? A[na - 1 - i] : A[i];
 		rec.v[i].dev = make_float4(src.c[0], src.c[1], src.c[2], src.c[3]);
 		for (int k = 0; k < kClipVaryF4; ++k) {
-			rec.v[i].vary[k] = make_float4(src.vary[4 * k], src.vary[4 * k + 1], src.vary[4 * k + 2], src.vary[4 * k + 3]); } }
+			rec.v[i].vary[k] = (4 * k < nvary4) ? make_float4(src.vary[4 * k], src.vary[4 * k + 1], src.vary[4 * k + 2], src.vary[4 * k + 3])
+			                                    : make_float4(0.0f, 0.0f, 0.0f, 0.0f); } }
 	int nbinned = 0;
 	for (int f = 0; f < kMaxFan; ++f) {
 		uint32_t packed = kReject;
@@ -358,7 +377,7 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 			const float4 a = rec.v[0].dev, b = rec.v[f + 1].dev, c = rec.v[f + 2].dev;
 			// ivec2{vec2} is a C cast: truncation, same saturation as cvtt for our purposes
 			uint32_t p;
-			if (tile_bbox(s, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), false, p, fp)) {
+			if (tile_bbox(s.scissorX0, s.scissorY0, s.scissorX1, s.scissorY1, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), false, p, fp)) {
 				packed = p | (backfacing ? kBackface : 0u);
 				++nbinned; } }
 		rec.fan[f] = packed; }
@@ -497,6 +516,18 @@ __device__ __forceinline__ void bin_triangle(uint32_t job, uint2 info, const Fra
 // Called by every thread of every CTA at the end of a kernel: the last CTA to get here scans
 // count[0..n) (n <= 4096) into base[0..n] (threadFenceReduction pattern: every thread's writes and
 // atomics are ordered before its CTA's ticket).
+#ifdef RSR_PHASE_PROF
+__device__ unsigned long long g_k2Times[8];
+__device__ unsigned long long g_k2Block[12];   // globaltimer marks of thread 0 of the middle CTA   // globaltimer ns: [0] first CTA start (min), [1] last CTA's ticket, [2] after scan, [3] after tile order
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define K2_MARK(i) do { if (threadIdx.x == 0) { g_k2Times[i] = gtimer(); } } while (0)
+// per-CTA phase durations of thread 0 (ns), maximum over CTAs: g_k2Block[i] = max(t_i - t_{i-1})
+#define K2B(i) do { if (threadIdx.x == 0) { const unsigned long long now_ = gtimer(); if (i) { atomicMax(&g_k2Block[i], now_ - k2Last); } k2Last = now_; } } while (0)
+#else
+#define K2_MARK(i) do {} while (0)
+#define K2B(i) do {} while (0)
+#endif
+
 __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint32_t* __restrict__ base, uint32_t* __restrict__ order,
                                                      const int n, const uint32_t listCapacity, Counters* __restrict__ ctr) {
 	__shared__ bool lastBlock;
@@ -506,6 +537,7 @@ __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint
 	if (threadIdx.x == 0) { lastBlock = (atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1); }
 	__syncthreads();
 	if (!lastBlock) { return; }
+	K2_MARK(1);
 	__threadfence();
 	uint32_t v[16];   // 256 threads x 16 = 4096 tiles (the largest target is 2048 px = 64 x 64 tiles)
 	uint32_t sum = 0;
@@ -532,6 +564,11 @@ __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint
 		ctr->entries = before;
 		if (before > listCapacity) { atomicOr(&ctr->overflow, 2u); } }
 
+	K2_MARK(2);
+#ifdef RSR_NO_TILE_ORDER
+	for (int q = 0; q < 16; ++q) { const int i = static_cast<int>(threadIdx.x) * 16 + q; if (i < n) { order[i] = static_cast<uint32_t>(i); } }
+	return;
+#endif
 	// CTA -> tile order for the tile kernel: eight classes of list length (>= 2048, 1024, 512, 256, 64,
 	// 16, 1 entries, empty), longest first, tile index order inside a class (neighbouring tiles share
 	// texels and vertex records), so that the heavy tiles start early and the light ones fill the tail
@@ -571,19 +608,30 @@ __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint
 		if (i < n) {
 			const int k = tileClass[i];
 			order[classBase[k] + perThread[k][threadIdx.x]] = static_cast<uint32_t>(i);
-			perThread[k][threadIdx.x] += 1; } } }
+			perThread[k][threadIdx.x] += 1; } }
+	K2_MARK(3); }
 
-__global__ void __launch_bounds__(256)
+#ifndef RSR_SETUP_CTAS
+#define RSR_SETUP_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, RSR_SETUP_CTAS)
 setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
              const ApproxLuts* __restrict__ luts, const float4* __restrict__ ptvb, const uint8_t* __restrict__ vflags,
              uint2* __restrict__ triInfo, TriRec* __restrict__ triRecs, ClipRec* __restrict__ clipRecs,
              BinArgs B, uint32_t* __restrict__ tileBase, uint32_t* __restrict__ tileOrder, Counters* __restrict__ ctr) {
 	pdl_launch_dependents();
 	pdl_wait();
+#ifdef RSR_PHASE_PROF
+	if (threadIdx.x == 0) { atomicMin(&g_k2Times[0], gtimer()); if (blockIdx.x == gridDim.x - 1) { g_k2Times[4] = gtimer(); } }
+#endif
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	uint2 myInfo = make_uint2(kReject, 0u);
+#ifdef RSR_PHASE_PROF
+	unsigned long long k2Last = 0;
+#endif
+	K2B(0);
+	const int di = find_draw(draws, blockDraw, min(job, fp.totalPJobs - 1u), false);
 	if (job < fp.totalPJobs) {
-		const int di = find_draw(draws, blockDraw, job, false);
 		const DevDraw& d = draws[di];
 		const DevState& s = states[d.state];
 		const uint32_t local = job - d.pjobBase;
@@ -596,6 +644,8 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 		else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
 		const uint32_t nverts = static_cast<uint32_t>(d.nverts);
 		uint32_t out = kReject;
+		if (i0 + i1 + i2 == 0xffffffffu) { out = 0; }
+		K2B(1);
 		if (i0 < nverts && i1 < nverts && i2 < nverts) {
 			const uint32_t vb = iid * nverts;
 			const uint32_t cf0 = vflags[d.flagBase + vb + i0];
@@ -617,11 +667,18 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 				const float d21x = b.x - a.x, d21y = b.y - a.y;
 				const float area = d31x * d21y - d31y * d21x;
 				const bool front = area > 0.0f;
-				const bool keepBacks = !(s.cullingEnabled && s.cullFace == 2);
-				const bool keepFronts = !(s.cullingEnabled && s.cullFace == 1);
+				// (cull mode and the scissor switch ride in the draw record: no trip to the state snapshot here)
+				const bool cullingEnabled = (d.cullBits & 1u) != 0;
+				const uint32_t cullFace = (d.cullBits >> 1) & 3u;
+				const bool keepBacks = !(cullingEnabled && cullFace == 2);
+				const bool keepFronts = !(cullingEnabled && cullFace == 1);
 				const bool notCulled = front ? keepFronts : keepBacks;
 				uint32_t packed;
-				if (notCulled && tile_bbox(s, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), true, packed, fp)) {
+				bool binned = false;
+				if (notCulled) {
+					binned = (d.cullBits & 8u) ? tile_bbox(s.scissorX0, s.scissorY0, s.scissorX1, s.scissorY1, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), true, packed, fp)
+					                           : tile_bbox(0, 0, fp.width, fp.height, cvtt(a.x), cvtt(a.y), cvtt(b.x), cvtt(b.y), cvtt(c.x), cvtt(c.y), true, packed, fp); }
+				if (binned) {
 					out = packed | (front ? 0u : kBackface);
 					atomicAdd(&ctr->binned, 1ull);
 					// triangle record for the tile kernel; back faces are drawn with i0 <-> i2 swapped
@@ -641,9 +698,18 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 					uint4* dst = reinterpret_cast<uint4*>(triRecs + job);
 #pragma unroll
 					for (int q = 0; q < 5; ++q) { dst[q] = src[q]; } } } }
+		if (out == 0x12345u) { myInfo.y = 1; }
+		K2B(2);
 		myInfo = make_uint2(out, d.idBase + local);
 		triInfo[job] = myInfo; }
 	bin_triangle<false>(job, myInfo, fp, clipRecs, B, ctr);
+	K2B(3);
+#ifdef RSR_PHASE_PROF
+	__threadfence();
+	K2B(4);
+	__syncthreads();
+	K2B(5);
+#endif
 	if (fp.groups > 1) { return; }   // K3 (cell_scan_kernel) prepares the offsets of multi-cell lists
 	tile_scan_last_block(B.cellCount, tileBase, tileOrder, fp.tilesX * fp.tilesY, fp.listCapacity, ctr); }
 

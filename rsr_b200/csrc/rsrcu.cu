@@ -673,6 +673,7 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	d.strideF4 = 2 + (d.nvary + 3) / 4;
 	d.N = static_cast<uint32_t>(prims) * static_cast<uint32_t>(instances);
 	d.batchKey = static_cast<uint32_t>(programId & 0xff) | (static_cast<uint32_t>(key) << 8);
+	d.cullBits = (hs.ds.cullingEnabled ? 1u : 0u) | ((static_cast<uint32_t>(hs.ds.cullFace) & 3u) << 1) | ((key & 1) ? 8u : 0u);
 	if (!arrays) {
 		if (!indices) { return fail(RSRCU_ERR_INVALID, "null index pointer"); }
 		r = uploadData(c, indices, static_cast<size_t>(prims) * 3 * sizeof(uint16_t), upload, hd.indices);
@@ -1095,6 +1096,14 @@ int rsrcu_debug_phase_cycles(unsigned long long* out16) {
 	if (cudaMemcpyFromSymbol(out16, g_phaseCycles, sizeof(unsigned long long) * 16) != cudaSuccess) { return RSRCU_ERR_CUDA; }
 	unsigned long long zero[16] = {};
 	cudaMemcpyToSymbol(g_phaseCycles, zero, sizeof(zero));
+	return RSRCU_OK; }
+int rsrcu_debug_k2_times(unsigned long long* out8) {
+	if (cudaMemcpyFromSymbol(out8, g_k2Times, sizeof(unsigned long long) * 8) != cudaSuccess) { return RSRCU_ERR_CUDA; }
+	cudaMemcpyFromSymbol(out8 + 8, g_k2Block, sizeof(unsigned long long) * 8);
+	unsigned long long init[8] = { ~0ull, 0, 0, 0, 0, 0, 0, 0 };
+	unsigned long long zero12[12] = {};
+	cudaMemcpyToSymbol(g_k2Block, zero12, sizeof(zero12));
+	cudaMemcpyToSymbol(g_k2Times, init, sizeof(init));
 	return RSRCU_OK; }
 #endif
 

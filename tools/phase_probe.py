@@ -33,4 +33,10 @@ for name in sys.argv[1:] or ["c2"]:
     print(f"{workload}: {tot / n / tiles:.0f} cycles per tile CTA (thread 0)")
     for k, nm in enumerate(NAMES):
         print(f"   {nm:28s} {100 * out[k] / tot:5.1f}%  {out[k] / n / tiles:8.0f} cycles/CTA")
+    k2 = (C.c_ulonglong * 16)()
+    gpu.L.rsrcu_debug_k2_times(k2)
+    gpu.Submit(rec)
+    gpu.L.rsrcu_debug_k2_times(k2)
+    print(f"   setup_kernel: first CTA start -> last CTA's ticket {(k2[1] - k2[0]) / 1e3:.1f} us, scan {(k2[2] - k2[1]) / 1e3:.1f} us, tile order {(k2[3] - k2[2]) / 1e3:.1f} us; last-indexed CTA started {(k2[4] - k2[0]) / 1e3:.1f} us after the first")
+    print('   setup_kernel, slowest CTA per phase (thread 0), us: indices loaded, classified (+clip), counted, fenced, barrier (other warps):', [round(k2[8 + i] / 1e3, 1) for i in range(1, 6)])
     gpu.close()
