@@ -162,7 +162,7 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
     p2p = args.exchange == "p2p"
     gpu.set_overlap(True)            # sub-frames are independent frames: front end of the next one under the current tile kernel
     cur = torch.cuda.current_stream()
-    recs = []
+    recs, retained = [], []
     if p2p:
         pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist)
         gpu.EnablePeerAccess(pf.presenter_device)
@@ -172,6 +172,9 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
             scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf),
                          device_out=(pf.pointer(sf.x0, sf.y0), pf.stride_px))
             recs.append(gpu.Finish())
+            if args.resident == "retained":
+                gpu.Submit(recs[-1])
+                retained.append(gpu.Retain())
     else:
         local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
         for k, sf in enumerate(mine):
@@ -181,8 +184,12 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
         frame = torch.zeros((4320, 7680), dtype=torch.int32, device=dev) if rank == 0 else None
 
     def step():
-        for rec in recs:
-            gpu.Submit(rec, sync=False)
+        if retained:
+            for fr in retained:
+                gpu.Replay(fr)
+        else:
+            for rec in recs:
+                gpu.Submit(rec, sync=False)
         done = torch.cuda.Event()
         with torch.cuda.stream(stream):
             done.record(stream)
@@ -233,6 +240,7 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
                 "dtype": "f32+i32", "data": "synthetic",
                 "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
                            "subframes_per_rank": len(mine), "exchange": exchange,
+                           "submission": "retained sub-frame tables replayed" if retained else "recorded streams decoded and uploaded every frame",
                            "cache": "L2 flushed before every timed frame"},
                 "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks, "frame_checksum": checksum,
                 "gpu_launches": int(st["kernel_launches"]) * len(mine) * args.steps}
@@ -251,6 +259,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
+                    help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5 only: how resolved pixels reach the presenting GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -262,7 +272,8 @@ def main():
     scene, size, workload = make_scene(args.workload)
     W, H = size
     config = {"workload": workload, "triangles_per_frame": scene.triangles, "draws_per_frame": getattr(scene, "draws", None),
-              "width": W, "height": H, "cache": "L2 flushed (256 MiB memset) before every timed frame"}
+              "width": W, "height": H, "cache": "L2 flushed (256 MiB memset) before every timed frame",
+              "resident_leg": "retained frame tables replayed (rsrcu_replay_frame)" if args.resident == "retained" else "recorded stream decoded and uploaded every step (rsrcu_run_stream)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -302,10 +313,19 @@ def main():
         return bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flush, barrier)
 
     scene.record(gpu, size, None, t=0.0, static=True)
-    resident = gpu.Finish()        # the recorded command stream of one frame; replayed every step
+    resident = gpu.Finish()        # the recorded command stream of one frame
+    retained = None
+    if args.resident == "retained":
+        # the frame's state / draw tables stay on the device with its meshes and textures (rsrcu_retain_frame): a step
+        # is every kernel of the frame (K0 zeroes the control block, vertex, setup, binning, tile) and nothing else
+        gpu.Submit(resident)
+        retained = gpu.Retain()
 
     def frame_resident(i):
-        gpu.Submit(resident, sync=False)
+        if retained is not None:
+            gpu.Replay(retained)
+        else:
+            gpu.Submit(resident, sync=False)   # decode the recorded stream, rebuild and upload the tables every step
 
     for i in range(args.warmup):
         frame_resident(i)

@@ -187,6 +187,19 @@ int rsrcu_end_frame(rsrcu_ctx* ctx);
 /* Waits for the frame; reports device-side errors (clip buffer overflow...) */
 int rsrcu_sync(rsrcu_ctx* ctx);
 
+/* Retained frames.  The reference records every frame anew; a caller that submits the same recorded
+ * frame again and again (a static scene, or the sub-frames of a split frame whose camera did not move)
+ * can keep the frame's tables on the device instead: rsrcu_retain_frame, called after rsrcu_end_frame /
+ * rsrcu_run_stream and before the next rsrcu_begin_frame, snapshots the last submitted frame -- state and
+ * draw tables, per-frame (UPLOAD_ALWAYS) data, clear / store commands (at most 6) with their destinations --
+ * into an rsrcu_frame; rsrcu_replay_frame launches its kernels without decoding, table building or upload.
+ * Store destinations are the ones recorded: host destinations are written again by every replay (wait
+ * with rsrcu_sync / rsrcu_sync_frame before reading them), device-resident results stay in the same buffer. */
+typedef struct rsrcu_frame rsrcu_frame;
+int rsrcu_retain_frame(rsrcu_ctx* ctx, rsrcu_frame** out);
+int rsrcu_replay_frame(rsrcu_ctx* ctx, rsrcu_frame* frame);
+int rsrcu_release_frame(rsrcu_ctx* ctx, rsrcu_frame* frame);
+
 /* Frame overlap (off by default).  When on, the front end of a frame (upload, vertex, setup, binning: latency-bound
  * kernels that leave most of the GPU idle) runs on a second, high-priority stream into its own set of intermediate
  * buffers, and only the tile kernel runs on the context's stream: the front end of frame N+1 executes while the tile

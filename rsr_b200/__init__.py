@@ -117,6 +117,9 @@ def load_library():
         "rsrcu_store_color_quads": [vp, vp, ci, ci, ci],
         "rsrcu_enable_peer_access": [vp, ci],
         "rsrcu_set_overlap": [vp, ci],
+        "rsrcu_retain_frame": [vp, C.POINTER(C.c_void_p)],
+        "rsrcu_replay_frame": [vp, vp],
+        "rsrcu_release_frame": [vp, vp],
         "rsrcu_store_depth": [vp, vp],
         "rsrcu_end_frame": [vp],
         "rsrcu_sync": [vp],
@@ -142,7 +145,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
     "rsrcu_release_static", "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
-    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_retain_frame", "rsrcu_replay_frame", "rsrcu_release_frame", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
@@ -477,6 +480,21 @@ class GPU:
             self._check(self.L.rsrcu_store_color_tc_device(self.h, int(bool(gamma)), C.c_void_p(device_ptr), w, h, stride_px))
         else:
             self._emit(OP_STORE_TC_DEV, struct.pack("<iiiiQ", int(bool(gamma)), w, h, stride_px, int(device_ptr)))
+
+    def Retain(self) -> int:
+        """snapshot of the frame submitted last (tables and per-frame data stay on the device): handle for Replay"""
+        h = C.c_void_p()
+        self._check(self.L.rsrcu_retain_frame(self.h, C.byref(h)))
+        return h.value
+
+    def Replay(self, frame: int, sync: bool = False):
+        """launch a retained frame's kernels: no stream decode, no table build, no upload"""
+        self._check(self.L.rsrcu_replay_frame(self.h, C.c_void_p(frame)))
+        if sync:
+            self.Sync()
+
+    def Release(self, frame: int):
+        self._check(self.L.rsrcu_release_frame(self.h, C.c_void_p(frame)))
 
     def set_overlap(self, enabled: bool):
         """front end of frame N+1 (second stream, own intermediate buffers) under the tile kernel of frame N"""

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -115,6 +116,24 @@ struct HostDraw {
 
 constexpr int kSlots = 3;
 
+// everything rsrcu_end_frame derives from a recorded frame before it can launch: kept per context for the last
+// frame, and copied into an rsrcu_frame by rsrcu_retain_frame
+struct FramePlan {
+	bool valid{false};
+	FrameParams fp{};
+	size_t offStates{0}, offDraws{0}, offCmds{0}, offVBlocks{0}, offPBlocks{0}, arenaBytes{0};
+	uint64_t ptvbF4{0}, nvertsTotal{0}, pjobs{0};
+	int ncmdInline{0};
+	FrameCmd icmd[kInlineCmds]{};
+	CmdState icmdState[kInlineCmds]{};
+	std::vector<PendingCopy> copies;
+	uint64_t trianglesSubmitted{0}; };
+
+struct rsrcu_frame {
+	FramePlan plan;
+	void* devArena{nullptr};
+	int device{0}; };
+
 struct rsrcu_ctx {
 	int device{0};
 	cudaStream_t stream{nullptr};
@@ -173,6 +192,8 @@ struct rsrcu_ctx {
 	cudaEvent_t evFrontDone[2]{}, evTileDone[2]{};
 	bool overlap{false};
 	uint64_t frameNo{0};
+	FramePlan lastPlan;
+	int lastArena{0};
 	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
 	DevBuf tcOut[kSlots], fpOut[kSlots], halfOut[kSlots], quadsOut[kSlots], depthOut[kSlots];
 	uint32_t clipCapacity{1u << 16};
@@ -420,6 +441,128 @@ int flushDeferredCopies(rsrcu_ctx* c) {
 	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 3], c->copyStream)); }
 	return RSRCU_OK; }
 
+// Launches the kernels of a frame whose tables (plan) are final: K0 (upload of `uploadBytes` from `hostArena`, or
+// nothing for a retained frame whose tables already live on the device, plus the zeroed control block), K1-K6,
+// and the read-back.  `arenaDev` is where the tables live on the device.
+int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, const uint8_t* hostArena, size_t uploadBytes, int arenaIdx) {
+	const FrameParams& fp = plan.fp;
+	const int ntiles = fp.tilesX * fp.tilesY;
+	const uint64_t ptvbF4 = plan.ptvbF4, nvertsTotal = plan.nvertsTotal, pjobs = plan.pjobs;
+	const size_t offStates = plan.offStates, offDraws = plan.offDraws, offCmds = plan.offCmds, offVBlocks = plan.offVBlocks, offPBlocks = plan.offPBlocks;
+	// overlap mode: the front end of this frame runs on its own high-priority stream into work set (frame & 1) and only
+	// the tile kernel on the context's stream, so K0-K5 of frame N+1 fill the SMs the tile kernel of frame N leaves idle
+	const int si = c->overlap ? static_cast<int>(c->frameNo & 1) : 0;
+	++c->frameNo;
+	rsrcu_ctx::WorkSet& w = c->sets[si];
+	cudaStream_t st = c->overlap ? c->frontStream : c->stream;
+	cudaStream_t tileStream = c->stream;
+	c->launches = 0;
+
+	// ---- device buffers -------------------------------------------------------------------
+	CU(w.ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
+	CU(w.vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
+	CU(w.triInfo.reserve(std::max<uint64_t>(1, pjobs) * sizeof(uint2)));
+	CU(w.triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
+	CU(w.clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
+	const size_t ncells = static_cast<size_t>(ntiles) * fp.groups;
+	const size_t ctrlBytes = 64 + ncells * 8;   // Counters | cellCount[] | cellCursor[]
+	static_assert(sizeof(Counters) <= 64, "control block layout");
+	CU(c->counters[c->outSlot].reserve(ctrlBytes));
+	CU(w.tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
+	CU(w.cellRel.reserve(ncells * 4));
+	CU(w.tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(w.tileOrder.reserve(static_cast<size_t>(ntiles) * 4));
+	CU(w.lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
+	CU(w.largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
+
+	const uint8_t* ab = arenaDev;
+	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
+	const DevDraw* dDraws = reinterpret_cast<const DevDraw*>(ab + offDraws);
+	const FrameCmd* dCmds = reinterpret_cast<const FrameCmd*>(ab + offCmds);
+	Counters* dCtr = static_cast<Counters*>(c->counters[c->outSlot].ptr);
+	BinArgs bin{};
+	bin.cellCount = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->counters[c->outSlot].ptr) + 64);
+	bin.cellCursor = bin.cellCount + ncells;
+	bin.tileBase = static_cast<const uint32_t*>(w.tileBase.ptr);
+	bin.cellRel = static_cast<const uint32_t*>(w.cellRel.ptr);
+	bin.lists = static_cast<uint2*>(w.lists.ptr);
+	bin.large = static_cast<LargeItem*>(w.largeItems.ptr);
+
+	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
+	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
+	{
+		// K0: upload + zeroed control block in one kernel (kernels.cuh)
+		const size_t n16 = (uploadBytes + 15) / 16, nz16 = (ctrlBytes + 15) / 16;
+		const int blocks = static_cast<int>(std::min<size_t>(148 * 8, (std::max(n16, nz16) + 255) / 256));
+		CU(launchPdl(upload_kernel, static_cast<unsigned>(std::max(blocks, 1)), 256u, 0, st, reinterpret_cast<const uint4*>(hostArena),
+			reinterpret_cast<uint4*>(const_cast<uint8_t*>(arenaDev)), n16, reinterpret_cast<uint4*>(dCtr), nz16));
+		++c->launches; }
+	if (arenaIdx >= 0) { CU(cudaEventRecord(c->arenaFree[arenaIdx], st)); }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[1], st)); }
+	const int traceIdx = (c->trace && c->traceFrames < 64) ? c->traceFrames++ : -1;
+	if (traceIdx >= 0) { c->traceFrameOfSlot[c->outSlot] = traceIdx; CU(cudaEventRecord(c->traceEv[4 * traceIdx], st)); }
+	else { c->traceFrameOfSlot[c->outSlot] = -1; }
+
+	if (fp.totalVJobs) {
+		CU(launchPdl(vertex_kernel, (fp.totalVJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(w.ptvb.ptr), static_cast<uint8_t*>(w.vflags.ptr)));
+		++c->launches; }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
+	if (fp.totalPJobs) {
+		CU(launchPdl(setup_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp,
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<const float4*>(w.ptvb.ptr), static_cast<const uint8_t*>(w.vflags.ptr),
+			static_cast<uint2*>(w.triInfo.ptr), static_cast<TriRec*>(w.triRecs.ptr), static_cast<ClipRec*>(w.clipRecs.ptr),
+			bin, static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
+		++c->launches; }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
+	if (fp.totalPJobs && fp.groups > 1) {
+		CU(launchPdl(cell_scan_kernel, static_cast<unsigned>((ntiles + 7) / 8), 256u, 0, st, fp, static_cast<const uint32_t*>(bin.cellCount), static_cast<uint32_t*>(w.cellRel.ptr),
+			static_cast<uint32_t*>(w.tileTotal.ptr), static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
+		++c->launches; }
+	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
+	if (fp.totalPJobs) {
+		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(w.triInfo.ptr),
+			static_cast<const ClipRec*>(w.clipRecs.ptr), bin, dCtr));
+		++c->launches; }
+	if (c->overlap) {
+		CU(cudaEventRecord(c->evFrontDone[si], st));
+		CU(cudaStreamWaitEvent(tileStream, c->evFrontDone[si], 0)); }
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], tileStream)); }
+
+	TileArgs ta{};
+	for (int i = 0; i < plan.ncmdInline; ++i) { ta.icmd[i] = plan.icmd[i]; ta.icmdState[i] = plan.icmdState[i]; }
+	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
+	ta.ptvb = static_cast<const float4*>(w.ptvb.ptr);
+	ta.triRecs = static_cast<const TriRec*>(w.triRecs.ptr);
+	ta.clipRecs = static_cast<const ClipRec*>(w.clipRecs.ptr);
+	ta.lists = static_cast<const uint2*>(w.lists.ptr);
+	ta.tileBase = bin.tileBase;
+	ta.cellRel = bin.cellRel;
+	ta.large = bin.large;
+	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
+	ta.ctr = dCtr;
+	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
+	++c->launches;
+	CU(cudaGetLastError());
+	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], tileStream)); }
+	if (c->overlap) { CU(cudaEventRecord(c->evTileDone[si], tileStream)); }
+
+	c->lastH2D = uploadBytes;
+	c->lastD2H = 0;
+	CU(cudaEventRecord(c->evRendered[c->outSlot], tileStream));
+	if (traceIdx >= 0) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 1], tileStream)); }
+	for (const PendingCopy& pc : plan.copies) { c->lastD2H += pc.rowBytes * pc.rows; }
+	c->deferredCopies = plan.copies;
+	c->stats.triangles_submitted = plan.trianglesSubmitted;
+	c->deferredSlot = c->outSlot;
+	c->framePending = true;
+	// the read-back goes to the copy stream right away (it waits for evRendered there): the upload is a kernel
+	// (K0), so a queued device->host copy cannot hold up the next frame's upload on a copy engine
+	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
+	return RSRCU_OK; }
+
+
 }  // namespace
 
 extern "C" {
@@ -553,6 +696,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->refTileH = (rh % kTile == 0) ? rh : kTile;
 	c->postTileW = rw; c->postTileH = rh;
 	c->states.clear(); c->draws.clear(); c->cmds.clear(); c->cmdDstKind.clear(); c->copies.clear();
+	c->lastPlan.valid = false;
 	c->arenas[c->cur].used = 0;
 	c->trianglesSubmitted = 0;
 	c->haveState = false; c->stateDirty = true;
@@ -769,14 +913,6 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	c->inFrame = false;
 	const auto tSubmit = std::chrono::steady_clock::now();
 	c->recordNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(tSubmit - c->tBegin).count());
-	// overlap mode: the front end of this frame runs on its own high-priority stream into work set (frame & 1) and only
-	// the tile kernel on the context's stream, so K0-K5 of frame N+1 fill the SMs the tile kernel of frame N leaves idle
-	const int si = c->overlap ? static_cast<int>(c->frameNo & 1) : 0;
-	++c->frameNo;
-	rsrcu_ctx::WorkSet& w = c->sets[si];
-	cudaStream_t st = c->overlap ? c->frontStream : c->stream;
-	cudaStream_t tileStream = c->stream;
-	c->launches = 0;
 
 	const int W = c->width, H = c->height;
 	FrameParams fp{};
@@ -861,113 +997,80 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 			pb[b] = static_cast<uint32_t>(dp); } }
 	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
 
-	// ---- device buffers -------------------------------------------------------------------
-	CU(w.ptvb.reserve(std::max<uint64_t>(1, ptvbF4) * 16));
-	CU(w.vflags.reserve(std::max<uint64_t>(1, nvertsTotal)));
-	CU(w.triInfo.reserve(std::max<uint64_t>(1, pjobs) * sizeof(uint2)));
-	CU(w.triRecs.reserve(std::max<uint64_t>(1, pjobs) * sizeof(TriRec)));
-	CU(w.clipRecs.reserve(static_cast<size_t>(c->clipCapacity) * sizeof(ClipRec)));
-	const size_t ncells = static_cast<size_t>(ntiles) * fp.groups;
-	const size_t ctrlBytes = 64 + ncells * 8;   // Counters | cellCount[] | cellCursor[]
-	static_assert(sizeof(Counters) <= 64, "control block layout");
-	CU(c->counters[c->outSlot].reserve(ctrlBytes));
-	CU(w.tileBase.reserve((static_cast<size_t>(ntiles) + 1) * 4));
-	CU(w.cellRel.reserve(ncells * 4));
-	CU(w.tileTotal.reserve(static_cast<size_t>(ntiles) * 4));
-	CU(w.tileOrder.reserve(static_cast<size_t>(ntiles) * 4));
-	CU(w.lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
-	CU(w.largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
-
-	const uint8_t* ab = static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr);
-	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
-	const DevDraw* dDraws = reinterpret_cast<const DevDraw*>(ab + offDraws);
-	const FrameCmd* dCmds = reinterpret_cast<const FrameCmd*>(ab + offCmds);
-	Counters* dCtr = static_cast<Counters*>(c->counters[c->outSlot].ptr);
-	BinArgs bin{};
-	bin.cellCount = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->counters[c->outSlot].ptr) + 64);
-	bin.cellCursor = bin.cellCount + ncells;
-	bin.tileBase = static_cast<const uint32_t*>(w.tileBase.ptr);
-	bin.cellRel = static_cast<const uint32_t*>(w.cellRel.ptr);
-	bin.lists = static_cast<uint2*>(w.lists.ptr);
-	bin.large = static_cast<LargeItem*>(w.largeItems.ptr);
-
-	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
-	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
-	{
-		// K0: upload + zeroed control block in one kernel (kernels.cuh)
-		const size_t n16 = (c->arenas[c->cur].used + 15) / 16, nz16 = (ctrlBytes + 15) / 16;
-		const int blocks = static_cast<int>(std::min<size_t>(148 * 8, (std::max(n16, nz16) + 255) / 256));
-		CU(launchPdl(upload_kernel, static_cast<unsigned>(std::max(blocks, 1)), 256u, 0, st, reinterpret_cast<const uint4*>(c->arenas[c->cur].host),
-			static_cast<uint4*>(c->arenas[c->cur].dev.ptr), n16, reinterpret_cast<uint4*>(dCtr), nz16));
-		++c->launches; }
-	CU(cudaEventRecord(c->arenaFree[c->cur], st));
-	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[1], st)); }
-	const int traceIdx = (c->trace && c->traceFrames < 64) ? c->traceFrames++ : -1;
-	if (traceIdx >= 0) { c->traceFrameOfSlot[c->outSlot] = traceIdx; CU(cudaEventRecord(c->traceEv[4 * traceIdx], st)); }
-	else { c->traceFrameOfSlot[c->outSlot] = -1; }
-
-	if (fp.totalVJobs) {
-		CU(launchPdl(vertex_kernel, (fp.totalVJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
-			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(w.ptvb.ptr), static_cast<uint8_t*>(w.vflags.ptr)));
-		++c->launches; }
-	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
-	if (fp.totalPJobs) {
-		CU(launchPdl(setup_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp,
-			static_cast<const ApproxLuts*>(c->devLuts), static_cast<const float4*>(w.ptvb.ptr), static_cast<const uint8_t*>(w.vflags.ptr),
-			static_cast<uint2*>(w.triInfo.ptr), static_cast<TriRec*>(w.triRecs.ptr), static_cast<ClipRec*>(w.clipRecs.ptr),
-			bin, static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
-		++c->launches; }
-	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[3], st)); CU(cudaEventRecord(c->evStage[4], st)); }
-	if (fp.totalPJobs && fp.groups > 1) {
-		CU(launchPdl(cell_scan_kernel, static_cast<unsigned>((ntiles + 7) / 8), 256u, 0, st, fp, static_cast<const uint32_t*>(bin.cellCount), static_cast<uint32_t*>(w.cellRel.ptr),
-			static_cast<uint32_t*>(w.tileTotal.ptr), static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
-		++c->launches; }
-	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
-	if (fp.totalPJobs) {
-		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(w.triInfo.ptr),
-			static_cast<const ClipRec*>(w.clipRecs.ptr), bin, dCtr));
-		++c->launches; }
-	if (c->overlap) {
-		CU(cudaEventRecord(c->evFrontDone[si], st));
-		CU(cudaStreamWaitEvent(tileStream, c->evFrontDone[si], 0)); }
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], tileStream)); }
-
-	TileArgs ta{};
+	FramePlan& plan = c->lastPlan;
+	plan.fp = fp;
+	plan.offStates = offStates; plan.offDraws = offDraws; plan.offCmds = offCmds; plan.offVBlocks = offVBlocks; plan.offPBlocks = offPBlocks;
+	plan.ptvbF4 = ptvbF4; plan.nvertsTotal = nvertsTotal; plan.pjobs = pjobs;
+	plan.arenaBytes = c->arenas[c->cur].used;
+	plan.ncmdInline = 0;
 	for (int i = 0; i < kInlineCmds && i < fp.ncmds; ++i) {
-		ta.icmd[i] = c->cmds[i];
+		plan.icmd[i] = c->cmds[i];
 		const DevState& ds = c->states[c->cmds[i].state].ds;
-		CmdState& cs = ta.icmdState[i];
+		CmdState& cs = plan.icmdState[i];
 		std::memcpy(cs.clearColor, ds.clearColor, sizeof(cs.clearColor));
-		cs.clearDepth = ds.clearDepth; cs.programId = ds.programId; cs.uniform0 = ds.uniforms[0]; cs.color0Type = ds.color0Type; }
-	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
-	ta.ptvb = static_cast<const float4*>(w.ptvb.ptr);
-	ta.triRecs = static_cast<const TriRec*>(w.triRecs.ptr);
-	ta.clipRecs = static_cast<const ClipRec*>(w.clipRecs.ptr);
-	ta.lists = static_cast<const uint2*>(w.lists.ptr);
-	ta.tileBase = bin.tileBase;
-	ta.cellRel = bin.cellRel;
-	ta.large = bin.large;
-	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
-	ta.ctr = dCtr;
-	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
-	++c->launches;
-	CU(cudaGetLastError());
-	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], tileStream)); }
-	if (c->overlap) { CU(cudaEventRecord(c->evTileDone[si], tileStream)); }
-
-	c->lastH2D = c->arenas[c->cur].used;
-	c->lastD2H = 0;
-	CU(cudaEventRecord(c->evRendered[c->outSlot], tileStream));
-	if (traceIdx >= 0) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 1], tileStream)); }
-	for (const PendingCopy& pc : c->copies) { c->lastD2H += pc.rowBytes * pc.rows; }
-	c->deferredCopies = c->copies;
-	c->deferredSlot = c->outSlot;
-	c->framePending = true;
-	// the read-back goes to the copy stream right away (it waits for evRendered there): the upload is a kernel
-	// (K0), so a queued device->host copy cannot hold up the next frame's upload on a copy engine
-	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
+		cs.clearDepth = ds.clearDepth; cs.programId = ds.programId; cs.uniform0 = ds.uniforms[0]; cs.color0Type = ds.color0Type;
+		++plan.ncmdInline; }
+	plan.copies = c->copies;
+	plan.trianglesSubmitted = c->trianglesSubmitted;
+	plan.valid = true;
+	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
+	c->lastArena = c->cur;
+	const int r = launchFrame(c, plan, static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr), c->arenas[c->cur].host, c->arenas[c->cur].used, c->cur);
 	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tSubmit).count());
+	return r; }
+
+int rsrcu_retain_frame(rsrcu_ctx* c, rsrcu_frame** out) {
+	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (c->inFrame || !c->lastPlan.valid) { return fail(RSRCU_ERR_INVALID, "rsrcu_retain_frame: no submitted frame (call it after rsrcu_end_frame, before the next rsrcu_begin_frame)"); }
+	if (c->lastPlan.fp.ncmds > kInlineCmds) { return fail(RSRCU_ERR_UNSUPPORTED, "a retained frame holds at most %d clear / store commands", kInlineCmds); }
+	CU(cudaSetDevice(c->device));
+	const UploadArena& ar = c->arenas[c->lastArena];
+	const FramePlan& plan = c->lastPlan;
+	auto* f = new rsrcu_frame();
+	f->plan = plan;
+	f->device = c->device;
+	const size_t bytes = std::max<size_t>(plan.arenaBytes, 16);
+	if (cudaMalloc(&f->devArena, bytes) != cudaSuccess) { delete f; return fail(RSRCU_ERR_CUDA, "cudaMalloc of %zu bytes for a retained frame failed", bytes); }
+	// the tables hold device addresses; those that point into the context's arena mirror move to the private copy
+	std::vector<uint8_t> tmp(ar.host, ar.host + plan.arenaBytes);
+	const uintptr_t oldBase = reinterpret_cast<uintptr_t>(ar.dev.ptr), newBase = reinterpret_cast<uintptr_t>(f->devArena);
+	auto rebase = [&](auto& ptr) {
+		const uintptr_t v = reinterpret_cast<uintptr_t>(ptr);
+		if (v >= oldBase && v < oldBase + plan.arenaBytes) { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(v - oldBase + newBase); } };
+	DevState* st = reinterpret_cast<DevState*>(tmp.data() + plan.offStates);
+	for (size_t i = 0; i < c->states.size(); ++i) {
+		for (int b = 0; b < 16; ++b) { rebase(st[i].buffers[b]); }
+		rebase(st[i].tu[0].texels); rebase(st[i].tu[1].texels); rebase(st[i].tu3); }
+	DevDraw* dr = reinterpret_cast<DevDraw*>(tmp.data() + plan.offDraws);
+	for (size_t i = 0; i < c->draws.size(); ++i) { rebase(dr[i].indices); }
+	if (cudaMemcpy(f->devArena, tmp.data(), plan.arenaBytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+		cudaFree(f->devArena); delete f; return fail(RSRCU_ERR_CUDA, "upload of a retained frame failed"); }
+	*out = f;
+	return RSRCU_OK; }
+
+int rsrcu_replay_frame(rsrcu_ctx* c, rsrcu_frame* f) {
+	if (!c || !f) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_replay_frame inside begin/end frame"); }
+	if (f->device != c->device) { return fail(RSRCU_ERR_INVALID, "frame was retained on device %d", f->device); }
+	CU(cudaSetDevice(c->device));
+	const auto t0 = std::chrono::steady_clock::now();
+	if (!f->plan.copies.empty()) {
+		// the store targets are the recorded ones: the previous frame's read-back (possibly of the same buffer) goes first
+		CU(cudaStreamWaitEvent(c->overlap ? c->frontStream : c->stream, c->evCopied[c->outSlot], 0)); }
+	c->outSlot = (c->outSlot + 1) % kSlots;   // counters ring; the store targets stay the ones recorded
+	c->recordNs = 0;
+	const int r = launchFrame(c, f->plan, static_cast<const uint8_t*>(f->devArena), nullptr, 0, -1);
+	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+	return r; }
+
+int rsrcu_release_frame(rsrcu_ctx* c, rsrcu_frame* f) {
+	if (!f) { return RSRCU_OK; }
+	if (c) {
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->frontStream);
+		cudaStreamSynchronize(c->stream); }
+	if (f->devArena) { cudaFree(f->devArena); }
+	delete f;
 	return RSRCU_OK; }
 
 int rsrcu_sync(rsrcu_ctx* c) {
@@ -980,7 +1083,6 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	if (!c->framePending) { return RSRCU_OK; }
 	c->framePending = false;
 	const Counters& k = c->hostCounters[c->outSlot];
-	c->stats.triangles_submitted = c->trianglesSubmitted;
 	c->stats.triangles_binned = k.binned;
 	c->stats.triangles_clipped = k.clipped;
 	c->stats.bin_entries = k.entries;

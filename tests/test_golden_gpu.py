@@ -189,6 +189,42 @@ def test_frame_overlap_mode_front_end_under_previous_tile_kernel():
         g.close()
 
 
+@pytest.mark.parametrize("overlap", [False, True])
+def test_retained_frames_replay_bit_identical(overlap):
+    """rsrcu_retain_frame / rsrcu_replay_frame: the tables of a submitted frame (including its per-frame UPLOAD_ALWAYS
+    data, whose device addresses move to the private copy) stay on the device; replays -- interleaved with other
+    frames and with each other -- reproduce the frame bit for bit"""
+    g = R.GPU(0)
+    try:
+        g.set_overlap(overlap)
+        a_scene, b_scene = scenes.BundledLikeScene(cubes=300), scenes.CubesScene(instances=120)
+        size = (1920, 1080)
+        outs, want, handles = [], [], []
+        for sc, kw in ((a_scene, {"t": 0.7}), (b_scene, {"t": 0.2}), (a_scene, {"t": 1.9, "static": True})):
+            out = np.zeros((size[1], size[0]), np.uint32)
+            sc.record(g, size, out, **kw)
+            g.Run()
+            handles.append(g.Retain())
+            outs.append(out)
+            want.append(out.copy())
+        assert not np.array_equal(want[0], want[2])
+        other = np.zeros((360, 640), np.uint32)
+        for rounds in range(3):
+            for o in outs:
+                o[:] = 0
+            for k in (2, 0, 1):
+                g.Replay(handles[k])
+            scenes.WavyGridScene(n=10).record(g, (640, 360), other)   # an ordinary frame in between
+            g.Run()
+            for k in range(3):
+                assert np.array_equal(outs[k], want[k]), f"replay of frame {k} differs (round {rounds})"
+        st = g.stats()
+        for h in handles:
+            g.Release(h)
+    finally:
+        g.close()
+
+
 def test_tile_list_overflow_is_reported_and_recovered(ref_gpu, monkeypatch):
     """more (triangle, tile) pairs than the list buffer holds: the frame reports OVERFLOW, the buffer
     grows, and rendering the same frame again gives the reference's pixels"""
