@@ -181,6 +181,7 @@ public:
 	GPU& operator=(const GPU&) = delete;
 
 	auto IC() -> GL& { return ic_; }
+	static void Check(int rc) { if (rc != RSRCU_OK) { throw Error(rc, rsrcu_last_error()); } }
 
 	// GPU::Reset (rglv_gpu.cxx:50-56)
 	void Reset(int widthPx, int heightPx, int tileBlocksX = 8, int tileBlocksY = 8) {
@@ -196,6 +197,14 @@ public:
 
 	// what waiting on the reference's Finalize job does
 	void Sync() { if (int rc = rsrcu_sync(ctx_); rc != RSRCU_OK) { throw Error(rc, rsrcu_last_error()); } }
+
+	// beyond the reference's surface (include/rsrcu.h): pipelining, retained frames, split-frame presentation
+	void SyncFrame(int lag) { Check(rsrcu_sync_frame(ctx_, lag)); }
+	void SetOverlap(bool on) { Check(rsrcu_set_overlap(ctx_, on ? 1 : 0)); }
+	void EnablePeerAccess(int peerDevice) { Check(rsrcu_enable_peer_access(ctx_, peerDevice)); }
+	rsrcu_frame* Retain() { rsrcu_frame* f = nullptr; Check(rsrcu_retain_frame(ctx_, &f)); return f; }
+	void Replay(rsrcu_frame* f) { Check(rsrcu_replay_frame(ctx_, f)); }
+	void Release(rsrcu_frame* f) { Check(rsrcu_release_frame(ctx_, f)); }
 
 	rsrcu_ctx* context() { return ctx_; }
 
