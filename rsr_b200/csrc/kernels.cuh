@@ -476,12 +476,18 @@ __device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t o
 	// Items that cover more tiles make short lists (few of them fit a tile): every lane appends on its
 	// own, four independent atomics in flight; each entry is a run of its own.
 	if (small && !single && !walked) {
+		// (row-major walk over the tile range with running coordinates: a division per tile would cost more than the atomic)
+		const uint32_t rowStep = static_cast<uint32_t>((fp.tilesX - w) * fp.groups);
+		uint32_t cur = static_cast<uint32_t>((ty0 * fp.tilesX + tx0) * fp.groups) + group;
+		int col = 0;
 		for (int i0 = 0; i0 < ntile; i0 += 4) {
 			uint32_t cell[4], pos[4];
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
-				const int i = min(i0 + q, ntile - 1);
-				cell[q] = static_cast<uint32_t>(((ty0 + i / w) * fp.tilesX + tx0 + i % w) * fp.groups) + group; }
+				cell[q] = cur;
+				if (i0 + q + 1 < ntile) {
+					cur += static_cast<uint32_t>(fp.groups);
+					if (++col == w) { col = 0; cur += rowStep; } } }
 			if (!FILL) {
 #pragma unroll
 				for (int q = 0; q < 4; ++q) { if (i0 + q < ntile) { atomicAdd(B.cellCount + cell[q], 1u); } } }
@@ -491,7 +497,8 @@ __device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t o
 #pragma unroll
 				for (int q = 0; q < 4; ++q) {
 					if (i0 + q < ntile) {
-						uint32_t p = pos[q] + __ldg(B.tileBase + cell[q] / static_cast<uint32_t>(fp.groups));
+						const uint32_t tile = (fp.groups == 1) ? cell[q] : cell[q] / static_cast<uint32_t>(fp.groups);
+						uint32_t p = pos[q] + __ldg(B.tileBase + tile);
 						if (fp.groups > 1) { p += __ldg(B.cellRel + cell[q]); }
 						if (p < fp.listCapacity) { B.lists[p] = make_uint2(okey, code | kRunStartBit); } } } } } } }
 
