@@ -286,7 +286,7 @@ __device__ __forceinline__ float clip_dist(int plane, const float* c) {
 __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIndex, uint32_t local, const DevState& s, const FrameParams& fp,
                                                const float4* __restrict__ r0, const float4* __restrict__ r1,
                                                const float4* __restrict__ r2, const ApproxLuts* __restrict__ luts,
-                                               ClipRec* __restrict__ clipRecs, Counters* __restrict__ ctr) {
+                                               ClipRec* __restrict__ clipRecs, Counters* __restrict__ ctr, const unsigned int slot) {
 	CVert bufA[9], bufB[9];
 	CVert* A = bufA; CVert* Bv = bufB;
 	int na = 3;
@@ -355,7 +355,7 @@ __device__ __noinline__ uint32_t clip_triangle(const DevDraw& d, uint32_t drawIn
 	else { if (!s.cullingEnabled || ((s.cullFace & 1) == 0)) { willCull = false; } }
 	if (willCull) { return kClipSrc | kNoClipRec; }
 
-	const unsigned int slot = atomicAdd(&ctr->clipAlloc, 1u);
+	// (the record was reserved by the caller, one atomic per warp; a triangle that clips away or is culled leaves it unused)
 	if (slot >= fp.clipCapacity) { atomicOr(&ctr->overflow, 1u); return kClipSrc | kNoClipRec; }
 	ClipRec& rec = clipRecs[slot];
 	rec.nverts = na;
@@ -638,6 +638,8 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 #endif
 	K2B(0);
 	const int di = find_draw(draws, blockDraw, min(job, fp.totalPJobs - 1u), false);
+	bool needClip = false;
+	const float4* clipR0 = nullptr; const float4* clipR1 = nullptr; const float4* clipR2 = nullptr;
 	if (job < fp.totalPJobs) {
 		const DevDraw& d = draws[di];
 		const DevState& s = states[d.state];
@@ -651,7 +653,6 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 		else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
 		const uint32_t nverts = static_cast<uint32_t>(d.nverts);
 		uint32_t out = kReject;
-		if (i0 + i1 + i2 == 0xffffffffu) { out = 0; }
 		K2B(1);
 		if (i0 < nverts && i1 < nverts && i2 < nverts) {
 			const uint32_t vb = iid * nverts;
@@ -664,9 +665,7 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 			const bool pointsOutside = (cf0 | cf1 | cf2) != 0;
 			const bool primOutside = (cf0 & cf1 & cf2) != 0;
 			if (primOutside) { out = kReject; }
-			else if (pointsOutside) {
-				atomicAdd(&ctr->clipped, 1ull);
-				out = clip_triangle(d, static_cast<uint32_t>(di), local, s, fp, r0, r1, r2, luts, clipRecs, ctr); }
+			else if (pointsOutside) { needClip = true; clipR0 = r0; clipR1 = r1; clipR2 = r2; }
 			else {
 				const float4 a = __ldg(r0), b = __ldg(r1), c = __ldg(r2);
 				// rmlg::Area (rmlg_triangle.hxx:18-27)
@@ -705,10 +704,27 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 					uint4* dst = reinterpret_cast<uint4*>(triRecs + job);
 #pragma unroll
 					for (int q = 0; q < 5; ++q) { dst[q] = src[q]; } } } }
-		if (out == 0x12345u) { myInfo.y = 1; }
 		K2B(2);
 		myInfo = make_uint2(out, d.idBase + local);
-		triInfo[job] = myInfo; }
+		if (!needClip) { triInfo[job] = myInfo; } }
+	// Clip sources: the warp reserves their records with ONE atomic (lanes reach the clipper through
+	// different paths, so per-lane allocations would be one round trip each), then clips.
+	{
+		const unsigned lane = threadIdx.x & 31u;
+		const unsigned m = __ballot_sync(0xffffffffu, needClip);
+		if (m) {
+			const int leader = __ffs(m) - 1;
+			unsigned base = 0;
+			if (static_cast<int>(lane) == leader) {
+				base = atomicAdd(&ctr->clipAlloc, static_cast<unsigned>(__popc(m)));
+				atomicAdd(&ctr->clipped, static_cast<unsigned long long>(__popc(m))); }
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (needClip) {
+				const DevDraw& d = draws[di];
+				const uint32_t local = job - d.pjobBase;
+				myInfo.x = clip_triangle(d, static_cast<uint32_t>(di), local, states[d.state], fp, clipR0, clipR1, clipR2, luts, clipRecs, ctr,
+				                         base + __popc(m & ((1u << lane) - 1u)));
+				triInfo[job] = myInfo; } } }
 	bin_triangle<false>(job, myInfo, fp, clipRecs, B, ctr);
 	K2B(3);
 #ifdef RSR_PHASE_PROF
