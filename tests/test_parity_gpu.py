@@ -180,3 +180,43 @@ def test_half_size_and_quad_swizzled_float_stores(attachments, size, ref_gpu, cu
     assert np.unique(rh.view(np.uint32)).size > 100
     assert np.array_equal(rh.view(np.uint32), ch.view(np.uint32)), "half-size float store differs"
     assert np.array_equal(rq.view(np.uint32), cq.view(np.uint32)), "quad-swizzled float store differs"
+
+
+def test_maximum_target_2048x2048(ref_gpu, cuda_gpu):
+    """the largest target either renderer accepts (guard band ends at 2048, rglv_view_frustum.hxx:36-39): 64 x 64 device tiles,
+    4096 CTAs, every tile-index field at its limit"""
+    assert_identical(render_both(SoupScene(n=400, seed=17), (2048, 2048), ref_gpu, cuda_gpu, with_depth=True, attachments="split"), "2048x2048")
+    assert_identical(render_both(CubesScene(instances=400), (2048, 2048), ref_gpu, cuda_gpu), "2048x2048 cubes")
+
+
+def test_error_behaviour_matches_the_reference_contract(cuda_gpu):
+    """what the reference treats as fatal (std::exit / assert) is an error code here, and the context stays usable"""
+    from rsr_b200.scenes import begin, finish
+    g = R.GPU(0, direct=True)
+    try:
+        # target beyond the guard band
+        with pytest.raises(R.RsrError) as e:
+            g.Reset((4096, 2160), (8, 8))
+        assert e.value.code == 5   # RSRCU_ERR_UNSUPPORTED
+        # odd dimensions cannot hold 2x2 quads
+        with pytest.raises(R.RsrError):
+            g.Reset((641, 360), (8, 8))
+        # a stencil clear is not implemented (rglv_gpu.cxx:313-315)
+        g.Reset((640, 360), (8, 8))
+        g.ClearColor((0.0, 0.0, 0.0))
+        with pytest.raises(R.RsrError):
+            g.Clear(R.GL_STENCIL_BUFFER_BIT)
+        # RB_COLOR_DEPTH needs colour and depth cleared together (rglv_gpu.cxx:317-319)
+        with pytest.raises(R.RsrError):
+            g.Clear(R.GL_COLOR_BUFFER_BIT)
+        # a store canvas of the wrong size
+        bad = np.zeros((100, 100), np.uint32)
+        with pytest.raises(R.RsrError):
+            g.StoreColor(bad)
+    finally:
+        g.close()
+    # the shared context still renders
+    out = np.zeros((360, 640), np.uint32)
+    WavyGridScene(n=8).record(cuda_gpu, (640, 360), out)
+    cuda_gpu.Run()
+    assert np.unique(out).size > 10
