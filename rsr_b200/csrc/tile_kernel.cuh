@@ -399,7 +399,7 @@ __device__ __forceinline__ uint32_t quad_coverage(const TileShared& sh, int ti, 
 //            (depth LESS ties, blending): __match_any_sync groups them and the group is replayed
 //            rank by rank.  With little overdraw inside 32 consecutive items that is one pass.
 template <class P, bool FAST>
-__device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const TileArgs& A, const uint32_t flags, int nb, int ox, int oy) {
+__device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const TileArgs& A, const uint32_t flags, const int base, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
@@ -419,9 +419,9 @@ __device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const Tile
 		while (qn < 32) {
 			if (pending == 0) {
 				if (k >= nb) { break; }
-				const int i = k + lane;
+				const int i = base + k + lane;
 				bool hit = false, small = false;
-				if (i < nb) {
+				if (k + lane < nb) {
 					const uint32_t bb = sh.bbox[i];
 					const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
 					hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry);
@@ -431,7 +431,7 @@ __device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const Tile
 						small = (bqx1 - bqx0 <= 1) && (bqy1 - bqy0 <= 1); } }
 				pending = __ballot_sync(0xffffffffu, hit);
 				smallMask = __ballot_sync(0xffffffffu, small);
-				kbase = k;
+				kbase = base + k;
 				k += 32;
 				continue; }
 			const int j = __ffs(pending) - 1;
@@ -504,16 +504,16 @@ __device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const Tile
 // Direct variant: every lane tests and shades its own quad, triangle by triangle.  No queue
 // traffic; best when triangles are large (most lanes covered) or the batch is short.
 template <class P, bool FAST>
-__device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const TileArgs& A, const uint32_t flags, int nb, int ox, int oy) {
+__device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const TileArgs& A, const uint32_t flags, const int base, int nb, int ox, int oy) {
 	const int t = threadIdx.x;
 	const int warp = t >> 5, lane = t & 31;
 	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
 	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;
 	unsigned frags = 0;
 	for (int k = 0; k < nb; k += 32) {
-		const int i = k + lane;
+		const int i = base + k + lane;
 		bool hit = false;
-		if (i < nb) {
+		if (k + lane < nb) {
 			const uint32_t bb = sh.bbox[i];
 			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
 			hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
@@ -521,7 +521,7 @@ __device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const Tile
 		while (m) {
 			const int j = __ffs(m) - 1;
 			m &= m - 1;
-			const int ti = k + j;
+			const int ti = base + k + j;
 			int e1[4], e2[4];
 			const uint32_t covered = quad_coverage(sh, ti, lx, ly, e1, e2);
 			if (covered == 0) { continue; }
@@ -531,12 +531,28 @@ __device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const Tile
 // picks the variant per batch: long batches of small triangles go through the work queue; the
 // common pipeline state gets the specialised instantiation
 template <class P>
-__device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, uint32_t key, int nb, int ox, int oy, bool queued) {
+__device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A, uint32_t key, int base, int nb, int ox, int oy, bool queued) {
 	const uint32_t flags = key >> 8;
 	const bool fast = (flags & kKeyFastMask) == kKeyFastValue;
 	if (queued) {
-		return fast ? draw_batch_queued<P, true>(sh, A, flags, nb, ox, oy) : draw_batch_queued<P, false>(sh, A, flags, nb, ox, oy); }
-	return fast ? draw_batch_direct<P, true>(sh, A, flags, nb, ox, oy) : draw_batch_direct<P, false>(sh, A, flags, nb, ox, oy); }
+		return fast ? draw_batch_queued<P, true>(sh, A, flags, base, nb, ox, oy) : draw_batch_queued<P, false>(sh, A, flags, base, nb, ox, oy); }
+	return fast ? draw_batch_direct<P, true>(sh, A, flags, base, nb, ox, oy) : draw_batch_direct<P, false>(sh, A, flags, base, nb, ox, oy); }
+
+// program dispatch for one batch of set-up triangles in slots [base, base + nb)
+__device__ __forceinline__ unsigned draw_batch_any(TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy, bool queued) {
+	switch (key0 & 0xffu) {
+	case ProgAmy::id:          return draw_batch<ProgAmy>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgAlphaTexture::id: return draw_batch<ProgAlphaTexture>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgText::id:         return draw_batch<ProgText>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgDepth::id:        return draw_batch<ProgDepth>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgPattern::id:      return draw_batch<ProgPattern>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgMany::id:         return draw_batch<ProgMany>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgOBJ1::id:         return draw_batch<ProgOBJ1>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgOBJ2::id:         return draw_batch<ProgOBJ2>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgOBJ2S::id:        return draw_batch<ProgOBJ2S>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgEnvmap::id:       return draw_batch<ProgEnvmap>(sh, A, key0, base, nb, ox, oy, queued);
+	case ProgWireframe::id:    return draw_batch<ProgWireframe>(sh, A, key0, base, nb, ox, oy, queued);
+	default: return 0u; } }
 
 // ---- IQPostProgram::ShadeCanvas (src/viewer/shaders.hxx:56-66) --------------------------------
 // pow(x, y) = exp2f4(log2f4(x) * y)  (rmlv_mvec4.hxx:652-654, 3rdparty/sse-pow/sse_pow.h:19-95):
@@ -773,7 +789,9 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const TileArgs& A, con
 				while (lo < hi) {
 					const int mid = (lo + hi + 1) >> 1;
 					if (sh.runPre[mid] <= pos) { lo = mid; } else { hi = mid - 1; } }
-				sh.sorted[i] = __ldg(list + sh.runStart[lo] + (pos - sh.runPre[lo])).y & ~kRunStartBit; }
+				const uint32_t code = __ldg(list + sh.runStart[lo] + (pos - sh.runPre[lo])).y & ~kRunStartBit;
+				sh.sorted[i] = code;
+				prefetch_entry(A, code); }
 			lc.taken += static_cast<uint32_t>(n);
 			if (lc.taken >= size0) { ++lc.g; lc.taken = 0; lc.mode = 0; lc.runs = 0; }
 			__syncthreads();
@@ -811,6 +829,121 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const TileArgs& A, con
 	if (lc.taken >= size0 || n == 0) { ++lc.g; lc.taken = 0; lc.mode = 0; lc.runs = 0; }
 	sort_scratch(sh, scr, n, begin, 0, 0);
 	return n; }
+
+// Runs the clear / store commands that precede draw `di` for this thread's own 2x2 quad (tile colour and depth of a
+// quad are only ever touched by its thread, so no CTA-wide synchronisation is involved).
+__device__ __forceinline__ void exec_cmds(TileShared& sh, const TileArgs& A, int& ci, const int di, const int t, const int px, const int py, const bool onScreen) {
+	// non-draw commands that precede that draw
+	while (ci < A.fp.ncmds && cmd_before_draw(A, ci) <= di) {
+		FrameCmd cmd;
+		CmdState s;
+		if (ci < kInlineCmds) { cmd = A.icmd[ci]; s = A.icmdState[ci]; }
+		else {
+			cmd = A.cmds[ci];
+			const DevState& gs = A.states[cmd.state];
+			s.clearColor[0] = gs.clearColor[0]; s.clearColor[1] = gs.clearColor[1]; s.clearColor[2] = gs.clearColor[2]; s.clearColor[3] = gs.clearColor[3];
+			s.clearDepth = gs.clearDepth; s.programId = gs.programId; s.uniform0 = gs.uniforms[0]; s.color0Type = gs.color0Type; }
+		++ci;
+		switch (cmd.type) {
+		case kCmdClear: {
+			// GPU::DrawImpl CMD_CLEAR (rglv_gpu.cxx:311-344)
+			const bool clearColor = (cmd.arg & 1) != 0, clearDepth = (cmd.arg & 2) != 0;
+#pragma unroll
+			for (int l = 0; l < 4; ++l) {
+				if (clearColor) { sh.chan[0][l][t] = s.clearColor[0]; sh.chan[1][l][t] = s.clearColor[1]; sh.chan[2][l][t] = s.clearColor[2]; }
+				if (clearDepth) { sh.chan[3][l][t] = s.clearDepth; } } }
+			break;
+		case kCmdStoreTC: {
+			// GPUBltImpl::StoreTrueColor -> FilterTile<SHADER, sRGB|LinearColor>
+			if (onScreen) {
+				uint32_t out[4];
+#pragma unroll
+				for (int l = 0; l < 4; ++l) {
+					float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
+					if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
+						const float ex = s.uniform0;
+						r = r * ex; g = g * ex; b = b * ex; }
+					else if (s.programId == 3) {
+						// FilterTile's running fragment coordinate (rglr_algorithm.hxx:75-96): starts at the
+						// reference tile's left/top edge and is advanced by repeated float adds per quad
+						const int ptx = (px / A.fp.postTileW) * A.fp.postTileW, pty = (py / A.fp.postTileH) * A.fp.postTileH;
+						const float iw = 1.0f / itof(A.fp.width), ih = 1.0f / itof(A.fp.height);
+						float fcx = (itof(ptx) + 0.5f) / itof(A.fp.width) + ((l & 1) ? iw : 0.0f);
+						float fcy = ((itof(A.fp.height - pty)) - 0.5f) / itof(A.fp.height) - ((l & 2) ? ih : 0.0f);
+						const float fcdx = iw * 2.0f, fcdy = -ih * 2.0f;
+						for (int kx = ptx; kx < px; kx += 2) { fcx += fcdx; }
+						for (int ky = pty; ky < py; ky += 2) { fcy += fcdy; }
+						post_iq(r, g, b, fcx, fcy); }
+					out[l] = (cmd.arg & 1) ? ((srgb8(r, sh.srgbTab) << 16) | (srgb8(g, sh.srgbTab) << 8) | srgb8(b, sh.srgbTab))
+					                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
+				uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
+				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
+				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_uint2(out[2], out[3]); } }
+			break;
+		case kCmdStoreFP: {
+			// Copy(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:247-279): alpha = 0
+			if (onScreen) {
+				float4* dst = static_cast<float4*>(cmd.dst);
+#pragma unroll
+				for (int l = 0; l < 4; ++l) {
+					dst[static_cast<size_t>(py + (l >> 1)) * cmd.dstStride + px + (l & 1)] =
+						make_float4(sh.chan[0][l][t], sh.chan[1][l][t], sh.chan[2][l][t], 0.0f); } } }
+			break;
+		case kCmdStoreHalfFP: {
+			// Downsample(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:118-141): one output
+			// pixel per quad, ((p0 + p1) + p2) + p3 then * 0.25, alpha = 0
+			if (onScreen) {
+				float4* dst = static_cast<float4*>(cmd.dst);
+				float avg[3];
+#pragma unroll
+				for (int ch = 0; ch < 3; ++ch) {
+					avg[ch] = (((sh.chan[ch][0][t] + sh.chan[ch][1][t]) + sh.chan[ch][2][t]) + sh.chan[ch][3][t]) * 0.25f; }
+				dst[static_cast<size_t>(py >> 1) * cmd.dstStride + (px >> 1)] = make_float4(avg[0], avg[1], avg[2], 0.0f); } }
+			break;
+		case kCmdStoreQuadsFP: {
+			// Copy(QFloat4Canvas | QFloat3Canvas -> QFloat4Canvas) (rglr_algorithm.cxx:320-368): the quad-
+			// swizzled layout itself, 64 bytes per 2x2 quad {r[4], g[4], b[4], a[4]}.  The fourth plane is
+			// what the reference's tile holds there: depth (RB_COLOR_DEPTH), 1.0 (RB_RGBF32), or the
+			// clear colour's alpha (RB_RGBAF32: no program writes alpha)
+			if (onScreen) {
+				float4* dst = static_cast<float4*>(cmd.dst) + (static_cast<size_t>(py >> 1) * cmd.dstStride + (px >> 1)) * 4;
+#pragma unroll
+				for (int ch = 0; ch < 3; ++ch) {
+					dst[ch] = make_float4(sh.chan[ch][0][t], sh.chan[ch][1][t], sh.chan[ch][2][t], sh.chan[ch][3][t]); }
+				if (s.color0Type == 0) { dst[3] = make_float4(sh.chan[3][0][t], sh.chan[3][1][t], sh.chan[3][2][t], sh.chan[3][3][t]); }
+				else {
+					const float a = (s.color0Type == 1) ? 1.0f : s.clearColor[3];
+					dst[3] = make_float4(a, a, a, a); } } }
+			break;
+		case kCmdStoreDepth: {
+			if (onScreen) {
+				float* dst = static_cast<float*>(cmd.dst);
+				*reinterpret_cast<float2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_float2(sh.chan[3][0][t], sh.chan[3][1][t]);
+				*reinterpret_cast<float2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_float2(sh.chan[3][2][t], sh.chan[3][3][t]); } }
+			break;
+		default: break; } } }
+
+// RSR_WARP_WALK=1 (experiment, off): warp-autonomous list walk, see the comment in tile_kernel and profiles/README.md
+#ifndef RSR_WARP_WALK
+#define RSR_WARP_WALK 0
+#endif
+#ifndef RSR_WARP_QUEUE_MIN
+#define RSR_WARP_QUEUE_MIN 12
+#endif
+
+// one warp rasterises the nb (<= 32) triangles it has set up in its own record slots [base, base + nb)
+__device__ __forceinline__ unsigned raster_slots(TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy) {
+	__syncwarp();
+	const int lane = threadIdx.x & 31;
+	bool tiny = false;
+	if (lane < nb) {
+		const uint32_t bb = sh.bbox[base + lane];
+		tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
+	const int ntiny = __popc(__ballot_sync(0xffffffffu, tiny));
+	const bool queued = nb >= RSR_WARP_QUEUE_MIN && ntiny * 2 > nb;
+	const unsigned frags = draw_batch_any(sh, A, key0, base, nb, ox, oy, queued);
+	__syncwarp();
+	return frags; }
 
 #ifndef RSR_TILE_CTAS
 #define RSR_TILE_CTAS 3
@@ -883,6 +1016,72 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	// (DevDraw::batchKey) and no clear/store command lies between them -- a scene made of hundreds
 	// of tiny draws (one per textured quad) still fills whole batches.
 	int ci = 0;
+#if RSR_WARP_WALK
+	// Warp-autonomous walk.  Only fetching + sorting a chunk of the list is CTA-wide; inside a chunk every warp
+	// walks the sorted entries on its own: 32 at a time it reads their records, finds where the current run (same
+	// program + pipeline flags, no clear / store in between) ends, keeps the triangles whose bounding box touches
+	// its 16x8-pixel region, sets those up in its own 32 record slots and rasterises them when the slots are full
+	// or the run ends.  No warp ever waits for another one inside a chunk: a batch whose triangles cluster in one
+	// region no longer stalls the other seven warps at a barrier.  All warps take the same decisions (they read
+	// the same entries), so run boundaries and the commands between runs need no agreement protocol.
+	const unsigned ltMask = (1u << lane) - 1u;
+	const int wbase = warp * 32;
+	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;
+	while (true) {
+		if (chunkPos == chunkN && lc.g < G) {
+			PHASE(2);
+			chunkN = load_chunk(sh, A, A.lists, G, A.fp.totalKeys, lc, A.ctr);
+			chunkPos = 0; }
+		PHASE(3);
+		int di = A.fp.ndraws;   // draw owning the next list entry (ndraws = none left)
+		uint32_t key0 = 0;
+		if (chunkPos < chunkN) {
+			const EntryRec head = load_entry(A, sh.sorted[chunkPos]);
+			di = static_cast<int>(head.q3.w);
+			key0 = head.q4.x; }
+		PHASE(5);
+		exec_cmds(sh, A, ci, di, t, px, py, onScreen);
+		if (di >= A.fp.ndraws) { break; }
+		PHASE(6);
+		const int bound = (ci < A.fp.ncmds) ? cmd_before_draw(A, ci) : 0x7fffffff;   // draws >= bound come after cmds[ci]
+		int pos = chunkPos, nrec = 0;
+		bool runOver = false;
+		while (!runOver) {
+			const int e = pos + lane;
+			const bool valid = e < chunkN;
+			uint32_t myId = 0;
+			EntryRec myRec;
+			myRec.q0 = myRec.q1 = myRec.q2 = myRec.q3 = myRec.q4 = make_uint4(0u, 0u, 0u, 0u);
+			if (valid) { myId = sh.sorted[e]; myRec = load_entry(A, myId); }
+			const bool bad = valid && (static_cast<int>(myRec.q3.w) >= bound || myRec.q4.x != key0);
+			const unsigned badMask = __ballot_sync(0xffffffffu, bad);
+			const int nvalid = min(32, chunkN - pos);
+			const int take = badMask ? (__ffs(badMask) - 1) : nvalid;
+			runOver = (badMask != 0u) || (pos + take >= chunkN);
+			bool mine = static_cast<int>(lane) < take;
+			if (mine && !(myId & kFanIdBit)) {
+				// conservative pixel bounding box (setup_edges clamps it further) against this warp's region
+				const int X0 = static_cast<int>(myRec.q0.x), X1 = static_cast<int>(myRec.q0.y), X2 = static_cast<int>(myRec.q0.z);
+				const int Y0 = static_cast<int>(myRec.q0.w), Y1 = static_cast<int>(myRec.q1.x), Y2 = static_cast<int>(myRec.q1.y);
+				const int minx = ((min(min(X0, X1), X2) >> 4) & ~1) - ox, maxx = ((max(max(X0, X1), X2) + 15) >> 4) - ox;
+				const int miny = ((min(min(Y0, Y1), Y2) >> 4) & ~1) - oy, maxy = ((max(max(Y0, Y1), Y2) + 15) >> 4) - oy;
+				mine = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+			const unsigned hitMask = __ballot_sync(0xffffffffu, mine);
+			const int nhit = __popc(hitMask);
+			if (nrec + nhit > 32) {
+				frags += raster_slots(sh, A, key0, wbase, nrec, ox, oy);
+				nrec = 0; }
+			if (mine) {
+				const int slot = wbase + nrec + __popc(hitMask & ltMask);
+				sh.state[slot] = static_cast<uint16_t>(myRec.q4.y);
+				setup_triangle(sh, slot, myId, myRec, A, ox, oy, rl, rt, rr, rb); }
+			nrec += nhit;
+			pos += take; }
+		if (nrec) { frags += raster_slots(sh, A, key0, wbase, nrec, ox, oy); }
+		PHASE(8);
+		chunkPos = pos; }
+	PHASE(9);
+#else
 	while (true) {
 		if (chunkPos == chunkN && lc.g < G) {
 			PHASE(2);
@@ -905,95 +1104,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		const int di = sh.headDraw;   // draw owning the next list entry (ndraws = none left)
 		const uint32_t key0 = sh.headKey;
 		PHASE(5);
-		// non-draw commands that precede that draw
-		while (ci < A.fp.ncmds && cmd_before_draw(A, ci) <= di) {
-			FrameCmd cmd;
-			CmdState s;
-			if (ci < kInlineCmds) { cmd = A.icmd[ci]; s = A.icmdState[ci]; }
-			else {
-				cmd = A.cmds[ci];
-				const DevState& gs = A.states[cmd.state];
-				s.clearColor[0] = gs.clearColor[0]; s.clearColor[1] = gs.clearColor[1]; s.clearColor[2] = gs.clearColor[2]; s.clearColor[3] = gs.clearColor[3];
-				s.clearDepth = gs.clearDepth; s.programId = gs.programId; s.uniform0 = gs.uniforms[0]; s.color0Type = gs.color0Type; }
-			++ci;
-			switch (cmd.type) {
-			case kCmdClear: {
-				// GPU::DrawImpl CMD_CLEAR (rglv_gpu.cxx:311-344)
-				const bool clearColor = (cmd.arg & 1) != 0, clearDepth = (cmd.arg & 2) != 0;
-#pragma unroll
-				for (int l = 0; l < 4; ++l) {
-					if (clearColor) { sh.chan[0][l][t] = s.clearColor[0]; sh.chan[1][l][t] = s.clearColor[1]; sh.chan[2][l][t] = s.clearColor[2]; }
-					if (clearDepth) { sh.chan[3][l][t] = s.clearDepth; } } }
-				break;
-			case kCmdStoreTC: {
-				// GPUBltImpl::StoreTrueColor -> FilterTile<SHADER, sRGB|LinearColor>
-				if (onScreen) {
-					uint32_t out[4];
-#pragma unroll
-					for (int l = 0; l < 4; ++l) {
-						float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
-						if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
-							const float ex = s.uniform0;
-							r = r * ex; g = g * ex; b = b * ex; }
-						else if (s.programId == 3) {
-							// FilterTile's running fragment coordinate (rglr_algorithm.hxx:75-96): starts at the
-							// reference tile's left/top edge and is advanced by repeated float adds per quad
-							const int ptx = (px / A.fp.postTileW) * A.fp.postTileW, pty = (py / A.fp.postTileH) * A.fp.postTileH;
-							const float iw = 1.0f / itof(A.fp.width), ih = 1.0f / itof(A.fp.height);
-							float fcx = (itof(ptx) + 0.5f) / itof(A.fp.width) + ((l & 1) ? iw : 0.0f);
-							float fcy = ((itof(A.fp.height - pty)) - 0.5f) / itof(A.fp.height) - ((l & 2) ? ih : 0.0f);
-							const float fcdx = iw * 2.0f, fcdy = -ih * 2.0f;
-							for (int kx = ptx; kx < px; kx += 2) { fcx += fcdx; }
-							for (int ky = pty; ky < py; ky += 2) { fcy += fcdy; }
-							post_iq(r, g, b, fcx, fcy); }
-						out[l] = (cmd.arg & 1) ? ((srgb8(r, sh.srgbTab) << 16) | (srgb8(g, sh.srgbTab) << 8) | srgb8(b, sh.srgbTab))
-						                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
-					uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
-					*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
-					*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_uint2(out[2], out[3]); } }
-				break;
-			case kCmdStoreFP: {
-				// Copy(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:247-279): alpha = 0
-				if (onScreen) {
-					float4* dst = static_cast<float4*>(cmd.dst);
-#pragma unroll
-					for (int l = 0; l < 4; ++l) {
-						dst[static_cast<size_t>(py + (l >> 1)) * cmd.dstStride + px + (l & 1)] =
-							make_float4(sh.chan[0][l][t], sh.chan[1][l][t], sh.chan[2][l][t], 0.0f); } } }
-				break;
-			case kCmdStoreHalfFP: {
-				// Downsample(QFloat4Canvas -> FloatingPointCanvas) (rglr_algorithm.cxx:118-141): one output
-				// pixel per quad, ((p0 + p1) + p2) + p3 then * 0.25, alpha = 0
-				if (onScreen) {
-					float4* dst = static_cast<float4*>(cmd.dst);
-					float avg[3];
-#pragma unroll
-					for (int ch = 0; ch < 3; ++ch) {
-						avg[ch] = (((sh.chan[ch][0][t] + sh.chan[ch][1][t]) + sh.chan[ch][2][t]) + sh.chan[ch][3][t]) * 0.25f; }
-					dst[static_cast<size_t>(py >> 1) * cmd.dstStride + (px >> 1)] = make_float4(avg[0], avg[1], avg[2], 0.0f); } }
-				break;
-			case kCmdStoreQuadsFP: {
-				// Copy(QFloat4Canvas | QFloat3Canvas -> QFloat4Canvas) (rglr_algorithm.cxx:320-368): the quad-
-				// swizzled layout itself, 64 bytes per 2x2 quad {r[4], g[4], b[4], a[4]}.  The fourth plane is
-				// what the reference's tile holds there: depth (RB_COLOR_DEPTH), 1.0 (RB_RGBF32), or the
-				// clear colour's alpha (RB_RGBAF32: no program writes alpha)
-				if (onScreen) {
-					float4* dst = static_cast<float4*>(cmd.dst) + (static_cast<size_t>(py >> 1) * cmd.dstStride + (px >> 1)) * 4;
-#pragma unroll
-					for (int ch = 0; ch < 3; ++ch) {
-						dst[ch] = make_float4(sh.chan[ch][0][t], sh.chan[ch][1][t], sh.chan[ch][2][t], sh.chan[ch][3][t]); }
-					if (s.color0Type == 0) { dst[3] = make_float4(sh.chan[3][0][t], sh.chan[3][1][t], sh.chan[3][2][t], sh.chan[3][3][t]); }
-					else {
-						const float a = (s.color0Type == 1) ? 1.0f : s.clearColor[3];
-						dst[3] = make_float4(a, a, a, a); } } }
-				break;
-			case kCmdStoreDepth: {
-				if (onScreen) {
-					float* dst = static_cast<float*>(cmd.dst);
-					*reinterpret_cast<float2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_float2(sh.chan[3][0][t], sh.chan[3][1][t]);
-					*reinterpret_cast<float2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_float2(sh.chan[3][2][t], sh.chan[3][3][t]); } }
-				break;
-			default: break; } }
+		exec_cmds(sh, A, ci, di, t, px, py, onScreen);
 		if (di >= A.fp.ndraws) { break; }
 		PHASE(6);
 
@@ -1016,23 +1127,12 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 #define RSR_QUEUE_MIN_NB 96
 #endif
 		const bool queued = nb >= RSR_QUEUE_MIN_NB && ntiny * 2 > nb;
-		switch (key0 & 0xffu) {
-		case ProgAmy::id:          frags += draw_batch<ProgAmy>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgAlphaTexture::id: frags += draw_batch<ProgAlphaTexture>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgText::id:         frags += draw_batch<ProgText>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgDepth::id:        frags += draw_batch<ProgDepth>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgPattern::id:      frags += draw_batch<ProgPattern>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgMany::id:         frags += draw_batch<ProgMany>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgOBJ1::id:         frags += draw_batch<ProgOBJ1>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgOBJ2::id:         frags += draw_batch<ProgOBJ2>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgOBJ2S::id:        frags += draw_batch<ProgOBJ2S>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgEnvmap::id:       frags += draw_batch<ProgEnvmap>(sh, A, key0, nb, ox, oy, queued); break;
-		case ProgWireframe::id:    frags += draw_batch<ProgWireframe>(sh, A, key0, nb, ox, oy, queued); break;
-		default: break; }
+		frags += draw_batch_any(sh, A, key0, 0, nb, ox, oy, queued);
 		PHASE(8);
 		chunkPos += max(nb, 1); }
 	PHASE(9);
 
+#endif
 	// fragment statistics: one atomic per CTA
 	for (int o = 16; o > 0; o >>= 1) { frags += __shfl_down_sync(0xffffffffu, frags, o); }
 	__syncthreads();
