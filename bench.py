@@ -155,10 +155,27 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
     from rsr_b200 import scenes
     from rsr_b200.present import PresentedFrame
     from rsr_b200.subframes import SubframePlan
-    plan = SubframePlan(7680, 4320, world, 1920, 1080)
-    mine = plan.owned_by(rank)
     dev = f"cuda:{local_rank}"
     P = scenes.perspective(45.0, 7680 / 4320, 1.0, 400.0)
+    plan = SubframePlan(7680, 4320, world, 1920, 1080)
+    owners = None
+    if world > 1 and args.balance == "cost":
+        # sub-frames differ in cost (screen centre vs corners): rank 0 measures each once (device time of the frame's
+        # kernels) and deals them longest-first to the least loaded rank; every rank uses the same table
+        costs = torch.zeros(len(plan.subframes), dtype=torch.float64, device=dev)
+        if rank == 0:
+            gpu.set_profiling(1)
+            for sf in plan.subframes:
+                scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf))
+                probe = gpu.Finish()
+                for _ in range(3):
+                    gpu.Submit(probe)
+                costs[sf.index] = gpu.stage_ms()["frame"]
+            gpu.set_profiling(0)
+        dist.broadcast(costs, src=0)
+        owners = SubframePlan.balance([float(c) for c in costs.tolist()], world)
+        plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
+    mine = plan.owned_by(rank)
     p2p = args.exchange == "p2p"
     gpu.set_overlap(True)            # sub-frames are independent frames: front end of the next one under the current tile kernel
     cur = torch.cuda.current_stream()
@@ -240,6 +257,7 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
                 "dtype": "f32+i32", "data": "synthetic",
                 "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
                            "subframes_per_rank": len(mine), "exchange": exchange,
+                           "ownership": "round robin" if owners is None else f"cost balanced (longest first): {owners}",
                            "submission": "retained sub-frame tables replayed" if retained else "recorded streams decoded and uploaded every frame",
                            "cache": "L2 flushed before every timed frame"},
                 "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks, "frame_checksum": checksum,
@@ -261,6 +279,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
+    ap.add_argument("--balance", default="cost", choices=["cost", "roundrobin"], help="c5 only: how sub-frames are dealt to the ranks")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5 only: how resolved pixels reach the presenting GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -42,7 +42,7 @@ class Subframe:
 class SubframePlan:
     """grid of equal sub-frames covering width x height, each <= max_w x max_h, owners round-robin"""
 
-    def __init__(self, width: int, height: int, world_size: int = 1, max_w: int = 1920, max_h: int = 1080):
+    def __init__(self, width: int, height: int, world_size: int = 1, max_w: int = 1920, max_h: int = 1080, owners=None):
         assert max_w <= MAX_DIM and max_h <= MAX_DIM
         self.width, self.height = width, height
         self.nx = -(-width // max_w)
@@ -55,7 +55,21 @@ class SubframePlan:
         for gy in range(self.ny):
             for gx in range(self.nx):
                 i = gy * self.nx + gx
-                self.subframes.append(Subframe(i, gx, gy, gx * self.sub_w, gy * self.sub_h, self.sub_w, self.sub_h, i % world_size))
+                owner = i % world_size if owners is None else int(owners[i])
+                assert 0 <= owner < world_size
+                self.subframes.append(Subframe(i, gx, gy, gx * self.sub_w, gy * self.sub_h, self.sub_w, self.sub_h, owner))
+
+    @staticmethod
+    def balance(costs, world_size: int):
+        """owners for sub-frames of the given costs (e.g. measured device time): longest processing time first,
+        each sub-frame to the currently least loaded rank -- sub-frames of a scene differ a lot in cost"""
+        load = [0.0] * world_size
+        owners = [0] * len(costs)
+        for i in sorted(range(len(costs)), key=lambda k: -costs[k]):
+            r = min(range(world_size), key=lambda k: (load[k], k))
+            owners[i] = r
+            load[r] += costs[i]
+        return owners
 
     def owned_by(self, rank: int):
         return [s for s in self.subframes if s.owner == rank]

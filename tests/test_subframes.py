@@ -122,3 +122,17 @@ def test_stress_scenes_match_the_reference(which, ref_gpu, cuda_gpu):
                 "c4_small": (scenes.FillStressScene(layers=4, size=(640, 360), tex_dim=512), (640, 360)),
                 "c4_front_to_back": (scenes.FillStressScene(layers=4, size=(640, 360), tex_dim=512, front_to_back=True), (640, 360))}[which]
     assert_identical(render_both(sc, size, ref_gpu, cuda_gpu), which)
+
+
+def test_cost_balanced_ownership():
+    """longest-processing-time-first dealing: every sub-frame has exactly one owner and the heaviest rank is no
+    worse than with round robin"""
+    costs = [5.0, 1.0, 1.0, 5.0, 1.0, 9.0, 9.0, 1.0, 1.0, 9.0, 9.0, 1.0, 5.0, 1.0, 1.0, 5.0]
+    for world in (2, 4, 8):
+        owners = SubframePlan.balance(costs, world)
+        assert len(owners) == 16 and set(owners) == set(range(world))
+        load = [sum(c for c, o in zip(costs, owners) if o == r) for r in range(world)]
+        rr = [sum(c for i, c in enumerate(costs) if i % world == r) for r in range(world)]
+        assert max(load) <= max(rr)
+        plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
+        assert sorted(s.index for r in range(world) for s in plan.owned_by(r)) == list(range(16))
