@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
-    ap.add_argument("--balance", default="cost", choices=["cost", "roundrobin"], help="c5 only: how sub-frames are dealt to the ranks")
+    ap.add_argument("--balance", default="roundrobin", choices=["cost", "roundrobin"], help="c5 only: how sub-frames are dealt to the ranks")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5 only: how resolved pixels reach the presenting GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
