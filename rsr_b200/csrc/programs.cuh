@@ -73,6 +73,39 @@ __device__ __forceinline__ int level_of_detail(float u0, float u1, float v0, flo
 	const float sqd = dux * dux + dvx * dvx;
 	return (static_cast<int>(f2u(sqd)) - (127 << 23)) >> 24; }
 
+// one bilinear blend (rglr_texture_sampler.cxx:262-286): ((t00*w00 + t10*w10) + t01*w01) + t11*w11, two channels per packed pair
+__device__ __forceinline__ void blend_taps(const float4 p00, const float4 p10, const float4 p01, const float4 p11,
+                                           const float a00, const float a10, const float a01, const float a11,
+                                           float& r, float& g, float& b, float& a) {
+	const f2 rg = add2(add2(add2(mul2(mk2(p00.x, p00.y), a00), mul2(mk2(p10.x, p10.y), a10)), mul2(mk2(p01.x, p01.y), a01)),
+	                   mul2(mk2(p11.x, p11.y), a11));
+	const f2 ba = add2(add2(add2(mul2(mk2(p00.z, p00.w), a00), mul2(mk2(p10.z, p10.w), a10)), mul2(mk2(p01.z, p01.w), a01)),
+	                   mul2(mk2(p11.z, p11.w), a11));
+	r = lo2(rg); g = hi2(rg); b = lo2(ba); a = hi2(ba); }
+
+// The 16 taps of a 2x2 quad collapse to a 3x3 texel footprint when neighbouring pixels are one texel apart
+// (1:1 mapping and magnification): nine loads instead of sixteen, same texels, same weights, same arithmetic.
+// UP = false: the lower pixel pair's first tap row is the upper pair's second one; UP = true: the other way round.
+template <bool UP>
+__device__ __forceinline__ bool taps_share_rows(const uint32_t (&ofs)[4][4]) {
+	constexpr int t0 = UP ? 2 : 0, t1 = UP ? 3 : 1, b0 = UP ? 0 : 2, b1 = UP ? 1 : 3;
+	return (ofs[t1][0] == ofs[t0][1]) && (ofs[t1][2] == ofs[t0][3]) && (ofs[b1][0] == ofs[b0][1]) && (ofs[b1][2] == ofs[b0][3]) &&
+	       (ofs[b0][0] == ofs[t0][2]) && (ofs[b0][1] == ofs[t0][3]) && (ofs[b1][1] == ofs[t1][3]); }
+
+template <bool UP>
+__device__ __forceinline__ void blend_shared_rows(const float4* __restrict__ tex, const uint32_t (&ofs)[4][4],
+                                                  const f2 (&w00)[2], const f2 (&w10)[2], const f2 (&w01)[2], const f2 (&w11)[2],
+                                                  float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4]) {
+	constexpr int t0 = UP ? 2 : 0, t1 = UP ? 3 : 1, b0 = UP ? 0 : 2, b1 = UP ? 1 : 3;
+	const float4 A0 = __ldg(tex + ofs[t0][0]), A1 = __ldg(tex + ofs[t0][1]), A2 = __ldg(tex + ofs[t1][1]);
+	const float4 B0 = __ldg(tex + ofs[t0][2]), B1 = __ldg(tex + ofs[t0][3]), B2 = __ldg(tex + ofs[t1][3]);
+	const float4 C0 = __ldg(tex + ofs[b0][2]), C1 = __ldg(tex + ofs[b0][3]), C2 = __ldg(tex + ofs[b1][3]);
+	auto wt = [&](const f2 (&w)[2], int l) { return (l & 1) ? hi2(w[l >> 1]) : lo2(w[l >> 1]); };
+	blend_taps(A0, A1, B0, B1, wt(w00, t0), wt(w10, t0), wt(w01, t0), wt(w11, t0), r[t0], g[t0], b[t0], a[t0]);
+	blend_taps(A1, A2, B1, B2, wt(w00, t1), wt(w10, t1), wt(w01, t1), wt(w11, t1), r[t1], g[t1], b[t1], a[t1]);
+	blend_taps(B0, B1, C0, C1, wt(w00, b0), wt(w10, b0), wt(w01, b0), wt(w11, b0), r[b0], g[b0], b[b0], a[b0]);
+	blend_taps(B1, B2, C1, C2, wt(w00, b1), wt(w10, b1), wt(w01, b1), wt(w11, b1), r[b1], g[b1], b[b1], a[b1]); }
+
 __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[4], const float (&v)[4],
                                             float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4]) {
 	if (tu.kind == 0) {
@@ -153,6 +186,10 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 	for (int l = 1; l < 4; ++l) {
 #pragma unroll
 		for (int k = 0; k < 4; ++k) { asm volatile("prefetch.global.L1 [%0];" :: "l"(tu.texels + ofs[l][k])); } }
+#endif
+#if RSR_TAP_MODE == 3
+	if (taps_share_rows<false>(ofs)) { blend_shared_rows<false>(tu.texels, ofs, w00, w10, w01, w11, r, g, b, a); return; }
+	if (taps_share_rows<true>(ofs)) { blend_shared_rows<true>(tu.texels, ofs, w00, w10, w01, w11, r, g, b, a); return; }
 #endif
 #if RSR_TAP_MODE == 1
 	float4 tap[4][4];
