@@ -208,6 +208,11 @@ struct rsrcu_ctx {
 	uint64_t lastH2D{0}, lastD2H{0};
 	std::chrono::steady_clock::time_point tBegin{};
 	uint64_t recordNs{0}, submitNs{0};
+	// RSRCU_HOST_PROF=1: where the submitting thread's time goes (averages printed by rsrcu_destroy)
+	bool hostProf{false};
+	uint64_t hp[6]{};   // layout, tables, plan, reserve, launches, read-back enqueue (ns, summed)
+	uint64_t hpFrames{0};
+	std::chrono::steady_clock::time_point hpLast{};
 };
 
 namespace {
@@ -488,6 +493,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	bin.lists = static_cast<uint2*>(w.lists.ptr);
 	bin.large = static_cast<LargeItem*>(w.largeItems.ptr);
 
+	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[3] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
 	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
@@ -548,6 +554,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], tileStream)); }
 	if (c->overlap) { CU(cudaEventRecord(c->evTileDone[si], tileStream)); }
 
+	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[4] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
 	c->lastH2D = uploadBytes;
 	c->lastD2H = 0;
 	CU(cudaEventRecord(c->evRendered[c->outSlot], tileStream));
@@ -560,6 +567,8 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	// the read-back goes to the copy stream right away (it waits for evRendered there): the upload is a kernel
 	// (K0), so a queued device->host copy cannot hold up the next frame's upload on a copy engine
 	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
+	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[5] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
+	if (c->hostProf) { ++c->hpFrames; }
 	return RSRCU_OK; }
 
 
@@ -599,6 +608,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 		delete c;
 		return fail(RSRCU_ERR_UNSUPPORTED, "host rcpps/rsqrtps do not follow the table model (%llu mismatches); "
 		            "bit-exact parity with the reference on this CPU is not possible", static_cast<unsigned long long>(mismatches)); }
+	c->hostProf = std::getenv("RSRCU_HOST_PROF") != nullptr;
 	if (std::getenv("RSRCU_TRACE")) {
 		c->trace = true;
 		c->traceEv.resize(4 * 64);
@@ -623,6 +633,10 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	cudaStreamSynchronize(c->frontStream);
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copyStream);
+	if (c->hostProf && c->hpFrames) {
+		const double n = static_cast<double>(c->hpFrames) * 1e3;
+		std::fprintf(stderr, "rsrcu host profile over %llu frames (us per frame): layout %.1f, tables %.1f, plan %.1f, reserve %.1f, launches %.1f, read-back enqueue %.1f\n",
+		             static_cast<unsigned long long>(c->hpFrames), c->hp[0] / n, c->hp[1] / n, c->hp[2] / n, c->hp[3] / n, c->hp[4] / n, c->hp[5] / n); }
 	if (c->trace) {
 		for (int f = 0; f + 1 < c->traceFrames; ++f) {
 			float t[4] = {0, 0, 0, 0};
@@ -912,6 +926,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	CU(cudaSetDevice(c->device));
 	c->inFrame = false;
 	const auto tSubmit = std::chrono::steady_clock::now();
+	c->hpLast = tSubmit;
 	c->recordNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(tSubmit - c->tBegin).count());
 
 	const int W = c->width, H = c->height;
@@ -959,6 +974,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	fp.clipCapacity = c->clipCapacity;
 	fp.listCapacity = c->listCapacity;
 
+	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[0] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
 	// ---- frame tables into the arena (state / draw tables need final device addresses) -----
 	size_t offStates = 0, offDraws = 0, offCmds = 0, offVBlocks = 0, offPBlocks = 0;
 	const size_t nVBlocks = static_cast<size_t>((vjobs + 255) / 256) + 1, nPBlocks = static_cast<size_t>((pjobs + 255) / 256) + 1;
@@ -997,6 +1013,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 			pb[b] = static_cast<uint32_t>(dp); } }
 	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
 
+	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[1] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
 	FramePlan& plan = c->lastPlan;
 	plan.fp = fp;
 	plan.offStates = offStates; plan.offDraws = offDraws; plan.offCmds = offCmds; plan.offVBlocks = offVBlocks; plan.offPBlocks = offPBlocks;
@@ -1014,6 +1031,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	plan.trianglesSubmitted = c->trianglesSubmitted;
 	plan.valid = true;
 	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
+	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[2] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
 	c->lastArena = c->cur;
 	const int r = launchFrame(c, plan, static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr), c->arenas[c->cur].host, c->arenas[c->cur].used, c->cur);
 	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tSubmit).count());
