@@ -35,7 +35,8 @@ extern "C" {
 #define RSRCU_ERR_NO_PROGRAM     4   /* (program id, fragment state key) not in the dispatch table;
                                         the reference calls std::exit(1) here (rglv_gpu.cxx:199-202) */
 #define RSRCU_ERR_UNSUPPORTED    5   /* state the reference itself cannot render (e.g. >2048 px) */
-#define RSRCU_ERR_OVERFLOW       6   /* a device-side buffer (clip records) overflowed */
+#define RSRCU_ERR_OVERFLOW       6   /* a device-side buffer still overflows after the library grew it and rendered
+                                        the frame again several times (rsrcu_sync / rsrcu_sync_frame retry internally) */
 
 /* constants: same numeric values as src/rgl/rglv/rglv_gl.hxx:20-62 */
 #define RSRCU_GL_FRONT 1
@@ -184,7 +185,9 @@ int rsrcu_store_depth(rsrcu_ctx* ctx, float* dst);
  * store destinations on the context's stream, and returns without waiting. */
 int rsrcu_end_frame(rsrcu_ctx* ctx);
 
-/* Waits for the frame; reports device-side errors (clip buffer overflow...) */
+/* Waits for every submitted frame.  A frame whose tile lists, clip records or large-item queue did not fit is
+ * never delivered truncated: the buffer is grown and the frame is launched again from its device-resident tables
+ * (RsrStats::frames_retried counts those launches). */
 int rsrcu_sync(rsrcu_ctx* ctx);
 
 /* Retained frames.  The reference records every frame anew; a caller that submits the same recorded
@@ -214,7 +217,8 @@ int rsrcu_set_overlap(rsrcu_ctx* ctx, int enabled);
  * landed in its store destinations, so frame N's read-back overlaps the recording and the kernels of
  * the frames after it -- the GPU counterpart of the reference's doubleBuffer mode
  * (rglv_gpu.cxx:16,111-112).  A store destination must not be reused before its frame has been
- * waited for.  Does not report device-side errors. */
+ * waited for.  Like rsrcu_sync it launches a frame again whose device-side buffers overflowed (the frame's
+ * tables stay on the device until three frames later), so the destination always holds the complete frame. */
 int rsrcu_sync_frame(rsrcu_ctx* ctx, int lag);
 
 /* ---- packed command stream ---------------------------------------------------------------------
@@ -276,6 +280,7 @@ typedef struct RsrStats {
 	uint64_t list_chunks_key_range; /* ... and by key ranges + bitonic sort (long lists) */
 	uint64_t host_record_ns;        /* host time spent recording the frame (begin_frame .. end_frame, all calls) */
 	uint64_t host_submit_ns;        /* host time spent in rsrcu_end_frame (tables, upload, launches) */
+	uint64_t frames_retried;        /* cumulative: frames launched again because a device-side buffer overflowed */
 } RsrStats;
 int rsrcu_get_stats(rsrcu_ctx* ctx, RsrStats* out);
 

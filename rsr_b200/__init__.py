@@ -74,7 +74,7 @@ class RsrState(C.Structure):
 class RsrStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("triangles_submitted", "triangles_binned", "triangles_clipped",
                                            "bin_entries", "fragments_shaded", "kernel_launches", "h2d_bytes", "d2h_bytes",
-                                           "list_chunks_run_merge", "list_chunks_key_range", "host_record_ns", "host_submit_ns")]
+                                           "list_chunks_run_merge", "list_chunks_key_range", "host_record_ns", "host_submit_ns", "frames_retried")]
 
 
 _lib = None
@@ -282,17 +282,8 @@ class GPU:
         """GPU::Run on a recorded frame: one C-ABI call (rsrcu_run_stream)"""
         self._check(self.L.rsrcu_run_stream(self.h, rec.buf, len(rec.data)))
         if sync:
-            for attempt in range(6):
-                try:
-                    self.Sync()
-                    break
-                except RsrError as e:
-                    if e.code != 6 or attempt == 5:
-                        raise
-                    # a device buffer (tile lists, clip records, large-item queue) was too small, or a tile
-                    # took more queued large triangles than it can hold; the library has adjusted itself --
-                    # render the same frame again
-                    self._check(self.L.rsrcu_run_stream(self.h, rec.buf, len(rec.data)))
+            # (a frame whose device-side buffers overflowed is grown for and launched again inside rsrcu_sync)
+            self.Sync()
 
     def Run(self, manage_workers: bool = True, sync: bool = True):
         """GPU::Run: end of recording -> kernels; `sync` waits and fills the store destinations"""

@@ -425,7 +425,9 @@ __device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t o
 	const bool single = small && ntile == 1 && fp.groups == 1;   // (frames with several cells per tile: see the walk below)
 	if (__any_sync(0xffffffffu, single)) {
 		const uint32_t cell = single ? static_cast<uint32_t>((ty0 * fp.tilesX + tx0) * fp.groups) + group : (0xffffff00u | lane);
-		const unsigned peers = __match_any_sync(0xffffffffu, cell);
+		// (fan triangles carry keys above every unclipped key of their draw: they must not share a run with the
+		// unclipped lanes around them, or the run would not ascend -- the fan bit is part of the match key)
+		const unsigned peers = __match_any_sync(0xffffffffu, single ? (cell | (code & kFanIdBit)) : cell);
 		const int leader = __ffs(peers) - 1;
 		const uint32_t rank = __popc(peers & ltMask);
 		if (!FILL) {
@@ -453,10 +455,10 @@ __device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t o
 			const uint32_t tile = __reduce_min_sync(0xffffffffu, cur);
 			if (tile == 0xffffffffu) { break; }
 			const int leader = __ffs(__ballot_sync(0xffffffffu, cur == tile)) - 1;
-			const uint32_t g = __shfl_sync(0xffffffffu, group, leader);   // (lanes differ in group only among clip fans)
-			const bool mine = (cur == tile) && (group == g);
+			const uint32_t g = __shfl_sync(0xffffffffu, group | (code & kFanIdBit), leader);   // (lanes differ in group only among clip fans; fans never share a run with unclipped lanes)
+			const bool mine = (cur == tile) && ((group | (code & kFanIdBit)) == g);
 			const unsigned m = __ballot_sync(0xffffffffu, mine);
-			const uint32_t cell = tile * static_cast<uint32_t>(fp.groups) + g;
+			const uint32_t cell = tile * static_cast<uint32_t>(fp.groups) + (g & ~kFanIdBit);
 			if (!FILL) {
 				if (static_cast<int>(lane) == leader) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(m))); } }
 			else {

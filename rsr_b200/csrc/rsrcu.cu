@@ -127,12 +127,22 @@ struct FramePlan {
 	FrameCmd icmd[kInlineCmds]{};
 	CmdState icmdState[kInlineCmds]{};
 	std::vector<PendingCopy> copies;
+	void* tcDev{nullptr}; int tcStride{0};   // the frame's last true-colour store (rsrcu_device_truecolor)
+	int storesUsed{0};                       // store targets of the context's pool the frame's commands point into
 	uint64_t trianglesSubmitted{0}; };
 
 struct rsrcu_frame {
 	FramePlan plan;
 	void* devArena{nullptr};
+	std::vector<DevBuf> stores;              // a retained frame owns its store targets (taken from the context's pool)
 	int device{0}; };
+
+// what was launched into a slot of the ring (counters, store targets, arena): enough to launch it again when its
+// read-back shows that a device-side buffer overflowed
+struct Launched {
+	const FramePlan* plan{nullptr};
+	const uint8_t* arenaDev{nullptr};
+	bool checked{true}; };
 
 struct rsrcu_ctx {
 	int device{0};
@@ -178,9 +188,9 @@ struct rsrcu_ctx {
 	std::vector<PendingCopy> copies;
 	uint64_t trianglesSubmitted{0};
 
-	UploadArena arenas[2];            // double-buffered: frame N+1 records while frame N's upload is in flight
-	cudaEvent_t arenaFree[2]{};
-	int cur{0};
+	UploadArena arenas[kSlots];       // ring, indexed like the store targets (outSlot): frame N+1 records while frame N's upload is in flight, and the
+	                                  // device mirror of a frame stays intact until three frames later (an overflowed frame can be launched again)
+	cudaEvent_t arenaFree[kSlots]{};
 	std::unordered_map<const void*, StaticAlloc> staticCache;
 	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr});
 
@@ -192,10 +202,17 @@ struct rsrcu_ctx {
 	cudaEvent_t evFrontDone[2]{}, evTileDone[2]{};
 	bool overlap{false};
 	uint64_t frameNo{0};
-	FramePlan lastPlan;
-	int lastArena{0};
+	FramePlan slotPlan[kSlots];          // plan of the frame recorded into each slot (the last one: slotPlan[lastArena])
+	Launched launched[kSlots];
+	int lastArena{-1};
+	uint64_t framesRetried{0};
 	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
-	DevBuf tcOut[kSlots], fpOut[kSlots], halfOut[kSlots], quadsOut[kSlots], depthOut[kSlots];
+	// store targets: one device buffer per store command of a frame (a frame may hold several stores of one kind with
+	// draws in between: each keeps its own image), a pool per slot of the ring, reused by the frames that follow
+	std::vector<DevBuf> storePool[kSlots];
+	int storesUsed{0};
+	void* tcDev{nullptr};              // recording: the frame's last true-colour target
+	void* shownTcDev{nullptr}; int shownTcStride{0};   // of the frame launched last (rsrcu_device_truecolor)
 	uint32_t clipCapacity{1u << 16};
 	uint32_t listCapacity{1u << 24};
 	uint32_t largeCapacity{1u << 16};
@@ -308,7 +325,7 @@ void mat4Transpose(const float* m, float* out) {
 
 const void* resolve(const rsrcu_ctx* c, const DevRef& r) {
 	if (r.null) { return nullptr; }
-	if (r.arena) { return static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr) + r.off; }
+	if (r.arena) { return static_cast<const uint8_t*>(c->arenas[c->outSlot].dev.ptr) + r.off; }
 	return r.abs; }
 
 template <class T>
@@ -344,7 +361,7 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 		out.null = false; out.arena = false; out.abs = d;
 		return RSRCU_OK; }
 	size_t off = 0;
-	CU(c->arenas[c->cur].push(host, bytes, off));
+	CU(c->arenas[c->outSlot].push(host, bytes, off));
 	out.null = false; out.arena = true; out.off = off;
 	return RSRCU_OK; }
 
@@ -450,7 +467,12 @@ int flushDeferredCopies(rsrcu_ctx* c) {
 // nothing for a retained frame whose tables already live on the device, plus the zeroed control block), K1-K6,
 // and the read-back.  `arenaDev` is where the tables live on the device.
 int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, const uint8_t* hostArena, size_t uploadBytes, int arenaIdx) {
-	const FrameParams& fp = plan.fp;
+	// (the capacities are the context's current ones: a frame launched again after an overflow, or a retained frame
+	// replayed after one, runs with the grown buffers)
+	FrameParams fp = plan.fp;
+	fp.largeCapacity = c->largeCapacity; fp.largeTiles = c->largeTiles; fp.clipCapacity = c->clipCapacity; fp.listCapacity = c->listCapacity;
+	c->launched[c->outSlot] = Launched{&plan, arenaDev, false};
+	c->shownTcDev = plan.tcDev; c->shownTcStride = plan.tcStride;
 	const int ntiles = fp.tilesX * fp.tilesY;
 	const uint64_t ptvbF4 = plan.ptvbF4, nvertsTotal = plan.nvertsTotal, pjobs = plan.pjobs;
 	const size_t offStates = plan.offStates, offDraws = plan.offDraws, offCmds = plan.offCmds, offVBlocks = plan.offVBlocks, offPBlocks = plan.offPBlocks;
@@ -646,9 +668,9 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	for (auto& w : c->sets) {
 		for (DevBuf* b : { &w.ptvb, &w.vflags, &w.triInfo, &w.triRecs, &w.clipRecs, &w.tileBase, &w.cellRel, &w.tileTotal, &w.tileOrder, &w.lists, &w.largeItems }) { b->release(); } }
-	for (DevBuf* b : { &c->counters[0], &c->counters[1], &c->counters[2], &c->tcOut[0], &c->tcOut[1], &c->tcOut[2], &c->fpOut[0], &c->fpOut[1], &c->fpOut[2], &c->halfOut[0], &c->halfOut[1], &c->halfOut[2], &c->quadsOut[0], &c->quadsOut[1], &c->quadsOut[2],
-	                   &c->depthOut[0], &c->depthOut[1], &c->depthOut[2] }) { b->release(); }
-	c->arenas[0].release(); c->arenas[1].release();
+	for (auto& b : c->counters) { b.release(); }
+	for (auto& pool : c->storePool) { for (auto& b : pool) { b.release(); } }
+	for (auto& a : c->arenas) { a.release(); }
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
 	if (c->hostCounters) { cudaFreeHost(c->hostCounters); }
@@ -699,9 +721,8 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	if (tileWBlocks <= 0 || tileHBlocks <= 0) { return fail(RSRCU_ERR_INVALID, "tile blocks must be positive"); }
 	CU(cudaSetDevice(c->device));
 	// take the other staging arena; wait only until the frame that last used it has been uploaded
-	c->cur ^= 1;
 	c->outSlot = (c->outSlot + 1) % kSlots;
-	CU(cudaEventSynchronize(c->arenaFree[c->cur]));
+	CU(cudaEventSynchronize(c->arenaFree[c->outSlot]));
 	c->width = width; c->height = height;
 	const int rw = tileWBlocks * 8, rh = tileHBlocks * 8;
 	// the device tile must lie inside one reference tile to reproduce its start point exactly;
@@ -710,8 +731,10 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->refTileH = (rh % kTile == 0) ? rh : kTile;
 	c->postTileW = rw; c->postTileH = rh;
 	c->states.clear(); c->draws.clear(); c->cmds.clear(); c->cmdDstKind.clear(); c->copies.clear();
-	c->lastPlan.valid = false;
-	c->arenas[c->cur].used = 0;
+	c->slotPlan[c->outSlot].valid = false;
+	c->launched[c->outSlot] = Launched{};
+	c->storesUsed = 0; c->tcDev = nullptr;
+	c->arenas[c->outSlot].used = 0;
 	c->trianglesSubmitted = 0;
 	c->haveState = false; c->stateDirty = true;
 	for (auto& b : c->curBuffers) { b = DevRef{}; }
@@ -762,6 +785,15 @@ int rsrcu_bind_depth_texture(rsrcu_ctx* c, const float* host, int dim, int uploa
 	c->stateDirty = true;
 	return RSRCU_OK; }
 
+// the device target of the frame's next store command: its own buffer from the slot's pool
+static cudaError_t takeStore(rsrcu_ctx* c, size_t bytes, void*& out) {
+	auto& pool = c->storePool[c->outSlot];
+	if (static_cast<size_t>(c->storesUsed) >= pool.size()) { pool.emplace_back(); }
+	DevBuf& b = pool[c->storesUsed];
+	const cudaError_t e = b.reserve(bytes);
+	if (e == cudaSuccess) { ++c->storesUsed; out = b.ptr; }
+	return e; }
+
 static int pushCmd(rsrcu_ctx* c, int type, int arg, void* dst, int stride, int kind) {
 	int r = snapshotState(c);
 	if (r != RSRCU_OK) { return r; }
@@ -810,6 +842,7 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	d.instanced = instanced ? 1 : 0;
 	// vertex extent: explicit buffer length (slot 0) or, for arrays, the count
 	size_t nverts = 0;
+	if (!arrays && !indices) { return fail(RSRCU_ERR_INVALID, "null index pointer"); }
 	if (arrays) { nverts = static_cast<size_t>(prims) * 3; }
 	else {
 		nverts = hs.bufferFloats[0];
@@ -833,7 +866,6 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	d.batchKey = static_cast<uint32_t>(programId & 0xff) | (static_cast<uint32_t>(key) << 8);
 	d.cullBits = (hs.ds.cullingEnabled ? 1u : 0u) | ((static_cast<uint32_t>(hs.ds.cullFace) & 3u) << 1) | ((key & 1) ? 8u : 0u);
 	if (!arrays) {
-		if (!indices) { return fail(RSRCU_ERR_INVALID, "null index pointer"); }
 		r = uploadData(c, indices, static_cast<size_t>(prims) * 3 * sizeof(uint16_t), upload, hd.indices);
 		if (r != RSRCU_OK) { return r; } }
 	c->trianglesSubmitted += d.N;
@@ -853,12 +885,13 @@ int rsrcu_store_color_tc(rsrcu_ctx* c, int gamma, uint32_t* dst, int width, int 
 	if (c->haveState && !bltProgramInstalled(c->curStatePtr->program_id)) {
 		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d (src/viewer/shaders.cxx:57-67)", c->curStatePtr->program_id); }
 	CU(cudaSetDevice(c->device));
-	CU(c->tcOut[c->outSlot].reserve(static_cast<size_t>(width) * height * 4));
-	c->tcStride = width;
-	int r = pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, c->tcOut[c->outSlot].ptr, width, 1);
+	void* dev = nullptr;
+	CU(takeStore(c, static_cast<size_t>(width) * height * 4, dev));
+	c->tcStride = width; c->tcDev = dev;
+	int r = pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, dev, width, 1);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->tcOut[c->outSlot].ptr, static_cast<size_t>(width) * 4, static_cast<size_t>(height),
+		c->copies.push_back(PendingCopy{dst, dev, static_cast<size_t>(width) * 4, static_cast<size_t>(height),
 		                                static_cast<size_t>(stridePx) * 4, static_cast<size_t>(width) * 4}); }
 	return RSRCU_OK; }
 
@@ -868,6 +901,7 @@ int rsrcu_store_color_tc_device(rsrcu_ctx* c, int gamma, void* deviceDst, int wi
 	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
 	if (c->haveState && !bltProgramInstalled(c->curStatePtr->program_id)) {
 		return fail(RSRCU_ERR_NO_PROGRAM, "no blt dispatch entry for program %d", c->curStatePtr->program_id); }
+	c->tcStride = stridePx; c->tcDev = deviceDst;
 	return pushCmd(c, kCmdStoreTC, gamma ? 1 : 0, deviceDst, stridePx, 1); }
 
 int rsrcu_enable_peer_access(rsrcu_ctx* c, int peerDevice) {
@@ -888,12 +922,12 @@ int rsrcu_store_color_fp(rsrcu_ctx* c, float* dst, int width, int height, int st
 	const int wantW = half ? c->width / 2 : c->width, wantH = half ? c->height / 2 : c->height;
 	if (width != wantW || height != wantH) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != %s target %dx%d", width, height, half ? "half" : "full", wantW, wantH); }
 	CU(cudaSetDevice(c->device));
-	DevBuf& out = half ? c->halfOut[c->outSlot] : c->fpOut[c->outSlot];
-	CU(out.reserve(static_cast<size_t>(width) * height * 16));
-	int r = pushCmd(c, half ? kCmdStoreHalfFP : kCmdStoreFP, 0, out.ptr, width, 2);
+	void* dev = nullptr;
+	CU(takeStore(c, static_cast<size_t>(width) * height * 16, dev));
+	int r = pushCmd(c, half ? kCmdStoreHalfFP : kCmdStoreFP, 0, dev, width, 2);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, out.ptr, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
+		c->copies.push_back(PendingCopy{dst, dev, static_cast<size_t>(width) * 16, static_cast<size_t>(height),
 		                                static_cast<size_t>(stridePx) * 16, static_cast<size_t>(width) * 16}); }
 	return RSRCU_OK; }
 
@@ -903,21 +937,23 @@ int rsrcu_store_color_quads(rsrcu_ctx* c, float* dst, int width, int height, int
 	if (strideQuads < width / 2) { return fail(RSRCU_ERR_INVALID, "quad canvas stride %d < %d quads per row", strideQuads, width / 2); }
 	CU(cudaSetDevice(c->device));
 	const size_t rowBytes = static_cast<size_t>(width / 2) * 64, rows = static_cast<size_t>(height / 2);
-	CU(c->quadsOut[c->outSlot].reserve(rowBytes * rows));
-	int r = pushCmd(c, kCmdStoreQuadsFP, 0, c->quadsOut[c->outSlot].ptr, width / 2, 2);
+	void* dev = nullptr;
+	CU(takeStore(c, rowBytes * rows, dev));
+	int r = pushCmd(c, kCmdStoreQuadsFP, 0, dev, width / 2, 2);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->quadsOut[c->outSlot].ptr, rowBytes, rows, static_cast<size_t>(strideQuads) * 64, rowBytes}); }
+		c->copies.push_back(PendingCopy{dst, dev, rowBytes, rows, static_cast<size_t>(strideQuads) * 64, rowBytes}); }
 	return RSRCU_OK; }
 
 int rsrcu_store_depth(rsrcu_ctx* c, float* dst) {
 	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
 	CU(cudaSetDevice(c->device));
-	CU(c->depthOut[c->outSlot].reserve(static_cast<size_t>(c->width) * c->height * 4));
-	int r = pushCmd(c, kCmdStoreDepth, 0, c->depthOut[c->outSlot].ptr, c->width, 3);
+	void* dev = nullptr;
+	CU(takeStore(c, static_cast<size_t>(c->width) * c->height * 4, dev));
+	int r = pushCmd(c, kCmdStoreDepth, 0, dev, c->width, 3);
 	if (r != RSRCU_OK) { return r; }
 	if (dst) {
-		c->copies.push_back(PendingCopy{dst, c->depthOut[c->outSlot].ptr, static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->height),
+		c->copies.push_back(PendingCopy{dst, dev, static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->height),
 		                                static_cast<size_t>(c->width) * 4, static_cast<size_t>(c->width) * 4}); }
 	return RSRCU_OK; }
 
@@ -978,16 +1014,16 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	// ---- frame tables into the arena (state / draw tables need final device addresses) -----
 	size_t offStates = 0, offDraws = 0, offCmds = 0, offVBlocks = 0, offPBlocks = 0;
 	const size_t nVBlocks = static_cast<size_t>((vjobs + 255) / 256) + 1, nPBlocks = static_cast<size_t>((pjobs + 255) / 256) + 1;
-	CU(c->arenas[c->cur].push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
-	CU(c->arenas[c->cur].push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
-	CU(c->arenas[c->cur].push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
-	CU(c->arenas[c->cur].push(nullptr, sizeof(uint32_t) * nVBlocks, offVBlocks));
-	CU(c->arenas[c->cur].push(nullptr, sizeof(uint32_t) * nPBlocks, offPBlocks));
-	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
+	CU(c->arenas[c->outSlot].push(nullptr, sizeof(DevState) * std::max<size_t>(1, c->states.size()), offStates));
+	CU(c->arenas[c->outSlot].push(nullptr, sizeof(DevDraw) * std::max<size_t>(1, c->draws.size()), offDraws));
+	CU(c->arenas[c->outSlot].push(nullptr, sizeof(FrameCmd) * std::max<size_t>(1, c->cmds.size()), offCmds));
+	CU(c->arenas[c->outSlot].push(nullptr, sizeof(uint32_t) * nVBlocks, offVBlocks));
+	CU(c->arenas[c->outSlot].push(nullptr, sizeof(uint32_t) * nPBlocks, offPBlocks));
+	CU(c->arenas[c->outSlot].dev.reserve(c->arenas[c->outSlot].used));
 
 	{
-		const uint8_t* arenaDev = static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr);
-		DevState* out = reinterpret_cast<DevState*>(c->arenas[c->cur].host + offStates);
+		const uint8_t* arenaDev = static_cast<const uint8_t*>(c->arenas[c->outSlot].dev.ptr);
+		DevState* out = reinterpret_cast<DevState*>(c->arenas[c->outSlot].host + offStates);
 		for (size_t i = 0; i < c->states.size(); ++i) {
 			const HostState& hs = c->states[i];
 			std::memcpy(out + i, &hs.ds, sizeof(DevState));
@@ -998,11 +1034,11 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	for (size_t i = 0; i < c->draws.size(); ++i) {
 		DevDraw d = c->draws[i].d;
 		d.indices = static_cast<const uint16_t*>(resolve(c, c->draws[i].indices));
-		std::memcpy(c->arenas[c->cur].host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
+		std::memcpy(c->arenas[c->outSlot].host + offDraws + i * sizeof(DevDraw), &d, sizeof(d)); }
 	{
 		// draw of the first job of every block of 256 vertex / triangle jobs (find_draw, kernels.cuh)
-		uint32_t* vb = reinterpret_cast<uint32_t*>(c->arenas[c->cur].host + offVBlocks);
-		uint32_t* pb = reinterpret_cast<uint32_t*>(c->arenas[c->cur].host + offPBlocks);
+		uint32_t* vb = reinterpret_cast<uint32_t*>(c->arenas[c->outSlot].host + offVBlocks);
+		uint32_t* pb = reinterpret_cast<uint32_t*>(c->arenas[c->outSlot].host + offPBlocks);
 		size_t dv = 0, dp = 0;
 		const size_t nd = c->draws.size();
 		for (size_t b = 0; b < nVBlocks; ++b) {
@@ -1011,14 +1047,14 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		for (size_t b = 0; b < nPBlocks; ++b) {
 			while (dp + 1 < nd && c->draws[dp + 1].d.pjobBase <= b * 256) { ++dp; }
 			pb[b] = static_cast<uint32_t>(dp); } }
-	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->cur].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
+	if (!c->cmds.empty()) { std::memcpy(c->arenas[c->outSlot].host + offCmds, c->cmds.data(), sizeof(FrameCmd) * c->cmds.size()); }
 
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[1] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
-	FramePlan& plan = c->lastPlan;
+	FramePlan& plan = c->slotPlan[c->outSlot];
 	plan.fp = fp;
 	plan.offStates = offStates; plan.offDraws = offDraws; plan.offCmds = offCmds; plan.offVBlocks = offVBlocks; plan.offPBlocks = offPBlocks;
 	plan.ptvbF4 = ptvbF4; plan.nvertsTotal = nvertsTotal; plan.pjobs = pjobs;
-	plan.arenaBytes = c->arenas[c->cur].used;
+	plan.arenaBytes = c->arenas[c->outSlot].used;
 	plan.ncmdInline = 0;
 	for (int i = 0; i < kInlineCmds && i < fp.ncmds; ++i) {
 		plan.icmd[i] = c->cmds[i];
@@ -1028,25 +1064,30 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		cs.clearDepth = ds.clearDepth; cs.programId = ds.programId; cs.uniform0 = ds.uniforms[0]; cs.color0Type = ds.color0Type;
 		++plan.ncmdInline; }
 	plan.copies = c->copies;
+	plan.tcDev = c->tcDev; plan.tcStride = c->tcStride; plan.storesUsed = c->storesUsed;
 	plan.trianglesSubmitted = c->trianglesSubmitted;
 	plan.valid = true;
-	CU(c->arenas[c->cur].dev.reserve(c->arenas[c->cur].used));
+	CU(c->arenas[c->outSlot].dev.reserve(c->arenas[c->outSlot].used));
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[2] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
-	c->lastArena = c->cur;
-	const int r = launchFrame(c, plan, static_cast<const uint8_t*>(c->arenas[c->cur].dev.ptr), c->arenas[c->cur].host, c->arenas[c->cur].used, c->cur);
+	c->lastArena = c->outSlot;
+	const int r = launchFrame(c, plan, static_cast<const uint8_t*>(c->arenas[c->outSlot].dev.ptr), c->arenas[c->outSlot].host, c->arenas[c->outSlot].used, c->outSlot);
 	c->submitNs = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tSubmit).count());
 	return r; }
 
 int rsrcu_retain_frame(rsrcu_ctx* c, rsrcu_frame** out) {
 	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }
-	if (c->inFrame || !c->lastPlan.valid) { return fail(RSRCU_ERR_INVALID, "rsrcu_retain_frame: no submitted frame (call it after rsrcu_end_frame, before the next rsrcu_begin_frame)"); }
-	if (c->lastPlan.fp.ncmds > kInlineCmds) { return fail(RSRCU_ERR_UNSUPPORTED, "a retained frame holds at most %d clear / store commands", kInlineCmds); }
+	if (c->inFrame || c->lastArena < 0 || !c->slotPlan[c->lastArena].valid) { return fail(RSRCU_ERR_INVALID, "rsrcu_retain_frame: no submitted frame (call it after rsrcu_end_frame, before the next rsrcu_begin_frame)"); }
+	if (c->slotPlan[c->lastArena].fp.ncmds > kInlineCmds) { return fail(RSRCU_ERR_UNSUPPORTED, "a retained frame holds at most %d clear / store commands", kInlineCmds); }
 	CU(cudaSetDevice(c->device));
 	const UploadArena& ar = c->arenas[c->lastArena];
-	const FramePlan& plan = c->lastPlan;
+	const FramePlan& plan = c->slotPlan[c->lastArena];
 	auto* f = new rsrcu_frame();
 	f->plan = plan;
 	f->device = c->device;
+	// the frame's store targets leave the context's pool with it: later frames (of any size) get fresh buffers
+	{
+		auto& pool = c->storePool[c->lastArena];
+		for (int i = 0; i < plan.storesUsed && i < static_cast<int>(pool.size()); ++i) { f->stores.push_back(pool[i]); pool[i] = DevBuf{}; } }
 	const size_t bytes = std::max<size_t>(plan.arenaBytes, 16);
 	if (cudaMalloc(&f->devArena, bytes) != cudaSuccess) { delete f; return fail(RSRCU_ERR_CUDA, "cudaMalloc of %zu bytes for a retained frame failed", bytes); }
 	// the tables hold device addresses; those that point into the context's arena mirror move to the private copy
@@ -1063,6 +1104,8 @@ int rsrcu_retain_frame(rsrcu_ctx* c, rsrcu_frame** out) {
 	for (size_t i = 0; i < c->draws.size(); ++i) { rebase(dr[i].indices); }
 	if (cudaMemcpy(f->devArena, tmp.data(), plan.arenaBytes, cudaMemcpyHostToDevice) != cudaSuccess) {
 		cudaFree(f->devArena); delete f; return fail(RSRCU_ERR_CUDA, "upload of a retained frame failed"); }
+	// the slot's launch record now refers to a plan whose store targets belong to the retained frame: settle it here
+	c->slotPlan[c->lastArena].valid = false;
 	*out = f;
 	return RSRCU_OK; }
 
@@ -1087,20 +1130,84 @@ int rsrcu_release_frame(rsrcu_ctx* c, rsrcu_frame* f) {
 		cudaSetDevice(c->device);
 		cudaStreamSynchronize(c->frontStream);
 		cudaStreamSynchronize(c->stream); }
+	if (c) { for (auto& L : c->launched) { if (L.plan == &f->plan) { L = Launched{}; } } }
 	if (f->devArena) { cudaFree(f->devArena); }
+	for (auto& b : f->stores) { b.release(); }
 	delete f;
 	return RSRCU_OK; }
+
+// Reads the overflow bits a finished frame left in its counters and grows the buffer concerned.  Returns the
+// message for the caller (nullptr: the frame is complete).
+static const char* growAfterOverflow(rsrcu_ctx* c, const Counters& k, char* buf, size_t n) {
+	if (k.overflow & 2u) {
+		const uint64_t need = k.entries + k.entries / 4;
+		c->listCapacity = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(need, c->listCapacity), 0xfffffff0ull));
+		std::snprintf(buf, n, "tile list capacity exceeded (%llu entries)", static_cast<unsigned long long>(k.entries));
+		return buf; }
+	if (k.overflow & 8u) {
+		c->largeTiles = std::min(c->largeTiles * 4, 1 << 12);
+		std::snprintf(buf, n, "a tile is covered by more than %d queued large triangles (threshold now %d tiles)", kTileLargeCap, c->largeTiles);
+		return buf; }
+	if (k.overflow & 4u) {
+		c->largeCapacity = std::max(c->largeCapacity * 2, k.nLarge + k.nLarge / 4);
+		std::snprintf(buf, n, "large-item queue exceeded (%u items)", k.nLarge);
+		return buf; }
+	if (k.overflow & 1u) {
+		c->clipCapacity = std::max(c->clipCapacity * 2, k.clipAlloc + k.clipAlloc / 4);
+		std::snprintf(buf, n, "clip record capacity exceeded (%u needed)", k.clipAlloc);
+		return buf; }
+	return nullptr; }
+
+// Waits for the read-back of the frame launched into `slot`.  A frame whose tile lists, clip records or large-item
+// queue overflowed was rendered truncated: the buffer is grown and the frame is launched again from its tables,
+// which are still on the device (arena ring / retained frame), until it fits -- the caller never sees a truncated
+// frame.  `force`: launch it again even if it fitted (a frame submitted before it was launched again, and the two
+// may share a store destination).
+static int settleSlot(rsrcu_ctx* c, int slot, bool force, bool& relaunched) {
+	Launched& L = c->launched[slot];
+	relaunched = false;
+	if (!L.plan) { return RSRCU_OK; }
+	for (int attempt = 0; ; ++attempt) {
+		CU(cudaEventSynchronize(c->evCopied[slot]));
+		char msg[160];
+		const char* why = growAfterOverflow(c, c->hostCounters[slot], msg, sizeof(msg));
+		if (!why && !force) { L.checked = true; return RSRCU_OK; }
+		if (why && (attempt >= 8 || c->clipCapacity >= (1u << 24))) {
+			L.checked = true;
+			return fail(RSRCU_ERR_OVERFLOW, "%s: still not enough after %d attempts", why, attempt); }
+		force = false;
+		relaunched = true;
+		++c->framesRetried;
+		const FramePlan* plan = L.plan;
+		const uint8_t* arenaDev = L.arenaDev;
+		const int keep = c->outSlot;
+		void* const keepTc = c->shownTcDev; const int keepStride = c->shownTcStride;
+		c->outSlot = slot;
+		const int r = launchFrame(c, *plan, arenaDev, nullptr, 0, -1);
+		c->outSlot = keep;
+		if (slot != keep) { c->shownTcDev = keepTc; c->shownTcStride = keepStride; }
+		if (r != RSRCU_OK) { return r; } } }
 
 int rsrcu_sync(rsrcu_ctx* c) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	CU(cudaSetDevice(c->device));
 	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
+	// every frame still in flight, oldest first
+	bool again = false;
+	for (int k = kSlots - 1; k >= 0; --k) {
+		const int slot = (c->outSlot + kSlots - k) % kSlots;
+		if (c->launched[slot].plan && !c->launched[slot].checked) {
+			bool relaunched = false;
+			const int r = settleSlot(c, slot, again, relaunched);
+			if (r != RSRCU_OK) { return r; }
+			again = again || relaunched; } }
 	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaStreamSynchronize(c->copyStream));
 	if (!c->framePending) { return RSRCU_OK; }
 	c->framePending = false;
 	const Counters& k = c->hostCounters[c->outSlot];
+	if (c->launched[c->outSlot].plan) { c->stats.triangles_submitted = c->launched[c->outSlot].plan->trianglesSubmitted; }
 	c->stats.triangles_binned = k.binned;
 	c->stats.triangles_clipped = k.clipped;
 	c->stats.bin_entries = k.entries;
@@ -1112,28 +1219,13 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	c->stats.list_chunks_key_range = k.chunksKeyRange;
 	c->stats.host_record_ns = c->recordNs;
 	c->stats.host_submit_ns = c->submitNs;
+	c->stats.frames_retried = c->framesRetried;
 	if (c->profiling) {
 		for (int i = 0; i < 6; ++i) { c->stageMs[i] = 0.0f; }
 		if (c->profiling > 1) { for (int i = 0; i < 5; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); } }
 		cudaEventElapsedTime(&c->stageMs[5], c->evStage[6], c->evStage[7]);
 		// stage order of the header: vertex, setup, count, scan, fill, tile
 		cudaEventElapsedTime(&c->stageMs[6], c->evStage[0], c->evStage[7]); }
-	if (k.overflow & 2u) {
-		// grow for the next frame and report: this frame's tile lists were truncated
-		const uint64_t need = k.entries + k.entries / 4;
-		c->listCapacity = static_cast<uint32_t>(std::min<uint64_t>(need, 0xfffffff0ull));
-		return fail(RSRCU_ERR_OVERFLOW, "tile list capacity exceeded (%llu entries); capacity raised, render the frame again",
-		            static_cast<unsigned long long>(k.entries)); }
-	if (k.overflow & 8u) {
-		c->largeTiles = std::min(c->largeTiles * 4, 1 << 12);
-		return fail(RSRCU_ERR_OVERFLOW, "a tile is covered by more than %d queued large triangles; threshold raised to %d tiles, render the frame again",
-		            kTileLargeCap, c->largeTiles); }
-	if (k.overflow & 4u) {
-		c->largeCapacity = std::max(c->largeCapacity * 2, k.nLarge + k.nLarge / 4);
-		return fail(RSRCU_ERR_OVERFLOW, "large-item queue exceeded (%u items); capacity raised, render the frame again", k.nLarge); }
-	if (k.overflow & 1u) {
-		c->clipCapacity = c->clipCapacity * 2;
-		return fail(RSRCU_ERR_OVERFLOW, "clip record capacity exceeded (%u needed); capacity raised, render the frame again", k.clipAlloc); }
 	return RSRCU_OK; }
 
 int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
@@ -1192,12 +1284,16 @@ int rsrcu_sync_frame(rsrcu_ctx* c, int lag) {
 	if (!c || lag < 0 || lag >= kSlots) { return fail(RSRCU_ERR_INVALID, "lag must be 0 .. %d", kSlots - 1); }
 	CU(cudaSetDevice(c->device));
 	if (lag == 0) { const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
-	CU(cudaEventSynchronize(c->evCopied[(c->outSlot + kSlots - lag) % kSlots]));
-	return RSRCU_OK; }
+	const int slot = (c->outSlot + kSlots - lag) % kSlots;
+	if (!c->launched[slot].plan) { CU(cudaEventSynchronize(c->evCopied[slot])); return RSRCU_OK; }
+	bool relaunched = false;
+	const int r = settleSlot(c, slot, false, relaunched);
+	c->stats.frames_retried = c->framesRetried;
+	return r; }
 
 int rsrcu_device_truecolor(rsrcu_ctx* c, void** devPtr, int* stridePx) {
 	if (!c || !devPtr || !stridePx) { return fail(RSRCU_ERR_INVALID, "null argument"); }
-	*devPtr = c->tcOut[c->outSlot].ptr; *stridePx = c->tcStride;
+	*devPtr = c->shownTcDev; *stridePx = c->shownTcStride;
 	return RSRCU_OK; }
 
 int rsrcu_stream(rsrcu_ctx* c, void** stream) {

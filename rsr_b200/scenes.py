@@ -444,10 +444,11 @@ class SoupScene:
     (rglv_gpu_impl.hxx:427-494, :678-793)"""
 
     def __init__(self, n=600, seed=3, spread=1.6, near_cross=True, program=PROGRAM_AMY, cull=None, blend=False,
-                 instanced=0, depth_func=None, tex_dim=64, bilinear=True, tiny=False):
+                 instanced=0, depth_func=None, tex_dim=64, bilinear=True, tiny=False, zrange=None):
         rng = np.random.default_rng(seed)
         c = rng.uniform(-spread, spread, (n, 1, 3))
-        c[:, :, 2] = rng.uniform(-12.0, 0.5 if near_cross else -1.5, (n, 1))
+        zr = zrange if zrange is not None else (-12.0, 0.5 if near_cross else -1.5)
+        c[:, :, 2] = rng.uniform(zr[0], zr[1], (n, 1))
         ext = rng.choice([0.02, 0.2, 1.0, 4.0], size=(n, 1, 1), p=[0.3, 0.4, 0.2, 0.1]) if not tiny else 0.02
         tri = c + rng.normal(0, 1, (n, 3, 3)) * ext
         # a few exact degenerates and slivers
@@ -473,12 +474,14 @@ class SoupScene:
         self.triangles = n * max(1, instanced)
 
     def record(self, gl, size, out, depth=None, tile_blocks=(8, 8), arrays=False, gamma=True, fp_out=None,
-               attachments=None, post=PROGRAM_DEFAULT_POST, post_uniform=None, half_out=None, quads_out=None):
+               attachments=None, post=PROGRAM_DEFAULT_POST, post_uniform=None, half_out=None, quads_out=None, viewport=None):
         from . import GL_COLOR_ATTACHMENT0, GL_DEPTH_ATTACHMENT, RB_F32, RB_RGBF32
         gl.Reset(size, tile_blocks)
         if attachments == "split":
             gl.RenderbufferType(GL_COLOR_ATTACHMENT0, RB_RGBF32)
             gl.RenderbufferType(GL_DEPTH_ATTACHMENT, RB_F32)
+        if viewport is not None:
+            gl.Viewport(*viewport)
         gl.ClearColor((0.1, 0.2, 0.3))
         gl.ClearDepth(1.0)
         gl.Clear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT)
@@ -496,10 +499,17 @@ class SoupScene:
             gl.StoreColorQuads(quads_out)
         gl.StoreColor(out, gamma)
 
-    def draw(self, gl, size, arrays=False):
-        """the soup's state and draw call alone (inside a frame somebody else begins and finishes)"""
-        from . import GL_BLEND, PROGRAM_OBJ2S, PROGRAM_PATTERN
+    def draw(self, gl, size, arrays=False, color_write=None, depth_write=None, depth_test=None, depth_func=None, blend=None):
+        """the soup's state and draw call alone (inside a frame somebody else begins and finishes); the keyword
+        arguments override the pipeline state for this draw (depth pre-pass / EQUAL passes)"""
+        from . import GL_BLEND, GL_DEPTH_TEST, PROGRAM_OBJ2S, PROGRAM_PATTERN
         w, h = size
+        if color_write is not None:
+            gl.ColorWriteMask(color_write)
+        if depth_write is not None:
+            gl.DepthWriteMask(depth_write)
+        if depth_test is not None:
+            (gl.Enable if depth_test else gl.Disable)(GL_DEPTH_TEST)
         gl.UseProgram(self.program)
         gl.ViewMatrix(translate(0.1, -0.05, -1.0) @ rotate(0.2, 0.1, 1.0, 0.3))
         gl.ProjectionMatrix(perspective(70.0, w / h, 0.5, 50.0))
@@ -508,12 +518,12 @@ class SoupScene:
             gl.CullFace(self.cull)
         else:
             gl.Disable(GL_CULL_FACE)
-        if self.blend:
+        if self.blend if blend is None else blend:
             gl.Enable(GL_BLEND)
         else:
             gl.Disable(GL_BLEND)
-        if self.depth_func is not None:
-            gl.DepthFunc(self.depth_func)
+        if depth_func is not None or self.depth_func is not None:
+            gl.DepthFunc(depth_func if depth_func is not None else self.depth_func)
         gl.UseBuffer(0, self.pos)
         gl.UseBuffer(3, self.nrm)
         gl.UseBuffer(6, self.kd)

@@ -225,25 +225,49 @@ def test_retained_frames_replay_bit_identical(overlap):
         g.close()
 
 
-def test_tile_list_overflow_is_reported_and_recovered(ref_gpu, monkeypatch):
-    """more (triangle, tile) pairs than the list buffer holds: the frame reports OVERFLOW, the buffer
-    grows, and rendering the same frame again gives the reference's pixels"""
+def test_tile_list_overflow_is_recovered_inside_sync(ref_gpu, monkeypatch):
+    """more (triangle, tile) pairs than the list buffer holds: rsrcu_sync grows the buffer and launches the
+    frame again from its device-resident tables; the caller gets the reference's pixels, never a truncated frame"""
     monkeypatch.setenv("RSRCU_LIST_CAPACITY", "2000")
     g = R.GPU(0)
     try:
         sc = scenes.CubesScene(instances=300)
         a = np.zeros((360, 640), np.uint32)
         sc.record(g, (640, 360), a)
-        rec = g.Finish()
-        g._check(g.L.rsrcu_run_stream(g.h, rec.buf, len(rec.data)))
-        with pytest.raises(R.RsrError) as e:
-            g.Sync()
-        assert e.value.code == 6
-        g.Submit(rec)            # capacity was raised by the failed attempt
-        assert g.stats()["bin_entries"] > 2000
+        g.Run()
+        st = g.stats()
+        assert st["bin_entries"] > 2000 and st["frames_retried"] >= 1
         b = np.zeros_like(a)
         sc.record(ref_gpu, (640, 360), b)
         ref_gpu.Run()
         assert np.array_equal(a, b)
+    finally:
+        g.close()
+
+
+def test_overflow_in_a_pipelined_frame_is_recovered_by_sync_frame(ref_gpu, monkeypatch):
+    """three frames in flight (Submit(sync=False) + SyncFrame, the end-to-end path of bench.py), the first one
+    overflows the tile lists: rsrcu_sync_frame launches exactly that frame again from the arena ring while the
+    later frames are already queued; every host destination ends up with its own complete frame"""
+    monkeypatch.setenv("RSRCU_LIST_CAPACITY", "2000")
+    g = R.GPU(0)
+    try:
+        sc = scenes.CubesScene(instances=300)
+        outs = [np.zeros((360, 640), np.uint32) for _ in range(4)]
+        recs = []
+        for i in range(4):
+            sc.record(g, (640, 360), outs[i], t=0.5 * i)
+            recs.append(g.Finish())
+        for i, rec in enumerate(recs):
+            g.Submit(rec, sync=False)
+            if i >= 2:
+                g.SyncFrame(2)
+        g.Sync()
+        assert g.stats()["frames_retried"] >= 1
+        for i in range(4):
+            want = np.zeros((360, 640), np.uint32)
+            sc.record(ref_gpu, (640, 360), want, t=0.5 * i)
+            ref_gpu.Run()
+            assert np.array_equal(outs[i], want), f"pipelined frame {i} differs"
     finally:
         g.close()

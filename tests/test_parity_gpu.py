@@ -10,7 +10,7 @@ import pytest
 
 import rsr_b200 as R
 from parity import assert_identical, render_both
-from rsr_b200.scenes import BundledLikeScene, CubesScene, SoupScene, WavyGridScene
+from rsr_b200.scenes import BundledLikeScene, CubesScene, FillStressScene, GeometryStressScene, SoupScene, WavyGridScene
 
 pytestmark = pytest.mark.gpu
 
@@ -220,3 +220,24 @@ def test_error_behaviour_matches_the_reference_contract(cuda_gpu):
     WavyGridScene(n=8).record(cuda_gpu, (640, 360), out)
     cuda_gpu.Run()
     assert np.unique(out).size > 10
+
+
+def test_bench_size_fill_stress_matches_the_reference(ref_gpu, cuda_gpu):
+    """the C4 workload exactly as bench.py renders it: 8 layers of 960x540 quads, 32 distinct 1024^2 mip-mapped
+    textures sampled 1:1 with bilinear filtering, one 1920x1080 sub-frame"""
+    scene = FillStressScene(layers=8, size=(1920, 1080), quads=(2, 2), tex_dim=1024)
+    outs = render_both(scene, (1920, 1080), ref_gpu, cuda_gpu)
+    assert np.unique(outs["ref"][0]).size > 100000
+    assert_identical(outs, "c4 at bench size")
+    assert cuda_gpu.stats()["fragments_shaded"] == 8 * 1920 * 1080
+
+
+def test_bench_size_geometry_stress_matches_the_reference(ref_gpu, cuda_gpu):
+    """the C3 workload exactly as bench.py renders it: 30 icospheres at 6 subdivisions = 2.46 M triangles of about a
+    pixel, several list cells per tile (groups > 1), run-merged lists.  (Reference tiles of 4x4 blocks keep its
+    unchecked 100 000-byte tile lists (rglv_gpu.hxx:29) within bounds; results do not depend on the tile size.)"""
+    scene = GeometryStressScene(spheres=30, divs=6)
+    outs = render_both(scene, (1920, 1080), ref_gpu, cuda_gpu, tile_blocks=(4, 4))
+    st = cuda_gpu.stats()
+    assert st["triangles_submitted"] == 2457600 and st["list_chunks_run_merge"] > 0, st
+    assert_identical(outs, "c3 at bench size")
