@@ -234,10 +234,10 @@ def test_device_truecolor_follows_the_frame_launched_last(cuda_gpu):
     import ctypes as C
     g = R.GPU(0)
     try:
-        outs = []
-        handles = []
+        outs, live, handles = [], [], []
         for seed in (5, 6):
             out = np.zeros((360, 640), np.uint32)
+            live.append(out)      # a retained frame keeps writing its recorded host destination at every replay
             SoupScene(n=200, seed=seed).record(g, (640, 360), out)
             g.Run()
             outs.append(out.copy())
