@@ -1,16 +1,19 @@
 #!/usr/bin/env python3
 """bench.py -- frames/s of the frame-rendering hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c4|c3] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c4|c3|c4_4k|c3_4k|c5] [--impl reference]
 
-A step is one frame of the workload.  Default workload = BASELINE.json configs[1]: the bundled-
-scene-shaped frame sequence at 1920x1080 (`rsr_b200.scenes.BundledLikeScene`, synthetic, seeded).
-One JSON line is printed by rank 0:
-  value  frames/s with every input resident in HBM (device timed, CUDA events, L2 flushed
-         between iterations), aggregate over ranks (each rank renders its own frames: weak scaling)
-  e2e    frames/s through the public API with HOST buffers: per frame the host rebuilds and
-         uploads the instance matrices + state and reads the 1080p frame back
-  roofline / cpu_baseline / clocks / gpu_launches as the contract asks
+A step is one frame of the workload.  Default workload = BASELINE.json configs[1]: the bundled-scene-shaped frame
+sequence at 1920x1080 (`rsr_b200.scenes.BundledLikeScene`, synthetic, seeded).  One JSON line is printed by rank 0:
+  value      frames/s with every input resident in HBM (device timed, CUDA events, L2 flushed between iterations),
+             aggregate over ranks (each rank renders its own frames: weak scaling)
+  e2e        frames/s through the public API with HOST buffers: per frame the host rebuilds and uploads the instance
+             matrices + state and reads the 1080p frame back (>= 200 frames whatever --steps says)
+  parity     frame 0 of the workload rendered by the reference's own CPU rasteriser in the same run and compared
+  roofline   SURVEY 8(d) algorithmic bytes / the tile kernel's time, against MEASURED_PEAKS.json
+  sustained  the same step back to back for >= 2 s with its own clock samples
+  c4_4k / c3_4k   (1 GPU) the fill / geometry stress configs of BASELINE.json at 3840x2160 = 2x2 sub-frames
+  split_frame     (N > 1) the 7680x4320 frame split over the ranks by sub-frame ownership, NVLink peer stores
 `--impl reference` times the reference's own CPU renderer (oracle/_ref) on this box's host cores.
 """
 from __future__ import annotations
@@ -32,17 +35,53 @@ METRIC = "frames_per_sec_1080p"
 SIZE = (1920, 1080)
 
 
-def make_scene(name):
-    """workloads: c2 (default, BASELINE.json configs[1]); c3 / c4 = one 1920x1080 sub-frame of the 4K
-    geometry / fill stress (the largest target the reference itself can render); c5 = 8K split-frame"""
-    from rsr_b200 import scenes
-    if name in ("c2", "c5"):
-        return scenes.BundledLikeScene(), SIZE, "c2_bundled_like_1920x1080"
-    if name == "c4":
-        return scenes.FillStressScene(layers=8, size=SIZE, quads=(2, 2)), SIZE, "c4_fill_stress_8layers_bilinear_1to1_1920x1080_subframe"
-    if name == "c3":
-        return scenes.GeometryStressScene(spheres=30, divs=6, size=SIZE), SIZE, "c3_geometry_stress_2p46Mtris_1920x1080_subframe"
-    raise SystemExit(f"unknown workload {name}")
+# ---------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------
+
+class Workload:
+    """a scene + the grid of <= 2048 px sub-frames it is rendered as (1x1 for the 1080p workloads)"""
+
+    def __init__(self, key):
+        from rsr_b200 import scenes
+        from rsr_b200.subframes import SubframePlan
+        self.key = key
+        if key in ("c2", "c5"):
+            self.scene, self.frame, self.name = scenes.BundledLikeScene(), SIZE, "c2_bundled_like_1920x1080"
+        elif key == "c4":
+            self.scene, self.frame = scenes.FillStressScene(layers=8, size=SIZE, quads=(2, 2)), SIZE
+            self.name = "c4_fill_stress_8layers_bilinear_1to1_1920x1080_subframe"
+        elif key == "c3":
+            self.scene, self.frame = scenes.GeometryStressScene(spheres=30, divs=6, size=SIZE), SIZE
+            self.name = "c3_geometry_stress_2p46Mtris_1920x1080_subframe"
+        elif key == "c4_4k":
+            self.frame = (3840, 2160)
+            self.scene = scenes.FillStressScene(layers=8, size=self.frame, quads=(4, 4), fast_textures=True)
+            self.name = "c4_fill_stress_8layers_128textures_bilinear_1to1_3840x2160_as_2x2_subframes"
+        elif key == "c3_4k":
+            self.frame = (3840, 2160)
+            self.scene = scenes.GeometryStressScene(spheres=122, divs=6, size=self.frame)
+            self.name = "c3_geometry_stress_9p99Mtris_3840x2160_as_2x2_subframes"
+        else:
+            raise SystemExit(f"unknown workload {key}")
+        self.plan = SubframePlan(self.frame[0], self.frame[1], 1, 1920, 1080)
+        self.subframes = self.plan.subframes
+        self.sub_size = (self.plan.sub_w, self.plan.sub_h)
+        self.single = len(self.subframes) == 1
+
+    def record(self, gl, sf, out, t=0.0, **kw):
+        """records sub-frame `sf` of the frame at time t into gl"""
+        if self.single:
+            self.scene.record(gl, self.sub_size, out, t=t, **kw)
+        else:
+            self.scene.record(gl, self.sub_size, out, t=t, proj=self.plan.projection(self.scene.projection(), sf), **kw)
+
+    def config(self, args):
+        return {"workload": self.name, "triangles_per_frame": self.scene.triangles, "draws_per_frame": getattr(self.scene, "draws", None),
+                "width": self.frame[0], "height": self.frame[1], "subframes": len(self.subframes),
+                "cache": "L2 flushed (256 MiB memset) before every timed frame",
+                "resident_leg": "retained frame tables replayed (rsrcu_replay_frame)" if args.resident == "retained"
+                                else "recorded stream decoded and uploaded every step (rsrcu_run_stream)"}
 
 
 class ClockSampler:
@@ -51,7 +90,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.path = f"/tmp/rsr_clocks_{os.getpid()}.csv"
+        self.path = f"/tmp/rsr_clocks_{os.getpid()}_{time.monotonic_ns()}.csv"
         self.proc = None
         self.gpu = gpu_index
 
@@ -62,6 +101,7 @@ class ClockSampler:
                                           "-lms", "50", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -74,14 +114,14 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             p = [x.strip() for x in line.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
             except ValueError:
                 continue
             for n, v in zip(names, p[5:9]):
@@ -94,14 +134,15 @@ class ClockSampler:
         if sm:
             out["sm_mhz"] = statistics.median(sm)
             out["sm_max_mhz"] = max(mx)
+            out["power_w_max"] = max(pw)
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
 
 
 def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of tile_kernel from the committed `ncu --set full`
-    capture of the same workload (profiles/, tools/capture_profiles.sh); None if there is none"""
+    """dram__bytes_read.sum + dram__bytes_write.sum of tile_kernel from the committed `ncu --set full` capture of
+    the same workload (profiles/, tools/capture_profiles.sh; L2 flushed before the captured launch); None if none"""
     import glob
     import re
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_tile_kernel_{workload}.txt")))
@@ -115,27 +156,33 @@ def ncu_traffic(workload):
     return total or None
 
 
-def time_reference(scene, size, steps, warmup, threads=None, budget_s=25.0):
-    """the reference's multithreaded CPU renderer on this box's cores, method of perf.cxx:216-235:
-    priming frames, N timed frames, discard the worst 5 %, report the mean of the rest"""
+# ---------------------------------------------------------------------------------------------------------
+# the reference's CPU renderer (cpu_baseline, parity gate, --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+
+def time_reference(wl, steps, warmup, threads=None, budget_s=25.0):
+    """the reference's multithreaded CPU renderer on this box's cores, method of perf.cxx:216-235: priming frames,
+    N timed frames, discard the worst 5 %, report the mean of the rest.  A frame of a > 2048 px workload is the sum
+    of its sub-frames (the only way the reference can produce it)."""
     from oracle import refgl
     threads = refgl.init(threads or os.cpu_count())
     g = refgl.RefGPU(double_buffer=True)   # the reference's default: bin of frame N overlaps draw of N-1
-    out = np.zeros((size[1], size[0]), np.uint32)
+    w, h = wl.sub_size
+    out = np.zeros((h, w), np.uint32)
     refgl.lib().ref_work_start()
     times = []
     t_begin = time.perf_counter()
-    n = 0
     try:
         for i in range(warmup + steps):
-            scene.record(g, size, out, t=i / 60.0)
-            t0 = time.perf_counter()
-            g.Run(manage_workers=False)
-            dt = time.perf_counter() - t0
+            dt = 0.0
+            for sf in wl.subframes:
+                wl.record(g, sf, out, t=i / 60.0)
+                t0 = time.perf_counter()
+                g.Run(manage_workers=False)
+                dt += time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-                n += 1
-            if time.perf_counter() - t_begin > budget_s and n >= 3:
+            if time.perf_counter() - t_begin > budget_s and len(times) >= 3:
                 break
     finally:
         refgl.lib().ref_work_end()
@@ -146,22 +193,279 @@ def time_reference(scene, size, steps, warmup, threads=None, budget_s=25.0):
     return {"ms_per_frame": ms, "fps": 1e3 / ms, "frames": len(times), "threads": threads}
 
 
-def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flush, barrier):
-    """C5: one 7680x4320 frame = 4x4 sub-frames of 1920x1080 (the reference's guard band ends at 2048 px),
-    sub-frames dealt round-robin to the ranks.  Strong scaling: the frame is fixed.
-    --exchange p2p (default): every rank's tile kernel resolves straight into the presenting GPU's frame
-    buffer (CUDA-IPC mapping, peer stores over NVLink while it rasterises); a frame ends with one small
-    NCCL all-reduce as the completion barrier.  --exchange nccl: render locally, NCCL gather, assemble."""
+def parity_gate(wl, gpu):
+    """frame 0 of the workload (every sub-frame) through the reference's CPU rasteriser and through the CUDA path on
+    the same recorded calls: differing pixels and the largest 8-bit channel difference"""
+    from oracle import refgl
+    refgl.init(os.cpu_count())
+    ref = refgl.RefGPU()
+    w, h = wl.sub_size
+    diff, max_lsb, pixels = 0, 0, 0
+    try:
+        for sf in wl.subframes:
+            a, b = np.zeros((h, w), np.uint32), np.zeros((h, w), np.uint32)
+            wl.record(ref, sf, a, t=0.0, tile_blocks=(4, 4))   # (4x4-block reference tiles keep its unchecked 100 000-byte lists in bounds; results do not depend on the tile size)
+            ref.Run()
+            wl.record(gpu, sf, b, t=0.0, tile_blocks=(4, 4), static=True)
+            gpu.Run()
+            diff += int(np.count_nonzero(a != b))
+            pixels += a.size
+            for s in (0, 8, 16):
+                max_lsb = max(max_lsb, int(np.abs(((a >> s) & 0xff).astype(np.int32) - ((b >> s) & 0xff).astype(np.int32)).max()))
+    finally:
+        ref.close()
+    return {"diff_pixels": diff, "max_lsb": max_lsb, "pixels_compared": pixels,
+            "against": "the unmodified reference (oracle/_ref/librsr_ref.so) on this box's CPU, frame 0 of this workload"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device-resident leg + roofline for one workload on this rank's GPU
+# ---------------------------------------------------------------------------------------------------------
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ResidentRun:
+    """the workload's frame recorded once with every input static; a step replays it (all kernels run in full)"""
+
+    def __init__(self, wl, gpu, args, torch, local_rank):
+        self.wl, self.gpu, self.torch = wl, gpu, torch
+        self.stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
+        self.recs, self.retained = [], []
+        for sf in wl.subframes:
+            wl.record(gpu, sf, None, t=0.0, static=True)
+            self.recs.append(gpu.Finish())
+            if args.resident == "retained":
+                gpu.Submit(self.recs[-1])
+                self.retained.append(gpu.Retain())
+        gpu.set_overlap(not wl.single)   # sub-frames of one frame: front end of the next one under the current tile kernel
+
+    def step(self):
+        if self.retained:
+            for fr in self.retained:
+                self.gpu.Replay(fr)
+        else:
+            for rec in self.recs:
+                self.gpu.Submit(rec, sync=False)
+
+    def close(self):
+        self.gpu.Sync()
+        for fr in self.retained:
+            self.gpu.Release(fr)
+        self.gpu.set_overlap(False)
+
+
+def measure_resident(run, flush, steps, warmup, barrier, sampler=None):
+    """per-step device time (CUDA events on the context's stream, L2 flushed before every step), tile-kernel time
+    and frame statistics"""
+    torch, gpu, stream = run.torch, run.gpu, run.stream
+    gpu.set_profiling(1)
+    for i in range(warmup):
+        run.step()
+        gpu.Sync()
+    barrier()
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    tile_ms = []
+    stats = None
+    nsub = len(run.wl.subframes)
+    for i in range(steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(i & 0xff)
+            ev[i][0].record(stream)
+        if nsub == 1:
+            run.step()
+            with torch.cuda.stream(stream):
+                ev[i][1].record(stream)
+            gpu.Sync()
+            tile_ms.append(gpu.stage_ms()["tile"])
+        else:
+            run.step()
+            with torch.cuda.stream(stream):
+                ev[i][1].record(stream)
+            gpu.Sync()
+        stats = gpu.stats()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # per-stage breakdown and per-sub-frame statistics: a few extra, untimed frames with an event after every kernel
+    gpu.set_profiling(2)
+    stage_acc, nstage = {}, 4
+    frags = entries = inbytes = 0
+    tile_sum = 0.0
+    for i in range(nstage):
+        for k in range(nsub):
+            with torch.cuda.stream(stream):
+                flush.fill_(i & 0xff)
+            if run.retained:
+                gpu.Replay(run.retained[k])
+            else:
+                gpu.Submit(run.recs[k], sync=False)
+            gpu.Sync()
+            st = gpu.stats()
+            if i == 0:
+                frags += st["fragments_shaded"]; entries += st["bin_entries"]; inbytes += st["input_bytes"]
+            for name, v in gpu.stage_ms().items():
+                stage_acc[name] = stage_acc.get(name, 0.0) + v / nstage
+    gpu.set_profiling(0)
+    tile_avg = sum(tile_ms) / len(tile_ms) if tile_ms else stage_acc.get("tile", 0.0)
+    return {"dev_ms": dev_ms, "tile_ms": tile_avg, "stage_ms": stage_acc, "clocks": clocks, "stats": stats,
+            "fragments": frags, "bin_entries": entries, "input_bytes": inbytes}
+
+
+def roofline_of(wl, m, ms_per_step):
+    """B = 4 W H (resolved output) + draw inputs (bound SoA floats x vertices + indices + instance
+    matrices) + 2 x 6 R (bin entries written then read) + 16 U (unique texels at the selected LOD), per frame;
+    achieved = B / the tile kernel's time (summed over the frame's sub-frames), measured with CUDA events on the
+    context's stream in this run"""
+    pk = peaks()
+    peak = float(pk.get("hbm_gbs", 6650.0))
+    W, H = wl.frame
+    nsub = len(wl.subframes)
+    texels = wl.scene.unique_texels({"fragments_shaded": m["fragments"]}, wl.frame)
+    B = 4 * W * H + m["input_bytes"] + 12 * m["bin_entries"] + 16 * texels
+    kernel_ms = m["tile_ms"]
+    achieved = B / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "frac_of_whole_step": B / (ms_per_step * 1e-3) / 1e9 / peak,
+            "traffic": ncu_traffic(wl.key), "algorithmic_bytes_per_launch": B,
+            "algorithmic_bytes": {"output_4WH": 4 * W * H, "draw_inputs": m["input_bytes"], "bin_entries_12R": 12 * m["bin_entries"],
+                                  "unique_texels_16U": 16 * texels},
+            "kernel_ms": kernel_ms, "kernel_launches_per_step": nsub,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if pk else "fallback 6650",
+            "stage_ms": m["stage_ms"]}
+
+
+def sustained_leg(run, flush, seconds, local_rank):
+    """the same step back to back for `seconds` (no per-step host sync): what a long run clocks at"""
+    torch, gpu, stream = run.torch, run.gpu, run.stream
+    sampler = ClockSampler(local_rank).start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fl0, fl1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the flush's own time is measured first and subtracted: the timed region is one unbroken stream of work
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        fl0.record(stream)
+        for i in range(20):
+            flush.fill_(i)
+        fl1.record(stream)
+    torch.cuda.synchronize()
+    flush_ms = fl0.elapsed_time(fl1) / 20
+    n = 0
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(16):
+            with torch.cuda.stream(stream):
+                flush.fill_(n & 0xff)
+            run.step()
+            n += 1
+        if n % 64 == 0:
+            torch.cuda.synchronize()   # bound the queue depth
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    gpu.Sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    clocks = sampler.stop()
+    return {"seconds": e0.elapsed_time(e1) / 1e3, "steps": n, "ms_per_step_incl_flush": ms, "flush_ms": flush_ms,
+            "ms_per_step": ms - flush_ms, "frames_per_s": 1e3 / max(ms - flush_ms, 1e-6), "clocks": clocks}
+
+
+def e2e_leg(wl, gpu, frames, torch, dist, world, local_rank, barrier):
+    """end to end through rsrcu_run_stream + rsrcu_sync_frame with HOST buffers.  Each frame of the sequence is
+    recorded beforehand (that is the callers' job in the reference: node graph -> GL calls); the timed region is what
+    replaces GPU::Run -- decode the stream, upload that frame's host buffers (instance matrices, state), kernels,
+    read the frame back.  Frames are pipelined like the reference's doubleBuffer mode, three in flight: while frame N
+    is read back (copy stream) frames N+1 and N+2 are decoded, uploaded and rendered; every frame is waited for
+    (rsrcu_sync_frame) and lands in one of three rotating pinned host buffers."""
+    W, H = wl.sub_size
+    gpu.set_overlap(True)            # front end of frame N+1 under the tile kernel of frame N (rsrcu_set_overlap)
+    host_out = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(3)]
+    recs = []
+    distinct = min(frames + 2, 64)   # a 64-frame loop of the sequence (each with its own instance matrices)
+    for i in range(distinct):
+        wl.record(gpu, wl.subframes[0], host_out[i % 3], t=i / 60.0)
+        recs.append(gpu.Finish())
+    # destinations rotate with period 3, recordings with period 64: index recordings so that frame i writes buffer i % 3
+    order = [recs[(i % (distinct // 3 * 3))] for i in range(frames + 2)]
+    for rec in order[:2]:
+        gpu.Submit(rec)
+    retried0 = gpu.stats()["frames_retried"]
+    barrier()
+    t0 = time.perf_counter()
+    for i, rec in enumerate(order[2:]):
+        gpu.Submit(rec, sync=False)      # rsrcu_run_stream
+        if i > 1:
+            gpu.SyncFrame(2)             # frame i-2 is complete in host memory
+    gpu.Sync()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = gpu.stats()
+    gpu.set_overlap(False)
+    return {"value": world * frames / float(t.item()), "unit": "frames/s", "frames": frames,
+            "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
+            "frames_retried_for_overflow": st["frames_retried"] - retried0,
+            "timing": "wall clock over `frames` frames of rsrcu_run_stream + rsrcu_sync_frame (stream decode, H2D, kernels, D2H), "
+                      "three frames in flight, frame overlap on, max over ranks"}
+
+
+def stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier):
+    """BASELINE.json configs[2] / [3] at their full size on one GPU: a 3840x2160 frame = 2x2 sub-frames of 1920x1080
+    (the reference's guard band ends at 2048 px), every sub-frame submits the whole scene"""
+    wl = Workload(key)
+    par = parity_gate(wl, gpu)
+    run = ResidentRun(wl, gpu, args, torch, local_rank)
+    steps = max(10, min(args.steps, 30))
+    m = measure_resident(run, flush, steps, 3, barrier)
+    run.close()
+    ms = m["dev_ms"] / steps
+    fps = 1e3 / ms
+    out = {"workload": wl.name, "frames_per_s": fps, "ms_per_frame": ms, "steps": steps,
+           "mtris_per_s": wl.scene.triangles * fps / 1e6, "gpix_per_s": m["fragments"] * fps / 1e9,
+           "triangles_per_frame": wl.scene.triangles, "triangle_setups_per_frame": wl.scene.triangles * len(wl.subframes),
+           "fragments_per_frame": m["fragments"], "bin_entries_per_frame": m["bin_entries"],
+           "parity": par, "roofline": roofline_of(wl, m, ms)}
+    if not args.no_cpu_baseline:
+        try:
+            r = time_reference(wl, 6, 1, budget_s=12.0)
+            out["cpu_baseline"] = {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
+                                   "sample": f"{r['frames']} frames (sum over the 4 sub-frames), doubleBuffer=true"}
+        except Exception as exc:
+            out["cpu_baseline"] = {"value": None, "sample": f"unavailable: {exc}"}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C5: 8K split-frame
+# ---------------------------------------------------------------------------------------------------------
+
+def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier, scene=None):
+    """C5: one 7680x4320 frame = 4x4 sub-frames of 1920x1080 (the reference's guard band ends at 2048 px), sub-frames
+    dealt to the ranks.  Strong scaling: the frame is fixed.  Every rank's tile kernel resolves straight into the
+    presenting GPU's frame buffer (CUDA-IPC mapping, peer stores over NVLink while it rasterises); a frame ends with
+    one small NCCL all-reduce as the completion barrier.  Rank 0 also renders the whole frame alone (all 16
+    sub-frames on one GPU) so that the line carries its own single-GPU figure and efficiency.
+    --exchange nccl: render locally, NCCL gather, assemble."""
     from rsr_b200 import scenes
     from rsr_b200.present import PresentedFrame
     from rsr_b200.subframes import SubframePlan
+    scene = scene or scenes.BundledLikeScene()
     dev = f"cuda:{local_rank}"
+    stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
     P = scenes.perspective(45.0, 7680 / 4320, 1.0, 400.0)
     plan = SubframePlan(7680, 4320, world, 1920, 1080)
     owners = None
     if world > 1 and args.balance == "cost":
-        # sub-frames differ in cost (screen centre vs corners): rank 0 measures each once (device time of the frame's
-        # kernels) and deals them longest-first to the least loaded rank; every rank uses the same table
         costs = torch.zeros(len(plan.subframes), dtype=torch.float64, device=dev)
         if rank == 0:
             gpu.set_profiling(1)
@@ -175,38 +479,90 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
         dist.broadcast(costs, src=0)
         owners = SubframePlan.balance([float(c) for c in costs.tolist()], world)
         plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
-    mine = plan.owned_by(rank)
     p2p = args.exchange == "p2p"
     gpu.set_overlap(True)            # sub-frames are independent frames: front end of the next one under the current tile kernel
     cur = torch.cuda.current_stream()
-    recs, retained = [], []
+    pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist)
+    gpu.EnablePeerAccess(pf.presenter_device)
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def retain(subframes, local=None):
+        out = []
+        for k, sf in enumerate(subframes):
+            target = (pf.pointer(sf.x0, sf.y0), pf.stride_px) if local is None else (local[k].data_ptr(), 1920)
+            scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf), device_out=target)
+            gpu.Submit(gpu.Finish())
+            out.append(gpu.Retain())
+        return out
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        t_ms = 0.0
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+            step_fn()
+            e1.record(cur)
+            torch.cuda.synchronize()
+            t_ms += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    steps = max(10, min(args.steps, 50))
+    # ---- the whole frame on ONE GPU (rank 0 alone): the strong-scaling baseline of this very run -------------
+    single_ms = None
+    checksum1 = None
+    if rank == 0:
+        alone = retain(plan.subframes)
+        def step_alone():
+            for fr in alone:
+                gpu.Replay(fr)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(stream):
+                done.record(stream)
+            cur.wait_event(done)
+        for _ in range(3):
+            step_alone()
+        torch.cuda.synchronize()
+        t_ms = 0.0
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+            step_alone()
+            e1.record(cur)
+            torch.cuda.synchronize()
+            t_ms += e0.elapsed_time(e1)
+        single_ms = t_ms / steps
+        checksum1 = int(pf.local.to(torch.int64).sum().item())
+        gpu.Sync()
+        for fr in alone:
+            gpu.Release(fr)
+        pf.local.zero_()
+    barrier()
+
+    # ---- split over the ranks ------------------------------------------------------------------------------
+    mine = plan.owned_by(rank)
     if p2p:
-        pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist)
-        gpu.EnablePeerAccess(pf.presenter_device)
-        frame = pf.local
-        token = torch.zeros(1, dtype=torch.int32, device=dev)
-        for sf in mine:
-            scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf),
-                         device_out=(pf.pointer(sf.x0, sf.y0), pf.stride_px))
-            recs.append(gpu.Finish())
-            if args.resident == "retained":
-                gpu.Submit(recs[-1])
-                retained.append(gpu.Retain())
+        retained = retain(mine)
     else:
         local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
-        for k, sf in enumerate(mine):
-            scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf), device_out=(local[k].data_ptr(), 1920))
-            recs.append(gpu.Finish())
+        retained = retain(mine, local)
         gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
-        frame = torch.zeros((4320, 7680), dtype=torch.int32, device=dev) if rank == 0 else None
 
     def step():
-        if retained:
-            for fr in retained:
-                gpu.Replay(fr)
-        else:
-            for rec in recs:
-                gpu.Submit(rec, sync=False)
+        for fr in retained:
+            gpu.Replay(fr)
         done = torch.cuda.Event()
         with torch.cuda.stream(stream):
             done.record(stream)
@@ -221,52 +577,50 @@ def bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flu
             parts = gathered if world > 1 else [local]
             for r, part in enumerate(parts):
                 for k, sf in enumerate(plan.owned_by(r)):
-                    frame[sf.y0:sf.y0 + sf.height, sf.x0:sf.x0 + sf.width].copy_(part[k])
+                    pf.local[sf.y0:sf.y0 + sf.height, sf.x0:sf.x0 + sf.width].copy_(part[k])
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_ms = 0.0
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-        step()
-        e1.record(cur)
-        torch.cuda.synchronize()
-        t_ms += e0.elapsed_time(e1)
-    barrier()
+    ms = timed(step, steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.steps
     gpu.Sync()
     st = gpu.stats()
+    for fr in retained:
+        gpu.Release(fr)
+    gpu.set_overlap(False)
+    rec = None
     if rank == 0:
-        checksum = int(frame.to(torch.int64).sum().item())
+        checksum = int(pf.local.to(torch.int64).sum().item())
         exchange = "none" if world == 1 else ("tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce as barrier"
                                               if p2p else "NCCL gather of resolved sub-frames to rank 0 + assembly copies")
-        line = {"metric": "frames_per_sec_8k_split_frame", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32+i32", "data": "synthetic",
-                "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
-                           "subframes_per_rank": len(mine), "exchange": exchange,
-                           "ownership": "round robin" if owners is None else f"cost balanced (longest first): {owners}",
-                           "submission": "retained sub-frame tables replayed" if retained else "recorded streams decoded and uploaded every frame",
-                           "cache": "L2 flushed before every timed frame"},
-                "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks, "frame_checksum": checksum,
-                "gpu_launches": int(st["kernel_launches"]) * len(mine) * args.steps}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        remote = sum(1 for s in plan.subframes if s.owner != 0)
+        rec = {"metric": "frames_per_sec_8k_split_frame", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
+               "ms_per_step": ms, "scaling": "strong",
+               "single_gpu_frames_per_s": 1e3 / single_ms, "single_gpu_ms": single_ms,
+               "speedup_vs_single_gpu": single_ms / ms, "efficiency": single_ms / ms / world,
+               "nvlink_bytes_per_frame": remote * 1920 * 1080 * 4,
+               "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
+                          "subframes_per_rank": len(mine), "exchange": exchange,
+                          "ownership": "round robin" if owners is None else f"cost balanced (longest first): {owners}",
+                          "submission": "retained sub-frame tables replayed", "cache": "L2 flushed before every timed frame"},
+               "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks,
+               "frame_checksum": checksum, "frame_checksum_single_gpu": checksum1, "checksums_equal": checksum == checksum1,
+               "gpu_launches": int(st["kernel_launches"]) * len(mine) * steps}
+    return rec
+
+
+def pin_rank_to_cores(local_rank, world):
+    """one process per GPU on one host: give every rank its own slice of the cores (submit thread, CUDA's helper
+    threads and the interpreter of eight ranks otherwise migrate over the same cores)"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
 
 
 def main():
@@ -277,10 +631,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the c4_4k / c3_4k (1 GPU) and split_frame (N > 1) sub-records")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--e2e-frames", type=int, default=200)
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
-    ap.add_argument("--balance", default="roundrobin", choices=["cost", "roundrobin"], help="c5 only: how sub-frames are dealt to the ranks")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5 only: how resolved pixels reach the presenting GPU")
+    ap.add_argument("--balance", default="roundrobin", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="split-frame: how resolved pixels reach the presenting GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -288,26 +646,22 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    scene, size, workload = make_scene(args.workload)
-    W, H = size
-    config = {"workload": workload, "triangles_per_frame": scene.triangles, "draws_per_frame": getattr(scene, "draws", None),
-              "width": W, "height": H, "cache": "L2 flushed (256 MiB memset) before every timed frame",
-              "resident_leg": "retained frame tables replayed (rsrcu_replay_frame)" if args.resident == "retained" else "recorded stream decoded and uploaded every step (rsrcu_run_stream)"}
-
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = time_reference(scene, size, args.steps, args.warmup)
+        wl = Workload("c2" if args.workload == "c5" else args.workload)
+        r = time_reference(wl, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": r["frames"], "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic", "config": config,
-                "mtris_per_s": scene.triangles * r["fps"] / 1e6,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic", "config": wl.config(args),
+                "mtris_per_s": wl.scene.triangles * r["fps"] / 1e6,
                 "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
                                  "sample": f"{r['frames']} frames of the same workload, doubleBuffer=true, worst 5% dropped"},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
+    cores_per_rank = pin_rank_to_cores(local_rank, world) if world > 1 else None
     import torch
     import rsr_b200
     torch.cuda.set_device(local_rank)
@@ -317,8 +671,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     gpu = rsr_b200.GPU(local_rank)
-    gpu.set_profiling(1)           # events around the tile kernel (roofline) and the frame; per-stage events in a separate pass
-    stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
     def barrier():
@@ -327,121 +679,74 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident leg: everything static, result stays on the device -----------------
     if args.workload == "c5":
-        return bench_c5(args, scene, gpu, torch, dist, rank, local_rank, world, stream, flush, barrier)
+        rec = split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier)
+        if rank == 0:
+            rec.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic"})
+            print(json.dumps(rec))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
-    scene.record(gpu, size, None, t=0.0, static=True)
-    resident = gpu.Finish()        # the recorded command stream of one frame
-    retained = None
-    if args.resident == "retained":
-        # the frame's state / draw tables stay on the device with its meshes and textures (rsrcu_retain_frame): a step
-        # is every kernel of the frame (K0 zeroes the control block, vertex, setup, binning, tile) and nothing else
-        gpu.Submit(resident)
-        retained = gpu.Retain()
+    wl = Workload(args.workload)
+    config = wl.config(args)
+    if cores_per_rank:
+        config["host_cores_per_rank"] = cores_per_rank
 
-    def frame_resident(i):
-        if retained is not None:
-            gpu.Replay(retained)
-        else:
-            gpu.Submit(resident, sync=False)   # decode the recorded stream, rebuild and upload the tables every step
+    # ---- parity gate: frame 0 against the reference's CPU rasteriser, in this run -------------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = parity_gate(wl, gpu)
+        except Exception as exc:  # oracle not shipped: say so, never fake
+            parity = {"diff_pixels": None, "max_lsb": None, "against": f"unavailable: {exc}"}
 
-    for i in range(args.warmup):
-        frame_resident(i)
-        gpu.Sync()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    tile_ms, stage_acc = [], {}
-    stats = None
-    for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.fill_(i & 0xff)
-            ev[i][0].record(stream)
-        frame_resident(i)
-        with torch.cuda.stream(stream):
-            ev[i][1].record(stream)
-        gpu.Sync()
-        tile_ms.append(gpu.stage_ms()["tile"])
-        stats = gpu.stats()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    # per-stage breakdown: a few extra, untimed frames with an event after every kernel
-    gpu.set_profiling(2)
-    stage_acc, nstage = {}, 8
-    for i in range(nstage):
-        with torch.cuda.stream(stream):
-            flush.fill_(i & 0xff)
-        frame_resident(i)
-        gpu.Sync()
-        for k, v in gpu.stage_ms().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v / nstage
-    gpu.set_profiling(0)
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    # ---- device-resident leg ----------------------------------------------------------------------------------
+    run = ResidentRun(wl, gpu, args, torch, local_rank)
+    m = measure_resident(run, flush, args.steps, args.warmup, barrier, ClockSampler(local_rank) if rank == 0 else None)
+    t = torch.tensor([m["dev_ms"]], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
     ms_per_step = dev_ms_max / args.steps
     value = world * args.steps / (dev_ms_max / 1e3)
-
-    # ---- end-to-end leg: host buffers in, host frame out --------------------------------------
-    # Each frame of the sequence is recorded beforehand (that is the callers' job in the reference:
-    # node graph -> GL calls); the timed region is what replaces GPU::Run -- decode the stream,
-    # upload that frame's host buffers (instance matrices, state), kernels, read the frame back.
-    # Frames are pipelined like the reference's doubleBuffer mode, three in flight: while frame N is read
-    # back (copy stream) frames N+1 and N+2 are decoded, uploaded and rendered; every frame is waited
-    # for (rsrcu_sync_frame) and lands in one of three rotating pinned host buffers.
-    gpu.set_overlap(True)            # front end of frame N+1 under the tile kernel of frame N (rsrcu_set_overlap)
-    host_out = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(3)]
-    frames = []
-    for i in range(args.steps + 2):
-        scene.record(gpu, size, host_out[i % 3], t=i / 60.0)
-        frames.append(gpu.Finish())
-    for rec in frames[:2]:
-        gpu.Submit(rec)
+    sustained = None
+    if args.sustained_seconds > 0 and rank == 0 and world == 1:
+        sustained = sustained_leg(run, flush, args.sustained_seconds, local_rank)
+    run.close()
     barrier()
-    t0 = time.perf_counter()
-    for i, rec in enumerate(frames[2:]):
-        gpu.Submit(rec, sync=False)      # rsrcu_run_stream
-        if i > 1:
-            gpu.SyncFrame(2)             # frame i-2 is complete in host memory
-    gpu.Sync()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_fps = world * args.steps / float(t.item())
-    e2e_stats = gpu.stats()
-    h2d, d2h = e2e_stats["h2d_bytes"], e2e_stats["d2h_bytes"]
+
+    # ---- end-to-end leg ------------------------------------------------------------------------------------------
+    e2e = e2e_leg(wl, gpu, max(args.e2e_frames, args.steps), torch, dist, world, local_rank, barrier) if wl.single else None
+    barrier()
+
+    # ---- sub-records -----------------------------------------------------------------------------------------------
+    extra = {}
+    if args.workload == "c2" and not args.no_subrecords:
+        if world == 1:
+            for key in ("c4_4k", "c3_4k"):
+                try:
+                    extra[key] = stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier)
+                except Exception as exc:
+                    extra[key] = {"error": repr(exc)}
+        else:
+            rec = split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier, scene=wl.scene)
+            if rank == 0:
+                extra["split_frame"] = rec
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (tile_kernel) -----------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    tile_avg_ms = sum(tile_ms) / len(tile_ms)
-    tex_texels = scene.unique_texels(stats)
-    vertex_bytes = scene.vertex_record_bytes
-    algo_bytes = 4 * W * H + 4 * stats["bin_entries"] + vertex_bytes + 16 * tex_texels
-    achieved = algo_bytes / (tile_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "algorithmic_bytes_per_launch": algo_bytes,
-                "kernel_ms": tile_avg_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                "stage_ms": stage_acc}
-
+    stats = m["stats"]
+    roofline = roofline_of(wl, m, ms_per_step)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # (rank 0 at N = 1 only: at N > 1 the ranks are pinned to slices of the cores)
         try:
-            r = time_reference(scene, size, 30, 3, budget_s=20.0)
+            r = time_reference(wl, 30, 3, budget_s=20.0)
             cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
                    "sample": f"{r['frames']} frames of the same workload on the host cores, doubleBuffer=true, worst 5% dropped"}
         except Exception as exc:  # oracle not shipped: say so, never fake
@@ -450,16 +755,16 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i32", "data": "synthetic", "config": config,
-            "mtris_per_s": scene.triangles * value / 1e6,
-            "gpix_per_s": stats["fragments_shaded"] * value / 1e9,
-            "fragments_per_frame": stats["fragments_shaded"], "bin_entries_per_frame": stats["bin_entries"],
-            "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timing": "wall clock over K frames of rsrcu_run_stream + rsrcu_sync_frame (stream decode, H2D, kernels, D2H), three frames in flight, frame overlap on, max over ranks"},
-            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu}
+            "mtris_per_s": wl.scene.triangles * value / 1e6,
+            "gpix_per_s": m["fragments"] * value / 1e9,
+            "fragments_per_frame": m["fragments"], "bin_entries_per_frame": m["bin_entries"],
+            "clocks": m["clocks"], "parity": parity, "e2e": e2e,
+            "gpu_launches": int(stats["kernel_launches"]) * len(wl.subframes) * args.steps,
+            "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu}
+    line.update(extra)
     print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -281,6 +281,7 @@ typedef struct RsrStats {
 	uint64_t host_record_ns;        /* host time spent recording the frame (begin_frame .. end_frame, all calls) */
 	uint64_t host_submit_ns;        /* host time spent in rsrcu_end_frame (tables, upload, launches) */
 	uint64_t frames_retried;        /* cumulative: frames launched again because a device-side buffer overflowed */
+	uint64_t input_bytes;           /* the frame's draw inputs: bound vertex SoA floats x vertices + indices + instance matrices */
 } RsrStats;
 int rsrcu_get_stats(rsrcu_ctx* ctx, RsrStats* out);
 

@@ -129,7 +129,8 @@ struct FramePlan {
 	std::vector<PendingCopy> copies;
 	void* tcDev{nullptr}; int tcStride{0};   // the frame's last true-colour store (rsrcu_device_truecolor)
 	int storesUsed{0};                       // store targets of the context's pool the frame's commands point into
-	uint64_t trianglesSubmitted{0}; };
+	uint64_t trianglesSubmitted{0};
+	uint64_t inputBytes{0}; };
 
 struct rsrcu_frame {
 	FramePlan plan;
@@ -187,6 +188,7 @@ struct rsrcu_ctx {
 	std::vector<int> cmdDstKind;      // 0 none, 1 tc, 2 fp, 3 depth
 	std::vector<PendingCopy> copies;
 	uint64_t trianglesSubmitted{0};
+	uint64_t inputBytes{0};            // vertex SoA floats bound x vertices referenced + indices + instance matrices
 
 	UploadArena arenas[kSlots];       // ring, indexed like the store targets (outSlot): frame N+1 records while frame N's upload is in flight, and the
 	                                  // device mirror of a frame stays intact until three frames later (an overflowed frame can be launched again)
@@ -735,7 +737,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->launched[c->outSlot] = Launched{};
 	c->storesUsed = 0; c->tcDev = nullptr;
 	c->arenas[c->outSlot].used = 0;
-	c->trianglesSubmitted = 0;
+	c->trianglesSubmitted = 0; c->inputBytes = 0;
 	c->haveState = false; c->stateDirty = true;
 	for (auto& b : c->curBuffers) { b = DevRef{}; }
 	for (auto& f : c->curBufferFloats) { f = 0; }
@@ -869,6 +871,10 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 		r = uploadData(c, indices, static_cast<size_t>(prims) * 3 * sizeof(uint16_t), upload, hd.indices);
 		if (r != RSRCU_OK) { return r; } }
 	c->trianglesSubmitted += d.N;
+	{
+		int attrs = 0;
+		for (int slot = 0; slot <= 10; ++slot) { attrs += hs.ds.buffers[slot] != nullptr ? 1 : 0; }
+		c->inputBytes += static_cast<uint64_t>(nverts) * 4u * attrs + (arrays ? 0u : static_cast<uint64_t>(prims) * 6u) + (instanced ? static_cast<uint64_t>(instances) * 64u : 0u); }
 	c->draws.push_back(hd);
 	return RSRCU_OK; }
 
@@ -1065,7 +1071,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		++plan.ncmdInline; }
 	plan.copies = c->copies;
 	plan.tcDev = c->tcDev; plan.tcStride = c->tcStride; plan.storesUsed = c->storesUsed;
-	plan.trianglesSubmitted = c->trianglesSubmitted;
+	plan.trianglesSubmitted = c->trianglesSubmitted; plan.inputBytes = c->inputBytes;
 	plan.valid = true;
 	CU(c->arenas[c->outSlot].dev.reserve(c->arenas[c->outSlot].used));
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[2] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
@@ -1207,7 +1213,7 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	if (!c->framePending) { return RSRCU_OK; }
 	c->framePending = false;
 	const Counters& k = c->hostCounters[c->outSlot];
-	if (c->launched[c->outSlot].plan) { c->stats.triangles_submitted = c->launched[c->outSlot].plan->trianglesSubmitted; }
+	if (c->launched[c->outSlot].plan) { c->stats.triangles_submitted = c->launched[c->outSlot].plan->trianglesSubmitted; c->stats.input_bytes = c->launched[c->outSlot].plan->inputBytes; }
 	c->stats.triangles_binned = k.binned;
 	c->stats.triangles_clipped = k.clipped;
 	c->stats.bin_entries = k.entries;

@@ -354,9 +354,16 @@ class BundledLikeScene:
         self.mats = self.instance_matrices(0.0)
         self.vertex_record_bytes = 48 * (groups * cubes * cp.shape[1] + field * field * 4) + 80 * 2 * p.shape[1]
 
-    def unique_texels(self, stats):
-        """upper bound used for the roofline: the two 512^2 base levels"""
-        return 2 * 512 * 512
+    def unique_texels(self, stats, size=(1920, 1080)):
+        """unique texels touched at the LOD the sampler selects.  Every quad maps the whole
+        [0,1]^2 of its 512^2 texture onto (0.9 x 0.5) world units at z = -30, so the per-pixel texel step and with
+        it the coarse LOD (rglr_texture_sampler.cxx:25-42) follow from the projection; both textures are then
+        touched at that one level, counted once however many quads and taps read them"""
+        h = size[1]
+        px_per_unit = (h / 2.0) / (np.tan(np.radians(45.0) / 2.0) * 30.0)
+        du = 512.0 / (0.9 * px_per_unit)
+        lod = max(0, min(9, int(np.floor(np.log2(du * du))) >> 1))
+        return 2 * (512 >> lod) ** 2
 
     def instance_matrices(self, t):
         """per-frame CPU work of the $many node (node/many.cxx:188-226): rebuild instance matrices"""
@@ -558,7 +565,7 @@ class FillStressScene:
     sampled 1 texel : 1 pixel with bilinear filtering (program Amy).  No texel is reused across
     quads, so texture traffic really comes from HBM.  `size` is one <= 2048 px (sub-)frame."""
 
-    def __init__(self, layers=8, size=(1920, 1080), quads=(2, 2), seed=11, tex_dim=1024, front_to_back=False):
+    def __init__(self, layers=8, size=(1920, 1080), quads=(2, 2), seed=11, tex_dim=1024, front_to_back=False, fast_textures=False):
         self.layers, self.size, self.quads, self.tex_dim = layers, size, quads, tex_dim
         w, h = size
         qw, qh = w // quads[0], h // quads[1]
@@ -572,31 +579,43 @@ class FillStressScene:
                     pos = np.array([[x0, x0 + qw, x0 + qw, x0], [y0, y0, y0 + qh, y0 + qh], [z, z, z, z]], np.float32)
                     uv = np.array([[0, qw / tex_dim, qw / tex_dim, 0], [0, 0, qh / tex_dim, qh / tex_dim]], np.float32)
                     tid = len(self.items)
-                    tex = make_mipmap(hash_texture(tex_dim, seed, tid))
-                    self.items.append((soa(pos), soa(uv), tex))
+                    if fast_textures:
+                        # (128 textures at 4K: a seeded generator per texture instead of the integer hash, same layout)
+                        base = np.random.default_rng(seed * 1000003 + tid).random((tex_dim, tex_dim, 4), dtype=np.float32)
+                    else:
+                        base = hash_texture(tex_dim, seed, tid)
+                    self.items.append((soa(pos), soa(uv), make_mipmap(base)))
         self.idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
         self.triangles = 2 * len(self.items)
         self.draws = len(self.items)
         self.vertex_record_bytes = 48 * 4 * len(self.items)
 
-    def unique_texels(self, stats):
+    def unique_texels(self, stats, size=None):
         # 1:1 mapping by construction: every shaded fragment touches its own texel (+ shared borders)
-        return self.layers * self.size[0] * self.size[1]
+        w, h = size if size is not None else self.size
+        return self.layers * w * h
 
-    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), static=False, gamma=True):
-        assert tuple(size) == tuple(self.size)
-        w, h = size
+    def projection(self):
+        """of the whole frame (`size` of the constructor); a sub-frame uses crop @ projection (rsr_b200.subframes)"""
+        return orthographic(0, self.size[0], 0, self.size[1], 1.0, 20.0)
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), static=False, gamma=True, proj=None, device_out=None):
+        assert proj is not None or tuple(size) == tuple(self.size)
         up = {"upload": 1} if hasattr(gl, "stats") else {}
         begin(gl, size, clear=(0.0, 0.0, 0.0), tile_blocks=tile_blocks)
         gl.UseProgram(PROGRAM_AMY)
         gl.ViewMatrix(np.eye(4, dtype=np.float32))
-        gl.ProjectionMatrix(orthographic(0, w, 0, h, 1.0, 20.0))
+        gl.ProjectionMatrix(self.projection() if proj is None else proj)
         for pos, uv, tex in self.items:
             gl.UseBuffer(0, pos, **up)
             gl.UseBuffer(9, uv, **up)
             gl.BindTexture(0, tex, self.tex_dim, self.tex_dim, self.tex_dim, GL_LINEAR_MIPMAP_NEAREST, **up)
             gl.DrawElements(6, self.idx, 0, **up)
-        finish(gl, out, gamma, depth)
+        if device_out is not None:
+            gl.UseProgram(PROGRAM_DEFAULT_POST)
+            gl.StoreColorDevice(device_out[0], device_out[1], gamma)
+        else:
+            finish(gl, out, gamma, depth)
 
 
 class GeometryStressScene:
@@ -627,10 +646,15 @@ class GeometryStressScene:
         self.draws = spheres * len(self.hunks)
         self.vertex_record_bytes = 48 * spheres * p.shape[1]
 
-    def unique_texels(self, stats):
-        return min(stats["fragments_shaded"], self.tex_dim * self.tex_dim * 4 // 3)
+    def unique_texels(self, stats, size=None):
+        # uv = normal.xy / 2 + 0.5: a sphere's visible hemisphere covers the unit disc of the texture at LOD 0
+        # (radius_px > tex_dim / 4), every sphere the same texels
+        return min(stats["fragments_shaded"], int(self.tex_dim * self.tex_dim * np.pi / 4))
 
-    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True):
+    def projection(self):
+        return perspective(self.fov, self.size[0] / self.size[1], self.zn, self.zf)
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True, device_out=None):
         w, h = size
         up = {"upload": 1} if hasattr(gl, "stats") else {}
         begin(gl, size, clear=(0.02, 0.02, 0.05), tile_blocks=tile_blocks)
@@ -646,4 +670,8 @@ class GeometryStressScene:
                 gl.UseBuffer(3, hn, **up)
                 gl.UseBuffer(9, huv, **up)
                 gl.DrawElements(len(hidx), hidx, 0, **up)
-        finish(gl, out, gamma, depth)
+        if device_out is not None:
+            gl.UseProgram(PROGRAM_DEFAULT_POST)
+            gl.StoreColorDevice(device_out[0], device_out[1], gamma)
+        else:
+            finish(gl, out, gamma, depth)
