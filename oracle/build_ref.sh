@@ -5,6 +5,7 @@
 # $RSR_REFERENCE (default /root/reference, read-only) plus oracle/ref_harness.cpp into
 #   oracle/_ref/librsr_ref.so          (git-ignored; travels to the GPU box with gpurun)
 #   oracle/_ref/rglv_triangle_test     (the reference's own rglv_triangle.t.cxx, run as a check)
+#   oracle/_ref/librsr_dropin.so       (the reference with GPU::RunImpl replaced by the C-ABI binding: drop-in test)
 # Nothing from the reference tree is copied into the repository; the two g++-compat overlay
 # headers are generated into oracle/_ref/overlay/ by make_overlay.py at build time.
 # The reference's own build system (bazel / MSVC) is not used.
@@ -57,6 +58,27 @@ ho="$OUT/obj/ref_harness.o"
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 "$CXX" -shared -o "$OUT/librsr_ref.so" "${OBJS[@]}" "$ho" -lpthread
+
+# ---- the compiled drop-in: the reference's own GL / GLState / command stream in front of librsrcu.so ------------
+# Same translation units, except that GPU::RunImpl's body (rglv_gpu.cxx:90-116) is compiled out and supplied by
+# rsr_b200/host/rglv_gpu_cuda.cxx, which forwards the recorded stream to the C ABI of include/rsrcu.h.
+# tests/test_dropin_gpu.py renders through both libraries and compares bit for bit.
+RSRCU_DIR="$(cd "$HERE/../rsr_b200" && pwd)"
+if [ -f "$RSRCU_DIR/librsrcu.so" ]; then
+  DOBJS=()
+  for o in "${OBJS[@]}"; do
+    case "$o" in *src_rgl_rglv_rglv_gpu.cxx.o) ;; *) DOBJS+=("$o");; esac
+  done
+  "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -c "$OUT/overlay/dropin/rglv_gpu.cxx" -o "$OUT/obj/dropin_rglv_gpu.o" &
+  "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -I"$HERE/../include" -c "$RSRCU_DIR/host/rglv_gpu_cuda.cxx" -o "$OUT/obj/dropin_rglv_gpu_cuda.o" &
+  "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -c "$HERE/ref_harness.cpp" -o "$OUT/obj/dropin_ref_harness.o" &
+  wait
+  "$CXX" -shared -o "$OUT/librsr_dropin.so" "${DOBJS[@]}" "$OUT/obj/dropin_rglv_gpu.o" "$OUT/obj/dropin_rglv_gpu_cuda.o" \
+      "$OUT/obj/dropin_ref_harness.o" -L"$RSRCU_DIR" -lrsrcu -Wl,-rpath,'$ORIGIN/../../rsr_b200' -lpthread
+  echo "build_ref.sh: built $OUT/librsr_dropin.so"
+else
+  echo "build_ref.sh: rsr_b200/librsrcu.so not built yet, skipping librsr_dropin.so" >&2
+fi
 
 # the reference's own rasteriser test (plain main(), no gtest): fill-rule KAT + UV interpolation
 "$CXX" "${FLAGS[@]}" "$REF/src/rgl/rglv/rglv_triangle.t.cxx" \

@@ -10,6 +10,8 @@ patched copies into oracle/_ref/overlay/ (git-ignored build output, never commit
   aggregate").  Each such union is rewritten to one anonymous union per component plus an
   empty, offset-0 `v` accessor so `v[i]` keeps working.  Object layout is unchanged.
 * src/rgl/rglv/rglv_mesh_store.hxx -- `throw std::exception("...")` is MSVC-only.
+* dropin/rglv_gpu.cxx -- src/rgl/rglv/rglv_gpu.cxx with `#ifndef RSR_CUDA_RUNIMPL` around the body of
+  GPU::RunImpl (lines 90-116), for the compiled drop-in test (see build_ref.sh).
 
 Usage: make_overlay.py <reference_root> <overlay_out_dir>
 """
@@ -66,6 +68,17 @@ def main():
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         with open(dst, "w", encoding="utf-8") as f:
             f.write(fn(src))
+    # the drop-in build (librsr_dropin.so): rglv_gpu.cxx with the body of GPU::RunImpl compiled out under
+    # -DRSR_CUDA_RUNIMPL, so that rsr_b200/host/rglv_gpu_cuda.cxx can supply it; everything else in the file
+    # (Install, Reset, Retile, BinImpl, DrawImpl) is compiled as it is
+    src = open(os.path.join(ref, "src/rgl/rglv/rglv_gpu.cxx"), encoding="utf-8", errors="replace").read()
+    a = src.index("void GPU::RunImpl(rclmt::jobsys::Job* job) {")
+    b = src.index("void GPU::BinImpl() {")
+    patched = src[:a] + "#ifndef RSR_CUDA_RUNIMPL\n" + src[a:b] + "#endif  // RSR_CUDA_RUNIMPL\n\n" + src[b:]
+    dst = os.path.join(out, "dropin", "rglv_gpu.cxx")
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    with open(dst, "w", encoding="utf-8") as f:
+        f.write(patched)
     # an empty <intrin.h> (MSVC-only header; x86intrin.h comes from the shim)
     open(os.path.join(out, "intrin.h"), "w").close()
 

@@ -32,6 +32,15 @@
 using namespace rqdq;
 namespace jobsys = rclmt::jobsys;
 
+#ifdef RSR_CUDA_RUNIMPL
+/* the drop-in build (librsr_dropin.so): GPU::RunImpl comes from rsr_b200/host/rglv_gpu_cuda.cxx */
+namespace rqdq { namespace rglv {
+void CudaRelease(const GPU* gpu);
+void CudaFlush(const GPU* gpu);
+void CudaSetUploadPolicy(int buffers, int textures, int indices);
+}}
+#endif
+
 namespace {
 
 bool g_jobsysReady = false;
@@ -102,7 +111,26 @@ void* ref_gpu_create() {
 	rqv::Install(h->gpu);
 	return h; }
 
-void ref_gpu_destroy(void* h) { delete static_cast<RefGPU*>(h); }
+void ref_gpu_destroy(void* h) {
+#ifdef RSR_CUDA_RUNIMPL
+	rglv::CudaRelease(&static_cast<RefGPU*>(h)->gpu);
+#endif
+	delete static_cast<RefGPU*>(h); }
+
+/* 1 in librsr_dropin.so (GPU::Run renders through librsrcu.so), 0 in the pure reference */
+int ref_is_dropin() {
+#ifdef RSR_CUDA_RUNIMPL
+	return 1;
+#else
+	return 0;
+#endif
+}
+
+#ifdef RSR_CUDA_RUNIMPL
+/* drop-in only: wait for the frame still in flight in doubleBuffer mode; upload policy of the binding */
+void ref_dropin_flush(void* h) { rglv::CudaFlush(&static_cast<RefGPU*>(h)->gpu); }
+void ref_dropin_set_upload_policy(int buffers, int textures, int indices) { rglv::CudaSetUploadPolicy(buffers, textures, indices); }
+#endif
 
 void ref_gpu_reset(void* h, int w, int hgt, int tileBlocksX, int tileBlocksY) {
 	auto* g = static_cast<RefGPU*>(h);

@@ -20,14 +20,18 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "librsr_ref.so")
 
+DROPIN_PATH = os.path.join(HERE, "_ref", "librsr_dropin.so")
+
 _lib = None
 _threads = None
+_dropin = None
+_dropin_threads = None
 
 
 def build(force: bool = False) -> bool:
-    """Build oracle/_ref/librsr_ref.so when the reference tree is present. Returns availability."""
+    """Build oracle/_ref/librsr_ref.so (and librsr_dropin.so) when the reference tree is present. Returns availability."""
     ref = os.environ.get("RSR_REFERENCE", "/root/reference")
-    if os.path.isdir(os.path.join(ref, "src", "rgl", "rglv")) and (force or not os.path.exists(LIB_PATH)):
+    if os.path.isdir(os.path.join(ref, "src", "rgl", "rglv")) and (force or not os.path.exists(LIB_PATH) or not os.path.exists(DROPIN_PATH)):
         subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
     return os.path.exists(LIB_PATH)
 
@@ -36,67 +40,91 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def dropin_available() -> bool:
+    return os.path.exists(DROPIN_PATH)
+
+
+def _bind(path):
+    L = C.CDLL(path)
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    sigs = {
+        "ref_init": (ci, [ci]),
+        "ref_work_start": (None, []),
+        "ref_work_end": (None, []),
+        "ref_shutdown": (None, []),
+        "ref_set_double_buffer": (None, [ci]),
+        "ref_gpu_create": (vp, []),
+        "ref_gpu_destroy": (None, [vp]),
+        "ref_is_dropin": (ci, []),
+        "ref_gpu_reset": (None, [vp, ci, ci, ci, ci]),
+        "ref_gpu_run": (None, [vp]),
+        "ref_gl_enable": (None, [vp, ci]),
+        "ref_gl_disable": (None, [vp, ci]),
+        "ref_gl_depth_func": (None, [vp, ci]),
+        "ref_gl_depth_write_mask": (None, [vp, ci]),
+        "ref_gl_color_write_mask": (None, [vp, ci]),
+        "ref_gl_cull_face": (None, [vp, ci]),
+        "ref_gl_scissor": (None, [vp, ci, ci, ci, ci]),
+        "ref_gl_viewport": (None, [vp, ci, ci, ci, ci]),
+        "ref_gl_use_program": (None, [vp, ci]),
+        "ref_gl_renderbuffer_type": (None, [vp, ci, ci]),
+        "ref_gl_clear_color": (None, [vp, cf, cf, cf]),
+        "ref_gl_clear_depth": (None, [vp, cf]),
+        "ref_gl_view_matrix": (None, [vp, vp]),
+        "ref_gl_projection_matrix": (None, [vp, vp]),
+        "ref_gl_normal_matrix": (None, [vp, vp]),
+        "ref_gl_use_buffer": (None, [vp, ci, vp]),
+        "ref_gl_uniforms": (None, [vp, vp, ci]),
+        "ref_gl_bind_texture": (None, [vp, ci, vp, ci, ci, ci, ci]),
+        "ref_gl_bind_texture3": (None, [vp, vp, ci]),
+        "ref_gl_clear": (None, [vp, ci]),
+        "ref_gl_draw_elements": (None, [vp, ci, vp, ci]),
+        "ref_gl_draw_arrays": (None, [vp, ci]),
+        "ref_gl_draw_elements_instanced": (None, [vp, ci, vp, ci]),
+        "ref_gl_draw_arrays_instanced": (None, [vp, ci, ci]),
+        "ref_gl_store_color_tc": (None, [vp, vp, ci, ci, ci, ci]),
+        "ref_gl_store_color_fp": (None, [vp, vp, ci, ci, ci, ci]),
+        "ref_gl_store_color_quads": (None, [vp, vp, ci, ci, ci]),
+        "ref_gl_store_depth": (None, [vp, vp]),
+        "ref_make_mipmap": (None, [vp, ci, vp]),
+        "ref_rcp": (None, [vp, vp, ci]),
+        "ref_rsqrt": (None, [vp, vp, ci]),
+        "ref_oneover": (None, [vp, vp, ci]),
+        "ref_mat4_mul": (None, [vp, vp, vp]),
+        "ref_mat4_inverse": (None, [vp, vp]),
+        "ref_raster_coverage": (None, [vp, ci, ci, vp]),
+        "ref_vraster_coverage": (None, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.ref_is_dropin():
+        L.ref_dropin_flush.restype = None
+        L.ref_dropin_flush.argtypes = [vp]
+        L.ref_dropin_set_upload_policy.restype = None
+        L.ref_dropin_set_upload_policy.argtypes = [ci, ci, ci]
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
         if not available():
             raise RuntimeError(f"reference oracle not built: {LIB_PATH} (run oracle/build_ref.sh)")
-        L = C.CDLL(LIB_PATH)
-        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
-        fp = C.POINTER(C.c_float)
-        sigs = {
-            "ref_init": (ci, [ci]),
-            "ref_work_start": (None, []),
-            "ref_work_end": (None, []),
-            "ref_shutdown": (None, []),
-            "ref_set_double_buffer": (None, [ci]),
-            "ref_gpu_create": (vp, []),
-            "ref_gpu_destroy": (None, [vp]),
-            "ref_gpu_reset": (None, [vp, ci, ci, ci, ci]),
-            "ref_gpu_run": (None, [vp]),
-            "ref_gl_enable": (None, [vp, ci]),
-            "ref_gl_disable": (None, [vp, ci]),
-            "ref_gl_depth_func": (None, [vp, ci]),
-            "ref_gl_depth_write_mask": (None, [vp, ci]),
-            "ref_gl_color_write_mask": (None, [vp, ci]),
-            "ref_gl_cull_face": (None, [vp, ci]),
-            "ref_gl_scissor": (None, [vp, ci, ci, ci, ci]),
-            "ref_gl_viewport": (None, [vp, ci, ci, ci, ci]),
-            "ref_gl_use_program": (None, [vp, ci]),
-            "ref_gl_renderbuffer_type": (None, [vp, ci, ci]),
-            "ref_gl_clear_color": (None, [vp, cf, cf, cf]),
-            "ref_gl_clear_depth": (None, [vp, cf]),
-            "ref_gl_view_matrix": (None, [vp, vp]),
-            "ref_gl_projection_matrix": (None, [vp, vp]),
-            "ref_gl_normal_matrix": (None, [vp, vp]),
-            "ref_gl_use_buffer": (None, [vp, ci, vp]),
-            "ref_gl_uniforms": (None, [vp, vp, ci]),
-            "ref_gl_bind_texture": (None, [vp, ci, vp, ci, ci, ci, ci]),
-            "ref_gl_bind_texture3": (None, [vp, vp, ci]),
-            "ref_gl_clear": (None, [vp, ci]),
-            "ref_gl_draw_elements": (None, [vp, ci, vp, ci]),
-            "ref_gl_draw_arrays": (None, [vp, ci]),
-            "ref_gl_draw_elements_instanced": (None, [vp, ci, vp, ci]),
-            "ref_gl_draw_arrays_instanced": (None, [vp, ci, ci]),
-            "ref_gl_store_color_tc": (None, [vp, vp, ci, ci, ci, ci]),
-            "ref_gl_store_color_fp": (None, [vp, vp, ci, ci, ci, ci]),
-            "ref_gl_store_color_quads": (None, [vp, vp, ci, ci, ci]),
-            "ref_gl_store_depth": (None, [vp, vp]),
-            "ref_make_mipmap": (None, [vp, ci, vp]),
-            "ref_rcp": (None, [vp, vp, ci]),
-            "ref_rsqrt": (None, [vp, vp, ci]),
-            "ref_oneover": (None, [vp, vp, ci]),
-            "ref_mat4_mul": (None, [vp, vp, vp]),
-            "ref_mat4_inverse": (None, [vp, vp]),
-            "ref_raster_coverage": (None, [vp, ci, ci, vp]),
-            "ref_vraster_coverage": (None, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
-        }
-        for name, (res, args) in sigs.items():
-            fn = getattr(L, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = L
+        _lib = _bind(LIB_PATH)
     return _lib
+
+
+def dropin_lib():
+    """oracle/_ref/librsr_dropin.so: the reference's translation units with GPU::RunImpl replaced by the C-ABI binding
+    (rsr_b200/host/rglv_gpu_cuda.cxx) -- the reference's own GL recording in front of librsrcu.so.  Needs a CUDA device."""
+    global _dropin
+    if _dropin is None:
+        if not dropin_available():
+            raise RuntimeError(f"drop-in library not built: {DROPIN_PATH} (run oracle/build_ref.sh after building librsrcu.so)")
+        _dropin = _bind(DROPIN_PATH)
+    return _dropin
 
 
 def init(threads: int | None = None) -> int:
@@ -107,6 +135,15 @@ def init(threads: int | None = None) -> int:
         _threads = lib().ref_init(int(n))
         atexit.register(lib().ref_shutdown)
     return _threads
+
+
+def init_dropin(threads: int = 2) -> int:
+    """the drop-in library carries its own copy of the job system (GPU::Run is a job): a small pool is enough"""
+    global _dropin_threads
+    if _dropin_threads is None:
+        _dropin_threads = dropin_lib().ref_init(int(threads))
+        atexit.register(dropin_lib().ref_shutdown)
+    return _dropin_threads
 
 
 def _ptr(a: np.ndarray):
@@ -120,9 +157,14 @@ def _f32(a) -> np.ndarray:
 class RefGPU:
     """The reference `rglv::GPU` (with `rqv::Install`ed programs) and its recording `GL` context."""
 
-    def __init__(self, threads: int | None = None, double_buffer: bool = False):
-        init(threads)
-        self.L = lib()
+    def __init__(self, threads: int | None = None, double_buffer: bool = False, dropin: bool = False):
+        if dropin:
+            init_dropin()
+            self.L = dropin_lib()
+        else:
+            init(threads)
+            self.L = lib()
+        self.dropin = dropin
         self.L.ref_set_double_buffer(1 if double_buffer else 0)
         self.h = self.L.ref_gpu_create()
         self._keep = []
@@ -147,6 +189,11 @@ class RefGPU:
         # reference caller sets them right after Reset (node/gpu.cxx:132-133).  Do the same.
         self.RenderbufferType(2, 0)  # GL_COLOR_ATTACHMENT0 <- RB_COLOR_DEPTH
         self.RenderbufferType(0, 0)  # GL_DEPTH_ATTACHMENT  <- RB_COLOR_DEPTH
+
+    def Flush(self):
+        """drop-in, doubleBuffer mode: wait for the frame still in flight on the GPU"""
+        if self.dropin:
+            self.L.ref_dropin_flush(self.h)
 
     def Run(self, manage_workers: bool = True):
         if manage_workers:
