@@ -53,11 +53,10 @@ struct FragIn {
 	const uint32_t* rsqrtLut;
 	float fragX[4], fragY[4];   // gl_FragCoord
 	float depth[4];             // gl_FragDepth
-	float BPx[4], BPy[4], BPz[4]; };
+	float BPx[4], BPy[4], BPz[4];
+	float4* stage; };           // the warp's texel staging area when all 32 lanes shade together (direct rasteriser), else nullptr
 
-#ifndef RSR_TAP_MODE
-#define RSR_TAP_MODE 0
-#endif
+constexpr int kStageTexels = 160;   // texels of per-warp staging for the cooperative sampler (17 x 9 at one texel per pixel)
 
 // ---- texture units (src/rgl/rglr/rglr_texture_sampler.cxx) -------------------------------------
 
@@ -83,31 +82,22 @@ __device__ __forceinline__ void blend_taps(const float4 p00, const float4 p10, c
 	                   mul2(mk2(p11.z, p11.w), a11));
 	r = lo2(rg); g = hi2(rg); b = lo2(ba); a = hi2(ba); }
 
-// The 16 taps of a 2x2 quad collapse to a 3x3 texel footprint when neighbouring pixels are one texel apart
-// (1:1 mapping and magnification): nine loads instead of sixteen, same texels, same weights, same arithmetic.
-// UP = false: the lower pixel pair's first tap row is the upper pair's second one; UP = true: the other way round.
-template <bool UP>
-__device__ __forceinline__ bool taps_share_rows(const uint32_t (&ofs)[4][4]) {
-	constexpr int t0 = UP ? 2 : 0, t1 = UP ? 3 : 1, b0 = UP ? 0 : 2, b1 = UP ? 1 : 3;
-	return (ofs[t1][0] == ofs[t0][1]) && (ofs[t1][2] == ofs[t0][3]) && (ofs[b1][0] == ofs[b0][1]) && (ofs[b1][2] == ofs[b0][3]) &&
-	       (ofs[b0][0] == ofs[t0][2]) && (ofs[b0][1] == ofs[t0][3]) && (ofs[b1][1] == ofs[t1][3]); }
-
-template <bool UP>
-__device__ __forceinline__ void blend_shared_rows(const float4* __restrict__ tex, const uint32_t (&ofs)[4][4],
-                                                  const f2 (&w00)[2], const f2 (&w10)[2], const f2 (&w01)[2], const f2 (&w11)[2],
-                                                  float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4]) {
-	constexpr int t0 = UP ? 2 : 0, t1 = UP ? 3 : 1, b0 = UP ? 0 : 2, b1 = UP ? 1 : 3;
-	const float4 A0 = __ldg(tex + ofs[t0][0]), A1 = __ldg(tex + ofs[t0][1]), A2 = __ldg(tex + ofs[t1][1]);
-	const float4 B0 = __ldg(tex + ofs[t0][2]), B1 = __ldg(tex + ofs[t0][3]), B2 = __ldg(tex + ofs[t1][3]);
-	const float4 C0 = __ldg(tex + ofs[b0][2]), C1 = __ldg(tex + ofs[b0][3]), C2 = __ldg(tex + ofs[b1][3]);
-	auto wt = [&](const f2 (&w)[2], int l) { return (l & 1) ? hi2(w[l >> 1]) : lo2(w[l >> 1]); };
-	blend_taps(A0, A1, B0, B1, wt(w00, t0), wt(w10, t0), wt(w01, t0), wt(w11, t0), r[t0], g[t0], b[t0], a[t0]);
-	blend_taps(A1, A2, B1, B2, wt(w00, t1), wt(w10, t1), wt(w01, t1), wt(w11, t1), r[t1], g[t1], b[t1], a[t1]);
-	blend_taps(B0, B1, C0, C1, wt(w00, b0), wt(w10, b0), wt(w01, b0), wt(w11, b0), r[b0], g[b0], b[b0], a[b0]);
-	blend_taps(B1, B2, C1, C2, wt(w00, b1), wt(w10, b1), wt(w01, b1), wt(w11, b1), r[b1], g[b1], b[b1], a[b1]); }
-
-__device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[4], const float (&v)[4],
-                                            float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4]) {
+// Samples texture unit `tu` at the four pixels of a quad.  `mask`: the pixels whose result is used (the reference
+// samples all four SSE lanes and discards; here unused pixels are skipped and return zeros).
+//
+// Two routes for the bilinear sampler.  GATHER: every tap is a 128-bit load from global memory (L1).  STAGED
+// (f.stage != nullptr: the direct rasteriser, where the 32 lanes of a warp shade the quads of ONE triangle inside
+// a 16x8-pixel region, all of them in this call together): when the quads agree on the level of detail, the taps of
+// the whole region fall into a small box of texels -- 17 x 9 at one texel per pixel.  The warp loads that box once
+// with coalesced 128-bit row loads into its own shared-memory staging area and takes the 16 taps of every quad
+// from there: same texels, same weights, same arithmetic as the gather route (bit-identical), but each texel
+// crosses the L1 tag stage once per warp instead of once per tap, and a tap address is two adds instead of
+// wrap / row / clamp arithmetic.  Staged columns are split by texel-x parity (even columns first, then odd): the
+// lanes of a quarter warp sit two pixels = two texels apart, so their taps then read consecutive 16-byte slots
+// (no bank conflicts).  A box that does not fit (minification near the next level, anisotropy) or quads that
+// disagree on the level take the gather route.
+__device__ __forceinline__ void sample_quad(const FragIn& f, const TexUnit& tu, const float (&u)[4], const float (&v)[4],
+                                            float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], const uint32_t mask) {
 	if (tu.kind == 0) {
 		// TextureUnitRGBAF32_NM_ONEMAP_WRAP_NEAREST (rglr_texture_sampler.cxx:289-311)
 		const float fw = itof(tu.width), fh = itof(tu.height);
@@ -142,17 +132,12 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 	// ..._P2_MIPMAP_WRAP_LINEAR (rglr_texture_sampler.cxx:166-286).  Coordinates and weights are
 	// computed for two pixels at a time (packed pairs); the four taps of one pixel are blended two
 	// channels at a time (the 128-bit texel is two register pairs) with the weight broadcast.
-	// All 16 tap addresses of the quad are formed first so that every texel request is in flight
-	// before the first blend needs its data: pixel 0's taps as loads, the other twelve as L1
-	// prefetches (no destination registers), then the blends load them from L1 pixel by pixel.
 	const int levelDimI = 1 << (POWER - lod);
-	const int wrapMask = levelDimI - 1;
-	const int levelLastRow = static_cast<int>((0xffffffffu << (POWER - lod)) & ((1u << (POWER + 1)) - 1u)) - 1;
 	const float levelDim = itof(levelDimI);
 	const uint32_t lastTexel = tu.texelCount - 1u;
 	const f2 one = one2();
 	const f2 negHalf = dup2(-0.5f);
-	uint32_t ofs[4][4];
+	int tx0[4], ty0[4];
 	f2 w00[2], w10[2], w01[2], w11[2];
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
@@ -160,62 +145,80 @@ __device__ __forceinline__ void sample_quad(const TexUnit& tu, const float (&u)[
 		const f2 levelY = mul2(mk2(v[2 * h], v[2 * h + 1]), levelDim);
 		const f2 sx = add2(levelX, negHalf);   // levelX - 0.5
 		const f2 sy = add2(levelY, negHalf);
-		const int tx0[2] = { cvtt(lo2(sx)), cvtt(hi2(sx)) };
-		const int ty0[2] = { cvtt(lo2(sy)), cvtt(hi2(sy)) };
-		const f2 fx = add2(sub2(levelX, mk2(itof(tx0[0]), itof(tx0[1]))), negHalf);
-		const f2 fy = add2(sub2(levelY, mk2(itof(ty0[0]), itof(ty0[1]))), negHalf);
+		tx0[2 * h] = cvtt(lo2(sx)); tx0[2 * h + 1] = cvtt(hi2(sx));
+		ty0[2 * h] = cvtt(lo2(sy)); ty0[2 * h + 1] = cvtt(hi2(sy));
+		const f2 fx = add2(sub2(levelX, mk2(itof(tx0[2 * h]), itof(tx0[2 * h + 1]))), negHalf);
+		const f2 fy = add2(sub2(levelY, mk2(itof(ty0[2 * h]), itof(ty0[2 * h + 1]))), negHalf);
 		const f2 fx1 = sub2(one, fx);
 		const f2 fy1 = sub2(one, fy);
 		w00[h] = mul2(fx1, fy1);
 		w10[h] = mul2(fx, fy1);
 		w01[h] = mul2(fx1, fy);
-		w11[h] = mul2(fx, fy);
+		w11[h] = mul2(fx, fy); }
+
+	if (f.stage != nullptr) {
+		// ---- STAGED: every lane of the warp is here ---------------------------------------------------------
+		const unsigned full = 0xffffffffu;
+		const unsigned lane = threadIdx.x & 31u;
+		int mnx = 0x7fffffff, mxx = static_cast<int>(0x80000000u), mny = 0x7fffffff, mxy = static_cast<int>(0x80000000u);
 #pragma unroll
-		for (int j = 0; j < 2; ++j) {
-			const int l = 2 * h + j;
-			const int x0 = tx0[j] & wrapMask, x1 = (tx0[j] + 1) & wrapMask;
-			const int by0 = levelLastRow - (ty0[j] & wrapMask);
-			const int by1 = levelLastRow - ((ty0[j] + 1) & wrapMask);
-			// (the reference would read out of bounds for a texture without its mip rows; stay inside)
-			ofs[l][0] = min(static_cast<uint32_t>((by0 << POWER) + x0), lastTexel);
-			ofs[l][1] = min(static_cast<uint32_t>((by0 << POWER) + x1), lastTexel);
-			ofs[l][2] = min(static_cast<uint32_t>((by1 << POWER) + x0), lastTexel);
-			ofs[l][3] = min(static_cast<uint32_t>((by1 << POWER) + x1), lastTexel); } }
-#if RSR_TAP_MODE == 2
+		for (int l = 0; l < 4; ++l) {
+			if ((mask >> l) & 1u) { mnx = min(mnx, tx0[l]); mxx = max(mxx, tx0[l]); mny = min(mny, ty0[l]); mxy = max(mxy, ty0[l]); } }
+		const int lodLo = __reduce_min_sync(full, mask ? lod : 0x7fffffff);
+		const int lodHi = __reduce_max_sync(full, mask ? lod : static_cast<int>(0x80000000u));
+		const int bx0 = __reduce_min_sync(full, mnx), bx1 = __reduce_max_sync(full, mxx);   // (the taps reach one texel further: + 1 below)
+		const int by0 = __reduce_min_sync(full, mny), by1 = __reduce_max_sync(full, mxy);
+		const int me = bx0 & ~1;                                                   // first staged column (even)
+		const unsigned spanX = static_cast<unsigned>(bx1 - me) + 1u, spanY = static_cast<unsigned>(by1 - by0) + 1u;
+		const unsigned half = (spanX >> 1) + 1u;                                   // staged columns per parity
+		const unsigned pitch = 2u * half, rows = spanY + 1u;
+		if (lodLo == lodHi && spanX < 64u && spanY < 64u && pitch <= 32u && pitch * rows <= static_cast<unsigned>(kStageTexels)) {
+			const int shift = POWER - lodLo;
+			const uint32_t wrapMask = (1u << shift) - 1u;
+			const uint32_t lastRow = ((0xffffffffu << shift) & ((1u << (POWER + 1)) - 1u)) - 1u;
+			float4* stage = f.stage;
+			if (lane < pitch) {
+				const unsigned col = lane < half ? lane : lane - half;
+				const uint32_t xw = static_cast<uint32_t>(me + 2 * static_cast<int>(col) + (lane >= half ? 1 : 0)) & wrapMask;
+#pragma unroll 4
+				for (unsigned rr = 0; rr < rows; ++rr) {
+					const uint32_t yw = static_cast<uint32_t>(by0 + static_cast<int>(rr)) & wrapMask;
+					const uint32_t ofs = min(((lastRow - yw) << POWER) + xw, lastTexel);
+					stage[rr * pitch + lane] = __ldg(tu.texels + ofs); } }
+			__syncwarp();
 #pragma unroll
-	for (int l = 1; l < 4; ++l) {
-#pragma unroll
-		for (int k = 0; k < 4; ++k) { asm volatile("prefetch.global.L1 [%0];" :: "l"(tu.texels + ofs[l][k])); } }
-#endif
-#if RSR_TAP_MODE == 3
-	if (taps_share_rows<false>(ofs)) { blend_shared_rows<false>(tu.texels, ofs, w00, w10, w01, w11, r, g, b, a); return; }
-	if (taps_share_rows<true>(ofs)) { blend_shared_rows<true>(tu.texels, ofs, w00, w10, w01, w11, r, g, b, a); return; }
-#endif
-#if RSR_TAP_MODE == 1
-	float4 tap[4][4];
+			for (int l = 0; l < 4; ++l) {
+				if ((mask >> l) & 1u) {
+					const int hh = l >> 1, j = l & 1;
+					const unsigned k = static_cast<unsigned>(tx0[l] - me) >> 1;
+					const bool odd = (tx0[l] & 1) != 0;
+					const unsigned c0 = odd ? k + half : k, c1 = odd ? k + 1u : k + half;
+					const float4* row0 = stage + static_cast<unsigned>(ty0[l] - by0) * pitch;
+					const float4* row1 = row0 + pitch;
+					const float4 p00 = row0[c0], p10 = row0[c1], p01 = row1[c0], p11 = row1[c1];
+					blend_taps(p00, p10, p01, p11, j ? hi2(w00[hh]) : lo2(w00[hh]), j ? hi2(w10[hh]) : lo2(w10[hh]),
+					           j ? hi2(w01[hh]) : lo2(w01[hh]), j ? hi2(w11[hh]) : lo2(w11[hh]), r[l], g[l], b[l], a[l]); }
+				else { r[l] = 0.0f; g[l] = 0.0f; b[l] = 0.0f; a[l] = 0.0f; } }
+			__syncwarp();   // the staging area is free again
+			return; } }
+
+	// ---- GATHER ----------------------------------------------------------------------------------------------
+	const int wrapMask = levelDimI - 1;
+	const int levelLastRow = static_cast<int>((0xffffffffu << (POWER - lod)) & ((1u << (POWER + 1)) - 1u)) - 1;
 #pragma unroll
 	for (int l = 0; l < 4; ++l) {
-#pragma unroll
-		for (int k = 0; k < 4; ++k) { tap[l][k] = __ldg(tu.texels + ofs[l][k]); } }
-#endif
-#pragma unroll
-	for (int l = 0; l < 4; ++l) {
-		const int h = l >> 1, j = l & 1;
-#if RSR_TAP_MODE == 1
-		const float4 p00 = tap[l][0], p10 = tap[l][1], p01 = tap[l][2], p11 = tap[l][3];
-#else
-		const float4 p00 = __ldg(tu.texels + ofs[l][0]);
-		const float4 p10 = __ldg(tu.texels + ofs[l][1]);
-		const float4 p01 = __ldg(tu.texels + ofs[l][2]);
-		const float4 p11 = __ldg(tu.texels + ofs[l][3]);
-#endif
-		const float a00 = j ? hi2(w00[h]) : lo2(w00[h]), a10 = j ? hi2(w10[h]) : lo2(w10[h]);
-		const float a01 = j ? hi2(w01[h]) : lo2(w01[h]), a11 = j ? hi2(w11[h]) : lo2(w11[h]);
-		const f2 rg = add2(add2(add2(mul2(mk2(p00.x, p00.y), a00), mul2(mk2(p10.x, p10.y), a10)), mul2(mk2(p01.x, p01.y), a01)),
-		                   mul2(mk2(p11.x, p11.y), a11));
-		const f2 ba = add2(add2(add2(mul2(mk2(p00.z, p00.w), a00), mul2(mk2(p10.z, p10.w), a10)), mul2(mk2(p01.z, p01.w), a01)),
-		                   mul2(mk2(p11.z, p11.w), a11));
-		r[l] = lo2(rg); g[l] = hi2(rg); b[l] = lo2(ba); a[l] = hi2(ba); } }
+		if (!((mask >> l) & 1u)) { r[l] = 0.0f; g[l] = 0.0f; b[l] = 0.0f; a[l] = 0.0f; continue; }
+		const int hh = l >> 1, j = l & 1;
+		const int x0 = tx0[l] & wrapMask, x1 = (tx0[l] + 1) & wrapMask;
+		const int by0 = levelLastRow - (ty0[l] & wrapMask);
+		const int by1 = levelLastRow - ((ty0[l] + 1) & wrapMask);
+		// (the reference would read out of bounds for a texture without its mip rows; stay inside)
+		const float4 p00 = __ldg(tu.texels + min(static_cast<uint32_t>((by0 << POWER) + x0), lastTexel));
+		const float4 p10 = __ldg(tu.texels + min(static_cast<uint32_t>((by0 << POWER) + x1), lastTexel));
+		const float4 p01 = __ldg(tu.texels + min(static_cast<uint32_t>((by1 << POWER) + x0), lastTexel));
+		const float4 p11 = __ldg(tu.texels + min(static_cast<uint32_t>((by1 << POWER) + x1), lastTexel));
+		blend_taps(p00, p10, p01, p11, j ? hi2(w00[hh]) : lo2(w00[hh]), j ? hi2(w10[hh]) : lo2(w10[hh]),
+		           j ? hi2(w01[hh]) : lo2(w01[hh]), j ? hi2(w11[hh]) : lo2(w11[hh]), r[l], g[l], b[l], a[l]); } }
 
 // DepthTextureUnit::sample (rglr_texture_sampler.hxx:61-79): nearest, clamp-to-border(-1)
 __device__ __forceinline__ float sample_depth(const DevState& st, float cx, float cy) {
@@ -243,15 +246,15 @@ struct ProgAmy : ProgBase {   // shaders.hxx:69-161
 		vary[0] = v.u; vary[1] = v.v;
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
-	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
-		sample_quad(f.st->tu[0], at[0], at[1], r, g, b, a); } };
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
+		sample_quad(f, f.st->tu[0], at[0], at[1], r, g, b, a, mask); } };
 
 struct ProgAlphaTexture : ProgAmy {   // shaders.hxx:164-229
 	static constexpr int id = 65;
 	static constexpr bool earlyZ = false;
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
-		sample_quad(f.st->tu[0], at[0], at[1], r, g, b, a);
+		sample_quad(f, f.st->tu[0], at[0], at[1], r, g, b, a, mask);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { if (!(a[l] > 0.0f)) { mask &= ~(1u << l); } } } };
 
@@ -264,7 +267,7 @@ struct ProgText : ProgBase {   // shaders.hxx:232-318
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
-		sample_quad(f.st->tu[0], at[3], at[4], r, g, b, a);
+		sample_quad(f, f.st->tu[0], at[3], at[4], r, g, b, a, mask);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
 			r[l] *= at[0][l]; g[l] *= at[1][l]; b[l] *= at[2][l];
@@ -286,14 +289,14 @@ struct ProgPattern : ProgBase {   // shaders.hxx:422-479; uniforms: vec4 offset,
 	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float*) {
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&)[kMaxVaryings][4],
-	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
 		const float offx = f.st->uniforms[0], offy = f.st->uniforms[1], dimy = f.st->uniforms[5];
 		float u[4], v[4];
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
 			u[l] = f.fragX[l] / dimy + offx;
 			v[l] = f.fragY[l] / dimy + offy; }
-		sample_quad(f.st->tu[0], u, v, r, g, b, a); } };
+		sample_quad(f, f.st->tu[0], u, v, r, g, b, a, mask); } };
 
 struct ProgMany : ProgBase {   // shaders.hxx:482-583; uniforms: float magic
 	static constexpr int id = 6;
@@ -395,8 +398,8 @@ struct ProgEnvmap : ProgBase {   // shaders_envmap.hxx:26-140
 		vary[1] = ry / m + 0.5f;
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
-	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
-		sample_quad(f.st->tu[0], at[0], at[1], r, g, b, a);
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
+		sample_quad(f, f.st->tu[0], at[0], at[1], r, g, b, a, mask);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { a[l] = 0.5f; } } };
 

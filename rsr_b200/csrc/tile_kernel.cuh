@@ -48,7 +48,7 @@ __device__ unsigned long long g_phaseCycles[16];
 
 constexpr int kSortCap = 1024;           // most list entries sorted in one round
 #ifndef RSR_RUN_CAP
-#define RSR_RUN_CAP 1024
+#define RSR_RUN_CAP 512
 #endif
 constexpr int kRunCap = RSR_RUN_CAP;     // most runs of one cell that the run merge handles
 
@@ -63,7 +63,9 @@ struct TileShared {
 	float iw[3][kBatch];
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
-	uint16_t queue[kTileThreads / 32][160];   // per-warp (triangle, quad) work items awaiting shading
+	// per-warp scratch: the queued rasteriser's (triangle, quad) work items awaiting shading (160 x uint16), or the direct
+	// rasteriser's texel staging area (sample_quad, programs.cuh)
+	float4 warpScratch[kTileThreads / 32][kStageTexels];
 	uint32_t rcpLut[2048];               // rcpps table (dev_math.cuh), staged once per CTA
 	uint32_t sorted[kSortCap];           // triangle codes of the current chunk of the tile list, in submission order
 	uint32_t cellOff[kMaxGroups + 1];    // list offsets of this tile's cells (clamped to the list capacity)
@@ -235,7 +237,9 @@ constexpr uint32_t kKeyFastMask = 0x7eu, kKeyFastValue = 0x62u;
 // FAST: the pipeline flags are the compile-time combination above; otherwise `flags` (uniform for
 // the batch) is decoded at run time.  The four lanes of the reference's SSE registers are two
 // packed pairs here: (0,1) and (2,3).
-template <class P, bool FAST>
+// COOP: all 32 lanes of the warp are in the call (the direct rasteriser: one triangle, every lane its own quad), lanes
+// whose quad is not covered with triMask = 0; they skip the arithmetic but take part in the cooperative texel staging.
+template <class P, bool FAST, bool COOP>
 __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, const int i, const TileArgs& A, const uint32_t flags,
                                                 const DevState& s, const int (&e1)[4], const int (&e2)[4], const uint32_t triMask,
                                                 const int px, const int py, const bool clipped) {
@@ -264,8 +268,9 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 		for (int l = 0; l < 4; ++l) {
 			const float dest = sh.chan[3][l][t];
 			const bool pass = FAST ? (fragDepth[l] < dest) : depth_pass(depthFunc, fragDepth[l], dest);
-			if (!pass) { fragMask &= ~(1u << l); } }
-		if (fragMask == 0) { return 0; } }
+			if (!pass) { fragMask &= ~(1u << l); } } }
+	if (COOP) { if (!__any_sync(0xffffffffu, fragMask != 0)) { return 0; } }
+	else if (fragMask == 0) { return 0; }
 	if (P::earlyZ && depthWrite) {
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { if (fragMask & (1u << l)) { sh.chan[3][l][t] = fragDepth[l]; } } }
@@ -275,6 +280,7 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 	f.st = &s;
 	f.rcpLut = A.luts->rcp;
 	f.rsqrtLut = A.luts->rsqrt;
+	f.stage = COOP ? sh.warpScratch[threadIdx.x >> 5] : nullptr;
 	const float iw0 = sh.iw[0][i], iw1 = sh.iw[1][i], iw2 = sh.iw[2][i];
 	f2 BPx[2], BPy[2], BPz[2], wsum[2], wx[2], wz[2];
 	float rcp[4];
@@ -405,7 +411,7 @@ __device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const Tile
 	const unsigned ltMask = (1u << lane) - 1u;
 	const int rx = (warp & 1) * 16, ry = (warp >> 1) * 8;            // region origin (tile-local)
 	const int lx = rx + (lane & 7) * 2, ly = ry + (lane >> 3) * 2;   // own quad origin
-	uint16_t* queue = sh.queue[warp];
+	uint16_t* queue = reinterpret_cast<uint16_t*>(sh.warpScratch[warp]);
 	unsigned frags = 0;
 	int qn = 0;              // queued items
 	int k = 0, kbase = 0;    // next triangle group / base of the current one
@@ -487,7 +493,7 @@ __device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const Tile
 			if (have && rank == r) {
 				int e1[4], e2[4];
 				const uint32_t covered = quad_coverage(sh, ti, qx, qy, e1, e2);
-				frags += render_quad<P, FAST>(sh, warp * 32 + ql, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + qx, oy + qy,
+				frags += render_quad<P, FAST, false>(sh, warp * 32 + ql, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + qx, oy + qy,
 				                        (sh.bbox[ti] >> 24) & 1u); }
 			__syncwarp(); }
 		// keep the items that did not fit (the queue holds at most 31 + 128)
@@ -522,10 +528,11 @@ __device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const Tile
 			const int j = __ffs(m) - 1;
 			m &= m - 1;
 			const int ti = base + k + j;
-			int e1[4], e2[4];
+			int e1[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
 			const uint32_t covered = quad_coverage(sh, ti, lx, ly, e1, e2);
-			if (covered == 0) { continue; }
-			frags += render_quad<P, FAST>(sh, t, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
+			if (!__any_sync(0xffffffffu, covered != 0)) { continue; }
+			// (all 32 lanes go in, uncovered ones with an empty mask: the texel staging of sample_quad is a warp-wide effort)
+			frags += render_quad<P, FAST, true>(sh, t, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
 	return frags; }
 
 // picks the variant per batch: long batches of small triangles go through the work queue; the
@@ -720,7 +727,7 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const TileArgs& A, con
 			uint32_t* rKey = rStart + kRunCap;
 			uint32_t* rOrder = rKey + kRunCap;
 			static_assert(offsetof(TileShared, vref) - offsetof(TileShared, ec) >= 12 * kRunCap, "run scratch aliases the batch records");
-			uint32_t* warpCnt = reinterpret_cast<uint32_t*>(sh.queue);
+			uint32_t* warpCnt = reinterpret_cast<uint32_t*>(sh.warpScratch);
 			if (t == 0) { sh.sortCount = 0; sh.firstBad = 0; }
 			__syncthreads();
 			for (uint32_t strip = 0; strip < size0; strip += kTileThreads) {
