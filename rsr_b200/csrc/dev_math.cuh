@@ -99,6 +99,32 @@ __device__ __forceinline__ float rcp_fast(float x, const uint32_t* __restrict__ 
 	const uint32_t r = lut[(b >> 12) & 0x7ffu];
 	return u2f(((r + 0x3f800000u) - e) | (b & 0x80000000u)); }
 
+// The same table at 16 bits per entry, as the tile kernel keeps it in shared memory (4 KB instead of 8): every
+// rcpps result for a mantissa in [1, 2) lies in (0.5, 1] -- exponent field 126 -- and carries at most 16
+// significant mantissa bits (Intel: 12), so entry = (bits >> 7) & 0xffff loses nothing.  rcp_table_fits16
+// (host, rsrcu.cu) checks that this holds for the harvested table before a context is created.
+__device__ __forceinline__ uint32_t rcp_entry16(uint32_t bits) { return (bits >> 7) & 0xffffu; }
+__device__ __forceinline__ uint32_t rcp_expand16(uint32_t e16) { return 0x3f000000u | (e16 << 7); }
+
+__device__ __forceinline__ float rcp_fast16(float x, const uint16_t* __restrict__ lut, bool& ok) {
+	const uint32_t b = f2u(x);
+	const uint32_t e = b & 0x7f800000u;
+	ok = ok && ((e - 0x00800000u) < 0x7e000000u);
+	const uint32_t r = lut[(b >> 12) & 0x7ffu];
+	return u2f((((r << 7) + 0x7e800000u) - e) | (b & 0x80000000u)); }   // (0x3f000000 | r << 7) + 0x3f800000 - e
+
+__device__ __forceinline__ float rcp_intel16(float x, const uint16_t* __restrict__ lut) {
+	const uint32_t b = f2u(x);
+	const uint32_t sign = b & 0x80000000u;
+	const int E = static_cast<int>((b >> 23) & 0xffu);
+	const uint32_t m = b & 0x007fffffu;
+	if (E == 0) { return u2f(sign | 0x7f800000u); }
+	if (E == 255) { return m ? u2f(b | 0x00400000u) : u2f(sign); }
+	const uint32_t r = rcp_expand16(lut[m >> 12]);
+	const int re = static_cast<int>(r >> 23) + (127 - E);
+	if (re <= 0) { return u2f(sign); }
+	return u2f(sign | (static_cast<uint32_t>(re) << 23) | (r & 0x007fffffu)); }
+
 // rmlv::oneover (rmlv_mvec4.hxx:630-650): rcpps + one Newton-Raphson step
 __device__ __forceinline__ float oneover(float a, const uint32_t* __restrict__ rcpLut) {
 	const float r = rcp_intel(a, rcpLut);

@@ -56,7 +56,7 @@ struct FragIn {
 	float BPx[4], BPy[4], BPz[4];
 	float4* stage; };           // the warp's texel staging area when all 32 lanes shade together (direct rasteriser), else nullptr
 
-constexpr int kStageTexels = 160;   // texels of per-warp staging for the cooperative sampler (17 x 9 at one texel per pixel)
+constexpr int kStageTexels = 208;   // texels of per-warp staging for the cooperative sampler (a 16x8-pixel region at one texel per pixel: <= 20 x 10)
 
 // ---- texture units (src/rgl/rglr/rglr_texture_sampler.cxx) -------------------------------------
 

@@ -199,7 +199,7 @@ struct rsrcu_ctx {
 	// device work buffers
 	// the frame's intermediate buffers; two sets so that, in overlap mode, the front end (K0-K5) of frame N+1 can fill one
 	// set while the tile kernel of frame N still reads the other
-	struct WorkSet { DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems; } sets[2];
+	struct WorkSet { DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems, runScratch; } sets[2];
 	cudaStream_t frontStream{nullptr};   // overlap mode: K0-K5 run here (high priority), the tile kernel on `stream`
 	cudaEvent_t evFrontDone[2]{}, evTileDone[2]{};
 	bool overlap{false};
@@ -235,6 +235,11 @@ struct rsrcu_ctx {
 };
 
 namespace {
+
+// the tile kernel keeps the rcpps table at 16 bits per entry (dev_math.cuh: rcp_entry16)
+bool rcpTableFits16(const uint32_t* rcp2048) {
+	for (int i = 0; i < 2048; ++i) { if ((rcp2048[i] >> 23) != 126u || (rcp2048[i] & 0x7fu) != 0u) { return false; } }
+	return true; }
 
 int keyOf(const RsrState& s) {
 	uint32_t key = 0;
@@ -503,6 +508,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	CU(w.tileOrder.reserve(static_cast<size_t>(ntiles) * 4));
 	CU(w.lists.reserve(static_cast<size_t>(c->listCapacity) * sizeof(uint2)));
 	CU(w.largeItems.reserve(static_cast<size_t>(c->largeCapacity) * sizeof(LargeItem)));
+	CU(w.runScratch.reserve(static_cast<size_t>(ntiles) * 2 * kRunCap * sizeof(uint32_t)));
 
 	const uint8_t* ab = arenaDev;
 	const DevState* dStates = reinterpret_cast<const DevState*>(ab + offStates);
@@ -571,6 +577,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	ta.cellRel = bin.cellRel;
 	ta.large = bin.large;
 	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
+	ta.runScratch = static_cast<uint32_t*>(w.runScratch.ptr);
 	ta.ctr = dCtr;
 	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
 	++c->launches;
@@ -632,6 +639,9 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 		delete c;
 		return fail(RSRCU_ERR_UNSUPPORTED, "host rcpps/rsqrtps do not follow the table model (%llu mismatches); "
 		            "bit-exact parity with the reference on this CPU is not possible", static_cast<unsigned long long>(mismatches)); }
+	if (!rcpTableFits16(c->hostLuts.rcp)) {
+		delete c;
+		return fail(RSRCU_ERR_UNSUPPORTED, "host rcpps results do not fit the 16-bit table the tile kernel uses (exponent 126, <= 16 mantissa bits)"); }
 	c->hostProf = std::getenv("RSRCU_HOST_PROF") != nullptr;
 	if (std::getenv("RSRCU_TRACE")) {
 		c->trace = true;
@@ -669,7 +679,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	for (auto& w : c->sets) {
-		for (DevBuf* b : { &w.ptvb, &w.vflags, &w.triInfo, &w.triRecs, &w.clipRecs, &w.tileBase, &w.cellRel, &w.tileTotal, &w.tileOrder, &w.lists, &w.largeItems }) { b->release(); } }
+		for (DevBuf* b : { &w.ptvb, &w.vflags, &w.triInfo, &w.triRecs, &w.clipRecs, &w.tileBase, &w.cellRel, &w.tileTotal, &w.tileOrder, &w.lists, &w.largeItems, &w.runScratch }) { b->release(); } }
 	for (auto& b : c->counters) { b.release(); }
 	for (auto& pool : c->storePool) { for (auto& b : pool) { b.release(); } }
 	for (auto& a : c->arenas) { a.release(); }
@@ -689,6 +699,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 
 int rsrcu_set_host_luts(rsrcu_ctx* c, const uint32_t* rcp2048, const uint32_t* rsqrt2x1024) {
 	if (!c || !rcp2048 || !rsqrt2x1024) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (!rcpTableFits16(rcp2048)) { return fail(RSRCU_ERR_UNSUPPORTED, "rcpps table does not fit the 16-bit form the tile kernel uses (exponent 126, <= 16 mantissa bits)"); }
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));

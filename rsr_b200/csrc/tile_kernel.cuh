@@ -48,7 +48,7 @@ __device__ unsigned long long g_phaseCycles[16];
 
 constexpr int kSortCap = 1024;           // most list entries sorted in one round
 #ifndef RSR_RUN_CAP
-#define RSR_RUN_CAP 512
+#define RSR_RUN_CAP 1024
 #endif
 constexpr int kRunCap = RSR_RUN_CAP;     // most runs of one cell that the run merge handles
 
@@ -66,14 +66,13 @@ struct TileShared {
 	// per-warp scratch: the queued rasteriser's (triangle, quad) work items awaiting shading (160 x uint16), or the direct
 	// rasteriser's texel staging area (sample_quad, programs.cuh)
 	float4 warpScratch[kTileThreads / 32][kStageTexels];
-	uint32_t rcpLut[2048];               // rcpps table (dev_math.cuh), staged once per CTA
+	uint16_t rcpLut[2048];               // rcpps table at 16 bits per entry (dev_math.cuh: rcp_entry16), staged once per CTA
 	uint32_t sorted[kSortCap];           // triangle codes of the current chunk of the tile list, in submission order
 	uint32_t cellOff[kMaxGroups + 1];    // list offsets of this tile's cells (clamped to the list capacity)
 	uint32_t lgKey[kTileLargeCap], lgCode[kTileLargeCap];   // queued large items that cover this tile
 	uint8_t lgGroup[kTileLargeCap];
 	alignas(4) uint16_t lgPerGroup[kMaxGroups];
 	int lgCount;
-	uint32_t runStart[kRunCap], runPre[kRunCap];   // long cell in run mode: start of each run / entries before it, in key order
 	uint32_t srgbTab[104];               // ryg table: per-pixel indices diverge, constant memory would serialise
 	int firstBad;
 	int sortCount;
@@ -105,6 +104,7 @@ struct TileArgs {
 	const uint32_t* cellRel;             // [tile * groups + g]: offset of the cell inside the tile's list (groups > 1)
 	const LargeItem* large;              // queued large items (kernels.cuh)
 	const uint32_t* tileOrder;           // CTA -> tile, tiles with the longest lists first (nullptr: identity)
+	uint32_t* runScratch;                // [tile][2 x kRunCap]: run tables of a long list cell (load_chunk, mode B)
 	Counters* ctr; };
 
 __device__ __forceinline__ void prefetch_entry(const TileArgs& A, uint32_t id) {
@@ -237,6 +237,9 @@ constexpr uint32_t kKeyFastMask = 0x7eu, kKeyFastValue = 0x62u;
 // FAST: the pipeline flags are the compile-time combination above; otherwise `flags` (uniform for
 // the batch) is decoded at run time.  The four lanes of the reference's SSE registers are two
 // packed pairs here: (0,1) and (2,3).
+#ifndef RSR_STAGE_MIN_LANES
+#define RSR_STAGE_MIN_LANES 12
+#endif
 // COOP: all 32 lanes of the warp are in the call (the direct rasteriser: one triangle, every lane its own quad), lanes
 // whose quad is not covered with triMask = 0; they skip the arithmetic but take part in the cooperative texel staging.
 template <class P, bool FAST, bool COOP>
@@ -269,7 +272,10 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 			const float dest = sh.chan[3][l][t];
 			const bool pass = FAST ? (fragDepth[l] < dest) : depth_pass(depthFunc, fragDepth[l], dest);
 			if (!pass) { fragMask &= ~(1u << l); } } }
-	if (COOP) { if (!__any_sync(0xffffffffu, fragMask != 0)) { return 0; } }
+	// (COOP: texel staging pays when the triangle fills a good part of the warp's region; a triangle that touches a few
+	// quads samples with plain gathers)
+	unsigned activeLanes = 0;
+	if (COOP) { activeLanes = __ballot_sync(0xffffffffu, fragMask != 0); if (activeLanes == 0) { return 0; } }
 	else if (fragMask == 0) { return 0; }
 	if (P::earlyZ && depthWrite) {
 #pragma unroll
@@ -280,7 +286,7 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 	f.st = &s;
 	f.rcpLut = A.luts->rcp;
 	f.rsqrtLut = A.luts->rsqrt;
-	f.stage = COOP ? sh.warpScratch[threadIdx.x >> 5] : nullptr;
+	f.stage = (COOP && __popc(activeLanes) >= RSR_STAGE_MIN_LANES) ? sh.warpScratch[threadIdx.x >> 5] : nullptr;
 	const float iw0 = sh.iw[0][i], iw1 = sh.iw[1][i], iw2 = sh.iw[2][i];
 	f2 BPx[2], BPy[2], BPz[2], wsum[2], wx[2], wz[2];
 	float rcp[4];
@@ -290,13 +296,13 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 		wx[h] = mul2(BSx[h], iw0);
 		wz[h] = mul2(BSz[h], iw2);
 		wsum[h] = add2(add2(wx[h], mul2(BSy[h], iw1)), wz[h]);
-		rcp[2 * h] = rcp_fast(lo2(wsum[h]), sh.rcpLut, ok);
-		rcp[2 * h + 1] = rcp_fast(hi2(wsum[h]), sh.rcpLut, ok); }
+		rcp[2 * h] = rcp_fast16(lo2(wsum[h]), sh.rcpLut, ok);
+		rcp[2 * h + 1] = rcp_fast16(hi2(wsum[h]), sh.rcpLut, ok); }
 	if (!ok) {
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			rcp[2 * h] = rcp_intel(lo2(wsum[h]), sh.rcpLut);
-			rcp[2 * h + 1] = rcp_intel(hi2(wsum[h]), sh.rcpLut); } }
+			rcp[2 * h] = rcp_intel16(lo2(wsum[h]), sh.rcpLut);
+			rcp[2 * h + 1] = rcp_intel16(hi2(wsum[h]), sh.rcpLut); } }
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
 		// oneover (rmlv_mvec4.hxx:630-650): r = rcpps(a); (r + r) - a * (r * r)
@@ -649,7 +655,8 @@ struct ListCursor {
 	int mode;              // of cell g: 0 = undecided / B, 2 = C
 	int runs;              // B: runs of cell g (0 = not analysed yet)
 	uint32_t nextKey;      // C: pending entries of cell g have order keys >= nextKey
-	uint32_t span; };
+	uint32_t span;
+	uint32_t* runTab; };   // B: this tile's run tables in global memory: [kRunCap] start of each run, [kRunCap] entries before it, in key order
 
 __device__ __forceinline__ void sort_scratch(TileShared& sh, uint2* scr, const int n, const uint32_t begin, const int g0, const int gEnd) {
 	const int t = threadIdx.x;
@@ -780,8 +787,8 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const TileArgs& A, con
 				for (int w = 0; w < warp; ++w) { before += warpCnt[w]; }
 				for (int p = p0; p < p1; ++p) {
 					const uint32_t r = rOrder[p];
-					sh.runStart[p] = rStart[r];
-					sh.runPre[p] = before;
+					lc.runTab[p] = rStart[r];
+					lc.runTab[kRunCap + p] = before;
 					before += ((r + 1 < static_cast<uint32_t>(R)) ? rStart[r + 1] : size0) - rStart[r]; }
 				__syncthreads();
 				if (sh.firstBad == 0) { lc.runs = R; } }
@@ -795,8 +802,8 @@ __device__ __forceinline__ int load_chunk(TileShared& sh, const TileArgs& A, con
 				int lo = 0, hi = R - 1;
 				while (lo < hi) {
 					const int mid = (lo + hi + 1) >> 1;
-					if (sh.runPre[mid] <= pos) { lo = mid; } else { hi = mid - 1; } }
-				const uint32_t code = __ldg(list + sh.runStart[lo] + (pos - sh.runPre[lo])).y & ~kRunStartBit;
+					if (lc.runTab[kRunCap + mid] <= pos) { lo = mid; } else { hi = mid - 1; } }
+				const uint32_t code = __ldg(list + lc.runTab[lo] + (pos - lc.runTab[kRunCap + lo])).y & ~kRunStartBit;
 				sh.sorted[i] = code;
 				prefetch_entry(A, code); }
 			lc.taken += static_cast<uint32_t>(n);
@@ -968,7 +975,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	// approximation tables, constants): with programmatic dependent launch this prologue runs while the
 	// list fill kernel is still draining.
 #pragma unroll
-	for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = __ldg(A.luts->rcp + k * kTileThreads + t); }
+	for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = static_cast<uint16_t>(rcp_entry16(__ldg(A.luts->rcp + k * kTileThreads + t))); }
 	if (t < 104) { sh.srgbTab[t] = kSrgbTab4[t]; }
 	if (t < kMaxGroups) { sh.lgPerGroup[t] = 0; }
 	if (t == 0) { sh.lgCount = 0; }
@@ -1012,7 +1019,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		__syncthreads();
 		if (t == 0) { atomicOr(&A.ctr->overflow, 8u); sh.lgCount = kTileLargeCap; }
 		__syncthreads(); }
-	ListCursor lc{0, 0u, 0, 0, 0u, 1u};
+	ListCursor lc{0, 0u, 0, 0, 0u, 1u, A.runScratch + static_cast<size_t>(tile) * (2 * kRunCap)};
 	int chunkN = 0, chunkPos = 0;
 	unsigned frags = 0;
 
