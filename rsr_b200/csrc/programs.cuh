@@ -56,7 +56,12 @@ struct FragIn {
 	float BPx[4], BPy[4], BPz[4];
 	float4* stage; };           // the warp's texel staging area when all 32 lanes shade together (direct rasteriser), else nullptr
 
-constexpr int kStageTexels = 208;   // texels of per-warp staging for the cooperative sampler (a 16x8-pixel region at one texel per pixel: <= 20 x 10)
+#ifndef RSR_COOP_STAGE
+#define RSR_COOP_STAGE 0
+#endif
+// texels of per-warp staging for the cooperative sampler (a 16x8-pixel region at one texel per pixel: <= 20 x 10); without
+// it the per-warp scratch only holds the queued rasteriser's work items (160 x uint16 = 20 texels' worth)
+constexpr int kStageTexels = RSR_COOP_STAGE ? 208 : 20;
 
 // ---- texture units (src/rgl/rglr/rglr_texture_sampler.cxx) -------------------------------------
 

@@ -240,6 +240,9 @@ constexpr uint32_t kKeyFastMask = 0x7eu, kKeyFastValue = 0x62u;
 #ifndef RSR_STAGE_MIN_LANES
 #define RSR_STAGE_MIN_LANES 12
 #endif
+#ifndef RSR_COOP_STAGE
+#define RSR_COOP_STAGE 0   // 1: the direct rasteriser stages texel boxes in shared memory (sample_quad); measured slower than gathers, see profiles/README.md
+#endif
 // COOP: all 32 lanes of the warp are in the call (the direct rasteriser: one triangle, every lane its own quad), lanes
 // whose quad is not covered with triMask = 0; they skip the arithmetic but take part in the cooperative texel staging.
 template <class P, bool FAST, bool COOP>
@@ -374,6 +377,21 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 					sh.chan[2][l][t] = cb[l]; } } } }
 	return __popc(fragMask); }
 
+// Can triangle ti cover any pixel of the region [x0, x1] x [y0, y1] (tile-local pixel coordinates, inclusive; whole quads: x0, y0 even, x1, y1 odd)?  Each
+// edge function is evaluated at the region corner where it is largest; if it is negative there it is negative at
+// every pixel of the region and the per-quad tests can be skipped.  The edge functions live in wrapping 32-bit
+// arithmetic (the reference's 4-wide setup, rglv_triangle.hxx:216-238): the shortcut is taken only when the
+// corner value is far enough from INT_MIN that no pixel of the region can have wrapped past it (a pixel's value is
+// the corner's minus less than 2^23), so the answer is exactly what the per-pixel tests would give.
+__device__ __forceinline__ bool region_may_be_covered(const TileShared& sh, int ti, int x0, int y0, int x1, int y1) {
+#pragma unroll
+	for (int e = 0; e < 3; ++e) {
+		const int dy = sh.edy[e][ti], dx = sh.edx[e][ti];
+		const uint32_t cx = static_cast<uint32_t>(dy > 0 ? x1 : x0), cy = static_cast<uint32_t>(dx > 0 ? y1 : y0);
+		const int emax = static_cast<int>(static_cast<uint32_t>(sh.ec[e][ti]) + cx * static_cast<uint32_t>(dy) + cy * static_cast<uint32_t>(dx));
+		if (emax < 0 && emax > static_cast<int>(0x80000000u) + (1 << 23) && abs(dy) < (1 << 17) && abs(dx) < (1 << 17)) { return false; } }
+	return true; }
+
 // edge functions of triangle ti at the four pixels of the quad whose tile-local origin is (lx, ly);
 // returns the coverage mask (bit l = lane l inside all three edges); 0 if the quad is outside the
 // triangle's bbox (the reference never visits it)
@@ -437,6 +455,7 @@ __device__ __forceinline__ unsigned draw_batch_queued(TileShared& sh, const Tile
 					const uint32_t bb = sh.bbox[i];
 					const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
 					hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry);
+					hit = hit && region_may_be_covered(sh, i, max(minx, rx), max(miny, ry), (min(maxx, rx + 16) - 1) | 1, (min(maxy, ry + 8) - 1) | 1);
 					if (hit) {
 						bqx0 = (max(minx, rx) - rx) >> 1; bqx1 = (min(maxx, rx + 16) - 1 - rx) >> 1;
 						bqy0 = (max(miny, ry) - ry) >> 1; bqy1 = (min(maxy, ry + 8) - 1 - ry) >> 1;
@@ -528,17 +547,25 @@ __device__ __forceinline__ unsigned draw_batch_direct(TileShared& sh, const Tile
 		if (k + lane < nb) {
 			const uint32_t bb = sh.bbox[i];
 			const int minx = bb & 63, miny = (bb >> 6) & 63, maxx = (bb >> 12) & 63, maxy = (bb >> 18) & 63;
-			hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry); }
+			hit = (minx < rx + 16) && (maxx > rx) && (miny < ry + 8) && (maxy > ry);
+			hit = hit && region_may_be_covered(sh, i, max(minx, rx), max(miny, ry), (min(maxx, rx + 16) - 1) | 1, (min(maxy, ry + 8) - 1) | 1); }
 		unsigned m = __ballot_sync(0xffffffffu, hit);
 		while (m) {
 			const int j = __ffs(m) - 1;
 			m &= m - 1;
 			const int ti = base + k + j;
+#if RSR_COOP_STAGE
 			int e1[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
 			const uint32_t covered = quad_coverage(sh, ti, lx, ly, e1, e2);
 			if (!__any_sync(0xffffffffu, covered != 0)) { continue; }
 			// (all 32 lanes go in, uncovered ones with an empty mask: the texel staging of sample_quad is a warp-wide effort)
 			frags += render_quad<P, FAST, true>(sh, t, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
+#else
+			int e1[4], e2[4];
+			const uint32_t covered = quad_coverage(sh, ti, lx, ly, e1, e2);
+			if (covered == 0) { continue; }
+			frags += render_quad<P, FAST, false>(sh, t, ti, A, flags, A.states[sh.state[ti]], e1, e2, covered, ox + lx, oy + ly, (sh.bbox[ti] >> 24) & 1u); } }
+#endif
 	return frags; }
 
 // picks the variant per batch: long batches of small triangles go through the work queue; the
