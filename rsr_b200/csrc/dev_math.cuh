@@ -19,6 +19,7 @@ namespace rsr {
 struct ApproxLuts {
 	uint32_t rcp[2048];
 	uint32_t rsqrt[2048];
+	alignas(16) uint16_t rcp16[2048];   // rcp at 16 bits per entry (rcp_entry16 below), what the tile kernel stages in shared memory
 };
 
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }

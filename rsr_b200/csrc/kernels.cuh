@@ -196,10 +196,14 @@ __device__ __forceinline__ void run_vertex_program(const DevState& s, const Vert
 
 __global__ void __launch_bounds__(256)
 vertex_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
-              const ApproxLuts* __restrict__ luts, float4* __restrict__ ptvb, uint8_t* __restrict__ vflags) {
+              const ApproxLuts* __restrict__ luts, float4* __restrict__ ptvb, uint8_t* __restrict__ vflags,
+              uint4* __restrict__ zero, uint32_t nzero16) {
 	pdl_launch_dependents();
 	pdl_wait();
 	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
+	// a replayed (retained) frame has nothing to upload: its first kernel is this one, and it zeroes the frame's control
+	// block (counters, cell counts and cursors) instead of a separate K0 launch
+	for (uint32_t i = job; i < nzero16; i += gridDim.x * blockDim.x) { zero[i] = make_uint4(0u, 0u, 0u, 0u); }
 	const int di = find_draw(draws, blockDraw, min(job, fp.totalVJobs - 1u), true);
 	if (job >= fp.totalVJobs) { return; }
 	const DevDraw& d = draws[di];

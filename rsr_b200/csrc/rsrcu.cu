@@ -527,7 +527,9 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
-	{
+	// (a replayed frame has nothing to upload: the vertex kernel zeroes the control block itself)
+	const bool zeroInVertexKernel = uploadBytes == 0 && fp.totalVJobs > 0;
+	if (!zeroInVertexKernel) {
 		// K0: upload + zeroed control block in one kernel (kernels.cuh)
 		const size_t n16 = (uploadBytes + 15) / 16, nz16 = (ctrlBytes + 15) / 16;
 		const int blocks = static_cast<int>(std::min<size_t>(148 * 8, (std::max(n16, nz16) + 255) / 256));
@@ -542,7 +544,8 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 
 	if (fp.totalVJobs) {
 		CU(launchPdl(vertex_kernel, (fp.totalVJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
-			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(w.ptvb.ptr), static_cast<uint8_t*>(w.vflags.ptr)));
+			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(w.ptvb.ptr), static_cast<uint8_t*>(w.vflags.ptr),
+			reinterpret_cast<uint4*>(dCtr), zeroInVertexKernel ? static_cast<uint32_t>((ctrlBytes + 15) / 16) : 0u));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
 	if (fp.totalPJobs) {
@@ -653,6 +656,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 		const long v = std::atol(cap);
 		if (v > 0) { c->listCapacity = static_cast<uint32_t>(v); } }
 	CU(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TileShared))));
+	for (int i = 0; i < 2048; ++i) { c->hostLuts.rcp16[i] = static_cast<uint16_t>((c->hostLuts.rcp[i] >> 7) & 0xffffu); }
 	CU(cudaMalloc(&c->devLuts, sizeof(ApproxLuts)));
 	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
 	CU(cudaMallocHost(&c->hostCounters, kSlots * sizeof(Counters)));
@@ -705,6 +709,7 @@ int rsrcu_set_host_luts(rsrcu_ctx* c, const uint32_t* rcp2048, const uint32_t* r
 	CU(cudaStreamSynchronize(c->stream));
 	std::memcpy(c->hostLuts.rcp, rcp2048, sizeof(c->hostLuts.rcp));
 	std::memcpy(c->hostLuts.rsqrt, rsqrt2x1024, sizeof(c->hostLuts.rsqrt));
+	for (int i = 0; i < 2048; ++i) { c->hostLuts.rcp16[i] = static_cast<uint16_t>((c->hostLuts.rcp[i] >> 7) & 0xffffu); }
 	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
 	return RSRCU_OK; }
 

@@ -66,7 +66,7 @@ struct TileShared {
 	// per-warp scratch: the queued rasteriser's (triangle, quad) work items awaiting shading (160 x uint16), or the direct
 	// rasteriser's texel staging area (sample_quad, programs.cuh)
 	float4 warpScratch[kTileThreads / 32][kStageTexels];
-	uint16_t rcpLut[2048];               // rcpps table at 16 bits per entry (dev_math.cuh: rcp_entry16), staged once per CTA
+	alignas(16) uint16_t rcpLut[2048];   // rcpps table at 16 bits per entry (dev_math.cuh: rcp_entry16), staged once per CTA
 	uint32_t sorted[kSortCap];           // triangle codes of the current chunk of the tile list, in submission order
 	uint32_t cellOff[kMaxGroups + 1];    // list offsets of this tile's cells (clamped to the list capacity)
 	uint32_t lgKey[kTileLargeCap], lgCode[kTileLargeCap];   // queued large items that cover this tile
@@ -896,28 +896,41 @@ __device__ __forceinline__ void exec_cmds(TileShared& sh, const TileArgs& A, int
 			break;
 		case kCmdStoreTC: {
 			// GPUBltImpl::StoreTrueColor -> FilterTile<SHADER, sRGB|LinearColor>
-			if (onScreen) {
-				uint32_t out[4];
+			// (every lane converts its quad, on screen or not: the lanes of a pair exchange halves below)
+			uint32_t out[4];
 #pragma unroll
-				for (int l = 0; l < 4; ++l) {
-					float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
-					if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
-						const float ex = s.uniform0;
-						r = r * ex; g = g * ex; b = b * ex; }
-					else if (s.programId == 3) {
-						// FilterTile's running fragment coordinate (rglr_algorithm.hxx:75-96): starts at the
-						// reference tile's left/top edge and is advanced by repeated float adds per quad
-						const int ptx = (px / A.fp.postTileW) * A.fp.postTileW, pty = (py / A.fp.postTileH) * A.fp.postTileH;
-						const float iw = 1.0f / itof(A.fp.width), ih = 1.0f / itof(A.fp.height);
-						float fcx = (itof(ptx) + 0.5f) / itof(A.fp.width) + ((l & 1) ? iw : 0.0f);
-						float fcy = ((itof(A.fp.height - pty)) - 0.5f) / itof(A.fp.height) - ((l & 2) ? ih : 0.0f);
-						const float fcdx = iw * 2.0f, fcdy = -ih * 2.0f;
-						for (int kx = ptx; kx < px; kx += 2) { fcx += fcdx; }
-						for (int ky = pty; ky < py; ky += 2) { fcy += fcdy; }
-						post_iq(r, g, b, fcx, fcy); }
-					out[l] = (cmd.arg & 1) ? ((srgb8(r, sh.srgbTab) << 16) | (srgb8(g, sh.srgbTab) << 8) | srgb8(b, sh.srgbTab))
-					                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
-				uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
+			for (int l = 0; l < 4; ++l) {
+				float r = sh.chan[0][l][t], g = sh.chan[1][l][t], b = sh.chan[2][l][t];
+				if (s.programId == 2) {   // ExposurePostProgram (shaders.hxx:40-53)
+					const float ex = s.uniform0;
+					r = r * ex; g = g * ex; b = b * ex; }
+				else if (s.programId == 3) {
+					// FilterTile's running fragment coordinate (rglr_algorithm.hxx:75-96): starts at the
+					// reference tile's left/top edge and is advanced by repeated float adds per quad
+					const int ptx = (px / A.fp.postTileW) * A.fp.postTileW, pty = (py / A.fp.postTileH) * A.fp.postTileH;
+					const float iw = 1.0f / itof(A.fp.width), ih = 1.0f / itof(A.fp.height);
+					float fcx = (itof(ptx) + 0.5f) / itof(A.fp.width) + ((l & 1) ? iw : 0.0f);
+					float fcy = ((itof(A.fp.height - pty)) - 0.5f) / itof(A.fp.height) - ((l & 2) ? ih : 0.0f);
+					const float fcdx = iw * 2.0f, fcdy = -ih * 2.0f;
+					for (int kx = ptx; kx < px; kx += 2) { fcx += fcdx; }
+					for (int ky = pty; ky < py; ky += 2) { fcy += fcdy; }
+					post_iq(r, g, b, fcx, fcy); }
+				out[l] = (cmd.arg & 1) ? ((srgb8(r, sh.srgbTab) << 16) | (srgb8(g, sh.srgbTab) << 8) | srgb8(b, sh.srgbTab))
+				                       : ((linear8(r) << 16) | (linear8(g) << 8) | linear8(b)); }
+			// 128-bit stores: lanes 2k and 2k+1 hold horizontally adjacent quads (4 x 2 pixels); they swap halves so that
+			// the even lane writes the four pixels of the upper row and the odd lane those of the lower row -- a tile row is
+			// eight 16-byte stores = one full 128-byte line.  Needs 16-byte aligned rows (destination, stride and width
+			// multiples of 4 pixels: then both lanes of a pair are on screen together); otherwise 64-bit stores.
+			uint32_t* dst = static_cast<uint32_t*>(cmd.dst);
+			const bool wide = ((reinterpret_cast<uintptr_t>(dst) | (static_cast<uintptr_t>(cmd.dstStride) * 4u)) & 15u) == 0 && (A.fp.width & 3) == 0;
+			if (wide) {
+				const bool odd = (threadIdx.x & 1) != 0;
+				const uint32_t give0 = odd ? out[0] : out[2], give1 = odd ? out[1] : out[3];
+				const uint32_t got0 = __shfl_xor_sync(0xffffffffu, give0, 1), got1 = __shfl_xor_sync(0xffffffffu, give1, 1);
+				if (onScreen) {
+					if (!odd) { *reinterpret_cast<uint4*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint4(out[0], out[1], got0, got1); }
+					else { *reinterpret_cast<uint4*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + (px - 2)) = make_uint4(got0, got1, out[2], out[3]); } } }
+			else if (onScreen) {
 				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py) * cmd.dstStride + px) = make_uint2(out[0], out[1]);
 				*reinterpret_cast<uint2*>(dst + static_cast<size_t>(py + 1) * cmd.dstStride + px) = make_uint2(out[2], out[3]); } }
 			break;
@@ -1001,8 +1014,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	// Everything up to the grid dependency wait touches only data that no kernel of the frame writes (the
 	// approximation tables, constants): with programmatic dependent launch this prologue runs while the
 	// list fill kernel is still draining.
-#pragma unroll
-	for (int k = 0; k < 2048 / kTileThreads; ++k) { sh.rcpLut[k * kTileThreads + t] = static_cast<uint16_t>(rcp_entry16(__ldg(A.luts->rcp + k * kTileThreads + t))); }
+	reinterpret_cast<uint4*>(sh.rcpLut)[t] = __ldg(reinterpret_cast<const uint4*>(A.luts->rcp16) + t);   // 2048 x 16 bit = 256 x 16 bytes
 	if (t < 104) { sh.srgbTab[t] = kSrgbTab4[t]; }
 	if (t < kMaxGroups) { sh.lgPerGroup[t] = 0; }
 	if (t == 0) { sh.lgCount = 0; }
