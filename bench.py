@@ -488,6 +488,10 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist)
     gpu.EnablePeerAccess(pf.presenter_device)
     token = torch.zeros(1, dtype=torch.int32, device=dev)
+    flags = p2p and args.barrier == "flag"
+    units_done = 0       # value of the completion counter after the frames launched so far (same arithmetic on every rank)
+    if flags:
+        gpu.SetCompletionCounter(pf.counter_pointer())
 
     def retain(subframes, local=None):
         out = []
@@ -525,6 +529,10 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     checksum1 = None
     if rank == 0:
         alone = retain(plan.subframes)
+        if flags:
+            gpu.Sync()
+            pf.local_counter.zero_()     # (the retaining submits counted too)
+            torch.cuda.synchronize()
         def step_alone():
             for fr in alone:
                 gpu.Replay(fr)
@@ -553,19 +561,45 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
             gpu.Release(fr)
         pf.local.zero_()
     barrier()
+    if flags:
+        gpu.Sync()
+        barrier()
+        if rank == 0:
+            pf.local_counter.zero_()
+        barrier()
 
     # ---- split over the ranks ------------------------------------------------------------------------------
     mine = plan.owned_by(rank)
     if p2p:
         retained = retain(mine)
+        if flags:
+            gpu.Sync()
+            barrier()
+            if rank == 0:
+                pf.local_counter.zero_()
+            barrier()
     else:
         local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
         retained = retain(mine, local)
         gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
 
+    nunits = len(plan.subframes)
+
     def step():
+        nonlocal units_done
         for fr in retained:
             gpu.Replay(fr)
+        if flags:
+            # no host-side barrier, no collective: every tile kernel adds 1 to the counter in the presenter's memory
+            # when its last CTA is done; the presenter's stream waits until all units of this frame have arrived
+            units_done += nunits
+            if rank == 0:
+                gpu.WaitCounter(pf.counter_pointer(), units_done)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(stream):
+                done.record(stream)
+            cur.wait_event(done)
+            return
         done = torch.cuda.Event()
         with torch.cuda.stream(stream):
             done.record(stream)
@@ -595,7 +629,9 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     rec = None
     if rank == 0:
         checksum = int(pf.local.to(torch.int64).sum().item())
-        exchange = "none" if world == 1 else ("tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce as barrier"
+        exchange = "none" if world == 1 else (("tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory); completion = a counter in the presenter's "
+                                               "memory that every rank's last tile CTA increments (system-scope atomic), the presenter's stream waits on it: no host barrier, no collective"
+                                               if flags else "tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce as barrier")
                                               if p2p else "NCCL gather of resolved sub-frames to rank 0 + assembly copies")
         remote = sum(1 for s in plan.subframes if s.owner != 0)
         rec = {"metric": "frames_per_sec_8k_split_frame", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
@@ -642,6 +678,7 @@ def main():
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
     ap.add_argument("--balance", default="roundrobin", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="split-frame: how resolved pixels reach the presenting GPU")
+    ap.add_argument("--barrier", default="flag", choices=["flag", "nccl"], help="split-frame with p2p stores: completion counter in the presenter's memory, or an NCCL all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

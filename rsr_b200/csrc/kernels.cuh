@@ -117,7 +117,8 @@ struct Counters {
 	unsigned long long entries;      // (triangle, tile) pairs
 	unsigned long long fragments;    // pixels written
 	unsigned int chunksRunMerge;     // list chunks the tile kernel ordered by run merge (mode B) ...
-	unsigned int chunksKeyRange; };  // ... and by key ranges + bitonic sort (mode C)
+	unsigned int chunksKeyRange;     // ... and by key ranges + bitonic sort (mode C)
+	unsigned int tilesDone; };       // tile CTAs that have finished (and fenced) their stores: the last one signals the frame's completion counter
 
 // Draw that owns a vertex / triangle job.  The host tabulates, per block of 256 jobs, the draw of the
 // block's first job.  A block that lies inside one draw (the usual case) needs no search; a block that
@@ -783,5 +784,24 @@ fill_kernel(FrameParams fp, const uint2* __restrict__ triInfo, const ClipRec* __
 	uint2 info = make_uint2(kReject, 0u);
 	if (job < fp.totalPJobs) { info = triInfo[job]; }
 	bin_triangle<true>(job, info, fp, clipRecs, B, ctr); }
+
+// ---------------------------------------------------------------------------------------------
+// Split-frame presentation: completion counters instead of a host-side barrier.  Every rank's tile kernel
+// adds 1 to a counter in the presenting GPU's memory when its last CTA has finished (tile_kernel epilogue);
+// the presenter's stream waits here until the counter has reached the number of units of the frame.
+// A bounded spin (2 s) so that a rank that died cannot hang the GPU.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void wait_counter_kernel(const unsigned long long* counter, unsigned long long value, unsigned int* timedOut) {
+	if (threadIdx.x != 0) { return; }
+	unsigned long long t0, now;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	while (true) {
+		unsigned long long v;
+		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+		if (v >= value) { break; }
+		__nanosleep(200);
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+		if (now - t0 > 2000000000ull) { if (timedOut) { *timedOut = 1u; } break; } } }
 
 }  // namespace rsr

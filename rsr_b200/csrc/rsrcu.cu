@@ -208,6 +208,8 @@ struct rsrcu_ctx {
 	Launched launched[kSlots];
 	int lastArena{-1};
 	uint64_t framesRetried{0};
+	unsigned long long* doneCounter{nullptr};   // rsrcu_set_completion_counter
+	unsigned int* waitTimedOut{nullptr};        // device flag of wait_counter_kernel
 	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
 	// store targets: one device buffer per store command of a frame (a frame may hold several stores of one kind with
 	// draws in between: each keeps its own image), a pool per slot of the ring, reused by the frames that follow
@@ -581,6 +583,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	ta.large = bin.large;
 	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
 	ta.runScratch = static_cast<uint32_t*>(w.runScratch.ptr);
+	ta.doneCounter = c->doneCounter;
 	ta.ctr = dCtr;
 	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
 	++c->launches;
@@ -689,6 +692,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	for (auto& a : c->arenas) { a.release(); }
 	for (auto& ev : c->arenaFree) { cudaEventDestroy(ev); }
 	if (c->devLuts) { cudaFree(c->devLuts); }
+	if (c->waitTimedOut) { cudaFree(c->waitTimedOut); }
 	if (c->hostCounters) { cudaFreeHost(c->hostCounters); }
 	for (auto& ev : c->evStage) { cudaEventDestroy(ev); }
 	for (auto& ev : c->evRendered) { cudaEventDestroy(ev); }
@@ -1344,6 +1348,22 @@ int rsrcu_debug_k2_times(unsigned long long* out8) {
 	cudaMemcpyToSymbol(g_k2Times, init, sizeof(init));
 	return RSRCU_OK; }
 #endif
+
+int rsrcu_set_completion_counter(rsrcu_ctx* c, void* deviceCounter) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (reinterpret_cast<uintptr_t>(deviceCounter) & 7u) { return fail(RSRCU_ERR_INVALID, "completion counter must be 8-byte aligned"); }
+	c->doneCounter = static_cast<unsigned long long*>(deviceCounter);
+	return RSRCU_OK; }
+
+int rsrcu_wait_counter(rsrcu_ctx* c, const void* deviceCounter, uint64_t value) {
+	if (!c || !deviceCounter) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	CU(cudaSetDevice(c->device));
+	if (!c->waitTimedOut) {
+		CU(cudaMalloc(&c->waitTimedOut, sizeof(unsigned int)));
+		CU(cudaMemset(c->waitTimedOut, 0, sizeof(unsigned int))); }
+	wait_counter_kernel<<<1, 32, 0, c->stream>>>(static_cast<const unsigned long long*>(deviceCounter), static_cast<unsigned long long>(value), c->waitTimedOut);
+	CU(cudaGetLastError());
+	return RSRCU_OK; }
 
 int rsrcu_set_overlap(rsrcu_ctx* c, int enabled) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }

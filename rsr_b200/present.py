@@ -12,7 +12,9 @@ from __future__ import annotations
 
 
 class PresentedFrame:
-    """frame: (height, width) int32 tensor on the presenting rank's GPU; on other ranks a peer mapping"""
+    """frame: (height, width) int32 tensor on the presenting rank's GPU; on other ranks a peer mapping.
+    counter: one int64 next to it (same sharing): the completion counter every rank's tile kernels add to
+    (rsrcu_set_completion_counter) and the presenter's stream waits on (rsrcu_wait_counter)."""
 
     def __init__(self, width: int, height: int, rank: int, local_rank: int, world: int, dist=None, presenter: int = 0):
         import torch
@@ -20,31 +22,37 @@ class PresentedFrame:
         self.width, self.height = width, height
         self.rank, self.world, self.presenter = rank, world, presenter
         self.local = None
+        self.local_counter = None
         if rank == presenter:
             self.local = torch.zeros((height, width), dtype=torch.int32, device=f"cuda:{local_rank}")
+            self.local_counter = torch.zeros(2, dtype=torch.int64, device=f"cuda:{local_rank}")
         if world == 1:
-            self.frame = self.local
+            self.frame, self.counter = self.local, self.local_counter
             self.presenter_device = local_rank
             return
         box = [None]
         if rank == presenter:
-            fn, args = reduce_tensor(self.local)
-            box = [(fn, args, local_rank)]
+            box = [(reduce_tensor(self.local), reduce_tensor(self.local_counter), local_rank)]
         dist.broadcast_object_list(box, src=presenter)
-        fn, args, self.presenter_device = box[0]
+        (fn, args), (cfn, cargs), self.presenter_device = box[0]
         if rank == presenter:
-            self.frame = self.local
+            self.frame, self.counter = self.local, self.local_counter
         else:
-            # open the handle from THIS rank's device (argument 6 of rebuild_cuda_tensor = the device whose context maps
+            # open the handles from THIS rank's device (argument 6 of rebuild_cuda_tensor = the device whose context maps
             # the memory): cudaIpcOpenMemHandle then maps the presenter's memory for this GPU with peer access
-            # over NVLink.  The tensor only carries the address; it is never used for torch compute.
-            args = list(args)
+            # over NVLink.  The tensors only carry the addresses; they are never used for torch compute.
+            args, cargs = list(args), list(cargs)
             args[6] = local_rank
+            cargs[6] = local_rank
             self.frame = fn(*args)
+            self.counter = cfn(*cargs)
 
     def pointer(self, x0: int, y0: int) -> int:
         """device address of pixel (x0, y0) -- valid in this process for kernels on any GPU with peer access"""
         return self.frame.data_ptr() + 4 * (y0 * self.width + x0)
+
+    def counter_pointer(self) -> int:
+        return self.counter.data_ptr()
 
     @property
     def stride_px(self) -> int:
