@@ -489,9 +489,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     gpu.EnablePeerAccess(pf.presenter_device)
     token = torch.zeros(1, dtype=torch.int32, device=dev)
     flags = p2p and args.barrier == "flag"
-    units_done = 0       # value of the completion counter after the frames launched so far (same arithmetic on every rank)
-    if flags:
-        gpu.SetCompletionCounter(pf.counter_pointer())
+    signals_done = 0     # value of the completion counter after the frames launched so far (same arithmetic on every rank)
 
     def retain(subframes, local=None):
         out = []
@@ -517,6 +515,8 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
             e1.record(cur)
             torch.cuda.synchronize()
             t_ms += e0.elapsed_time(e1)
+            if os.environ.get("RSR_BENCH_DEBUG"):
+                print(f"rank {rank} step {i}: {e0.elapsed_time(e1):.3f} ms", file=sys.stderr)
         barrier()
         t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -529,10 +529,6 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     checksum1 = None
     if rank == 0:
         alone = retain(plan.subframes)
-        if flags:
-            gpu.Sync()
-            pf.local_counter.zero_()     # (the retaining submits counted too)
-            torch.cuda.synchronize()
         def step_alone():
             for fr in alone:
                 gpu.Replay(fr)
@@ -561,40 +557,27 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
             gpu.Release(fr)
         pf.local.zero_()
     barrier()
-    if flags:
-        gpu.Sync()
-        barrier()
-        if rank == 0:
-            pf.local_counter.zero_()
-        barrier()
 
     # ---- split over the ranks ------------------------------------------------------------------------------
     mine = plan.owned_by(rank)
     if p2p:
         retained = retain(mine)
-        if flags:
-            gpu.Sync()
-            barrier()
-            if rank == 0:
-                pf.local_counter.zero_()
-            barrier()
     else:
         local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
         retained = retain(mine, local)
         gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
 
-    nunits = len(plan.subframes)
-
     def step():
-        nonlocal units_done
+        nonlocal signals_done
         for fr in retained:
             gpu.Replay(fr)
         if flags:
-            # no host-side barrier, no collective: every tile kernel adds 1 to the counter in the presenter's memory
-            # when its last CTA is done; the presenter's stream waits until all units of this frame have arrived
-            units_done += nunits
+            # no host-side barrier, no collective: behind its last sub-frame every rank adds 1 to a counter in the
+            # presenter's memory (over NVLink); the presenter's stream waits until all ranks of this frame have arrived
+            gpu.SignalCounter(pf.counter_pointer())
+            signals_done += world
             if rank == 0:
-                gpu.WaitCounter(pf.counter_pointer(), units_done)
+                gpu.WaitCounter(pf.counter_pointer(), signals_done)
             done = torch.cuda.Event()
             with torch.cuda.stream(stream):
                 done.record(stream)
@@ -630,7 +613,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     if rank == 0:
         checksum = int(pf.local.to(torch.int64).sum().item())
         exchange = "none" if world == 1 else (("tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory); completion = a counter in the presenter's "
-                                               "memory that every rank's last tile CTA increments (system-scope atomic), the presenter's stream waits on it: no host barrier, no collective"
+                                               "memory that every rank increments behind its last sub-frame (system-scope atomic over NVLink), the presenter's stream waits on it: no host barrier, no collective"
                                                if flags else "tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce as barrier")
                                               if p2p else "NCCL gather of resolved sub-frames to rank 0 + assembly copies")
         remote = sum(1 for s in plan.subframes if s.owner != 0)

@@ -165,13 +165,13 @@ int rsrcu_store_color_tc_device(rsrcu_ctx* ctx, int enable_gamma, void* device_d
  * there is no separate gather step. */
 int rsrcu_enable_peer_access(rsrcu_ctx* ctx, int peer_device);
 
-/* Split-frame completion without a host-side barrier.  rsrcu_set_completion_counter: from now on every frame this
- * context launches adds 1 to the 64-bit counter at `device_counter` (device memory of this or -- after
- * rsrcu_enable_peer_access -- of another GPU, 8-byte aligned; NULL switches it off) once the last CTA of its tile
- * kernel has finished and all its stores, peer stores included, are visible system-wide.  rsrcu_wait_counter enqueues
- * on this context's stream a wait until the counter has reached `value`: the presenting GPU of a frame split into U
- * units waits for (frames so far) x U.  The wait gives up after 2 s (a rank that died must not hang the GPU). */
-int rsrcu_set_completion_counter(rsrcu_ctx* ctx, void* device_counter);
+/* Split-frame completion without a host-side barrier or a collective.  rsrcu_signal_counter enqueues on this context's
+ * stream: "add 1 to the 64-bit counter at `device_counter`" (device memory of this or -- after rsrcu_enable_peer_access --
+ * of another GPU, 8-byte aligned), executed once every frame submitted so far has completed and all its stores, peer
+ * stores included, are visible system-wide.  rsrcu_wait_counter enqueues a wait until the counter has reached `value`:
+ * each rank signals after the units of the frame it owns, the presenting GPU waits for (frames so far) x (ranks).
+ * The wait gives up after 2 s (a rank that died must not hang the GPU). */
+int rsrcu_signal_counter(rsrcu_ctx* ctx, void* device_counter);
 int rsrcu_wait_counter(rsrcu_ctx* ctx, const void* device_counter, uint64_t value);
 
 /* CMD_STORE_COLOR_FULL_LINEAR_FP (half = 0; Copy, rglr_algorithm.cxx:247-279) and

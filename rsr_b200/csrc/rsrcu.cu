@@ -208,7 +208,6 @@ struct rsrcu_ctx {
 	Launched launched[kSlots];
 	int lastArena{-1};
 	uint64_t framesRetried{0};
-	unsigned long long* doneCounter{nullptr};   // rsrcu_set_completion_counter
 	unsigned int* waitTimedOut{nullptr};        // device flag of wait_counter_kernel
 	DevBuf counters[kSlots];   // Counters | cellCount[] | cellCursor[]; alternate per frame like the store targets (read back while the next frame runs)
 	// store targets: one device buffer per store command of a frame (a frame may hold several stores of one kind with
@@ -583,12 +582,12 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	ta.large = bin.large;
 	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
 	ta.runScratch = static_cast<uint32_t*>(w.runScratch.ptr);
-	ta.doneCounter = c->doneCounter;
 	ta.ctr = dCtr;
 	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
 	++c->launches;
 	CU(cudaGetLastError());
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], tileStream)); }
+
 	if (c->overlap) { CU(cudaEventRecord(c->evTileDone[si], tileStream)); }
 
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[4] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
@@ -1349,10 +1348,13 @@ int rsrcu_debug_k2_times(unsigned long long* out8) {
 	return RSRCU_OK; }
 #endif
 
-int rsrcu_set_completion_counter(rsrcu_ctx* c, void* deviceCounter) {
-	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+int rsrcu_signal_counter(rsrcu_ctx* c, void* deviceCounter) {
+	if (!c || !deviceCounter) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	if (reinterpret_cast<uintptr_t>(deviceCounter) & 7u) { return fail(RSRCU_ERR_INVALID, "completion counter must be 8-byte aligned"); }
-	c->doneCounter = static_cast<unsigned long long*>(deviceCounter);
+	CU(cudaSetDevice(c->device));
+	// an ordinary launch on the context's stream: runs after the tile kernels enqueued so far have completed
+	signal_counter_kernel<<<1, 32, 0, c->stream>>>(static_cast<unsigned long long*>(deviceCounter));
+	CU(cudaGetLastError());
 	return RSRCU_OK; }
 
 int rsrcu_wait_counter(rsrcu_ctx* c, const void* deviceCounter, uint64_t value) {

@@ -105,7 +105,6 @@ struct TileArgs {
 	const LargeItem* large;              // queued large items (kernels.cuh)
 	const uint32_t* tileOrder;           // CTA -> tile, tiles with the longest lists first (nullptr: identity)
 	uint32_t* runScratch;                // [tile][2 x kRunCap]: run tables of a long list cell (load_chunk, mode B)
-	unsigned long long* doneCounter;     // nullptr, or a counter (possibly in another GPU's memory) that receives + 1 when every tile of the frame has been stored
 	Counters* ctr; };
 
 __device__ __forceinline__ void prefetch_entry(const TileArgs& A, uint32_t id) {
@@ -1195,16 +1194,6 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 	if (lane == 0 && frags) { atomicAdd(&sh.sortCount, static_cast<int>(frags)); }
 	__syncthreads();
 	if (t == 0 && sh.sortCount) { atomicAdd(&A.ctr->fragments, static_cast<unsigned long long>(sh.sortCount)); }
-	// Frame completion signal (split-frame presentation: the stores above may have gone to the presenting GPU over
-	// NVLink).  Every thread makes its stores visible system-wide, the CTA takes a ticket; the last CTA of the grid has
-	// then (transitively) observed every other CTA's fence and publishes the frame with one system-scope atomic.
-	if (A.doneCounter != nullptr) {
-		__threadfence_system();
-		__syncthreads();
-		if (t == 0) {
-			if (atomicAdd(&A.ctr->tilesDone, 1u) == gridDim.x - 1) {
-				__threadfence_system();
-				atomicAdd_system(A.doneCounter, 1ull); } } }
 	PHASE(10); }
 
 }  // namespace rsr
