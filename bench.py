@@ -453,12 +453,16 @@ def stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier):
 # ---------------------------------------------------------------------------------------------------------
 
 def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier, scene=None):
-    """C5: one 7680x4320 frame = 4x4 sub-frames of 1920x1080 (the reference's guard band ends at 2048 px), sub-frames
-    dealt to the ranks.  Strong scaling: the frame is fixed.  Every rank's tile kernel resolves straight into the
-    presenting GPU's frame buffer (CUDA-IPC mapping, peer stores over NVLink while it rasterises); a frame ends with
-    one small NCCL all-reduce as the completion barrier.  Rank 0 also renders the whole frame alone (all 16
-    sub-frames on one GPU) so that the line carries its own single-GPU figure and efficiency.
-    --exchange nccl: render locally, NCCL gather, assemble."""
+    """C5 (BASELINE.json configs[4]): 7680x4320 frames = 4x4 sub-frames of 1920x1080 (the reference's guard band ends at
+    2048 px), sub-frames dealt to the ranks; a step is a BATCH of frames submitted back to back.  Strong scaling: the
+    frames are fixed.  Every rank's tile kernel resolves straight into the presenting GPU's frame buffer (CUDA-IPC
+    mapping, peer stores over NVLink while it rasterises).  The presenter's frame is double buffered; behind its
+    sub-frames of frame f every rank adds 1 to a counter in the presenter's memory, and before it starts frame f + 1
+    it waits (on its stream, no host involvement, no collective) until frame f - 1 is complete on all ranks -- the
+    buffer it is about to overwrite has been presented.  The presenter waits for the last frame of the batch.
+    Rank 0 also renders the same batches alone (all 16 sub-frames on one GPU): the line carries its own single-GPU
+    figure and efficiency.  --barrier nccl: an NCCL all-reduce per frame instead of the counters; --exchange nccl:
+    render locally, NCCL gather, assemble (both single-buffered, for comparison)."""
     from rsr_b200 import scenes
     from rsr_b200.present import PresentedFrame
     from rsr_b200.subframes import SubframePlan
@@ -467,168 +471,184 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
     P = scenes.perspective(45.0, 7680 / 4320, 1.0, 400.0)
     plan = SubframePlan(7680, 4320, world, 1920, 1080)
-    owners = None
-    if world > 1 and args.balance == "cost":
-        costs = torch.zeros(len(plan.subframes), dtype=torch.float64, device=dev)
-        if rank == 0:
-            gpu.set_profiling(1)
-            for sf in plan.subframes:
-                scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf))
-                probe = gpu.Finish()
-                for _ in range(3):
-                    gpu.Submit(probe)
-                costs[sf.index] = gpu.stage_ms()["frame"]
-            gpu.set_profiling(0)
-        dist.broadcast(costs, src=0)
-        owners = SubframePlan.balance([float(c) for c in costs.tolist()], world)
-        plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
     p2p = args.exchange == "p2p"
+    flags = p2p and args.barrier == "flag"
+    batch = max(1, args.batch_frames)
+    nbuf = 2 if flags else 1
     gpu.set_overlap(True)            # sub-frames are independent frames: front end of the next one under the current tile kernel
     cur = torch.cuda.current_stream()
-    pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist)
+    pf = PresentedFrame(7680, 4320, rank, local_rank, world, dist, buffers=nbuf)
     gpu.EnablePeerAccess(pf.presenter_device)
     token = torch.zeros(1, dtype=torch.int32, device=dev)
-    flags = p2p and args.barrier == "flag"
-    signals_done = 0     # value of the completion counter after the frames launched so far (same arithmetic on every rank)
 
-    def retain(subframes, local=None):
+    def retain(subframes, buf=0, local=None):
         out = []
         for k, sf in enumerate(subframes):
-            target = (pf.pointer(sf.x0, sf.y0), pf.stride_px) if local is None else (local[k].data_ptr(), 1920)
+            target = (pf.pointer(sf.x0, sf.y0, buf), pf.stride_px) if local is None else (local[k].data_ptr(), 1920)
             scene.record(gpu, (sf.width, sf.height), None, t=0.0, static=True, proj=plan.projection(P, sf), device_out=target)
             gpu.Submit(gpu.Finish())
             out.append(gpu.Retain())
         return out
 
-    def timed(step_fn, steps, warmup):
+    # ---- ownership ------------------------------------------------------------------------------------------------
+    owners = None
+    costs_ms = None
+    if world > 1 and args.balance == "cost":
+        # sub-frames differ in cost (screen centre vs corners): rank 0 measures the tile kernel of each one (retained
+        # replays, best of 3) and deals them longest first to the least loaded rank; every rank uses the same table
+        costs = torch.zeros(len(plan.subframes), dtype=torch.float64, device=dev)
+        if rank == 0:
+            gpu.set_profiling(1)
+            probes = retain(plan.subframes)
+            for k, fr in enumerate(probes):
+                best = 1e9
+                for _ in range(3):
+                    gpu.Replay(fr, sync=True)
+                    best = min(best, gpu.stage_ms()["tile"])
+                costs[k] = best
+            for fr in probes:
+                gpu.Release(fr)
+            gpu.set_profiling(0)
+        dist.broadcast(costs, src=0)
+        costs_ms = [round(float(c), 4) for c in costs.tolist()]
+        owners = SubframePlan.balance(costs_ms, world)
+        plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
+
+    frames_done = 0      # frames launched so far in the current phase (same arithmetic on every rank)
+
+    def run_batch(sets, nranks, presenter):
+        """one batch: `sets[b]` = this rank's retained sub-frames that resolve into presenter buffer b"""
+        nonlocal frames_done
+        for _ in range(batch):
+            f = frames_done
+            if flags:
+                if f >= 2:
+                    gpu.WaitCounters(pf.counter_pointer(0), nranks, f - 1)      # every rank has finished frame f - 2: its buffer is free
+                for fr in sets[f % nbuf]:
+                    gpu.Replay(fr)
+                gpu.SignalCounter(pf.counter_pointer(rank))
+            else:
+                for fr in sets[0]:
+                    gpu.Replay(fr)
+                done = torch.cuda.Event()
+                with torch.cuda.stream(stream):
+                    done.record(stream)
+                cur.wait_event(done)                       # NCCL runs on torch's stream, after the render stream
+                if p2p:
+                    if nranks > 1:
+                        dist.all_reduce(token)             # every rank's kernels (and with them their peer stores) have completed
+                else:
+                    if nranks > 1:
+                        dist.gather(local, gathered, dst=0)
+                    if rank == 0:
+                        parts = gathered if nranks > 1 else [local]
+                        for r, part in enumerate(parts):
+                            for k, sf in enumerate(plan.owned_by(r) if nranks > 1 else plan.subframes):
+                                pf.local[0, sf.y0:sf.y0 + sf.height, sf.x0:sf.x0 + sf.width].copy_(part[k])
+            frames_done += 1
+        if flags:
+            if presenter:
+                gpu.WaitCounters(pf.counter_pointer(0), nranks, frames_done)   # the last frame of the batch is complete on every rank
+            done = torch.cuda.Event()
+            with torch.cuda.stream(stream):
+                done.record(stream)
+            cur.wait_event(done)
+
+    def timed(sets, nranks, presenter, steps, warmup, sync_all):
         for _ in range(warmup):
-            step_fn()
-        barrier()
+            run_batch(sets, nranks, presenter)
+        sync_all()
         t_ms = 0.0
         for i in range(steps):
             flush.fill_(i & 0xff)
-            barrier()
+            sync_all()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
                 e0.record(stream)
-            step_fn()
+            run_batch(sets, nranks, presenter)
             e1.record(cur)
             torch.cuda.synchronize()
             t_ms += e0.elapsed_time(e1)
             if os.environ.get("RSR_BENCH_DEBUG"):
                 print(f"rank {rank} step {i}: {e0.elapsed_time(e1):.3f} ms", file=sys.stderr)
-        barrier()
-        t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps
+        sync_all()
+        return t_ms / steps
 
-    steps = max(10, min(args.steps, 50))
+    steps = max(5, min(args.steps, 50))
     # ---- the whole frame on ONE GPU (rank 0 alone): the strong-scaling baseline of this very run -------------
     single_ms = None
     checksum1 = None
     if rank == 0:
-        alone = retain(plan.subframes)
-        def step_alone():
-            for fr in alone:
-                gpu.Replay(fr)
-            done = torch.cuda.Event()
-            with torch.cuda.stream(stream):
-                done.record(stream)
-            cur.wait_event(done)
-        for _ in range(3):
-            step_alone()
-        torch.cuda.synchronize()
-        t_ms = 0.0
-        for i in range(steps):
-            flush.fill_(i & 0xff)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(stream):
-                e0.record(stream)
-            step_alone()
-            e1.record(cur)
-            torch.cuda.synchronize()
-            t_ms += e0.elapsed_time(e1)
-        single_ms = t_ms / steps
-        checksum1 = int(pf.local.to(torch.int64).sum().item())
+        alone = [retain(plan.subframes, b) for b in range(nbuf)] if p2p else None
+        if not p2p:
+            local = torch.zeros((len(plan.subframes), 1080, 1920), dtype=torch.int32, device=dev)
+            alone = [retain(plan.subframes, 0, local)]
         gpu.Sync()
-        for fr in alone:
-            gpu.Release(fr)
+        single_ms = timed(alone, 1, True, steps, 3, torch.cuda.synchronize) / batch
+        gpu.Sync()
+        checksum1 = int(pf.local[0].to(torch.int64).sum().item())
+        for sset in alone:
+            for fr in sset:
+                gpu.Release(fr)
         pf.local.zero_()
+        pf.local_counter.zero_()
+        torch.cuda.synchronize()
     barrier()
 
-    # ---- split over the ranks ------------------------------------------------------------------------------
+    # ---- split over the ranks ------------------------------------------------------------------------------------
+    frames_done = 0
     mine = plan.owned_by(rank)
     if p2p:
-        retained = retain(mine)
+        sets = [retain(mine, b) for b in range(nbuf)]
     else:
         local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
-        retained = retain(mine, local)
+        sets = [retain(mine, 0, local)]
         gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
-
-    def step():
-        nonlocal signals_done
-        for fr in retained:
-            gpu.Replay(fr)
-        if flags:
-            # no host-side barrier, no collective: behind its last sub-frame every rank adds 1 to a counter in the
-            # presenter's memory (over NVLink); the presenter's stream waits until all ranks of this frame have arrived
-            gpu.SignalCounter(pf.counter_pointer())
-            signals_done += world
-            if rank == 0:
-                gpu.WaitCounter(pf.counter_pointer(), signals_done)
-            done = torch.cuda.Event()
-            with torch.cuda.stream(stream):
-                done.record(stream)
-            cur.wait_event(done)
-            return
-        done = torch.cuda.Event()
-        with torch.cuda.stream(stream):
-            done.record(stream)
-        cur.wait_event(done)                       # NCCL runs on torch's stream, after the render stream
-        if p2p:
-            if world > 1:
-                dist.all_reduce(token)             # every rank's kernels (and with them their peer stores) have completed
-            return
-        if world > 1:
-            dist.gather(local, gathered, dst=0)
-        if rank == 0:
-            parts = gathered if world > 1 else [local]
-            for r, part in enumerate(parts):
-                for k, sf in enumerate(plan.owned_by(r)):
-                    pf.local[sf.y0:sf.y0 + sf.height, sf.x0:sf.x0 + sf.width].copy_(part[k])
-
+    gpu.Sync()
+    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = timed(step, steps, max(args.warmup, 3))
+    ms_local = timed(sets, world, rank == 0, steps, max(args.warmup, 3), barrier)
     clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / batch
     gpu.Sync()
     st = gpu.stats()
-    for fr in retained:
-        gpu.Release(fr)
+    for sset in sets:
+        for fr in sset:
+            gpu.Release(fr)
     gpu.set_overlap(False)
     rec = None
     if rank == 0:
-        checksum = int(pf.local.to(torch.int64).sum().item())
-        exchange = "none" if world == 1 else (("tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory); completion = a counter in the presenter's "
-                                               "memory that every rank increments behind its last sub-frame (system-scope atomic over NVLink), the presenter's stream waits on it: no host barrier, no collective"
-                                               if flags else "tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce as barrier")
-                                              if p2p else "NCCL gather of resolved sub-frames to rank 0 + assembly copies")
+        checksum = int(pf.local[0].to(torch.int64).sum().item())
+        if world == 1:
+            exchange = "none"
+        elif flags:
+            exchange = ("tile kernels store into the presenting GPU's double-buffered frame over NVLink (CUDA IPC peer memory); completion = a counter in the "
+                        "presenter's memory that every rank increments behind its sub-frames of a frame (system-scope atomic over NVLink) and every rank's stream "
+                        "waits on before it reuses a buffer: no host barrier, no collective")
+        elif p2p:
+            exchange = "tile kernels store into the presenting GPU's frame over NVLink (CUDA IPC peer memory) + 4-byte NCCL all-reduce per frame as barrier"
+        else:
+            exchange = "NCCL gather of resolved sub-frames to rank 0 + assembly copies"
         remote = sum(1 for s in plan.subframes if s.owner != 0)
         rec = {"metric": "frames_per_sec_8k_split_frame", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
-               "ms_per_step": ms, "scaling": "strong",
-               "single_gpu_frames_per_s": 1e3 / single_ms, "single_gpu_ms": single_ms,
+               "frames_per_step": batch, "ms_per_step": ms * batch, "ms_per_frame": ms, "scaling": "strong",
+               "single_gpu_frames_per_s": 1e3 / single_ms, "single_gpu_ms_per_frame": single_ms,
                "speedup_vs_single_gpu": single_ms / ms, "efficiency": single_ms / ms / world,
                "nvlink_bytes_per_frame": remote * 1920 * 1080 * 4,
                "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
                           "subframes_per_rank": len(mine), "exchange": exchange,
                           "ownership": "round robin" if owners is None else f"cost balanced (longest first): {owners}",
-                          "submission": "retained sub-frame tables replayed", "cache": "L2 flushed before every timed frame"},
+                          "subframe_tile_ms": costs_ms,
+                          "submission": f"batches of {batch} frames back to back, retained sub-frame tables replayed",
+                          "cache": "L2 flushed before every timed batch"},
                "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks,
                "frame_checksum": checksum, "frame_checksum_single_gpu": checksum1, "checksums_equal": checksum == checksum1,
-               "gpu_launches": int(st["kernel_launches"]) * len(mine) * steps}
+               "gpu_launches": int(st["kernel_launches"]) * len(mine) * steps * batch}
     return rec
 
 
@@ -661,6 +681,7 @@ def main():
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
     ap.add_argument("--balance", default="roundrobin", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="split-frame: how resolved pixels reach the presenting GPU")
+    ap.add_argument("--batch-frames", type=int, default=8, help="split-frame: frames per step (a batch submitted back to back)")
     ap.add_argument("--barrier", default="flag", choices=["flag", "nccl"], help="split-frame with p2p stores: completion counter in the presenter's memory, or an NCCL all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

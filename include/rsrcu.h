@@ -165,14 +165,16 @@ int rsrcu_store_color_tc_device(rsrcu_ctx* ctx, int enable_gamma, void* device_d
  * there is no separate gather step. */
 int rsrcu_enable_peer_access(rsrcu_ctx* ctx, int peer_device);
 
-/* Split-frame completion without a host-side barrier or a collective.  rsrcu_signal_counter enqueues on this context's
- * stream: "add 1 to the 64-bit counter at `device_counter`" (device memory of this or -- after rsrcu_enable_peer_access --
- * of another GPU, 8-byte aligned), executed once every frame submitted so far has completed and all its stores, peer
- * stores included, are visible system-wide.  rsrcu_wait_counter enqueues a wait until the counter has reached `value`:
- * each rank signals after the units of the frame it owns, the presenting GPU waits for (frames so far) x (ranks).
- * The wait gives up after 2 s (a rank that died must not hang the GPU). */
+/* Split-frame completion without a host-side barrier or a collective: 64-bit counters in device memory (of this or --
+ * after rsrcu_enable_peer_access -- of another GPU, 8-byte aligned), one per rank, as stream operations.
+ * rsrcu_signal_counter enqueues on this context's stream "add 1 to *device_counter", executed once every frame
+ * submitted so far has completed and all its stores, peer stores included, are visible system-wide.
+ * rsrcu_wait_counters enqueues a wait until each of the `count` consecutive counters has reached `value`.
+ * Each rank signals its own counter behind its units of frame f; a rank waits for "all >= f - 1" before it reuses a
+ * buffer of the double-buffered presented frame, the presenter for "all >= f + 1" before it presents frame f.
+ * A wait gives up after 2 s (a rank that died must not hang the GPU). */
 int rsrcu_signal_counter(rsrcu_ctx* ctx, void* device_counter);
-int rsrcu_wait_counter(rsrcu_ctx* ctx, const void* device_counter, uint64_t value);
+int rsrcu_wait_counters(rsrcu_ctx* ctx, const void* device_counters, int count, uint64_t value);
 
 /* CMD_STORE_COLOR_FULL_LINEAR_FP (half = 0; Copy, rglr_algorithm.cxx:247-279) and
  * CMD_STORE_COLOR_HALF_LINEAR_FP (half = 1; Downsample, rglr_algorithm.cxx:118-141: one pixel per

@@ -118,7 +118,7 @@ def load_library():
         "rsrcu_enable_peer_access": [vp, ci],
         "rsrcu_set_overlap": [vp, ci],
         "rsrcu_signal_counter": [vp, vp],
-        "rsrcu_wait_counter": [vp, vp, C.c_uint64],
+        "rsrcu_wait_counters": [vp, vp, ci, C.c_uint64],
         "rsrcu_retain_frame": [vp, C.POINTER(C.c_void_p)],
         "rsrcu_replay_frame": [vp, vp],
         "rsrcu_release_frame": [vp, vp],
@@ -147,7 +147,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_create", "rsrcu_destroy", "rsrcu_last_error", "rsrcu_set_host_luts", "rsrcu_get_host_luts",
     "rsrcu_release_static", "rsrcu_begin_frame", "rsrcu_set_state", "rsrcu_bind_buffer", "rsrcu_bind_texture",
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
-    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_signal_counter", "rsrcu_wait_counter", "rsrcu_retain_frame", "rsrcu_replay_frame", "rsrcu_release_frame", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
+    "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_signal_counter", "rsrcu_wait_counters", "rsrcu_retain_frame", "rsrcu_replay_frame", "rsrcu_release_frame", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
@@ -502,9 +502,9 @@ class GPU:
         every frame submitted so far has completed and its stores are visible system-wide"""
         self._check(self.L.rsrcu_signal_counter(self.h, C.c_void_p(device_ptr)))
 
-    def WaitCounter(self, device_ptr, value):
-        """enqueue on this context's stream a wait until the counter at `device_ptr` has reached `value`"""
-        self._check(self.L.rsrcu_wait_counter(self.h, C.c_void_p(device_ptr), int(value)))
+    def WaitCounters(self, device_ptr, count, value):
+        """enqueue on this context's stream a wait until each of the `count` counters at `device_ptr` has reached `value`"""
+        self._check(self.L.rsrcu_wait_counters(self.h, C.c_void_p(device_ptr), int(count), int(value)))
 
     def StoreDepth(self, dst):
         assert dst.dtype == np.float32 and dst.flags.c_contiguous

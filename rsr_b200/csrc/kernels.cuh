@@ -786,9 +786,9 @@ fill_kernel(FrameParams fp, const uint2* __restrict__ triInfo, const ClipRec* __
 
 // ---------------------------------------------------------------------------------------------
 // Split-frame presentation: completion counters instead of a host-side barrier.  Behind every frame's tile kernel
-// a one-thread kernel adds 1 to a counter in the presenting GPU's memory (stream order: the tile kernel, and with
-// it its peer stores, has completed; a system fence, then a system-scope atomic over NVLink); the presenter's
-// stream waits until the counter has reached the number of units of the frame.  (Signalling from the tile kernel's
+// a one-thread kernel adds 1 to this rank's counter in the presenting GPU's memory (stream order: the tile kernel,
+// and with it its peer stores, has completed; a system fence, then a system-scope atomic over NVLink); a stream
+// waits until all ranks' counters have reached a frame number.  (Signalling from the tile kernel's
 // last CTA instead costs a system-scope fence per CTA: measured 20 % slower on the whole frame.)
 // The wait is a bounded spin (2 s) so that a rank that died cannot hang the GPU.
 // ---------------------------------------------------------------------------------------------
@@ -798,16 +798,20 @@ __global__ void signal_counter_kernel(unsigned long long* counter) {
 		__threadfence_system();
 		atomicAdd_system(counter, 1ull); } }
 
-__global__ void wait_counter_kernel(const unsigned long long* counter, unsigned long long value, unsigned int* timedOut) {
-	if (threadIdx.x != 0) { return; }
+__global__ void wait_counter_kernel(const unsigned long long* counters, unsigned int count, unsigned long long value, unsigned int* timedOut) {
+	// lane i watches counters[i], i + 32, ...: done when every one of the `count` counters has reached `value`
 	unsigned long long t0, now;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	unsigned int next = threadIdx.x;
 	while (true) {
-		unsigned long long v;
-		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
-		if (v >= value) { break; }
+		while (next < count) {
+			unsigned long long v;
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counters + next) : "memory");
+			if (v < value) { break; }
+			next += 32u; }
+		if (__all_sync(0xffffffffu, next >= count)) { break; }
 		__nanosleep(200);
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-		if (now - t0 > 2000000000ull) { if (timedOut) { *timedOut = 1u; } break; } } }
+		if (__any_sync(0xffffffffu, now - t0 > 2000000000ull)) { if (timedOut && threadIdx.x == 0) { *timedOut = 1u; } break; } } }
 
 }  // namespace rsr

@@ -1357,13 +1357,14 @@ int rsrcu_signal_counter(rsrcu_ctx* c, void* deviceCounter) {
 	CU(cudaGetLastError());
 	return RSRCU_OK; }
 
-int rsrcu_wait_counter(rsrcu_ctx* c, const void* deviceCounter, uint64_t value) {
-	if (!c || !deviceCounter) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+int rsrcu_wait_counters(rsrcu_ctx* c, const void* deviceCounters, int count, uint64_t value) {
+	if (!c || !deviceCounters || count <= 0) { return fail(RSRCU_ERR_INVALID, "bad argument"); }
 	CU(cudaSetDevice(c->device));
 	if (!c->waitTimedOut) {
 		CU(cudaMalloc(&c->waitTimedOut, sizeof(unsigned int)));
 		CU(cudaMemset(c->waitTimedOut, 0, sizeof(unsigned int))); }
-	wait_counter_kernel<<<1, 32, 0, c->stream>>>(static_cast<const unsigned long long*>(deviceCounter), static_cast<unsigned long long>(value), c->waitTimedOut);
+	wait_counter_kernel<<<1, 32, 0, c->stream>>>(static_cast<const unsigned long long*>(deviceCounters), static_cast<unsigned int>(count),
+	                                             static_cast<unsigned long long>(value), c->waitTimedOut);
 	CU(cudaGetLastError());
 	return RSRCU_OK; }
 

@@ -12,11 +12,12 @@ from __future__ import annotations
 
 
 class PresentedFrame:
-    """frame: (height, width) int32 tensor on the presenting rank's GPU; on other ranks a peer mapping.
-    counter: one int64 next to it (same sharing): the completion counter every rank's tile kernels add to
-    (rsrcu_set_completion_counter) and the presenter's stream waits on (rsrcu_wait_counter)."""
+    """frame: (buffers, height, width) int32 tensor on the presenting rank's GPU (double buffered presentation: buffers = 2);
+    on other ranks a peer mapping.
+    counter: one int64 per rank next to it (same sharing): rank r adds 1 to counter r behind its sub-frames of a frame
+    (rsrcu_signal_counter); streams wait on all of them (rsrcu_wait_counters)."""
 
-    def __init__(self, width: int, height: int, rank: int, local_rank: int, world: int, dist=None, presenter: int = 0):
+    def __init__(self, width: int, height: int, rank: int, local_rank: int, world: int, dist=None, presenter: int = 0, buffers: int = 1):
         import torch
         from torch.multiprocessing.reductions import reduce_tensor
         self.width, self.height = width, height
@@ -24,8 +25,8 @@ class PresentedFrame:
         self.local = None
         self.local_counter = None
         if rank == presenter:
-            self.local = torch.zeros((height, width), dtype=torch.int32, device=f"cuda:{local_rank}")
-            self.local_counter = torch.zeros(2, dtype=torch.int64, device=f"cuda:{local_rank}")
+            self.local = torch.zeros((buffers, height, width), dtype=torch.int32, device=f"cuda:{local_rank}")
+            self.local_counter = torch.zeros(max(world, 1), dtype=torch.int64, device=f"cuda:{local_rank}")
         if world == 1:
             self.frame, self.counter = self.local, self.local_counter
             self.presenter_device = local_rank
@@ -47,12 +48,13 @@ class PresentedFrame:
             self.frame = fn(*args)
             self.counter = cfn(*cargs)
 
-    def pointer(self, x0: int, y0: int) -> int:
-        """device address of pixel (x0, y0) -- valid in this process for kernels on any GPU with peer access"""
-        return self.frame.data_ptr() + 4 * (y0 * self.width + x0)
+    def pointer(self, x0: int, y0: int, buffer: int = 0) -> int:
+        """device address of pixel (x0, y0) of frame buffer `buffer` -- valid in this process for kernels on any GPU with peer access"""
+        return self.frame.data_ptr() + 4 * ((buffer * self.height + y0) * self.width + x0)
 
-    def counter_pointer(self) -> int:
-        return self.counter.data_ptr()
+    def counter_pointer(self, rank: int = 0) -> int:
+        """device address of rank `rank`'s completion counter (the counters are consecutive: wait on counter_pointer(0), world)"""
+        return self.counter.data_ptr() + 8 * rank
 
     @property
     def stride_px(self) -> int:
