@@ -679,7 +679,7 @@ def main():
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
-    ap.add_argument("--balance", default="roundrobin", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
+    ap.add_argument("--balance", default="cost", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="split-frame: how resolved pixels reach the presenting GPU")
     ap.add_argument("--batch-frames", type=int, default=8, help="split-frame: frames per step (a batch submitted back to back)")
     ap.add_argument("--barrier", default="flag", choices=["flag", "nccl"], help="split-frame with p2p stores: completion counter in the presenter's memory, or an NCCL all-reduce")

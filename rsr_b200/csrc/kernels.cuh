@@ -794,12 +794,18 @@ fill_kernel(FrameParams fp, const uint2* __restrict__ triInfo, const ClipRec* __
 // ---------------------------------------------------------------------------------------------
 
 __global__ void signal_counter_kernel(unsigned long long* counter) {
+	// (launched with programmatic stream serialization: resident early, then waits here until the kernels before it
+	// in the stream -- the frame's tile kernel -- have completed and their stores are visible)
+	pdl_launch_dependents();
+	pdl_wait();
 	if (threadIdx.x == 0) {
 		__threadfence_system();
 		atomicAdd_system(counter, 1ull); } }
 
 __global__ void wait_counter_kernel(const unsigned long long* counters, unsigned int count, unsigned long long value, unsigned int* timedOut) {
 	// lane i watches counters[i], i + 32, ...: done when every one of the `count` counters has reached `value`
+	pdl_launch_dependents();
+	pdl_wait();
 	unsigned long long t0, now;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 	unsigned int next = threadIdx.x;

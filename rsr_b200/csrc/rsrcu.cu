@@ -157,6 +157,7 @@ struct rsrcu_ctx {
 	// RSRCU_TRACE=1: timestamps of the first 64 frames (kernels start/end on the render stream, read-back start/end on
 	// the copy stream), printed by rsrcu_destroy -- a poor man's timeline for pipelining problems
 	bool trace{false};
+	bool traceStages{false};   // RSRCU_TRACE=2: events 2 and 3 of a frame are front end done / tile kernel start instead of the read-back
 	std::vector<cudaEvent_t> traceEv;   // 4 per frame
 	int traceFrames{0};
 	int traceFrameOfSlot[kSlots]{};
@@ -460,7 +461,7 @@ int flushDeferredCopies(rsrcu_ctx* c) {
 	c->deferredSlot = -1;
 	CU(cudaStreamWaitEvent(c->copyStream, c->evRendered[slot], 0));
 	const int tf = c->trace ? c->traceFrameOfSlot[slot] : -1;
-	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 2], c->copyStream)); }
+	if (tf >= 0 && !c->traceStages) { CU(cudaEventRecord(c->traceEv[4 * tf + 2], c->copyStream)); }
 	for (const PendingCopy& pc : c->deferredCopies) {
 		if (pc.hostPitch == pc.rowBytes && pc.devPitch == pc.rowBytes) {   // contiguous on both sides: one linear copy (a 2-D copy pays per row)
 			CU(cudaMemcpyAsync(pc.hostDst, pc.devSrc, pc.rowBytes * pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); }
@@ -468,7 +469,7 @@ int flushDeferredCopies(rsrcu_ctx* c) {
 			CU(cudaMemcpy2DAsync(pc.hostDst, pc.hostPitch, pc.devSrc, pc.devPitch, pc.rowBytes, pc.rows, cudaMemcpyDeviceToHost, c->copyStream)); } }
 	CU(cudaMemcpyAsync(c->hostCounters + slot, c->counters[slot].ptr, sizeof(Counters), cudaMemcpyDeviceToHost, c->copyStream));
 	CU(cudaEventRecord(c->evCopied[slot], c->copyStream));
-	if (tf >= 0) { CU(cudaEventRecord(c->traceEv[4 * tf + 3], c->copyStream)); }
+	if (tf >= 0 && !c->traceStages) { CU(cudaEventRecord(c->traceEv[4 * tf + 3], c->copyStream)); }
 	return RSRCU_OK; }
 
 // Launches the kernels of a frame whose tables (plan) are final: K0 (upload of `uploadBytes` from `hostArena`, or
@@ -565,9 +566,11 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(w.triInfo.ptr),
 			static_cast<const ClipRec*>(w.clipRecs.ptr), bin, dCtr));
 		++c->launches; }
+	if (traceIdx >= 0 && c->traceStages) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 2], st)); }
 	if (c->overlap) {
 		CU(cudaEventRecord(c->evFrontDone[si], st));
 		CU(cudaStreamWaitEvent(tileStream, c->evFrontDone[si], 0)); }
+	if (traceIdx >= 0 && c->traceStages) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 3], tileStream)); }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], tileStream)); }
 
 	TileArgs ta{};
@@ -650,6 +653,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	c->hostProf = std::getenv("RSRCU_HOST_PROF") != nullptr;
 	if (std::getenv("RSRCU_TRACE")) {
 		c->trace = true;
+		c->traceStages = std::atoi(std::getenv("RSRCU_TRACE")) == 2;
 		c->traceEv.resize(4 * 64);
 		for (auto& ev : c->traceEv) { CU(cudaEventCreate(&ev)); } }
 	if (const char* v = std::getenv("RSRCU_LARGE_TILES")) { const int n = std::atoi(v); if (n > 0) { c->largeTiles = n; } }   // tests
@@ -681,7 +685,8 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 		for (int f = 0; f + 1 < c->traceFrames; ++f) {
 			float t[4] = {0, 0, 0, 0};
 			for (int k = 0; k < 4; ++k) { if (cudaEventElapsedTime(&t[k], c->traceEv[0], c->traceEv[4 * f + k]) != cudaSuccess) { t[k] = -1.0f; cudaGetLastError(); } }
-			std::fprintf(stderr, "rsrcu trace frame %2d: kernels %8.1f .. %8.1f us   read-back %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f); }
+			if (c->traceStages) { std::fprintf(stderr, "rsrcu trace frame %2d: front end %8.1f .. %8.1f us   tile kernel %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[1] * 1e3f); }
+			else { std::fprintf(stderr, "rsrcu trace frame %2d: kernels %8.1f .. %8.1f us   read-back %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f); } }
 		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	for (auto& w : c->sets) {
@@ -1352,9 +1357,7 @@ int rsrcu_signal_counter(rsrcu_ctx* c, void* deviceCounter) {
 	if (!c || !deviceCounter) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	if (reinterpret_cast<uintptr_t>(deviceCounter) & 7u) { return fail(RSRCU_ERR_INVALID, "completion counter must be 8-byte aligned"); }
 	CU(cudaSetDevice(c->device));
-	// an ordinary launch on the context's stream: runs after the tile kernels enqueued so far have completed
-	signal_counter_kernel<<<1, 32, 0, c->stream>>>(static_cast<unsigned long long*>(deviceCounter));
-	CU(cudaGetLastError());
+	CU(launchPdl(signal_counter_kernel, 1u, 32u, 0, c->stream, static_cast<unsigned long long*>(deviceCounter)));
 	return RSRCU_OK; }
 
 int rsrcu_wait_counters(rsrcu_ctx* c, const void* deviceCounters, int count, uint64_t value) {
@@ -1363,9 +1366,8 @@ int rsrcu_wait_counters(rsrcu_ctx* c, const void* deviceCounters, int count, uin
 	if (!c->waitTimedOut) {
 		CU(cudaMalloc(&c->waitTimedOut, sizeof(unsigned int)));
 		CU(cudaMemset(c->waitTimedOut, 0, sizeof(unsigned int))); }
-	wait_counter_kernel<<<1, 32, 0, c->stream>>>(static_cast<const unsigned long long*>(deviceCounters), static_cast<unsigned int>(count),
-	                                             static_cast<unsigned long long>(value), c->waitTimedOut);
-	CU(cudaGetLastError());
+	CU(launchPdl(wait_counter_kernel, 1u, 32u, 0, c->stream, static_cast<const unsigned long long*>(deviceCounters), static_cast<unsigned int>(count),
+	             static_cast<unsigned long long>(value), c->waitTimedOut));
 	return RSRCU_OK; }
 
 int rsrcu_set_overlap(rsrcu_ctx* c, int enabled) {
