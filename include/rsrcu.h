@@ -293,6 +293,7 @@ typedef struct RsrStats {
 	uint64_t host_submit_ns;        /* host time spent in rsrcu_end_frame (tables, upload, launches) */
 	uint64_t frames_retried;        /* cumulative: frames launched again because a device-side buffer overflowed */
 	uint64_t input_bytes;           /* the frame's draw inputs: bound vertex SoA floats x vertices + indices + instance matrices */
+	uint64_t draws_culled;          /* cumulative: draws skipped because their bounding box lies outside one guard-band plane */
 } RsrStats;
 int rsrcu_get_stats(rsrcu_ctx* ctx, RsrStats* out);
 

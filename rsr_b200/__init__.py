@@ -74,7 +74,7 @@ class RsrState(C.Structure):
 class RsrStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("triangles_submitted", "triangles_binned", "triangles_clipped",
                                            "bin_entries", "fragments_shaded", "kernel_launches", "h2d_bytes", "d2h_bytes",
-                                           "list_chunks_run_merge", "list_chunks_key_range", "host_record_ns", "host_submit_ns", "frames_retried", "input_bytes")]
+                                           "list_chunks_run_merge", "list_chunks_key_range", "host_record_ns", "host_submit_ns", "frames_retried", "input_bytes", "draws_culled")]
 
 
 _lib = None

@@ -82,17 +82,17 @@ struct UploadArena {
 		return cudaSuccess; }
 	void release() { if (host) { cudaFreeHost(host); host = nullptr; hostCap = 0; } dev.release(); } };
 
-struct StaticAlloc { void* dev; size_t bytes; };
+struct StaticAlloc { void* dev; size_t bytes; float lo, hi; bool ranged; };   // (lo, hi: value range of a float array, when asked for)
 
 // direct-mapped front of the static cache: a frame binds the same few hundred pointers thousands of times
-struct PtrCacheEntry { const void* host; size_t bytes; void* dev; };
+struct PtrCacheEntry { const void* host; size_t bytes; void* dev; float lo, hi; bool ranged; };
 constexpr size_t kPtrCacheSize = 2048;
 inline size_t ptrCacheIndex(const void* p) { return static_cast<size_t>((reinterpret_cast<uintptr_t>(p) >> 4) * 0x9E3779B97F4A7C15ull >> 53); }
 
 struct PendingCopy { void* hostDst; const void* devSrc; size_t rowBytes; size_t rows; size_t hostPitch; size_t devPitch; };
 
 // a device pointer that is either absolute (static cache) or an offset into the frame arena
-struct DevRef { bool arena{false}; size_t off{0}; const void* abs{nullptr}; bool null{true}; };
+struct DevRef { bool arena{false}; size_t off{0}; const void* abs{nullptr}; bool null{true}; float lo{0.0f}, hi{0.0f}; bool ranged{false}; };
 
 struct HostTex { DevRef ref; uint32_t texelCount{0}; int width{8}, height{8}, stride{8}, filter{0}; };
 
@@ -102,6 +102,8 @@ struct HostTex { DevRef ref; uint32_t texelCount{0}; int width{8}, height{8}, st
 struct HostState {
 	DevState ds;
 	size_t bufferFloats[16];
+	float posLo[3], posHi[3];     // value ranges of the position arrays (static buffers only): the draw's object-space bounding box
+	bool posRanged;
 	int programId, key;
 	bool posNull, tex0Null, hasArenaRef;
 	int tex0Width, tex0Height, tex0Stride; };
@@ -195,7 +197,9 @@ struct rsrcu_ctx {
 	                                  // device mirror of a frame stays intact until three frames later (an overflowed frame can be launched again)
 	cudaEvent_t arenaFree[kSlots]{};
 	std::unordered_map<const void*, StaticAlloc> staticCache;
-	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr});
+	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr, 0.0f, 0.0f, false});
+	float guardFactor{1.0f};
+	uint64_t drawsCulled{0};
 
 	// device work buffers
 	// the frame's intermediate buffers; two sets so that, in overlap mode, the front end (K0-K5) of frame N+1 can fill one
@@ -348,31 +352,71 @@ void patchRef(const T*& p, const uint8_t* arenaDev) {
 	const uint64_t v = reinterpret_cast<uintptr_t>(p);
 	if (v & kArenaRefBit) { p = reinterpret_cast<const T*>(arenaDev + (v & ~kArenaRefBit)); } }
 
-int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef& out) {
+// value range of a float array (bounding boxes of static meshes); false if it holds a NaN
+bool floatRange(const float* p, size_t n, float& lo, float& hi) {
+	if (n == 0) { return false; }
+	float a = p[0], b = p[0];
+	bool ok = true;
+	for (size_t i = 0; i < n; ++i) { const float v = p[i]; ok = ok && (v == v); a = v < a ? v : a; b = v > b ? v : b; }
+	lo = a; hi = b;
+	return ok; }
+
+int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef& out, bool wantRange = false) {
 	if (!host || bytes == 0) { out = DevRef{}; return RSRCU_OK; }
 	if (upload == RSRCU_UPLOAD_STATIC) {
 		PtrCacheEntry& pe = c->ptrCache[ptrCacheIndex(host)];
-		if (pe.host == host && pe.bytes == bytes) {
-			out.null = false; out.arena = false; out.abs = pe.dev;
+		if (pe.host == host && pe.bytes == bytes && (pe.ranged || !wantRange)) {
+			out.null = false; out.arena = false; out.abs = pe.dev; out.lo = pe.lo; out.hi = pe.hi; out.ranged = pe.ranged;
 			return RSRCU_OK; }
 		auto it = c->staticCache.find(host);
 		if (it != c->staticCache.end() && it->second.bytes == bytes) {
-			pe = PtrCacheEntry{host, bytes, it->second.dev};
-			out.null = false; out.arena = false; out.abs = it->second.dev;
+			StaticAlloc& sa = it->second;
+			if (wantRange && !sa.ranged) { sa.ranged = floatRange(static_cast<const float*>(host), bytes / 4, sa.lo, sa.hi); if (!sa.ranged) { sa.lo = 0.0f; sa.hi = 0.0f; } }
+			pe = PtrCacheEntry{host, bytes, sa.dev, sa.lo, sa.hi, sa.ranged || wantRange};   // (a failed range is not tried again: ranged stays false in `out`)
+			out.null = false; out.arena = false; out.abs = sa.dev; out.lo = sa.lo; out.hi = sa.hi; out.ranged = sa.ranged;
+			pe.ranged = sa.ranged;
 			return RSRCU_OK; }
 		if (it != c->staticCache.end()) { cudaFree(it->second.dev); c->staticCache.erase(it); }
 		void* d = nullptr;
 		CU(cudaSetDevice(c->device));
 		CU(cudaMalloc(&d, bytes));
 		CU(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
-		c->staticCache[host] = StaticAlloc{d, bytes};
-		pe = PtrCacheEntry{host, bytes, d};
-		out.null = false; out.arena = false; out.abs = d;
+		StaticAlloc sa{d, bytes, 0.0f, 0.0f, false};
+		if (wantRange) { sa.ranged = floatRange(static_cast<const float*>(host), bytes / 4, sa.lo, sa.hi); if (!sa.ranged) { sa.lo = 0.0f; sa.hi = 0.0f; } }
+		c->staticCache[host] = sa;
+		pe = PtrCacheEntry{host, bytes, d, sa.lo, sa.hi, sa.ranged};
+		out.null = false; out.arena = false; out.abs = d; out.lo = sa.lo; out.hi = sa.hi; out.ranged = sa.ranged;
 		return RSRCU_OK; }
 	size_t off = 0;
 	CU(c->arenas[c->outSlot].push(host, bytes, off));
-	out.null = false; out.arena = true; out.off = off;
+	out.null = false; out.arena = true; out.off = off; out.ranged = false;
 	return RSRCU_OK; }
+
+// Is the box [lo, hi] (object space), transformed by vpm, outside one plane of the reference's guard-band frustum
+// (ViewFrustum::Test, rglv_view_frustum.hxx:60-73) with all of its corners?  Then every vertex of the draw carries
+// that plane's flag, every triangle is dropped by the "all three share a flag" test (rglv_gpu_impl.hxx:427-433), and
+// the draw can be skipped: nothing of it reaches a tile.  The plane values are linear in the object coordinates, so
+// the corners bound them; evaluated in double with a margin far above the float rounding of the vertex kernel, so
+// the decision never disagrees with the per-vertex flags.
+bool boxOutsideFrustum(const float* vpm, const float* lo, const float* hi, float guardFactor) {
+	double val[5][8], mag[5][8];
+	for (int k = 0; k < 8; ++k) {
+		const double x = (k & 1) ? hi[0] : lo[0], y = (k & 2) ? hi[1] : lo[1], z = (k & 4) ? hi[2] : lo[2];
+		double c[4], m[4];
+		for (int r = 0; r < 4; ++r) {
+			c[r] = vpm[r] * x + vpm[4 + r] * y + vpm[8 + r] * z + vpm[12 + r];
+			m[r] = std::fabs(vpm[r] * x) + std::fabs(vpm[4 + r] * y) + std::fabs(vpm[8 + r] * z) + std::fabs(static_cast<double>(vpm[12 + r])); }
+		const double g = guardFactor;
+		val[0][k] = g * c[3] + c[0]; mag[0][k] = g * m[3] + m[0];
+		val[1][k] = g * c[3] + c[1]; mag[1][k] = g * m[3] + m[1];
+		val[2][k] = c[3] + c[2];     mag[2][k] = m[3] + m[2];
+		val[3][k] = g * c[3] - c[0]; mag[3][k] = g * m[3] + m[0];
+		val[4][k] = g * c[3] - c[1]; mag[4][k] = g * m[3] + m[1]; }
+	for (int p = 0; p < 5; ++p) {
+		bool all = true;
+		for (int k = 0; k < 8; ++k) { all = all && (val[p][k] <= -(1e-4 * mag[p][k] + 1e-30)); }   // (false for NaN / inf)
+		if (all) { return true; } }
+	return false; }
 
 // GL::MaybeUpdateState (rglv_gl.cxx:100-106): snapshot on first use after a change.  The device
 // record (DevState) is built here, once; rsrcu_end_frame only copies it into the upload arena.
@@ -431,6 +475,8 @@ int snapshotState(rsrcu_ctx* c) {
 		tu.kind = !isPow2 ? 0 : (ht.filter ? 2 : 1); }
 	ds.tu3 = encodeRef<float>(c->curTu3, anyArena);
 	ds.tu3dim = c->curTu3dim;
+	hs.posRanged = true;
+	for (int b = 0; b < 3; ++b) { hs.posRanged = hs.posRanged && !c->curBuffers[b].null && c->curBuffers[b].ranged; hs.posLo[b] = c->curBuffers[b].lo; hs.posHi[b] = c->curBuffers[b].hi; }
 	hs.programId = s.program_id;
 	hs.key = keyOf(s);
 	hs.posNull = c->curBuffers[0].null;
@@ -734,7 +780,7 @@ int rsrcu_release_static(rsrcu_ctx* c) {
 	CU(cudaStreamSynchronize(c->stream));
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	c->staticCache.clear();
-	std::fill(c->ptrCache.begin(), c->ptrCache.end(), PtrCacheEntry{nullptr, 0, nullptr});
+	std::fill(c->ptrCache.begin(), c->ptrCache.end(), PtrCacheEntry{nullptr, 0, nullptr, 0.0f, 0.0f, false});
 	return RSRCU_OK; }
 
 int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int tileHBlocks) {
@@ -750,6 +796,10 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->outSlot = (c->outSlot + 1) % kSlots;
 	CU(cudaEventSynchronize(c->arenaFree[c->outSlot]));
 	c->width = width; c->height = height;
+	{
+		// CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
+		const int half = std::max(width, height) / 2;
+		c->guardFactor = (2048.0f - static_cast<float>(half)) / static_cast<float>(half); }
 	const int rw = tileWBlocks * 8, rh = tileHBlocks * 8;
 	// the device tile must lie inside one reference tile to reproduce its start point exactly;
 	// otherwise use the device tile itself (identical unless an int32 edge product overflows)
@@ -783,7 +833,7 @@ int rsrcu_set_state(rsrcu_ctx* c, const RsrState* st) {
 int rsrcu_bind_buffer(rsrcu_ctx* c, int slot, const float* host, size_t nFloats, int upload) {
 	if (!c || slot < 0 || slot >= 16) { return fail(RSRCU_ERR_INVALID, "bad buffer slot %d", slot); }
 	if (!c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_bind_buffer outside begin/end frame"); }
-	int r = uploadData(c, host, nFloats * sizeof(float), upload, c->curBuffers[slot]);
+	int r = uploadData(c, host, nFloats * sizeof(float), upload, c->curBuffers[slot], slot < 3);
 	if (r != RSRCU_OK) { return r; }
 	c->curBufferFloats[slot] = host ? nFloats : 0;
 	c->stateDirty = true;
@@ -859,6 +909,12 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 	if (instances > 65536) { return fail(RSRCU_ERR_INVALID, "instance id must fit uint16 (rglv_gpu_impl.hxx:490)"); }
 	const int prims = count / 3;
 	if (prims == 0) { return RSRCU_OK; }
+	// whole-draw frustum rejection (sub-frames of a large target see most of the scene off screen): every program except
+	// Many transforms the position attribute by vpm alone
+	if (!instanced && programId != 6 && hs.posRanged && boxOutsideFrustum(hs.ds.vpm, hs.posLo, hs.posHi, c->guardFactor)) {
+		c->trianglesSubmitted += static_cast<uint64_t>(prims);
+		++c->drawsCulled;
+		return RSRCU_OK; }
 
 	HostDraw hd{};
 	DevDraw& d = hd.d;
@@ -1001,10 +1057,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 	fp.tilesX = (W + kTile - 1) / kTile; fp.tilesY = (H + kTile - 1) / kTile;
 	fp.refTileW = c->refTileW; fp.refTileH = c->refTileH;
 	fp.postTileW = c->postTileW; fp.postTileH = c->postTileH;
-	{
-		// CalcGuardBandFactor (rglv_view_frustum.hxx:36-39)
-		const int half = std::max(W, H) / 2;
-		fp.guardFactor = (2048.0f - static_cast<float>(half)) / static_cast<float>(half); }
+	fp.guardFactor = c->guardFactor;
 	fp.ndraws = static_cast<int>(c->draws.size());
 	fp.ncmds = static_cast<int>(c->cmds.size());
 	const int ntiles = fp.tilesX * fp.tilesY;
@@ -1250,6 +1303,7 @@ int rsrcu_sync(rsrcu_ctx* c) {
 	c->stats.host_record_ns = c->recordNs;
 	c->stats.host_submit_ns = c->submitNs;
 	c->stats.frames_retried = c->framesRetried;
+	c->stats.draws_culled = c->drawsCulled;
 	if (c->profiling) {
 		for (int i = 0; i < 6; ++i) { c->stageMs[i] = 0.0f; }
 		if (c->profiling > 1) { for (int i = 0; i < 5; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); } }

@@ -136,3 +136,44 @@ def test_cost_balanced_ownership():
         assert max(load) <= max(rr)
         plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
         assert sorted(s.index for r in range(world) for s in plan.owned_by(r)) == list(range(16))
+
+
+@pytest.mark.gpu
+def test_whole_draw_frustum_rejection_is_invisible(ref_gpu):
+    """sub-frames of a large target see most draws entirely off screen: a draw whose cached bounding box lies beyond one
+    guard-band plane is skipped on the host (every one of its triangles would be dropped by the reference's
+    'all three vertices share a flag' test, rglv_gpu_impl.hxx:427-433).  Static buffers only; the frames stay
+    bit-identical to the reference's, which processes every triangle."""
+    g = R.GPU(0)
+    try:
+        plan = SubframePlan(1280, 720, 1, max_w=640, max_h=360)
+        sc = scenes.GeometryStressScene(spheres=40, divs=3, size=(1280, 720), radius_px=40.0)
+        culled_before = 0
+        total_culled = 0
+        for s in plan.subframes:
+            a, b = np.zeros((s.height, s.width), np.uint32), np.zeros((s.height, s.width), np.uint32)
+            proj = plan.projection(sc.projection(), s)
+            sc.record(ref_gpu, (s.width, s.height), a, proj=proj); ref_gpu.Run()
+            sc.record(g, (s.width, s.height), b, proj=proj, static=True); g.Run()
+            assert np.unique(a).size > 50
+            assert np.array_equal(a, b), f"sub-frame {s.index}: {np.count_nonzero(a != b)} pixels differ"
+            st = g.stats()
+            assert st["triangles_submitted"] == sc.triangles
+            total_culled += st["draws_culled"] - culled_before
+            culled_before = st["draws_culled"]
+        assert total_culled > sc.draws            # on average more than a quarter of the draws per sub-frame
+        # dynamic (UPLOAD_ALWAYS) buffers carry no bounding box: nothing is skipped, same pixels
+        s = plan.subframes[0]
+        a, b = np.zeros((s.height, s.width), np.uint32), np.zeros((s.height, s.width), np.uint32)
+        proj = plan.projection(sc.projection(), s)
+        sc.record(ref_gpu, (s.width, s.height), a, proj=proj); ref_gpu.Run()
+        class NoStatic:        # (the scenes mark their buffers static when the GL object has a stats() method)
+            def __getattr__(self, n):
+                if n == "stats":
+                    raise AttributeError(n)
+                return getattr(g, n)
+        dyn = NoStatic()
+        sc.record(dyn, (s.width, s.height), b, proj=proj); g.Run()
+        assert np.array_equal(a, b)
+    finally:
+        g.close()
