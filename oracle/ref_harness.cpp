@@ -24,6 +24,7 @@
 #include "src/rgl/rglr/rglr_texture.hxx"
 #include "src/rgl/rglv/rglv_gl.hxx"
 #include "src/rgl/rglv/rglv_gpu.hxx"
+#include "src/rgl/rglv/rglv_math.hxx"
 #include "src/rgl/rglv/rglv_triangle.hxx"
 #include "src/rml/rmlm/rmlm_mat4.hxx"
 #include "src/rml/rmlv/rmlv_mvec4.hxx"
@@ -235,6 +236,15 @@ void ref_oneover(const float* in, float* out, int n) {
 void ref_mat4_mul(const float* a, const float* b, float* out) {
 	auto r = ToMat4(a) * ToMat4(b);
 	std::memcpy(out, r.ff.data(), sizeof(float) * 16); }
+/* the reference's camera matrices (rglv_math.cxx:66-106), column-major out: used to build the bundled-scene fixtures */
+void ref_look_at(const float* eye, const float* center, const float* up, float* out16) {
+	const auto m = rglv::LookAt(rmlv::vec3{eye[0], eye[1], eye[2]}, rmlv::vec3{center[0], center[1], center[2]}, rmlv::vec3{up[0], up[1], up[2]});
+	std::memcpy(out16, m.ff.data(), sizeof(float) * 16); }
+
+void ref_perspective2(float fovy, float aspect, float znear, float zfar, float* out16) {
+	const auto m = rglv::Perspective2(fovy, aspect, znear, zfar);
+	std::memcpy(out16, m.ff.data(), sizeof(float) * 16); }
+
 void ref_mat4_inverse(const float* a, float* out) {
 	auto r = rmlm::inverse(ToMat4(a));
 	std::memcpy(out, r.ff.data(), sizeof(float) * 16); }

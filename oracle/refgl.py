@@ -92,6 +92,8 @@ def _bind(path):
         "ref_oneover": (None, [vp, vp, ci]),
         "ref_mat4_mul": (None, [vp, vp, vp]),
         "ref_mat4_inverse": (None, [vp, vp]),
+        "ref_look_at": (None, [vp, vp, vp, vp]),
+        "ref_perspective2": (None, [cf, cf, cf, cf, vp]),
         "ref_raster_coverage": (None, [vp, ci, ci, vp]),
         "ref_vraster_coverage": (None, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     }
@@ -341,6 +343,21 @@ def mat4_inverse(a):
     aa = _f32(np.asarray(a).T.reshape(16))
     out = np.empty(16, np.float32)
     lib().ref_mat4_inverse(_ptr(aa), _ptr(out))
+    return out.reshape(4, 4).T.copy()
+
+
+def look_at(eye, center, up):
+    """rglv::LookAt (rglv_math.cxx:66-86) -> 4x4 row-major numpy (math convention)"""
+    e, c, u = (_f32(v).reshape(3) for v in (eye, center, up))
+    out = np.empty(16, np.float32)
+    lib().ref_look_at(_ptr(e), _ptr(c), _ptr(u), _ptr(out))
+    return out.reshape(4, 4).T.copy()
+
+
+def perspective2(fovy, aspect, znear, zfar):
+    """rglv::Perspective2 (rglv_math.cxx:101-106) -> 4x4 row-major numpy"""
+    out = np.empty(16, np.float32)
+    lib().ref_perspective2(float(fovy), float(aspect), float(znear), float(zfar), _ptr(out))
     return out.reshape(4, 4).T.copy()
 
 

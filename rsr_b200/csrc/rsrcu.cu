@@ -132,7 +132,8 @@ struct FramePlan {
 	void* tcDev{nullptr}; int tcStride{0};   // the frame's last true-colour store (rsrcu_device_truecolor)
 	int storesUsed{0};                       // store targets of the context's pool the frame's commands point into
 	uint64_t trianglesSubmitted{0};
-	uint64_t inputBytes{0}; };
+	uint64_t inputBytes{0};
+	uint32_t progMask{0}; };                 // programs the frame's draws use (prog_bit): selects the tile kernel instantiation
 
 struct rsrcu_frame {
 	FramePlan plan;
@@ -200,6 +201,7 @@ struct rsrcu_ctx {
 	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr, 0.0f, 0.0f, false});
 	float guardFactor{1.0f};
 	uint64_t drawsCulled{0};
+	uint32_t progMask{0};
 
 	// device work buffers
 	// the frame's intermediate buffers; two sets so that, in overlap mode, the front end (K0-K5) of frame N+1 can fill one
@@ -487,6 +489,30 @@ int snapshotState(rsrcu_ctx* c) {
 	return RSRCU_OK; }
 
 // every kernel of the frame is launched with programmatic stream serialization (see pdl_wait in kernels.cuh)
+// Instantiations of the tile kernel: the general one carries all eleven programs; frames whose draws use a subset get a
+// kernel compiled for just those programs (registers are allotted for the programs present, not for the hungriest of all)
+using TileKernelFn = void (*)(const TileArgs);
+struct TileVariant { uint32_t progs; TileKernelFn fn; const char* name; };
+constexpr uint32_t kPAmy = prog_bit(ProgAmy::id), kPOBJ2 = prog_bit(ProgOBJ2::id), kPMany = prog_bit(ProgMany::id);
+#ifndef RSR_TILE_CTAS_AMY
+#define RSR_TILE_CTAS_AMY 3   // (4 CTAs / 64 registers: measured slower on c3 and c4, spills)
+#endif
+#ifndef RSR_TILE_CTAS_LIT
+#define RSR_TILE_CTAS_LIT 4   // c2: 121 -> 117 us
+#endif
+const TileVariant kTileVariants[] = {
+	{ kPAmy, tile_kernel<kPAmy, RSR_TILE_CTAS_AMY>, "amy" },
+	{ kPOBJ2 | kPMany, tile_kernel<kPOBJ2 | kPMany, RSR_TILE_CTAS_LIT>, "obj2+many" },
+	{ kPAmy | kPOBJ2 | kPMany, tile_kernel<kPAmy | kPOBJ2 | kPMany, RSR_TILE_CTAS_LIT>, "amy+obj2+many" },
+	{ kAllProgs, tile_kernel<kAllProgs, RSR_TILE_CTAS>, "all" } };
+
+const TileVariant& tileVariantFor(uint32_t progMask) {
+	static const int forced = std::getenv("RSRCU_TILE_VARIANT") ? std::atoi(std::getenv("RSRCU_TILE_VARIANT")) : -1;
+	constexpr int n = static_cast<int>(sizeof(kTileVariants) / sizeof(kTileVariants[0]));
+	if (forced >= 0 && forced < n && (progMask & ~kTileVariants[forced].progs) == 0u) { return kTileVariants[forced]; }
+	for (const TileVariant& v : kTileVariants) { if ((progMask & ~v.progs) == 0u) { return v; } }
+	return kTileVariants[n - 1]; }
+
 template <class... KArgs, class... Args>
 cudaError_t launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
 	cudaLaunchConfig_t cfg{};
@@ -632,7 +658,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	ta.tileOrder = fp.totalPJobs ? static_cast<const uint32_t*>(w.tileOrder.ptr) : nullptr;
 	ta.runScratch = static_cast<uint32_t*>(w.runScratch.ptr);
 	ta.ctr = dCtr;
-	CU(launchPdl(tile_kernel, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
+	CU(launchPdl(tileVariantFor(plan.progMask).fn, static_cast<unsigned>(ntiles), static_cast<unsigned>(kTileThreads), sizeof(TileShared), tileStream, ta));
 	++c->launches;
 	CU(cudaGetLastError());
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[7], tileStream)); }
@@ -707,7 +733,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	if (const char* cap = std::getenv("RSRCU_LIST_CAPACITY")) {   // initial tile-list capacity in entries (tests)
 		const long v = std::atol(cap);
 		if (v > 0) { c->listCapacity = static_cast<uint32_t>(v); } }
-	CU(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TileShared))));
+	for (const TileVariant& v : kTileVariants) { CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TileShared)))); }
 	for (int i = 0; i < 2048; ++i) { c->hostLuts.rcp16[i] = static_cast<uint16_t>((c->hostLuts.rcp[i] >> 7) & 0xffffu); }
 	CU(cudaMalloc(&c->devLuts, sizeof(ApproxLuts)));
 	CU(cudaMemcpy(c->devLuts, &c->hostLuts, sizeof(ApproxLuts), cudaMemcpyHostToDevice));
@@ -811,7 +837,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->launched[c->outSlot] = Launched{};
 	c->storesUsed = 0; c->tcDev = nullptr;
 	c->arenas[c->outSlot].used = 0;
-	c->trianglesSubmitted = 0; c->inputBytes = 0;
+	c->trianglesSubmitted = 0; c->inputBytes = 0; c->progMask = 0;
 	c->haveState = false; c->stateDirty = true;
 	for (auto& b : c->curBuffers) { b = DevRef{}; }
 	for (auto& f : c->curBufferFloats) { f = 0; }
@@ -955,6 +981,7 @@ static int recordDraw(rsrcu_ctx* c, int count, const uint16_t* indices, int inst
 		int attrs = 0;
 		for (int slot = 0; slot <= 10; ++slot) { attrs += hs.ds.buffers[slot] != nullptr ? 1 : 0; }
 		c->inputBytes += static_cast<uint64_t>(nverts) * 4u * attrs + (arrays ? 0u : static_cast<uint64_t>(prims) * 6u) + (instanced ? static_cast<uint64_t>(instances) * 64u : 0u); }
+	c->progMask |= prog_bit(programId);
 	c->draws.push_back(hd);
 	return RSRCU_OK; }
 
@@ -1148,7 +1175,7 @@ int rsrcu_end_frame(rsrcu_ctx* c) {
 		++plan.ncmdInline; }
 	plan.copies = c->copies;
 	plan.tcDev = c->tcDev; plan.tcStride = c->tcStride; plan.storesUsed = c->storesUsed;
-	plan.trianglesSubmitted = c->trianglesSubmitted; plan.inputBytes = c->inputBytes;
+	plan.trianglesSubmitted = c->trianglesSubmitted; plan.inputBytes = c->inputBytes; plan.progMask = c->progMask;
 	plan.valid = true;
 	CU(c->arenas[c->outSlot].dev.reserve(c->arenas[c->outSlot].used));
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[2] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }

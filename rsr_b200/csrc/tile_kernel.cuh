@@ -578,21 +578,35 @@ __device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A
 		return fast ? draw_batch_queued<P, true>(sh, A, flags, base, nb, ox, oy) : draw_batch_queued<P, false>(sh, A, flags, base, nb, ox, oy); }
 	return fast ? draw_batch_direct<P, true>(sh, A, flags, base, nb, ox, oy) : draw_batch_direct<P, false>(sh, A, flags, base, nb, ox, oy); }
 
-// program dispatch for one batch of set-up triangles in slots [base, base + nb)
+// program dispatch for one batch of set-up triangles in slots [base, base + nb).  PROGS: the programs this instantiation
+// of the tile kernel carries (bit = prog_bit(id)); a frame is launched on the smallest instantiation that holds its programs
+__host__ __device__ constexpr uint32_t prog_bit(int id) {
+	return id == ProgAmy::id ? 1u : id == ProgAlphaTexture::id ? 2u : id == ProgText::id ? 4u : id == ProgDepth::id ? 8u :
+	       id == ProgPattern::id ? 16u : id == ProgMany::id ? 32u : id == ProgOBJ1::id ? 64u : id == ProgOBJ2::id ? 128u :
+	       id == ProgOBJ2S::id ? 256u : id == ProgEnvmap::id ? 512u : id == ProgWireframe::id ? 1024u : 0u; }
+constexpr uint32_t kAllProgs = 0x7ffu;
+
+template <uint32_t PROGS, class P>
+__device__ __forceinline__ bool draw_batch_if(unsigned& frags, TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy, bool queued) {
+	if constexpr ((PROGS & prog_bit(P::id)) != 0u) {
+		if ((key0 & 0xffu) == static_cast<uint32_t>(P::id)) { frags = draw_batch<P>(sh, A, key0, base, nb, ox, oy, queued); return true; } }
+	return false; }
+
+template <uint32_t PROGS>
 __device__ __forceinline__ unsigned draw_batch_any(TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy, bool queued) {
-	switch (key0 & 0xffu) {
-	case ProgAmy::id:          return draw_batch<ProgAmy>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgAlphaTexture::id: return draw_batch<ProgAlphaTexture>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgText::id:         return draw_batch<ProgText>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgDepth::id:        return draw_batch<ProgDepth>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgPattern::id:      return draw_batch<ProgPattern>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgMany::id:         return draw_batch<ProgMany>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgOBJ1::id:         return draw_batch<ProgOBJ1>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgOBJ2::id:         return draw_batch<ProgOBJ2>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgOBJ2S::id:        return draw_batch<ProgOBJ2S>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgEnvmap::id:       return draw_batch<ProgEnvmap>(sh, A, key0, base, nb, ox, oy, queued);
-	case ProgWireframe::id:    return draw_batch<ProgWireframe>(sh, A, key0, base, nb, ox, oy, queued);
-	default: return 0u; } }
+	unsigned frags = 0;
+	draw_batch_if<PROGS, ProgAmy>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgOBJ2>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgMany>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgAlphaTexture>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgText>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgDepth>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgPattern>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgOBJ1>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgOBJ2S>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgEnvmap>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgWireframe>(frags, sh, A, key0, base, nb, ox, oy, queued);
+	return frags; }
 
 // ---- IQPostProgram::ShadeCanvas (src/viewer/shaders.hxx:56-66) --------------------------------
 // pow(x, y) = exp2f4(log2f4(x) * y)  (rmlv_mvec4.hxx:652-654, 3rdparty/sse-pow/sse_pow.h:19-95):
@@ -986,6 +1000,7 @@ __device__ __forceinline__ void exec_cmds(TileShared& sh, const TileArgs& A, int
 #endif
 
 // one warp rasterises the nb (<= 32) triangles it has set up in its own record slots [base, base + nb)
+template <uint32_t PROGS>
 __device__ __forceinline__ unsigned raster_slots(TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy) {
 	__syncwarp();
 	const int lane = threadIdx.x & 31;
@@ -995,14 +1010,15 @@ __device__ __forceinline__ unsigned raster_slots(TileShared& sh, const TileArgs&
 		tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
 	const int ntiny = __popc(__ballot_sync(0xffffffffu, tiny));
 	const bool queued = nb >= RSR_WARP_QUEUE_MIN && ntiny * 2 > nb;
-	const unsigned frags = draw_batch_any(sh, A, key0, base, nb, ox, oy, queued);
+	const unsigned frags = draw_batch_any<PROGS>(sh, A, key0, base, nb, ox, oy, queued);
 	__syncwarp();
 	return frags; }
 
 #ifndef RSR_TILE_CTAS
 #define RSR_TILE_CTAS 3
 #endif
-__global__ void __launch_bounds__(kTileThreads, RSR_TILE_CTAS)
+template <uint32_t PROGS, int MIN_CTAS>
+__global__ void __launch_bounds__(kTileThreads, MIN_CTAS)
 tile_kernel(const __grid_constant__ TileArgs A) {
 	extern __shared__ __align__(16) unsigned char tileSmem[];
 	TileShared& sh = *reinterpret_cast<TileShared*>(tileSmem);
@@ -1122,7 +1138,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 			const unsigned hitMask = __ballot_sync(0xffffffffu, mine);
 			const int nhit = __popc(hitMask);
 			if (nrec + nhit > 32) {
-				frags += raster_slots(sh, A, key0, wbase, nrec, ox, oy);
+				frags += raster_slots<PROGS>(sh, A, key0, wbase, nrec, ox, oy);
 				nrec = 0; }
 			if (mine) {
 				const int slot = wbase + nrec + __popc(hitMask & ltMask);
@@ -1130,7 +1146,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 				setup_triangle(sh, slot, myId, myRec, A, ox, oy, rl, rt, rr, rb); }
 			nrec += nhit;
 			pos += take; }
-		if (nrec) { frags += raster_slots(sh, A, key0, wbase, nrec, ox, oy); }
+		if (nrec) { frags += raster_slots<PROGS>(sh, A, key0, wbase, nrec, ox, oy); }
 		PHASE(8);
 		chunkPos = pos; }
 	PHASE(9);
@@ -1180,7 +1196,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 #define RSR_QUEUE_MIN_NB 96
 #endif
 		const bool queued = nb >= RSR_QUEUE_MIN_NB && ntiny * 2 > nb;
-		frags += draw_batch_any(sh, A, key0, 0, nb, ox, oy, queued);
+		frags += draw_batch_any<PROGS>(sh, A, key0, 0, nb, ox, oy, queued);
 		PHASE(8);
 		chunkPos += max(nb, 1); }
 	PHASE(9);

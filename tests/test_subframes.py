@@ -146,8 +146,9 @@ def test_whole_draw_frustum_rejection_is_invisible(ref_gpu):
     bit-identical to the reference's, which processes every triangle."""
     g = R.GPU(0)
     try:
-        plan = SubframePlan(1280, 720, 1, max_w=640, max_h=360)
-        sc = scenes.GeometryStressScene(spheres=40, divs=3, size=(1280, 720), radius_px=40.0)
+        # (1920x1080 sub-frames: the guard band reaches only 13 % beyond the sub-frame, rglv_view_frustum.hxx:36-39)
+        plan = SubframePlan(3840, 2160, 1, max_w=1920, max_h=1080)
+        sc = scenes.GeometryStressScene(spheres=40, divs=3, size=(3840, 2160), radius_px=60.0)
         culled_before = 0
         total_culled = 0
         for s in plan.subframes:
