@@ -38,6 +38,11 @@ SRCS=(
   src/rcl/rclmt/rclmt_jobsys.cxx
   src/rcl/rclmt/rclmt_barrier.cxx
   src/rml/rmlm/rmlm_mat4.cxx
+  src/rml/rmlv/rmlv_vec.cxx
+  src/rgl/rglv/rglv_obj.cxx
+  src/rgl/rglv/rglv_mesh.cxx
+  src/rgl/rglv/rglv_mesh_util.cxx
+  src/rgl/rglv/rglv_material.cxx
   src/viewer/shaders.cxx
   src/viewer/shaders_envmap.cxx
   src/viewer/shaders_wireframe.cxx
@@ -55,6 +60,11 @@ for s in "${SRCS[@]}"; do
 done
 ho="$OUT/obj/ref_harness.o"
 "$CXX" "${FLAGS[@]}" -c "$HERE/ref_harness.cpp" -o "$ho" &
+pids+=($!)
+# POSIX stand-ins for the Windows-only string / path helpers the reference's OBJ loader calls (see the file's header)
+po="$OUT/obj/ref_posix_util.o"
+OBJS+=("$po")
+"$CXX" "${FLAGS[@]}" -c "$HERE/ref_posix_util.cpp" -o "$po" &
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 "$CXX" -shared -o "$OUT/librsr_ref.so" "${OBJS[@]}" "$ho" -lpthread

@@ -25,6 +25,10 @@
 #include "src/rgl/rglv/rglv_gl.hxx"
 #include "src/rgl/rglv/rglv_gpu.hxx"
 #include "src/rgl/rglv/rglv_math.hxx"
+#include "src/rgl/rglv/rglv_mesh.hxx"
+#include "src/rgl/rglv/rglv_mesh_util.hxx"
+#include "src/rgl/rglv/rglv_obj.hxx"
+#include "src/rgl/rglv/rglv_vao.hxx"
 #include "src/rgl/rglv/rglv_triangle.hxx"
 #include "src/rml/rmlm/rmlm_mat4.hxx"
 #include "src/rml/rmlv/rmlv_mvec4.hxx"
@@ -244,6 +248,43 @@ void ref_look_at(const float* eye, const float* center, const float* up, float* 
 void ref_perspective2(float fovy, float aspect, float znear, float zfar, float* out16) {
 	const auto m = rglv::Perspective2(fovy, aspect, znear, zfar);
 	std::memcpy(out16, m.ff.data(), sizeof(float) * 16); }
+
+/* The reference's own mesh path: LoadOBJ (rglv_obj.cxx:193-283: parse, triangulate, normals) then
+ * MakeArray(mesh, spec, ...) (rglv_mesh_util.cxx:81-136: de-duplicated SoA vertex arrays + uint16 indices, padded to
+ * a multiple of four) -- what the viewer's $mesh node binds with UseBuffer(0 / 3 / 6) (src/viewer/node/mesh.cxx:40,
+ * 101-104).  Returns the vertex count (padding included) or -1; arrays are [9][maxVerts]-style: a0.x a0.y a0.z a1.x ... */
+int ref_load_obj_arrays(const char* path, const char* spec, float* soa9, int maxVerts, uint16_t* idx, int maxIdx, int* nIdx) {
+	try {
+		const auto mesh = rglv::LoadOBJ(std::pmr::string(path));
+		rglv::VertexArray_F3F3F3 buf;
+		rcls::vector<uint16_t> indices;
+		rglv::MakeArray(mesh, std::string(spec), buf, indices);
+		const int nv = buf.size();
+		*nIdx = static_cast<int>(indices.size());
+		if (nv > maxVerts || *nIdx > maxIdx) { return -1; }
+		const rglv::Float3Array* arrs[3] = { &buf.a0, &buf.a1, &buf.a2 };
+		for (int a = 0; a < 3; ++a) {
+			std::memcpy(soa9 + (a * 3 + 0) * maxVerts, arrs[a]->x.data(), sizeof(float) * nv);
+			std::memcpy(soa9 + (a * 3 + 1) * maxVerts, arrs[a]->y.data(), sizeof(float) * nv);
+			std::memcpy(soa9 + (a * 3 + 2) * maxVerts, arrs[a]->z.data(), sizeof(float) * nv); }
+		std::memcpy(idx, indices.data(), sizeof(uint16_t) * indices.size());
+		return nv; }
+	catch (...) { return -1; } }
+
+/* The viewer's $perspective camera node (src/viewer/node/perspective.cxx:51-69), restated here because the node
+ * classes live in anonymous namespaces of translation units that need the whole scene compiler: direction and right
+ * vector from the two angles, up = cross(right, dir), view = LookAt(position, position + dir, up),
+ * projection = translate(origin) * Perspective2(fov, aspect, 10, 1000) with origin = 0. */
+void ref_perspective_camera(const float* position, float ha, float va, float fov, float aspect, float* view16, float* proj16) {
+	const rmlv::vec3 pos{position[0], position[1], position[2]};
+	const rmlv::vec3 dir{ cosf(va)*sinf(ha), sinf(va), cosf(va)*cosf(ha) };
+	const rmlv::vec3 right{ sinf(ha-3.14F/2.0F), 0.0F, cosf(ha-3.14F/2.0F) };
+	const rmlv::vec3 up = cross(right, dir);
+	const auto v = rglv::LookAt(pos, pos + dir, up);
+	auto p = rglv::Perspective2(fov, aspect, 10, 1000);
+	p = rmlm::mat4::translate(0.0F, 0.0F, 0) * p;
+	std::memcpy(view16, v.ff.data(), sizeof(float) * 16);
+	std::memcpy(proj16, p.ff.data(), sizeof(float) * 16); }
 
 void ref_mat4_inverse(const float* a, float* out) {
 	auto r = rmlm::inverse(ToMat4(a));

@@ -94,6 +94,8 @@ def _bind(path):
         "ref_mat4_inverse": (None, [vp, vp]),
         "ref_look_at": (None, [vp, vp, vp, vp]),
         "ref_perspective2": (None, [cf, cf, cf, cf, vp]),
+        "ref_perspective_camera": (None, [vp, cf, cf, cf, cf, vp, vp]),
+        "ref_load_obj_arrays": (ci, [C.c_char_p, C.c_char_p, vp, ci, vp, ci, vp]),
         "ref_raster_coverage": (None, [vp, ci, ci, vp]),
         "ref_vraster_coverage": (None, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     }
@@ -359,6 +361,27 @@ def perspective2(fovy, aspect, znear, zfar):
     out = np.empty(16, np.float32)
     lib().ref_perspective2(float(fovy), float(aspect), float(znear), float(zfar), _ptr(out))
     return out.reshape(4, 4).T.copy()
+
+
+def perspective_camera(position, h, v, fov, aspect):
+    """the viewer's $perspective node (src/viewer/node/perspective.cxx:51-69) -> (view, projection), 4x4 row-major numpy"""
+    pos = _f32(position).reshape(3)
+    vm, pm = np.empty(16, np.float32), np.empty(16, np.float32)
+    lib().ref_perspective_camera(_ptr(pos), float(h), float(v), float(fov), float(aspect), _ptr(vm), _ptr(pm))
+    return vm.reshape(4, 4).T.copy(), pm.reshape(4, 4).T.copy()
+
+
+def load_obj_arrays(path, spec="PND", max_verts=65536):
+    """rglv::LoadOBJ + rglv::MakeArray(mesh, spec) (rglv_obj.cxx:193-283, rglv_mesh_util.cxx:81-136): the three SoA
+    vertex arrays the viewer's $mesh node binds to buffer slots 0 / 3 / 6 (each (3, nverts) float32, padded to a
+    multiple of four vertices like the reference's) and the uint16 index list"""
+    soa = np.zeros((9, max_verts), np.float32)
+    idx = np.zeros(3 * 65536, np.uint16)
+    nidx = C.c_int(0)
+    nv = lib().ref_load_obj_arrays(os.fsencode(path), spec.encode(), _ptr(soa), max_verts, _ptr(idx), idx.size, C.byref(nidx))
+    if nv < 0:
+        raise RuntimeError(f"reference OBJ loader failed on {path}")
+    return [np.ascontiguousarray(soa[3 * a:3 * a + 3, :nv]) for a in range(3)], idx[:nidx.value].copy()
 
 
 def raster_coverage(xy, w, h):

@@ -47,8 +47,16 @@ struct VertexIn {
 	float u, v;            // slots 9-10
 	const float* imat; };  // slot 15: per-instance mat4 (column-major)
 
+// what the pow2 samplers need of texture unit 0, staged per triangle in the tile kernel's shared memory (a state lookup in
+// global memory per rasterised quad would sit on the critical path in front of the texel taps)
+struct TexDesc {
+	const float4* texels;
+	uint32_t texelCount;
+	int kind, power; };
+
 struct FragIn {
 	const DevState* st;
+	TexDesc tex0;               // texture unit 0 of the triangle's draw
 	const uint32_t* rcpLut;
 	const uint32_t* rsqrtLut;
 	float fragX[4], fragY[4];   // gl_FragCoord
@@ -65,7 +73,7 @@ constexpr int kStageTexels = RSR_COOP_STAGE ? 208 : 20;
 
 // ---- texture units (src/rgl/rglr/rglr_texture_sampler.cxx) -------------------------------------
 
-__device__ __forceinline__ float4 fetch_texel(const TexUnit& tu, int ofs) {
+__device__ __forceinline__ float4 fetch_texel(const TexDesc& tu, int ofs) {
 	// the reference would read out of bounds for wild coordinates; stay inside the allocation
 	const uint32_t o = static_cast<uint32_t>(ofs);
 	return __ldg(tu.texels + (o < tu.texelCount ? o : 0u)); }
@@ -101,17 +109,19 @@ __device__ __forceinline__ void blend_taps(const float4 p00, const float4 p10, c
 // lanes of a quarter warp sit two pixels = two texels apart, so their taps then read consecutive 16-byte slots
 // (no bank conflicts).  A box that does not fit (minification near the next level, anisotropy) or quads that
 // disagree on the level take the gather route.
-__device__ __forceinline__ void sample_quad(const FragIn& f, const TexUnit& tu, const float (&u)[4], const float (&v)[4],
+__device__ __forceinline__ void sample_quad(const FragIn& f, const float (&u)[4], const float (&v)[4],
                                             float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], const uint32_t mask) {
+	const TexDesc& tu = f.tex0;
 	if (tu.kind == 0) {
 		// TextureUnitRGBAF32_NM_ONEMAP_WRAP_NEAREST (rglr_texture_sampler.cxx:289-311)
-		const float fw = itof(tu.width), fh = itof(tu.height);
+		const TexUnit& gtu = f.st->tu[0];   // (width / height / stride: only this sampler needs them)
+		const float fw = itof(gtu.width), fh = itof(gtu.height);
 		const float almostOne = u2f(0x3f7fffffu);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
 			const int pxU = cvtt(fract_sse(u[l] + 100.0f) * fw);
 			const int pxV = cvtt((almostOne - fract_sse(v[l] + 100.0f)) * fh);
-			const float4 t = fetch_texel(tu, pxV * tu.stride + pxU);
+			const float4 t = fetch_texel(tu, pxV * gtu.stride + pxU);
 			r[l] = t.x; g[l] = t.y; b[l] = t.z; a[l] = t.w; }
 		return; }
 
@@ -241,30 +251,33 @@ __device__ __forceinline__ float sample_depth(const DevState& st, float cx, floa
 
 struct ProgBase {   // rglv::BaseProgram
 	static constexpr int id = 0;
+	static constexpr bool samples = false;   // fragment stage samples texture unit 0 (the tile kernel stages its TexDesc)
 	static constexpr bool earlyZ = true;
 	static constexpr int NV = 0; };
 
 struct ProgAmy : ProgBase {   // shaders.hxx:69-161
 	static constexpr int id = 4;
+	static constexpr bool samples = true;
 	static constexpr int NV = 2;
 	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
 		vary[0] = v.u; vary[1] = v.v;
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
-		sample_quad(f, f.st->tu[0], at[0], at[1], r, g, b, a, mask); } };
+		sample_quad(f, at[0], at[1], r, g, b, a, mask); } };
 
 struct ProgAlphaTexture : ProgAmy {   // shaders.hxx:164-229
 	static constexpr int id = 65;
 	static constexpr bool earlyZ = false;
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
-		sample_quad(f, f.st->tu[0], at[0], at[1], r, g, b, a, mask);
+		sample_quad(f, at[0], at[1], r, g, b, a, mask);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { if (!(a[l] > 0.0f)) { mask &= ~(1u << l); } } } };
 
 struct ProgText : ProgBase {   // shaders.hxx:232-318
 	static constexpr int id = 26;
+	static constexpr bool samples = true;
 	static constexpr bool earlyZ = false;
 	static constexpr int NV = 5;
 	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary) {
@@ -272,7 +285,7 @@ struct ProgText : ProgBase {   // shaders.hxx:232-318
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
-		sample_quad(f, f.st->tu[0], at[3], at[4], r, g, b, a, mask);
+		sample_quad(f, at[3], at[4], r, g, b, a, mask);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
 			r[l] *= at[0][l]; g[l] *= at[1][l]; b[l] *= at[2][l];
@@ -280,6 +293,7 @@ struct ProgText : ProgBase {   // shaders.hxx:232-318
 
 struct ProgDepth : ProgAmy {   // shaders.hxx:321-419
 	static constexpr int id = 5;
+	static constexpr bool samples = false;
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
 		const float zNear = 10.0f, zFar = 1000.0f;
@@ -291,6 +305,7 @@ struct ProgDepth : ProgAmy {   // shaders.hxx:321-419
 
 struct ProgPattern : ProgBase {   // shaders.hxx:422-479; uniforms: vec4 offset, vec4 dim
 	static constexpr int id = 41;
+	static constexpr bool samples = true;
 	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float*) {
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&)[kMaxVaryings][4],
@@ -301,7 +316,7 @@ struct ProgPattern : ProgBase {   // shaders.hxx:422-479; uniforms: vec4 offset,
 		for (int l = 0; l < 4; ++l) {
 			u[l] = f.fragX[l] / dimy + offx;
 			v[l] = f.fragY[l] / dimy + offy; }
-		sample_quad(f, f.st->tu[0], u, v, r, g, b, a, mask); } };
+		sample_quad(f, u, v, r, g, b, a, mask); } };
 
 struct ProgMany : ProgBase {   // shaders.hxx:482-583; uniforms: float magic
 	static constexpr int id = 6;
@@ -380,6 +395,7 @@ struct ProgOBJ2S : ProgBase {   // shaders.hxx:821-978; varyings sp(4) sn(4) kd(
 
 struct ProgEnvmap : ProgBase {   // shaders_envmap.hxx:26-140
 	static constexpr int id = 10;
+	static constexpr bool samples = true;
 	static constexpr int NV = 2;
 	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float* vary,
 	                                   const uint32_t* rsqrtLut) {
@@ -404,7 +420,7 @@ struct ProgEnvmap : ProgBase {   // shaders_envmap.hxx:26-140
 		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
 	__device__ static void ShadeFragment(const FragIn& f, const float (&at)[kMaxVaryings][4],
 	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t& mask) {
-		sample_quad(f, f.st->tu[0], at[0], at[1], r, g, b, a, mask);
+		sample_quad(f, at[0], at[1], r, g, b, a, mask);
 #pragma unroll
 		for (int l = 0; l < 4; ++l) { a[l] = 0.5f; } } };
 

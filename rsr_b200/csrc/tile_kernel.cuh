@@ -63,6 +63,9 @@ struct TileShared {
 	float iw[3][kBatch];
 	uint32_t vref[3][kBatch];            // float4 index of the vertex' varyings; bit 31 = clip buffer
 	uint16_t state[kBatch];              // DevState index of the triangle's draw
+	uint4 tex0[kBatch];                  // texture unit 0 of the triangle's draw: texels pointer, texel count, kind | power << 8 (TexDesc)
+	uint32_t key[kBatch];                // DevDraw::batchKey of the triangle's draw (program | pipeline flags << 8)
+	uint32_t runStartBits[kBatch / 32], tinyBits[kBatch / 32];   // per batch: entries that start a run of equal keys; tiny triangles
 	// per-warp scratch: the queued rasteriser's (triangle, quad) work items awaiting shading (160 x uint16), or the direct
 	// rasteriser's texel staging area (sample_quad, programs.cuh)
 	float4 warpScratch[kTileThreads / 32][kStageTexels];
@@ -225,6 +228,13 @@ __device__ __forceinline__ void setup_triangle(TileShared& sh, int slot, uint32_
 		            cvtt(v0.x * 16.0f), cvtt(v1.x * 16.0f), cvtt(v2.x * 16.0f),
 		            cvtt(v0.y * 16.0f), cvtt(v1.y * 16.0f), cvtt(v2.y * 16.0f), ox, oy, rl, rt, rr, rb); } }
 
+// stages texture unit 0 of the slot's draw (TexDesc) next to the triangle record
+__device__ __forceinline__ void setup_texture(TileShared& sh, int slot, const TileArgs& A, uint32_t state) {
+	const TexUnit& tu = A.states[state].tu[0];
+	const uintptr_t p = reinterpret_cast<uintptr_t>(tu.texels);
+	sh.tex0[slot] = make_uint4(static_cast<uint32_t>(p), static_cast<uint32_t>(p >> 32), tu.texelCount,
+	                           static_cast<uint32_t>(tu.kind & 0xff) | (static_cast<uint32_t>(tu.power) << 8)); }
+
 __device__ __forceinline__ bool depth_pass(int func, float frag, float dest) {
 	return func == 0 ? (frag < dest) : (func == 1 ? (frag <= dest) : (frag == dest)); }
 
@@ -287,6 +297,10 @@ __device__ __forceinline__ unsigned render_quad(TileShared& sh, const int t, con
 	// perspective-correct barycentrics
 	FragIn f;
 	f.st = &s;
+	if constexpr (P::samples) {
+		const uint4 td = sh.tex0[i];
+		f.tex0.texels = reinterpret_cast<const float4*>(static_cast<uintptr_t>(td.x) | (static_cast<uintptr_t>(td.y) << 32));
+		f.tex0.texelCount = td.z; f.tex0.kind = static_cast<int>(td.w & 0xffu); f.tex0.power = static_cast<int>(td.w >> 8); }
 	f.rcpLut = A.luts->rcp;
 	f.rsqrtLut = A.luts->rsqrt;
 	f.stage = (COOP && __popc(activeLanes) >= RSR_STAGE_MIN_LANES) ? sh.warpScratch[threadIdx.x >> 5] : nullptr;
@@ -585,6 +599,8 @@ __host__ __device__ constexpr uint32_t prog_bit(int id) {
 	       id == ProgPattern::id ? 16u : id == ProgMany::id ? 32u : id == ProgOBJ1::id ? 64u : id == ProgOBJ2::id ? 128u :
 	       id == ProgOBJ2S::id ? 256u : id == ProgEnvmap::id ? 512u : id == ProgWireframe::id ? 1024u : 0u; }
 constexpr uint32_t kAllProgs = 0x7ffu;
+// programs whose fragment stage samples texture unit 0 (P::samples)
+constexpr uint32_t kSamplingProgs = prog_bit(ProgAmy::id) | prog_bit(ProgAlphaTexture::id) | prog_bit(ProgText::id) | prog_bit(ProgPattern::id) | prog_bit(ProgEnvmap::id);
 
 template <uint32_t PROGS, class P>
 __device__ __forceinline__ bool draw_batch_if(unsigned& frags, TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy, bool queued) {
@@ -1143,6 +1159,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 			if (mine) {
 				const int slot = wbase + nrec + __popc(hitMask & ltMask);
 				sh.state[slot] = static_cast<uint16_t>(myRec.q4.y);
+				if constexpr ((PROGS & kSamplingProgs) != 0u) { setup_texture(sh, slot, A, myRec.q4.y & 0xffffu); }
 				setup_triangle(sh, slot, myId, myRec, A, ox, oy, rl, rt, rr, rb); }
 			nrec += nhit;
 			pos += take; }
@@ -1168,35 +1185,60 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 			myRec = load_entry(A, myId); }
 		__syncthreads();   // previous batch fully rasterised: its records, sh.headDraw / headKey / firstBad may be overwritten
 		PHASE(4);
-		if (t == 0) { sh.headDraw = avail ? static_cast<int>(myRec.q3.w) : A.fp.ndraws; sh.headKey = myRec.q4.x; sh.firstBad = avail; }
+		if (t == 0) { sh.headDraw = avail ? static_cast<int>(myRec.q3.w) : A.fp.ndraws; sh.firstBad = avail; }
 		__syncthreads();
 		const int di = sh.headDraw;   // draw owning the next list entry (ndraws = none left)
-		const uint32_t key0 = sh.headKey;
 		PHASE(5);
 		exec_cmds(sh, A, ci, di, t, px, py, onScreen);
 		if (di >= A.fp.ndraws) { break; }
 		PHASE(6);
 
+		// The batch ends at the next clear / store command (or after 256 entries).  Inside it entries of different programs /
+		// pipeline states form RUNS (DevDraw::batchKey); all of the batch's triangles are set up in one go -- setup does not
+		// depend on the program -- and every warp then walks the runs on its own: no CTA barrier between the runs of a batch.
 		const int bound = (ci < A.fp.ncmds) ? cmd_before_draw(A, ci) : 0x7fffffff;   // draws >= bound come after cmds[ci]
-		if (t < avail && (static_cast<int>(myRec.q3.w) >= bound || myRec.q4.x != key0)) { atomicMin(&sh.firstBad, t); }
+		if (t < avail && static_cast<int>(myRec.q3.w) >= bound) { atomicMin(&sh.firstBad, t); }
+		if (t < avail) { sh.key[t] = myRec.q4.x; }
 		__syncthreads();
 		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
 		// start the trip for the records of the batch after this one while this one is rasterised
 		if (chunkPos + nb + t < chunkN) { prefetch_entry(A, sh.sorted[chunkPos + nb + t]); }
-		bool tiny = false;
+		bool tiny = false, runStart = false;
 		if (t < nb) {
 			sh.state[t] = static_cast<uint16_t>(myRec.q4.y);
+			if constexpr ((PROGS & kSamplingProgs) != 0u) { setup_texture(sh, t, A, myRec.q4.y & 0xffffu); }
 			setup_triangle(sh, t, myId, myRec, A, ox, oy, rl, rt, rr, rb);
 			const uint32_t bb = sh.bbox[t];
-			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6; }
-		// (this barrier also publishes the setup records)
-		const int ntiny = __syncthreads_count(tiny);
+			tiny = bb != 0 && (((bb >> 12) & 63) - (bb & 63)) <= 6 && (((bb >> 18) & 63) - ((bb >> 6) & 63)) <= 6;
+			runStart = (t == 0) || (sh.key[t - 1] != myRec.q4.x); }
+		const unsigned startBits = __ballot_sync(0xffffffffu, runStart), tinyBits = __ballot_sync(0xffffffffu, tiny);
+		if (lane == 0) { sh.runStartBits[warp] = startBits; sh.tinyBits[warp] = tinyBits; }
+		__syncthreads();   // (publishes the setup records and the run masks)
 		PHASE(7);
 #ifndef RSR_QUEUE_MIN_NB
 #define RSR_QUEUE_MIN_NB 96
 #endif
-		const bool queued = nb >= RSR_QUEUE_MIN_NB && ntiny * 2 > nb;
-		frags += draw_batch_any<PROGS>(sh, A, key0, 0, nb, ox, oy, queued);
+		for (int r0 = 0; r0 < nb; ) {
+			// the run [r0, r1): r1 = next set bit of the start mask after r0
+			int r1 = nb;
+			if (r0 + 1 < nb) {
+				const int wEnd = (nb + 31) >> 5;   // (bits at or beyond nb are never set)
+				int w = (r0 + 1) >> 5;
+				unsigned m = sh.runStartBits[w] & (0xffffffffu << ((r0 + 1) & 31));
+				while (m == 0u && ++w < wEnd) { m = sh.runStartBits[w]; }
+				if (m != 0u) { r1 = w * 32 + __ffs(m) - 1; } }
+			const int len = r1 - r0;
+			bool queued = false;
+			if (len >= RSR_QUEUE_MIN_NB) {
+				int ntiny = 0;
+				for (int w = r0 >> 5; w <= (r1 - 1) >> 5; ++w) {
+					unsigned m = sh.tinyBits[w];
+					if (w == (r0 >> 5)) { m &= 0xffffffffu << (r0 & 31); }
+					if (w == ((r1 - 1) >> 5) && ((r1 & 31) != 0)) { m &= (1u << (r1 & 31)) - 1u; }
+					ntiny += __popc(m); }
+				queued = ntiny * 2 > len; }
+			frags += draw_batch_any<PROGS>(sh, A, sh.key[r0], r0, len, ox, oy, queued);
+			r0 = r1; }
 		PHASE(8);
 		chunkPos += max(nb, 1); }
 	PHASE(9);

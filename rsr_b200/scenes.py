@@ -7,6 +7,8 @@ generation is input preparation, not part of the hot path; everything is seeded.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import (GL_BACK, GL_BLEND, GL_COLOR_BUFFER_BIT, GL_CULL_FACE, GL_DEPTH_BUFFER_BIT, GL_FRONT,
@@ -314,9 +316,49 @@ class CubesScene:
         finish(gl, out, True, depth)
 
 
+def colortest_fixture():
+    """the reference's data/mesh/colortest.obj as its own loader turns it into vertex arrays (LoadOBJ + MakeArray "PND"),
+    plus the camera of data/scene/colortest.lua -- tests/golden/colortest_c1.npz, written by tests/golden/make_bundled.py
+    from the compiled reference (the GPU box has no reference tree)"""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "colortest_c1.npz")
+    return np.load(path)
+
+
+class ColortestScene:
+    """BASELINE.json configs[0] / SURVEY 8(d) C1: data/scene/colortest.lua -- one lit mesh (data/mesh/colortest.obj,
+    168 faces), program OBJ2 (no lights in the scene: node/mesh.cxx:97-99), Perspective camera at (88, 80, 93),
+    background sRGB(128,128,128), Default post program, sRGB store.  The GL calls are the ones the viewer's nodes make:
+    node/gpu.cxx:126-137 (reset, clear), node/mesh.cxx:101-108 (matrices, buffers 0 / 3 / 6, DrawElements),
+    node/truecolor.cxx:93-104 (post program, StoreColor)."""
+
+    def __init__(self):
+        f = colortest_fixture()
+        self.pos, self.nrm, self.kd = (soa(f[k]) for k in ("pos", "nrm", "kd"))
+        self.idx = f["idx"].astype(np.uint16)
+        self.view, self.proj, self.clear = f["view"], f["proj"], tuple(float(v) for v in f["clear"])
+        self.triangles = len(self.idx) // 3
+        self.draws = 1
+
+    def projection(self):
+        return self.proj
+
+    def record(self, gl, size, out, depth=None, t=0.0, tile_blocks=(8, 8), proj=None, static=False, gamma=True):
+        up = {"upload": 1} if (static and hasattr(gl, "stats")) else {}
+        begin(gl, size, clear=self.clear, tile_blocks=tile_blocks)
+        gl.UseProgram(PROGRAM_OBJ2)
+        gl.ViewMatrix(self.view)          # vmat * mmat, mmat = identity (node/gllayer.cxx:136)
+        gl.ProjectionMatrix(self.proj if proj is None else proj)
+        gl.UseBuffer(0, self.pos, **up)
+        gl.UseBuffer(3, self.nrm, **up)
+        gl.UseBuffer(6, self.kd, **up)
+        gl.DrawElements(len(self.idx), self.idx, 0, **up)
+        finish(gl, out, gamma, depth)
+
+
 class BundledLikeScene:
-    """C2: the shape of the reference's bundled scenes at once, all synthetic and seeded --
-    a lit OBJ2 mesh (data/scene/colortest.lua: 168-face mesh, program OBJ2), a 24x24 field of
+    """C2: the shape of the reference's bundled scenes at once --
+    the lit OBJ2 mesh of data/scene/colortest.lua (the real data/mesh/colortest.obj, 168 faces, as the reference's
+    loader produces it: tests/golden/colortest_c1.npz), drawn twice; a seeded 24x24 field of
     bilinear-textured Amy quads with two 512^2 mip-mapped textures, one draw per quad
     (data/scene/tucker-and-dino.lua), and 3 x 3000 instanced cubes, program Many
     (data/scene/instanced-cubes.lua; matrices from a fixed seed instead of std::random_device,
@@ -324,11 +366,13 @@ class BundledLikeScene:
 
     def __init__(self, seed=1, cubes=3000, groups=3, field=24):
         rng = np.random.default_rng(seed)
-        # lit mesh: icosphere(divs=1) = 80 faces x 2 + a cube = 172 faces
-        p, n, f = icosphere(1, 1.0)
-        self.m_pos, self.m_nrm = soa(p), soa(n)
-        self.m_kd = soa((rng.random((3, p.shape[1])) * 0.09).astype(np.float32))
-        self.m_idx = f.astype(np.uint16).ravel()
+        # lit mesh: data/mesh/colortest.obj (positions, normals, diffuse colours, indices from the reference's loader)
+        fx = colortest_fixture()
+        p = fx["pos"]
+        self.m_pos, self.m_nrm, self.m_kd = soa(fx["pos"]), soa(fx["nrm"]), soa(fx["kd"])
+        self.m_idx = fx["idx"].astype(np.uint16)
+        lo, hi = p[:, :-4].min(axis=1), p[:, :-4].max(axis=1)   # (the last four vertices are MakeArray's padding)
+        self.m_model = scale(3.2 / float((hi - lo).max())) @ translate(*(-(lo + hi) / 2))   # into a 3.2-unit box around the origin
         # textured quads
         q = np.array([[0, 1, 1, 0], [0, 0, 1, 1], [0, 0, 0, 0]], np.float32)
         self.q_pos = soa(q)
@@ -420,7 +464,7 @@ class BundledLikeScene:
         gl.UseBuffer(9, None)
         gl.UseBuffer(10, None)
         for k in range(2):
-            gl.ViewMatrix(translate(-3.0 + 6.0 * k, 1.5 * np.sin(t + k), -9.0) @ rotate(0.7 * t + k, 0.3, 1.0, 0.2) @ scale(1.6))
+            gl.ViewMatrix(translate(-3.0 + 6.0 * k, 1.5 * np.sin(t + k), -9.0) @ rotate(0.7 * t + k, 0.3, 1.0, 0.2) @ self.m_model)
             gl.DrawElements(len(self.m_idx), self.m_idx, 0, **up)
 
         # textured quad field, orthographic-like placement in front of the camera

@@ -35,6 +35,35 @@ def test_cuda_reproduces_golden_frames(name):
     assert np.array_equal(out, g["frame"]), f"{np.count_nonzero(out != g['frame'])} pixels differ from the golden frame"
 
 
+def test_cuda_reproduces_the_bundled_colortest_scene():
+    """C1 parity gate (BASELINE.json configs[0]): data/scene/colortest.lua at 640x360 -- the reference's
+    mesh, camera and frame from tests/golden/colortest_c1.npz"""
+    g = np.load(os.path.join(GOLDEN, "colortest_c1.npz"))
+    size = tuple(int(v) for v in g["size"])
+    gpu = R.GPU(0)
+    try:
+        gpu.set_host_luts(g["rcp"], g["rsqrt"])
+        out = np.zeros((size[1], size[0]), np.uint32)
+        scenes.ColortestScene().record(gpu, size, out)
+        gpu.Run()
+    finally:
+        gpu.close()
+    assert np.array_equal(out, g["frame"]), f"{np.count_nonzero(out != g['frame'])} pixels differ from the reference's frame"
+
+
+@pytest.mark.parametrize("size", [(640, 360), (1920, 1080)])
+def test_bundled_colortest_scene_against_the_live_reference(size, ref_gpu, cuda_gpu):
+    """configs[0] and configs[1]: the same bundled scene at 640x360 and 1920x1080 through both renderers on this box"""
+    sc = scenes.ColortestScene()
+    a, b = np.zeros((size[1], size[0]), np.uint32), np.zeros((size[1], size[0]), np.uint32)
+    sc.record(ref_gpu, size, a)
+    ref_gpu.Run()
+    sc.record(cuda_gpu, size, b)
+    cuda_gpu.Run()
+    assert np.count_nonzero(a != a[0, 0]) > size[0] * size[1] // 5
+    assert np.array_equal(a, b), f"{np.count_nonzero(a != b)} pixels differ"
+
+
 def test_host_lut_harvest_equals_oracle_harvest(cuda_gpu):
     rcp, rsq = cuda_gpu.get_host_luts()
     want = restate.harvest_luts()

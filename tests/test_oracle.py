@@ -63,6 +63,35 @@ def test_restatement_reproduces_golden_frames(name):
     assert np.array_equal(out, g["frame"]), f"{np.count_nonzero(out != g['frame'])} pixels differ from the reference's frame"
 
 
+def test_restatement_reproduces_the_bundled_colortest_scene():
+    """SURVEY 8(d) C1 / BASELINE.json configs[0]: data/scene/colortest.lua (the reference's own OBJ loader, camera
+    and renderer, tests/golden/make_bundled.py) at 640x360 -- the C restatement reproduces the committed frame"""
+    from rsr_b200 import scenes
+    g = np.load(os.path.join(GOLDEN, "colortest_c1.npz"))
+    size = tuple(int(v) for v in g["size"])
+    assert size == (640, 360) and g["idx"].size == 168 * 3
+    rst = restate.RestateGPU(luts=(g["rcp"], g["rsqrt"]))
+    out = np.zeros((size[1], size[0]), np.uint32)
+    scenes.ColortestScene().record(rst, size, out)
+    rst.Run()
+    assert np.count_nonzero(g["frame"] != g["frame"][0, 0]) > 50000
+    assert np.array_equal(out, g["frame"]), f"{np.count_nonzero(out != g['frame'])} pixels differ from the reference's frame"
+
+
+def test_bundled_colortest_fixture_is_what_the_reference_loads(refgl):
+    """(only where the reference tree is present) the committed vertex arrays / camera equal what the reference's
+    LoadOBJ + MakeArray and LookAt / Perspective2 produce from data/mesh/colortest.obj today"""
+    ref = os.environ.get("RSR_REFERENCE", "/root/reference")
+    obj = os.path.join(ref, "data", "mesh", "colortest.obj")
+    if not os.path.exists(obj):
+        pytest.skip("no reference tree here")
+    g = np.load(os.path.join(GOLDEN, "colortest_c1.npz"))
+    (pos, nrm, kd), idx = refgl.load_obj_arrays(obj, "PND")
+    assert np.array_equal(pos, g["pos"]) and np.array_equal(nrm, g["nrm"]) and np.array_equal(kd, g["kd"]) and np.array_equal(idx, g["idx"])
+    view, proj = refgl.perspective_camera((88.0, 80.0, 93.0), 3.72, -0.35, 45.0, 640 / 360)
+    assert np.array_equal(view, g["view"]) and np.array_equal(proj, g["proj"])
+
+
 def test_lut_model_matches_golden_tables_on_same_cpu_family():
     """harvest is deterministic; (on another CPU family the tables may legitimately differ)"""
     a = restate.harvest_luts()

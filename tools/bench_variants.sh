@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
 # Runs ON the GPU box: bench each tuning variant (rsr_b200/variants/*.so) on the given workloads.
+shopt -s nullglob
 for lib in default rsr_b200/variants/*.so; do
   for w in "$@"; do
     if [ "$lib" = default ]; then unset RSRCU_LIB; else export RSRCU_LIB=$PWD/$lib; fi

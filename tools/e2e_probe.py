@@ -7,7 +7,8 @@ import torch
 import bench, rsr_b200
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
-scene, size, workload = bench.make_scene(name)
+wl = bench.Workload(name)
+scene, size, workload = wl.scene, wl.sub_size, wl.name
 W, H = size
 gpu = rsr_b200.GPU(0)
 host_out = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(3)]

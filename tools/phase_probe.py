@@ -14,9 +14,10 @@ import bench  # noqa: E402
 import rsr_b200  # noqa: E402
 
 NAMES = ["prologue(pre-wait)", "tile offsets+large scan", "load_chunk", "entry fetch + warp wait", "head publish", "clear/store cmds",
-         "batch cut", "setup", "draw_batch (warp 0)", "loop end", "epilogue"]
+         "batch cut + setup", "draw_batch (warp 0)", "loop end", "epilogue (stores of the last commands incl.)", "-"]
 for name in sys.argv[1:] or ["c2"]:
-    scene, size, workload = bench.make_scene(name)
+    wl = bench.Workload(name)
+    scene, size, workload = wl.scene, wl.sub_size, wl.name
     gpu = rsr_b200.GPU(0)
     scene.record(gpu, size, None, t=0.0, static=True)
     rec = gpu.Finish()
