@@ -124,11 +124,11 @@ struct Counters {
 // spans many small draws (hundreds of two-triangle draws) stages their job bases in shared memory
 // with one coalesced trip and searches there -- a per-thread binary search over global memory is a
 // chain of up to eight dependent misses.  Every thread of the block must call it.
-__device__ __forceinline__ int find_draw(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, uint32_t job,
+__device__ __forceinline__ int find_draw(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, uint32_t vblock, uint32_t job,
                                          bool vertexJobs) {
 	__shared__ uint32_t sBase[260];
-	const int first = static_cast<int>(__ldg(blockDraw + blockIdx.x));
-	const int last = static_cast<int>(__ldg(blockDraw + blockIdx.x + 1));
+	const int first = static_cast<int>(__ldg(blockDraw + vblock));
+	const int last = static_cast<int>(__ldg(blockDraw + vblock + 1));
 	if (last <= first) { return first; }
 	const int n = min(last - first + 1, 258);   // (every draw has at least one job: a block of 256 jobs spans <= 257 draws)
 	for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -200,12 +200,17 @@ vertex_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ bl
               uint4* __restrict__ zero, uint32_t nzero16) {
 	pdl_launch_dependents();
 	pdl_wait();
-	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
 	// a replayed (retained) frame has nothing to upload: its first kernel is this one, and it zeroes the frame's control
 	// block (counters, cell counts and cursors) instead of a separate K0 launch
-	for (uint32_t i = job; i < nzero16; i += gridDim.x * blockDim.x) { zero[i] = make_uint4(0u, 0u, 0u, 0u); }
-	const int di = find_draw(draws, blockDraw, min(job, fp.totalVJobs - 1u), true);
-	if (job >= fp.totalVJobs) { return; }
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero16; i += gridDim.x * blockDim.x) { zero[i] = make_uint4(0u, 0u, 0u, 0u); }
+	// (the grid may be smaller than the number of 256-job blocks: a frame whose front end runs under the previous
+	// frame's tile kernel is launched on a capped grid so that it shares the SMs instead of displacing the tile CTAs)
+	const uint32_t nblocks = (fp.totalVJobs + 255u) >> 8;
+	for (uint32_t vblock = blockIdx.x; vblock < nblocks; vblock += gridDim.x) {
+	if (vblock != blockIdx.x) { __syncthreads(); }   // find_draw's shared table
+	const uint32_t job = vblock * blockDim.x + threadIdx.x;
+	const int di = find_draw(draws, blockDraw, vblock, min(job, fp.totalVJobs - 1u), true);
+	if (job >= fp.totalVJobs) { continue; }
 	const DevDraw& d = draws[di];
 	const DevState& s = states[d.state];
 	const uint32_t local = job - d.vjobBase;
@@ -252,7 +257,7 @@ vertex_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ bl
 	const int nf4 = d.strideF4 - 2;
 	for (int k = 0; k < nf4; ++k) {
 		rec[2 + k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]); }
-	vflags[d.flagBase + local] = static_cast<uint8_t>(flags); }
+	vflags[d.flagBase + local] = static_cast<uint8_t>(flags); } }
 
 // ---------------------------------------------------------------------------------------------
 // K2: triangle setup (classify, cull, tile bbox) + clipper
@@ -637,13 +642,16 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 #ifdef RSR_PHASE_PROF
 	if (threadIdx.x == 0) { atomicMin(&g_k2Times[0], gtimer()); if (blockIdx.x == gridDim.x - 1) { g_k2Times[4] = gtimer(); } }
 #endif
-	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
-	uint2 myInfo = make_uint2(kReject, 0u);
 #ifdef RSR_PHASE_PROF
 	unsigned long long k2Last = 0;
 #endif
+	const uint32_t nblocks = (fp.totalPJobs + 255u) >> 8;   // (capped grids: see vertex_kernel)
+	for (uint32_t vblock = blockIdx.x; vblock < nblocks; vblock += gridDim.x) {
+	if (vblock != blockIdx.x) { __syncthreads(); }   // find_draw's shared table
+	const uint32_t job = vblock * blockDim.x + threadIdx.x;
+	uint2 myInfo = make_uint2(kReject, 0u);
 	K2B(0);
-	const int di = find_draw(draws, blockDraw, min(job, fp.totalPJobs - 1u), false);
+	const int di = find_draw(draws, blockDraw, vblock, min(job, fp.totalPJobs - 1u), false);
 	bool needClip = false;
 	const float4* clipR0 = nullptr; const float4* clipR1 = nullptr; const float4* clipR2 = nullptr;
 	if (job < fp.totalPJobs) {
@@ -732,7 +740,7 @@ setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blo
 				                         base + __popc(m & ((1u << lane) - 1u)));
 				triInfo[job] = myInfo; } } }
 	bin_triangle<false>(job, myInfo, fp, clipRecs, B, ctr);
-	K2B(3);
+	K2B(3); }
 #ifdef RSR_PHASE_PROF
 	__threadfence();
 	K2B(4);
@@ -779,10 +787,12 @@ fill_kernel(FrameParams fp, const uint2* __restrict__ triInfo, const ClipRec* __
             BinArgs B, Counters* __restrict__ ctr) {
 	pdl_launch_dependents();
 	pdl_wait();
-	const uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
-	uint2 info = make_uint2(kReject, 0u);
-	if (job < fp.totalPJobs) { info = triInfo[job]; }
-	bin_triangle<true>(job, info, fp, clipRecs, B, ctr); }
+	const uint32_t nblocks = (fp.totalPJobs + 255u) >> 8;   // (capped grids: see vertex_kernel)
+	for (uint32_t vblock = blockIdx.x; vblock < nblocks; vblock += gridDim.x) {
+		const uint32_t job = vblock * blockDim.x + threadIdx.x;
+		uint2 info = make_uint2(kReject, 0u);
+		if (job < fp.totalPJobs) { info = triInfo[job]; }
+		bin_triangle<true>(job, info, fp, clipRecs, B, ctr); } }
 
 // ---------------------------------------------------------------------------------------------
 // Split-frame presentation: completion counters instead of a host-side barrier.  Behind every frame's tile kernel

@@ -513,6 +513,10 @@ const TileVariant& tileVariantFor(uint32_t progMask) {
 	for (const TileVariant& v : kTileVariants) { if ((progMask & ~v.progs) == 0u) { return v; } }
 	return kTileVariants[n - 1]; }
 
+// (off for the front-end kernels of a frame in overlap mode: a dependent kernel that is resident early only to sit in
+// griddepcontrol.wait holds registers and thread slots the concurrent tile kernel of the previous frame could use)
+bool g_pdl = true;
+
 template <class... KArgs, class... Args>
 cudaError_t launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
 	cudaLaunchConfig_t cfg{};
@@ -524,7 +528,7 @@ cudaError_t launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, s
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
-	cfg.numAttrs = 1;
+	cfg.numAttrs = g_pdl ? 1 : 0;
 	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); }
 
 int flushDeferredCopies(rsrcu_ctx* c) {
@@ -598,6 +602,12 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	bin.large = static_cast<LargeItem*>(w.largeItems.ptr);
 
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[3] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
+	static const bool frontPdl = std::getenv("RSRCU_FRONT_PDL") ? std::atoi(std::getenv("RSRCU_FRONT_PDL")) != 0 : false;
+	// overlap mode: the front-end kernels run on at most this many CTAs (grid-stride over their 256-job blocks), about three
+	// per SM, so that they share the SMs with the previous frame's tile kernel instead of displacing its CTAs
+	static const unsigned frontCtas = std::getenv("RSRCU_FRONT_CTAS") ? static_cast<unsigned>(std::atoi(std::getenv("RSRCU_FRONT_CTAS"))) : 444u;
+	const unsigned gridCap = (c->overlap && frontCtas > 0) ? frontCtas : 0xffffffffu;
+	g_pdl = !c->overlap || frontPdl;
 	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
@@ -617,13 +627,13 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	else { c->traceFrameOfSlot[c->outSlot] = -1; }
 
 	if (fp.totalVJobs) {
-		CU(launchPdl(vertex_kernel, (fp.totalVJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
+		CU(launchPdl(vertex_kernel, std::min(gridCap, (fp.totalVJobs + 255) / 256), 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offVBlocks), dStates, fp,
 			static_cast<const ApproxLuts*>(c->devLuts), static_cast<float4*>(w.ptvb.ptr), static_cast<uint8_t*>(w.vflags.ptr),
 			reinterpret_cast<uint4*>(dCtr), zeroInVertexKernel ? static_cast<uint32_t>((ctrlBytes + 15) / 16) : 0u));
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[2], st)); }
 	if (fp.totalPJobs) {
-		CU(launchPdl(setup_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp,
+		CU(launchPdl(setup_kernel, std::min(gridCap, (fp.totalPJobs + 255) / 256), 256u, 0, st, dDraws, reinterpret_cast<const uint32_t*>(ab + offPBlocks), dStates, fp,
 			static_cast<const ApproxLuts*>(c->devLuts), static_cast<const float4*>(w.ptvb.ptr), static_cast<const uint8_t*>(w.vflags.ptr),
 			static_cast<uint2*>(w.triInfo.ptr), static_cast<TriRec*>(w.triRecs.ptr), static_cast<ClipRec*>(w.clipRecs.ptr),
 			bin, static_cast<uint32_t*>(w.tileBase.ptr), static_cast<uint32_t*>(w.tileOrder.ptr), dCtr));
@@ -635,7 +645,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 		++c->launches; }
 	if (c->profiling > 1) { CU(cudaEventRecord(c->evStage[5], st)); }
 	if (fp.totalPJobs) {
-		CU(launchPdl(fill_kernel, (fp.totalPJobs + 255) / 256, 256u, 0, st, fp, static_cast<const uint2*>(w.triInfo.ptr),
+		CU(launchPdl(fill_kernel, std::min(gridCap, (fp.totalPJobs + 255) / 256), 256u, 0, st, fp, static_cast<const uint2*>(w.triInfo.ptr),
 			static_cast<const ClipRec*>(w.clipRecs.ptr), bin, dCtr));
 		++c->launches; }
 	if (traceIdx >= 0 && c->traceStages) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 2], st)); }
@@ -645,6 +655,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	if (traceIdx >= 0 && c->traceStages) { CU(cudaEventRecord(c->traceEv[4 * traceIdx + 3], tileStream)); }
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[6], tileStream)); }
 
+	g_pdl = true;
 	TileArgs ta{};
 	for (int i = 0; i < plan.ncmdInline; ++i) { ta.icmd[i] = plan.icmd[i]; ta.icmdState[i] = plan.icmdState[i]; }
 	ta.fp = fp; ta.cmds = dCmds; ta.draws = dDraws; ta.states = dStates; ta.luts = c->devLuts;
@@ -704,7 +715,8 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	{
 		int lo = 0, hi = 0;
 		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		CU(cudaStreamCreateWithPriority(&c->frontStream, cudaStreamNonBlocking, hi)); }
+		const char* pr = std::getenv("RSRCU_FRONT_PRIO");   // (experiments: 0 = lowest priority for the front-end stream)
+		CU(cudaStreamCreateWithPriority(&c->frontStream, cudaStreamNonBlocking, (pr && std::atoi(pr) == 0) ? lo : hi)); }
 	for (auto& ev : c->evFrontDone) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evTileDone) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
 	for (auto& ev : c->evRendered) { CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }

@@ -1237,6 +1237,9 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 					if (w == ((r1 - 1) >> 5) && ((r1 & 31) != 0)) { m &= (1u << (r1 & 31)) - 1u; }
 					ntiny += __popc(m); }
 				queued = ntiny * 2 > len; }
+#ifdef RSR_FORCE_QUEUED   // (experiment: the queued rasteriser for every run of at least this many entries; c2 120 -> 153-188 us)
+			queued = len >= RSR_FORCE_QUEUED;
+#endif
 			frags += draw_batch_any<PROGS>(sh, A, sh.key[r0], r0, len, ox, oy, queued);
 			r0 = r1; }
 		PHASE(8);
