@@ -4,14 +4,18 @@
     python bench.py --gpus N --steps K --warmup W [--workload c2|c4|c3|c4_4k|c3_4k|c5] [--impl reference]
 
 A step is one frame of the workload.  Default workload = BASELINE.json configs[1]: the bundled-scene-shaped frame
-sequence at 1920x1080 (`rsr_b200.scenes.BundledLikeScene`, synthetic, seeded).  One JSON line is printed by rank 0:
-  value      frames/s with every input resident in HBM (device timed, CUDA events, L2 flushed between iterations),
-             aggregate over ranks (each rank renders its own frames: weak scaling)
+sequence at 1920x1080 (`rsr_b200.scenes.BundledLikeScene`: the reference's colortest mesh + seeded synthetic quads and
+instanced cubes).  One JSON line is printed by rank 0:
+  value      frames/s of the frame SEQUENCE with every input resident in HBM: K distinct frames of a ring whose
+             per-frame data exceeds L2, submitted back to back with frame overlap (device timed, CUDA events around the
+             K frames), aggregate over ranks (each rank renders its own frames: weak scaling)
+  flushed_frame   the same frames one at a time with the L2 flushed before each (cold single-frame latency); the
+             roofline's kernel time and the per-stage times come from this leg
   e2e        frames/s through the public API with HOST buffers: per frame the host rebuilds and uploads the instance
              matrices + state and reads the 1080p frame back (>= 200 frames whatever --steps says)
   parity     frame 0 of the workload rendered by the reference's own CPU rasteriser in the same run and compared
   roofline   SURVEY 8(d) algorithmic bytes / the tile kernel's time, against MEASURED_PEAKS.json
-  sustained  the same step back to back for >= 2 s with its own clock samples
+  sustained  the sequence leg for >= 2 s with its own clock samples
   c4_4k / c3_4k   (1 GPU) the fill / geometry stress configs of BASELINE.json at 3840x2160 = 2x2 sub-frames
   split_frame     (N > 1) the 7680x4320 frame split over the ranks by sub-frame ownership, NVLink peer stores
 `--impl reference` times the reference's own CPU renderer (oracle/_ref) on this box's host cores.
@@ -260,6 +264,72 @@ class ResidentRun:
         for fr in self.retained:
             self.gpu.Release(fr)
         self.gpu.set_overlap(False)
+
+
+class SequenceRun:
+    """the frame-sequence leg: a ring of `ring` DISTINCT frames of the workload's animation (t = i / 60 s), each retained
+    with its own state / draw tables, its own per-frame inputs (instance matrices) and its own output buffer, replayed
+    back to back with frame overlap on (the front end of frame N+1 runs under the tile kernel of frame N -- the
+    counterpart of the reference's doubleBuffer mode, which bins frame N+1 while its workers draw frame N).  The ring's
+    per-frame data (outputs 8.3 MB + inputs each) exceeds the 126 MB L2, so no frame finds its own data cached; the
+    scene-static meshes and textures are shared by the frames, as in any frame sequence."""
+
+    def __init__(self, wl, gpu, torch, local_rank, ring):
+        self.wl, self.gpu, self.torch = wl, gpu, torch
+        self.stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
+        self.retained = []
+        for i in range(ring):
+            wl.record(gpu, wl.subframes[0], None, t=i / 60.0, static=True)
+            gpu.Submit(gpu.Finish())
+            self.retained.append(gpu.Retain())
+        self.pos = 0
+        gpu.set_overlap(True)
+
+    def frames(self, n):
+        for _ in range(n):
+            self.gpu.Replay(self.retained[self.pos % len(self.retained)])
+            self.pos += 1
+
+    def timed(self, n):
+        """device time of n frames submitted back to back (CUDA events on the context's stream)"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+        self.frames(n)
+        with torch.cuda.stream(self.stream):
+            e1.record(self.stream)
+        self.gpu.Sync()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def close(self):
+        self.gpu.Sync()
+        for fr in self.retained:
+            self.gpu.Release(fr)
+        self.gpu.set_overlap(False)
+
+
+def sequence_sustained(seq, seconds, local_rank):
+    """the sequence leg for `seconds` (no host sync except to bound the queue): what a long run clocks at"""
+    torch = seq.torch
+    sampler = ClockSampler(local_rank).start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    t0 = time.perf_counter()
+    with torch.cuda.stream(seq.stream):
+        e0.record(seq.stream)
+    while time.perf_counter() - t0 < seconds:
+        seq.frames(64)
+        n += 64
+        if n % 256 == 0:
+            seq.gpu.Sync()   # bound the queue depth
+    with torch.cuda.stream(seq.stream):
+        e1.record(seq.stream)
+    seq.gpu.Sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"seconds": e0.elapsed_time(e1) / 1e3, "steps": n, "ms_per_step": ms, "frames_per_s": 1e3 / ms, "clocks": sampler.stop()}
 
 
 def measure_resident(run, flush, steps, warmup, barrier, sampler=None):
@@ -677,6 +747,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--e2e-frames", type=int, default=200)
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--ring", type=int, default=24, help="distinct frames in the frame-sequence leg's ring")
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
     ap.add_argument("--balance", default="cost", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
@@ -746,17 +817,41 @@ def main():
         except Exception as exc:  # oracle not shipped: say so, never fake
             parity = {"diff_pixels": None, "max_lsb": None, "against": f"unavailable: {exc}"}
 
-    # ---- device-resident leg ----------------------------------------------------------------------------------
+    # ---- device-resident legs ---------------------------------------------------------------------------------
+    # (a) frame sequence (single-sub-frame workloads): `value`.  (b) one frame at a time, L2 flushed before each, an
+    # event after every kernel: the per-stage times, the tile kernel's launch duration for the roofline, and the
+    # cold single-frame latency (`flushed_frame`); `value` of the workloads rendered as several sub-frames.
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    seq_ms = None
+    sustained = None
+    if wl.single and args.resident == "retained":
+        seq = SequenceRun(wl, gpu, torch, local_rank, args.ring)
+        seq.frames(max(args.warmup, args.ring))   # every frame of the ring once: buffers sized, pipeline primed
+        gpu.Sync()
+        barrier()
+        seq_ms = seq.timed(args.steps)
+        barrier()
+        if args.sustained_seconds > 0 and rank == 0 and world == 1:
+            sustained = sequence_sustained(seq, args.sustained_seconds, local_rank)
+        seq.close()
+        config["cache"] = (f"ring of {args.ring} distinct frames replayed back to back: per-frame outputs + inputs "
+                           f"({args.ring} x {4 * wl.frame[0] * wl.frame[1] / 1e6:.1f} MB of outputs alone) exceed the 126 MB L2; "
+                           "scene-static meshes / textures are shared by the frames as in any frame sequence")
+        config["resident_leg"] = "frame sequence: retained frame tables replayed (rsrcu_replay_frame), frame overlap on"
     run = ResidentRun(wl, gpu, args, torch, local_rank)
-    m = measure_resident(run, flush, args.steps, args.warmup, barrier, ClockSampler(local_rank) if rank == 0 else None)
-    t = torch.tensor([m["dev_ms"]], dtype=torch.float64, device=f"cuda:{local_rank}")
+    m = measure_resident(run, flush, args.steps, args.warmup, barrier, None)
+    if sampler:
+        m["clocks"] = sampler.stop()
+    flushed_ms = m["dev_ms"]
+    t = torch.tensor([seq_ms if seq_ms is not None else flushed_ms, flushed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
+    dev_ms_max, flushed_ms_max = float(t[0].item()), float(t[1].item())
     ms_per_step = dev_ms_max / args.steps
     value = world * args.steps / (dev_ms_max / 1e3)
-    sustained = None
-    if args.sustained_seconds > 0 and rank == 0 and world == 1:
+    flushed_frame = {"ms": flushed_ms_max / args.steps, "frames_per_s": world * args.steps / (flushed_ms_max / 1e3),
+                     "what": "one frame at a time, 256 MiB L2 flush before each, CUDA events around the frame's kernels (cold single-frame latency)"}
+    if sustained is None and args.sustained_seconds > 0 and rank == 0 and world == 1:
         sustained = sustained_leg(run, flush, args.sustained_seconds, local_rank)
     run.close()
     barrier()
@@ -802,7 +897,7 @@ def main():
             "mtris_per_s": wl.scene.triangles * value / 1e6,
             "gpix_per_s": m["fragments"] * value / 1e9,
             "fragments_per_frame": m["fragments"], "bin_entries_per_frame": m["bin_entries"],
-            "clocks": m["clocks"], "parity": parity, "e2e": e2e,
+            "flushed_frame": flushed_frame, "clocks": m["clocks"], "parity": parity, "e2e": e2e,
             "gpu_launches": int(stats["kernel_launches"]) * len(wl.subframes) * args.steps,
             "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu}
     line.update(extra)

@@ -30,12 +30,27 @@ def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
 
 
+STAMP = LIB + ".stamp"
+
+
+def source_hash() -> str:
+    """content hash of everything the library is built from (file times do not survive a copy to another box)"""
+    import hashlib
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    for p in sources() + [os.path.join(HERE, "..", "include", "rsrcu.h")]:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(HERE, "..", "include", "rsrcu.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(p) > t for p in deps)
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return False   # a shipped library without its stamp: take it as it is
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -50,6 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 
