@@ -297,6 +297,7 @@ class SequenceRun:
         with torch.cuda.stream(self.stream):
             e0.record(self.stream)
         self.frames(n)
+        self.gpu.Join()   # (overlap mode: tile kernels alternate between two streams)
         with torch.cuda.stream(self.stream):
             e1.record(self.stream)
         self.gpu.Sync()
@@ -324,6 +325,7 @@ def sequence_sustained(seq, seconds, local_rank):
         n += 64
         if n % 256 == 0:
             seq.gpu.Sync()   # bound the queue depth
+    seq.gpu.Join()
     with torch.cuda.stream(seq.stream):
         e1.record(seq.stream)
     seq.gpu.Sync()
@@ -353,12 +355,14 @@ def measure_resident(run, flush, steps, warmup, barrier, sampler=None):
             ev[i][0].record(stream)
         if nsub == 1:
             run.step()
+            gpu.Join()
             with torch.cuda.stream(stream):
                 ev[i][1].record(stream)
             gpu.Sync()
             tile_ms.append(gpu.stage_ms()["tile"])
         else:
             run.step()
+            gpu.Join()
             with torch.cuda.stream(stream):
                 ev[i][1].record(stream)
             gpu.Sync()
@@ -441,6 +445,7 @@ def sustained_leg(run, flush, seconds, local_rank):
             n += 1
         if n % 64 == 0:
             torch.cuda.synchronize()   # bound the queue depth
+    gpu.Join()
     with torch.cuda.stream(stream):
         e1.record(stream)
     gpu.Sync()
@@ -601,6 +606,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
                 for fr in sets[0]:
                     gpu.Replay(fr)
                 done = torch.cuda.Event()
+                gpu.Join()
                 with torch.cuda.stream(stream):
                     done.record(stream)
                 cur.wait_event(done)                       # NCCL runs on torch's stream, after the render stream
@@ -620,6 +626,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
             if presenter:
                 gpu.WaitCounters(pf.counter_pointer(0), nranks, frames_done)   # the last frame of the batch is complete on every rank
             done = torch.cuda.Event()
+            gpu.Join()
             with torch.cuda.stream(stream):
                 done.record(stream)
             cur.wait_event(done)

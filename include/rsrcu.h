@@ -218,9 +218,13 @@ int rsrcu_release_frame(rsrcu_ctx* ctx, rsrcu_frame* frame);
  * kernels that leave most of the GPU idle) runs on a second, high-priority stream into its own set of intermediate
  * buffers, and only the tile kernel runs on the context's stream: the front end of frame N+1 executes while the tile
  * kernel of frame N is still rasterising -- the counterpart of the reference binning frame N+1 on the main thread
- * while the tile jobs of frame N run (doubleBuffer, rglv_gpu.cxx:16,111-112).  Frames still complete in order on
- * the stream of rsrcu_stream(); work enqueued there by the caller is ordered against the tile kernels only. */
+ * while the tile jobs of frame N run (doubleBuffer, rglv_gpu.cxx:16,111-112).  The tile kernels of consecutive frames
+ * alternate between the context's stream and a second one (the tail of one and the head of the next share the GPU):
+ * call rsrcu_join before enqueueing work of your own on rsrcu_stream() that must come after every submitted frame
+ * (rsrcu_sync, rsrcu_sync_frame and rsrcu_signal_counter order themselves). */
 int rsrcu_set_overlap(rsrcu_ctx* ctx, int enabled);
+/* orders the stream of rsrcu_stream() behind every frame submitted so far (no host wait) */
+int rsrcu_join(rsrcu_ctx* ctx);
 
 /* Frames are pipelined (upload arena double-buffered; store targets, counters and their device->host
  * copies in a ring of three; copies run on a second stream): rsrcu_sync_frame(ctx, lag) waits only

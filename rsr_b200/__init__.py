@@ -129,6 +129,7 @@ def load_library():
         "rsrcu_run_stream": [vp, vp, sz],
         "rsrcu_device_truecolor": [vp, C.POINTER(vp), C.POINTER(ci)],
         "rsrcu_stream": [vp, C.POINTER(vp)],
+        "rsrcu_join": [vp],
         "rsrcu_get_stats": [vp, C.POINTER(RsrStats)],
         "rsrcu_set_profiling": [vp, ci],
         "rsrcu_get_stage_ms": [vp, vp],
@@ -149,7 +150,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_bind_depth_texture", "rsrcu_clear", "rsrcu_draw_elements", "rsrcu_draw_arrays",
     "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_signal_counter", "rsrcu_wait_counters", "rsrcu_retain_frame", "rsrcu_replay_frame", "rsrcu_release_frame", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_sync_frame", "rsrcu_run_stream",
-    "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
+    "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_join", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
 )
 
 
@@ -541,6 +542,10 @@ class GPU:
         p = C.c_void_p()
         self._check(self.L.rsrcu_stream(self.h, C.byref(p)))
         return p.value or 0
+
+    def Join(self):
+        """orders stream() behind every frame submitted so far (overlap mode runs tile kernels on two streams)"""
+        self._check(self.L.rsrcu_join(self.h))
 
     def get_host_luts(self):
         rcp = np.zeros(2048, np.uint32)

@@ -207,6 +207,9 @@ struct rsrcu_ctx {
 	// the frame's intermediate buffers; two sets so that, in overlap mode, the front end (K0-K5) of frame N+1 can fill one
 	// set while the tile kernel of frame N still reads the other
 	struct WorkSet { DevBuf ptvb, vflags, triInfo, triRecs, clipRecs, tileBase, cellRel, tileTotal, tileOrder, lists, largeItems, runScratch; } sets[2];
+	cudaStream_t tileStream2{nullptr};  // overlap mode: the tile kernels of odd frames run here, so that the tail of frame N's tile kernel and the head of frame N+1's share the GPU
+	cudaEvent_t evGate{nullptr};
+	bool tile2Pending{false};           // work on tileStream2 that `stream` has not been ordered behind yet
 	cudaStream_t frontStream{nullptr};   // overlap mode: K0-K5 run here (high priority), the tile kernel on `stream`
 	cudaEvent_t evFrontDone[2]{}, evTileDone[2]{};
 	bool overlap{false};
@@ -531,6 +534,13 @@ cudaError_t launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, s
 	cfg.numAttrs = g_pdl ? 1 : 0;
 	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); }
 
+// orders the context's stream behind the tile kernels that went to the second tile stream (overlap mode)
+int joinTileStreams(rsrcu_ctx* c) {
+	if (c->tile2Pending) {
+		CU(cudaStreamWaitEvent(c->stream, c->evTileDone[1], 0));
+		c->tile2Pending = false; }
+	return RSRCU_OK; }
+
 int flushDeferredCopies(rsrcu_ctx* c) {
 	if (c->deferredSlot < 0) { return RSRCU_OK; }
 	const int slot = c->deferredSlot;
@@ -567,7 +577,9 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	++c->frameNo;
 	rsrcu_ctx::WorkSet& w = c->sets[si];
 	cudaStream_t st = c->overlap ? c->frontStream : c->stream;
-	cudaStream_t tileStream = c->stream;
+	static const bool dualTile = std::getenv("RSRCU_TILE_STREAMS") ? std::atoi(std::getenv("RSRCU_TILE_STREAMS")) == 2 : true;
+	cudaStream_t tileStream = (c->overlap && dualTile && si == 1) ? c->tileStream2 : c->stream;
+	if (tileStream != c->stream) { c->tile2Pending = true; }
 	c->launches = 0;
 
 	// ---- device buffers -------------------------------------------------------------------
@@ -712,6 +724,8 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	c->device = device;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->tileStream2, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->evGate, cudaEventDisableTiming));
 	{
 		int lo = 0, hi = 0;
 		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -760,6 +774,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	flushDeferredCopies(c);
 	cudaStreamSynchronize(c->frontStream);
 	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->tileStream2);
 	cudaStreamSynchronize(c->copyStream);
 	if (c->hostProf && c->hpFrames) {
 		const double n = static_cast<double>(c->hpFrames) * 1e3;
@@ -790,6 +805,7 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 	cudaStreamDestroy(c->copyStream);
 	cudaStreamDestroy(c->frontStream);
 	cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->tileStream2);
 	delete c;
 	return RSRCU_OK; }
 
@@ -799,6 +815,7 @@ int rsrcu_set_host_luts(rsrcu_ctx* c, const uint32_t* rcp2048, const uint32_t* r
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->tileStream2));
 	std::memcpy(c->hostLuts.rcp, rcp2048, sizeof(c->hostLuts.rcp));
 	std::memcpy(c->hostLuts.rsqrt, rsqrt2x1024, sizeof(c->hostLuts.rsqrt));
 	for (int i = 0; i < 2048; ++i) { c->hostLuts.rcp16[i] = static_cast<uint16_t>((c->hostLuts.rcp[i] >> 7) & 0xffffu); }
@@ -816,6 +833,7 @@ int rsrcu_release_static(rsrcu_ctx* c) {
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->tileStream2));
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	c->staticCache.clear();
 	std::fill(c->ptrCache.begin(), c->ptrCache.end(), PtrCacheEntry{nullptr, 0, nullptr, 0.0f, 0.0f, false});
@@ -1251,7 +1269,8 @@ int rsrcu_release_frame(rsrcu_ctx* c, rsrcu_frame* f) {
 	if (c) {
 		cudaSetDevice(c->device);
 		cudaStreamSynchronize(c->frontStream);
-		cudaStreamSynchronize(c->stream); }
+		cudaStreamSynchronize(c->stream);
+		cudaStreamSynchronize(c->tileStream2); }
 	if (c) { for (auto& L : c->launched) { if (L.plan == &f->plan) { L = Launched{}; } } }
 	if (f->devArena) { cudaFree(f->devArena); }
 	for (auto& b : f->stores) { b.release(); }
@@ -1325,6 +1344,7 @@ int rsrcu_sync(rsrcu_ctx* c) {
 			again = again || relaunched; } }
 	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->tileStream2));
 	CU(cudaStreamSynchronize(c->copyStream));
 	if (!c->framePending) { return RSRCU_OK; }
 	c->framePending = false;
@@ -1424,6 +1444,11 @@ int rsrcu_stream(rsrcu_ctx* c, void** stream) {
 	*stream = c->stream;
 	return RSRCU_OK; }
 
+int rsrcu_join(rsrcu_ctx* c) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	CU(cudaSetDevice(c->device));
+	return joinTileStreams(c); }
+
 int rsrcu_get_stats(rsrcu_ctx* c, RsrStats* out) {
 	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	*out = c->stats;
@@ -1450,6 +1475,7 @@ int rsrcu_signal_counter(rsrcu_ctx* c, void* deviceCounter) {
 	if (!c || !deviceCounter) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	if (reinterpret_cast<uintptr_t>(deviceCounter) & 7u) { return fail(RSRCU_ERR_INVALID, "completion counter must be 8-byte aligned"); }
 	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
 	CU(launchPdl(signal_counter_kernel, 1u, 32u, 0, c->stream, static_cast<unsigned long long*>(deviceCounter)));
 	return RSRCU_OK; }
 
@@ -1461,6 +1487,9 @@ int rsrcu_wait_counters(rsrcu_ctx* c, const void* deviceCounters, int count, uin
 		CU(cudaMemset(c->waitTimedOut, 0, sizeof(unsigned int))); }
 	CU(launchPdl(wait_counter_kernel, 1u, 32u, 0, c->stream, static_cast<const unsigned long long*>(deviceCounters), static_cast<unsigned int>(count),
 	             static_cast<unsigned long long>(value), c->waitTimedOut));
+	// the tile kernels of later frames must stay behind this wait on whichever stream they run
+	CU(cudaEventRecord(c->evGate, c->stream));
+	CU(cudaStreamWaitEvent(c->tileStream2, c->evGate, 0));
 	return RSRCU_OK; }
 
 int rsrcu_set_overlap(rsrcu_ctx* c, int enabled) {
@@ -1469,6 +1498,7 @@ int rsrcu_set_overlap(rsrcu_ctx* c, int enabled) {
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->frontStream));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->tileStream2));
 	c->overlap = enabled != 0;
 	return RSRCU_OK; }
 

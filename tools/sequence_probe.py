@@ -32,6 +32,7 @@ for overlap in (False, True):
         e0.record(stream)
     for i in range(frames):
         gpu.Replay(retained[i % ring])
+    gpu.Join()
     with torch.cuda.stream(stream):
         e1.record(stream)
     t1 = time.perf_counter()
