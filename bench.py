@@ -456,45 +456,54 @@ def sustained_leg(run, flush, seconds, local_rank):
             "ms_per_step": ms - flush_ms, "frames_per_s": 1e3 / max(ms - flush_ms, 1e-6), "clocks": clocks}
 
 
-def e2e_leg(wl, gpu, frames, torch, dist, world, local_rank, barrier):
-    """end to end through rsrcu_run_stream + rsrcu_sync_frame with HOST buffers.  Each frame of the sequence is
-    recorded beforehand (that is the callers' job in the reference: node graph -> GL calls); the timed region is what
-    replaces GPU::Run -- decode the stream, upload that frame's host buffers (instance matrices, state), kernels,
-    read the frame back.  Frames are pipelined like the reference's doubleBuffer mode, three in flight: while frame N
-    is read back (copy stream) frames N+1 and N+2 are decoded, uploaded and rendered; every frame is waited for
-    (rsrcu_sync_frame) and lands in one of three rotating pinned host buffers."""
+def e2e_leg(wl, gpu, frames, torch, dist, world, local_rank, barrier, contexts=2):
+    """end to end through the public API with HOST buffers.  Each frame of the sequence is recorded beforehand (that
+    is the callers' job in the reference: node graph -> GL calls); the timed region is what replaces GPU::Run -- decode
+    the recorded stream (rsrcu_run_stream), upload that frame's host buffers (instance matrices, state), kernels, read
+    the frame back into pinned host memory (rsrcu_sync_frame).  Frames are submitted through rsr_b200.SubmitPool:
+    `contexts` rendering contexts on this GPU, one host thread each, frames dealt round robin, three frames in flight per
+    context, frame overlap on -- the reference renders with every host core (its job system); this leg uses `contexts`
+    host threads.  Every frame is waited for and lands in its own slot of a ring of pinned host buffers."""
+    import rsr_b200
     W, H = wl.sub_size
-    gpu.set_overlap(True)            # front end of frame N+1 under the tile kernel of frame N (rsrcu_set_overlap)
-    host_out = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(3)]
+    K = max(1, contexts)
+    pool = rsr_b200.SubmitPool(local_rank, contexts=K, overlap=True)
+    recorder = pool.gpus[0]
+    host_out = [[torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(3)] for _ in range(K)]
+    distinct = 33                       # per context: a 33-frame loop of the sequence (each frame with its own instance matrices)
     recs = []
-    distinct = min(frames + 2, 64)   # a 64-frame loop of the sequence (each with its own instance matrices)
-    for i in range(distinct):
-        wl.record(gpu, wl.subframes[0], host_out[i % 3], t=i / 60.0)
-        recs.append(gpu.Finish())
-    # destinations rotate with period 3, recordings with period 64: index recordings so that frame i writes buffer i % 3
-    order = [recs[(i % (distinct // 3 * 3))] for i in range(frames + 2)]
-    for rec in order[:2]:
-        gpu.Submit(rec)
-    retried0 = gpu.stats()["frames_retried"]
+    for k in range(K):
+        row = []
+        for j in range(distinct):
+            wl.record(recorder, wl.subframes[0], host_out[k][j % 3], t=(j * K + k) / 60.0)
+            row.append(recorder.Finish())
+        recs.append(row)
+    frame = lambda i: recs[i % K][(i // K) % distinct]   # frame i goes to context i % K as its (i // K)-th frame -> buffer (i // K) % 3
+    for i in range(2 * K):              # warm every context (static uploads, buffer growth)
+        pool.submit(frame(i))
+    pool.drain()
+    retried0 = sum(st["frames_retried"] for st in pool.stats())
     barrier()
     t0 = time.perf_counter()
-    for i, rec in enumerate(order[2:]):
-        gpu.Submit(rec, sync=False)      # rsrcu_run_stream
-        if i > 1:
-            gpu.SyncFrame(2)             # frame i-2 is complete in host memory
-    gpu.Sync()
+    base = 2 * K
+    for i in range(frames):
+        ticket = pool.submit(frame(base + i))
+        if i >= 3 * K:
+            pool.wait(ticket - 3 * K)      # bounded queue: at most three frames per context outstanding
+    pool.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    st = gpu.stats()
-    gpu.set_overlap(False)
+    st = pool.stats()[0]
+    retried = sum(s_["frames_retried"] for s_ in pool.stats()) - retried0
+    pool.close()
     return {"value": world * frames / float(t.item()), "unit": "frames/s", "frames": frames,
             "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
-            "frames_retried_for_overflow": st["frames_retried"] - retried0,
-            "timing": "wall clock over `frames` frames of rsrcu_run_stream + rsrcu_sync_frame (stream decode, H2D, kernels, D2H), "
-                      "three frames in flight, frame overlap on, max over ranks"}
+            "frames_retried_for_overflow": retried, "host_threads": K,
+            "timing": "wall clock over `frames` frames of rsrcu_run_stream + rsrcu_sync_frame (stream decode, H2D, kernels, D2H) "
+                      f"through rsr_b200.SubmitPool: {K} contexts / host threads, three frames in flight each, frame overlap on, max over ranks"}
 
 
 def stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier):
@@ -753,6 +762,7 @@ def main():
     ap.add_argument("--no-subrecords", action="store_true", help="skip the c4_4k / c3_4k (1 GPU) and split_frame (N > 1) sub-records")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--e2e-frames", type=int, default=200)
+    ap.add_argument("--e2e-contexts", type=int, default=0, help="submission threads / contexts of the end-to-end leg (0: 2 at one or two GPUs, 1 per rank beyond: the ranks share the host's cores)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--ring", type=int, default=24, help="distinct frames in the frame-sequence leg's ring")
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
@@ -864,7 +874,8 @@ def main():
     barrier()
 
     # ---- end-to-end leg ------------------------------------------------------------------------------------------
-    e2e = e2e_leg(wl, gpu, max(args.e2e_frames, args.steps), torch, dist, world, local_rank, barrier) if wl.single else None
+    e2e_ctx = args.e2e_contexts or (2 if world <= 2 else 1)   # (measured: 1 / 2 / 3 / 4 contexts = 4.0 / 5.5 / 5.0 / 4.9 k frames/s on a fast host, 2.6 / 4.7 / 5.0 k on a slow one; 5.5 k is the PCIe read-back limit)
+    e2e = e2e_leg(wl, gpu, max(args.e2e_frames, args.steps), torch, dist, world, local_rank, barrier, e2e_ctx) if wl.single else None
     barrier()
 
     # ---- sub-records -----------------------------------------------------------------------------------------------

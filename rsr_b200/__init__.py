@@ -558,3 +558,97 @@ class GPU:
         rsq = np.ascontiguousarray(rsq, dtype=np.uint32)
         assert rcp.size == 2048 and rsq.size == 2048
         self._check(self.L.rsrcu_set_host_luts(self.h, _ptr(rcp), _ptr(rsq)))
+
+
+class SubmitPool:
+    """Frame submission on several host threads: `contexts` rendering contexts on one GPU, each fed by its own thread,
+    frames dealt round robin.  Recording a frame (the caller's job, as in the reference: node graph -> GL calls) stays on
+    the caller's thread; decoding the recorded stream, building the frame's tables, launching its kernels and waiting
+    for its read-back run on the pool's threads -- what the reference spreads over its job system's worker threads
+    (src/rcl/rclmt/rclmt_jobsys.cxx), one frame per worker here instead of one tile per job.  Frames of one context
+    complete in order; `wait(ticket)` returns when that frame has landed in its store destinations.  Every context
+    keeps up to three frames in flight (upload / kernels / read-back) and uploads its own copy of static buffers."""
+
+    def __init__(self, device: int = 0, contexts: int = 3, overlap: bool = True):
+        import queue
+        import threading
+        self.gpus = [GPU(device) for _ in range(max(1, contexts))]
+        for g in self.gpus:
+            g.set_overlap(overlap)
+        self._q = [queue.Queue() for _ in self.gpus]
+        self._done = [0] * len(self.gpus)          # frames completed per context
+        self._cv = threading.Condition()
+        self._submitted = 0
+        self._error = None
+        self._threads = [threading.Thread(target=self._run, args=(k,), daemon=True) for k in range(len(self.gpus))]
+        for t in self._threads:
+            t.start()
+
+    def _run(self, k):
+        gpu, q = self.gpus[k], self._q[k]
+        inflight = 0
+        while True:
+            rec = q.get()
+            try:
+                if rec is None or rec == "drain":
+                    gpu.Sync()
+                    with self._cv:
+                        self._done[k] += inflight
+                        inflight = 0
+                        if rec == "drain":
+                            self._drained[k] = True
+                        self._cv.notify_all()
+                    if rec is None:
+                        return
+                    continue
+                gpu.Submit(rec, sync=False)
+                inflight += 1
+                if inflight > 2:
+                    gpu.SyncFrame(2)
+                    inflight -= 1
+                    with self._cv:
+                        self._done[k] += 1
+                        self._cv.notify_all()
+            except Exception as exc:  # surfaces in wait() / drain()
+                with self._cv:
+                    self._error = exc
+                    self._cv.notify_all()
+                return
+
+    def submit(self, rec: RecordedFrame) -> int:
+        """hands a recorded frame to the next context; returns its ticket"""
+        t = self._submitted
+        self._q[t % len(self.gpus)].put(rec)
+        self._submitted += 1
+        return t
+
+    def wait(self, ticket: int):
+        """blocks until frame `ticket` is complete in host memory (frames of its context before it included)"""
+        k, n = ticket % len(self.gpus), ticket // len(self.gpus) + 1
+        with self._cv:
+            while self._done[k] < n and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+
+    def drain(self):
+        """waits for every submitted frame"""
+        self._drained = [False] * len(self.gpus)
+        for q in self._q:
+            q.put("drain")
+        with self._cv:
+            while not all(self._drained) and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+
+    def stats(self):
+        return [g.stats() for g in self.gpus]
+
+    def close(self):
+        for q in self._q:
+            q.put(None)
+        for t in self._threads:
+            t.join()
+        for g in self.gpus:
+            g.close()

@@ -218,6 +218,39 @@ def test_frame_overlap_mode_front_end_under_previous_tile_kernel():
         g.close()
 
 
+def test_submit_pool_three_contexts_render_the_sequence_bit_identical():
+    """rsr_b200.SubmitPool: frames dealt round robin to three contexts / host threads land bit-identical to the same
+    frames rendered one at a time on one context"""
+    heavy = scenes.BundledLikeScene(cubes=300)
+    light = scenes.WavyGridScene(n=12)
+    plan = [(heavy, (1920, 1080)), (light, (640, 360)), (heavy, (640, 360)), (light, (1920, 1080))] * 4
+    g = R.GPU(0)
+    try:
+        want = []
+        for i, (sc, size) in enumerate(plan):
+            out = np.zeros((size[1], size[0]), np.uint32)
+            sc.record(g, size, out, t=0.25 * i)
+            g.Run()
+            want.append(out)
+    finally:
+        g.close()
+    pool = R.SubmitPool(0, contexts=3)
+    try:
+        bufs = [np.zeros_like(w) for w in want]
+        tickets = []
+        for i, (sc, size) in enumerate(plan):
+            sc.record(pool.gpus[0], size, bufs[i], t=0.25 * i)
+            tickets.append(pool.submit(pool.gpus[0].Finish()))
+            if i >= 9:
+                pool.wait(tickets[i - 9])
+                assert np.array_equal(bufs[i - 9], want[i - 9]), f"frame {i - 9} differs"
+        pool.drain()
+        for i, (a, b) in enumerate(zip(bufs, want)):
+            assert np.array_equal(a, b), f"frame {i} differs"
+    finally:
+        pool.close()
+
+
 @pytest.mark.parametrize("overlap", [False, True])
 def test_retained_frames_replay_bit_identical(overlap):
     """rsrcu_retain_frame / rsrcu_replay_frame: the tables of a submitted frame (including its per-frame UPLOAD_ALWAYS
