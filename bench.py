@@ -493,6 +493,8 @@ def e2e_leg(wl, gpu, frames, torch, dist, world, local_rank, barrier, contexts=2
     pool.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("RSR_BENCH_DEBUG"):
+        print(f"rank {os.environ.get('RANK', '0')}: e2e {frames} frames in {e2e_s * 1e3:.1f} ms = {frames / e2e_s:.0f} frames/s", file=sys.stderr)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -554,7 +556,8 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     dev = f"cuda:{local_rank}"
     stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
     P = scenes.perspective(45.0, 7680 / 4320, 1.0, 400.0)
-    plan = SubframePlan(7680, 4320, world, 1920, 1080)
+    SH = args.split_sub_h
+    plan = SubframePlan(7680, 4320, world, 1920, SH)
     p2p = args.exchange == "p2p"
     flags = p2p and args.barrier == "flag"
     batch = max(1, args.batch_frames)
@@ -596,7 +599,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
         dist.broadcast(costs, src=0)
         costs_ms = [round(float(c), 4) for c in costs.tolist()]
         owners = SubframePlan.balance(costs_ms, world)
-        plan = SubframePlan(7680, 4320, world, 1920, 1080, owners=owners)
+        plan = SubframePlan(7680, 4320, world, 1920, SH, owners=owners)
 
     frames_done = 0      # frames launched so far in the current phase (same arithmetic on every rank)
 
@@ -667,7 +670,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     if rank == 0:
         alone = [retain(plan.subframes, b) for b in range(nbuf)] if p2p else None
         if not p2p:
-            local = torch.zeros((len(plan.subframes), 1080, 1920), dtype=torch.int32, device=dev)
+            local = torch.zeros((len(plan.subframes), SH, 1920), dtype=torch.int32, device=dev)
             alone = [retain(plan.subframes, 0, local)]
         gpu.Sync()
         single_ms = timed(alone, 1, True, steps, 3, torch.cuda.synchronize) / batch
@@ -687,7 +690,7 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
     if p2p:
         sets = [retain(mine, b) for b in range(nbuf)]
     else:
-        local = torch.zeros((len(mine), 1080, 1920), dtype=torch.int32, device=dev)
+        local = torch.zeros((len(mine), SH, 1920), dtype=torch.int32, device=dev)
         sets = [retain(mine, 0, local)]
         gathered = [torch.zeros_like(local) for _ in range(world)] if (rank == 0 and world > 1) else None
     gpu.Sync()
@@ -725,14 +728,14 @@ def split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier,
                "frames_per_step": batch, "ms_per_step": ms * batch, "ms_per_frame": ms, "scaling": "strong",
                "single_gpu_frames_per_s": 1e3 / single_ms, "single_gpu_ms_per_frame": single_ms,
                "speedup_vs_single_gpu": single_ms / ms, "efficiency": single_ms / ms / world,
-               "nvlink_bytes_per_frame": remote * 1920 * 1080 * 4,
-               "config": {"workload": "c5_8k_split_frame_4x4_subframes_of_c2", "width": 7680, "height": 4320,
+               "nvlink_bytes_per_frame": remote * 1920 * SH * 4,
+               "config": {"workload": f"c5_8k_split_frame_{plan.nx}x{plan.ny}_subframes_of_c2", "width": 7680, "height": 4320,
                           "subframes_per_rank": len(mine), "exchange": exchange,
                           "ownership": "round robin" if owners is None else f"cost balanced (longest first): {owners}",
                           "subframe_tile_ms": costs_ms,
                           "submission": f"batches of {batch} frames back to back, retained sub-frame tables replayed",
                           "cache": "L2 flushed before every timed batch"},
-               "mtris_per_s": 16 * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks,
+               "mtris_per_s": len(plan.subframes) * scene.triangles * 1e3 / ms / 1e6, "clocks": clocks,
                "frame_checksum": checksum, "frame_checksum_single_gpu": checksum1, "checksums_equal": checksum == checksum1,
                "gpu_launches": int(st["kernel_launches"]) * len(mine) * steps * batch}
     return rec
@@ -769,6 +772,7 @@ def main():
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
     ap.add_argument("--balance", default="cost", choices=["cost", "roundrobin"], help="split-frame: how sub-frames are dealt to the ranks")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="split-frame: how resolved pixels reach the presenting GPU")
+    ap.add_argument("--split-sub-h", type=int, default=1080, help="split-frame: sub-frame height (1080: 4x4 sub-frames of the 8K frame; 540: 4x8)")
     ap.add_argument("--batch-frames", type=int, default=8, help="split-frame: frames per step (a batch submitted back to back)")
     ap.add_argument("--barrier", default="flag", choices=["flag", "nccl"], help="split-frame with p2p stores: completion counter in the presenter's memory, or an NCCL all-reduce")
     args = ap.parse_args()
@@ -793,7 +797,7 @@ def main():
         print(json.dumps(line))
         return 0
 
-    cores_per_rank = pin_rank_to_cores(local_rank, world) if world > 1 else None
+    cores_per_rank = pin_rank_to_cores(local_rank, world) if (world > 1 and not os.environ.get("RSR_BENCH_NO_PIN")) else None
     import torch
     import rsr_b200
     torch.cuda.set_device(local_rank)
