@@ -201,6 +201,8 @@ public:
 	// beyond the reference's surface (include/rsrcu.h): pipelining, retained frames, split-frame presentation
 	void SyncFrame(int lag) { Check(rsrcu_sync_frame(ctx_, lag)); }
 	void SetOverlap(bool on) { Check(rsrcu_set_overlap(ctx_, on ? 1 : 0)); }
+	/// orders Stream() behind every frame submitted so far (overlap mode runs tile kernels on two streams)
+	void Join() { Check(rsrcu_join(ctx_)); }
 	void EnablePeerAccess(int peerDevice) { Check(rsrcu_enable_peer_access(ctx_, peerDevice)); }
 	rsrcu_frame* Retain() { rsrcu_frame* f = nullptr; Check(rsrcu_retain_frame(ctx_, &f)); return f; }
 	void Replay(rsrcu_frame* f) { Check(rsrcu_replay_frame(ctx_, f)); }
