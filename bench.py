@@ -200,6 +200,21 @@ def time_reference(wl, steps, warmup, threads=None, budget_s=25.0):
     return {"ms_per_frame": ms, "fps": 1e3 / ms, "frames": len(times), "threads": threads}
 
 
+def time_reference_isolated(key, steps, warmup, budget_s):
+    """time_reference in a process of its own (`bench.py --impl reference`): the reference is timed with none of this
+    process's threads (CUDA, submission pool) beside it, and a fault inside the reference's unchecked CPU code -- its tile
+    lists are fixed 100 000-byte arrays, rglv_gpu.hxx:29 -- costs the baseline figure, not the measurement"""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", key, "--steps", str(steps),
+           "--warmup", str(warmup), "--ref-budget", str(budget_s)]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    lines = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not lines:
+        raise RuntimeError(f"reference process ended with code {p.returncode}: {p.stderr.strip()[-200:]}")
+    d = json.loads(lines[-1])
+    return {"ms_per_frame": d["ms_per_step"], "fps": d["value"], "frames": d["steps"], "threads": d["cpu_baseline"]["cores"]}
+
+
 def parity_gate(wl, gpu):
     """frame 0 of the workload (every sub-frame) through the reference's CPU rasteriser and through the CUDA path on
     the same recorded calls: differing pixels and the largest 8-bit channel difference"""
@@ -526,7 +541,7 @@ def stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier):
            "parity": par, "roofline": roofline_of(wl, m, ms)}
     if not args.no_cpu_baseline:
         try:
-            r = time_reference(wl, 6, 1, budget_s=12.0)
+            r = time_reference_isolated(wl.key, 6, 1, 12.0)
             out["cpu_baseline"] = {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
                                    "sample": f"{r['frames']} frames (sum over the 4 sub-frames), doubleBuffer=true"}
         except Exception as exc:
@@ -754,7 +769,17 @@ def pin_rank_to_cores(local_rank, world):
         return None
 
 
+def finish(code=0):
+    """the line is out: flush and leave without running interpreter / library teardown (worker threads of the reference's
+    job system, CUDA contexts of several host threads: nothing there is worth a crash after the measurement)"""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
+
+
 def main():
+    import faulthandler
+    faulthandler.enable()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -767,6 +792,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=200)
     ap.add_argument("--e2e-contexts", type=int, default=0, help="submission threads / contexts of the end-to-end leg (0: 2 at one or two GPUs, 1 per rank beyond: the ranks share the host's cores)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--ref-budget", type=float, default=25.0, help="--impl reference: stop after this many seconds of timed frames (at least 3 frames)")
     ap.add_argument("--ring", type=int, default=24, help="distinct frames in the frame-sequence leg's ring")
     ap.add_argument("--resident", default="retained", choices=["retained", "stream"],
                     help="device-resident leg: replay retained frame tables, or decode + upload the recorded stream every step")
@@ -786,7 +812,7 @@ def main():
         if rank != 0:
             return 0
         wl = Workload("c2" if args.workload == "c5" else args.workload)
-        r = time_reference(wl, args.steps, args.warmup)
+        r = time_reference(wl, args.steps, args.warmup, budget_s=args.ref_budget)
         line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": r["frames"], "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic", "config": wl.config(args),
@@ -794,8 +820,8 @@ def main():
                 "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
                                  "sample": f"{r['frames']} frames of the same workload, doubleBuffer=true, worst 5% dropped"},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+        print(json.dumps(line), flush=True)
+        finish(0)
 
     cores_per_rank = pin_rank_to_cores(local_rank, world) if (world > 1 and not os.environ.get("RSR_BENCH_NO_PIN")) else None
     import torch
@@ -819,11 +845,11 @@ def main():
         rec = split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier)
         if rank == 0:
             rec.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic"})
-            print(json.dumps(rec))
+            print(json.dumps(rec), flush=True)
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
-        return 0
+        finish(0)
 
     wl = Workload(args.workload)
     config = wl.config(args)
@@ -900,14 +926,14 @@ def main():
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
-        return 0
+        finish(0)
 
     stats = m["stats"]
     roofline = roofline_of(wl, m, ms_per_step)
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # (rank 0 at N = 1 only: at N > 1 the ranks are pinned to slices of the cores)
         try:
-            r = time_reference(wl, 30, 3, budget_s=20.0)
+            r = time_reference_isolated(wl.key, 30, 3, 20.0)
             cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "reference",
                    "sample": f"{r['frames']} frames of the same workload on the host cores, doubleBuffer=true, worst 5% dropped"}
         except Exception as exc:  # oracle not shipped: say so, never fake
@@ -923,11 +949,11 @@ def main():
             "gpu_launches": int(stats["kernel_launches"]) * len(wl.subframes) * args.steps,
             "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu}
     line.update(extra)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    finish(0)
 
 
 if __name__ == "__main__":

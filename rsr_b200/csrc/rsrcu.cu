@@ -518,7 +518,7 @@ const TileVariant& tileVariantFor(uint32_t progMask) {
 
 // (off for the front-end kernels of a frame in overlap mode: a dependent kernel that is resident early only to sit in
 // griddepcontrol.wait holds registers and thread slots the concurrent tile kernel of the previous frame could use)
-bool g_pdl = true;
+thread_local bool g_pdl = true;   // (contexts may be driven from different host threads: rsr_b200.SubmitPool)
 
 template <class... KArgs, class... Args>
 cudaError_t launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -23,6 +23,12 @@ def test_plan_grid_and_ownership():
     assert (p4.nx, p4.ny) == (2, 2) and [s.owner for s in p4.subframes] == [0, 1, 0, 1]
     with pytest.raises(AssertionError):
         SubframePlan(4000, 2160, 1, max_w=4000)          # wider than the reference's guard band
+    # finer units (bench.py --split-sub-h 540): 4 x 8 half-height sub-frames, four per rank at 8 ranks
+    ph = SubframePlan(7680, 4320, 8, 1920, 540)
+    assert (ph.nx, ph.ny, ph.sub_w, ph.sub_h) == (4, 8, 1920, 540) and [len(ph.owned_by(r)) for r in range(8)] == [4] * 8
+    img = {s_.index: np.full((s_.height, s_.width), s_.index, np.uint32) for s_ in ph.subframes}
+    whole = ph.assemble(img)
+    assert whole.shape == (4320, 7680) and all(int(whole[s_.y0, s_.x0]) == s_.index and int(whole[s_.y0 + 539, s_.x0 + 1919]) == s_.index for s_ in ph.subframes)
 
 
 def test_crop_matrix_maps_subwindow_to_full_ndc():

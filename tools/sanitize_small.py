@@ -9,7 +9,8 @@ from rsr_b200 import scenes
 g = R.GPU(0)
 size = (320, 192)
 for sc, kw in ((scenes.WavyGridScene(n=24), {}), (scenes.CubesScene(instances=40), {}), (scenes.SoupScene(n=150, seed=3), {}),
-               (scenes.SoupScene(n=120, seed=7, blend=True, cull=R.GL_BACK), {}), (scenes.GeometryStressScene(spheres=2, divs=4, size=size, radius_px=40.0), {})):
+               (scenes.SoupScene(n=120, seed=7, blend=True, cull=R.GL_BACK), {}), (scenes.GeometryStressScene(spheres=2, divs=4, size=size, radius_px=40.0), {}),
+               (scenes.BundledLikeScene(cubes=60, field=6), {"t": 0.4}), (scenes.ColortestScene(), {})):
     out = np.zeros((size[1], size[0]), np.uint32)
     sc.record(g, size, out, **kw)
     g.Run()
