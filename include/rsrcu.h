@@ -59,6 +59,10 @@ extern "C" {
 /* upload policy for rsrcu_bind_buffer / rsrcu_bind_texture / index data */
 #define RSRCU_UPLOAD_ALWAYS 0   /* contents may have changed since the last call: copy again */
 #define RSRCU_UPLOAD_STATIC 1   /* (pointer, size) identifies immutable data: copy once, then reuse */
+#define RSRCU_UPLOAD_DEVICE 2   /* the pointer IS device memory on the context's device (a canvas of rsrcu_canvas_alloc,
+                                   the output of rsrcu_march_surface, any CUDA allocation): used in place, nothing is
+                                   copied.  The caller orders producer and consumer (same context: stream order;
+                                   another context: rsrcu_wait_for) */
 
 typedef struct rsrcu_ctx rsrcu_ctx;
 
@@ -257,6 +261,7 @@ int rsrcu_sync_frame(rsrcu_ctx* ctx, int lag);
  *   RSRCU_OP_END_FRAME     (no payload)
  *   RSRCU_OP_STORE_TC_DEV  int32 gamma, width, height, stride_px; uint64 device ptr
  *   RSRCU_OP_STORE_QUADS   int32 pad, width, height, stride_quads; uint64 ptr
+ *   RSRCU_OP_STORE_FP_DEV / _QUADS_DEV / _DEPTH_DEV   same payloads as STORE_FP / STORE_QUADS / STORE_DEPTH, device ptr
  */
 #define RSRCU_OP_BEGIN_FRAME 1
 #define RSRCU_OP_STATE 2
@@ -272,6 +277,9 @@ int rsrcu_sync_frame(rsrcu_ctx* ctx, int lag);
 #define RSRCU_OP_END_FRAME 12
 #define RSRCU_OP_STORE_TC_DEV 13
 #define RSRCU_OP_STORE_QUADS 14
+#define RSRCU_OP_STORE_FP_DEV 15
+#define RSRCU_OP_STORE_QUADS_DEV 16
+#define RSRCU_OP_STORE_DEPTH_DEV 17
 int rsrcu_run_stream(rsrcu_ctx* ctx, const void* stream, size_t bytes);
 
 /* ---- device-side access (viewer presents from the device-resolved buffer; bench; sharding) --- */
@@ -280,6 +288,77 @@ int rsrcu_run_stream(rsrcu_ctx* ctx, const void* stream, size_t bytes);
 int rsrcu_device_truecolor(rsrcu_ctx* ctx, void** dev_ptr, int* stride_px);
 /* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
 int rsrcu_stream(rsrcu_ctx* ctx, void** stream);
+
+/* ---- device canvases: render-to-texture, shadow maps and glow chains that never leave the device ----
+ * The reference's node graph passes canvases between nodes in host memory: a `$layer` renders its lights' depth maps
+ * with a second rglv::GPU and StoreDepth (src/viewer/node/gllayer.cxx:154-181) before the main pass samples them;
+ * `$buffers` exposes StoreColor results (quads / half-size linear, node/buffers.cxx), `$kawase` blurs them
+ * (node/kawase.cxx:83-129), `$glow` combines image + blur into the true-colour output (node/glow.cxx:146-160),
+ * `$rendertotexture` feeds a frame back as a texture.  Here those canvases are device memory: the store commands take
+ * a device destination, the bind calls take a device source (RSRCU_UPLOAD_DEVICE), the post filters are kernels on the
+ * context's stream, and only the final true-colour frame crosses PCIe. */
+int rsrcu_canvas_alloc(rsrcu_ctx* ctx, size_t bytes, void** device_ptr);   /* 256-byte aligned, zero-filled */
+int rsrcu_canvas_free(rsrcu_ctx* ctx, void* device_ptr);
+/* blocking copies, ordered behind everything submitted to the context so far (tests, fixtures, debugging) */
+int rsrcu_canvas_read(rsrcu_ctx* ctx, const void* device_ptr, void* host_dst, size_t bytes);
+int rsrcu_canvas_write(rsrcu_ctx* ctx, void* device_ptr, const void* host_src, size_t bytes);
+
+/* rsrcu_store_color_fp / _quads / rsrcu_store_depth with a DEVICE destination (same layouts, same arguments) */
+int rsrcu_store_color_fp_device(rsrcu_ctx* ctx, void* device_dst, int width, int height, int stride_px, int half);
+int rsrcu_store_color_quads_device(rsrcu_ctx* ctx, void* device_dst, int width, int height, int stride_quads);
+int rsrcu_store_depth_device(rsrcu_ctx* ctx, void* device_dst);
+
+/* Orders `ctx` behind `producer` (two contexts on the same device, e.g. the shadow-map context of a `$layer` and the
+ * main one): everything submitted to `producer` so far completes before anything submitted to `ctx` from now on
+ * starts.  No host wait.  (jobsys::add_link(gpu_.Run(), lightJobs[li]) ... jobsys::wait, gllayer.cxx:177-187) */
+int rsrcu_wait_for(rsrcu_ctx* ctx, rsrcu_ctx* producer);
+
+/* rglr::KawaseBlurFilter (src/rgl/rglr/rglr_kawase.cxx:22-81): dst(x, y) = 1/16 of the sum of four 2x2 boxes at the
+ * offsets (-d-1,-d-1) (d,-d-1) (-d-1,d) (d,d), coordinates clamped to the canvas; RGBA32F linear canvases, strides in
+ * pixels, src != dst.  `$kawase` with intensity N = N calls with dist 0 .. N-1 ping-ponging two canvases. */
+int rsrcu_kawase_blur(rsrcu_ctx* ctx, const void* src_device, int src_stride_px, void* dst_device, int dst_stride_px,
+                      int width, int height, int dist);
+
+/* `$glow` (node/glow.cxx:24-39, :146-160; rglr::Filter<GlowShader, sRGB|LinearColor>, rglr_algorithm.hxx:107-144):
+ * out = (image + blur * 0.7) * 0.5 per quad, converted to 0x00RRGGBB.  image: quad-swizzled canvas of the frame
+ * (rsrcu_store_color_quads[_device]); blur: linear RGBA32F canvas read at (x/2, y/2) -- one blur pixel per quad, as
+ * the reference does.  dst: host memory (written when the call returns) or, with dst_is_device, device memory
+ * (stream-ordered; rsrcu_device_truecolor then reports it). */
+int rsrcu_glow(rsrcu_ctx* ctx, const void* image_quads_device, int image_stride_quads, const void* blur_device,
+               int blur_stride_px, int enable_gamma, uint32_t* dst, int dst_is_device, int width, int height, int stride_px);
+
+/* ---- geometry produced on the device -----------------------------------------------------------------
+ * `$mc` (src/viewer/node/mc.cxx:230-300 + rglv::march_sdf_vao, src/rgl/rglv/rglv_marching_cubes.hxx:66-109): marching
+ * cubes over the node's signed-distance field (sphere of radius 3 + sine distortion, mc.cxx:95-110) on a
+ * precision^3 grid over [-range, range]^3, split into 8^fork_depth blocks like the reference's jobs.  The vertices
+ * (position SoA in slots 0-2, normal SoA in slots 3-5, three per triangle, DrawArrays order) are written to device
+ * memory owned by the context and never cross PCIe: bind them with RSRCU_UPLOAD_DEVICE and rsrcu_draw_arrays.
+ * Blocks are emitted in the reference's block order and cells in its y / z / x order, so the triangle sequence is
+ * the one the reference draws (its jobs append to per-block arrays that are drawn in allocation order; here the
+ * order is deterministic).  Positions are bit-identical to the reference's; normals go through libm's sinf there and
+ * CUDA's sinf here and agree to about 1e-6.  out_soa6: device pointers to x, y, z, nx, ny, nz (vertex_total floats
+ * each; valid until the third call from now on this context); blocks: per non-empty block its first vertex (a
+ * multiple of 4: the reference pads every block's arrays for its 4-wide loader, the padding is zeros) and its vertex
+ * count -- the reference issues one DrawArrays per block (mc.cxx:212-226).  Blocking (the counts come back to the
+ * host).  1 <= precision >> fork_depth <= 32. */
+typedef struct RsrMarchBlock { int32_t first_vertex, vertex_count; } RsrMarchBlock;
+int rsrcu_march_surface(rsrcu_ctx* ctx, float time_seconds, int precision, int fork_depth, float range,
+                        const float** out_soa6, RsrMarchBlock* blocks, int block_capacity, int* block_count, int* vertex_total);
+
+/* ---- presentation + telemetry --------------------------------------------------------------------------
+ * The viewer draws a per-thread timeline of job spans over the frame (render_jobsys, src/viewer/jobsys_vis.cxx:26-90:
+ * one 8-pixel bar per lane, 2-pixel gap, brightness ramp 1 -> 0 along the span, colours picked by hashed bits) and
+ * hands the canvas to the window.  Here the lanes are the frame's pipeline stages timed with CUDA events instead of
+ * jobsys::measurements_pt, the bars are drawn by a kernel into the device-resolved true-colour buffer, and the
+ * presentation step is a device-to-device blit into the presentation surface (the interop-mapped swap-chain image in a
+ * viewer; any device allocation here). */
+typedef struct RsrSpan { double start, end; uint32_t raw; int32_t lane; } RsrSpan;   /* jobsys::JobStat (rclmt_jobsys.hxx:94-97) + its lane */
+int rsrcu_draw_spans(rsrcu_ctx* ctx, void* truecolor_device, int stride_px, int width, int height,
+                     int left, int top, float xscale, const RsrSpan* spans, int count);
+/* the spans of the context's last profiled frame (rsrcu_set_profiling level 2): one lane per stage, raw = stage index */
+int rsrcu_frame_spans(rsrcu_ctx* ctx, RsrSpan* out, int capacity, int* count);
+int rsrcu_present(rsrcu_ctx* ctx, const void* truecolor_device, int src_stride_px, void* surface_device,
+                  int surface_stride_px, int width, int height);
 
 /* counters of the last completed frame (filled by rsrcu_sync) */
 typedef struct RsrStats {

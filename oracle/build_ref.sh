@@ -43,6 +43,9 @@ SRCS=(
   src/rgl/rglv/rglv_mesh.cxx
   src/rgl/rglv/rglv_mesh_util.cxx
   src/rgl/rglv/rglv_material.cxx
+  src/rgl/rglr/rglr_kawase.cxx
+  src/rgl/rglv/rglv_marching_cubes.cxx
+  src/viewer/jobsys_vis.cxx
   src/viewer/shaders.cxx
   src/viewer/shaders_envmap.cxx
   src/viewer/shaders_wireframe.cxx

@@ -33,6 +33,14 @@
 #include "src/rml/rmlm/rmlm_mat4.hxx"
 #include "src/rml/rmlv/rmlv_mvec4.hxx"
 #include "src/viewer/shaders.hxx"
+#include "src/rgl/rglr/rglr_algorithm.hxx"
+#include "src/rgl/rglr/rglr_canvas_util.hxx"
+#include "src/rgl/rglr/rglr_kawase.hxx"
+#include "src/rgl/rglv/rglv_marching_cubes.hxx"
+#include "src/rgl/rglr/rglr_fragmentcursor.hxx"
+#include "src/rgl/rglv/rglv_gpu_impl.hxx"
+#include "src/rgl/rglv/rglv_gpu_shaders.hxx"
+#include "src/viewer/jobsys_vis.hxx"
 
 using namespace rqdq;
 namespace jobsys = rclmt::jobsys;
@@ -309,5 +317,168 @@ void ref_vraster_coverage(const int* x3, const int* y3, int rx0, int ry0, int rx
 	rglv::VTriangleRasterizer<false, LaneProgram> tr(lp, rect, hgt);
 	tr.Draw(rmlv::mvec4i{x3[0]}, rmlv::mvec4i{x3[1]}, rmlv::mvec4i{x3[2]},
 	        rmlv::mvec4i{y3[0]}, rmlv::mvec4i{y3[1]}, rmlv::mvec4i{y3[2]}, 1); }
+
+/* ---- post filters, shadow-map program, marching cubes, telemetry overlay ------------------------ */
+
+/* rglr::KawaseBlurFilter (src/rgl/rglr/rglr_kawase.cxx:22-81), the reference's own function over caller memory */
+void ref_kawase_blur(const float* src, int srcStride, float* dst, int dstStride, int w, int hgt, int dist) {
+	rglr::FloatingPointCanvas s(reinterpret_cast<PixelToaster::FloatingPointPixel*>(const_cast<float*>(src)), w, hgt, srcStride);
+	rglr::FloatingPointCanvas d(reinterpret_cast<PixelToaster::FloatingPointPixel*>(dst), w, hgt, dstStride);
+	rglr::KawaseBlurFilter(s, d, dist, 0, hgt); }
+
+namespace {
+/* `$glow`'s canvas shader.  It lives in an unnamed namespace of src/viewer/node/glow.cxx:24-39 and cannot be linked, so
+ * its one expression is restated here; the filter that applies it, rglr::Filter<SHADER, CONVERTER>
+ * (rglr_algorithm.hxx:107-144), and the converters (rglr_canvas_util.hxx) are the reference's own. */
+struct GlowShaderRestated {
+	static rmlv::qfloat3 ShadeCanvas(rmlv::qfloat2, rmlv::qfloat3 c1, rmlv::qfloat3 c2) {
+		const rmlv::qfloat blurAmt{ 0.700F };
+		const rmlv::qfloat brightness{ 0.5F };
+		rmlv::qfloat3 out;
+		out = (c1 + c2*blurAmt) * brightness;
+		return out; }};
+}
+
+void ref_glow_filter(const float* quads, int strideQuads, const float* blur, int blurW, int blurH, int blurStride,
+                     uint32_t* dst, int w, int hgt, int stride, int gamma) {
+	rglr::QFloat4Canvas src0(w, hgt, reinterpret_cast<rmlv::qfloat4*>(const_cast<float*>(quads)), strideQuads);
+	rglr::FloatingPointCanvas src1(reinterpret_cast<PixelToaster::FloatingPointPixel*>(const_cast<float*>(blur)), blurW, blurH, blurStride);
+	rglr::TrueColorCanvas out(reinterpret_cast<PixelToaster::TrueColorPixel*>(dst), w, hgt, stride);
+	rmlg::irect rect{ { 0, 0 }, { w, hgt } };
+	if (gamma) { rglr::Filter<GlowShaderRestated, rglr::sRGB>(src0, src1, out, rect); }
+	else { rglr::Filter<GlowShaderRestated, rglr::LinearColor>(src0, src1, out, rect); } }
+
+/* the shadow-map GPU of a `$layer` (src/viewer/node/gllayer.cxx:39-45): BaseProgram, depth only */
+void ref_gpu_install_shadow_program(void* h) {
+	auto& gpu = static_cast<RefGPU*>(h)->gpu;
+	gpu.Install(0, 0, rglv::GPUBinImpl<rglv::BaseProgram>::MakeBinProgramPtrs());
+	gpu.Install(0, 0x6a2, rglv::GPUTileImpl<rglr::QFloat3FragmentCursor, rglr::QFloatFragmentCursor, rglv::BaseProgram, false, true, rglv::DepthLT, true, false, rglv::BlendOff>::MakeDrawProgramPtrs()); }
+
+/* the reference's marching-cubes tables (rglv_marching_cubes.cxx) */
+void ref_mc_tables(int16_t* edgeFlags256, int8_t* tri256x16, uint8_t* edgeConn12x2) {
+	for (int i = 0; i < 256; ++i) {
+		edgeFlags256[i] = rglv::cube_edge_flags[i];
+		for (int k = 0; k < 16; ++k) { tri256x16[i * 16 + k] = static_cast<int8_t>(rglv::tritable[i][k]); } }
+	for (int e = 0; e < 12; ++e) { edgeConn12x2[2 * e] = rglv::edge_connection[e][0]; edgeConn12x2[2 * e + 1] = rglv::edge_connection[e][1]; } }
+
+namespace {
+/* `$mc`'s field and block walk.  Both live in the unnamed namespace of src/viewer/node/mc.cxx (Surface :95-110,
+ * BlockDivider :33-93, Impl::ResolveImpl :230-300) and cannot be linked without the node graph, so they are restated
+ * here line by line; what they call -- rglv::march_sdf_vao, the case tables, rmlv's vec / mvec4f arithmetic and its
+ * sine approximation -- is the reference's own code.  `sin` / `abs` on floats are the float overloads, as with the
+ * reference's native compiler. */
+struct McSurface {
+	float timeInSeconds_;
+	float sample(rmlv::vec3 pos) const {
+		float distort = 0.60F * sinf(5.0F*(pos.x + timeInSeconds_ / 4.0F))* sinf(2.0F*(pos.y + (timeInSeconds_ / 1.33F)));
+		return (length(pos) - 3.0F) + (distort * sinf(timeInSeconds_ / 2.0F) + 1.0F); }
+	rmlv::mvec4f sample(rmlv::qfloat3 pos) const {
+		using rmlv::mvec4f;
+		auto T = mvec4f{ timeInSeconds_ };
+		auto distort = mvec4f{0.60F} * sin(5.0F*(pos.x + T / 4.0F))* sin(2.0F*(pos.y + (T / 1.33F)));
+		return (rmlv::length(pos) - 3.0F) + (distort * sin(T / 2.0F) + 1.0F); }};
+
+struct McAABB { rmlv::vec3 leftTopBack, rightBottomFront; };
+
+void McDivide(McAABB b, int limit, std::vector<McAABB>& out) {
+	using rmlv::vec3;
+	if (limit == 0) { out.emplace_back(b); return; }
+	const auto mid = mix(b.leftTopBack, b.rightBottomFront, 0.5F);
+	const auto ltb = b.leftTopBack;
+	const auto rbf = b.rightBottomFront;
+	const McAABB sub[8] = {
+		{ vec3{ ltb.x, ltb.y, ltb.z }, vec3{ mid.x, mid.y, mid.z } }, { vec3{ mid.x, ltb.y, ltb.z }, vec3{ rbf.x, mid.y, mid.z } },
+		{ vec3{ ltb.x, mid.y, ltb.z }, vec3{ mid.x, rbf.y, mid.z } }, { vec3{ mid.x, mid.y, ltb.z }, vec3{ rbf.x, rbf.y, mid.z } },
+		{ vec3{ ltb.x, ltb.y, mid.z }, vec3{ mid.x, mid.y, rbf.z } }, { vec3{ mid.x, ltb.y, mid.z }, vec3{ rbf.x, mid.y, rbf.z } },
+		{ vec3{ ltb.x, mid.y, mid.z }, vec3{ mid.x, rbf.y, rbf.z } }, { vec3{ mid.x, mid.y, mid.z }, vec3{ rbf.x, rbf.y, rbf.z } } };
+	for (const auto& s : sub) { McDivide(s, limit - 1, out); } }
+
+/* ResolveImpl (mc.cxx:230-300); returns false when the block is skipped by the distance test */
+bool McResolve(const McSurface& field_, McAABB block, int dim, rglv::VertexArray_F3F3F3& vao) {
+	using rmlv::vec3; using rmlv::mvec4f; using rmlv::qfloat;
+	const int stride = 64;
+	std::array<std::array<float, stride*stride>, 2> buf;
+	int top = 1, bot = 0;
+	float sy = block.leftTopBack.y;
+	float delta = (block.rightBottomFront.x - block.leftTopBack.x) / float(dim);
+	const qfloat vdelta{ delta * 4 };
+	const auto mid = mix(block.leftTopBack, block.rightBottomFront, 0.5F);
+	const auto R = length(block.leftTopBack - mid);
+	float D = field_.sample(mid);
+	if (fabsf(D)*0.5F > R) { return false; }
+	auto fillSlice = [&]() {
+		mvec4f fooZ{ block.leftTopBack.z };
+		mvec4f fooY{ sy };
+		for (int iz=0; iz<dim+1; iz++, fooZ += delta) {
+			mvec4f fooX{ block.leftTopBack.x };
+			fooX += mvec4f{ 0, delta, delta*2, delta*3 };
+			for (int ix{0}; ix<dim+1; ix+=4, fooX+=vdelta) {
+				auto distance = field_.sample({ fooX, fooY, fooZ });
+				_mm_storeu_ps(&(buf[bot][iz*stride + ix]), distance.v); }}};
+	fillSlice();
+	sy -= delta;
+	vec3 origin = block.leftTopBack;
+	for (int iy=0; iy<dim; iy++, sy -= delta) {
+		origin.y -= delta;
+		std::swap(top, bot);
+		fillSlice();
+		origin.z = block.leftTopBack.z;
+		for (int iz = 0; iz < dim; iz++, origin.z += delta) {
+			origin.x = block.leftTopBack.x;
+			for (int ix = 0; ix < dim; ix++, origin.x += delta) {
+				rglv::Cell cell;
+				cell.value[0] = buf[bot][ iz   *stride + ix];     cell.pos[0] = origin;
+				cell.value[1] = buf[bot][ iz   *stride + ix + 1]; cell.pos[1] = vec3{ origin.x + delta, origin.y, origin.z };
+				cell.value[2] = buf[top][ iz   *stride + ix + 1]; cell.pos[2] = vec3{ origin.x + delta, origin.y + delta, origin.z };
+				cell.value[3] = buf[top][ iz   *stride + ix];     cell.pos[3] = vec3{ origin.x,         origin.y + delta, origin.z };
+				cell.value[4] = buf[bot][(iz+1)*stride + ix];     cell.pos[4] = vec3{ origin.x,         origin.y, origin.z + delta };
+				cell.value[5] = buf[bot][(iz+1)*stride + ix + 1]; cell.pos[5] = vec3{ origin.x + delta, origin.y, origin.z + delta };
+				cell.value[6] = buf[top][(iz+1)*stride + ix + 1]; cell.pos[6] = vec3{ origin.x + delta, origin.y + delta, origin.z + delta };
+				cell.value[7] = buf[top][(iz+1)*stride + ix];     cell.pos[7] = vec3{ origin.x,         origin.y + delta, origin.z + delta };
+				rglv::march_sdf_vao(vao, delta, cell, field_); }}}
+	return true; }
+}
+
+/* `$mc`'s Main (mc.cxx:171-193) with the jobs run one after the other in block order.  Output: vertex SoA
+ * (x | y | z and nx | ny | nz, `cap` floats each), per non-empty block its first vertex (padded to 4 like the device
+ * library) and vertex count.  Returns the padded vertex total, or -1 when `cap` / `blockCap` is too small. */
+int ref_march_surface(float t, int precision, int forkDepth, float range, float* pos3, float* nrm3, int cap,
+                      int* blockFirst, int* blockVerts, int blockCap, int* nblocks) {
+	McSurface field{t};
+	std::vector<McAABB> blocks;
+	McDivide(McAABB{ rmlv::vec3{-range, range, -range}, rmlv::vec3{ range, -range, range} }, forkDepth, blocks);
+	const int subDim = precision >> forkDepth;
+	int total = 0, nb = 0;
+	for (const auto& b : blocks) {
+		rglv::VertexArray_F3F3F3 vao;
+		if (!McResolve(field, b, subDim, vao)) { continue; }
+		const int n = vao.size();
+		if (n == 0) { continue; }
+		const int padded = (n + 3) & ~3;
+		if (total + padded > cap || nb >= blockCap) { return -1; }
+		for (int i = 0; i < n; ++i) {
+			pos3[total + i] = vao.a0.x[i]; pos3[cap + total + i] = vao.a0.y[i]; pos3[2 * cap + total + i] = vao.a0.z[i];
+			nrm3[total + i] = vao.a1.x[i]; nrm3[cap + total + i] = vao.a1.y[i]; nrm3[2 * cap + total + i] = vao.a1.z[i]; }
+		for (int i = n; i < padded; ++i) {
+			pos3[total + i] = pos3[cap + total + i] = pos3[2 * cap + total + i] = 0.0F;
+			nrm3[total + i] = nrm3[cap + total + i] = nrm3[2 * cap + total + i] = 0.0F; }
+		blockFirst[nb] = total; blockVerts[nb] = n; ++nb;
+		total += padded; }
+	*nblocks = nb;
+	return total; }
+
+/* render_jobsys (src/viewer/jobsys_vis.cxx:26-90) over a given list of spans: they are put where the reference's
+ * job system keeps its measurements (jobsys::measurements_pt, one vector per worker = lane) */
+void ref_render_spans(uint32_t* canvas, int w, int hgt, int stride, int left, int top, float xscale,
+                      const double* startEnd, const uint32_t* raw, const int* lane, int count) {
+	auto saved = jobsys::measurements_pt;
+	int lanes = 0;
+	for (int i = 0; i < count; ++i) { lanes = std::max(lanes, lane[i] + 1); }
+	jobsys::measurements_pt.assign(lanes, {});
+	for (int i = 0; i < count; ++i) {
+		jobsys::measurements_pt[lane[i]].push_back(jobsys::JobStat{ startEnd[2 * i], startEnd[2 * i + 1], raw[i] }); }
+	rglr::TrueColorCanvas c(reinterpret_cast<PixelToaster::TrueColorPixel*>(canvas), w, hgt, stride);
+	rqv::render_jobsys(left, top, xscale, c);
+	jobsys::measurements_pt = saved; }
 
 }  // extern "C"

@@ -98,6 +98,12 @@ def _bind(path):
         "ref_load_obj_arrays": (ci, [C.c_char_p, C.c_char_p, vp, ci, vp, ci, vp]),
         "ref_raster_coverage": (None, [vp, ci, ci, vp]),
         "ref_vraster_coverage": (None, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+        "ref_kawase_blur": (None, [vp, ci, vp, ci, ci, ci, ci]),
+        "ref_glow_filter": (None, [vp, ci, vp, ci, ci, ci, vp, ci, ci, ci, ci]),
+        "ref_gpu_install_shadow_program": (None, [vp]),
+        "ref_mc_tables": (None, [vp, vp, vp]),
+        "ref_march_surface": (ci, [cf, ci, ci, cf, vp, vp, ci, vp, vp, ci, vp]),
+        "ref_render_spans": (None, [vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, ci]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -308,6 +314,10 @@ class RefGPU:
         self._keep.append(dst)
         self.L.ref_gl_store_depth(self.h, _ptr(dst))
 
+    def InstallShadowProgram(self):
+        """the depth-only BaseProgram of a `$layer`'s shadow-map GPU (src/viewer/node/gllayer.cxx:44-45)"""
+        self.L.ref_gpu_install_shadow_program(self.h)
+
 
 # -- free helpers ------------------------------------------------------------------------------
 
@@ -397,3 +407,61 @@ def vraster_coverage(x3, y3, rect, w, h):
     out = np.zeros((h, w), np.uint8)
     lib().ref_vraster_coverage(_ptr(xs), _ptr(ys), rect[0], rect[1], rect[2], rect[3], w, h, _ptr(out))
     return out
+
+
+# -- post filters, marching cubes, telemetry overlay ---------------------------
+
+def kawase_blur(src: np.ndarray, dist: int) -> np.ndarray:
+    """rglr::KawaseBlurFilter (rglr_kawase.cxx:22-81) over an (H, W, 4) float32 canvas"""
+    s = _f32(src)
+    h, w, _ = s.shape
+    out = np.zeros_like(s)
+    lib().ref_kawase_blur(_ptr(s), w, _ptr(out), w, w, h, int(dist))
+    return out
+
+
+def glow_filter(quads: np.ndarray, blur: np.ndarray, gamma: bool = True) -> np.ndarray:
+    """rglr::Filter<GlowShader, sRGB|LinearColor> (rglr_algorithm.hxx:107-144, node/glow.cxx:24-39):
+    quads (H/2, W/2, 4, 4) float32, blur (h, w, 4) float32 -> (H, W) uint32"""
+    q = _f32(quads)
+    b = _f32(blur)
+    assert q.ctypes.data % 16 == 0
+    hq, wq = q.shape[:2]
+    bh, bw, _ = b.shape
+    out = np.zeros((hq * 2, wq * 2), np.uint32)
+    lib().ref_glow_filter(_ptr(q), wq, _ptr(b), bw, bh, bw, _ptr(out), wq * 2, hq * 2, wq * 2, int(bool(gamma)))
+    return out
+
+
+def mc_tables():
+    """the reference's marching-cubes tables: (cube_edge_flags[256] int16, tritable[256][16] int8, edge_connection[12][2] uint8)"""
+    flags = np.zeros(256, np.int16)
+    tri = np.zeros((256, 16), np.int8)
+    conn = np.zeros((12, 2), np.uint8)
+    lib().ref_mc_tables(_ptr(flags), _ptr(tri), _ptr(conn))
+    return flags, tri, conn
+
+
+def march_surface(t: float, precision: int, fork_depth: int, rng: float, cap: int = 1 << 21):
+    """`$mc` (node/mc.cxx:171-300 + rglv::march_sdf_vao) -> positions (3, n), normals (3, n), [(first_vertex, count)]"""
+    pos = np.zeros((3, cap), np.float32)
+    nrm = np.zeros((3, cap), np.float32)
+    first = np.zeros(4096, np.int32)
+    cnt = np.zeros(4096, np.int32)
+    nb = C.c_int(0)
+    total = lib().ref_march_surface(float(t), int(precision), int(fork_depth), float(rng), _ptr(pos), _ptr(nrm), cap,
+                                    _ptr(first), _ptr(cnt), 4096, C.byref(nb))
+    if total < 0:
+        raise RuntimeError("ref_march_surface: capacity too small")
+    blocks = [(int(first[i]), int(cnt[i])) for i in range(nb.value)]
+    return np.ascontiguousarray(pos[:, :total]), np.ascontiguousarray(nrm[:, :total]), blocks
+
+
+def render_spans(canvas: np.ndarray, left: int, top: int, xscale: float, spans):
+    """render_jobsys (src/viewer/jobsys_vis.cxx:26-90) over spans = [(start, end, raw, lane)] into an (H, W) uint32 canvas"""
+    assert canvas.dtype == np.uint32 and canvas.flags.c_contiguous
+    se = np.ascontiguousarray([[s[0], s[1]] for s in spans], dtype=np.float64).reshape(-1)
+    raw = np.ascontiguousarray([s[2] for s in spans], dtype=np.uint32)
+    lane = np.ascontiguousarray([s[3] for s in spans], dtype=np.int32)
+    h, w = canvas.shape
+    lib().ref_render_spans(_ptr(canvas), w, h, w, int(left), int(top), float(xscale), _ptr(se), _ptr(raw), _ptr(lane), len(spans))

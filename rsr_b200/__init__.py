@@ -31,7 +31,7 @@ PROGRAM_DEFAULT_POST, PROGRAM_EXPOSURE_POST, PROGRAM_IQ_POST = 1, 2, 3
 PROGRAM_AMY, PROGRAM_DEPTH, PROGRAM_MANY, PROGRAM_OBJ1, PROGRAM_OBJ2, PROGRAM_OBJ2S = 4, 5, 6, 7, 8, 9
 PROGRAM_ENVMAP, PROGRAM_WIREFRAME, PROGRAM_TEXT, PROGRAM_PATTERN, PROGRAM_ALPHATEXTURE = 10, 11, 26, 41, 65
 
-UPLOAD_ALWAYS, UPLOAD_STATIC = 0, 1
+UPLOAD_ALWAYS, UPLOAD_STATIC, UPLOAD_DEVICE = 0, 1, 2
 
 RSRCU_OK = 0
 ERROR_NAMES = {1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "NO_PROGRAM", 5: "UNSUPPORTED", 6: "OVERFLOW"}
@@ -133,6 +133,20 @@ def load_library():
         "rsrcu_get_stats": [vp, C.POINTER(RsrStats)],
         "rsrcu_set_profiling": [vp, ci],
         "rsrcu_get_stage_ms": [vp, vp],
+        "rsrcu_canvas_alloc": [vp, sz, C.POINTER(vp)],
+        "rsrcu_canvas_free": [vp, vp],
+        "rsrcu_canvas_read": [vp, vp, vp, sz],
+        "rsrcu_canvas_write": [vp, vp, vp, sz],
+        "rsrcu_store_color_fp_device": [vp, vp, ci, ci, ci, ci],
+        "rsrcu_store_color_quads_device": [vp, vp, ci, ci, ci],
+        "rsrcu_store_depth_device": [vp, vp],
+        "rsrcu_wait_for": [vp, vp],
+        "rsrcu_kawase_blur": [vp, vp, ci, vp, ci, ci, ci, ci],
+        "rsrcu_glow": [vp, vp, ci, vp, ci, ci, vp, ci, ci, ci, ci],
+        "rsrcu_march_surface": [vp, C.c_float, ci, ci, C.c_float, vp, vp, ci, C.POINTER(ci), C.POINTER(ci)],
+        "rsrcu_draw_spans": [vp, vp, ci, ci, ci, ci, ci, C.c_float, vp, ci],
+        "rsrcu_frame_spans": [vp, vp, ci, C.POINTER(ci)],
+        "rsrcu_present": [vp, vp, ci, vp, ci, ci, ci],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -151,6 +165,9 @@ EXPORTED_SYMBOLS = (
     "rsrcu_store_color_tc", "rsrcu_store_color_tc_device", "rsrcu_store_color_fp", "rsrcu_store_color_quads", "rsrcu_enable_peer_access", "rsrcu_set_overlap", "rsrcu_signal_counter", "rsrcu_wait_counters", "rsrcu_retain_frame", "rsrcu_replay_frame", "rsrcu_release_frame", "rsrcu_store_depth", "rsrcu_end_frame", "rsrcu_sync",
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_join", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
+    "rsrcu_canvas_alloc", "rsrcu_canvas_free", "rsrcu_canvas_read", "rsrcu_canvas_write", "rsrcu_store_color_fp_device",
+    "rsrcu_store_color_quads_device", "rsrcu_store_depth_device", "rsrcu_wait_for", "rsrcu_kawase_blur", "rsrcu_glow",
+    "rsrcu_march_surface", "rsrcu_draw_spans", "rsrcu_frame_spans", "rsrcu_present",
 )
 
 
@@ -159,7 +176,47 @@ def _ptr(a):
 
 
 (OP_BEGIN_FRAME, OP_STATE, OP_BIND_BUFFER, OP_BIND_TEXTURE, OP_BIND_DEPTH, OP_CLEAR, OP_DRAW_ELEMENTS,
- OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME, OP_STORE_TC_DEV, OP_STORE_QUADS) = range(1, 15)
+ OP_DRAW_ARRAYS, OP_STORE_TC, OP_STORE_FP, OP_STORE_DEPTH, OP_END_FRAME, OP_STORE_TC_DEV, OP_STORE_QUADS,
+ OP_STORE_FP_DEV, OP_STORE_QUADS_DEV, OP_STORE_DEPTH_DEV) = range(1, 18)
+
+
+class RsrSpan(C.Structure):
+    """include/rsrcu.h `RsrSpan`: a jobsys::JobStat (start / end in seconds, raw bits for the colour) and its lane"""
+    _fields_ = [("start", C.c_double), ("end", C.c_double), ("raw", C.c_uint32), ("lane", C.c_int32)]
+
+
+class RsrMarchBlock(C.Structure):
+    _fields_ = [("first_vertex", C.c_int32), ("vertex_count", C.c_int32)]
+
+
+class DeviceCanvas:
+    """Device memory standing in for one of the reference's canvases (rglr_canvas.hxx): kind 'fp' =
+    FloatingPointCanvas (H, W, 4) float32, 'quads' = QFloat4Canvas (H/2, W/2, 4, 4) float32, 'depth' = (H, W) float32,
+    'tc' = TrueColorCanvas (H, W) uint32.  Created by GPU.Canvas(); ptr is the device address."""
+
+    def __init__(self, gpu, kind, width, height):
+        self.gpu, self.kind, self.width, self.height = gpu, kind, int(width), int(height)
+        self.shape, self.dtype = {"fp": ((height, width, 4), np.float32), "quads": ((height // 2, width // 2, 4, 4), np.float32),
+                                  "depth": ((height, width), np.float32), "tc": ((height, width), np.uint32)}[kind]
+        self.nbytes = int(np.prod(self.shape)) * 4
+        p = C.c_void_p()
+        gpu._check(gpu.L.rsrcu_canvas_alloc(gpu.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def read(self) -> np.ndarray:
+        out = np.empty(self.shape, self.dtype)
+        self.gpu._check(self.gpu.L.rsrcu_canvas_read(self.gpu.h, C.c_void_p(self.ptr), _ptr(out), self.nbytes))
+        return out
+
+    def write(self, arr):
+        a = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert a.shape == self.shape
+        self.gpu._check(self.gpu.L.rsrcu_canvas_write(self.gpu.h, C.c_void_p(self.ptr), _ptr(a), self.nbytes))
+
+    def free(self):
+        if self.ptr:
+            self.gpu._check(self.gpu.L.rsrcu_canvas_free(self.gpu.h, C.c_void_p(self.ptr)))
+            self.ptr = None
 
 
 def _addr(a) -> int:
@@ -515,6 +572,129 @@ class GPU:
             self._check(self.L.rsrcu_store_depth(self.h, _ptr(dst)))
         else:
             self._emit(OP_STORE_DEPTH, struct.pack("<Q", _addr(dst)))
+
+    # -- device canvases, post filters, geometry producers, presentation ---------------
+    def Canvas(self, kind, width, height) -> "DeviceCanvas":
+        return DeviceCanvas(self, kind, width, height)
+
+    def UseBufferDevice(self, slot, device_ptr: int, n_floats: int):
+        """GL::UseBuffer with an array that already lives on the device (marching-cubes output): nothing is uploaded"""
+        if self.direct:
+            self._check(self.L.rsrcu_bind_buffer(self.h, slot, C.c_void_p(device_ptr), int(n_floats), UPLOAD_DEVICE))
+        else:
+            self._emit(OP_BIND_BUFFER, struct.pack("<iiQQ", slot, UPLOAD_DEVICE, int(device_ptr), int(n_floats)))
+
+    def BindTextureDevice(self, unit, canvas: "DeviceCanvas", mode):
+        """GL::BindTexture on a frame another pass stored into a device canvas ('fp'): render to texture without a
+        PCIe round trip.  Like the reference's `$rendertotexture`, the canvas is sampled without a mip chain unless it
+        is a power-of-two square whose rows hold one (rows = 2 x height)."""
+        assert canvas.kind == "fp"
+        w, h = canvas.width, canvas.height
+        if self.direct:
+            self._check(self.L.rsrcu_bind_texture(self.h, unit, C.c_void_p(canvas.ptr), w, h, w, mode, h, UPLOAD_DEVICE))
+        else:
+            self._emit(OP_BIND_TEXTURE, struct.pack("<iiiiiiiiQ", unit, w, h, w, mode, h, UPLOAD_DEVICE, 0, int(canvas.ptr)))
+
+    def BindTexture3Device(self, canvas: "DeviceCanvas"):
+        """GL::BindTexture3 on a depth canvas rendered on the device (the shadow map of a `$layer`, gllayer.cxx:154-181)"""
+        assert canvas.kind == "depth" and canvas.width == canvas.height
+        if self.direct:
+            self._check(self.L.rsrcu_bind_depth_texture(self.h, C.c_void_p(canvas.ptr), canvas.width, UPLOAD_DEVICE))
+        else:
+            self._emit(OP_BIND_DEPTH, struct.pack("<iiQ", canvas.width, UPLOAD_DEVICE, int(canvas.ptr)))
+
+    def StoreToCanvas(self, canvas: "DeviceCanvas", half: bool = False):
+        """GL::StoreColor / StoreDepth into a device canvas: 'fp' (full size, or half size with half=True), 'quads', 'depth'"""
+        self._flush_state()
+        w, h = canvas.width, canvas.height
+        if canvas.kind == "fp":
+            if self.direct:
+                self._check(self.L.rsrcu_store_color_fp_device(self.h, C.c_void_p(canvas.ptr), w, h, w, int(half)))
+            else:
+                self._emit(OP_STORE_FP_DEV, struct.pack("<iiiiQ", int(half), w, h, w, int(canvas.ptr)))
+        elif canvas.kind == "quads":
+            if self.direct:
+                self._check(self.L.rsrcu_store_color_quads_device(self.h, C.c_void_p(canvas.ptr), w, h, w // 2))
+            else:
+                self._emit(OP_STORE_QUADS_DEV, struct.pack("<iiiiQ", 0, w, h, w // 2, int(canvas.ptr)))
+        elif canvas.kind == "depth":
+            if self.direct:
+                self._check(self.L.rsrcu_store_depth_device(self.h, C.c_void_p(canvas.ptr)))
+            else:
+                self._emit(OP_STORE_DEPTH_DEV, struct.pack("<Q", int(canvas.ptr)))
+        else:
+            raise ValueError("true-colour canvases are stored with StoreColorDevice")
+
+    def WaitFor(self, producer: "GPU"):
+        """everything submitted to `producer` so far happens before anything submitted to this context from now on"""
+        self._check(self.L.rsrcu_wait_for(self.h, producer.h))
+
+    def KawaseBlur(self, src: "DeviceCanvas", dst: "DeviceCanvas", dist: int):
+        """rglr::KawaseBlurFilter (rglr_kawase.cxx:22-81) between two 'fp' canvases of one size"""
+        assert src.kind == "fp" and dst.kind == "fp" and src.shape == dst.shape
+        self._check(self.L.rsrcu_kawase_blur(self.h, C.c_void_p(src.ptr), src.width, C.c_void_p(dst.ptr), dst.width, src.width, src.height, int(dist)))
+
+    def Kawase(self, src: "DeviceCanvas", intensity: int, scratch=None) -> "DeviceCanvas":
+        """the `$kawase` node (node/kawase.cxx:83-129): `intensity` passes with dist 0 .. intensity - 1, ping-ponging
+        two canvases; returns the canvas holding the result (src itself when intensity == 0)"""
+        if intensity == 0:
+            return src
+        a, b = scratch if scratch else (self.Canvas("fp", src.width, src.height), self.Canvas("fp", src.width, src.height) if intensity > 1 else None)
+        s, d = src, a
+        first = True
+        for dist in range(intensity):
+            self.KawaseBlur(s, d, dist)
+            if first:
+                first = False
+                s = b
+            s, d = d, s
+        return s
+
+    def Glow(self, image: "DeviceCanvas", blur: "DeviceCanvas", dst, gamma: bool = True):
+        """the `$glow` node (node/glow.cxx:146-160): (image + blur * 0.7) * 0.5 -> true colour.  dst: (H, W) uint32
+        host array (written on return) or a 'tc' DeviceCanvas"""
+        assert image.kind == "quads" and blur.kind == "fp"
+        w, h = image.width, image.height
+        if isinstance(dst, DeviceCanvas):
+            self._check(self.L.rsrcu_glow(self.h, C.c_void_p(image.ptr), w // 2, C.c_void_p(blur.ptr), blur.width, int(bool(gamma)),
+                                          C.c_void_p(dst.ptr), 1, w, h, dst.width))
+        else:
+            assert dst.dtype == np.uint32 and dst.shape == (h, w)
+            self._check(self.L.rsrcu_glow(self.h, C.c_void_p(image.ptr), w // 2, C.c_void_p(blur.ptr), blur.width, int(bool(gamma)),
+                                          _ptr(dst), 0, w, h, dst.strides[0] // 4))
+
+    def MarchSurface(self, t: float, precision: int = 32, fork_depth: int = 2, rng: float = 5.0):
+        """the `$mc` node's geometry (node/mc.cxx:171-300) produced on the device.  Returns (soa, blocks, total): six
+        device addresses (x, y, z, nx, ny, nz arrays of `total` floats) and [(first_vertex, vertex_count)] per
+        non-empty block, in the reference's draw order"""
+        soa = (C.c_void_p * 6)()
+        blocks = (RsrMarchBlock * 4096)()
+        nb, total = C.c_int(0), C.c_int(0)
+        self._check(self.L.rsrcu_march_surface(self.h, float(t), int(precision), int(fork_depth), float(rng), soa, blocks, 4096, C.byref(nb), C.byref(total)))
+        return [int(p or 0) for p in soa], [(blocks[i].first_vertex, blocks[i].vertex_count) for i in range(nb.value)], total.value
+
+    def read_device(self, device_ptr: int, count: int, dtype=np.float32) -> np.ndarray:
+        out = np.empty(count, dtype)
+        self._check(self.L.rsrcu_canvas_read(self.h, C.c_void_p(device_ptr), _ptr(out), out.nbytes))
+        return out
+
+    def DrawSpans(self, target, left, top, xscale, spans):
+        """render_jobsys (viewer/jobsys_vis.cxx:26-90) into a 'tc' canvas: spans = [(start, end, raw, lane)]"""
+        arr = (RsrSpan * max(1, len(spans)))()
+        for i, s in enumerate(spans):
+            arr[i] = RsrSpan(float(s[0]), float(s[1]), int(s[2]) & 0xffffffff, int(s[3]))
+        self._check(self.L.rsrcu_draw_spans(self.h, C.c_void_p(target.ptr), target.width, target.width, target.height, int(left), int(top), float(xscale), arr, len(spans)))
+
+    def FrameSpans(self):
+        """the pipeline stages of the last profiled frame (set_profiling(2)) as spans, one lane per stage"""
+        arr = (RsrSpan * 8)()
+        n = C.c_int(0)
+        self._check(self.L.rsrcu_frame_spans(self.h, arr, 8, C.byref(n)))
+        return [(arr[i].start, arr[i].end, arr[i].raw, arr[i].lane) for i in range(n.value)]
+
+    def Present(self, src: "DeviceCanvas", surface: "DeviceCanvas"):
+        """device-to-device blit of a true-colour canvas into the presentation surface"""
+        self._check(self.L.rsrcu_present(self.h, C.c_void_p(src.ptr), src.width, C.c_void_p(surface.ptr), surface.width, src.width, src.height))
 
     # -- beyond the reference surface -------------------------------------------------------------
     def stats(self) -> dict:

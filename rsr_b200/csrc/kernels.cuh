@@ -192,6 +192,7 @@ __device__ __forceinline__ void run_vertex_program(const DevState& s, const Vert
 	case ProgOBJ2S::id:        shade_vertex<ProgOBJ2S>(s, vi, pos, vary, rsqrtLut); break;
 	case ProgEnvmap::id:       shade_vertex<ProgEnvmap>(s, vi, pos, vary, rsqrtLut); break;
 	case ProgWireframe::id:    shade_vertex<ProgWireframe>(s, vi, pos, vary, rsqrtLut); break;
+	case ProgBase::id:         shade_vertex<ProgBase>(s, vi, pos, vary, rsqrtLut); break;
 	default: pos[0] = pos[1] = pos[2] = 0.0f; pos[3] = 1.0f; break; } }
 
 __global__ void __launch_bounds__(256)

@@ -249,11 +249,17 @@ __device__ __forceinline__ float sample_depth(const DevState& st, float cx, floa
 // ShadeVertex: writes clip position and NV varyings.
 // ShadeFragment: attrs[k][lane]; writes colour (r,g,b,a)[lane]; may clear bits of `mask` (discard).
 
-struct ProgBase {   // rglv::BaseProgram
+struct ProgBase {   // rglv::BaseProgram (rglv_gpu_shaders.hxx:21-95): the depth-only program of the shadow-map pass (node/gllayer.cxx:44-45, :162-176)
 	static constexpr int id = 0;
 	static constexpr bool samples = false;   // fragment stage samples texture unit 0 (the tile kernel stages its TexDesc)
 	static constexpr bool earlyZ = true;
-	static constexpr int NV = 0; };
+	static constexpr int NV = 0;
+	__device__ static void ShadeVertex(const DevState& s, const VertexIn& v, float (&pos)[4], float*) {
+		mat4_mul(s.vpm, v.px, v.py, v.pz, 1.0f, pos[0], pos[1], pos[2], pos[3]); }
+	__device__ static void ShadeFragment(const FragIn&, const float (&)[kMaxVaryings][4],
+	                                     float (&r)[4], float (&g)[4], float (&b)[4], float (&a)[4], uint32_t&) {
+#pragma unroll
+		for (int l = 0; l < 4; ++l) { r[l] = 1.0f; g[l] = 1.0f; b[l] = 1.0f; a[l] = 1.0f; } } };
 
 struct ProgAmy : ProgBase {   // shaders.hxx:69-161
 	static constexpr int id = 4;

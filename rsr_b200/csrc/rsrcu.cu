@@ -4,6 +4,7 @@
 // tiles are CTAs of one grid launch, frames are ordered by the stream.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,8 @@
 
 #include "../../include/rsrcu.h"
 #include "tile_kernel.cuh"
+#include "post_kernels.cuh"
+#include "march_kernels.cuh"
 
 namespace rsr {
 void harvest_luts(uint32_t* rcp2048, uint32_t* rsqrt2048);
@@ -239,6 +242,15 @@ struct rsrcu_ctx {
 	std::chrono::steady_clock::time_point tBegin{};
 	uint64_t recordNs{0}, submitNs{0};
 	// RSRCU_HOST_PROF=1: where the submitting thread's time goes (averages printed by rsrcu_destroy)
+	// device canvases (rsrcu_canvas_alloc), cross-context ordering (rsrcu_wait_for), post filters, marching cubes
+	std::vector<void*> canvases;
+	cudaEvent_t evExt{nullptr};          // recorded on a producer context's stream; the next frame's first stream waits for it
+	bool extWaitPending{false};
+	DevBuf spanBuf, glowOut;
+	float stageStartMs[8]{};             // profiling level 2: time of evStage[i] after evStage[0]
+	bool stageSpansValid{false};
+	DevBuf mcBlocks, mcTotals, mcBase, mcVerts[3];   // rsrcu_march_surface
+	int mcTurn{0};
 	bool hostProf{false};
 	uint64_t hp[6]{};   // layout, tables, plan, reserve, launches, read-back enqueue (ns, summed)
 	uint64_t hpFrames{0};
@@ -274,7 +286,8 @@ bool drawProgramInstalled(int programId, int key) {
 		{41, 0x6e2}, {41, 0x62}, {41, 0x72},
 		{5, 0x62}, {6, 0x62}, {7, 0x62}, {8, 0x62}, {9, 0x62},
 		{11, 0x62},
-		{10, 0x22}, {10, 0x5a}, {10, 0x6e2}, {10, 0x62}, {10, 0x72}, {10, 0x50} };
+		{10, 0x22}, {10, 0x5a}, {10, 0x6e2}, {10, 0x62}, {10, 0x72}, {10, 0x50},
+		{0, 0x6a2} };   // BaseProgram, depth only: the shadow-map GPU of a `$layer` (src/viewer/node/gllayer.cxx:44-45)
 	for (const auto& e : table) { if (e.id == programId && e.key == key) { return true; } }
 	return false; }
 
@@ -368,6 +381,9 @@ bool floatRange(const float* p, size_t n, float& lo, float& hi) {
 
 int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef& out, bool wantRange = false) {
 	if (!host || bytes == 0) { out = DevRef{}; return RSRCU_OK; }
+	if (upload == RSRCU_UPLOAD_DEVICE) {   // already on the device (a canvas, marching-cubes output): used in place
+		out = DevRef{}; out.null = false; out.arena = false; out.abs = host;
+		return RSRCU_OK; }
 	if (upload == RSRCU_UPLOAD_STATIC) {
 		PtrCacheEntry& pe = c->ptrCache[ptrCacheIndex(host)];
 		if (pe.host == host && pe.bytes == bytes && (pe.ranged || !wantRange)) {
@@ -496,7 +512,7 @@ int snapshotState(rsrcu_ctx* c) {
 // kernel compiled for just those programs (registers are allotted for the programs present, not for the hungriest of all)
 using TileKernelFn = void (*)(const TileArgs);
 struct TileVariant { uint32_t progs; TileKernelFn fn; const char* name; };
-constexpr uint32_t kPAmy = prog_bit(ProgAmy::id), kPOBJ2 = prog_bit(ProgOBJ2::id), kPMany = prog_bit(ProgMany::id);
+constexpr uint32_t kPAmy = prog_bit(ProgAmy::id), kPOBJ2 = prog_bit(ProgOBJ2::id), kPMany = prog_bit(ProgMany::id), kPBase = prog_bit(ProgBase::id);
 #ifndef RSR_TILE_CTAS_AMY
 #define RSR_TILE_CTAS_AMY 3   // (4 CTAs / 64 registers: measured slower on c3 and c4, spills)
 #endif
@@ -504,6 +520,7 @@ constexpr uint32_t kPAmy = prog_bit(ProgAmy::id), kPOBJ2 = prog_bit(ProgOBJ2::id
 #define RSR_TILE_CTAS_LIT 4   // c2: 121 -> 117 us
 #endif
 const TileVariant kTileVariants[] = {
+	{ kPBase, tile_kernel<kPBase, RSR_TILE_CTAS_LIT>, "base (depth only)" },
 	{ kPAmy, tile_kernel<kPAmy, RSR_TILE_CTAS_AMY>, "amy" },
 	{ kPOBJ2 | kPMany, tile_kernel<kPOBJ2 | kPMany, RSR_TILE_CTAS_LIT>, "obj2+many" },
 	{ kPAmy | kPOBJ2 | kPMany, tile_kernel<kPAmy | kPOBJ2 | kPMany, RSR_TILE_CTAS_LIT>, "amy+obj2+many" },
@@ -620,6 +637,7 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	static const unsigned frontCtas = std::getenv("RSRCU_FRONT_CTAS") ? static_cast<unsigned>(std::atoi(std::getenv("RSRCU_FRONT_CTAS"))) : 444u;
 	const unsigned gridCap = (c->overlap && frontCtas > 0) ? frontCtas : 0xffffffffu;
 	g_pdl = !c->overlap || frontPdl;
+	if (c->extWaitPending) { CU(cudaStreamWaitEvent(st, c->evExt, 0)); c->extWaitPending = false; }   // rsrcu_wait_for: a producer context's canvases
 	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
@@ -726,6 +744,7 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->tileStream2, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&c->evGate, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&c->evExt, cudaEventDisableTiming));
 	{
 		int lo = 0, hi = 0;
 		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -788,6 +807,9 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 			else { std::fprintf(stderr, "rsrcu trace frame %2d: kernels %8.1f .. %8.1f us   read-back %8.1f .. %8.1f us\n", f, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f); } }
 		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
+	for (void* p : c->canvases) { cudaFree(p); }
+	for (DevBuf* b : { &c->spanBuf, &c->glowOut, &c->mcBlocks, &c->mcTotals, &c->mcBase, &c->mcVerts[0], &c->mcVerts[1], &c->mcVerts[2] }) { b->release(); }
+	if (c->evExt) { cudaEventDestroy(c->evExt); }
 	for (auto& w : c->sets) {
 		for (DevBuf* b : { &w.ptvb, &w.vflags, &w.triInfo, &w.triRecs, &w.clipRecs, &w.tileBase, &w.cellRel, &w.tileTotal, &w.tileOrder, &w.lists, &w.largeItems, &w.runScratch }) { b->release(); } }
 	for (auto& b : c->counters) { b.release(); }
@@ -1368,7 +1390,11 @@ int rsrcu_sync(rsrcu_ctx* c) {
 		if (c->profiling > 1) { for (int i = 0; i < 5; ++i) { cudaEventElapsedTime(&c->stageMs[i], c->evStage[i + 1], c->evStage[i + 2]); } }
 		cudaEventElapsedTime(&c->stageMs[5], c->evStage[6], c->evStage[7]);
 		// stage order of the header: vertex, setup, count, scan, fill, tile
-		cudaEventElapsedTime(&c->stageMs[6], c->evStage[0], c->evStage[7]); }
+		cudaEventElapsedTime(&c->stageMs[6], c->evStage[0], c->evStage[7]);
+		c->stageSpansValid = c->profiling > 1;
+		if (c->stageSpansValid) {
+			for (int i = 0; i < 8; ++i) {
+				if (cudaEventElapsedTime(&c->stageStartMs[i], c->evStage[0], c->evStage[i]) != cudaSuccess) { cudaGetLastError(); c->stageSpansValid = false; } } } }
 	return RSRCU_OK; }
 
 int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
@@ -1411,6 +1437,11 @@ int rsrcu_run_stream(rsrcu_ctx* c, const void* stream, size_t bytes) {
 		case RSRCU_OP_END_FRAME: r = rsrcu_end_frame(c); break;
 		case RSRCU_OP_STORE_TC_DEV: if (!need(24)) { goto bad; }
 			r = rsrcu_store_color_tc_device(c, i32(0), reinterpret_cast<void*>(u64(16)), i32(1), i32(2), i32(3)); break;
+		case RSRCU_OP_STORE_FP_DEV: if (!need(24)) { goto bad; }
+			r = rsrcu_store_color_fp_device(c, reinterpret_cast<void*>(u64(16)), i32(1), i32(2), i32(3), i32(0)); break;
+		case RSRCU_OP_STORE_QUADS_DEV: if (!need(24)) { goto bad; }
+			r = rsrcu_store_color_quads_device(c, reinterpret_cast<void*>(u64(16)), i32(1), i32(2), i32(3)); break;
+		case RSRCU_OP_STORE_DEPTH_DEV: if (!need(8)) { goto bad; } r = rsrcu_store_depth_device(c, reinterpret_cast<void*>(u64(0))); break;
 		default: return fail(RSRCU_ERR_INVALID, "unknown stream opcode %u", op); }
 		if (r != RSRCU_OK) { return r; }
 		p += size;
@@ -1448,6 +1479,326 @@ int rsrcu_join(rsrcu_ctx* c) {
 	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
 	CU(cudaSetDevice(c->device));
 	return joinTileStreams(c); }
+
+// ---- device canvases, post filters, presentation ----------------------------------------------
+
+int rsrcu_canvas_alloc(rsrcu_ctx* c, size_t bytes, void** devicePtr) {
+	if (!c || !devicePtr || bytes == 0) { return fail(RSRCU_ERR_INVALID, "null argument / empty canvas"); }
+	CU(cudaSetDevice(c->device));
+	void* p = nullptr;
+	CU(cudaMalloc(&p, bytes));
+	CU(cudaMemset(p, 0, bytes));
+	c->canvases.push_back(p);
+	*devicePtr = p;
+	return RSRCU_OK; }
+
+int rsrcu_canvas_free(rsrcu_ctx* c, void* devicePtr) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	auto it = std::find(c->canvases.begin(), c->canvases.end(), devicePtr);
+	if (it == c->canvases.end()) { return fail(RSRCU_ERR_INVALID, "not a canvas of this context"); }
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());   // (other contexts may still read it)
+	CU(cudaFree(devicePtr));
+	c->canvases.erase(it);
+	return RSRCU_OK; }
+
+int rsrcu_canvas_read(rsrcu_ctx* c, const void* devicePtr, void* hostDst, size_t bytes) {
+	if (!c || !devicePtr || !hostDst) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	CU(cudaMemcpyAsync(hostDst, devicePtr, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return RSRCU_OK; }
+
+int rsrcu_canvas_write(rsrcu_ctx* c, void* devicePtr, const void* hostSrc, size_t bytes) {
+	if (!c || !devicePtr || !hostSrc) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	CU(cudaMemcpyAsync(devicePtr, hostSrc, bytes, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return RSRCU_OK; }
+
+int rsrcu_store_color_fp_device(rsrcu_ctx* c, void* deviceDst, int width, int height, int stridePx, int half) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (!deviceDst) { return fail(RSRCU_ERR_INVALID, "null device destination"); }
+	const int wantW = half ? c->width / 2 : c->width, wantH = half ? c->height / 2 : c->height;
+	if (width != wantW || height != wantH) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != %s target %dx%d", width, height, half ? "half" : "full", wantW, wantH); }
+	if (stridePx < width) { return fail(RSRCU_ERR_INVALID, "canvas stride %d < width %d", stridePx, width); }
+	return pushCmd(c, half ? kCmdStoreHalfFP : kCmdStoreFP, 0, deviceDst, stridePx, 2); }
+
+int rsrcu_store_color_quads_device(rsrcu_ctx* c, void* deviceDst, int width, int height, int strideQuads) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (!deviceDst) { return fail(RSRCU_ERR_INVALID, "null device destination"); }
+	if (width != c->width || height != c->height) { return fail(RSRCU_ERR_INVALID, "store canvas %dx%d != target %dx%d", width, height, c->width, c->height); }
+	if (strideQuads < width / 2) { return fail(RSRCU_ERR_INVALID, "quad canvas stride %d < %d quads per row", strideQuads, width / 2); }
+	return pushCmd(c, kCmdStoreQuadsFP, 0, deviceDst, strideQuads, 2); }
+
+int rsrcu_store_depth_device(rsrcu_ctx* c, void* deviceDst) {
+	if (!c || !c->inFrame) { return fail(RSRCU_ERR_INVALID, "store outside begin/end frame"); }
+	if (!deviceDst) { return fail(RSRCU_ERR_INVALID, "null device destination"); }
+	return pushCmd(c, kCmdStoreDepth, 0, deviceDst, c->width, 3); }
+
+int rsrcu_wait_for(rsrcu_ctx* c, rsrcu_ctx* producer) {
+	if (!c || !producer) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (c == producer) { return RSRCU_OK; }
+	if (c->device != producer->device) { return fail(RSRCU_ERR_INVALID, "rsrcu_wait_for: contexts on devices %d and %d (use the completion counters across GPUs)", c->device, producer->device); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(producer); if (r != RSRCU_OK) { return r; } }
+	if (c->extWaitPending) {   // an earlier producer nobody has waited for yet: fold it into the context's stream first
+		CU(cudaStreamWaitEvent(c->stream, c->evExt, 0));
+		if (c->overlap) { CU(cudaStreamWaitEvent(c->frontStream, c->evExt, 0)); } }
+	CU(cudaEventRecord(c->evExt, producer->stream));
+	CU(cudaStreamWaitEvent(c->stream, c->evExt, 0));   // post filters and copies of this context
+	c->extWaitPending = true;                             // the next frame's front end (its own stream in overlap mode)
+	return RSRCU_OK; }
+
+int rsrcu_kawase_blur(rsrcu_ctx* c, const void* src, int srcStride, void* dst, int dstStride, int width, int height, int dist) {
+	if (!c || !src || !dst) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (src == dst) { return fail(RSRCU_ERR_INVALID, "rsrcu_kawase_blur: src and dst must differ (the reference ping-pongs two canvases, node/kawase.cxx:96-124)"); }
+	if (width <= 0 || height <= 0 || dist < 0 || srcStride < width || dstStride < width) { return fail(RSRCU_ERR_INVALID, "bad canvas geometry"); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	const dim3 grid(static_cast<unsigned>((width + 31) / 32), static_cast<unsigned>((height + 7) / 8));
+	kawase_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const float4*>(src), srcStride, static_cast<float4*>(dst), dstStride, width, height, dist);
+	CU(cudaGetLastError());
+	return RSRCU_OK; }
+
+int rsrcu_glow(rsrcu_ctx* c, const void* imageQuads, int imageStrideQuads, const void* blur, int blurStride, int gamma,
+               uint32_t* dst, int dstIsDevice, int width, int height, int stridePx) {
+	if (!c || !imageQuads || !blur || !dst) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (width <= 0 || height <= 0 || (width & 3) || (height & 1)) { return fail(RSRCU_ERR_INVALID, "glow: width must be a multiple of 4 and height of 2 (the filter walks 4x2 pixels, rglr_algorithm.hxx:129)"); }
+	if (imageStrideQuads < width / 2 || blurStride < width / 2 || stridePx < width) { return fail(RSRCU_ERR_INVALID, "bad canvas stride"); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	uint32_t* target = dst;
+	int targetStride = stridePx;
+	if (!dstIsDevice) {
+		CU(c->glowOut.reserve(static_cast<size_t>(width) * height * 4));
+		target = static_cast<uint32_t*>(c->glowOut.ptr); targetStride = width; }
+	const dim3 grid(static_cast<unsigned>((width / 4 + 31) / 32), static_cast<unsigned>((height / 2 + 7) / 8));
+	glow_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const float4*>(imageQuads), imageStrideQuads, static_cast<const float4*>(blur), blurStride,
+	                                         target, targetStride, width, height, gamma ? 1 : 0);
+	CU(cudaGetLastError());
+	c->shownTcDev = target; c->shownTcStride = targetStride;
+	if (!dstIsDevice) {
+		CU(cudaMemcpy2DAsync(dst, static_cast<size_t>(stridePx) * 4, target, static_cast<size_t>(targetStride) * 4, static_cast<size_t>(width) * 4,
+		                     static_cast<size_t>(height), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream)); }
+	return RSRCU_OK; }
+
+int rsrcu_draw_spans(rsrcu_ctx* c, void* truecolor, int stridePx, int width, int height, int left, int top, float xscale,
+                     const RsrSpan* spans, int count) {
+	if (!c || !truecolor || (count > 0 && !spans)) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (count <= 0) { return RSRCU_OK; }
+	static_assert(sizeof(RsrSpan) == sizeof(DevSpan), "span layout");
+	int lanes = 0;
+	for (int i = 0; i < count; ++i) {
+		if (spans[i].lane < 0 || spans[i].lane >= 4096) { return fail(RSRCU_ERR_INVALID, "span lane %d out of range", spans[i].lane); }
+		lanes = std::max(lanes, spans[i].lane + 1); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	CU(cudaStreamSynchronize(c->stream));   // (spanBuf may still be read by an earlier call; overlays are drawn once per presented frame)
+	CU(c->spanBuf.reserve(static_cast<size_t>(count) * sizeof(DevSpan)));
+	CU(cudaMemcpyAsync(c->spanBuf.ptr, spans, static_cast<size_t>(count) * sizeof(DevSpan), cudaMemcpyHostToDevice, c->stream));
+	// const auto scale = xscale * canvas.width();  (jobsys_vis.cxx:30)
+	const float scale = xscale * static_cast<float>(width);
+	spans_kernel<<<static_cast<unsigned>(lanes), 256, 0, c->stream>>>(static_cast<uint32_t*>(truecolor), stridePx, width, height, left, top, scale,
+	                                                                  static_cast<const DevSpan*>(c->spanBuf.ptr), count);
+	CU(cudaGetLastError());
+	return RSRCU_OK; }
+
+int rsrcu_frame_spans(rsrcu_ctx* c, RsrSpan* out, int capacity, int* count) {
+	if (!c || !out || !count) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	*count = 0;
+	if (!c->stageSpansValid) { return fail(RSRCU_ERR_INVALID, "no profiled frame: rsrcu_set_profiling(ctx, 2), render, rsrcu_sync"); }
+	// evStage: 0 start, 1 after upload, 2 after vertex, 3 after setup, 4 after count, 5 after scan, 6 after fill / tile start, 7 after tile
+	static const int from[6] = {0, 1, 2, 4, 5, 6}, to[6] = {1, 2, 3, 5, 6, 7};
+	for (int lane = 0; lane < 6 && *count < capacity; ++lane) {
+		const double a = static_cast<double>(c->stageStartMs[from[lane]]) * 1e-3, b = static_cast<double>(c->stageStartMs[to[lane]]) * 1e-3;
+		if (b <= a) { continue; }
+		out[*count] = RsrSpan{a, b, static_cast<uint32_t>(lane) * 0x9e3779b1u, lane};
+		++*count; }
+	return RSRCU_OK; }
+
+int rsrcu_present(rsrcu_ctx* c, const void* truecolor, int srcStride, void* surface, int surfaceStride, int width, int height) {
+	if (!c || !truecolor || !surface) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (width <= 0 || height <= 0 || srcStride < width || surfaceStride < width) { return fail(RSRCU_ERR_INVALID, "bad surface geometry"); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	CU(cudaMemcpy2DAsync(surface, static_cast<size_t>(surfaceStride) * 4, truecolor, static_cast<size_t>(srcStride) * 4, static_cast<size_t>(width) * 4,
+	                     static_cast<size_t>(height), cudaMemcpyDeviceToDevice, c->stream));
+	return RSRCU_OK; }
+
+// ---- marching cubes on the device (kernels in march_kernels.cuh) ---------------------------------------
+
+namespace {
+
+// Bourke's polygonise case table, packed (see march_kernels.cuh: kMcTri); printed by tools/gen_mc_table.py
+const uint64_t kMcTriHost[256] = {
+	0xffffffffffffffffull, 0xfffffffffffff380ull, 0xfffffffffffff910ull, 0xffffffffff189381ull,
+	0xfffffffffffffa21ull, 0xffffffffffa21380ull, 0xffffffffff920a29ull, 0xfffffff89a8a2382ull,
+	0xfffffffffffff2b3ull, 0xffffffffff0b82b0ull, 0xffffffffffb32091ull, 0xfffffffb89b912b1ull,
+	0xffffffffff3ab1a3ull, 0xfffffffab8a801a0ull, 0xfffffff9ab9b3093ull, 0xffffffffffb8aa89ull,
+	0xfffffffffffff874ull, 0xffffffffff437034ull, 0xffffffffff748910ull, 0xfffffff137174914ull,
+	0xffffffffff748a21ull, 0xfffffffa21403743ull, 0xfffffff748209a29ull, 0xffff4973727929a2ull,
+	0xffffffffff2b3748ull, 0xfffffff40242b74bull, 0xfffffffb32748109ull, 0xffff1292b9b49b74ull,
+	0xfffffff487ab31a3ull, 0xffff4b7401b41ab1ull, 0xffff30bab9b09874ull, 0xfffffffab99b4b74ull,
+	0xfffffffffffff459ull, 0xffffffffff380459ull, 0xffffffffff051450ull, 0xfffffff513538458ull,
+	0xffffffffff459a21ull, 0xfffffff594a21803ull, 0xfffffff204245a25ull, 0xffff8434535235a2ull,
+	0xffffffffffb32459ull, 0xfffffff594b802b0ull, 0xfffffffb32510450ull, 0xffff584b82852512ull,
+	0xfffffff45931ab3aull, 0xffffab81a8180594ull, 0xffff30bab5b05045ull, 0xfffffffb8aa85845ull,
+	0xffffffffff975879ull, 0xfffffff375359039ull, 0xfffffff751710870ull, 0xffffffffff753351ull,
+	0xfffffff21a759879ull, 0xffff37503505921aull, 0xffff25a758528208ull, 0xfffffff7533525a2ull,
+	0xfffffff2b3987597ull, 0xffffb72029279759ull, 0xffff751871810b32ull, 0xfffffff51771b12bull,
+	0xffffb3a31a758859ull, 0xf0aba010b7905075ull, 0xf07570805a30b0abull, 0xffffffffff5b75abull,
+	0xfffffffffffff56aull, 0xffffffffff6a5380ull, 0xffffffffff6a5109ull, 0xfffffff6a5891381ull,
+	0xffffffffff162561ull, 0xfffffff803621561ull, 0xfffffff620609569ull, 0xffff823625285895ull,
+	0xffffffffff56ab32ull, 0xfffffff56a02b80bull, 0xfffffff6a5b32910ull, 0xffffb892b92916a5ull,
+	0xfffffff315356b36ull, 0xffff6b51505b0b80ull, 0xffff9505606306b3ull, 0xfffffff89bb96956ull,
+	0xffffffffff8746a5ull, 0xfffffffa56374034ull, 0xfffffff7486a5091ull, 0xffff49737179156aull,
+	0xfffffff874156216ull, 0xffff743403625521ull, 0xffff620560509748ull, 0xf962695923497937ull,
+	0xfffffff56a4872b3ull, 0xffffb720242746a5ull, 0xffff6a5b32874910ull, 0xf6a54b7b492b9129ull,
+	0xffff6b51535b3748ull, 0xfb404b7b016b5b15ull, 0xf74836b630560950ull, 0xffff9b7974b96956ull,
+	0xffffffffffa4694aull, 0xfffffff380a946a4ull, 0xfffffff04606a10aull, 0xffffa16468618138ull,
+	0xfffffff462421941ull, 0xffff462942921803ull, 0xffffffffff624420ull, 0xfffffff624428238ull,
+	0xfffffff32b46a94aull, 0xffff6a4a94b82280ull, 0xffffa164606102b3ull, 0xf1b8b12184a16146ull,
+	0xffff36b319639469ull, 0xf14641916b0181b8ull, 0xfffffff4600636b3ull, 0xffffffffff86b846ull,
+	0xfffffffa98a876a7ull, 0xffffa76a907a0370ull, 0xffff0818717a176aull, 0xfffffff37117a76aull,
+	0xffff768981861621ull, 0xf937390976192962ull, 0xfffffff206607087ull, 0xffffffffff276237ull,
+	0xffff76898a86ab32ull, 0xf7a9a76790b72702ull, 0xfb32a767a1871081ull, 0xffff17616a71b12bull,
+	0xf63136b619768698ull, 0xffffffffff76b190ull, 0xffff06b0b3607087ull, 0xfffffffffffff6b7ull,
+	0xfffffffffffffb67ull, 0xffffffffff67b803ull, 0xffffffffff67b910ull, 0xfffffff67b138918ull,
+	0xffffffffff7b621aull, 0xfffffff7b6803a21ull, 0xfffffff7b69a2092ull, 0xffff89a38a3a27b6ull,
+	0xffffffffff726327ull, 0xfffffff026067807ull, 0xfffffff910732672ull, 0xffff678891681261ull,
+	0xfffffff73171a67aull, 0xffff801781a7167aull, 0xffff7a69a0a70730ull, 0xfffffff9a88a7a67ull,
+	0xffffffffff68b486ull, 0xfffffff640603b63ull, 0xfffffff109648b68ull, 0xffff63b139369649ull,
+	0xfffffff1a28b6486ull, 0xffff640b60b03a21ull, 0xffff9a2920b648b4ull, 0xf36463b34923a39aull,
+	0xfffffff264248328ull, 0xffffffffff264240ull, 0xffff834642432091ull, 0xfffffff642241491ull,
+	0xffff1a6648168318ull, 0xfffffff40660a01aull, 0xf39a9303a6834364ull, 0xffffffffff4a649aull,
+	0xffffffffffb67594ull, 0xfffffff67b594380ull, 0xfffffffb67045105ull, 0xffff51345343867bull,
+	0xfffffffb6721a459ull, 0xffff594380a217b6ull, 0xffff204a24a45b67ull, 0xf67b25a523453843ull,
+	0xfffffff945267327ull, 0xffff786260680459ull, 0xffff045051673263ull, 0xf851584812786826ull,
+	0xffff73167161a459ull, 0xf459078701671a61ull, 0xfa737a6a305a4a04ull, 0xffffa84a458a7a67ull,
+	0xfffffff98b9b6596ull, 0xffff590650360b63ull, 0xffffb65510b508b0ull, 0xfffffff1355363b6ull,
+	0xffff65b8b9b59a21ull, 0xfa21965690b603b0ull, 0xf52025a50865b58bull, 0xffff35a3a25363b6ull,
+	0xffff283265825985ull, 0xfffffff260069659ull, 0xf826283865081851ull, 0xffffffffff612651ull,
+	0xf698965683a61631ull, 0xffff06505960a01aull, 0xffffffffffa65830ull, 0xfffffffffffff65aull,
+	0xffffffffffb57a5bull, 0xfffffff03857ba5bull, 0xfffffff091ba57b5ull, 0xffff1381897ba57aull,
+	0xfffffff15717b21bull, 0xffffb27571721380ull, 0xffff7b2209729579ull, 0xf289823295b27257ull,
+	0xfffffff573532a52ull, 0xffff52a578258028ull, 0xffff2a37353a5109ull, 0xf25752a278129289ull,
+	0xffffffffff573531ull, 0xfffffff571170780ull, 0xfffffff735539309ull, 0xffffffffff795789ull,
+	0xfffffff8ba8a5485ull, 0xffff03bba50b5405ull, 0xffff54aba8a48910ull, 0xf41314943b54a4baull,
+	0xffff8548b2582152ull, 0xfb151b2b543b0b40ull, 0xf58b8545b2950520ull, 0xffffffffff3b2549ull,
+	0xffff483543253a52ull, 0xfffffff0244252a5ull, 0xf910854583a532a3ull, 0xffff2492914252a5ull,
+	0xfffffff153358548ull, 0xffffffffff501540ull, 0xffff530509358548ull, 0xfffffffffffff549ull,
+	0xfffffffba9b947b4ull, 0xffffba97b9794380ull, 0xffffb470414b1ba1ull, 0xf4bab474a1843413ull,
+	0xffff219b294b97b4ull, 0xf3801b2b197b9479ull, 0xfffffff04224b47bull, 0xffff42343824b47bull,
+	0xffff947732972a92ull, 0xf70207872a4797a9ull, 0xfa040a1a472a3a73ull, 0xffffffffff4782a1ull,
+	0xfffffff317714194ull, 0xffff178180714194ull, 0xffffffffff347304ull, 0xfffffffffffff784ull,
+	0xffffffffff8ba8a9ull, 0xfffffffa9bb93903ull, 0xfffffffba88a0a10ull, 0xffffffffffa3ba13ull,
+	0xfffffff8b99b1b21ull, 0xffff9b2921b93903ull, 0xffffffffffb08b20ull, 0xfffffffffffffb23ull,
+	0xfffffff98aa82832ull, 0xffffffffff2902a9ull, 0xffff8a1810a82832ull, 0xfffffffffffff2a1ull,
+	0xffffffffff819831ull, 0xfffffffffffff190ull, 0xfffffffffffff830ull, 0xffffffffffffffffull };
+
+struct McAabb { float ltb[3], rbf[3]; };
+
+// rmlv::mix(a, b, 0.5F) = (1 - t) * a + t * b (rmlv_math.hxx:87-89); this file is compiled without FMA contraction
+inline float mixHalf(float a, float b) { const float t = 0.5f; return (1.0f - t) * a + t * b; }
+
+// BlockDivider::Compute (src/viewer/node/mc.cxx:39-88): octants in the reference's order, midpoints by mix()
+void mcDivide(const McAabb& b, int limit, std::vector<McAabb>& out) {
+	if (limit == 0) { out.push_back(b); return; }
+	float mid[3];
+	for (int k = 0; k < 3; ++k) { mid[k] = mixHalf(b.ltb[k], b.rbf[k]); }
+	for (int o = 0; o < 8; ++o) {
+		McAabb s;
+		for (int k = 0; k < 3; ++k) {
+			const bool hi = (o >> k) & 1;   // bit 0: right half in x, bit 1: lower half in y, bit 2: front half in z
+			s.ltb[k] = hi ? mid[k] : b.ltb[k];
+			s.rbf[k] = hi ? b.rbf[k] : mid[k]; }
+		mcDivide(s, limit - 1, out); } }
+
+// Surface::sample(vec3) (mc.cxx:97-101) on the host: the block-level distance test of ResolveImpl (mc.cxx:241-245) is
+// taken here, with this host's libm like the reference
+float mcFieldHost(float px, float py, float pz, float T) {
+	const float distort = 0.60f * sinf(5.0f * (px + T / 4.0f)) * sinf(2.0f * (py + (T / 1.33f)));
+	const float len = sqrtf(px * px + py * py + pz * pz);
+	return (len - 3.0f) + (distort * sinf(T / 2.0f) + 1.0f); }
+
+}  // namespace
+
+int rsrcu_march_surface(rsrcu_ctx* c, float timeSeconds, int precision, int forkDepth, float range,
+                        const float** outSoa6, RsrMarchBlock* blocks, int blockCapacity, int* blockCount, int* vertexTotal) {
+	if (!c || !outSoa6 || !blocks || !blockCount || !vertexTotal) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (precision != 8 && precision != 16 && precision != 32 && precision != 64 && precision != 128) {
+		return fail(RSRCU_ERR_INVALID, "precision %d must be one of 8, 16, 32, 64, 128 (mc.cxx:344-354)", precision); }
+	if (forkDepth < 0 || forkDepth > 4) { return fail(RSRCU_ERR_INVALID, "forkDepth %d exceeds limit 0 .. 4 (mc.cxx:357-360)", forkDepth); }
+	if (!(range >= 0.0001f)) { return fail(RSRCU_ERR_INVALID, "range %g is too small (mc.cxx:363-366)", static_cast<double>(range)); }
+	const int dim = precision >> forkDepth;
+	if (dim < 1 || dim > kMcMaxDim) {
+		return fail(RSRCU_ERR_UNSUPPORTED, "%d cells per block edge: 1 .. %d supported (the reference's 64-wide slices hold dim + 1 values plus padding)", dim, kMcMaxDim); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	static std::once_flag once;
+	static cudaError_t tableErr = cudaSuccess;
+	std::call_once(once, [&]() { tableErr = cudaMemcpyToSymbol(kMcTri, kMcTriHost, sizeof(kMcTriHost)); });
+	CU(tableErr);
+
+	// Main (mc.cxx:171-193): the root block, its subdivision, one job per block -- here one CTA per block that passes
+	// the distance test
+	std::vector<McAabb> all;
+	mcDivide(McAabb{{-range, range, -range}, {range, -range, range}}, forkDepth, all);
+	std::vector<McBlock> active;
+	active.reserve(all.size());
+	for (const McAabb& b : all) {
+		const float delta = (b.rbf[0] - b.ltb[0]) / static_cast<float>(dim);
+		const float mx = mixHalf(b.ltb[0], b.rbf[0]), my = mixHalf(b.ltb[1], b.rbf[1]), mz = mixHalf(b.ltb[2], b.rbf[2]);
+		const float dx = b.ltb[0] - mx, dy = b.ltb[1] - my, dz = b.ltb[2] - mz;
+		const float R = sqrtf(dx * dx + dy * dy + dz * dz);
+		const float D = mcFieldHost(mx, my, mz, timeSeconds);
+		if (fabsf(D) * 0.5f > R) { continue; }
+		active.push_back(McBlock{b.ltb[0], b.ltb[1], b.ltb[2], delta}); }
+	*blockCount = 0; *vertexTotal = 0;
+	for (int k = 0; k < 6; ++k) { outSoa6[k] = nullptr; }
+	const int n = static_cast<int>(active.size());
+	if (n == 0) { return RSRCU_OK; }
+
+	CU(c->mcBlocks.reserve(static_cast<size_t>(n) * sizeof(McBlock)));
+	CU(c->mcTotals.reserve(static_cast<size_t>(n) * 4));
+	CU(c->mcBase.reserve(static_cast<size_t>(n + 1) * 4));
+	CU(cudaMemcpyAsync(c->mcBlocks.ptr, active.data(), static_cast<size_t>(n) * sizeof(McBlock), cudaMemcpyHostToDevice, c->stream));
+	McOut out{};
+	march_kernel<false><<<static_cast<unsigned>(n), 256, 0, c->stream>>>(static_cast<const McBlock*>(c->mcBlocks.ptr), timeSeconds, dim,
+		static_cast<uint32_t*>(c->mcTotals.ptr), nullptr, out);
+	march_scan_kernel<<<1, 256, 0, c->stream>>>(static_cast<const uint32_t*>(c->mcTotals.ptr), static_cast<uint32_t*>(c->mcBase.ptr), n);
+	CU(cudaGetLastError());
+	std::vector<uint32_t> totals(static_cast<size_t>(n)), base(static_cast<size_t>(n) + 1);
+	CU(cudaMemcpyAsync(totals.data(), c->mcTotals.ptr, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(base.data(), c->mcBase.ptr, static_cast<size_t>(n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	const uint32_t padded = base[static_cast<size_t>(n)];
+	if (padded == 0) { return RSRCU_OK; }
+	int nonEmpty = 0;
+	for (int i = 0; i < n; ++i) { nonEmpty += totals[static_cast<size_t>(i)] ? 1 : 0; }
+	if (nonEmpty > blockCapacity) { return fail(RSRCU_ERR_INVALID, "%d non-empty blocks, room for %d", nonEmpty, blockCapacity); }
+
+	// the vertex arrays rotate over three buffers like the node's (mc.cxx:115, :206-208): a frame still in flight keeps
+	// reading the arrays of the previous call
+	DevBuf& vb = c->mcVerts[c->mcTurn];
+	c->mcTurn = (c->mcTurn + 1) % 3;
+	CU(vb.reserve(static_cast<size_t>(padded) * 6 * 4));
+	CU(cudaMemsetAsync(vb.ptr, 0, static_cast<size_t>(padded) * 6 * 4, c->stream));   // the padding vertices are zeros (VertexArray_F3F3F3::pad)
+	for (int k = 0; k < 6; ++k) { out.a[k] = static_cast<float*>(vb.ptr) + static_cast<size_t>(k) * padded; outSoa6[k] = out.a[k]; }
+	march_kernel<true><<<static_cast<unsigned>(n), 256, 0, c->stream>>>(static_cast<const McBlock*>(c->mcBlocks.ptr), timeSeconds, dim,
+		nullptr, static_cast<const uint32_t*>(c->mcBase.ptr), out);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(c->stream));   // (frames may run their front end on another stream: the arrays are complete on return)
+	int nb = 0;
+	for (int i = 0; i < n; ++i) {
+		if (totals[static_cast<size_t>(i)]) { blocks[nb++] = RsrMarchBlock{static_cast<int32_t>(base[static_cast<size_t>(i)]), static_cast<int32_t>(totals[static_cast<size_t>(i)])}; } }
+	*blockCount = nb;
+	*vertexTotal = static_cast<int>(padded);
+	return RSRCU_OK; }
 
 int rsrcu_get_stats(rsrcu_ctx* c, RsrStats* out) {
 	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }

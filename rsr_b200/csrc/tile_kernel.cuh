@@ -597,8 +597,8 @@ __device__ __forceinline__ unsigned draw_batch(TileShared& sh, const TileArgs& A
 __host__ __device__ constexpr uint32_t prog_bit(int id) {
 	return id == ProgAmy::id ? 1u : id == ProgAlphaTexture::id ? 2u : id == ProgText::id ? 4u : id == ProgDepth::id ? 8u :
 	       id == ProgPattern::id ? 16u : id == ProgMany::id ? 32u : id == ProgOBJ1::id ? 64u : id == ProgOBJ2::id ? 128u :
-	       id == ProgOBJ2S::id ? 256u : id == ProgEnvmap::id ? 512u : id == ProgWireframe::id ? 1024u : 0u; }
-constexpr uint32_t kAllProgs = 0x7ffu;
+	       id == ProgOBJ2S::id ? 256u : id == ProgEnvmap::id ? 512u : id == ProgWireframe::id ? 1024u : id == ProgBase::id ? 2048u : 0u; }
+constexpr uint32_t kAllProgs = 0xfffu;
 // programs whose fragment stage samples texture unit 0 (P::samples)
 constexpr uint32_t kSamplingProgs = prog_bit(ProgAmy::id) | prog_bit(ProgAlphaTexture::id) | prog_bit(ProgText::id) | prog_bit(ProgPattern::id) | prog_bit(ProgEnvmap::id);
 
@@ -621,7 +621,8 @@ __device__ __forceinline__ unsigned draw_batch_any(TileShared& sh, const TileArg
 	draw_batch_if<PROGS, ProgOBJ1>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
 	draw_batch_if<PROGS, ProgOBJ2S>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
 	draw_batch_if<PROGS, ProgEnvmap>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
-	draw_batch_if<PROGS, ProgWireframe>(frags, sh, A, key0, base, nb, ox, oy, queued);
+	draw_batch_if<PROGS, ProgWireframe>(frags, sh, A, key0, base, nb, ox, oy, queued) ||
+	draw_batch_if<PROGS, ProgBase>(frags, sh, A, key0, base, nb, ox, oy, queued);
 	return frags; }
 
 // ---- IQPostProgram::ShadeCanvas (src/viewer/shaders.hxx:56-66) --------------------------------
