@@ -550,6 +550,97 @@ def stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# the post chain and the geometry producer that follow / feed a frame on the device
+# ---------------------------------------------------------------------------------------------------------
+
+def f_rows_subrecord(gpu, torch, local_rank, flush, args):
+    """Kawase blur, glow combine and marching cubes: device time per launch (CUDA events on the context's stream, 256 MiB
+    L2 flush before every launch), algorithmic bytes per launch and the fraction of the measured HBM copy peak; each is
+    compared with the reference's own function on this box first (bit for bit; marching-cubes normals to 2e-5)."""
+    import numpy as np
+    stream = torch.cuda.ExternalStream(gpu.stream(), device=local_rank)
+    peak = float(peaks().get("hbm_gbs", 0.0)) or 6550.7
+    rng = np.random.default_rng(3)
+    try:
+        from oracle import refgl
+        have_ref = refgl.available()
+        if have_ref:
+            refgl.init(min(16, os.cpu_count() or 1))
+    except Exception:
+        have_ref = False
+
+    def timed(fn, n=10):
+        tot = 0.0
+        for i in range(n + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                flush.fill_(i & 0xff)
+                e0.record(stream)
+            fn()
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            e1.synchronize()
+            if i >= 2:
+                tot += e0.elapsed_time(e1)
+        return tot / n
+
+    def rec(ms, nbytes, **kw):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return dict(ms=ms, algorithmic_bytes_per_launch=int(nbytes), achieved_gbs=gbs, peak_gbs=peak, frac=gbs / peak, **kw)
+
+    out = {"what": f_rows_subrecord.__doc__.split(":")[0].strip(), "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)"}
+    # -- `$kawase`: 16 B read + 16 B written per pixel and pass (the 16 overlapping taps are on-chip reuse) -----------
+    for w, h in ((960, 540), (3840, 2160)):
+        a, b = gpu.Canvas("fp", w, h), gpu.Canvas("fp", w, h)
+        src = rng.random((h, w, 4), dtype=np.float32)
+        a.write(src)
+        par = None
+        if have_ref and w == 960:
+            gpu.KawaseBlur(a, b, 2)
+            par = int(np.count_nonzero(b.read().view(np.uint32) != refgl.kawase_blur(src, 2).view(np.uint32)))
+        ms = timed(lambda: gpu.KawaseBlur(a, b, 2))
+        out[f"kawase_{w}x{h}"] = rec(ms, 32 * w * h, differing_floats_vs_reference=par)
+        a.free(); b.free()
+    # -- `$glow` at 1080p: 12 B (r, g, b planes of the quad canvas) + 4 B (one 16-byte blur pixel per quad) read, 4 B written per pixel
+    w, h = 1920, 1080
+    cq, cb, tc = gpu.Canvas("quads", w, h), gpu.Canvas("fp", w // 2, h // 2), gpu.Canvas("tc", w, h)
+    quads = rng.random((h // 2, w // 2, 4, 4), dtype=np.float32)
+    blur = rng.random((h // 2, w // 2, 4), dtype=np.float32)
+    cq.write(quads); cb.write(blur)
+    par = None
+    if have_ref:
+        gpu.Glow(cq, cb, tc, True)
+        par = int(np.count_nonzero(tc.read() != refgl.glow_filter(quads, blur, True)))
+    ms = timed(lambda: gpu.Glow(cq, cb, tc, True))
+    out["glow_1920x1080"] = rec(ms, 20 * w * h, differing_pixels_vs_reference=par)
+    for c in (cq, cb, tc):
+        c.free()
+    # -- `$mc`: precision 128, forkDepth 2 = 64 blocks of 32^3 cells; a blocking call (count pass, scan, counts to the host, emit pass)
+    t, precision, fork, rngv = 1.25, 128, 2, 5.0
+    gpu.MarchSurface(t, precision, fork, rngv)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        soa, blocks, total = gpu.MarchSurface(t, precision, fork, rngv)
+    wall_ms = (time.perf_counter() - t0) / reps * 1e3
+    tris = sum(n for _, n in blocks) // 3
+    mc = {"precision": precision, "fork_depth": fork, "cells": precision ** 3, "triangles": tris, "ms_wall_per_call": wall_ms,
+          "mcells_per_s": precision ** 3 / wall_ms / 1e3, "mtris_per_s": tris / wall_ms / 1e3}
+    if have_ref:
+        t0 = time.perf_counter()
+        pos, nrm, rblocks = refgl.march_surface(t, precision, fork, rngv)
+        ref_ms = (time.perf_counter() - t0) * 1e3
+        got = [gpu.read_device(p, total) for p in soa]
+        mc["parity"] = {"blocks_equal": rblocks == blocks,
+                        "differing_position_floats": int(sum(np.count_nonzero(got[k].view(np.uint32) != pos[k].view(np.uint32)) for k in range(3))),
+                        "max_normal_error": float(max(np.abs(got[3 + k] - nrm[k]).max() for k in range(3))), "normal_tolerance": 2e-5}
+        mc["cpu_baseline"] = {"ms": ref_ms, "cores": 1, "kind": "reference",
+                              "sample": "rglv::march_sdf_vao driven block after block by oracle/ref_harness.cpp on one core (the node spreads its 64 block jobs over the job system)"}
+    out["march_surface"] = mc
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 # C5: 8K split-frame
 # ---------------------------------------------------------------------------------------------------------
 
@@ -808,6 +899,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload == "f_rows":   # (developer shortcut: only the SURVEY 8(f) sub-record of the default line)
+        import torch
+        import rsr_b200
+        torch.cuda.set_device(local_rank)
+        gpu = rsr_b200.GPU(local_rank)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        print(json.dumps({"f_rows": f_rows_subrecord(gpu, torch, local_rank, flush, args)}), flush=True)
+        finish(0)
+
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -917,6 +1017,10 @@ def main():
                     extra[key] = stress_subrecord(key, args, gpu, torch, local_rank, flush, barrier)
                 except Exception as exc:
                     extra[key] = {"error": repr(exc)}
+            try:
+                extra["f_rows"] = f_rows_subrecord(gpu, torch, local_rank, flush, args)
+            except Exception as exc:
+                extra["f_rows"] = {"error": repr(exc)}
         else:
             rec = split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier, scene=wl.scene)
             if rank == 0:

@@ -12,25 +12,43 @@ namespace rsr {
 //   dst(x, y) = (0 + box(x-d-1, y-d-1) + box(x+d, y-d-1) + box(x-d-1, y+d) + box(x+d, y+d)) * (1/16)
 //   box(x, y) = ((in(x, y) + in(x+1, y)) + in(x, y+1)) + in(x+1, y+1), every coordinate clamped to the canvas
 // The reference runs an unclamped fast path in the interior; the taps are the same there, so one clamped path
-// reproduces both.  Algorithmic bytes: 16 read + 16 written per pixel; the 16 taps of neighbouring pixels overlap
-// and are served by L1 / L2.
+// reproduces both.  Algorithmic bytes: 16 read + 16 written per pixel; everything else is on-chip reuse.
+//
+// A thread owns one column and walks `rows` rows down it (4 .. 16: enough threads to fill the GPU on a small canvas, little warm-up on a large one) (lanes = consecutive columns: every load and store of a
+// warp is one contiguous 512-byte row segment).  The upper row of each of the four boxes at output row y is the lower
+// row of the same box at row y - 1, so it stays in registers: 8 instead of 16 128-bit taps per pixel.  (One thread
+// per pixel with all 16 taps was L1-bound: 79 % L1 throughput at 37 % of the HBM roofline, profiles/r2_post_kernels.txt.)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 f4_add(const float4 a, const float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_box(const float4 a, const float4 b, const float4 c, const float4 d) { return f4_add(f4_add(f4_add(a, b), c), d); }
 
-__global__ void __launch_bounds__(256)
-kawase_kernel(const float4* __restrict__ src, int srcStride, float4* __restrict__ dst, int dstStride, int width, int height, int d) {
-	const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-	if (x >= width || y >= height) { return; }
-	float4 ax = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const int sx = x + ((k & 1) ? d : -d - 1), sy = y + ((k & 2) ? d : -d - 1);
-		const int x0 = min(max(sx, 0), width - 1), x1 = min(max(sx + 1, 0), width - 1);
-		const size_t r0 = static_cast<size_t>(min(max(sy, 0), height - 1)) * srcStride, r1 = static_cast<size_t>(min(max(sy + 1, 0), height - 1)) * srcStride;
-		const float4 box = f4_add(f4_add(f4_add(__ldg(src + r0 + x0), __ldg(src + r0 + x1)), __ldg(src + r1 + x0)), __ldg(src + r1 + x1));
-		ax = f4_add(ax, box); }
+__global__ void __launch_bounds__(128)
+kawase_kernel(const float4* __restrict__ src, int srcStride, float4* __restrict__ dst, int dstStride, int width, int height, int d, int rows) {
+	const int x = blockIdx.x * 128 + threadIdx.x, y0 = blockIdx.y * rows;
+	if (x >= width) { return; }
+	const int y1 = min(y0 + rows, height);
+	// columns of the left (-d-1) and right (+d) boxes
+	const int xl0 = min(max(x - d - 1, 0), width - 1), xl1 = min(max(x - d, 0), width - 1);
+	const int xr0 = min(max(x + d, 0), width - 1), xr1 = min(max(x + d + 1, 0), width - 1);
+	auto rowOf = [&](int r) { return src + static_cast<size_t>(min(max(r, 0), height - 1)) * srcStride; };
+	const float4* rt = rowOf(y0 - d - 1);   // upper row of the two upper boxes
+	const float4* rb = rowOf(y0 + d);       // upper row of the two lower boxes
+	float4 tl0 = __ldg(rt + xl0), tl1 = __ldg(rt + xl1), tr0 = __ldg(rt + xr0), tr1 = __ldg(rt + xr1);
+	float4 bl0 = __ldg(rb + xl0), bl1 = __ldg(rb + xl1), br0 = __ldg(rb + xr0), br1 = __ldg(rb + xr1);
 	const float k16 = 1.0f / 16.0f;
-	dst[static_cast<size_t>(y) * dstStride + x] = make_float4(ax.x * k16, ax.y * k16, ax.z * k16, ax.w * k16); }
+	for (int y = y0; y < y1; ++y) {
+		rt = rowOf(y - d);
+		rb = rowOf(y + d + 1);
+		const float4 ntl0 = __ldg(rt + xl0), ntl1 = __ldg(rt + xl1), ntr0 = __ldg(rt + xr0), ntr1 = __ldg(rt + xr1);
+		const float4 nbl0 = __ldg(rb + xl0), nbl1 = __ldg(rb + xl1), nbr0 = __ldg(rb + xr0), nbr1 = __ldg(rb + xr1);
+		float4 ax = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		ax = f4_add(ax, f4_box(tl0, tl1, ntl0, ntl1));   // (-d-1, -d-1)
+		ax = f4_add(ax, f4_box(tr0, tr1, ntr0, ntr1));   // ( d,   -d-1)
+		ax = f4_add(ax, f4_box(bl0, bl1, nbl0, nbl1));   // (-d-1,  d)
+		ax = f4_add(ax, f4_box(br0, br1, nbr0, nbr1));   // ( d,    d)
+		dst[static_cast<size_t>(y) * dstStride + x] = make_float4(ax.x * k16, ax.y * k16, ax.z * k16, ax.w * k16);
+		tl0 = ntl0; tl1 = ntl1; tr0 = ntr0; tr1 = ntr1;
+		bl0 = nbl0; bl1 = nbl1; br0 = nbr0; br1 = nbr1; } }
 
 // ---------------------------------------------------------------------------------------------
 // `$glow`: rglr::Filter<GlowShader, sRGB | LinearColor> (rglr_algorithm.hxx:107-144, node/glow.cxx:24-39)
@@ -38,6 +56,9 @@ kawase_kernel(const float4* __restrict__ src, int srcStride, float4* __restrict_
 //   blur = ONE pixel of the linear canvas per quad, read at (x/2, y/2), its r / g / b broadcast over the quad.
 // One thread converts two horizontally adjacent quads (the reference's `sub` loop) and writes two 16-byte rows.
 // Algorithmic bytes per 4x2 pixels: 2 x 48 (image r,g,b planes) + 2 x 16 (blur) read, 32 written.
+// (Measured and not taken: a warp loading eight quads as 32 contiguous plane vectors, lane = quad * 4 + plane, with the
+// channels gathered by shuffle -- L1 throughput 62 -> 39 %, but every fourth lane converts an alpha plane nobody needs
+// and the kernel turns issue-bound: 20.4 instead of 15.5 us, profiles/README.md.)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 glow_kernel(const float4* __restrict__ image, int imageStrideQuads, const float4* __restrict__ blur, int blurStride,

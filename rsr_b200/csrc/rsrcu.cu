@@ -1558,8 +1558,10 @@ int rsrcu_kawase_blur(rsrcu_ctx* c, const void* src, int srcStride, void* dst, i
 	if (width <= 0 || height <= 0 || dist < 0 || srcStride < width || dstStride < width) { return fail(RSRCU_ERR_INVALID, "bad canvas geometry"); }
 	CU(cudaSetDevice(c->device));
 	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
-	const dim3 grid(static_cast<unsigned>((width + 31) / 32), static_cast<unsigned>((height + 7) / 8));
-	kawase_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const float4*>(src), srcStride, static_cast<float4*>(dst), dstStride, width, height, dist);
+	// rows per thread: about 300 k threads on a small canvas, at most 16 rows (the first row of a strip costs twice the loads)
+	const int rows = static_cast<int>(std::min<long long>(16, std::max<long long>(4, static_cast<long long>(width) * height / 300000)));
+	const dim3 grid(static_cast<unsigned>((width + 127) / 128), static_cast<unsigned>((height + rows - 1) / rows));
+	kawase_kernel<<<grid, 128, 0, c->stream>>>(static_cast<const float4*>(src), srcStride, static_cast<float4*>(dst), dstStride, width, height, dist, rows);
 	CU(cudaGetLastError());
 	return RSRCU_OK; }
 
@@ -1763,21 +1765,29 @@ int rsrcu_march_surface(rsrcu_ctx* c, float timeSeconds, int precision, int fork
 	const int n = static_cast<int>(active.size());
 	if (n == 0) { return RSRCU_OK; }
 
+	// slabs: enough CTAs to fill the GPU when there are few large blocks (a slab pays one extra slice: at least 2 layers)
+	const int slabLayers = std::min(dim, std::max(2, static_cast<int>(static_cast<long long>(dim) * n / 592)));
+	const int slabs = (dim + slabLayers - 1) / slabLayers;
+	const size_t nslab = static_cast<size_t>(n) * slabs;
 	CU(c->mcBlocks.reserve(static_cast<size_t>(n) * sizeof(McBlock)));
-	CU(c->mcTotals.reserve(static_cast<size_t>(n) * 4));
-	CU(c->mcBase.reserve(static_cast<size_t>(n + 1) * 4));
+	CU(c->mcTotals.reserve((nslab + static_cast<size_t>(n)) * 4));   // slab totals | block totals
+	CU(c->mcBase.reserve((nslab + 1) * 4));
+	uint32_t* dSlabTotals = static_cast<uint32_t*>(c->mcTotals.ptr);
+	uint32_t* dBlockTotals = dSlabTotals + nslab;
 	CU(cudaMemcpyAsync(c->mcBlocks.ptr, active.data(), static_cast<size_t>(n) * sizeof(McBlock), cudaMemcpyHostToDevice, c->stream));
 	McOut out{};
-	march_kernel<false><<<static_cast<unsigned>(n), 256, 0, c->stream>>>(static_cast<const McBlock*>(c->mcBlocks.ptr), timeSeconds, dim,
-		static_cast<uint32_t*>(c->mcTotals.ptr), nullptr, out);
-	march_scan_kernel<<<1, 256, 0, c->stream>>>(static_cast<const uint32_t*>(c->mcTotals.ptr), static_cast<uint32_t*>(c->mcBase.ptr), n);
+	march_kernel<false><<<static_cast<unsigned>(nslab), 256, 0, c->stream>>>(static_cast<const McBlock*>(c->mcBlocks.ptr), timeSeconds, dim, slabs, slabLayers,
+		dSlabTotals, nullptr, out);
+	march_scan_kernel<<<1, 256, 0, c->stream>>>(dSlabTotals, static_cast<uint32_t*>(c->mcBase.ptr), dBlockTotals, n, slabs);
 	CU(cudaGetLastError());
-	std::vector<uint32_t> totals(static_cast<size_t>(n)), base(static_cast<size_t>(n) + 1);
-	CU(cudaMemcpyAsync(totals.data(), c->mcTotals.ptr, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaMemcpyAsync(base.data(), c->mcBase.ptr, static_cast<size_t>(n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+	std::vector<uint32_t> totals(static_cast<size_t>(n)), slabBase(nslab + 1);
+	CU(cudaMemcpyAsync(totals.data(), dBlockTotals, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(slabBase.data(), c->mcBase.ptr, (nslab + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
-	const uint32_t padded = base[static_cast<size_t>(n)];
+	const uint32_t padded = slabBase[nslab];
 	if (padded == 0) { return RSRCU_OK; }
+	std::vector<uint32_t> base(static_cast<size_t>(n));
+	for (int i = 0; i < n; ++i) { base[static_cast<size_t>(i)] = slabBase[static_cast<size_t>(i) * slabs]; }
 	int nonEmpty = 0;
 	for (int i = 0; i < n; ++i) { nonEmpty += totals[static_cast<size_t>(i)] ? 1 : 0; }
 	if (nonEmpty > blockCapacity) { return fail(RSRCU_ERR_INVALID, "%d non-empty blocks, room for %d", nonEmpty, blockCapacity); }
@@ -1789,7 +1799,7 @@ int rsrcu_march_surface(rsrcu_ctx* c, float timeSeconds, int precision, int fork
 	CU(vb.reserve(static_cast<size_t>(padded) * 6 * 4));
 	CU(cudaMemsetAsync(vb.ptr, 0, static_cast<size_t>(padded) * 6 * 4, c->stream));   // the padding vertices are zeros (VertexArray_F3F3F3::pad)
 	for (int k = 0; k < 6; ++k) { out.a[k] = static_cast<float*>(vb.ptr) + static_cast<size_t>(k) * padded; outSoa6[k] = out.a[k]; }
-	march_kernel<true><<<static_cast<unsigned>(n), 256, 0, c->stream>>>(static_cast<const McBlock*>(c->mcBlocks.ptr), timeSeconds, dim,
+	march_kernel<true><<<static_cast<unsigned>(nslab), 256, 0, c->stream>>>(static_cast<const McBlock*>(c->mcBlocks.ptr), timeSeconds, dim, slabs, slabLayers,
 		nullptr, static_cast<const uint32_t*>(c->mcBase.ptr), out);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(c->stream));   // (frames may run their front end on another stream: the arrays are complete on return)
