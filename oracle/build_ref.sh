@@ -46,23 +46,52 @@ SRCS=(
   src/rgl/rglr/rglr_kawase.cxx
   src/rgl/rglv/rglv_marching_cubes.cxx
   src/viewer/jobsys_vis.cxx
+  src/viewer/compile.cxx
+  src/viewer/fontloader.cxx
+  src/rcl/rclx/rclx_gason_util.cxx
+  src/rcl/rclma/rclma_framepool.cxx
+  src/rml/rmlg/rmlg_noise.cxx
+  src/rgl/rglv/rglv_icosphere.cxx
+  src/rgl/rglv/rglv_camera.cxx
+  src/rgl/rglv/rglv_mesh_store.cxx
+  src/rgl/rglr/rglr_texture_load.cxx
+  src/rgl/rglr/rglr_texture_store.cxx
+  3rdparty/gason/gason.cpp
+  3rdparty/picopng/picopng.cpp
   src/viewer/shaders.cxx
   src/viewer/shaders_envmap.cxx
   src/viewer/shaders_wireframe.cxx
   3rdparty/fmt/src/format.cc
 )
+# the scene front-end: every node of src/viewer/node
+for f in "$REF"/src/viewer/node/*.cxx; do SRCS+=("src/viewer/node/$(basename "$f")"); done
 OBJS=()
 pids=()
+# the vendored Lua 5.4 (3rdparty/lua): the library for `$writer`'s font loader, the interpreter for scene.lua -> JSON
+LUAOBJS=()
+for f in "$REF"/3rdparty/lua/*.c; do
+  b="$(basename "$f" .c)"
+  case "$b" in lua|luac) continue;; esac
+  o="$OUT/obj/lua_$b.o"
+  LUAOBJS+=("$o")
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then gcc -O2 -fPIC -w -DLUA_USE_POSIX -c "$f" -o "$o" & pids+=($!); fi
+done
 for s in "${SRCS[@]}"; do
   o="$OUT/obj/$(echo "$s" | tr '/' '_').o"
   OBJS+=("$o")
   if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ] || [ "$HERE/ref_shim.h" -nt "$o" ]; then
-    "$CXX" "${FLAGS[@]}" -c "$REF/$s" -o "$o" &
+    extra=()
+    case "$s" in src/viewer/node/many.cxx|src/viewer/node/particles.cxx) extra=(-DRSR_FIXED_SEED);; esac
+    "$CXX" "${FLAGS[@]}" "${extra[@]}" -c "$REF/$s" -o "$o" &
     pids+=($!)
   fi
 done
 ho="$OUT/obj/ref_harness.o"
 "$CXX" "${FLAGS[@]}" -c "$HERE/ref_harness.cpp" -o "$ho" &
+pids+=($!)
+so="$OUT/obj/ref_scene.o"
+OBJS+=("$so")
+"$CXX" "${FLAGS[@]}" -c "$HERE/ref_scene.cpp" -o "$so" &
 pids+=($!)
 # POSIX stand-ins for the Windows-only string / path helpers the reference's OBJ loader calls (see the file's header)
 po="$OUT/obj/ref_posix_util.o"
@@ -70,7 +99,21 @@ OBJS+=("$po")
 "$CXX" "${FLAGS[@]}" -c "$HERE/ref_posix_util.cpp" -o "$po" &
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
-"$CXX" -shared -o "$OUT/librsr_ref.so" "${OBJS[@]}" "$ho" -lpthread
+OBJS+=("${LUAOBJS[@]}")
+"$CXX" -shared -o "$OUT/librsr_ref.so" "${OBJS[@]}" "$ho" -lpthread -ldl -Wl,--no-undefined
+
+# ---- bundled scenes as inputs: the reference's data/scene/*.lua -> JSON through its own host.lua ------------------
+# (outputs only under oracle/_ref/, git-ignored like the libraries: they travel to the GPU box with gpurun)
+gcc -O2 -w -DLUA_USE_POSIX "$REF/3rdparty/lua/lua.c" "${LUAOBJS[@]}" -o "$OUT/lua" -lm -ldl
+mkdir -p "$OUT/data/scene" "$OUT/data/mesh" "$OUT/data/texture" "$OUT/data/font"
+cp -f "$REF"/data/mesh/*.obj "$REF"/data/mesh/*.mtl "$OUT/data/mesh/"
+cp -f "$REF"/data/texture/*.png "$OUT/data/texture/"
+cp -f "$REF"/data/font/* "$OUT/data/font/" 2>/dev/null || true
+for sc in colortest tucker-and-dino instanced-cubes render-to-texture sdf-polygonization-1 particles oldschool plusrqdq auraforlaura writer; do
+  if [ -f "$REF/data/scene/$sc.lua" ]; then
+    (cd "$REF/data/scene" && "$OUT/lua" sc.lua "$sc.lua" > "$OUT/data/scene/$sc.json") || echo "build_ref.sh: scene $sc did not convert" >&2
+  fi
+done
 
 # ---- the compiled drop-in: the reference's own GL / GLState / command stream in front of librsrcu.so ------------
 # Same translation units, except that GPU::RunImpl's body (rglv_gpu.cxx:90-116) is compiled out and supplied by

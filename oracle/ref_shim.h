@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <optional>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -42,3 +43,20 @@ namespace rqdq { namespace rmlv {
 struct mvec4i;
 void load_interleaved_lut(const uint32_t*, mvec4i, mvec4i&);
 }}
+
+/* src/viewer/node/gllayer.cxx:144 calls std::cosf (MSVC has it; glibc's <cmath> only declares ::cosf) */
+namespace std { using ::cosf; }
+
+/* `$many` and `$particles` seed std::mt19937 from std::random_device (node/many.cxx:56, node/particles.cxx:50).  The
+ * scene parity tests render one scene through two libraries (pure reference / drop-in) and need the same scene in
+ * both, so those two translation units are compiled with -DRSR_FIXED_SEED: the seed is 1. */
+#ifdef RSR_FIXED_SEED
+namespace std {
+struct rsr_fixed_random_device {
+	using result_type = unsigned int;
+	result_type operator()() { return 1u; }
+	static constexpr result_type min() { return 0u; }
+	static constexpr result_type max() { return 0xffffffffu; } };
+}
+#define random_device rsr_fixed_random_device
+#endif

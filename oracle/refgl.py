@@ -104,6 +104,9 @@ def _bind(path):
         "ref_mc_tables": (None, [vp, vp, vp]),
         "ref_march_surface": (ci, [cf, ci, ci, cf, vp, vp, ci, vp, vp, ci, vp]),
         "ref_render_spans": (None, [vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, ci]),
+        "ref_scene_load": (vp, [C.c_char_p, C.c_char_p]),
+        "ref_scene_free": (None, [vp]),
+        "ref_scene_render": (ci, [vp, ci, ci, ci, ci, cf, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -465,3 +468,53 @@ def render_spans(canvas: np.ndarray, left: int, top: int, xscale: float, spans):
     lane = np.ascontiguousarray([s[3] for s in spans], dtype=np.int32)
     h, w = canvas.shape
     lib().ref_render_spans(_ptr(canvas), w, h, w, int(left), int(top), float(xscale), _ptr(se), _ptr(raw), _ptr(lane), len(spans))
+
+
+# -- the reference's scene front-end (Lua scene -> JSON -> node graph -> rglv::GPU) ----------------------
+
+DATA_ROOT = os.path.join(HERE, "_ref")          # holds data/{scene,mesh,texture,font}, copied / generated by build_ref.sh
+BUNDLED_SCENES = ("colortest", "tucker-and-dino", "instanced-cubes", "render-to-texture", "sdf-polygonization-1")
+
+
+def scene_path(name: str) -> str:
+    return os.path.join(DATA_ROOT, "data", "scene", name + ".json")
+
+
+def scenes_available() -> bool:
+    return available() and os.path.exists(scene_path("colortest"))
+
+
+class RefScene:
+    """A bundled data/scene/NAME.lua compiled by the reference's own node graph (src/viewer/compile.cxx, src/viewer/node/*)
+    and rendered the way src/viewer/perf.cxx does.  dropin=True runs the same node graph in librsr_dropin.so, where
+    rglv::GPU::RunImpl is the C-ABI binding in front of librsrcu.so: the bundled scene then renders on the GPU."""
+
+    def __init__(self, name: str, dropin: bool = False):
+        if dropin:
+            init_dropin()
+            self.L = dropin_lib()
+        else:
+            init()
+            self.L = lib()
+        self.name = name
+        cwd = os.getcwd()
+        os.chdir(DATA_ROOT)   # `$image` nodes open "data/texture/..." relative to the working directory
+        try:
+            self.h = self.L.ref_scene_load(os.fsencode(scene_path(name)), os.fsencode(os.path.join(DATA_ROOT, "data")))
+        finally:
+            os.chdir(cwd)
+        if not self.h:
+            raise RuntimeError(f"scene {name} did not compile / link")
+
+    def render(self, size, t: float = 0.0, tile_blocks=(8, 8)) -> np.ndarray:
+        w, h = size
+        out = np.zeros((h, w), np.uint32)
+        rc = self.L.ref_scene_render(self.h, w, h, int(tile_blocks[0]), int(tile_blocks[1]), float(t), _ptr(out))
+        if rc != 0:
+            raise RuntimeError(f"scene {self.name}: render failed ({rc})")
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.ref_scene_free(self.h)
+            self.h = None

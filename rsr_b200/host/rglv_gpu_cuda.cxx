@@ -108,10 +108,24 @@ void BindTextures(rsrcu_ctx* ctx, const GLState& st) {
 	if (st.tu3ptr != nullptr) {
 		RSRCU_DO(rsrcu_bind_depth_texture(ctx, st.tu3ptr, st.tu3dim, g_texturePolicy)); } }
 
+// The buffer slots a program's Loader dereferences (src/viewer/shaders.hxx, shaders_envmap.hxx, rglv_gpu_shaders.hxx:
+// LoadMD / LoadLane).  GLState::buffers keeps whatever an earlier draw bound to the other slots -- arrays that may be
+// shorter than this draw or gone already (the `$writer` node's text after a mesh) -- and the reference never reads
+// them; neither may the upload.
+unsigned SlotsOf(int programId) {
+	constexpr unsigned kPos = 0x007u, kNrm = 0x038u, kKd = 0x1c0u, kUv = 0x600u;
+	switch (programId) {
+	case 4: case 5: case 6: return kPos | kNrm | kUv;          // Amy, Depth, Many (+ slot 15, bound separately)
+	case 65: return kPos | kUv;                                  // AlphaTexture
+	case 26: return kPos | kKd | kUv;                            // Text
+	case 7: case 8: case 9: case 10: return kPos | kNrm | kKd;  // OBJ1, OBJ2, OBJ2S, Envmap
+	default: return kPos; } }                                    // BaseProgram, Pattern, Wireframe
+
 // vertex arrays: bound per draw, once the draw's extent is known
 void BindBuffers(rsrcu_ctx* ctx, const GLState& st, int nverts, int instances) {
+	const unsigned used = SlotsOf(st.programId);
 	for (int slot = 0; slot <= 10; ++slot) {
-		const float* p = st.buffers[slot];
+		const float* p = ((used >> slot) & 1u) ? st.buffers[slot] : nullptr;
 		RSRCU_DO(rsrcu_bind_buffer(ctx, slot, p, p != nullptr ? static_cast<size_t>(nverts) : 0, g_bufferPolicy)); }
 	const float* mats = st.buffers[15];
 	RSRCU_DO(rsrcu_bind_buffer(ctx, 15, instances > 0 ? mats : nullptr, (instances > 0 && mats != nullptr) ? static_cast<size_t>(instances) * 16 : 0, g_bufferPolicy)); }

@@ -63,3 +63,33 @@ def test_reference_span_bars(refgl):
     # lane 0: columns left + 20 .. left + 100, brightness 1 -> 0 (the last pixel is black); lane 2 sits 2 x (8 + 2) rows lower
     assert canvas[5:13, 30:110].all() and not canvas[13:15].any() and canvas[25:33, 50:69].all() and not canvas[:, :30].any()
     assert (canvas[5:13] == canvas[5]).all() and canvas[5, 30] > canvas[5, 60] > canvas[5, 100]
+
+
+def test_colortest_lua_through_the_node_graph_is_the_golden_frame(refgl):
+    """data/scene/colortest.lua -> JSON -> the reference's node graph -> its CPU rasteriser at 640x360 equals the frame
+    tests/golden/colortest_c1.npz holds (made earlier from hand-recorded GL calls of the same scene): the C1 gate is the
+    bundled scene itself"""
+    import pytest
+    if not refgl.scenes_available():
+        pytest.skip("bundled scenes not built (oracle/build_ref.sh with /root/reference present)")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "colortest_c1.npz"))
+    sc = refgl.RefScene("colortest")
+    try:
+        frame = sc.render((640, 360), 0.0)
+        assert np.array_equal(frame, g["frame"])
+        assert np.array_equal(sc.render((640, 360), 0.0, tile_blocks=(4, 4)), g["frame"])   # tile size does not matter
+    finally:
+        sc.close()
+
+
+def test_bundled_scenes_compile_link_and_render(refgl):
+    import pytest
+    if not refgl.scenes_available():
+        pytest.skip("bundled scenes not built")
+    for name in refgl.BUNDLED_SCENES:
+        sc = refgl.RefScene(name)
+        try:
+            a, b = sc.render((320, 180), 0.5), sc.render((320, 180), 0.5)
+            assert len(np.unique(a)) > 20 and np.array_equal(a, b), name
+        finally:
+            sc.close()
