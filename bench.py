@@ -640,6 +640,45 @@ def f_rows_subrecord(gpu, torch, local_rank, flush, args):
     return out
 
 
+def bundled_scenes_subrecord(seconds=2.5):
+    """SURVEY 8(f)1 / BASELINE.json configs[1]: the reference's bundled data/scene files, unmodified, through its own
+    front-end (Lua scene -> JSON -> node graph -> rglv::GL; oracle/ref_scene.cpp = perf.cxx's loop, doubleBuffer on) on
+    the CPU reference and -- same node graph, GPU::RunImpl replaced by the C-ABI binding -- on the GPU, 1920x1080.  Each
+    run is a process of its own (tools/scene_bench.py).  The node graph and the GL recording run on the host in both; the
+    ratio is what a user of the reference sees when librsr's RunImpl (and, for glow scenes, the three post nodes of
+    rsr_b200/host/post_nodes_cuda.cxx) change and nothing else.  dropin: every pointer GL recorded is staged once per
+    frame (exact under the reference's own contract); dropin_static_assets: textures and index arrays declared immutable
+    by the host (uploaded once), which holds for these three scenes."""
+    out = {"what": "bundled data/scene files through the reference's own node graph: CPU reference vs drop-in GPU::RunImpl, 1920x1080, doubleBuffer on",
+           "scenes": {}}
+    tool = os.path.join(ROOT, "tools", "scene_bench.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    for scene in ("colortest", "tucker-and-dino", "instanced-cubes"):
+        rec = {}
+        for lib in ("ref", "dropin", "dropin_static"):
+            try:
+                cmd = [sys.executable, tool, "--lib", lib.split("_")[0], "--scene", scene, "--seconds", str(seconds)]
+                if lib == "dropin_static":
+                    cmd.append("--static-assets")
+                p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=120)
+                lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+                if p.returncode != 0 or not lines:
+                    raise RuntimeError(f"exit code {p.returncode}: {p.stderr.strip()[-160:]}")
+                rec[lib] = json.loads(lines[-1])
+            except Exception as exc:
+                rec[lib] = {"error": repr(exc)}
+        if "frames_per_s" in rec.get("ref", {}) and "frames_per_s" in rec.get("dropin", {}):
+            out["scenes"][scene] = {"reference_frames_per_s": rec["ref"]["frames_per_s"], "cores": rec["ref"]["threads"],
+                                    "dropin_frames_per_s": rec["dropin"]["frames_per_s"],
+                                    "ratio": rec["dropin"]["frames_per_s"] / rec["ref"]["frames_per_s"],
+                                    "dropin_static_assets_frames_per_s": rec.get("dropin_static", {}).get("frames_per_s"),
+                                    "frames_timed": [rec["ref"]["frames"], rec["dropin"]["frames"]],
+                                    "frame_identical": rec["ref"]["crc32_frame_t1"] == rec["dropin"]["crc32_frame_t1"]}
+        else:
+            out["scenes"][scene] = rec
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # C5: 8K split-frame
 # ---------------------------------------------------------------------------------------------------------
@@ -905,7 +944,7 @@ def main():
         torch.cuda.set_device(local_rank)
         gpu = rsr_b200.GPU(local_rank)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
-        print(json.dumps({"f_rows": f_rows_subrecord(gpu, torch, local_rank, flush, args)}), flush=True)
+        print(json.dumps({"f_rows": f_rows_subrecord(gpu, torch, local_rank, flush, args), "bundled_scenes": bundled_scenes_subrecord()}), flush=True)
         finish(0)
 
     if args.impl == "reference":
@@ -1021,6 +1060,11 @@ def main():
                 extra["f_rows"] = f_rows_subrecord(gpu, torch, local_rank, flush, args)
             except Exception as exc:
                 extra["f_rows"] = {"error": repr(exc)}
+            if not args.no_cpu_baseline:
+                try:
+                    extra["bundled_scenes"] = bundled_scenes_subrecord()
+                except Exception as exc:
+                    extra["bundled_scenes"] = {"error": repr(exc)}
         else:
             rec = split_frame(args, gpu, torch, dist, rank, local_rank, world, flush, barrier, scene=wl.scene)
             if rank == 0:

@@ -59,6 +59,9 @@ extern "C" {
 /* upload policy for rsrcu_bind_buffer / rsrcu_bind_texture / index data */
 #define RSRCU_UPLOAD_ALWAYS 0   /* contents may have changed since the last call: copy again */
 #define RSRCU_UPLOAD_STATIC 1   /* (pointer, size) identifies immutable data: copy once, then reuse */
+#define RSRCU_UPLOAD_FRAME 3    /* contents stay as they are until rsrcu_end_frame -- the reference's own contract (GL records
+                                   pointers, the renderer reads them at Run): staged once per frame however often the
+                                   pointer is bound (the drop-in binding's default) */
 #define RSRCU_UPLOAD_DEVICE 2   /* the pointer IS device memory on the context's device (a canvas of rsrcu_canvas_alloc,
                                    the output of rsrcu_march_surface, any CUDA allocation): used in place, nothing is
                                    copied.  The caller orders producer and consumer (same context: stream order;

@@ -123,14 +123,16 @@ RSRCU_DIR="$(cd "$HERE/../rsr_b200" && pwd)"
 if [ -f "$RSRCU_DIR/librsrcu.so" ]; then
   DOBJS=()
   for o in "${OBJS[@]}"; do
-    case "$o" in *src_rgl_rglv_rglv_gpu.cxx.o) ;; *) DOBJS+=("$o");; esac
+    # (GPU::RunImpl comes from rglv_gpu_cuda.cxx; the `$buffers` / `$kawase` / `$glow` nodes from post_nodes_cuda.cxx)
+    case "$o" in *src_rgl_rglv_rglv_gpu.cxx.o|*src_viewer_node_buffers.cxx.o|*src_viewer_node_kawase.cxx.o|*src_viewer_node_glow.cxx.o) ;; *) DOBJS+=("$o");; esac
   done
   "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -c "$OUT/overlay/dropin/rglv_gpu.cxx" -o "$OUT/obj/dropin_rglv_gpu.o" &
   "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -I"$HERE/../include" -c "$RSRCU_DIR/host/rglv_gpu_cuda.cxx" -o "$OUT/obj/dropin_rglv_gpu_cuda.o" &
   "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -c "$HERE/ref_harness.cpp" -o "$OUT/obj/dropin_ref_harness.o" &
+  "$CXX" "${FLAGS[@]}" -DRSR_CUDA_RUNIMPL -I"$HERE/../include" -c "$RSRCU_DIR/host/post_nodes_cuda.cxx" -o "$OUT/obj/dropin_post_nodes_cuda.o" &
   wait
   "$CXX" -shared -o "$OUT/librsr_dropin.so" "${DOBJS[@]}" "$OUT/obj/dropin_rglv_gpu.o" "$OUT/obj/dropin_rglv_gpu_cuda.o" \
-      "$OUT/obj/dropin_ref_harness.o" -L"$RSRCU_DIR" -lrsrcu -Wl,-rpath,'$ORIGIN/../../rsr_b200' -lpthread
+      "$OUT/obj/dropin_post_nodes_cuda.o" "$OUT/obj/dropin_ref_harness.o" -L"$RSRCU_DIR" -lrsrcu -Wl,-rpath,'$ORIGIN/../../rsr_b200' -lpthread
   echo "build_ref.sh: built $OUT/librsr_dropin.so"
 else
   echo "build_ref.sh: rsr_b200/librsrcu.so not built yet, skipping librsr_dropin.so" >&2

@@ -10,6 +10,7 @@
  * those ~60 lines of perf.cxx (its main() cannot be linked into a library and its mesh-store call is stale,
  * `load_dir`); every node, the compiler, the linker and the renderers underneath are the reference's own code.
  * tests/test_scenes_gpu.py renders the bundled scenes through both libraries and compares the frames bit for bit. */
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -120,5 +121,39 @@ int ref_scene_render(void* h, int w, int hgt, int tileX, int tileY, float t, uin
 	jobsys::wait(rootJob);
 	jobsys::work_end();
 	return 0; }
+
+/* perf.cxx's timed loop (Application::Main :207-232): `frames` frames at t0, t0 + dt, ... between one work_start /
+ * work_end, with the reference's default doubleBuffer mode if asked (a frame's pixels then land one Run later, which is
+ * what a viewer sees too).  Returns the elapsed seconds. */
+double ref_scene_bench(void* h, int w, int hgt, int tileX, int tileY, int frames, float t0, float dt, int doubleBuffer, uint32_t* out) {
+	auto* s = static_cast<Scene*>(h);
+	rglr::TrueColorCanvas canvas(reinterpret_cast<PixelToaster::TrueColorPixel*>(out), w, hgt);
+	s->globals->Upsert("windowSize", rmlv::vec2(float(w), float(hgt)));
+	s->globals->Upsert("tileSize", rmlv::vec2(float(tileX), float(tileY)));
+	s->globals->Upsert("windowAspect", w / float(hgt));
+	const std::string_view selector{"root"};
+	const auto match = rclr::find_if(s->nodes, [=](const auto& node) { return node->get_id() == selector; });
+	if (match == end(s->nodes)) { return -1.0; }
+	auto* node = dynamic_cast<rqv::IOutput*>(match->get());
+	if (node == nullptr) { return -1.0; }
+	rglv::doubleBuffer = doubleBuffer != 0;
+	jobsys::work_start();
+	const auto begin = std::chrono::steady_clock::now();
+	for (int fn = 0; fn < frames; ++fn) {
+		s->globals->Upsert("wallclock", t0 + dt * float(fn));
+		jobsys::reset();
+		framepool::Reset();
+		auto rootJob = jobsys::make_job(jobsys::noop);
+		for (auto& n : s->nodes) { n->Reset(); }
+		rqv::ComputeIndegreesFrom(node);
+		node->set_indegreeWaitCnt(1);
+		node->SetOutputCanvas(&canvas);
+		node->AddLink(rootJob);
+		node->Run();
+		jobsys::wait(rootJob); }
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
+	jobsys::work_end();
+	rglv::doubleBuffer = false;
+	return secs; }
 
 }  // extern "C"

@@ -107,6 +107,7 @@ def _bind(path):
         "ref_scene_load": (vp, [C.c_char_p, C.c_char_p]),
         "ref_scene_free": (None, [vp]),
         "ref_scene_render": (ci, [vp, ci, ci, ci, ci, cf, vp]),
+        "ref_scene_bench": (C.c_double, [vp, ci, ci, ci, ci, ci, cf, cf, ci, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -150,7 +151,7 @@ def init(threads: int | None = None) -> int:
     return _threads
 
 
-def init_dropin(threads: int = 2) -> int:
+def init_dropin(threads: int = 2) -> int:  # noqa: E302
     """the drop-in library carries its own copy of the job system (GPU::Run is a job): a small pool is enough"""
     global _dropin_threads
     if _dropin_threads is None:
@@ -513,6 +514,16 @@ class RefScene:
         if rc != 0:
             raise RuntimeError(f"scene {self.name}: render failed ({rc})")
         return out
+
+    def bench(self, size, frames: int, t0: float = 0.0, dt: float = 1.0 / 60.0, double_buffer: bool = True, tile_blocks=(8, 8)) -> float:
+        """perf.cxx's timed loop: seconds for `frames` frames of the animation (the reference's doubleBuffer default)"""
+        w, h = size
+        out = np.zeros((h, w), np.uint32)
+        secs = self.L.ref_scene_bench(self.h, w, h, int(tile_blocks[0]), int(tile_blocks[1]), int(frames), float(t0), float(dt),
+                                      int(bool(double_buffer)), _ptr(out))
+        if secs < 0:
+            raise RuntimeError(f"scene {self.name}: no output node")
+        return secs
 
     def close(self):
         if self.h:

@@ -89,6 +89,7 @@ struct StaticAlloc { void* dev; size_t bytes; float lo, hi; bool ranged; };   //
 
 // direct-mapped front of the static cache: a frame binds the same few hundred pointers thousands of times
 struct PtrCacheEntry { const void* host; size_t bytes; void* dev; float lo, hi; bool ranged; };
+struct FrameCacheEntry { const void* host{nullptr}; size_t bytes{0}; size_t off{0}; uint64_t stamp{0}; };   // RSRCU_UPLOAD_FRAME: staged once per frame
 constexpr size_t kPtrCacheSize = 2048;
 inline size_t ptrCacheIndex(const void* p) { return static_cast<size_t>((reinterpret_cast<uintptr_t>(p) >> 4) * 0x9E3779B97F4A7C15ull >> 53); }
 
@@ -202,6 +203,8 @@ struct rsrcu_ctx {
 	cudaEvent_t arenaFree[kSlots]{};
 	std::unordered_map<const void*, StaticAlloc> staticCache;
 	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr, 0.0f, 0.0f, false});
+	std::vector<FrameCacheEntry> frameCache = std::vector<FrameCacheEntry>(kPtrCacheSize);
+	uint64_t frameStamp{0};            // bumped by rsrcu_begin_frame: entries of earlier frames are stale without clearing
 	float guardFactor{1.0f};
 	uint64_t drawsCulled{0};
 	uint32_t progMask{0};
@@ -407,6 +410,18 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 		c->staticCache[host] = sa;
 		pe = PtrCacheEntry{host, bytes, d, sa.lo, sa.hi, sa.ranged};
 		out.null = false; out.arena = false; out.abs = d; out.lo = sa.lo; out.hi = sa.hi; out.ranged = sa.ranged;
+		return RSRCU_OK; }
+	if (upload == RSRCU_UPLOAD_FRAME) {
+		// the reference's own contract: GL records the pointer, the renderer reads it at Run -- every bind of one pointer
+		// inside a frame sees the same bytes, so they are staged once (a field of 576 quads binds its two textures 576 times)
+		FrameCacheEntry& fe = c->frameCache[ptrCacheIndex(host)];
+		if (fe.stamp == c->frameStamp && fe.host == host && fe.bytes >= bytes) {
+			out.null = false; out.arena = true; out.off = fe.off; out.ranged = false;
+			return RSRCU_OK; }
+		size_t off = 0;
+		CU(c->arenas[c->outSlot].push(host, bytes, off));
+		fe = FrameCacheEntry{host, bytes, off, c->frameStamp};
+		out.null = false; out.arena = true; out.off = off; out.ranged = false;
 		return RSRCU_OK; }
 	size_t off = 0;
 	CU(c->arenas[c->outSlot].push(host, bytes, off));
@@ -889,6 +904,7 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->launched[c->outSlot] = Launched{};
 	c->storesUsed = 0; c->tcDev = nullptr;
 	c->arenas[c->outSlot].used = 0;
+	++c->frameStamp;
 	c->trianglesSubmitted = 0; c->inputBytes = 0; c->progMask = 0;
 	c->haveState = false; c->stateDirty = true;
 	for (auto& b : c->curBuffers) { b = DevRef{}; }

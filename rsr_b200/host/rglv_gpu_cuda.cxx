@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 
@@ -51,7 +52,29 @@ std::unordered_map<const GPU*, CudaSide> g_side;
 int g_device = 0;
 // what may be assumed about the memory behind the pointers GL recorded: nothing by default (copied every frame);
 // a host that knows its meshes / textures are immutable says so (rsr_dropin_set_upload_policy)
-int g_bufferPolicy = RSRCU_UPLOAD_ALWAYS, g_texturePolicy = RSRCU_UPLOAD_ALWAYS, g_indexPolicy = RSRCU_UPLOAD_ALWAYS;
+// (RSRCU_UPLOAD_FRAME: the reference reads every pointer at Run, so one staging per frame and pointer is exact)
+int g_bufferPolicy = RSRCU_UPLOAD_FRAME, g_texturePolicy = RSRCU_UPLOAD_FRAME, g_indexPolicy = RSRCU_UPLOAD_FRAME;
+
+// Canvases that live on the device (rsr_b200/host/post_nodes_cuda.cxx: the `$buffers` / `$kawase` / `$glow` chain).
+// A device canvas is an ordinary rglr canvas object around memory from CudaCanvasAlloc; GL::StoreColor(&canvas) is
+// recorded as always, and the store commands below turn into the _device variants when the canvas's memory is in
+// this table.  `writer` is the context whose stream wrote the canvas last: a filter that reads it runs there.
+struct DeviceRange { size_t bytes; rsrcu_ctx* writer; };
+std::map<uintptr_t, DeviceRange> g_deviceCanvases;   // by start address (g_sideMutex)
+rsrcu_ctx* g_utilityCtx = nullptr;                    // owns the canvas memory (any context of the device may use it)
+
+DeviceRange* FindDeviceRange(const void* p) {
+	const auto a = reinterpret_cast<uintptr_t>(p);
+	auto it = g_deviceCanvases.upper_bound(a);
+	if (it == g_deviceCanvases.begin()) { return nullptr; }
+	--it;
+	return a < it->first + it->second.bytes ? &it->second : nullptr; }
+
+bool IsDeviceCanvas(const void* p, rsrcu_ctx* writer) {
+	std::lock_guard<std::mutex> lock(g_sideMutex);
+	DeviceRange* r = FindDeviceRange(p);
+	if (r != nullptr) { r->writer = writer; }
+	return r != nullptr; }
 
 [[noreturn]] void Die(const char* what) {
 	// same policy as a missing dispatch entry in the reference (rglv_gpu.cxx:199-202)
@@ -165,15 +188,18 @@ void SubmitFrame(CudaSide& side, GL& gl, rmlv::ivec2 sizeInPixels, rmlv::ivec2 t
 			break;
 		case CMD_STORE_COLOR_HALF_LINEAR_FP: {
 			auto* c = static_cast<rglr::FloatingPointCanvas*>(cs.consumePtr());
-			RSRCU_DO(rsrcu_store_color_fp(ctx, reinterpret_cast<float*>(c->data()), c->width(), c->height(), c->stride(), 1)); }
+			if (IsDeviceCanvas(c->data(), ctx)) { RSRCU_DO(rsrcu_store_color_fp_device(ctx, c->data(), c->width(), c->height(), c->stride(), 1)); }
+			else { RSRCU_DO(rsrcu_store_color_fp(ctx, reinterpret_cast<float*>(c->data()), c->width(), c->height(), c->stride(), 1)); } }
 			break;
 		case CMD_STORE_COLOR_FULL_LINEAR_FP: {
 			auto* c = static_cast<rglr::FloatingPointCanvas*>(cs.consumePtr());
-			RSRCU_DO(rsrcu_store_color_fp(ctx, reinterpret_cast<float*>(c->data()), c->width(), c->height(), c->stride(), 0)); }
+			if (IsDeviceCanvas(c->data(), ctx)) { RSRCU_DO(rsrcu_store_color_fp_device(ctx, c->data(), c->width(), c->height(), c->stride(), 0)); }
+			else { RSRCU_DO(rsrcu_store_color_fp(ctx, reinterpret_cast<float*>(c->data()), c->width(), c->height(), c->stride(), 0)); } }
 			break;
 		case CMD_STORE_COLOR_FULL_QUADS_FP: {
 			auto* c = static_cast<rglr::QFloat4Canvas*>(cs.consumePtr());
-			RSRCU_DO(rsrcu_store_color_quads(ctx, reinterpret_cast<float*>(c->data()), c->width(), c->height(), c->stride())); }
+			if (IsDeviceCanvas(c->data(), ctx)) { RSRCU_DO(rsrcu_store_color_quads_device(ctx, c->data(), c->width(), c->height(), c->stride())); }
+			else { RSRCU_DO(rsrcu_store_color_quads(ctx, reinterpret_cast<float*>(c->data()), c->width(), c->height(), c->stride())); } }
 			break;
 		case CMD_STORE_COLOR_FULL_LINEAR_TC: {
 			const auto enableGamma = cs.consumeByte();
@@ -251,6 +277,29 @@ void CudaFlush(const GPU* gpu) {
 	if (auto it = g_side.find(gpu); it != g_side.end() && it->second.ctx != nullptr) {
 		RSRCU_DO(rsrcu_sync(it->second.ctx));
 		it->second.frameInFlight = false; } }
+
+// ---- device canvases (see g_deviceCanvases) ---------------------------------------------------------------------
+void* CudaCanvasAlloc(size_t bytes) {
+	std::lock_guard<std::mutex> lock(g_sideMutex);
+	if (g_utilityCtx == nullptr) {
+		if (const char* dev = std::getenv("RSRCU_DEVICE")) { g_device = std::atoi(dev); }
+		RSRCU_DO(rsrcu_create(g_device, &g_utilityCtx)); }
+	void* p = nullptr;
+	RSRCU_DO(rsrcu_canvas_alloc(g_utilityCtx, bytes, &p));
+	g_deviceCanvases[reinterpret_cast<uintptr_t>(p)] = DeviceRange{bytes, nullptr};
+	return p; }
+
+void CudaCanvasFree(void* p) {
+	std::lock_guard<std::mutex> lock(g_sideMutex);
+	if (p != nullptr && g_deviceCanvases.erase(reinterpret_cast<uintptr_t>(p)) != 0) { RSRCU_DO(rsrcu_canvas_free(g_utilityCtx, p)); } }
+
+// the context whose stream wrote the device canvas last (a store command of its frame, or a filter run on it)
+rsrcu_ctx* CudaWriterOf(const void* p) {
+	std::lock_guard<std::mutex> lock(g_sideMutex);
+	DeviceRange* r = FindDeviceRange(p);
+	return r != nullptr ? r->writer : nullptr; }
+
+void CudaNoteWriter(const void* p, rsrcu_ctx* ctx) { IsDeviceCanvas(p, ctx); }
 
 void CudaSetUploadPolicy(int buffers, int textures, int indices) {
 	g_bufferPolicy = buffers; g_texturePolicy = textures; g_indexPolicy = indices; }
