@@ -459,31 +459,60 @@ __device__ __forceinline__ void bin_item(bool valid, uint32_t packed, uint32_t o
 	// medium-sized triangles of ordinary frames, whose short lists do not need runs.)
 	const bool walked = small && ntile <= 4 && fp.groups > 1;
 	if (fp.groups > 1) {
-		int cx = tx0, cy = ty0;
-		uint32_t cur = walked ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu;
-		while (true) {
-			const uint32_t tile = __reduce_min_sync(0xffffffffu, cur);
-			if (tile == 0xffffffffu) { break; }
-			const int leader = __ffs(__ballot_sync(0xffffffffu, cur == tile)) - 1;
-			const uint32_t g = __shfl_sync(0xffffffffu, group | (code & kFanIdBit), leader);   // (lanes differ in group only among clip fans; fans never share a run with unclipped lanes)
-			const bool mine = (cur == tile) && ((group | (code & kFanIdBit)) == g);
-			const unsigned m = __ballot_sync(0xffffffffu, mine);
-			const uint32_t cell = tile * static_cast<uint32_t>(fp.groups) + (g & ~kFanIdBit);
-			if (!FILL) {
-				if (static_cast<int>(lane) == leader) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(m))); } }
-			else {
+		if (!FILL) {
+			// Counting needs no order: round q adds the q-th tile of every item (row-major, like the walk below); the lanes
+			// of a round that aim at one cell share one fire-and-forget atomic.  (The count used to run the ordered walk
+			// too: a chain of warp votes per distinct tile of the warp, a quarter of K2's stall samples on c3.)
+			int cx = tx0, cy = ty0;
+			for (int q = 0; q < 4; ++q) {
+				const bool on = walked && q < ntile;
+				if (!__any_sync(0xffffffffu, on)) { break; }
+				const uint32_t cell = on ? static_cast<uint32_t>(cy * fp.tilesX + cx) * static_cast<uint32_t>(fp.groups) + group : (0xffffff00u | lane);
+				const unsigned peers = __match_any_sync(0xffffffffu, cell);
+				if (on && (peers & ltMask) == 0u) { atomicAdd(B.cellCount + cell, static_cast<uint32_t>(__popc(peers))); }
+				if (++cx > tx1) { cx = tx0; ++cy; } } }
+		else {
+			// The ordered walk, with its atomics deferred: the loop itself is warp votes only.  Step s (the s-th distinct
+			// (tile, group) the warp meets, in increasing tile index) is remembered by lane s -- its cell and how many lanes
+			// take part -- and every participating lane notes the step and its rank in it (at most four per item).  After
+			// the walk (or after 32 steps) the step lanes issue all cursor atomics at once: one round trip instead of one
+			// per step (K5 on c3: 370 warp instructions and about three serial atomic latencies per triangle thread before).
+			int cx = tx0, cy = ty0;
+			uint32_t cur = walked ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu;
+			const uint32_t mygf = group | (code & kFanIdBit);
+			uint32_t stepCell = 0, stepTile = 0, stepCnt = 0;   // of the step this lane remembers
+			uint32_t mySteps = 0, myRanks = 0;                  // 4 x 8 bits: step (0 .. 31) and rank of this lane's entries
+			int nmine = 0, nsteps = 0;
+			auto flush = [&]() {
 				uint32_t base = 0;
-				if (static_cast<int>(lane) == leader) {
-					base = atomicAdd(B.cellCursor + cell, static_cast<uint32_t>(__popc(m))) + __ldg(B.tileBase + tile) + __ldg(B.cellRel + cell); }
-				base = __shfl_sync(0xffffffffu, base, leader);
+				if (static_cast<int>(lane) < nsteps) {
+					base = atomicAdd(B.cellCursor + stepCell, stepCnt) + __ldg(B.tileBase + stepTile) + __ldg(B.cellRel + stepCell); }
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					const uint32_t b = __shfl_sync(0xffffffffu, base, static_cast<int>((mySteps >> (8 * k)) & 31u));
+					if (k < nmine) {
+						const uint32_t rank = (myRanks >> (8 * k)) & 0xffu;
+						const uint32_t pos = b + rank;
+						if (pos < fp.listCapacity) { B.lists[pos] = make_uint2(okey, rank ? code : (code | kRunStartBit)); } } }
+				mySteps = 0; myRanks = 0; nmine = 0; nsteps = 0; };
+			while (true) {
+				const uint32_t tile = __reduce_min_sync(0xffffffffu, cur);
+				if (tile == 0xffffffffu) { break; }
+				const int leader = __ffs(__ballot_sync(0xffffffffu, cur == tile)) - 1;
+				const uint32_t g = __shfl_sync(0xffffffffu, mygf, leader);   // (lanes differ in group only among clip fans; fans never share a run with unclipped lanes)
+				const bool mine = (cur == tile) && (mygf == g);
+				const unsigned m = __ballot_sync(0xffffffffu, mine);
+				if (static_cast<int>(lane) == nsteps) {
+					stepTile = tile; stepCell = tile * static_cast<uint32_t>(fp.groups) + (g & ~kFanIdBit); stepCnt = static_cast<uint32_t>(__popc(m)); }
 				if (mine) {
-					const uint32_t rank = __popc(m & ltMask);
-					const uint32_t pos = base + rank;
-					if (pos < fp.listCapacity) { B.lists[pos] = make_uint2(okey, rank ? code : (code | kRunStartBit)); } } }
-			if (mine) {
-				++cx;
-				if (cx > tx1) { cx = tx0; ++cy; }
-				cur = (cy <= ty1) ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu; } } }
+					mySteps |= static_cast<uint32_t>(nsteps) << (8 * nmine);
+					myRanks |= static_cast<uint32_t>(__popc(m & ltMask)) << (8 * nmine);
+					++nmine;
+					++cx;
+					if (cx > tx1) { cx = tx0; ++cy; }
+					cur = (cy <= ty1) ? static_cast<uint32_t>(cy * fp.tilesX + cx) : 0xffffffffu; }
+				if (++nsteps == 32) { flush(); } }
+			if (nsteps) { flush(); } } }
 
 	// Items that cover more tiles make short lists (few of them fit a tile): every lane appends on its
 	// own, four independent atomics in flight; each entry is a run of its own.
@@ -631,7 +660,7 @@ __device__ __forceinline__ void tile_scan_last_block(const uint32_t* count, uint
 	K2_MARK(3); }
 
 #ifndef RSR_SETUP_CTAS
-#define RSR_SETUP_CTAS 4
+#define RSR_SETUP_CTAS 5   // 48 registers (32 bytes of spill in the rare clip path): c3 setup 108 -> 101 us; 6 CTAs / 40 registers: 98 us but no faster overall
 #endif
 __global__ void __launch_bounds__(256, RSR_SETUP_CTAS)
 setup_kernel(const DevDraw* __restrict__ draws, const uint32_t* __restrict__ blockDraw, const DevState* __restrict__ states, FrameParams fp,
