@@ -322,6 +322,12 @@ int rsrcu_wait_for(rsrcu_ctx* ctx, rsrcu_ctx* producer);
 int rsrcu_kawase_blur(rsrcu_ctx* ctx, const void* src_device, int src_stride_px, void* dst_device, int dst_stride_px,
                       int width, int height, int dist);
 
+/* rglr::Texture::maybe_make_mipmap (src/rgl/rglr/rglr_texture.cxx:33-81), what `$renderToTexture` does to a power-of-two
+ * square target before it is sampled (node/rendertotexture.cxx:91): texels_device holds 2 * dim rows of dim RGBA32F
+ * texels, the base level in the first dim rows; the chain is written below it (each level ((a + b) + c) + d of the
+ * 2x2 texels above, / 4).  Stream-ordered on the context. */
+int rsrcu_make_mipmap(rsrcu_ctx* ctx, void* texels_device, int dim);
+
 /* `$glow` (node/glow.cxx:24-39, :146-160; rglr::Filter<GlowShader, sRGB|LinearColor>, rglr_algorithm.hxx:107-144):
  * out = (image + blur * 0.7) * 0.5 per quad, converted to 0x00RRGGBB.  image: quad-swizzled canvas of the frame
  * (rsrcu_store_color_quads[_device]); blur: linear RGBA32F canvas read at (x/2, y/2) -- one blur pixel per quad, as

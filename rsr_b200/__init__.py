@@ -143,6 +143,7 @@ def load_library():
         "rsrcu_wait_for": [vp, vp],
         "rsrcu_kawase_blur": [vp, vp, ci, vp, ci, ci, ci, ci],
         "rsrcu_glow": [vp, vp, ci, vp, ci, ci, vp, ci, ci, ci, ci],
+        "rsrcu_make_mipmap": [vp, vp, ci],
         "rsrcu_march_surface": [vp, C.c_float, ci, ci, C.c_float, vp, vp, ci, C.POINTER(ci), C.POINTER(ci)],
         "rsrcu_draw_spans": [vp, vp, ci, ci, ci, ci, ci, C.c_float, vp, ci],
         "rsrcu_frame_spans": [vp, vp, ci, C.POINTER(ci)],
@@ -166,7 +167,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_join", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
     "rsrcu_canvas_alloc", "rsrcu_canvas_free", "rsrcu_canvas_read", "rsrcu_canvas_write", "rsrcu_store_color_fp_device",
-    "rsrcu_store_color_quads_device", "rsrcu_store_depth_device", "rsrcu_wait_for", "rsrcu_kawase_blur", "rsrcu_glow",
+    "rsrcu_store_color_quads_device", "rsrcu_store_depth_device", "rsrcu_wait_for", "rsrcu_kawase_blur", "rsrcu_glow", "rsrcu_make_mipmap",
     "rsrcu_march_surface", "rsrcu_draw_spans", "rsrcu_frame_spans", "rsrcu_present",
 )
 
@@ -196,7 +197,8 @@ class DeviceCanvas:
 
     def __init__(self, gpu, kind, width, height):
         self.gpu, self.kind, self.width, self.height = gpu, kind, int(width), int(height)
-        self.shape, self.dtype = {"fp": ((height, width, 4), np.float32), "quads": ((height // 2, width // 2, 4, 4), np.float32),
+        # 'tex': a power-of-two square texture with room for its mip chain (2 x height rows), base level on top
+        self.shape, self.dtype = {"fp": ((height, width, 4), np.float32), "tex": ((2 * height, width, 4), np.float32), "quads": ((height // 2, width // 2, 4, 4), np.float32),
                                   "depth": ((height, width), np.float32), "tc": ((height, width), np.uint32)}[kind]
         self.nbytes = int(np.prod(self.shape)) * 4
         p = C.c_void_p()
@@ -588,12 +590,13 @@ class GPU:
         """GL::BindTexture on a frame another pass stored into a device canvas ('fp'): render to texture without a
         PCIe round trip.  Like the reference's `$rendertotexture`, the canvas is sampled without a mip chain unless it
         is a power-of-two square whose rows hold one (rows = 2 x height)."""
-        assert canvas.kind == "fp"
+        assert canvas.kind in ("fp", "tex")
         w, h = canvas.width, canvas.height
+        rows = 2 * h if canvas.kind == "tex" else h
         if self.direct:
-            self._check(self.L.rsrcu_bind_texture(self.h, unit, C.c_void_p(canvas.ptr), w, h, w, mode, h, UPLOAD_DEVICE))
+            self._check(self.L.rsrcu_bind_texture(self.h, unit, C.c_void_p(canvas.ptr), w, h, w, mode, rows, UPLOAD_DEVICE))
         else:
-            self._emit(OP_BIND_TEXTURE, struct.pack("<iiiiiiiiQ", unit, w, h, w, mode, h, UPLOAD_DEVICE, 0, int(canvas.ptr)))
+            self._emit(OP_BIND_TEXTURE, struct.pack("<iiiiiiiiQ", unit, w, h, w, mode, rows, UPLOAD_DEVICE, 0, int(canvas.ptr)))
 
     def BindTexture3Device(self, canvas: "DeviceCanvas"):
         """GL::BindTexture3 on a depth canvas rendered on the device (the shadow map of a `$layer`, gllayer.cxx:154-181)"""
@@ -607,7 +610,7 @@ class GPU:
         """GL::StoreColor / StoreDepth into a device canvas: 'fp' (full size, or half size with half=True), 'quads', 'depth'"""
         self._flush_state()
         w, h = canvas.width, canvas.height
-        if canvas.kind == "fp":
+        if canvas.kind in ("fp", "tex"):   # ('tex': the frame is the base level of a mip-mapped texture)
             if self.direct:
                 self._check(self.L.rsrcu_store_color_fp_device(self.h, C.c_void_p(canvas.ptr), w, h, w, int(half)))
             else:
@@ -624,6 +627,11 @@ class GPU:
                 self._emit(OP_STORE_DEPTH_DEV, struct.pack("<Q", int(canvas.ptr)))
         else:
             raise ValueError("true-colour canvases are stored with StoreColorDevice")
+
+    def MakeMipmap(self, canvas: "DeviceCanvas"):
+        """rglr::Texture::maybe_make_mipmap (rglr_texture.cxx:33-81) on a 'tex' canvas whose base level has been stored"""
+        assert canvas.kind == "tex" and canvas.width == canvas.height
+        self._check(self.L.rsrcu_make_mipmap(self.h, C.c_void_p(canvas.ptr), canvas.width))
 
     def WaitFor(self, producer: "GPU"):
         """everything submitted to `producer` so far happens before anything submitted to this context from now on"""

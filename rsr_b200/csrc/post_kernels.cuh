@@ -51,6 +51,42 @@ kawase_kernel(const float4* __restrict__ src, int srcStride, float4* __restrict_
 		bl0 = nbl0; bl1 = nbl1; br0 = nbr0; br1 = nbr1; } }
 
 // ---------------------------------------------------------------------------------------------
+// rglr::Texture::maybe_make_mipmap (src/rgl/rglr/rglr_texture.cxx:33-81): the mip chain of a power-of-two square
+// RGBA32F texture, stacked under the base level (level L starts at row dim + dim/2 + ... + dim >> (L-1), its rows keep
+// the base stride), each texel ((a + b) + c) + d of the 2x2 texels above it, divided by 4.  A level depends on the
+// rounded values of the one before, so a CTA builds a little pyramid: from a B x B block of the source level
+// (B = 2^k <= 32) it produces the next k levels, the first from global memory, the others from shared memory.
+// A 1024^2 render target is two launches (levels 1-5, then 6-10 by one CTA).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mipmap_kernel(float4* __restrict__ tex, int stride, int dim, int srcLevel, int srcSize, int k) {
+	__shared__ float4 pyr[256 + 64 + 16 + 4 + 1];
+	const int B = 1 << k;
+	const int t = threadIdx.x;
+	auto rowStart = [&](int level) { int r = 0; for (int l = 0; l < level; ++l) { r += dim >> l; } return r; };
+	const float4* src = tex + static_cast<size_t>(rowStart(srcLevel)) * stride;
+	int prevOfs = 0, ofs = 0;
+	for (int j = 1; j <= k; ++j) {
+		const int n = B >> j;   // this level's edge inside the block
+		float4* dst = tex + static_cast<size_t>(rowStart(srcLevel + j)) * stride;
+		for (int i = t; i < n * n; i += 256) {
+			const int x = i % n, y = i / n;
+			float4 a, b, c, d;
+			if (j == 1) {
+				const float4* p = src + static_cast<size_t>(blockIdx.y * B + 2 * y) * stride + blockIdx.x * B + 2 * x;
+				a = p[0]; b = p[1]; c = p[stride]; d = p[stride + 1]; }
+			else {
+				const float4* p = pyr + prevOfs + (2 * y) * (2 * n) + 2 * x;
+				a = p[0]; b = p[1]; c = p[2 * n]; d = p[2 * n + 1]; }
+			const float4 sum = f4_add(f4_add(f4_add(a, b), c), d);
+			const float4 avg = make_float4(sum.x / 4.0f, sum.y / 4.0f, sum.z / 4.0f, sum.w / 4.0f);
+			pyr[ofs + y * n + x] = avg;
+			dst[static_cast<size_t>(blockIdx.y * n + y) * stride + blockIdx.x * n + x] = avg; }
+		__syncthreads();
+		prevOfs = ofs;
+		ofs += n * n; } }
+
+// ---------------------------------------------------------------------------------------------
 // `$glow`: rglr::Filter<GlowShader, sRGB | LinearColor> (rglr_algorithm.hxx:107-144, node/glow.cxx:24-39)
 //   out = (image + blur * 0.7) * 0.5, image = quad-swizzled RGBA32F canvas {r[4], g[4], b[4], a[4]} per 2x2 quad,
 //   blur = ONE pixel of the linear canvas per quad, read at (x/2, y/2), its r / g / b broadcast over the quad.

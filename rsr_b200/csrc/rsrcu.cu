@@ -1581,6 +1581,21 @@ int rsrcu_kawase_blur(rsrcu_ctx* c, const void* src, int srcStride, void* dst, i
 	CU(cudaGetLastError());
 	return RSRCU_OK; }
 
+int rsrcu_make_mipmap(rsrcu_ctx* c, void* texelsDevice, int dim) {
+	if (!c || !texelsDevice) { return fail(RSRCU_ERR_INVALID, "null argument"); }
+	if (dim < 2 || (dim & (dim - 1)) != 0 || dim > 4096) { return fail(RSRCU_ERR_INVALID, "mipmap: %d is not a power of two in 2 .. 4096 (rglr_texture.cxx:35-52)", dim); }
+	CU(cudaSetDevice(c->device));
+	{ const int r = joinTileStreams(c); if (r != RSRCU_OK) { return r; } }
+	int pow = 0; while ((1 << pow) < dim) { ++pow; }
+	int level = 0, size = dim;
+	while (level < pow) {
+		const int k = std::min(5, pow - level);
+		const unsigned blocks = static_cast<unsigned>(size >> k);
+		mipmap_kernel<<<dim3(blocks, blocks), 256, 0, c->stream>>>(static_cast<float4*>(texelsDevice), dim, dim, level, size, k);
+		CU(cudaGetLastError());
+		level += k; size >>= k; }
+	return RSRCU_OK; }
+
 int rsrcu_glow(rsrcu_ctx* c, const void* imageQuads, int imageStrideQuads, const void* blur, int blurStride, int gamma,
                uint32_t* dst, int dstIsDevice, int width, int height, int stridePx) {
 	if (!c || !imageQuads || !blur || !dst) { return fail(RSRCU_ERR_INVALID, "null argument"); }

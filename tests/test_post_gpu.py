@@ -258,3 +258,71 @@ def test_frame_spans_from_cuda_events_drawn_over_the_frame(cuda_gpu):
         tc.free()
     finally:
         cuda_gpu.set_profiling(0)
+
+
+@pytest.mark.parametrize("dim", [4, 16, 64, 256, 1024])
+def test_device_mipmap_matches_reference(refgl, cuda_gpu, dim):
+    """rglr::Texture::maybe_make_mipmap (rglr_texture.cxx:33-81) on a device texture"""
+    rng = np.random.default_rng(dim)
+    base = rng.normal(0.5, 1.0, (dim, dim, 4)).astype(np.float32)
+    want = refgl.make_mipmap(base)
+    tex = cuda_gpu.Canvas("tex", dim, dim)
+    both = np.zeros((2 * dim, dim, 4), np.float32)
+    both[:dim] = base
+    tex.write(both)
+    cuda_gpu.MakeMipmap(tex)
+    got = tex.read()
+    # (the reference leaves the texels right of each level untouched -- zeros in a fresh buffer, as here)
+    assert np.array_equal(bits(got), bits(want)), f"{np.count_nonzero(bits(got) != bits(want))} floats differ"
+    tex.free()
+
+
+def test_render_to_a_mipmapped_texture_on_the_device(refgl, ref_gpu, cuda_gpu):
+    """`$renderToTexture` with a power-of-two target (node/rendertotexture.cxx:70-91): StoreColor into the texture's base
+    level, maybe_make_mipmap, then sampled bilinearly with LOD selection by the next pass -- all on the device"""
+    from rsr_b200 import GL_LINEAR_MIPMAP_NEAREST
+    from rsr_b200.scenes import begin
+    dim, size = 256, (640, 360)
+    inner, outer = WavyGridScene(n=12, tex_dim=64), WavyGridScene(n=8, tex_dim=64, wave=0.4)
+
+    def pass1(gl, store):
+        begin(gl, (dim, dim))
+        gl.UseProgram(PROGRAM_AMY)
+        gl.ViewMatrix(translate(0, 0, -6))
+        gl.ProjectionMatrix(perspective(45.0, 1.0, 1.0, 100.0))
+        gl.UseBuffer(0, inner.pos); gl.UseBuffer(3, inner.nrm); gl.UseBuffer(9, inner.uv)
+        gl.BindTexture(0, inner.tex, inner.tex_dim, inner.tex_dim, inner.tex_dim, inner.filter)
+        gl.DrawElements(len(inner.idx), inner.idx, 0)
+        gl.UseProgram(PROGRAM_DEFAULT_POST)
+        store(gl)
+
+    def pass2(gl, bind, out):
+        begin(gl, size)
+        gl.UseProgram(PROGRAM_AMY)
+        gl.ViewMatrix(translate(0, 0, -9) @ rsr_b200.scenes.rotate(0.9, 1.0, 0.2, 0.0))   # tilted and far: several LODs
+        gl.ProjectionMatrix(perspective(45.0, size[0] / size[1], 1.0, 100.0))
+        gl.UseBuffer(0, outer.pos); gl.UseBuffer(3, outer.nrm); gl.UseBuffer(9, outer.uv)
+        bind(gl)
+        gl.DrawElements(len(outer.idx), outer.idx, 0)
+        gl.UseProgram(PROGRAM_DEFAULT_POST)
+        gl.StoreColor(out, True)
+
+    base_ref = np.zeros((dim, dim, 4), np.float32)
+    pass1(ref_gpu, lambda gl: gl.StoreColor(base_ref))
+    ref_gpu.Run()
+    tex_ref = refgl.make_mipmap(base_ref)
+    want = np.zeros((size[1], size[0]), np.uint32)
+    pass2(ref_gpu, lambda gl: gl.BindTexture(0, tex_ref, dim, dim, dim, GL_LINEAR_MIPMAP_NEAREST), want)
+    ref_gpu.Run()
+
+    tex = cuda_gpu.Canvas("tex", dim, dim)
+    pass1(cuda_gpu, lambda gl: gl.StoreToCanvas(tex))
+    cuda_gpu.Run(sync=False)
+    cuda_gpu.MakeMipmap(tex)
+    got = np.zeros_like(want)
+    pass2(cuda_gpu, lambda gl: gl.BindTextureDevice(0, tex, GL_LINEAR_MIPMAP_NEAREST), got)
+    cuda_gpu.Run()
+    assert np.array_equal(bits(tex.read()), bits(tex_ref))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} pixels differ"
+    assert len(np.unique(got)) > 200
+    tex.free()
