@@ -120,6 +120,19 @@ public:
 	void StoreDepth(float* dst) {
 		MaybeUpdateState();
 		Emit(RSRCU_OP_STORE_DEPTH, nullptr, 0, reinterpret_cast<uint64_t>(dst)); }
+	// the same stores into DEVICE canvases (GPU::CanvasAlloc): the frame's float / depth results never cross PCIe and
+	// can be bound again as texture (BindTexture with RSRCU_UPLOAD_DEVICE), shadow map (BindTexture3) or filtered
+	void StoreColorDevice(void* deviceDst, int width, int height, int stridePx, bool downsample) {
+		MaybeUpdateState();
+		const int32_t p[4] = { downsample ? 1 : 0, width, height, stridePx };
+		Emit(RSRCU_OP_STORE_FP_DEV, p, sizeof(p), reinterpret_cast<uint64_t>(deviceDst)); }
+	void StoreColorQuadsDevice(void* deviceDst, int width, int height, int strideQuads) {
+		MaybeUpdateState();
+		const int32_t p[4] = { 0, width, height, strideQuads };
+		Emit(RSRCU_OP_STORE_QUADS_DEV, p, sizeof(p), reinterpret_cast<uint64_t>(deviceDst)); }
+	void StoreDepthDevice(void* deviceDst) {
+		MaybeUpdateState();
+		Emit(RSRCU_OP_STORE_DEPTH_DEV, nullptr, 0, reinterpret_cast<uint64_t>(deviceDst)); }
 	void Finish() {}
 	void Reset() {
 		stream_.clear();
@@ -207,6 +220,36 @@ public:
 	rsrcu_frame* Retain() { rsrcu_frame* f = nullptr; Check(rsrcu_retain_frame(ctx_, &f)); return f; }
 	void Replay(rsrcu_frame* f) { Check(rsrcu_replay_frame(ctx_, f)); }
 	void Release(rsrcu_frame* f) { Check(rsrcu_release_frame(ctx_, f)); }
+
+	// device canvases and the nodes next to the rasteriser (include/rsrcu.h): `$kawase`, `$glow`,
+	// `$renderToTexture`'s mip chain, `$mc`, the shadow pass of a second context, the telemetry bars, presentation
+	void* CanvasAlloc(size_t bytes) { void* p = nullptr; Check(rsrcu_canvas_alloc(ctx_, bytes, &p)); return p; }
+	void CanvasFree(void* p) { Check(rsrcu_canvas_free(ctx_, p)); }
+	void CanvasRead(const void* devicePtr, void* hostDst, size_t bytes) { Check(rsrcu_canvas_read(ctx_, devicePtr, hostDst, bytes)); }
+	void CanvasWrite(void* devicePtr, const void* hostSrc, size_t bytes) { Check(rsrcu_canvas_write(ctx_, devicePtr, hostSrc, bytes)); }
+	void WaitFor(GPU& producer) { Check(rsrcu_wait_for(ctx_, producer.ctx_)); }
+	void KawaseBlur(const void* src, int srcStridePx, void* dst, int dstStridePx, int width, int height, int dist) {
+		Check(rsrcu_kawase_blur(ctx_, src, srcStridePx, dst, dstStridePx, width, height, dist)); }
+	void Glow(const void* imageQuads, int imageStrideQuads, const void* blur, int blurStridePx, bool sRGB, uint32_t* dst, bool dstIsDevice,
+	          int width, int height, int stridePx) {
+		Check(rsrcu_glow(ctx_, imageQuads, imageStrideQuads, blur, blurStridePx, sRGB ? 1 : 0, dst, dstIsDevice ? 1 : 0, width, height, stridePx)); }
+	void MakeMipmap(void* texelsDevice, int dim) { Check(rsrcu_make_mipmap(ctx_, texelsDevice, dim)); }
+	struct Surface { const float* soa[6]; std::vector<RsrMarchBlock> blocks; int vertexTotal; };
+	Surface MarchSurface(float timeSeconds, int precision, int forkDepth, float range) {
+		Surface s{}; s.blocks.resize(4096);
+		int n = 0;
+		Check(rsrcu_march_surface(ctx_, timeSeconds, precision, forkDepth, range, s.soa, s.blocks.data(), 4096, &n, &s.vertexTotal));
+		s.blocks.resize(static_cast<size_t>(n));
+		return s; }
+	void DrawSpans(void* truecolorDevice, int stridePx, int width, int height, int left, int top, float xscale, const std::vector<RsrSpan>& spans) {
+		Check(rsrcu_draw_spans(ctx_, truecolorDevice, stridePx, width, height, left, top, xscale, spans.data(), static_cast<int>(spans.size()))); }
+	std::vector<RsrSpan> FrameSpans() {
+		std::vector<RsrSpan> spans(8); int n = 0;
+		Check(rsrcu_frame_spans(ctx_, spans.data(), 8, &n));
+		spans.resize(static_cast<size_t>(n));
+		return spans; }
+	void Present(const void* truecolorDevice, int srcStridePx, void* surfaceDevice, int surfaceStridePx, int width, int height) {
+		Check(rsrcu_present(ctx_, truecolorDevice, srcStridePx, surfaceDevice, surfaceStridePx, width, height)); }
 
 	rsrcu_ctx* context() { return ctx_; }
 

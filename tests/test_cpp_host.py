@@ -68,4 +68,20 @@ def test_cpp_mirror_equals_python_route(cuda_gpu, ref_gpu):
         gl.Run()
         outs.append(out)
     assert np.array_equal(outs[0], outs[1])
+    assert fnv1a(outs[1]) == got
+    # the second line: the glow chain on device canvases, against the reference's own filters on the reference's stores
+    from oracle import refgl
+    quads, half = np.zeros((H // 2, W // 2, 4, 4), np.float32), np.zeros((H // 2, W // 2, 4), np.float32)
+    gl = ref_gpu
+    scenes.begin(gl, (W, H))
+    gl.UseProgram(R.PROGRAM_AMY)
+    gl.ViewMatrix(view); gl.ProjectionMatrix(proj)
+    gl.UseBuffer(0, scenes.soa(q)); gl.UseBuffer(9, scenes.soa(uv))
+    gl.BindTexture(0, tex, D, D, D, R.GL_LINEAR_MIPMAP_NEAREST)
+    gl.DrawElements(6, np.array([0, 1, 2, 0, 2, 3], np.uint16), 0)
+    gl.UseProgram(R.PROGRAM_DEFAULT_POST)
+    gl.StoreColorQuads(quads); gl.StoreColorHalf(half)
+    gl.Run()
+    want = refgl.glow_filter(quads, refgl.kawase_blur(refgl.kawase_blur(half, 0), 1), True)
+    assert fnv1a(want) == int(r.stdout.split()[3], 16)
     assert fnv1a(outs[0]) == got
