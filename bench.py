@@ -648,20 +648,27 @@ def bundled_scenes_subrecord(seconds=2.5):
     ratio is what a user of the reference sees when librsr's RunImpl (and, for glow scenes, the three post nodes of
     rsr_b200/host/post_nodes_cuda.cxx) change and nothing else.  dropin: every pointer GL recorded is staged once per
     frame (exact under the reference's own contract); dropin_static_assets: textures and index arrays declared immutable
-    by the host (uploaded once), which holds for these three scenes."""
+    by the host (uploaded once), which holds for these three scenes; dropin_pin_in_place: arrays of 1 MiB or more copied
+    by the copy engine from where they lie (rsrcu_set_pin_in_place: for hosts whose assets outlive their use)."""
     out = {"what": "bundled data/scene files through the reference's own node graph: CPU reference vs drop-in GPU::RunImpl, 1920x1080, doubleBuffer on",
            "scenes": {}}
     tool = os.path.join(ROOT, "tools", "scene_bench.py")
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     for scene in ("colortest", "tucker-and-dino", "instanced-cubes"):
         rec = {}
-        for lib in ("ref", "dropin", "dropin_static"):
+        for lib in ("ref", "dropin", "dropin_static", "dropin_pinned"):
+            if lib == "dropin_pinned" and scene != "tucker-and-dino":
+                continue   # (only that scene binds arrays of 1 MiB or more per frame)
             try:
                 cmd = [sys.executable, tool, "--lib", lib.split("_")[0], "--scene", scene, "--seconds", str(seconds)]
                 if lib == "dropin_static":
                     cmd.append("--static-assets")
-                p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=120)
-                lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+                env["RSRCU_PIN_IN_PLACE"] = "1" if lib == "dropin_pinned" else "0"
+                for attempt in range(3):   # (the reference's binner occasionally faults on its own scenes: oracle/scene_ref.py)
+                    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=120)
+                    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+                    if p.returncode == 0 and lines:
+                        break
                 if p.returncode != 0 or not lines:
                     raise RuntimeError(f"exit code {p.returncode}: {p.stderr.strip()[-160:]}")
                 rec[lib] = json.loads(lines[-1])
@@ -672,6 +679,7 @@ def bundled_scenes_subrecord(seconds=2.5):
                                     "dropin_frames_per_s": rec["dropin"]["frames_per_s"],
                                     "ratio": rec["dropin"]["frames_per_s"] / rec["ref"]["frames_per_s"],
                                     "dropin_static_assets_frames_per_s": rec.get("dropin_static", {}).get("frames_per_s"),
+                                    "dropin_pin_in_place_frames_per_s": rec.get("dropin_pinned", {}).get("frames_per_s"),
                                     "frames_timed": [rec["ref"]["frames"], rec["dropin"]["frames"]],
                                     "frame_identical": rec["ref"]["crc32_frame_t1"] == rec["dropin"]["crc32_frame_t1"]}
         else:

@@ -369,6 +369,17 @@ int rsrcu_frame_spans(rsrcu_ctx* ctx, RsrSpan* out, int capacity, int* count);
 int rsrcu_present(rsrcu_ctx* ctx, const void* truecolor_device, int src_stride_px, void* surface_device,
                   int surface_stride_px, int width, int height);
 
+/* RSRCU_UPLOAD_FRAME arrays of 1 MiB or more copied IN PLACE (opt-in; also RSRCU_PIN_IN_PLACE=1): instead of a staging
+ * memcpy on the submitting thread the array's pages are locked where they lie (cudaHostRegister, once per pointer)
+ * and the copy engine reads them directly, once per frame; rsrcu_end_frame returns when the copies have left host
+ * memory.  ONLY for hosts whose large arrays outlive their last use by the context: memory that is freed while it is
+ * still registered poisons later copies to or from whatever is allocated there next (this is why it is not the
+ * default: the reference only promises its pointers until a frame's Finalize).  Only the pages wholly inside an array
+ * are locked (its first and last page may be shared with heap neighbours, whose own copies a locked page would break);
+ * the two edge fragments travel as pageable memory.  A copy the copy engine refuses falls back to staging.  Disabling
+ * it waits for everything submitted and releases all pages.  A frame that used it cannot be retained. */
+int rsrcu_set_pin_in_place(rsrcu_ctx* ctx, int enabled);
+
 /* counters of the last completed frame (filled by rsrcu_sync) */
 typedef struct RsrStats {
 	uint64_t triangles_submitted;   /* sum over draws of prims x instances */

@@ -31,7 +31,7 @@ PROGRAM_DEFAULT_POST, PROGRAM_EXPOSURE_POST, PROGRAM_IQ_POST = 1, 2, 3
 PROGRAM_AMY, PROGRAM_DEPTH, PROGRAM_MANY, PROGRAM_OBJ1, PROGRAM_OBJ2, PROGRAM_OBJ2S = 4, 5, 6, 7, 8, 9
 PROGRAM_ENVMAP, PROGRAM_WIREFRAME, PROGRAM_TEXT, PROGRAM_PATTERN, PROGRAM_ALPHATEXTURE = 10, 11, 26, 41, 65
 
-UPLOAD_ALWAYS, UPLOAD_STATIC, UPLOAD_DEVICE = 0, 1, 2
+UPLOAD_ALWAYS, UPLOAD_STATIC, UPLOAD_DEVICE, UPLOAD_FRAME = 0, 1, 2, 3
 
 RSRCU_OK = 0
 ERROR_NAMES = {1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "NO_PROGRAM", 5: "UNSUPPORTED", 6: "OVERFLOW"}
@@ -144,6 +144,7 @@ def load_library():
         "rsrcu_kawase_blur": [vp, vp, ci, vp, ci, ci, ci, ci],
         "rsrcu_glow": [vp, vp, ci, vp, ci, ci, vp, ci, ci, ci, ci],
         "rsrcu_make_mipmap": [vp, vp, ci],
+        "rsrcu_set_pin_in_place": [vp, ci],
         "rsrcu_march_surface": [vp, C.c_float, ci, ci, C.c_float, vp, vp, ci, C.POINTER(ci), C.POINTER(ci)],
         "rsrcu_draw_spans": [vp, vp, ci, ci, ci, ci, ci, C.c_float, vp, ci],
         "rsrcu_frame_spans": [vp, vp, ci, C.POINTER(ci)],
@@ -167,7 +168,7 @@ EXPORTED_SYMBOLS = (
     "rsrcu_sync_frame", "rsrcu_run_stream",
     "rsrcu_device_truecolor", "rsrcu_stream", "rsrcu_join", "rsrcu_get_stats", "rsrcu_set_profiling", "rsrcu_get_stage_ms",
     "rsrcu_canvas_alloc", "rsrcu_canvas_free", "rsrcu_canvas_read", "rsrcu_canvas_write", "rsrcu_store_color_fp_device",
-    "rsrcu_store_color_quads_device", "rsrcu_store_depth_device", "rsrcu_wait_for", "rsrcu_kawase_blur", "rsrcu_glow", "rsrcu_make_mipmap",
+    "rsrcu_store_color_quads_device", "rsrcu_store_depth_device", "rsrcu_wait_for", "rsrcu_kawase_blur", "rsrcu_glow", "rsrcu_make_mipmap", "rsrcu_set_pin_in_place",
     "rsrcu_march_surface", "rsrcu_draw_spans", "rsrcu_frame_spans", "rsrcu_present",
 )
 
@@ -627,6 +628,11 @@ class GPU:
                 self._emit(OP_STORE_DEPTH_DEV, struct.pack("<Q", int(canvas.ptr)))
         else:
             raise ValueError("true-colour canvases are stored with StoreColorDevice")
+
+    def set_pin_in_place(self, enabled: bool):
+        """UPLOAD_FRAME arrays of 1 MiB or more are page-locked where they lie and copied by the copy engine (opt-in: the
+        arrays must outlive their last use by this context; disable before freeing them)"""
+        self._check(self.L.rsrcu_set_pin_in_place(self.h, int(bool(enabled))))
 
     def MakeMipmap(self, canvas: "DeviceCanvas"):
         """rglr::Texture::maybe_make_mipmap (rglr_texture.cxx:33-81) on a 'tex' canvas whose base level has been stored"""

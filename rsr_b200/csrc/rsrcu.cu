@@ -16,6 +16,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 
 #include "../../include/rsrcu.h"
 #include "tile_kernel.cuh"
@@ -122,6 +125,20 @@ struct HostDraw {
 
 constexpr int kSlots = 3;
 
+// RSRCU_UPLOAD_FRAME, large arrays: the host memory is page-locked in place (cudaHostRegister) and copied by the copy
+// engine straight from where it lies -- no staging memcpy on the submitting thread.  One device buffer per slot of the
+// frame ring (a frame's copy may not overwrite what an earlier frame's kernels still read).
+struct PinnedInPlace {
+	size_t bytes{0};
+	uintptr_t regBase{0}; size_t regBytes{0};   // the page-aligned range that was registered
+	bool ok{false};                              // false: registration failed (shared pages, not host memory...): staged like small arrays
+	bool owned{false};                           // this context registered the range (another context may have done it first)
+	DevBuf dev[kSlots];
+	uint64_t lastFrame{0}; };
+constexpr size_t kPinInPlaceMin = static_cast<size_t>(1) << 20;
+constexpr size_t kPinnedMark = ~static_cast<size_t>(0);   // FrameCacheEntry::off of an array that went the in-place way
+
+
 // everything rsrcu_end_frame derives from a recorded frame before it can launch: kept per context for the last
 // frame, and copied into an rsrcu_frame by rsrcu_retain_frame
 struct FramePlan {
@@ -204,6 +221,12 @@ struct rsrcu_ctx {
 	std::unordered_map<const void*, StaticAlloc> staticCache;
 	std::vector<PtrCacheEntry> ptrCache = std::vector<PtrCacheEntry>(kPtrCacheSize, PtrCacheEntry{nullptr, 0, nullptr, 0.0f, 0.0f, false});
 	std::vector<FrameCacheEntry> frameCache = std::vector<FrameCacheEntry>(kPtrCacheSize);
+	std::unordered_map<const void*, PinnedInPlace> pinned;   // RSRCU_UPLOAD_FRAME arrays of >= 1 MiB
+	cudaStream_t h2dStream{nullptr};
+	cudaEvent_t evH2D{nullptr};
+	bool h2dPending{false};            // copies of the frame being recorded that its first kernel must wait for
+	bool frameUsedPinned{false};       // (such a frame cannot be retained: its inputs live in buffers later frames overwrite)
+	bool pinInPlace{false};            // rsrcu_set_pin_in_place / RSRCU_PIN_IN_PLACE=1: opt-in, see include/rsrcu.h
 	uint64_t frameStamp{0};            // bumped by rsrcu_begin_frame: entries of earlier frames are stale without clearing
 	float guardFactor{1.0f};
 	uint64_t drawsCulled{0};
@@ -416,8 +439,49 @@ int uploadData(rsrcu_ctx* c, const void* host, size_t bytes, int upload, DevRef&
 		// inside a frame sees the same bytes, so they are staged once (a field of 576 quads binds its two textures 576 times)
 		FrameCacheEntry& fe = c->frameCache[ptrCacheIndex(host)];
 		if (fe.stamp == c->frameStamp && fe.host == host && fe.bytes >= bytes) {
-			out.null = false; out.arena = true; out.off = fe.off; out.ranged = false;
+			out.null = false; out.ranged = false;
+			if (fe.off == kPinnedMark) { out.arena = false; out.abs = c->pinned[host].dev[c->outSlot].ptr; }
+			else { out.arena = true; out.off = fe.off; }
 			return RSRCU_OK; }
+		if (c->pinInPlace && bytes >= kPinInPlaceMin) {
+			PinnedInPlace& pp = c->pinned[host];
+			if (pp.bytes != bytes) {   // first sight, or the address now holds something else
+				if (pp.owned) { cudaHostUnregister(reinterpret_cast<void*>(pp.regBase)); cudaGetLastError(); }
+				pp.bytes = bytes;
+				// Only the pages that lie wholly inside the array are locked: its first and last page may be shared with heap
+				// neighbours, and a page-locked page poisons every later copy to or from whatever else lives on it (the copy
+				// engine refuses sources / destinations that are only partly registered).  The two edge fragments (< 4 KiB
+				// each) are copied as pageable memory.
+				pp.regBase = (reinterpret_cast<uintptr_t>(host) + 4095) & ~static_cast<uintptr_t>(4095);
+				const uintptr_t regEnd = (reinterpret_cast<uintptr_t>(host) + bytes) & ~static_cast<uintptr_t>(4095);
+				pp.regBytes = regEnd > pp.regBase ? regEnd - pp.regBase : 0;
+				CU(cudaSetDevice(c->device));
+				pp.owned = pp.regBytes != 0 && cudaHostRegister(reinterpret_cast<void*>(pp.regBase), pp.regBytes, cudaHostRegisterDefault) == cudaSuccess;
+				if (!pp.owned) { cudaGetLastError(); }
+				pp.ok = pp.owned; }
+			pp.lastFrame = c->frameStamp;
+			if (pp.ok) {
+				CU(pp.dev[c->outSlot].reserve(bytes));
+				// the slot's buffer was last read by the frame three submissions ago: its kernels are done when it has been read back
+				CU(cudaStreamWaitEvent(c->h2dStream, c->evCopied[c->outSlot], 0));
+				uint8_t* dev = static_cast<uint8_t*>(pp.dev[c->outSlot].ptr);
+				const uint8_t* src = static_cast<const uint8_t*>(host);
+				const size_t head = pp.regBase - reinterpret_cast<uintptr_t>(host), tailOff = head + pp.regBytes;
+				cudaError_t ce = cudaMemcpyAsync(dev + head, src + head, pp.regBytes, cudaMemcpyHostToDevice, c->h2dStream);
+				if (ce == cudaSuccess && head) { ce = cudaMemcpyAsync(dev, src, head, cudaMemcpyHostToDevice, c->h2dStream); }
+				if (ce == cudaSuccess && tailOff < bytes) { ce = cudaMemcpyAsync(dev + tailOff, src + tailOff, bytes - tailOff, cudaMemcpyHostToDevice, c->h2dStream); }
+				if (ce == cudaSuccess) {
+					c->h2dPending = true; c->frameUsedPinned = true;
+					fe = FrameCacheEntry{host, bytes, kPinnedMark, c->frameStamp};
+					out.null = false; out.arena = false; out.abs = pp.dev[c->outSlot].ptr; out.ranged = false;
+					return RSRCU_OK; }
+				// (another party has page-locked part of the range?) -- stage this array like a small one from now on
+				cudaGetLastError();
+				if (std::getenv("RSRCU_PIN_DEBUG")) {
+					std::fprintf(stderr, "rsrcu: in-place copy of %p (%zu bytes; registered %p + %zu, owned %d) refused: %s; staging it\n", host, bytes,
+					             reinterpret_cast<void*>(pp.regBase), pp.regBytes, pp.owned ? 1 : 0, cudaGetErrorString(ce)); }
+				if (pp.owned) { cudaHostUnregister(reinterpret_cast<void*>(pp.regBase)); cudaGetLastError(); pp.owned = false; }
+				pp.ok = false; } }
 		size_t off = 0;
 		CU(c->arenas[c->outSlot].push(host, bytes, off));
 		fe = FrameCacheEntry{host, bytes, off, c->frameStamp};
@@ -653,6 +717,12 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	const unsigned gridCap = (c->overlap && frontCtas > 0) ? frontCtas : 0xffffffffu;
 	g_pdl = !c->overlap || frontPdl;
 	if (c->extWaitPending) { CU(cudaStreamWaitEvent(st, c->evExt, 0)); c->extWaitPending = false; }   // rsrcu_wait_for: a producer context's canvases
+	bool waitH2D = false;
+	if (c->h2dPending) {   // arrays copied in place (uploadData): the frame's first kernel waits for the copy engine
+		CU(cudaEventRecord(c->evH2D, c->h2dStream));
+		CU(cudaStreamWaitEvent(st, c->evH2D, 0));
+		c->h2dPending = false;
+		waitH2D = true; }
 	if (c->overlap) { CU(cudaStreamWaitEvent(st, c->evTileDone[si], 0)); }   // the tile kernel of the frame that last used this work set (and this arena mirror)
 	if (c->profiling) { CU(cudaEventRecord(c->evStage[0], st)); }
 	CU(cudaStreamWaitEvent(st, c->evCopied[c->outSlot], 0));   // the frame that last used this slot (counters, store targets) has been read back
@@ -736,6 +806,9 @@ int launchFrame(rsrcu_ctx* c, const FramePlan& plan, const uint8_t* arenaDev, co
 	{ const int r = flushDeferredCopies(c); if (r != RSRCU_OK) { return r; } }
 	if (c->hostProf) { const auto now_ = std::chrono::steady_clock::now(); c->hp[5] += static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(now_ - c->hpLast).count()); c->hpLast = now_; }
 	if (c->hostProf) { ++c->hpFrames; }
+	// RSRCU_UPLOAD_FRAME promises the host its arrays back when the frame has been submitted: the in-place copies
+	// (started while the frame was being recorded) must have left host memory by then
+	if (waitH2D) { CU(cudaEventSynchronize(c->evH2D)); }
 	return RSRCU_OK; }
 
 
@@ -745,8 +818,16 @@ extern "C" {
 
 const char* rsrcu_last_error(void) { return g_lastError.c_str(); }
 
+// RSRCU_SEGV_TRACE=1 (developer aid): a SIGSEGV prints the native call stack (offsets resolve with addr2line on the same .so)
+static void segvTrace(int) {
+	void* frames[48];
+	const int n = backtrace(frames, 48);
+	backtrace_symbols_fd(frames, n, 2);
+	_exit(139); }
+
 int rsrcu_create(int device, rsrcu_ctx** out) {
 	if (!out) { return fail(RSRCU_ERR_INVALID, "out is null"); }
+	if (std::getenv("RSRCU_SEGV_TRACE")) { signal(SIGSEGV, segvTrace); }
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n == 0) {
@@ -760,6 +841,9 @@ int rsrcu_create(int device, rsrcu_ctx** out) {
 	CU(cudaStreamCreateWithFlags(&c->tileStream2, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&c->evGate, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->evExt, cudaEventDisableTiming));
+	CU(cudaStreamCreateWithFlags(&c->h2dStream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->evH2D, cudaEventDisableTiming));
+	if (const char* v = std::getenv("RSRCU_PIN_IN_PLACE")) { c->pinInPlace = std::atoi(v) != 0; }
 	{
 		int lo = 0, hi = 0;
 		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -823,6 +907,12 @@ int rsrcu_destroy(rsrcu_ctx* c) {
 		for (auto& ev : c->traceEv) { cudaEventDestroy(ev); } }
 	for (auto& kv : c->staticCache) { cudaFree(kv.second.dev); }
 	for (void* p : c->canvases) { cudaFree(p); }
+	if (c->h2dStream) { cudaStreamSynchronize(c->h2dStream); }
+	for (auto& kv : c->pinned) {
+		if (kv.second.owned) { cudaHostUnregister(reinterpret_cast<void*>(kv.second.regBase)); cudaGetLastError(); }
+		for (auto& b : kv.second.dev) { b.release(); } }
+	if (c->evH2D) { cudaEventDestroy(c->evH2D); }
+	if (c->h2dStream) { cudaStreamDestroy(c->h2dStream); }
 	for (DevBuf* b : { &c->spanBuf, &c->glowOut, &c->mcBlocks, &c->mcTotals, &c->mcBase, &c->mcVerts[0], &c->mcVerts[1], &c->mcVerts[2] }) { b->release(); }
 	if (c->evExt) { cudaEventDestroy(c->evExt); }
 	for (auto& w : c->sets) {
@@ -905,6 +995,16 @@ int rsrcu_begin_frame(rsrcu_ctx* c, int width, int height, int tileWBlocks, int 
 	c->storesUsed = 0; c->tcDev = nullptr;
 	c->arenas[c->outSlot].used = 0;
 	++c->frameStamp;
+	c->h2dPending = false; c->frameUsedPinned = false;
+	if ((c->frameStamp & 127u) == 0 && !c->pinned.empty()) {
+		// arrays not bound for a while: let their pages go (the host may have freed them long ago)
+		for (auto it = c->pinned.begin(); it != c->pinned.end();) {
+			if (c->frameStamp - it->second.lastFrame > 256) {
+				CU(cudaDeviceSynchronize());
+				if (it->second.owned) { cudaHostUnregister(reinterpret_cast<void*>(it->second.regBase)); cudaGetLastError(); }
+				for (auto& b : it->second.dev) { b.release(); }
+				it = c->pinned.erase(it); }
+			else { ++it; } } }
 	c->trianglesSubmitted = 0; c->inputBytes = 0; c->progMask = 0;
 	c->haveState = false; c->stateDirty = true;
 	for (auto& b : c->curBuffers) { b = DevRef{}; }
@@ -1256,6 +1356,7 @@ int rsrcu_retain_frame(rsrcu_ctx* c, rsrcu_frame** out) {
 	if (!c || !out) { return fail(RSRCU_ERR_INVALID, "null argument"); }
 	if (c->inFrame || c->lastArena < 0 || !c->slotPlan[c->lastArena].valid) { return fail(RSRCU_ERR_INVALID, "rsrcu_retain_frame: no submitted frame (call it after rsrcu_end_frame, before the next rsrcu_begin_frame)"); }
 	if (c->slotPlan[c->lastArena].fp.ncmds > kInlineCmds) { return fail(RSRCU_ERR_UNSUPPORTED, "a retained frame holds at most %d clear / store commands", kInlineCmds); }
+	if (c->frameUsedPinned) { return fail(RSRCU_ERR_UNSUPPORTED, "a frame with RSRCU_UPLOAD_FRAME arrays of 1 MiB or more cannot be retained (they live in buffers later frames overwrite): bind them RSRCU_UPLOAD_STATIC"); }
 	CU(cudaSetDevice(c->device));
 	const UploadArena& ar = c->arenas[c->lastArena];
 	const FramePlan& plan = c->slotPlan[c->lastArena];
@@ -1839,6 +1940,21 @@ int rsrcu_march_surface(rsrcu_ctx* c, float timeSeconds, int precision, int fork
 		if (totals[static_cast<size_t>(i)]) { blocks[nb++] = RsrMarchBlock{static_cast<int32_t>(base[static_cast<size_t>(i)]), static_cast<int32_t>(totals[static_cast<size_t>(i)])}; } }
 	*blockCount = nb;
 	*vertexTotal = static_cast<int>(padded);
+	return RSRCU_OK; }
+
+int rsrcu_set_pin_in_place(rsrcu_ctx* c, int enabled) {
+	if (!c) { return fail(RSRCU_ERR_INVALID, "null context"); }
+	if (c->inFrame) { return fail(RSRCU_ERR_INVALID, "rsrcu_set_pin_in_place inside begin/end frame"); }
+	CU(cudaSetDevice(c->device));
+	c->pinInPlace = enabled != 0;
+	if (!c->pinInPlace && !c->pinned.empty()) {
+		// everything submitted has to be through with the buffers before the pages are released
+		{ const int r = rsrcu_sync(c); if (r != RSRCU_OK) { return r; } }
+		CU(cudaStreamSynchronize(c->h2dStream));
+		for (auto& kv : c->pinned) {
+			if (kv.second.owned) { cudaHostUnregister(reinterpret_cast<void*>(kv.second.regBase)); cudaGetLastError(); }
+			for (auto& b : kv.second.dev) { b.release(); } }
+		c->pinned.clear(); }
 	return RSRCU_OK; }
 
 int rsrcu_get_stats(rsrcu_ctx* c, RsrStats* out) {

@@ -129,3 +129,52 @@ def test_drop_in_in_double_buffer_mode_has_the_reference_latency(ref_gpu):
     finally:
         g.L.ref_set_double_buffer(0)
         g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("in_place", [False, True])
+def test_frame_policy_large_arrays_follow_their_host_memory(refgl, ref_gpu, in_place):
+    """RSRCU_UPLOAD_FRAME (the drop-in binding's default): an array is staged once per frame however often it is bound, and
+    the host may change it between frames.  With rsrcu_set_pin_in_place arrays of 1 MiB or more are page-locked where
+    they lie and copied by the copy engine instead of through the staging arena."""
+    import rsr_b200
+    from rsr_b200 import GL_LINEAR_MIPMAP_NEAREST, PROGRAM_AMY, PROGRAM_DEFAULT_POST
+    from rsr_b200.scenes import WavyGridScene, begin, perspective, translate
+    from oracle.refgl import make_mipmap
+    size, dim = (640, 360), 512
+    sc = WavyGridScene(n=16, tex_dim=64)
+    rng = np.random.default_rng(12)
+    tex = make_mipmap(rng.random((dim, dim, 4), dtype=np.float32))   # 8 MiB with its mip chain
+    gpu = rsr_b200.GPU(0, direct=True)
+    gpu.set_pin_in_place(in_place)
+
+    def frame(gl, out, **kw):
+        begin(gl, size)
+        gl.UseProgram(PROGRAM_AMY)
+        gl.ViewMatrix(translate(0, 0, -6))
+        gl.ProjectionMatrix(perspective(45.0, size[0] / size[1], 1.0, 100.0))
+        gl.UseBuffer(0, sc.pos); gl.UseBuffer(3, sc.nrm); gl.UseBuffer(9, sc.uv)
+        for _ in range(3):   # bound again and again inside the frame, like a field of quads sharing a texture
+            gl.BindTexture(0, tex, dim, dim, dim, GL_LINEAR_MIPMAP_NEAREST, **kw)
+            gl.DrawElements(len(sc.idx), sc.idx, 0)
+        gl.UseProgram(PROGRAM_DEFAULT_POST)
+        gl.StoreColor(out, True)
+    try:
+        for i in range(5):
+            tex[:dim] = rng.random((dim, dim, 4), dtype=np.float32)   # (the mip rows keep old content: all that matters is that both see the same bytes)
+            want, got = np.zeros((size[1], size[0]), np.uint32), np.zeros((size[1], size[0]), np.uint32)
+            frame(ref_gpu, want)
+            ref_gpu.Run()
+            frame(gpu, got, upload=rsr_b200.UPLOAD_FRAME)
+            gpu.Run()
+            assert np.array_equal(got, want), f"frame {i}: {np.count_nonzero(got != want)} pixels differ"
+            if in_place:
+                assert gpu.stats()["h2d_bytes"] < tex.nbytes // 4          # the texture did not go through the staging arena
+            else:
+                assert tex.nbytes <= gpu.stats()["h2d_bytes"] < 2 * tex.nbytes   # staged once, not three times
+        if in_place:
+            with pytest.raises(rsr_b200.RsrError):
+                gpu.Retain()
+    finally:
+        gpu.set_pin_in_place(False)   # releases the pages before `tex` goes away
+        gpu.close()

@@ -24,26 +24,28 @@ def scene_libs(refgl):
 
 @pytest.mark.parametrize("name", SCENES)
 def test_bundled_scene_renders_identically_on_the_gpu(scene_libs, name):
-    ref = scene_libs.RefScene(name)
+    from oracle import scene_ref
+    times = (0.0, 1.5)
+    wants = scene_ref.frames(name, SIZE, times)   # (the CPU reference in a process of its own: see oracle/scene_ref.py)
     gpu = scene_libs.RefScene(name, dropin=True)
     try:
-        for t in (0.0, 1.5):
-            want = ref.render(SIZE, t)
+        for t, want in zip(times, wants):
             got = gpu.render(SIZE, t)
             assert len(np.unique(want)) > 20, "the reference frame is not blank"
             diff = int(np.count_nonzero(want != got))
             assert diff == 0, f"{name} at t={t}: {diff} of {want.size} pixels differ"
     finally:
-        ref.close()
         gpu.close()
 
 
 def test_bundled_scene_at_1080p(scene_libs):
     """BASELINE.json configs[1]: the bundled scenes at 1920x1080"""
+    from oracle import scene_ref
     for name in ("tucker-and-dino", "instanced-cubes"):
-        ref, gpu = scene_libs.RefScene(name), scene_libs.RefScene(name, dropin=True)
+        want = scene_ref.frames(name, (1920, 1080), (0.75,))[0]
+        gpu = scene_libs.RefScene(name, dropin=True)
         try:
-            want, got = ref.render((1920, 1080), 0.75), gpu.render((1920, 1080), 0.75)
+            got = gpu.render((1920, 1080), 0.75)
             assert np.array_equal(want, got), f"{name}: {np.count_nonzero(want != got)} pixels differ"
         finally:
-            ref.close(); gpu.close()
+            gpu.close()
