@@ -326,3 +326,38 @@ def test_render_to_a_mipmapped_texture_on_the_device(refgl, ref_gpu, cuda_gpu):
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} pixels differ"
     assert len(np.unique(got)) > 200
     tex.free()
+
+
+def test_new_entry_points_refuse_bad_arguments(cuda_gpu):
+    a, b = cuda_gpu.Canvas("fp", 64, 32), cuda_gpu.Canvas("fp", 64, 32)
+    q, tc = cuda_gpu.Canvas("quads", 64, 32), cuda_gpu.Canvas("tc", 64, 32)
+    L, h = cuda_gpu.L, cuda_gpu.h
+    import ctypes as C
+    vp = C.c_void_p
+    bad = [
+        lambda: L.rsrcu_kawase_blur(h, vp(a.ptr), 64, vp(a.ptr), 64, 64, 32, 1),                      # in place
+        lambda: L.rsrcu_kawase_blur(h, vp(a.ptr), 32, vp(b.ptr), 64, 64, 32, 1),                      # stride < width
+        lambda: L.rsrcu_kawase_blur(h, vp(a.ptr), 64, vp(b.ptr), 64, 64, 32, -1),                     # negative distance
+        lambda: L.rsrcu_glow(h, vp(q.ptr), 32, vp(a.ptr), 64, 1, vp(tc.ptr), 1, 62, 32, 64),          # width not a multiple of 4
+        lambda: L.rsrcu_glow(h, vp(q.ptr), 8, vp(a.ptr), 64, 1, vp(tc.ptr), 1, 64, 32, 64),           # quad stride too small
+        lambda: L.rsrcu_make_mipmap(h, vp(a.ptr), 48),                                                # not a power of two
+        lambda: L.rsrcu_canvas_free(h, vp(12345)),                                                     # not a canvas
+        lambda: L.rsrcu_canvas_alloc(h, 0, C.byref(vp())),                                             # empty
+        lambda: L.rsrcu_store_depth_device(h, vp(a.ptr)),                                              # outside a frame
+        lambda: L.rsrcu_frame_spans(h, (rsr_b200.RsrSpan * 8)(), 8, C.byref(C.c_int())),              # no profiled frame... unless one ran
+    ]
+    for i, call in enumerate(bad[:-1]):
+        assert call() != 0, f"call {i} was accepted"
+        assert cuda_gpu.L.rsrcu_last_error()
+    with pytest.raises(rsr_b200.RsrError):
+        cuda_gpu.MarchSurface(0.0, 32, 2, -1.0)
+    # a device store of the wrong size is refused when it is recorded
+    cuda_gpu.Reset((128, 64))
+    with pytest.raises(rsr_b200.RsrError):
+        cuda_gpu.direct = True
+        try:
+            cuda_gpu.StoreToCanvas(a)      # 64x32 canvas, 128x64 target
+        finally:
+            cuda_gpu.direct = False
+    for c in (a, b, q, tc):
+        c.free()
