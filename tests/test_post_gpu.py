@@ -352,12 +352,12 @@ def test_new_entry_points_refuse_bad_arguments(cuda_gpu):
     with pytest.raises(rsr_b200.RsrError):
         cuda_gpu.MarchSurface(0.0, 32, 2, -1.0)
     # a device store of the wrong size is refused when it is recorded
-    cuda_gpu.Reset((128, 64))
-    with pytest.raises(rsr_b200.RsrError):
-        cuda_gpu.direct = True
-        try:
-            cuda_gpu.StoreToCanvas(a)      # 64x32 canvas, 128x64 target
-        finally:
-            cuda_gpu.direct = False
+    g = rsr_b200.GPU(0, direct=True)
+    try:
+        g.Reset((128, 64))
+        with pytest.raises(rsr_b200.RsrError, match="store canvas"):
+            g.StoreToCanvas(a)      # 64x32 canvas, 128x64 target
+    finally:
+        g.close()
     for c in (a, b, q, tc):
         c.free()
