@@ -302,7 +302,7 @@ int keyOf(const RsrState& s) {
 	key |= s.depth_attachment_type << 9;
 	return static_cast<int>(key); }
 
-// the reference's dispatch tables (src/viewer/shaders.cxx:54-126, shaders_envmap.cxx:45-60,
+// the reference's dispatch tables (src/viewer/shaders.cxx:54-126, shaders_envmap.cxx:18-31,
 // shaders_wireframe.cxx:18-23): (program id, FragmentStateKey) pairs that have a tile program
 bool drawProgramInstalled(int programId, int key) {
 	static const struct { int id; int key; } table[] = {
