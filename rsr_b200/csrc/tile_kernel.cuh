@@ -602,6 +602,39 @@ constexpr uint32_t kAllProgs = 0xfffu;
 // programs whose fragment stage samples texture unit 0 (P::samples)
 constexpr uint32_t kSamplingProgs = prog_bit(ProgAmy::id) | prog_bit(ProgAlphaTexture::id) | prog_bit(ProgText::id) | prog_bit(ProgPattern::id) | prog_bit(ProgEnvmap::id);
 
+// RSR_PREFETCH_VARYINGS=1: the thread that sets a triangle up also asks for its three vertices' varyings (ptvb) in L1.  The
+// rasteriser walks a run triangle by triangle and the varyings of each one are the first thing render_quad waits for -- an
+// L2 round trip per triangle and warp on the critical path of the warp that owns the batch's triangles; with the lines
+// already on their way (one request per triangle and CTA instead of one per warp) that wait shrinks to an L1 hit.
+#ifndef RSR_PREFETCH_VARYINGS
+#define RSR_PREFETCH_VARYINGS 1
+#endif
+// float4s of varyings per vertex of program `id` among the programs of this instantiation (0: none / not carried)
+template <uint32_t PROGS>
+__device__ __forceinline__ int varying_f4s(uint32_t id) {
+	int n = 0;
+#define RSR_NV_CASE(P) if constexpr ((PROGS & prog_bit(P::id)) != 0u && P::NV > 0) { if (id == static_cast<uint32_t>(P::id)) { n = (P::NV + 3) / 4; } }
+	RSR_NV_CASE(ProgAmy) RSR_NV_CASE(ProgOBJ2) RSR_NV_CASE(ProgMany) RSR_NV_CASE(ProgAlphaTexture) RSR_NV_CASE(ProgText) RSR_NV_CASE(ProgDepth)
+	RSR_NV_CASE(ProgPattern) RSR_NV_CASE(ProgOBJ1) RSR_NV_CASE(ProgOBJ2S) RSR_NV_CASE(ProgEnvmap) RSR_NV_CASE(ProgWireframe)
+#undef RSR_NV_CASE
+	return n; }
+
+template <uint32_t PROGS>
+__device__ __forceinline__ void prefetch_varyings(const TileArgs& A, uint32_t id, const EntryRec& e) {
+#if RSR_PREFETCH_VARYINGS
+	if (id & kFanIdBit) { return; }   // (a clip fan's vertices live in its clip record, which setup_triangle reads anyway)
+	const int n = varying_f4s<PROGS>(e.q4.x & 0xffu);
+	if (n == 0) { return; }
+	// <= 4 float4s of a vertex lie in at most two (three for 64 bytes) 32-byte sectors: the first and the last float4 name them
+	const uint32_t r[3] = { e.q3.x, e.q3.y, e.q3.z };
+#pragma unroll
+	for (int v = 0; v < 3; ++v) {
+		const float4* p = A.ptvb + r[v];
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+		if (n > 1) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p + (n - 1))); } }
+#endif
+}
+
 template <uint32_t PROGS, class P>
 __device__ __forceinline__ bool draw_batch_if(unsigned& frags, TileShared& sh, const TileArgs& A, uint32_t key0, int base, int nb, int ox, int oy, bool queued) {
 	if constexpr ((PROGS & prog_bit(P::id)) != 0u) {
@@ -1199,7 +1232,7 @@ tile_kernel(const __grid_constant__ TileArgs A) {
 		// depend on the program -- and every warp then walks the runs on its own: no CTA barrier between the runs of a batch.
 		const int bound = (ci < A.fp.ncmds) ? cmd_before_draw(A, ci) : 0x7fffffff;   // draws >= bound come after cmds[ci]
 		if (t < avail && static_cast<int>(myRec.q3.w) >= bound) { atomicMin(&sh.firstBad, t); }
-		if (t < avail) { sh.key[t] = myRec.q4.x; }
+		if (t < avail) { sh.key[t] = myRec.q4.x; prefetch_varyings<PROGS>(A, myId, myRec); }
 		__syncthreads();
 		const int nb = sh.firstBad;   // >= 1: entry 0 belongs to draw di
 		// start the trip for the records of the batch after this one while this one is rasterised
